@@ -1,0 +1,159 @@
+/*
+ * openclaw_gov.h -- C ABI of the B200-native openclaw-governance hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or
+ * torch types, no exceptions, no library-owned memory handed to the caller.  The Node N-API
+ * shim (napi/openclaw_gov_napi.c) and the Python ctypes binding (vainplex_openclaw_b200/
+ * _native.py) bind exactly these symbols.  Each entry point names the reference interface
+ * it replaces; paths are relative to packages/openclaw-governance/ of the reference.
+ *
+ * Error model (replaces JS exceptions caught by the failMode blocks, src/hooks.ts:232-241,
+ * src/redaction/hooks.ts:193-204): every function returns CG_OK (0) or a negative code and
+ * cg_last_error() holds a thread-local message.  There is NO CPU fallback: without a usable
+ * CUDA device every compute call fails with CG_ERR_CUDA / CG_ERR_NOT_INITIALIZED.
+ *
+ * Text encoding: message bytes are UTF-8 as produced by Buffer.from(str,'utf8') (lone
+ * surrogates already replaced by U+FFFD).  All span offsets are reported both in bytes and in
+ * UTF-16 code units, the unit the reference's m.index / lastIndex use (registry.ts:226-231).
+ */
+#ifndef OPENCLAW_GOV_H
+#define OPENCLAW_GOV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_API __attribute__((visibility("default")))
+
+/* ---- status codes */
+#define CG_OK                   0
+#define CG_ERR_INVALID_ARG     -1
+#define CG_ERR_NOT_INITIALIZED -2
+#define CG_ERR_CUDA            -3   /* no device / kernel or copy failed: caller applies failMode */
+#define CG_ERR_SYNTAX          -4   /* `new RegExp(src)` would throw SyntaxError */
+#define CG_ERR_UNSUPPORTED     -5   /* valid JS regex outside the supported subset */
+#define CG_ERR_TOO_LARGE       -6   /* rule expands past the matcher program limit */
+#define CG_ERR_CAPACITY        -7   /* caller's output array too small; *out_count holds the need */
+#define CG_ERR_NOMEM           -8
+
+/* ---- rule flags / categories */
+#define CG_FLAG_ICASE 1u            /* RegExp flag "i" (registry.ts:112,223) */
+/* CATEGORY_ORDER of src/redaction/registry.ts:17-22 */
+#define CG_CAT_CREDENTIAL 0u
+#define CG_CAT_FINANCIAL  1u
+#define CG_CAT_PII        2u
+#define CG_CAT_CUSTOM     3u
+
+/* ---- ruleset options */
+#define CG_OPT_PREFILTER_DIRECT7 0u /* 128-column table indexed by byte&0x7f (default) */
+#define CG_OPT_PREFILTER_LUT     1u /* byte->class LUT + compact table */
+
+typedef struct cg_ruleset cg_ruleset;
+
+typedef struct cg_rule {
+  const char *source;      /* JS RegExp source, UTF-8, not NUL-terminated */
+  uint32_t source_len;
+  uint32_t flags;          /* CG_FLAG_* */
+  uint32_t category;       /* CG_CAT_* ; only used by cg_find_matches_* ordering */
+} cg_rule;
+
+typedef struct cg_hit {     /* one (message, rule) with RegExp.test(message) === true */
+  uint32_t msg;
+  uint32_t rule;
+} cg_hit;
+
+typedef struct cg_span {    /* one element of PatternRegistry.findMatches()'s result */
+  uint32_t msg;
+  uint32_t rule;
+  uint32_t start_byte, end_byte;   /* offsets into the message's UTF-8 bytes */
+  uint32_t start16, end16;         /* same span in UTF-16 code units (JS indices) */
+} cg_span;
+
+typedef struct cg_ruleset_info {
+  uint32_t n_rules, n_ok, n_always_candidate, n_sets;
+  uint32_t prefilter_mode, prefilter_states, prefilter_cols, prefilter_factor_len, prefilter_bytes;
+  uint32_t program_words;
+} cg_ruleset_info;
+
+typedef struct cg_stats {   /* cumulative since cg_init; surfaced by governance.status (index.ts:103-114) */
+  uint64_t messages_scanned, bytes_scanned, candidate_events, verified_pairs, hits, spans;
+  uint64_t sha256_items, merkle_leaves, kernel_launches;
+  double last_scan_ms, last_merkle_ms;   /* device time of the last call (CUDA events) */
+} cg_stats;
+
+/* ---- lifecycle.  Replaces nothing in the reference (it has no device); called from the
+ * plugin's register()/gateway_stop (index.ts:66-118).  device < 0 selects the current device. */
+CG_API int cg_init(int device);
+CG_API void cg_shutdown(void);
+CG_API const char *cg_last_error(void);
+CG_API int cg_version(void);
+CG_API int cg_device_count(void);
+CG_API int cg_get_stats(cg_stats *out);
+CG_API uint64_t cg_launch_count(void);   /* kernels launched by this library so far */
+
+/* ---- rule-set compile.  Replaces `new RegExp(pattern)` in buildPolicyIndex
+ * (src/policy-loader.ts:119-128), compileCustomPattern (src/redaction/registry.ts:249-281) and
+ * the per-call `new RegExp(source,"g"+i)` of findMatches (registry.ts:222-223).
+ * status_per_rule (may be NULL) receives CG_OK / CG_ERR_SYNTAX / CG_ERR_UNSUPPORTED /
+ * CG_ERR_TOO_LARGE per rule; rules that failed never match.  With status_per_rule == NULL the
+ * first failing rule fails the whole call. */
+CG_API int cg_ruleset_create(const cg_rule *rules, uint32_t n_rules, uint32_t options,
+                             cg_ruleset **out, int32_t *status_per_rule);
+CG_API void cg_ruleset_destroy(cg_ruleset *rs);
+CG_API int cg_ruleset_get_info(const cg_ruleset *rs, cg_ruleset_info *out);
+/* one rule, no device needed: what would `new RegExp(src, flags)` do?  (validateRegex,
+ * src/policy-loader.ts:15-31).  err/err_len may be NULL/0. */
+CG_API int cg_rule_check(const char *source, uint32_t source_len, uint32_t flags, char *err, uint32_t err_len);
+
+/* ---- policy-semantics scan: RegExp.test per (message, rule) -- matchesAny,
+ * src/conditions/context.ts:9-25, over a batch.  Host buffers; copies are inside the call.
+ *   bytes/offsets : n messages, message i = bytes[offsets[i] .. offsets[i+1])
+ *   out_words[n]  : hit ? 1<<63 | (#distinct rules hit)<<32 | lowest hit rule index : 0
+ *   out_hits      : optional sparse list sorted by (msg, rule); hits_cap entries available;
+ *                   *out_nhits = number of hits (CG_ERR_CAPACITY when it exceeds hits_cap). */
+CG_API int cg_scan_batch(cg_ruleset *rs, const uint8_t *bytes, const uint32_t *offsets, uint32_t n,
+                         uint64_t *out_words, cg_hit *out_hits, uint32_t hits_cap, uint32_t *out_nhits);
+/* single message, blocking: the path for the synchronous hooks before_message_write /
+ * tool_result_persist (src/hooks.ts:297-389).  out_rules receives the hit rule indices. */
+CG_API int cg_scan_one(cg_ruleset *rs, const uint8_t *bytes, uint32_t len, uint64_t *out_word,
+                       uint32_t *out_rules, uint32_t rules_cap, uint32_t *out_nrules);
+
+/* ---- redaction-semantics scan: PatternRegistry.findMatches (registry.ts:212-242) including
+ * resolveOverlaps (registry.ts:288-316) for every message of a batch.  Spans come back sorted
+ * by (msg, start); `rule` is the index passed to cg_ruleset_create. */
+CG_API int cg_find_matches_batch(cg_ruleset *rs, const uint8_t *bytes, const uint32_t *offsets, uint32_t n,
+                                 cg_span *out_spans, uint32_t spans_cap, uint32_t *out_nspans);
+
+/* ---- device-resident variants (inputs/outputs already in HBM; used by bench.py `value` and by
+ * callers that pipeline their own copies).  Pointers are CUDA device pointers; `stream` is a
+ * cudaStream_t (NULL = the library's own stream); asynchronous w.r.t. the host.
+ * d_bytes must be readable for 16 bytes past offsets[n] (padding). */
+CG_API int cg_scan_batch_device(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n,
+                                void *d_out_words, void *stream);
+
+/* ---- SHA-256.  Replaces createHash("sha256").update(s).digest() at src/util.ts:77-79,
+ * src/redaction/vault.ts:26-28 (and nats/src/hooks.ts:90-94) for a batch of n byte strings. */
+CG_API int cg_sha256_batch(const uint8_t *bytes, const uint64_t *offsets, uint32_t n, uint8_t *out_digests32);
+
+/* ---- Proof-of-Guardrails Merkle tree over event-log leaves (audit JSONL lines,
+ * src/audit-trail.ts:151-179; no implementation in the reference -- convention in DESIGN.md:
+ * leaf = SHA-256(0x00||bytes), node = SHA-256(0x01||L||R), unpaired node promoted, empty =
+ * SHA-256("")). */
+CG_API int cg_merkle_root(const uint8_t *bytes, const uint64_t *offsets, uint64_t n, uint8_t out_root[32]);
+CG_API int cg_merkle_root_fixed(const uint8_t *bytes, uint64_t leaf_len, uint64_t n, uint8_t out_root[32]);
+/* device-resident: fixed-size leaves in HBM -> roots of consecutive 2^block_log2-leaf blocks
+ * (d_out_roots[ceil(n / 2^block_log2)][32], device memory).  Shards call this, all-gather the
+ * block roots (the one collective on this path) and finish with cg_merkle_fold. */
+CG_API int cg_merkle_block_roots_device(const void *d_bytes, uint64_t leaf_len, uint64_t n, uint32_t block_log2,
+                                        void *d_out_roots, void *stream);
+/* fold m 32-byte subtree roots (host memory) into one root with the same level-wise rule */
+CG_API int cg_merkle_fold(const uint8_t *nodes32, uint64_t m, uint8_t out_root[32]);
+CG_API int cg_merkle_fold_device(const void *d_nodes32, uint64_t m, void *d_out_root32, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENCLAW_GOV_H */

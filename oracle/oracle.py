@@ -99,6 +99,10 @@ class RegexSyntaxError(ValueError):
     """What `new RegExp(src)` would throw as SyntaxError."""
 
 
+class OracleUnsupported(ValueError):
+    """Valid JS the oracle itself cannot evaluate exactly (flag i with non-ASCII literals)."""
+
+
 def js_units(s: str) -> np.ndarray:
     """A JS string as its UTF-16 code units."""
     return np.frombuffer(s.encode("utf-16-le", "surrogatepass"), dtype=np.uint16)
@@ -119,7 +123,10 @@ class Regex:
         self.handle = lib().jsre_compile(buf, len(u), 1 if "i" in flags else 0, err, 256)
         self.source, self.flags = source, flags
         if not self.handle:
-            raise RegexSyntaxError(err.value.decode() or "invalid regular expression")
+            msg = err.value.decode() or "invalid regular expression"
+            if msg.startswith("oracle:"):
+                raise OracleUnsupported(msg)
+            raise RegexSyntaxError(msg)
 
     def __del__(self):
         h = getattr(self, "handle", None)

@@ -1,0 +1,68 @@
+"""Shared helpers for the test-suite (CPU harness wrapper, oracle adapters)."""
+import ctypes as C
+
+import numpy as np
+
+
+class Harness:
+    """Host-compiled product compiler + VM (tests/native/vm_harness.cpp)."""
+
+    def __init__(self, L, rules, mode=0, budget_kb=0, max_factor_len=0):
+        self.L = L
+        self.srcs = [r[0] if isinstance(r[0], bytes) else r[0].encode("utf-8", "surrogatepass") for r in rules]
+        arr = (C.c_char_p * max(1, len(rules)))(*self.srcs)
+        lens = np.array([len(s) for s in self.srcs] or [0], dtype=np.uint32)
+        flags = np.array([r[1] for r in rules] or [0], dtype=np.uint32)
+        self.status = np.zeros(max(1, len(rules)), dtype=np.int32)
+        self.h = L.harness_create(arr, lens.ctypes.data, flags.ctypes.data, len(rules), mode, budget_kb, max_factor_len,
+                                  self.status.ctypes.data)
+        assert self.h
+        self.n = len(rules)
+        self.rw = max(1, (self.n + 31) // 32)
+
+    def info(self):
+        o = np.zeros(8, dtype=np.uint32)
+        self.L.harness_info(self.h, o.ctypes.data)
+        return dict(nstates=int(o[0]), first_accept=int(o[1]), ncols=int(o[2]), factor_len=int(o[3]),
+                    n_always=int(o[4]), image_bytes=int(o[5]), prog_words=int(o[6]))
+
+    def find_all(self, rule, msg: bytes):
+        cap = 64
+        while True:
+            out = np.zeros(4 * cap, dtype=np.uint32)
+            k = self.L.harness_find_all(self.h, rule, msg, len(msg), out.ctypes.data, cap)
+            assert k >= 0, "VM overflow"
+            if k <= cap:
+                return [tuple(int(x) for x in out[4 * j:4 * j + 4]) for j in range(k)]
+            cap = k
+
+    def test(self, rule, msg: bytes) -> bool:
+        r = self.L.harness_test(self.h, rule, msg, len(msg))
+        assert r >= 0
+        return bool(r)
+
+    def candidates(self, msg: bytes):
+        bits = np.zeros(self.rw, dtype=np.uint32)
+        self.L.harness_candidates(self.h, msg, len(msg), bits.ctypes.data)
+        return {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
+
+    def close(self):
+        if self.h:
+            self.L.harness_destroy(self.h)
+            self.h = None
+
+
+def oracle_regexes(O, rules):
+    """rules: (source, flags, category) -> list of oracle Regex or None when the oracle rejects it."""
+    out = []
+    for src, fl, _cat in rules:
+        try:
+            out.append(O.Regex(src, "i" if fl & 1 else ""))
+        except O.RegexSyntaxError:
+            out.append(None)
+    return out
+
+
+def words_to_tuple(w):
+    w = int(w)
+    return (w >> 63, (w >> 32) & 0x7fffffff, w & 0xffffffff) if w else (0, 0, 0xffffffff)

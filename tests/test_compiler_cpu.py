@@ -1,0 +1,214 @@
+"""CPU tier for the product's host logic: the rule compiler, the prefilter tables and the Pike-VM
+*source* (compiled for the host by tests/native/vm_harness.cpp) against the oracle.  No GPU needed;
+the GPU tier (test_gpu_parity.py) repeats the comparisons through the C ABI and the real kernels."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import Harness
+from vainplex_openclaw_b200 import workload as W
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VECTORS = json.load(open(os.path.join(HERE, "golden", "registry_vectors.json")))["vectors"]
+
+
+def oracle_spans(O, rx, msgs):
+    d, o = O.pack(msgs)
+    got = O.find_matches_batch([(rx, "custom")], d, o)
+    out = {}
+    for mi, _, s, e in got.tolist():
+        out.setdefault(mi, []).append((s, e))
+    return out
+
+
+def u16_to_byte_offsets(msg: bytes):
+    """map UTF-16 index -> byte offset for a valid UTF-8 message (tests only)."""
+    s = msg.decode("utf-8")
+    m, b = [0], 0
+    for ch in s:
+        enc = ch.encode("utf-8")
+        if len(enc) == 4:
+            m.append(b + 2)
+            b += 4
+            m.append(b)
+        else:
+            b += len(enc)
+            m.append(b)
+    return m
+
+
+def test_builtins_on_reference_vectors(oracle, harness_lib):
+    rules = W.rules_as_tuples(W.make_rules(17))
+    h = Harness(harness_lib, rules)
+    assert (h.status == 0).all()
+    regs = [oracle.Regex(r[0], "i" if r[1] else "") for r in rules]
+    msgs = [oracle.js_to_utf8(v["input"]) for v in VECTORS]
+    for ri, rx in enumerate(regs):
+        exp = oracle_spans(oracle, rx, msgs)
+        for mi, m in enumerate(msgs):
+            got = h.find_all(ri, m)
+            assert [(g[2], g[3]) for g in got] == exp.get(mi, []), (rules[ri][0], m)
+            if exp.get(mi):
+                assert ri in h.candidates(m), ("prefilter missed", rules[ri][0], m)
+                assert h.test(ri, m)
+            else:
+                assert not h.test(ri, m)
+    h.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("utf8_frac", [0.0, 0.15])
+def test_synthetic_rules_spans_and_prefilter_soundness(oracle, harness_lib, mode, utf8_frac):
+    rl = W.make_rules(160)
+    rules = W.rules_as_tuples(rl)
+    h = Harness(harness_lib, rules, mode=mode)
+    assert (h.status == 0).all(), [h.L.harness_rule_error(h.h, i) for i in np.nonzero(h.status)[0]]
+    data, off, inj = W.make_messages(1200, 200, rl, p_hit=0.25, utf8_frac=utf8_frac, seed=1234 + mode)
+    buf = data.numpy()
+    msgs = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(1200)]
+    n_hits = 0
+    cands = [h.candidates(m) for m in msgs]
+    for ri, r in enumerate(rules):
+        exp = oracle_spans(oracle, oracle.Regex(r[0], "i" if r[1] else ""), msgs)
+        for mi, m in enumerate(msgs):
+            e = exp.get(mi, [])
+            if e or ri in cands[mi]:
+                got = h.find_all(ri, m)
+                assert [(g[2], g[3]) for g in got] == e, (r[0], m)
+                if e:
+                    n_hits += 1
+                    assert ri in cands[mi], ("prefilter missed", r[0], m)
+    assert n_hits >= 200          # the injected tokens were really found
+    h.close()
+
+
+def test_byte_offsets_match_utf16_offsets(oracle, harness_lib):
+    rules = [(r"\d+", 0, 3), (r"[^\s]+@[a-z]+", 0, 3), (r".", 0, 3), (r"\b\w+\b", 0, 3), (r"", 0, 3), (r"x*", 0, 3)]
+    h = Harness(harness_lib, rules)
+    texts = ["héllo 123 wörld 45", "😀a@b 😀😀 c@d", "日本語 12 テスト", "", "a", "😀", "ab cd 7"]
+    for t in texts:
+        m = t.encode("utf-8")
+        mp = u16_to_byte_offsets(m)
+        for ri, r in enumerate(rules):
+            exp = oracle_spans(oracle, oracle.Regex(r[0]), [m]).get(0, [])
+            got = h.find_all(ri, m)
+            assert [(g[2], g[3]) for g in got] == exp, (r[0], t)
+            assert [(g[0], g[1]) for g in got] == [(mp[s], mp[e]) for s, e in exp], (r[0], t)
+    h.close()
+
+
+SYNTAX_ERRORS = ["a(b", "[abc", "a)", "*a", "a**", "a{2,1}", "(?<n", "x{3}{2}", "\\", "(?", "[b-a]", "+"]
+UNSUPPORTED = [r"(a)\1", r"(?=ab)c", r"(?<!ab)c", r"(?<n>a)\k<n>", r"(?=a)*b"]
+VALID = ["a{", "a{,3}", "x{1,2}y", "[]a]?", "[^]", r"\c", r"é+", r"a|", "()", "(?:)", r"[\d-x]", r"\x4", r"\08", "}{", "]"]
+
+
+def test_syntax_and_support_classification(oracle, harness_lib):
+    from vainplex_openclaw_b200 import _native as N
+    for s in SYNTAX_ERRORS:
+        assert N.rule_check(s) == N.CG_ERR_SYNTAX, s
+        with pytest.raises(oracle.RegexSyntaxError):
+            oracle.Regex(s)
+    for s in UNSUPPORTED:
+        assert N.rule_check(s) == N.CG_ERR_UNSUPPORTED, s
+        oracle.Regex(s)                       # valid JS: the oracle accepts it
+    for s in VALID:
+        assert N.rule_check(s) == 0, s
+        oracle.Regex(s)
+    assert N.rule_check("[a-z]{2000}") == N.CG_ERR_TOO_LARGE
+    assert N.rule_check("É", N.FLAG_ICASE) == N.CG_ERR_UNSUPPORTED
+
+
+ATOMS = ["a", "b", "c", "1", " ", "é", "😀", ".", r"\d", r"\w", r"\s", r"\S", r"\W", "[ab]", "[^a]", "[a-c1]", r"[^\s1]", r"\b", r"\B",
+         "^", "$", "(?!a)", "(?=b)", "(?<!a)", "(?<=b)", "(?<![a1])", r"(?!\d)"]
+QUANTS = ["", "", "", "*", "+", "?", "{2}", "{1,2}", "{2,}", "*?", "+?", "??", "{1,3}?"]
+
+
+def random_regex(rng, depth=0):
+    n = int(rng.integers(1, 5))
+    parts = []
+    for _ in range(n):
+        u = rng.random()
+        if depth < 2 and u < 0.25:
+            inner = random_regex(rng, depth + 1)
+            if rng.random() < 0.5:
+                inner = inner + "|" + random_regex(rng, depth + 1)
+            atom = ("(?:%s)" if rng.random() < 0.6 else "(%s)") % inner
+        else:
+            atom = ATOMS[int(rng.integers(0, len(ATOMS)))]
+        q = QUANTS[int(rng.integers(0, len(QUANTS)))]
+        if atom in ("^", "$", r"\b", r"\B") or atom.startswith("(?<") :
+            q = ""
+        if atom.startswith("(?=") or atom.startswith("(?!"):
+            q = ""
+        parts.append(atom + q)
+    return "".join(parts)
+
+
+def test_random_regex_differential(oracle, harness_lib):
+    """product compiler + VM vs oracle on random patterns / texts over a tiny alphabet (dense matches,
+    empty matches, astral characters, lazy quantifiers, lookarounds)."""
+    rng = np.random.default_rng(20260921)
+    alphabet = ["a", "b", "c", "1", " ", "é", "😀", "\n", "A"]
+    texts = ["".join(alphabet[int(k)] for k in rng.integers(0, len(alphabet), int(rng.integers(0, 24)))) for _ in range(60)]
+    texts += ["", "a", "aaaa", "abcabc", "😀", "a😀b", "1 a1"]
+    msgs = [t.encode("utf-8") for t in texts]
+    checked = 0
+    for it in range(700):
+        src = random_regex(rng)
+        fl = 1 if rng.random() < 0.2 else 0
+        try:
+            rx = oracle.Regex(src, "i" if fl else "")
+        except oracle.RegexSyntaxError:
+            rx = None
+        except oracle.OracleUnsupported:
+            continue
+        h = Harness(harness_lib, [(src, fl, 3)])
+        st = int(h.status[0])
+        if rx is None:
+            assert st == -1, ("oracle says syntax error, product says", st, src)
+            h.close()
+            continue
+        assert st != -1, ("product says syntax error, oracle accepts", src, harness_lib.harness_rule_error(h.h, 0))
+        if st != 0:
+            h.close()
+            continue
+        try:
+            exp = oracle_spans(oracle, rx, msgs)
+        except RuntimeError:          # exponential backtracking in the oracle: not a usable vector
+            h.close()
+            continue
+        for mi, m in enumerate(msgs):
+            got = [(g[2], g[3]) for g in h.find_all(0, m)]
+            assert got == exp.get(mi, []), (src, fl, texts[mi])
+            if exp.get(mi):
+                assert 0 in h.candidates(m), ("prefilter missed", src, texts[mi])
+        checked += 1
+        h.close()
+    assert checked > 400
+
+
+def test_abi_exports_every_declared_symbol():
+    """every CG_API symbol of include/openclaw_gov.h is exported by the built library (no compute calls)."""
+    from vainplex_openclaw_b200 import _native as N
+    hdr = open(os.path.join(HERE, "..", "include", "openclaw_gov.h")).read()
+    declared = set(re.findall(r"CG_API\s+[\w\s\*]+?\b(cg_\w+)\s*\(", hdr))
+    assert declared == set(N.EXPORTS), declared ^ set(N.EXPORTS)
+    L = N.load()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.cg_version() >= 100
+
+
+def test_no_device_fails_loudly():
+    """Without a CUDA device the product refuses to compute (no CPU fallback)."""
+    from vainplex_openclaw_b200 import _native as N
+    if N.load().cg_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(N.GovError) as ei:
+        N.init()
+    assert ei.value.code == -3
+    with pytest.raises(N.GovError):
+        N.Ruleset([("abc", 0, 3)])

@@ -1,0 +1,199 @@
+"""The oracle is pinned before it is trusted (CPU only):
+  * every vector of gov/test/redaction/registry.test.ts (tests/golden/registry_vectors.json)
+  * SHA-256: NIST/FIPS 180-4 vectors, hashlib, and the digests quoted in gov/RFC.md:1561-1562
+  * Merkle: level-wise fold == RFC 6962 recursive MTH for every n (tree shape), fold of aligned blocks
+  * a second, unrelated engine (Python `re` on UTF-16-unit strings) agrees on the built-in rules
+"""
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VECTORS = json.load(open(os.path.join(HERE, "golden", "registry_vectors.json")))["vectors"]
+
+
+def run_checks(matches, checks):
+    for c in checks:
+        if c["op"] == "some":
+            assert any(m["id"] in c["ids"] for m in matches) == c["value"], c
+        elif c["op"] in ("len_eq", "len_ge"):
+            n = len([m for m in matches if "filter_id" not in c or m["id"] == c["filter_id"]])
+            assert (n == c["n"]) if c["op"] == "len_eq" else (n >= c["n"]), (c, matches)
+        elif c["op"] == "id_at":
+            assert matches[c["i"]]["id"] == c["id"], c
+        elif c["op"] == "match_at":
+            assert matches[c["i"]]["match"] == c["match"], c
+        elif c["op"] == "find_defined":
+            assert any(m["id"] == c["id"] for m in matches), c
+
+
+@pytest.mark.parametrize("v", VECTORS, ids=lambda v: "L%d" % v["line"])
+def test_oracle_matches_reference_vectors(oracle, v):
+    reg = oracle.builtin_registry(v["categories"], v["custom"])
+    run_checks(oracle.find_matches(reg, v["input"]), v["checks"])
+
+
+def test_vector_count_is_complete():
+    assert len(VECTORS) >= 125 and sum(len(v["checks"]) for v in VECTORS) >= 140
+
+
+def test_survey_smoke_vectors(oracle):
+    reg = oracle.builtin_registry()
+    m = oracle.find_matches(reg, "api_key=sk-abcdefghijklmnopqrstuvwxyz")
+    assert [(x["id"], x["start"], x["end"]) for x in m] == [("key-value-credential", 0, 37)]
+    # Appendix B.1: identical spans from openai-api-key and generic-api-key -> iteration order wins
+    m = oracle.find_matches(reg, "sk-" + "a" * 26)
+    assert [x["id"] for x in m] == ["openai-api-key"]
+    assert oracle.find_matches(reg, "") == []
+
+
+def test_invalid_custom_pattern_is_dropped(oracle):
+    reg = oracle.builtin_registry(["custom"], [{"name": "bad", "regex": "[invalid", "category": "custom"}])
+    assert reg == []
+
+
+def test_matches_any_semantics(oracle):
+    cache = {"secret\\d+": oracle.Regex("secret\\d+")}
+    assert oracle.matches_any("secret\\d+", ["my secret42"], cache)
+    assert not oracle.matches_any("secret\\d+", ["my secret"], cache)
+    assert oracle.matches_any(["nope", "se+cret"], ["my seeecret"], {})          # compiled on the fly
+    assert oracle.matches_any("a(b", ["xa(by"], {})                               # syntax error -> includes()
+    assert not oracle.matches_any("a(b", ["xaby"], {})
+
+
+# ---------------------------------------------------------------------------------------- SHA-256
+
+NIST = [
+    (b"abc", "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"),
+    (b"", "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"),
+    (b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq",
+     "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1"),
+    (b"a" * 1000000, "cdc76e5c9914fb9281a1c7e284d73e67f1809a48a497200e046d39ccc7112cd0"),
+]
+
+
+@pytest.mark.parametrize("msg,hexd", NIST, ids=["abc", "empty", "448bit", "million_a"])
+def test_sha256_known_answers(oracle, msg, hexd):
+    assert oracle.sha256(msg).hex() == hexd
+
+
+def test_sha256_rfc_md_digests(oracle):
+    # gov/RFC.md:1561-1562 quotes these two digests
+    assert oracle.sha256_hex_of_js_string("") == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    assert oracle.sha256_hex_of_js_string("Hello World!") == "7f83b1657ff1fc53b92dc18148a1d65dfc2d4b1fa3d677284addd200126d9069"
+
+
+def test_sha256_every_length_against_hashlib(oracle):
+    rng = np.random.default_rng(1)
+    for n in list(range(0, 200)) + [255, 256, 257, 1000, 4095]:
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert oracle.sha256(b) == hashlib.sha256(b).digest()
+
+
+def test_vault_placeholder(oracle):
+    h = hashlib.sha256("s3cr3t-ü".encode()).hexdigest()
+    assert oracle.vault_placeholder("s3cr3t-ü", "credential") == "[REDACTED:credential:%s]" % h[:8]
+    assert oracle.vault_placeholder("s3cr3t-ü", "pii", long_form=True) == "[REDACTED:pii:%s]" % h[:12]
+    # lone surrogate hashes as U+FFFD
+    assert oracle.sha256_hex_of_js_string("\ud800") == hashlib.sha256(b"\xef\xbf\xbd").hexdigest()
+
+
+# ---------------------------------------------------------------------------------------- Merkle
+
+def _leaves(rng, n, lo=0, hi=300):
+    msgs = [rng.integers(0, 256, int(rng.integers(lo, hi + 1)), dtype=np.uint8).tobytes() for _ in range(n)]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    return np.frombuffer(b"".join(msgs) + b"\0", dtype=np.uint8).copy(), off, msgs
+
+
+def test_merkle_small_trees_by_hand(oracle):
+    H = lambda b: hashlib.sha256(b).digest()
+    rng = np.random.default_rng(2)
+    data, off, m = _leaves(rng, 5)
+    L = [H(b"\x00" + x) for x in m]
+    N = lambda a, b: H(b"\x01" + a + b)
+    assert oracle.merkle_root(data[:1], np.zeros(1, dtype=np.uint64)) == H(b"")
+    assert oracle.merkle_root(data, off[:2]) == L[0]
+    assert oracle.merkle_root(data, off[:3]) == N(L[0], L[1])
+    assert oracle.merkle_root(data, off[:4]) == N(N(L[0], L[1]), L[2])
+    assert oracle.merkle_root(data, off[:6]) == N(N(N(L[0], L[1]), N(L[2], L[3])), L[4])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 31, 32, 33, 100, 255, 1000, 1025])
+def test_merkle_levelwise_equals_rfc6962_shape(oracle, n):
+    rng = np.random.default_rng(n)
+    data, off, _ = _leaves(rng, n, 0, 80)
+    assert oracle.merkle_root(data, off) == oracle.merkle_root_rfc6962(data, off)
+
+
+@pytest.mark.parametrize("n,k", [(1000, 4), (1024, 5), (1025, 6), (37, 3), (5, 4)])
+def test_merkle_block_fold_composes(oracle, n, k):
+    """roots of aligned 2^k-leaf blocks folded with the same rule == the root (multi-GPU sharding rule)."""
+    rng = np.random.default_rng(n * 31 + k)
+    data, off, _ = _leaves(rng, n, 1, 64)
+    bs = 1 << k
+    roots = []
+    for s in range(0, n, bs):
+        e = min(n, s + bs)
+        sub_off = (off[s:e + 1] - off[s]).astype(np.uint64)
+        roots.append(np.frombuffer(oracle.merkle_root(data[int(off[s]):], sub_off), dtype=np.uint8))
+    assert oracle.merkle_fold(np.stack(roots)) == oracle.merkle_root(data, off)
+
+
+def test_merkle_fixed_equals_variable(oracle):
+    rng = np.random.default_rng(5)
+    n, ll = 300, 64
+    data = rng.integers(0, 256, n * ll + 1, dtype=np.uint8)
+    off = (np.arange(n + 1, dtype=np.uint64) * ll)
+    assert oracle.merkle_root_fixed(data, ll, n) == oracle.merkle_root(data, off)
+
+
+# ------------------------------------------------------------------ second opinion: Python `re`
+
+PY_WS = "\t\n\x0b\x0c\r \xa0  -     　﻿"
+
+
+def js_to_py(src: str) -> str:
+    """Enough of a JS->Python translation for the 17 built-ins (ASCII \\d \\w \\b via re.ASCII)."""
+    out, i, in_class = [], 0, False
+    while i < len(src):
+        c = src[i]
+        if c == "\\" and i + 1 < len(src):
+            n = src[i + 1]
+            if n == "s":
+                out.append(PY_WS if in_class else "[" + PY_WS + "]")
+                i += 2
+                continue
+            out.append(src[i:i + 2])
+            i += 2
+            continue
+        if c == "[":
+            in_class = True
+        elif c == "]":
+            in_class = False
+        out.append(c)
+        i += 1
+    return "".join(out)
+
+
+def test_python_re_agrees_on_builtins(oracle):
+    from vainplex_openclaw_b200 import workload as W
+    rules = W.make_rules(17)
+    data, off, _ = W.make_messages(1500, 192, rules, p_hit=0.3, utf8_frac=0.0, seed=77)
+    buf = data.numpy()
+    msgs = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(1500)]
+    for r in rules:
+        rx = oracle.Regex(r["source"], "i" if r["flags"] else "")
+        py = re.compile(js_to_py(r["source"]), re.ASCII | (re.IGNORECASE if r["flags"] else 0))
+        d, o = oracle.pack(msgs)
+        got = oracle.find_matches_batch([(rx, "custom")], d, o)
+        exp = []
+        for mi, m in enumerate(msgs):
+            s = m.decode("utf-8", "replace")
+            exp += [(mi, 0, x.start(), x.end()) for x in py.finditer(s)]
+        assert [tuple(x) for x in got.tolist()] == exp, r["id"]

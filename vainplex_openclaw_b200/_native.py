@@ -1,0 +1,244 @@
+"""ctypes binding of the C ABI in include/openclaw_gov.h (the same symbols the Node N-API shim binds).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable, every
+compute entry point raises GovError -- the caller's failMode decides (reference: src/hooks.ts:232-241).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+CG_OK = 0
+ERR_NAMES = {-1: "INVALID_ARG", -2: "NOT_INITIALIZED", -3: "CUDA", -4: "SYNTAX", -5: "UNSUPPORTED",
+             -6: "TOO_LARGE", -7: "CAPACITY", -8: "NOMEM"}
+CG_ERR_SYNTAX, CG_ERR_UNSUPPORTED, CG_ERR_TOO_LARGE, CG_ERR_CAPACITY = -4, -5, -6, -7
+FLAG_ICASE = 1
+CAT = {"credential": 0, "financial": 1, "pii": 2, "custom": 3}
+OPT_DIRECT7, OPT_LUT = 0, 1
+
+
+class GovError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("openclaw_gov: %s (%d): %s" % (ERR_NAMES.get(code, "?"), code, msg))
+        self.code = code
+
+
+class cg_rule(C.Structure):
+    _fields_ = [("source", C.c_char_p), ("source_len", C.c_uint32), ("flags", C.c_uint32), ("category", C.c_uint32)]
+
+
+class cg_ruleset_info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_rules", "n_ok", "n_always_candidate", "n_sets", "prefilter_mode",
+                                          "prefilter_states", "prefilter_cols", "prefilter_factor_len",
+                                          "prefilter_bytes", "program_words")]
+
+
+class cg_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("messages_scanned", "bytes_scanned", "candidate_events", "verified_pairs",
+                                          "hits", "spans", "sha256_items", "merkle_leaves", "kernel_launches")] + \
+               [("last_scan_ms", C.c_double), ("last_merkle_ms", C.c_double)]
+
+
+HIT_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32)])
+SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", np.uint32), ("end_byte", np.uint32),
+                       ("start16", np.uint32), ("end16", np.uint32)])
+
+EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
+           "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
+           "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
+           "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """dlopen the in-tree library (building it first when sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.needs_build():
+        if os.path.exists("/usr/local/cuda/bin/nvcc") or os.environ.get("NVCC"):
+            _build.build()
+        elif not os.path.exists(_build.LIB):
+            raise GovError(-2, "libopenclaw_gov.so is not built and nvcc is unavailable")
+    L = C.CDLL(_build.LIB)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.cg_init.argtypes = [i32]; L.cg_init.restype = i32
+    L.cg_shutdown.restype = None
+    L.cg_last_error.restype = C.c_char_p
+    L.cg_version.restype = i32
+    L.cg_device_count.restype = i32
+    L.cg_get_stats.argtypes = [C.POINTER(cg_stats)]; L.cg_get_stats.restype = i32
+    L.cg_launch_count.restype = u64
+    L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
+    L.cg_ruleset_destroy.argtypes = [vp]; L.cg_ruleset_destroy.restype = None
+    L.cg_ruleset_get_info.argtypes = [vp, C.POINTER(cg_ruleset_info)]; L.cg_ruleset_get_info.restype = i32
+    L.cg_rule_check.argtypes = [C.c_char_p, u32, u32, C.c_char_p, u32]; L.cg_rule_check.restype = i32
+    L.cg_scan_batch.argtypes = [vp, vp, vp, u32, vp, vp, u32, C.POINTER(u32)]; L.cg_scan_batch.restype = i32
+    L.cg_scan_one.argtypes = [vp, vp, u32, C.POINTER(u64), vp, u32, C.POINTER(u32)]; L.cg_scan_one.restype = i32
+    L.cg_find_matches_batch.argtypes = [vp, vp, vp, u32, vp, u32, C.POINTER(u32)]; L.cg_find_matches_batch.restype = i32
+    L.cg_scan_batch_device.argtypes = [vp, vp, vp, u32, vp, vp]; L.cg_scan_batch_device.restype = i32
+    L.cg_sha256_batch.argtypes = [vp, vp, u32, vp]; L.cg_sha256_batch.restype = i32
+    L.cg_merkle_root.argtypes = [vp, vp, u64, vp]; L.cg_merkle_root.restype = i32
+    L.cg_merkle_root_fixed.argtypes = [vp, u64, u64, vp]; L.cg_merkle_root_fixed.restype = i32
+    L.cg_merkle_block_roots_device.argtypes = [vp, u64, u64, u32, vp, vp]; L.cg_merkle_block_roots_device.restype = i32
+    L.cg_merkle_fold.argtypes = [vp, u64, vp]; L.cg_merkle_fold.restype = i32
+    L.cg_merkle_fold_device.argtypes = [vp, u64, vp, vp]; L.cg_merkle_fold_device.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != CG_OK:
+        raise GovError(rc, (load().cg_last_error() or b"").decode("utf-8", "replace"))
+
+
+_inited = False
+
+
+def init(device: int = -1):
+    """cg_init; raises GovError(CUDA) when no B200-class device is present."""
+    global _inited
+    check(load().cg_init(device))
+    _inited = True
+
+
+def rule_check(source: str, flags: int = 0) -> int:
+    """What would `new RegExp(source)` do: CG_OK, CG_ERR_SYNTAX, or CG_ERR_UNSUPPORTED/TOO_LARGE (no device needed)."""
+    b = js_utf8(source)
+    return load().cg_rule_check(b, len(b), flags, None, 0)
+
+
+def js_utf8(s: str) -> bytes:
+    """Buffer.from(str,'utf8'): lone surrogates become U+FFFD."""
+    try:
+        return s.encode("utf-8")
+    except UnicodeEncodeError:
+        return s.encode("utf-16-le", "surrogatepass").decode("utf-16-le", "replace").encode("utf-8")
+
+
+def pack(messages) -> tuple[np.ndarray, np.ndarray]:
+    """list of bytes -> (uint8 buffer padded by 64 bytes, uint32 offsets[n+1])."""
+    off = np.zeros(len(messages) + 1, dtype=np.uint32)
+    if len(messages):
+        off[1:] = np.cumsum([len(m) for m in messages], dtype=np.uint64).astype(np.uint32)
+    data = np.frombuffer(b"".join(messages) + b"\0" * 64, dtype=np.uint8).copy()
+    return data, off
+
+
+class Ruleset:
+    """cg_ruleset handle.  rules: iterable of (source:str|bytes, flags:int, category:int)."""
+
+    def __init__(self, rules, options: int = OPT_DIRECT7, strict: bool = False):
+        L = load()
+        if not _inited:
+            init()
+        rules = list(rules)
+        self._keep = [r[0] if isinstance(r[0], bytes) else js_utf8(r[0]) for r in rules]
+        arr = (cg_rule * max(1, len(rules)))()
+        for i, r in enumerate(rules):
+            arr[i].source = self._keep[i]; arr[i].source_len = len(self._keep[i])
+            arr[i].flags = r[1]; arr[i].category = r[2]
+        self.status = np.zeros(max(1, len(rules)), dtype=np.int32)
+        h = C.c_void_p()
+        check(L.cg_ruleset_create(arr, len(rules), options, C.byref(h), None if strict else self.status.ctypes.data))
+        self.handle = h
+        self.n_rules = len(rules)
+        self.status = self.status[:len(rules)]
+
+    def close(self):
+        if getattr(self, "handle", None):
+            load().cg_ruleset_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def info(self) -> cg_ruleset_info:
+        o = cg_ruleset_info()
+        check(load().cg_ruleset_get_info(self.handle, C.byref(o)))
+        return o
+
+    def scan_batch(self, data: np.ndarray, off: np.ndarray, want_hits: bool = True):
+        """-> (words[n] uint64, hits structured array sorted by (msg, rule))."""
+        n = len(off) - 1
+        words = np.zeros(max(n, 1), dtype=np.uint64)
+        nh = C.c_uint32(0)
+        cap = 1024
+        while True:
+            hits = np.zeros(cap, dtype=HIT_DTYPE)
+            rc = load().cg_scan_batch(self.handle, data.ctypes.data, off.ctypes.data, n, words.ctypes.data,
+                                      hits.ctypes.data if want_hits else None, cap, C.byref(nh))
+            if rc == CG_ERR_CAPACITY and nh.value > cap:
+                cap = nh.value
+                continue
+            check(rc)
+            return words[:n], hits[:nh.value]
+
+    def find_matches_batch(self, data: np.ndarray, off: np.ndarray):
+        """-> spans structured array, resolved per registry.ts:288-316, sorted by (msg, start)."""
+        n = len(off) - 1
+        ns = C.c_uint32(0)
+        cap = 1024
+        while True:
+            spans = np.zeros(cap, dtype=SPAN_DTYPE)
+            rc = load().cg_find_matches_batch(self.handle, data.ctypes.data, off.ctypes.data, n, spans.ctypes.data, cap, C.byref(ns))
+            if rc == CG_ERR_CAPACITY and ns.value > cap:
+                cap = ns.value
+                continue
+            check(rc)
+            return spans[:ns.value]
+
+    def scan_batch_device(self, d_bytes: int, d_off: int, n: int, d_words: int, stream: int = 0):
+        check(load().cg_scan_batch_device(self.handle, d_bytes, d_off, n, d_words, stream))
+
+
+def sha256_batch(data: np.ndarray, off64: np.ndarray) -> np.ndarray:
+    if not _inited:
+        init()
+    n = len(off64) - 1
+    out = np.zeros((max(n, 1), 32), dtype=np.uint8)
+    check(load().cg_sha256_batch(data.ctypes.data, off64.ctypes.data, n, out.ctypes.data))
+    return out[:n]
+
+
+def merkle_root(data: np.ndarray, off64: np.ndarray) -> bytes:
+    if not _inited:
+        init()
+    out = np.zeros(32, dtype=np.uint8)
+    check(load().cg_merkle_root(data.ctypes.data, off64.ctypes.data, len(off64) - 1, out.ctypes.data))
+    return out.tobytes()
+
+
+def merkle_root_fixed(data: np.ndarray, leaf_len: int, n: int) -> bytes:
+    if not _inited:
+        init()
+    out = np.zeros(32, dtype=np.uint8)
+    check(load().cg_merkle_root_fixed(data.ctypes.data, leaf_len, n, out.ctypes.data))
+    return out.tobytes()
+
+
+def merkle_fold(nodes: np.ndarray) -> bytes:
+    if not _inited:
+        init()
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint8)
+    out = np.zeros(32, dtype=np.uint8)
+    check(load().cg_merkle_fold(nodes.ctypes.data, nodes.shape[0], out.ctypes.data))
+    return out.tobytes()
+
+
+def stats() -> cg_stats:
+    s = cg_stats()
+    check(load().cg_get_stats(C.byref(s)))
+    return s
+
+
+def launch_count() -> int:
+    return int(load().cg_launch_count())

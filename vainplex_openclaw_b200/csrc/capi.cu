@@ -1,0 +1,516 @@
+// capi.cu -- the C ABI declared in include/openclaw_gov.h (host orchestration only; every byte of
+// matching and hashing happens in the kernels of scan_kernels.cu / sha256_kernels.cu).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/openclaw_gov.h"
+#include "kernels.h"
+#include "rulec.h"
+#include "ruleset_image.h"
+
+using namespace cg;
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+
+struct Ctx {
+  bool ready = false;
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cg_stats stats{};
+  uint64_t launches = 0;
+  // grow-only staging in HBM
+  uint8_t* d_bytes = nullptr; size_t cap_bytes = 0;
+  uint32_t* d_off32 = nullptr; size_t cap_off32 = 0;
+  uint64_t* d_off64 = nullptr; size_t cap_off64 = 0;
+  uint64_t* d_words = nullptr; size_t cap_words = 0;
+  uint32_t* d_dig[2] = {nullptr, nullptr}; size_t cap_dig[2] = {0, 0};
+} G;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return CG_ERR_CUDA;
+}
+#define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
+
+template <typename T>
+int grow(T** p, size_t* cap, size_t need_elems) {
+  if (need_elems <= *cap && *p) return CG_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  size_t n = need_elems + need_elems / 4 + 64;
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) { *p = nullptr; return cuda_fail(e, "cudaMalloc"); }
+  *cap = n;
+  return CG_OK;
+}
+
+}  // namespace
+
+struct cg_ruleset {
+  HostImage host;
+  std::vector<uint32_t> category;
+  DevRuleset dev{};
+  std::vector<void*> allocs;
+  uint32_t n_sets = 0, program_words = 0;
+  ScanWork work{};
+  ~cg_ruleset() {
+    for (void* p : allocs) cudaFree(p);
+    cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.spans);
+  }
+};
+
+namespace {
+
+template <typename T>
+int upload(cg_ruleset* rs, const std::vector<T>& v, const T** out, size_t pad_elems = 4) {
+  void* d = nullptr;
+  size_t bytes = (v.size() + pad_elems) * sizeof(T);
+  CU(cudaMalloc(&d, bytes));
+  rs->allocs.push_back(d);
+  CU(cudaMemset(d, 0, bytes));
+  if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const T*>(d);
+  return CG_OK;
+}
+
+int ensure_work(cg_ruleset* rs, uint32_t slot_cap, uint32_t event_cap, uint32_t span_cap) {
+  ScanWork& w = rs->work;
+  if (!w.counters) { CU(cudaMalloc((void**)&w.counters, 16 * sizeof(uint32_t))); }
+  if (slot_cap > w.slot_cap) {
+    cudaFree(w.slot_msg); cudaFree(w.cand); cudaFree(w.hit); w.slot_msg = w.cand = w.hit = nullptr; w.slot_cap = 0;
+    size_t rw = rs->dev.rw ? rs->dev.rw : 1;
+    CU(cudaMalloc((void**)&w.slot_msg, (size_t)slot_cap * 4));
+    CU(cudaMalloc((void**)&w.cand, (size_t)slot_cap * rw * 4));
+    CU(cudaMalloc((void**)&w.hit, (size_t)slot_cap * rw * 4));
+    w.slot_cap = slot_cap;
+  }
+  if (event_cap > w.event_cap) { cudaFree(w.events); w.events = nullptr; w.event_cap = 0; CU(cudaMalloc((void**)&w.events, (size_t)event_cap * sizeof(uint2))); w.event_cap = event_cap; }
+  if (span_cap > w.span_cap) { cudaFree(w.spans); w.spans = nullptr; w.span_cap = 0; CU(cudaMalloc((void**)&w.spans, (size_t)span_cap * 24)); w.span_cap = span_cap; }
+  return CG_OK;
+}
+
+// scan + verify + finalize on device-resident input; asynchronous
+int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words,
+                    bool spans, cudaStream_t st) {
+  CU(cudaMemsetAsync(rs->work.counters, 0, 16 * sizeof(uint32_t), st));
+  int k = 0;
+  k += launch_scan(rs->dev, rs->work, d_bytes, d_off, n, d_words, G.sm_count, st);
+  k += launch_verify(rs->dev, rs->work, d_bytes, d_off, spans, G.sm_count, st);
+  k += launch_finalize(rs->dev, rs->work, d_words, G.sm_count, st);
+  G.launches += k; G.stats.kernel_launches += k;
+  CU(cudaGetLastError());
+  return CG_OK;
+}
+
+struct HostScan {
+  std::vector<uint32_t> counters, slot_msg, hit, spans;
+};
+
+// full host-buffer scan with capacity retry; leaves words in G.d_words
+int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, bool spans, HostScan* hs) {
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!rs || (n && (!bytes || !offsets))) return fail(CG_ERR_INVALID_ARG, "null argument");
+  size_t total = n ? offsets[n] : 0;
+  int rc;
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
+  if ((rc = grow(&G.d_words, &G.cap_words, (size_t)n + 1))) return rc;
+  cudaStream_t st = G.stream;
+  if (n) {
+    CU(cudaMemcpyAsync(G.d_bytes, bytes, total, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(G.d_bytes + total, 0, 64, st));
+    CU(cudaMemcpyAsync(G.d_off32, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+  }
+  uint32_t slot_cap = std::max<uint32_t>(n, 1), event_cap = std::max<uint32_t>(4 * n, 4096), span_cap = spans ? std::max<uint32_t>(4 * n, 4096) : 1;
+  hs->counters.assign(16, 0);
+  for (int attempt = 0; attempt < 8; attempt++) {
+    if ((rc = ensure_work(rs, slot_cap, event_cap, span_cap))) return rc;
+    CU(cudaEventRecord(G.ev0, st));
+    if (n) { if ((rc = run_scan_device(rs, G.d_bytes, G.d_off32, n, G.d_words, spans, st))) return rc; }
+    else CU(cudaMemsetAsync(rs->work.counters, 0, 64, st));
+    CU(cudaEventRecord(G.ev1, st));
+    CU(cudaMemcpyAsync(hs->counters.data(), rs->work.counters, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_scan_ms = ms;
+    uint32_t flags = hs->counters[3];
+    if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
+    if (flags & ERR_EVENT_OVERFLOW) { event_cap = std::max(event_cap * 4, hs->counters[1] + 1024); continue; }
+    if (flags & ERR_SPAN_OVERFLOW) { span_cap = std::max(span_cap * 4, hs->counters[2] + 1024); continue; }
+    if (flags & ERR_SLOT_OVERFLOW) { slot_cap = slot_cap * 2; continue; }
+    G.stats.messages_scanned += n; G.stats.bytes_scanned += total;
+    G.stats.candidate_events += hs->counters[1]; G.stats.verified_pairs += hs->counters[1];
+    return CG_OK;
+  }
+  return fail(CG_ERR_CAPACITY, "candidate queue kept overflowing");
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_version(void) { return 100; }
+const char* cg_last_error(void) { return g_err.c_str(); }
+
+int cg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int cg_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (G.ready) return CG_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(CG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)"); }
+  if (device >= 0) CU(cudaSetDevice(device));
+  CU(cudaGetDevice(&G.device));
+  cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, G.device));
+  if (prop.major < 10) return fail(CG_ERR_CUDA, "device is not sm_100 class (kernels are built for sm_100a only)");
+  G.sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&G.ev0)); CU(cudaEventCreate(&G.ev1));
+  G.ready = true;
+  return CG_OK;
+}
+
+void cg_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return;
+  cudaStreamSynchronize(G.stream);
+  cudaFree(G.d_bytes); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
+  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); cudaStreamDestroy(G.stream);
+  G = Ctx();
+}
+
+int cg_get_stats(cg_stats* out) { if (!out) return fail(CG_ERR_INVALID_ARG, "null"); *out = G.stats; return CG_OK; }
+uint64_t cg_launch_count(void) { return G.launches; }
+
+int cg_rule_check(const char* source, uint32_t source_len, uint32_t flags, char* err, uint32_t err_len) {
+  CompiledRule r = compile_rule(source ? source : "", source_len, flags);
+  if (err && err_len) { snprintf(err, err_len, "%s", r.error.c_str()); }
+  if (r.status == RULE_OK) return CG_OK;
+  g_err = r.error;
+  return r.status == RULE_ERR_SYNTAX ? CG_ERR_SYNTAX : r.status == RULE_ERR_UNSUPPORTED ? CG_ERR_UNSUPPORTED : CG_ERR_TOO_LARGE;
+}
+
+int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, cg_ruleset** out, int32_t* status_per_rule) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out || (n_rules && !rules)) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  std::unique_ptr<cg_ruleset> rs(new cg_ruleset());
+  std::vector<RuleSrc> src(n_rules);
+  rs->category.resize(n_rules);
+  for (uint32_t i = 0; i < n_rules; i++) { src[i] = RuleSrc{rules[i].source, rules[i].source_len, rules[i].flags}; rs->category[i] = rules[i].category; }
+  ImageOptions io;
+  io.mode = (options & CG_OPT_PREFILTER_LUT) ? 1 : 0;
+  if (const char* e = getenv("CG_PREFILTER_MODE")) io.mode = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("CG_PREFILTER_KB")) io.budget_bytes = (size_t)atoi(e) * 1024;
+  if (const char* e = getenv("CG_PREFILTER_CLASSES")) io.max_classes = atoi(e);
+  if (const char* e = getenv("CG_FACTOR_LEN")) io.max_factor_len = atoi(e);
+  std::string perr;
+  if (!build_host_image(src.data(), n_rules, io, &rs->host, &perr)) return fail(CG_ERR_TOO_LARGE, perr);
+  HostImage& H = rs->host;
+  for (uint32_t i = 0; i < n_rules; i++) {
+    int32_t st = H.rules[i].status;
+    int32_t code = st == RULE_OK ? CG_OK : st == RULE_ERR_SYNTAX ? CG_ERR_SYNTAX : st == RULE_ERR_UNSUPPORTED ? CG_ERR_UNSUPPORTED : CG_ERR_TOO_LARGE;
+    if (status_per_rule) status_per_rule[i] = code;
+    else if (code != CG_OK) return fail(code, "rule " + std::to_string(i) + ": " + H.rules[i].error);
+  }
+  const Prefilter& P = H.pf;
+  const std::vector<uint8_t>& image = H.image;
+  const std::vector<uint32_t>&prog = H.prog, &prog_off = H.prog_off, &sets = H.sets, &first = H.first;
+  const std::vector<uint16_t>& ranges = H.ranges;
+  rs->n_sets = H.n_sets; rs->program_words = (uint32_t)H.prog.size();
+
+  DevRuleset& d = rs->dev;
+  int rc;
+  const uint8_t* d_image; if ((rc = upload(rs.get(), image, &d_image, 16))) return rc;
+  d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode;
+  d.ncols_log2 = 0; while ((1 << d.ncols_log2) < P.ncols) d.ncols_log2++;
+  d.nstates = (uint32_t)P.nstates; d.first_accept = (uint32_t)P.first_accept;
+  if ((rc = upload(rs.get(), P.out_offsets, &d.out_offsets))) return rc;
+  if ((rc = upload(rs.get(), P.out_rules, &d.out_rules))) return rc;
+  if ((rc = upload(rs.get(), P.always_rules, &d.always_rules))) return rc;
+  d.n_always = (uint32_t)P.always_rules.size();
+  if ((rc = upload(rs.get(), prog, &d.prog))) return rc;
+  if ((rc = upload(rs.get(), prog_off, &d.rule_prog_off))) return rc;
+  if ((rc = upload(rs.get(), sets, &d.sets, 8))) return rc;
+  if ((rc = upload(rs.get(), ranges, &d.set_ranges, 8))) return rc;
+  if ((rc = upload(rs.get(), first, &d.rule_first, 8))) return rc;
+  d.n_rules = n_rules; d.rw = (n_rules + 31) / 32; if (d.rw == 0) d.rw = 1;
+  *out = rs.release();
+  return CG_OK;
+}
+
+void cg_ruleset_destroy(cg_ruleset* rs) { std::lock_guard<std::mutex> lk(g_mu); if (rs) { if (G.ready) cudaStreamSynchronize(G.stream); delete rs; } }
+
+int cg_ruleset_get_info(const cg_ruleset* rs, cg_ruleset_info* o) {
+  if (!rs || !o) return fail(CG_ERR_INVALID_ARG, "null argument");
+  memset(o, 0, sizeof *o);
+  o->n_rules = (uint32_t)rs->host.rules.size();
+  for (auto& r : rs->host.rules) if (r.status == RULE_OK) o->n_ok++;
+  o->n_always_candidate = (uint32_t)rs->host.pf.always_rules.size(); o->n_sets = rs->n_sets;
+  o->prefilter_mode = (uint32_t)rs->host.pf.mode; o->prefilter_states = (uint32_t)rs->host.pf.nstates; o->prefilter_cols = (uint32_t)rs->host.pf.ncols;
+  o->prefilter_factor_len = (uint32_t)rs->host.pf.factor_len; o->prefilter_bytes = rs->dev.image_bytes; o->program_words = rs->program_words;
+  return CG_OK;
+}
+
+int cg_scan_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint64_t* out_words,
+                  cg_hit* out_hits, uint32_t hits_cap, uint32_t* out_nhits) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostScan hs;
+  int rc = scan_host(rs, bytes, offsets, n, false, &hs);
+  if (rc) return rc;
+  cudaStream_t st = G.stream;
+  if (out_words && n) CU(cudaMemcpyAsync(out_words, G.d_words, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  uint32_t n_slots = hs.counters[0], rw = rs->dev.rw;
+  uint32_t nh = 0;
+  if ((out_hits || out_nhits) && n_slots) {
+    hs.slot_msg.resize(n_slots); hs.hit.resize((size_t)n_slots * rw);
+    CU(cudaMemcpyAsync(hs.slot_msg.data(), rs->work.slot_msg, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hs.hit.data(), rs->work.hit, (size_t)n_slots * rw * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  if ((out_hits || out_nhits) && n_slots) {
+    std::vector<uint32_t> order(n_slots);
+    for (uint32_t i = 0; i < n_slots; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hs.slot_msg[a] < hs.slot_msg[b]; });
+    for (uint32_t oi = 0; oi < n_slots; oi++) {
+      uint32_t s = order[oi];
+      for (uint32_t k = 0; k < rw; k++) {
+        uint32_t v = hs.hit[(size_t)s * rw + k];
+        while (v) { uint32_t b = __builtin_ctz(v); v &= v - 1; if (out_hits && nh < hits_cap) { out_hits[nh].msg = hs.slot_msg[s]; out_hits[nh].rule = k * 32 + b; } nh++; }
+      }
+    }
+  }
+  if (out_nhits) *out_nhits = nh;
+  G.stats.hits += nh;
+  if (out_hits && nh > hits_cap) return fail(CG_ERR_CAPACITY, "out_hits too small");
+  return CG_OK;
+}
+
+int cg_scan_one(cg_ruleset* rs, const uint8_t* bytes, uint32_t len, uint64_t* out_word, uint32_t* out_rules, uint32_t rules_cap, uint32_t* out_nrules) {
+  uint32_t off[2] = {0, len};
+  std::vector<cg_hit> hits(rules_cap ? rules_cap : 1);
+  uint32_t nh = 0; uint64_t word = 0;
+  int rc = cg_scan_batch(rs, bytes, off, 1, &word, out_rules ? hits.data() : nullptr, rules_cap, &nh);
+  if (out_word) *out_word = word;
+  if (out_nrules) *out_nrules = nh;
+  if (out_rules) for (uint32_t i = 0; i < nh && i < rules_cap; i++) out_rules[i] = hits[i].rule;
+  return rc;
+}
+
+int cg_find_matches_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, cg_span* out_spans, uint32_t spans_cap, uint32_t* out_nspans) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostScan hs;
+  int rc = scan_host(rs, bytes, offsets, n, true, &hs);
+  if (rc) return rc;
+  uint32_t ns = hs.counters[2];
+  std::vector<cg_span> raw(ns);
+  if (ns) { CU(cudaMemcpyAsync(raw.data(), rs->work.spans, (size_t)ns * 24, cudaMemcpyDeviceToHost, G.stream)); CU(cudaStreamSynchronize(G.stream)); }
+  // collection order of findMatches (registry.ts:216-236): category order, storage order, position
+  const std::vector<uint32_t>& cat = rs->category;
+  std::sort(raw.begin(), raw.end(), [&](const cg_span& a, const cg_span& b) {
+    if (a.msg != b.msg) return a.msg < b.msg;
+    if (cat[a.rule] != cat[b.rule]) return cat[a.rule] < cat[b.rule];
+    if (a.rule != b.rule) return a.rule < b.rule;
+    return a.start16 < b.start16;
+  });
+  // resolveOverlaps (registry.ts:288-316): stable sort by start asc, length desc, category order; greedy keep
+  uint32_t outn = 0;
+  for (size_t i = 0; i < raw.size();) {
+    size_t j = i; while (j < raw.size() && raw[j].msg == raw[i].msg) j++;
+    std::stable_sort(raw.begin() + i, raw.begin() + j, [&](const cg_span& a, const cg_span& b) {
+      if (a.start16 != b.start16) return a.start16 < b.start16;
+      uint32_t la = a.end16 - a.start16, lb = b.end16 - b.start16;
+      if (la != lb) return la > lb;
+      return cat[a.rule] < cat[b.rule];
+    });
+    int64_t last_end = -1;
+    for (size_t k = i; k < j; k++) if ((int64_t)raw[k].start16 >= last_end) { if (out_spans && outn < spans_cap) out_spans[outn] = raw[k]; outn++; last_end = raw[k].end16; }
+    i = j;
+  }
+  if (out_nspans) *out_nspans = outn;
+  G.stats.spans += outn;
+  if (out_spans && outn > spans_cap) return fail(CG_ERR_CAPACITY, "out_spans too small");
+  return CG_OK;
+}
+
+int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offsets, uint32_t n, void* d_out_words, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!rs || !d_bytes || !d_offsets || !d_out_words) return fail(CG_ERR_INVALID_ARG, "null argument");
+  int rc = ensure_work(rs, std::max<uint32_t>(n, 1), std::max<uint32_t>(4 * n, 4096), 1);
+  if (rc) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+  if (!n) return CG_OK;
+  rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
+  if (rc == CG_OK) { G.stats.messages_scanned += n; }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------- SHA / Merkle
+
+int cg_sha256_batch(const uint8_t* bytes, const uint64_t* offsets, uint32_t n, uint8_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!n) return CG_OK;
+  if (!offsets || !out) return fail(CG_ERR_INVALID_ARG, "null argument");
+  size_t total = offsets[n]; int rc;
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)n + 1))) return rc;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)n * 8))) return rc;
+  cudaStream_t st = G.stream;
+  if (total) CU(cudaMemcpyAsync(G.d_bytes, bytes, total, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(G.d_off64, offsets, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  int k = launch_sha256_batch(G.d_bytes, G.d_off64, n, (uint8_t*)G.d_dig[0], st);
+  G.launches += k; G.stats.kernel_launches += k; G.stats.sha256_items += n;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, G.d_dig[0], (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return CG_OK;
+}
+
+namespace {
+// fold the n digests in G.d_dig[cur] down to `target` nodes (level by level); returns buffer index
+int fold_levels(uint64_t n, uint64_t stop_at, int cur, cudaStream_t st, uint32_t max_levels = 64) {
+  uint32_t lv = 0;
+  while (n > stop_at && lv < max_levels) {
+    int k = launch_merkle_level(G.d_dig[cur], n, G.d_dig[cur ^ 1], st);
+    G.launches += k; G.stats.kernel_launches += k;
+    n = (n + 1) / 2; cur ^= 1; lv++;
+  }
+  return cur;
+}
+int empty_root(uint8_t out[32]) {
+  // SHA-256("") -- computed by the same kernel, not on the CPU
+  int rc;
+  if ((rc = grow(&G.d_off64, &G.cap_off64, 2))) return rc;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], 8))) return rc;
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, 64))) return rc;
+  CU(cudaMemsetAsync(G.d_off64, 0, 16, G.stream));
+  int k = launch_sha256_batch(G.d_bytes, G.d_off64, 1, (uint8_t*)G.d_dig[0], G.stream);
+  G.launches += k; G.stats.kernel_launches += k;
+  CU(cudaMemcpyAsync(out, G.d_dig[0], 32, cudaMemcpyDeviceToHost, G.stream));
+  CU(cudaStreamSynchronize(G.stream));
+  return CG_OK;
+}
+}  // namespace
+
+int cg_merkle_root(const uint8_t* bytes, const uint64_t* offsets, uint64_t n, uint8_t out_root[32]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!out_root) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return empty_root(out_root);
+  if (!offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
+  size_t total = offsets[n]; int rc;
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)n + 1))) return rc;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)n * 8))) return rc;
+  if ((rc = grow(&G.d_dig[1], &G.cap_dig[1], (size_t)(n + 1) / 2 * 8 + 8))) return rc;
+  cudaStream_t st = G.stream;
+  if (total) CU(cudaMemcpyAsync(G.d_bytes, bytes, total, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(G.d_off64, offsets, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(G.ev0, st));
+  int k = launch_merkle_leaves_var(G.d_bytes, G.d_off64, n, G.d_dig[0], st);
+  G.launches += k; G.stats.kernel_launches += k; G.stats.merkle_leaves += n;
+  int cur = fold_levels(n, 1, 0, st);
+  CU(cudaEventRecord(G.ev1, st));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_root, G.d_dig[cur], 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_merkle_ms = ms;
+  return CG_OK;
+}
+
+int cg_merkle_root_fixed(const uint8_t* bytes, uint64_t leaf_len, uint64_t n, uint8_t out_root[32]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!out_root) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return empty_root(out_root);
+  size_t total = (size_t)leaf_len * n; int rc;
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)n * 8))) return rc;
+  if ((rc = grow(&G.d_dig[1], &G.cap_dig[1], (size_t)(n + 1) / 2 * 8 + 8))) return rc;
+  cudaStream_t st = G.stream;
+  if (total) CU(cudaMemcpyAsync(G.d_bytes, bytes, total, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(G.ev0, st));
+  int k = launch_merkle_leaves_fixed(G.d_bytes, leaf_len, n, G.d_dig[0], st);
+  G.launches += k; G.stats.kernel_launches += k; G.stats.merkle_leaves += n;
+  int cur = fold_levels(n, 1, 0, st);
+  CU(cudaEventRecord(G.ev1, st));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_root, G.d_dig[cur], 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_merkle_ms = ms;
+  return CG_OK;
+}
+
+int cg_merkle_block_roots_device(const void* d_bytes, uint64_t leaf_len, uint64_t n, uint32_t block_log2, void* d_out_roots, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!n) return CG_OK;
+  if (!d_bytes || !d_out_roots) return fail(CG_ERR_INVALID_ARG, "null argument");
+  int rc;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)n * 8))) return rc;
+  if ((rc = grow(&G.d_dig[1], &G.cap_dig[1], (size_t)(n + 1) / 2 * 8 + 8))) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+  int k = launch_merkle_leaves_fixed((const uint8_t*)d_bytes, leaf_len, n, G.d_dig[0], st);
+  G.launches += k; G.stats.kernel_launches += k; G.stats.merkle_leaves += n;
+  int cur = fold_levels(n, 1, 0, st, block_log2);
+  uint64_t nblocks = (n + ((1ull << block_log2) - 1)) >> block_log2;
+  CU(cudaMemcpyAsync(d_out_roots, G.d_dig[cur], nblocks * 32, cudaMemcpyDeviceToDevice, st));
+  CU(cudaGetLastError());
+  return CG_OK;
+}
+
+int cg_merkle_fold_device(const void* d_nodes32, uint64_t m, void* d_out_root32, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!m || !d_nodes32 || !d_out_root32) return fail(CG_ERR_INVALID_ARG, "null or empty input");
+  int rc;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)m * 8))) return rc;
+  if ((rc = grow(&G.d_dig[1], &G.cap_dig[1], (size_t)(m + 1) / 2 * 8 + 8))) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+  CU(cudaMemcpyAsync(G.d_dig[0], d_nodes32, m * 32, cudaMemcpyDeviceToDevice, st));
+  int cur = fold_levels(m, 1, 0, st);
+  CU(cudaMemcpyAsync(d_out_root32, G.d_dig[cur], 32, cudaMemcpyDeviceToDevice, st));
+  CU(cudaGetLastError());
+  return CG_OK;
+}
+
+int cg_merkle_fold(const uint8_t* nodes32, uint64_t m, uint8_t out_root[32]) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+    if (!out_root) return fail(CG_ERR_INVALID_ARG, "null argument");
+    if (m == 0) return empty_root(out_root);
+    if (!nodes32) return fail(CG_ERR_INVALID_ARG, "null argument");
+    int rc;
+    if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)m * 8))) return rc;
+    if ((rc = grow(&G.d_dig[1], &G.cap_dig[1], (size_t)(m + 1) / 2 * 8 + 8))) return rc;
+    cudaStream_t st = G.stream;
+    CU(cudaMemcpyAsync(G.d_dig[0], nodes32, m * 32, cudaMemcpyHostToDevice, st));
+    int cur = fold_levels(m, 1, 0, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_root, G.d_dig[cur], 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return CG_OK;
+}
+
+}  // extern "C"

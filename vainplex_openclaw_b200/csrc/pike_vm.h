@@ -1,0 +1,213 @@
+// pike_vm.h -- the exact matcher: a Pike VM over UTF-16 code units decoded on the fly from UTF-8.
+//
+// ECMAScript leftmost-first semantics (ECMA-262 22.2.2) for the supported subset: priority-ordered
+// thread list, closure with per-step visited marks (which is exactly the spec's empty-check for
+// `*` loops), MATCH cuts every lower-priority thread.  The global-exec iteration of
+// gov/src/redaction/registry.ts:225-236 and RegExp.test of gov/src/conditions/context.ts:9-25 are
+// built on vm.search().  The functions are CG_HD so that tests/native/vm_harness.cpp can run the
+// *same code* on the host against the oracle; the product only ever calls them from verify_kernel.
+#pragma once
+#include <cstdint>
+#include "kernels.h"
+#include "rulec.h"
+
+#ifdef __CUDACC__
+#define CG_HD __host__ __device__ __forceinline__
+#define CG_HD_NOINLINE __host__ __device__
+#else
+#define CG_HD inline
+#define CG_HD_NOINLINE inline
+#endif
+
+namespace cg {
+
+struct Cursor { uint32_t pos; uint32_t pending; };   // pending = low surrogate still to deliver (0 = none)
+
+// WHATWG UTF-8 decode of one UTF-16 unit at the cursor; returns -1 at end of message.
+CG_HD int next_unit(const uint8_t* __restrict__ m, uint32_t len, Cursor& c) {
+  if (c.pending) { int u = (int)c.pending; c.pending = 0; c.pos += 2; return u; }
+  if (c.pos >= len) return -1;
+  uint32_t b0 = m[c.pos];
+  if (b0 < 0x80) { c.pos += 1; return (int)b0; }
+  uint32_t need, cp, lo = 0x80, hi = 0xbf;
+  if (b0 >= 0xc2 && b0 <= 0xdf) { need = 1; cp = b0 & 0x1f; }
+  else if (b0 >= 0xe0 && b0 <= 0xef) { need = 2; cp = b0 & 0x0f; if (b0 == 0xe0) lo = 0xa0; if (b0 == 0xed) hi = 0x9f; }
+  else if (b0 >= 0xf0 && b0 <= 0xf4) { need = 3; cp = b0 & 0x07; if (b0 == 0xf0) lo = 0x90; if (b0 == 0xf4) hi = 0x8f; }
+  else { c.pos += 1; return 0xfffd; }
+  uint32_t j = c.pos + 1;
+  for (uint32_t t = 0; t < need; t++, j++) {
+    if (j >= len) { c.pos = j; return 0xfffd; }
+    uint32_t bj = m[j];
+    if (bj < lo || bj > hi) { c.pos = (j > c.pos + 1) ? j : c.pos + 1; return 0xfffd; }
+    cp = (cp << 6) | (bj & 0x3f); lo = 0x80; hi = 0xbf;
+  }
+  if (cp >= 0x10000) {   // astral: deliver the high surrogate now (2 bytes), the low one next
+    cp -= 0x10000; c.pending = 0xdc00 + (cp & 0x3ff); c.pos += 2; return (int)(0xd800 + (cp >> 10));
+  }
+  c.pos = j; return (int)cp;
+}
+
+CG_HD bool in_set(const DevRuleset& rs, uint32_t sid, int u) {
+  if (u < 0) return false;
+  const uint32_t* s = rs.sets + (size_t)sid * 6;
+  if (u < 128) return (s[u >> 5] >> (u & 31)) & 1u;
+  const uint16_t* r = rs.set_ranges + s[4];
+  for (uint32_t k = 0; k < s[5]; k++) if ((uint32_t)u >= r[2 * k] && (uint32_t)u <= r[2 * k + 1]) return true;
+  return false;
+}
+CG_HD bool is_word(int u) { return (u >= '0' && u <= '9') || (u >= 'A' && u <= 'Z') || u == '_' || (u >= 'a' && u <= 'z'); }
+
+constexpr int kVmStack = 192;
+
+struct VM {
+  const DevRuleset& rs; const uint32_t* prog; uint32_t plen;
+  uint16_t mark[kMaxProgLen]; uint16_t gen;
+  uint16_t pcs[2][kMaxProgLen]; uint32_t sts[2][kMaxProgLen]; uint32_t cnt[2];
+  uint16_t stk[kVmStack];
+  uint32_t err;
+  // best match of the current search
+  bool matched; uint32_t m_start, m_end, m_end16; int m_prev;
+
+  CG_HD_NOINLINE VM(const DevRuleset& r) : rs(r), gen(0), err(0) {}
+
+  CG_HD_NOINLINE void bump_gen() { if (++gen >= 0x7fff) { for (uint32_t k = 0; k < plen; k++) mark[k] = 0; gen = 1; } }
+
+  // Closure from pc0 at a position whose context is (prev, next, byte `pos`, unit index `upos`):
+  // a depth-first walk in priority order.  SPLIT nodes carry a per-step mark that is IN-PROGRESS
+  // while their lower-priority alternative is still pending and DONE afterwards; consuming
+  // instructions are marked DONE when their thread is queued.  Arriving at a DONE node is a
+  // duplicate of a higher-priority path and is dropped.  A loop back-edge (JMP_BACK / EMPTYCHK)
+  // that finds its own SPLIT in progress at this very position closes an iteration that consumed
+  // nothing -- RepeatMatcher's empty check (ECMA-262 22.2.2.3.1 step 2.b) -- and dies, while a
+  // *fresh* entry into an in-progress SPLIT (an inner loop re-entered by a new outer iteration) is
+  // explored again at its higher priority.  Returns true when MATCH was reached (the caller must
+  // then cut every lower-priority thread).
+  CG_HD_NOINLINE bool add(int L, uint32_t pc0, uint32_t start, int prev, int next, uint32_t pos, uint32_t upos) {
+    const uint16_t INPROG = (uint16_t)(gen * 2), DONE = (uint16_t)(gen * 2 + 1);
+    int sp = 0; stk[sp++] = (uint16_t)pc0;
+    while (sp) {
+      uint32_t x = stk[--sp];
+      if (x & 0x8000u) { mark[x & 0x7fffu] = DONE; continue; }
+      uint32_t pc = x;
+      for (;;) {
+        uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
+        bool go = false;
+        switch (op) {
+          case OP_SPLIT_NEXT: case OP_SPLIT_JUMP:
+            if (mark[pc] == DONE) break;
+            mark[pc] = INPROG;
+            if (sp + 2 <= kVmStack) { stk[sp++] = (uint16_t)(0x8000u | pc); stk[sp++] = (uint16_t)(op == OP_SPLIT_NEXT ? arg : pc + 1); }
+            else err |= ERR_VM_STACK;
+            pc = op == OP_SPLIT_NEXT ? pc + 1 : arg; go = true; break;
+          case OP_JMP: pc = arg; go = true; break;
+          case OP_JMP_BACK: if (mark[arg] != INPROG) { pc = arg; go = true; } break;
+          case OP_EMPTYCHK: if (mark[arg] != INPROG) { pc++; go = true; } break;
+          case OP_BOL: if (pos == 0) { pc++; go = true; } break;
+          case OP_EOL: if (next < 0) { pc++; go = true; } break;
+          case OP_WORDB: if (is_word(prev) != is_word(next)) { pc++; go = true; } break;
+          case OP_NWORDB: if (is_word(prev) == is_word(next)) { pc++; go = true; } break;
+          case OP_LOOKAHEAD: if (in_set(rs, arg, next)) { pc++; go = true; } break;
+          case OP_NLOOKAHEAD: if (!in_set(rs, arg, next)) { pc++; go = true; } break;
+          case OP_LOOKBEHIND: if (in_set(rs, arg, prev)) { pc++; go = true; } break;
+          case OP_NLOOKBEHIND: if (!in_set(rs, arg, prev)) { pc++; go = true; } break;
+          case OP_MATCH:
+            matched = true; m_start = start; m_end = pos; m_end16 = upos; m_prev = prev;
+            return true;
+          default:   // consuming instruction: queue the thread once per step
+            if (mark[pc] != DONE) {
+              mark[pc] = DONE;
+              uint32_t k = cnt[L];
+              if (k < kMaxProgLen) { pcs[L][k] = (uint16_t)pc; sts[L][k] = start; cnt[L] = k + 1; } else err |= ERR_VM_LIST;
+            }
+            break;
+        }
+        if (!go) break;
+      }
+    }
+    return false;
+  }
+
+  // One leftmost-first search starting at byte `from` (unit index from16, unit before it `prev`).
+  CG_HD_NOINLINE bool search(const uint8_t* __restrict__ m, uint32_t len, uint32_t from, uint32_t from16, int prev,
+                         const uint32_t* __restrict__ first, Cursor cur_c) {
+    matched = false;
+    Cursor c = cur_c;                 // cursor sits at `from`
+    uint32_t pos = from, upos = from16;
+    Cursor cn = c; int cur = next_unit(m, len, cn);      // unit at pos ; cn = cursor after it
+    int L = 0; cnt[0] = 0; bump_gen();
+    add(L, 0, pos, prev, cur, pos, upos);
+    for (;;) {
+      if (cnt[L] == 0) {
+        if (matched || cur < 0) break;
+        // Nothing alive and the start at `pos` has already failed: move on, skipping ASCII units
+        // that cannot begin a match (first-unit filter; nullable rules have an all-ones filter).
+        do { prev = cur; pos = cn.pos; upos++; c = cn; cur = next_unit(m, len, cn); }
+        while (cur >= 0 && cur < 128 && !((first[cur >> 5] >> (cur & 31)) & 1u));
+        bump_gen();
+        add(L, 0, pos, prev, cur, pos, upos);
+        continue;
+      }
+      if (cur < 0) break;
+      Cursor cnn = cn; int nxt = next_unit(m, len, cnn);  // unit after cur
+      int N = L ^ 1; cnt[N] = 0; bump_gen();
+      uint32_t npos = cn.pos, nupos = upos + 1;
+      bool cut = false;
+      for (uint32_t k = 0; k < cnt[L] && !cut; k++) {
+        uint32_t pc = pcs[L][k]; uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
+        bool ok = op == OP_CHAR ? ((uint32_t)cur == arg)
+                : op == OP_ANY ? !(cur == 0x0a || cur == 0x0d || cur == 0x2028 || cur == 0x2029)
+                : in_set(rs, arg, cur);
+        if (ok) cut = add(N, pc + 1, sts[L][k], cur, nxt, npos, nupos);
+      }
+      if (!cut && !matched) add(N, 0, npos, cur, nxt, npos, nupos);   // new lowest-priority start
+      L = N; prev = cur; pos = npos; upos = nupos; c = cn; cn = cnn; cur = nxt;
+    }
+    return matched;
+  }
+};
+
+// number of UTF-16 units in m[0, upto)
+CG_HD_NOINLINE uint32_t count_units(const uint8_t* __restrict__ m, uint32_t len, uint32_t upto) {
+  Cursor c{0, 0}; uint32_t k = 0;
+  while (c.pos < upto) { if (next_unit(m, len, c) < 0) break; k++; }
+  return k;
+}
+// cursor positioned at byte `at` (a unit boundary, possibly the middle of a 4-byte sequence)
+CG_HD_NOINLINE Cursor cursor_at(const uint8_t* __restrict__ m, uint32_t len, uint32_t at) {
+  uint32_t q = at; int back = 0;
+  while (q > 0 && back < 3 && q < len && (m[q] & 0xc0) == 0x80) { q--; back++; }
+  Cursor c{q, 0};
+  while (c.pos < at) { Cursor t = c; if (next_unit(m, len, t) < 0) break; if (t.pos > at) break; c = t; }
+  if (c.pos != at) { c.pos = at; c.pending = 0; }
+  return c;
+}
+
+
+// All matches of one rule in one message -- the exec loop of registry.ts:225-236 (SPANS) or just
+// RegExp.test (context.ts:9-25, !SPANS).  sink.span(start_byte, end_byte, start16, end16).
+template <bool SPANS, class Sink>
+CG_HD_NOINLINE bool run_rule(VM& vm, const DevRuleset& rs, uint32_t rule, const uint8_t* __restrict__ m, uint32_t len, Sink& sink) {
+  vm.prog = rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
+  if (vm.plen == 0) return false;                     // rule failed to compile: never matches
+  for (uint32_t k = 0; k < vm.plen; k++) vm.mark[k] = 0;
+  vm.gen = 0;
+  const uint32_t* first = rs.rule_first + (size_t)rule * 8;
+  uint32_t from = 0, from16 = 0; int prev = -1; Cursor c{0, 0};
+  bool any = false;
+  for (;;) {
+    if (!vm.search(m, len, from, from16, prev, first, c)) break;
+    any = true;
+    if (!SPANS) break;
+    sink.span(vm.m_start, vm.m_end, count_units(m, len, vm.m_start), vm.m_end16);
+    // lastIndex = end; after an empty match advance one code unit
+    from = vm.m_end; from16 = vm.m_end16; prev = vm.m_prev; c = cursor_at(m, len, from);
+    if (vm.m_end == vm.m_start) {
+      Cursor t = c; int u = next_unit(m, len, t);
+      if (u < 0) break;
+      prev = u; from = t.pos; from16++; c = t;
+    }
+  }
+  return any;
+}
+
+}  // namespace cg

@@ -1,0 +1,746 @@
+// rulec.cpp -- JS RegExp (non-unicode mode, Annex B) -> unit-level Pike program + necessary factors.
+// See rulec.h.  Independent of oracle/jsre.c (different data structures and matching model);
+// the two only share the language definition, ECMA-262 22.2.
+#include "rulec.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <set>
+
+namespace cg {
+namespace {
+
+constexpr int INF = 0x7fffffff;
+
+enum NType { T_EMPTY, T_CHAR, T_ANY, T_SET, T_CAT, T_ALT, T_GROUP, T_REPEAT, T_BOL, T_EOL, T_WORDB, T_NWORDB, T_LOOK };
+
+using Ranges = std::vector<std::pair<int, int>>;  // inclusive, over code units 0..0xffff
+
+struct Node {
+  int type = T_EMPTY;
+  int ch = 0;
+  Ranges set;          // T_SET (normalised, positive)
+  std::vector<int> kids;
+  int min = 0, max = 0;
+  bool greedy = true, neg = false, behind = false;
+};
+
+struct Fail { int status; std::string msg; };
+
+static void normalise(Ranges& r) {
+  std::sort(r.begin(), r.end());
+  Ranges o;
+  for (auto& p : r) {
+    if (!o.empty() && p.first <= o.back().second + 1) o.back().second = std::max(o.back().second, p.second);
+    else o.push_back(p);
+  }
+  r.swap(o);
+}
+static Ranges negate(const Ranges& r) {
+  Ranges o; int lo = 0;
+  for (auto& p : r) { if (p.first > lo) o.push_back({lo, p.first - 1}); lo = p.second + 1; }
+  if (lo <= 0xffff) o.push_back({lo, 0xffff});
+  return o;
+}
+static void add_case_closure(Ranges& r) {   // ASCII letters only (flag i)
+  Ranges extra;
+  for (auto& p : r) {
+    int lo = std::max(p.first, (int)'a'), hi = std::min(p.second, (int)'z');
+    if (lo <= hi) extra.push_back({lo - 32, hi - 32});
+    lo = std::max(p.first, (int)'A'); hi = std::min(p.second, (int)'Z');
+    if (lo <= hi) extra.push_back({lo + 32, hi + 32});
+  }
+  r.insert(r.end(), extra.begin(), extra.end());
+  normalise(r);
+}
+
+static const Ranges kDigit = {{'0', '9'}};
+static const Ranges kWord = {{'0', '9'}, {'A', 'Z'}, {'_', '_'}, {'a', 'z'}};
+static const Ranges kSpace = {{0x09, 0x0d}, {0x20, 0x20}, {0xa0, 0xa0}, {0x1680, 0x1680}, {0x2000, 0x200a},
+                              {0x2028, 0x2029}, {0x202f, 0x202f}, {0x205f, 0x205f}, {0x3000, 0x3000}, {0xfeff, 0xfeff}};
+
+struct Parser {
+  std::vector<uint16_t> p;
+  size_t i = 0;
+  bool icase = false;
+  std::vector<Node> nodes;
+  int total_groups = 0;
+  bool has_named = false;
+  bool explicit_nonascii = false;
+
+  int mk(int type) { nodes.emplace_back(); nodes.back().type = type; return (int)nodes.size() - 1; }
+  int peek(size_t k = 0) const { return i + k < p.size() ? p[i + k] : -1; }
+  [[noreturn]] void syntax(const std::string& m) { throw Fail{RULE_ERR_SYNTAX, m}; }
+  [[noreturn]] void unsupported(const std::string& m) { throw Fail{RULE_ERR_UNSUPPORTED, m}; }
+
+  static bool isdig(int c) { return c >= '0' && c <= '9'; }
+  static int hexv(int c) {
+    if (c >= '0' && c <= '9') return c - '0';
+    if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+    return -1;
+  }
+
+  void prescan() {
+    bool in_class = false;
+    for (size_t k = 0; k < p.size(); k++) {
+      int c = p[k];
+      if (c == '\\') { k++; continue; }
+      if (in_class) { if (c == ']') in_class = false; continue; }
+      if (c == '[') { in_class = true; continue; }
+      if (c == '(') {
+        if (k + 1 < p.size() && p[k + 1] == '?') {
+          if (k + 3 < p.size() && p[k + 2] == '<' && p[k + 3] != '=' && p[k + 3] != '!') { total_groups++; has_named = true; }
+        } else total_groups++;
+      }
+    }
+  }
+
+  // body of a character escape after '\' ; returns code unit
+  int char_escape(bool in_class) {
+    int c = peek();
+    if (c < 0) syntax("\\ at end of pattern");
+    i++;
+    switch (c) {
+      case 't': return 0x09; case 'n': return 0x0a; case 'v': return 0x0b; case 'f': return 0x0c; case 'r': return 0x0d;
+      case 'b': if (in_class) return 0x08; break;
+      case '0': if (!isdig(peek())) return 0; break;
+      case 'c': {
+        int l = peek();
+        if ((l >= 'a' && l <= 'z') || (l >= 'A' && l <= 'Z')) { i++; return l % 32; }
+        if (in_class && (isdig(l) || l == '_')) { i++; return l % 32; }
+        i--; return '\\';
+      }
+      case 'x': { int a = hexv(peek()), b = hexv(peek(1)); if (a >= 0 && b >= 0) { i += 2; return a * 16 + b; } return 'x'; }
+      case 'u': {
+        int v = 0; bool ok = true;
+        for (int k = 0; k < 4; k++) { int h = hexv(peek(k)); if (h < 0) { ok = false; break; } v = v * 16 + h; }
+        if (ok) { i += 4; return v; }
+        return 'u';
+      }
+      case 'k': if (has_named) unsupported("named backreference"); break;
+    }
+    if (c >= '0' && c <= '7') {
+      int v = c - '0'; int d = peek();
+      if (d >= '0' && d <= '7') { v = v * 8 + (d - '0'); i++; d = peek(); if (c <= '3' && d >= '0' && d <= '7') { v = v * 8 + (d - '0'); i++; } }
+      return v;
+    }
+    return c;
+  }
+
+  static const Ranges* class_escape(int c, bool* inv) {
+    *inv = (c == 'D' || c == 'W' || c == 'S');
+    switch (c) { case 'd': case 'D': return &kDigit; case 'w': case 'W': return &kWord; case 's': case 'S': return &kSpace; }
+    return nullptr;
+  }
+  static void add_set(Ranges& r, const Ranges& s, bool inv) {
+    if (!inv) { r.insert(r.end(), s.begin(), s.end()); return; }
+    Ranges n = negate(s); r.insert(r.end(), n.begin(), n.end());
+  }
+
+  int finish_set(Ranges r, bool neg) {
+    normalise(r);
+    if (icase) add_case_closure(r);
+    if (neg) r = negate(r);
+    int n = mk(T_SET); nodes[n].set = r; return n;
+  }
+
+  int parse_class() {
+    bool neg = false; Ranges r;
+    if (peek() == '^') { neg = true; i++; }
+    for (;;) {
+      int c = peek();
+      if (c < 0) syntax("unterminated character class");
+      if (c == ']') { i++; break; }
+      i++;
+      int lo = -1; bool lo_set = false;
+      if (c == '\\') {
+        bool inv; const Ranges* s = class_escape(peek(), &inv);
+        if (s) { i++; add_set(r, *s, inv); lo_set = true; } else lo = char_escape(true);
+      } else lo = c;
+      if (peek() == '-' && peek(1) != ']' && peek(1) >= 0) {
+        i++;
+        int c2 = peek(); i++;
+        int hi = -1;
+        if (c2 == '\\') {
+          bool inv; const Ranges* s = class_escape(peek(), &inv);
+          if (s) { i++; if (!lo_set) { r.push_back({lo, lo}); if (lo >= 128) explicit_nonascii = true; } r.push_back({'-', '-'}); add_set(r, *s, inv); continue; }
+          hi = char_escape(true);
+        } else hi = c2;
+        if (lo_set) { r.push_back({'-', '-'}); r.push_back({hi, hi}); if (hi >= 128) explicit_nonascii = true; continue; }
+        if (hi < lo) syntax("range out of order in character class");
+        r.push_back({lo, hi});
+        if (hi >= 128) explicit_nonascii = true;
+        continue;
+      }
+      if (!lo_set) { r.push_back({lo, lo}); if (lo >= 128) explicit_nonascii = true; }
+    }
+    return finish_set(r, neg);
+  }
+
+  bool braces(int* mn, int* mx) {
+    size_t j = i;
+    if (j >= p.size() || p[j] != '{') return false;
+    j++;
+    if (j >= p.size() || !isdig(p[j])) return false;
+    long a = 0; while (j < p.size() && isdig(p[j])) { a = std::min(a * 10 + (p[j] - '0'), (long)INF); j++; }
+    long b = a;
+    if (j < p.size() && p[j] == ',') {
+      j++;
+      if (j < p.size() && isdig(p[j])) { b = 0; while (j < p.size() && isdig(p[j])) { b = std::min(b * 10 + (p[j] - '0'), (long)INF); j++; } }
+      else b = INF;
+    }
+    if (j >= p.size() || p[j] != '}') return false;
+    i = j + 1; *mn = (int)a; *mx = (int)b; return true;
+  }
+
+  int mkchar(int c) {
+    if (c >= 128) explicit_nonascii = true;
+    if (icase && ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))) return finish_set({{c, c}}, false);
+    int n = mk(T_CHAR); nodes[n].ch = c; return n;
+  }
+
+  int atom_escape(bool* is_assert) {
+    int c = peek();
+    bool inv; const Ranges* s = class_escape(c, &inv);
+    if (s) { i++; Ranges r; add_set(r, *s, inv); return finish_set(r, false); }
+    if (c == 'b') { i++; *is_assert = true; return mk(T_WORDB); }
+    if (c == 'B') { i++; *is_assert = true; return mk(T_NWORDB); }
+    if (c >= '1' && c <= '9') {
+      size_t j = i; long v = 0;
+      while (j < p.size() && isdig(p[j])) { v = std::min(v * 10 + (p[j] - '0'), 100000L); j++; }
+      if (v <= total_groups) unsupported("backreference");
+      if (c >= '8') { i++; return mkchar(c); }
+    }
+    return mkchar(char_escape(false));
+  }
+
+  int parse_disjunction();
+
+  int parse_term(bool* is_assert) {
+    *is_assert = false;
+    int c = peek(); i++;
+    switch (c) {
+      case '^': *is_assert = true; return mk(T_BOL);
+      case '$': *is_assert = true; return mk(T_EOL);
+      case '.': return mk(T_ANY);
+      case '[': return parse_class();
+      case '\\': return atom_escape(is_assert);
+      case '(': {
+        int atom;
+        if (peek() == '?') {
+          int d = peek(1);
+          if (d == ':') { i += 2; atom = mk(T_GROUP); int k = parse_disjunction(); nodes[atom].kids.push_back(k); }
+          else if (d == '=' || d == '!') {
+            i += 2; atom = mk(T_LOOK); nodes[atom].neg = (d == '!'); nodes[atom].behind = false;
+            int k = parse_disjunction(); nodes[atom].kids.push_back(k);
+          } else if (d == '<' && (peek(2) == '=' || peek(2) == '!')) {
+            bool neg = peek(2) == '!'; i += 3; atom = mk(T_LOOK); nodes[atom].neg = neg; nodes[atom].behind = true;
+            int k = parse_disjunction(); nodes[atom].kids.push_back(k);
+            *is_assert = true;
+          } else if (d == '<') {
+            i += 2; while (peek() >= 0 && peek() != '>') i++;
+            if (peek() != '>') syntax("invalid capture group name");
+            i++; atom = mk(T_GROUP); int k = parse_disjunction(); nodes[atom].kids.push_back(k);
+          } else syntax("invalid group");
+        } else { atom = mk(T_GROUP); int k = parse_disjunction(); nodes[atom].kids.push_back(k); }
+        if (peek() != ')') syntax("unterminated group");
+        i++;
+        return atom;
+      }
+      case '*': case '+': case '?': syntax("nothing to repeat");
+      case '{': { i--; int a, b; size_t sv = i; if (braces(&a, &b)) { i = sv; syntax("nothing to repeat"); } i++; return mkchar('{'); }
+      default: return mkchar(c);
+    }
+  }
+
+  int parse_alternative() {
+    int seq = mk(T_CAT);
+    for (;;) {
+      int c = peek();
+      if (c < 0 || c == '|' || c == ')') break;
+      bool is_assert = false;
+      int t = parse_term(&is_assert);
+      if (!is_assert) {
+        int mn = -1, mx = -1; int q = peek();
+        if (q == '*') { mn = 0; mx = INF; i++; } else if (q == '+') { mn = 1; mx = INF; i++; }
+        else if (q == '?') { mn = 0; mx = 1; i++; } else if (q == '{') { if (!braces(&mn, &mx)) mn = -1; }
+        if (mn >= 0) {
+          if (mx < mn) syntax("numbers out of order in {} quantifier");
+          if (nodes[t].type == T_LOOK) unsupported("quantified lookahead");
+          int r = mk(T_REPEAT); nodes[r].min = mn; nodes[r].max = mx; nodes[r].greedy = true;
+          if (peek() == '?') { nodes[r].greedy = false; i++; }
+          nodes[r].kids.push_back(t); t = r;
+          int q2 = peek();
+          if (q2 == '*' || q2 == '+' || q2 == '?') syntax("nothing to repeat");
+          int a, b; size_t sv = i; if (q2 == '{' && braces(&a, &b)) { i = sv; syntax("nothing to repeat"); }
+        }
+      }
+      nodes[seq].kids.push_back(t);
+    }
+    return seq;
+  }
+};
+
+int Parser::parse_disjunction() {
+  int first = parse_alternative();
+  if (peek() != '|') return first;
+  int alt = mk(T_ALT); nodes[alt].kids.push_back(first);
+  while (peek() == '|') { i++; int k = parse_alternative(); nodes[alt].kids.push_back(k); }
+  return alt;
+}
+
+// ------------------------------------------------------------------ analysis + emission
+
+struct Compiler {
+  Parser& ps;
+  CompiledRule& out;
+  explicit Compiler(Parser& p, CompiledRule& o) : ps(p), out(o) {}
+  const Node& N(int n) const { return ps.nodes[n]; }
+
+  bool nullable(int n) const {
+    const Node& nd = N(n);
+    switch (nd.type) {
+      case T_CHAR: case T_ANY: case T_SET: return false;
+      case T_CAT: for (int k : nd.kids) if (!nullable(k)) return false; return true;
+      case T_ALT: for (int k : nd.kids) if (nullable(k)) return true; return false;
+      case T_GROUP: return nullable(nd.kids[0]);
+      case T_REPEAT: return nd.min == 0 || nullable(nd.kids[0]);
+      default: return true;
+    }
+  }
+
+  void check_supported(int n) {
+    const Node& nd = N(n);
+    if (nd.type == T_LOOK) {
+      int k = nd.kids[0];
+      for (;;) {
+        const Node& kn = N(k);
+        if ((kn.type == T_GROUP || kn.type == T_CAT || kn.type == T_ALT) && kn.kids.size() == 1) { k = kn.kids[0]; continue; }
+        break;
+      }
+      int t = N(k).type;
+      if (t != T_CHAR && t != T_SET && t != T_ANY) throw Fail{RULE_ERR_UNSUPPORTED, "lookaround over more than one character"};
+    }
+    for (int k : nd.kids) check_supported(k);
+  }
+
+  static Ranges any_set() { return negate({{0x0a, 0x0a}, {0x0d, 0x0d}, {0x2028, 0x2029}}); }
+  Ranges unit_ranges(int n) const {
+    const Node& nd = N(n);
+    if (nd.type == T_CHAR) return {{nd.ch, nd.ch}};
+    if (nd.type == T_ANY) return any_set();
+    return nd.set;
+  }
+
+  int set_id(const Ranges& r) {
+    UnitSet s; memset(s.ascii, 0, sizeof s.ascii);
+    for (auto& p : r) {
+      for (int c = p.first; c <= std::min(p.second, 127); c++) s.ascii[c >> 5] |= 1u << (c & 31);
+      if (p.second >= 128) { s.ranges.push_back((uint16_t)std::max(p.first, 128)); s.ranges.push_back((uint16_t)p.second); }
+    }
+    for (size_t k = 0; k < out.sets.size(); k++) if (out.sets[k] == s) return (int)k;
+    out.sets.push_back(s);
+    return (int)out.sets.size() - 1;
+  }
+
+  void emit(uint32_t op, uint32_t arg = 0) {
+    if ((int)out.prog.size() >= kMaxProgLen) throw Fail{RULE_ERR_TOO_LARGE, "pattern expands to more than 1024 matcher instructions"};
+    out.prog.push_back(op | (arg << 8));
+  }
+  void patch(size_t at, uint32_t arg) { out.prog[at] = (out.prog[at] & 0xff) | (arg << 8); }
+
+  void gen(int n) {
+    const Node& nd = N(n);
+    switch (nd.type) {
+      case T_EMPTY: return;
+      case T_CHAR: emit(OP_CHAR, (uint32_t)nd.ch); return;
+      case T_ANY: emit(OP_ANY); return;
+      case T_SET: {
+        if (nd.set.size() == 1 && nd.set[0].first == nd.set[0].second) { emit(OP_CHAR, (uint32_t)nd.set[0].first); return; }
+        emit(OP_SET, (uint32_t)set_id(nd.set)); return;
+      }
+      case T_CAT: for (int k : nd.kids) gen(k); return;
+      case T_GROUP: gen(nd.kids[0]); return;
+      case T_ALT: {
+        std::vector<size_t> jumps;
+        for (size_t a = 0; a < nd.kids.size(); a++) {
+          if (a + 1 < nd.kids.size()) {
+            size_t sp = out.prog.size(); emit(OP_SPLIT_NEXT, 0);
+            gen(nd.kids[a]);
+            jumps.push_back(out.prog.size()); emit(OP_JMP, 0);
+            patch(sp, (uint32_t)out.prog.size());
+          } else gen(nd.kids[a]);
+        }
+        for (size_t j : jumps) patch(j, (uint32_t)out.prog.size());
+        return;
+      }
+      case T_REPEAT: {
+        int body = nd.kids[0];
+        for (int c = 0; c < nd.min; c++) gen(body);
+        if (nd.max == INF) {
+          size_t L = out.prog.size();
+          emit(nd.greedy ? OP_SPLIT_NEXT : OP_SPLIT_JUMP, 0);
+          gen(body);
+          emit(OP_JMP_BACK, (uint32_t)L);
+          patch(L, (uint32_t)out.prog.size());
+        } else {
+          // optional iterations: RepeatMatcher's empty check (22.2.2.3.1 step 2.b) rejects an
+          // iteration that consumed nothing; EMPTYCHK tests the visited mark of this iteration's SPLIT.
+          std::vector<size_t> splits; bool nb = nullable(body);
+          for (int c = nd.min; c < nd.max; c++) {
+            splits.push_back(out.prog.size()); emit(nd.greedy ? OP_SPLIT_NEXT : OP_SPLIT_JUMP, 0);
+            gen(body);
+            if (nb) emit(OP_EMPTYCHK, (uint32_t)splits.back());
+          }
+          for (size_t s : splits) patch(s, (uint32_t)out.prog.size());
+        }
+        return;
+      }
+      case T_BOL: emit(OP_BOL); return;
+      case T_EOL: emit(OP_EOL); return;
+      case T_WORDB: emit(OP_WORDB); return;
+      case T_NWORDB: emit(OP_NWORDB); return;
+      case T_LOOK: {
+        int k = nd.kids[0];
+        for (;;) { const Node& kn = N(k); if ((kn.type == T_GROUP || kn.type == T_CAT || kn.type == T_ALT) && kn.kids.size() == 1) { k = kn.kids[0]; continue; } break; }
+        int sid = set_id(unit_ranges(k));
+        uint32_t op = nd.behind ? (nd.neg ? OP_NLOOKBEHIND : OP_LOOKBEHIND) : (nd.neg ? OP_NLOOKAHEAD : OP_LOOKAHEAD);
+        emit(op, (uint32_t)sid); return;
+      }
+    }
+  }
+
+  // FIRST set (units) of a node
+  void first(int n, Ranges& acc) const {
+    const Node& nd = N(n);
+    switch (nd.type) {
+      case T_CHAR: case T_ANY: case T_SET: { Ranges r = unit_ranges(n); acc.insert(acc.end(), r.begin(), r.end()); return; }
+      case T_CAT: for (int k : nd.kids) { first(k, acc); if (!nullable(k)) return; } return;
+      case T_ALT: for (int k : nd.kids) first(k, acc); return;
+      case T_GROUP: case T_REPEAT: first(nd.kids[0], acc); return;
+      default: return;
+    }
+  }
+
+  // ---------------------------------------------------------------- necessary factors
+  struct Info {
+    bool has_exact = false;             // language(node) subset of `exact` (as whole strings)
+    std::vector<FactorSeq> exact;
+    bool is_exact_tight = false;        // `exact` IS the language (no over-approximation, no assertions)
+    bool has_factors = false;           // every match contains one of `factors` as a substring
+    std::vector<FactorSeq> factors;
+  };
+  static constexpr size_t kMaxSeqs = 24;
+  static constexpr size_t kMaxRunLen = 16;
+
+  static double byte_weight(int b) {
+    // coarse frequency model of chat-like UTF-8 text, used only to rank factor candidates
+    if (b == ' ') return 0.15;
+    if (b >= 'a' && b <= 'z') { static const double f[26] = {.065,.012,.022,.034,.10,.018,.016,.049,.056,.001,.006,.032,.019,.054,.060,.015,.001,.048,.051,.072,.022,.008,.019,.001,.016,.001}; return f[b - 'a']; }
+    if (b >= 'A' && b <= 'Z') return 0.002;
+    if (b >= '0' && b <= '9') return 0.004;
+    if (b == '.' || b == ',') return 0.01;
+    if (b >= 0x21 && b <= 0x7e) return 0.0015;
+    if (b == '\n') return 0.003;
+    if (b >= 0x80) return 0.0004;
+    return 0.0001;
+  }
+  static double seq_prob(const FactorSeq& s) {
+    double p = 1.0;
+    for (auto& bs : s) { double q = 0; for (int b = 0; b < 256; b++) if (bs.has(b)) q += byte_weight(b); p *= std::min(q, 1.0); }
+    return p;
+  }
+  static double score(const std::vector<FactorSeq>& f) {
+    double s = 0; for (auto& q : f) { if (q.empty()) return 1.0; s += seq_prob(q); } return std::min(s, 1.0);
+  }
+
+  // byte-level view of one unit node; returns false when the node has non-ASCII members (no byte info)
+  bool unit_bytes(int n, std::vector<FactorSeq>* seqs) const {
+    Ranges r = unit_ranges(n);
+    bool ascii_only = true; for (auto& p : r) if (p.second >= 128) ascii_only = false;
+    if (ascii_only) { ByteSet b; for (auto& p : r) for (int c = p.first; c <= p.second; c++) b.set(c); if (b.empty()) return false; seqs->push_back({b}); return true; }
+    if (r.size() == 1 && r[0].first == r[0].second) {      // single non-ASCII literal: its UTF-8 bytes
+      int c = r[0].first;
+      if (c >= 0xd800 && c <= 0xdfff) return false;
+      FactorSeq s; ByteSet b0, b1, b2;
+      if (c < 0x800) { b0.set(0xc0 | (c >> 6)); b1.set(0x80 | (c & 0x3f)); s = {b0, b1}; }
+      else { b0.set(0xe0 | (c >> 12)); b1.set(0x80 | ((c >> 6) & 0x3f)); b2.set(0x80 | (c & 0x3f)); s = {b0, b1, b2}; }
+      seqs->push_back(s); return true;
+    }
+    return false;
+  }
+
+  static void consider(std::vector<FactorSeq>& best, bool& have, const std::vector<FactorSeq>& cand) {
+    if (cand.empty()) return;
+    for (auto& s : cand) if (s.empty()) return;
+    if (!have || score(cand) < score(best)) { best = cand; have = true; }
+  }
+
+  Info analyse(int n) const {
+    const Node& nd = N(n);
+    Info I;
+    switch (nd.type) {
+      case T_CHAR: case T_ANY: case T_SET: {
+        std::vector<FactorSeq> s;
+        if (unit_bytes(n, &s)) { I.has_exact = true; I.exact = s; I.is_exact_tight = true; I.has_factors = true; I.factors = s; }
+        return I;
+      }
+      case T_EMPTY: I.has_exact = true; I.exact = {FactorSeq{}}; I.is_exact_tight = true; return I;
+      case T_BOL: case T_EOL: case T_WORDB: case T_NWORDB: case T_LOOK:
+        I.has_exact = true; I.exact = {FactorSeq{}}; I.is_exact_tight = false; return I;
+      case T_GROUP: return analyse(nd.kids[0]);
+      case T_ALT: {
+        bool all_exact = true, all_fact = true, tight = true; std::vector<FactorSeq> ex, fa;
+        for (int k : nd.kids) {
+          Info c = analyse(k);
+          if (c.has_exact) ex.insert(ex.end(), c.exact.begin(), c.exact.end()); else all_exact = false;
+          tight = tight && c.is_exact_tight;
+          if (c.has_factors) fa.insert(fa.end(), c.factors.begin(), c.factors.end()); else all_fact = false;
+        }
+        if (all_exact && ex.size() <= kMaxSeqs) { I.has_exact = true; I.exact = ex; I.is_exact_tight = tight; }
+        if (all_fact && fa.size() <= 4 * kMaxSeqs) { I.has_factors = true; I.factors = fa; }
+        return I;
+      }
+      case T_REPEAT: {
+        // view X{m,n} as X^m followed by an optional tail (which gives no information)
+        Info b = analyse(nd.kids[0]);
+        if (nd.min == 0) { if (nd.max == 0) { I.has_exact = true; I.exact = {FactorSeq{}}; I.is_exact_tight = true; } return I; }
+        std::vector<FactorSeq> run; bool have = false;
+        if (b.has_exact) {
+          run = {FactorSeq{}};
+          int copies = std::min(nd.min, (int)kMaxRunLen);
+          bool ok = true;
+          for (int c = 0; c < copies && ok; c++) {
+            std::vector<FactorSeq> nx;
+            for (auto& a : run) for (auto& e : b.exact) { FactorSeq s = a; s.insert(s.end(), e.begin(), e.end()); if (s.size() > kMaxRunLen) { ok = false; break; } nx.push_back(s); }
+            if (!ok || nx.size() > kMaxSeqs) { ok = false; break; }
+            run.swap(nx);
+          }
+          if (!run.empty() && !run[0].empty()) {
+            have = true;
+            if (ok && nd.min == nd.max && copies == nd.min) { I.has_exact = true; I.exact = run; I.is_exact_tight = b.is_exact_tight; }
+          }
+        }
+        std::vector<FactorSeq> best; bool hb = false;
+        if (have) consider(best, hb, run);
+        if (b.has_factors) consider(best, hb, b.factors);
+        if (hb) { I.has_factors = true; I.factors = best; }
+        return I;
+      }
+      case T_CAT: {
+        std::vector<FactorSeq> run = {FactorSeq{}}; bool run_tight = true;
+        std::vector<FactorSeq> best; bool hb = false;
+        bool all_exact = true, tight = true;
+        auto close_run = [&]() { bool nonempty = false; for (auto& s : run) if (!s.empty()) nonempty = true; bool allne = true; for (auto& s : run) if (s.empty()) allne = false; if (nonempty && allne) consider(best, hb, run); run = {FactorSeq{}}; };
+        for (int k : nd.kids) {
+          Info c = analyse(k);
+          if (c.has_factors) consider(best, hb, c.factors);
+          // a REPEAT with min>=1 contributes its required prefix to the run and then breaks it
+          const Node& kn = N(k);
+          bool breaks_after = false;
+          std::vector<FactorSeq> piece; bool has_piece = false;
+          if (c.has_exact) { piece = c.exact; has_piece = true; tight = tight && c.is_exact_tight; }
+          else {
+            all_exact = false;
+            int kk = k; while (N(kk).type == T_GROUP) kk = N(kk).kids[0];
+            if (N(kk).type == T_REPEAT && N(kk).min >= 1) {
+              Info b = analyse(N(kk).kids[0]);
+              if (b.has_exact) {
+                piece = {FactorSeq{}}; has_piece = true; breaks_after = true;
+                int copies = std::min(N(kk).min, (int)kMaxRunLen);
+                for (int q = 0; q < copies && has_piece; q++) {
+                  std::vector<FactorSeq> nx;
+                  for (auto& a : piece) for (auto& e : b.exact) { FactorSeq s = a; s.insert(s.end(), e.begin(), e.end()); nx.push_back(s); }
+                  if (nx.size() > kMaxSeqs || (!nx.empty() && nx[0].size() > kMaxRunLen)) { breaks_after = true; break; }
+                  piece.swap(nx);
+                }
+              }
+            }
+            (void)kn;
+          }
+          if (!has_piece) { close_run(); run_tight = false; continue; }
+          // extend the run by the cross product, or restart it when it would grow too much
+          std::vector<FactorSeq> nx; bool ok = true;
+          for (auto& a : run) { for (auto& e : piece) { FactorSeq s = a; s.insert(s.end(), e.begin(), e.end()); if (s.size() > kMaxRunLen) { ok = false; break; } nx.push_back(s); } if (!ok) break; }
+          if (!ok || nx.size() > kMaxSeqs) { all_exact = false; close_run(); run = piece; if (run.size() > kMaxSeqs) run = {FactorSeq{}}; }
+          else run.swap(nx);
+          if (breaks_after) { all_exact = false; close_run(); }
+        }
+        if (all_exact) { I.has_exact = true; I.exact = run; I.is_exact_tight = tight && run_tight; }
+        close_run();
+        if (hb) { I.has_factors = true; I.factors = best; }
+        if (I.has_exact && !I.has_factors) { bool allne = true; for (auto& s : I.exact) if (s.empty()) allne = false; if (allne && !I.exact.empty()) { I.has_factors = true; I.factors = I.exact; } }
+        return I;
+      }
+    }
+    return I;
+  }
+};
+
+static std::vector<uint16_t> utf8_to_units(const char* s, size_t n) {
+  std::vector<uint16_t> u; size_t i = 0;
+  auto* p = reinterpret_cast<const unsigned char*>(s);
+  while (i < n) {
+    uint32_t c = p[i];
+    if (c < 0x80) { u.push_back((uint16_t)c); i++; continue; }
+    int need = 0; uint32_t cp = 0, lo = 0x80, hi = 0xbf;
+    if (c >= 0xc2 && c <= 0xdf) { need = 1; cp = c & 0x1f; }
+    else if (c >= 0xe0 && c <= 0xef) { need = 2; cp = c & 0x0f; if (c == 0xe0) lo = 0xa0; if (c == 0xed) hi = 0x9f; }
+    else if (c >= 0xf0 && c <= 0xf4) { need = 3; cp = c & 0x07; if (c == 0xf0) lo = 0x90; if (c == 0xf4) hi = 0x8f; }
+    else { u.push_back(0xfffd); i++; continue; }
+    size_t j = i + 1; bool ok = true;
+    for (int t = 0; t < need; t++, j++) { if (j >= n || p[j] < lo || p[j] > hi) { ok = false; break; } cp = (cp << 6) | (p[j] & 0x3f); lo = 0x80; hi = 0xbf; }
+    if (!ok) { u.push_back(0xfffd); i = j > i + 1 ? j : i + 1; continue; }
+    i = j;
+    if (cp >= 0x10000) { cp -= 0x10000; u.push_back((uint16_t)(0xd800 + (cp >> 10))); u.push_back((uint16_t)(0xdc00 + (cp & 0x3ff))); }
+    else u.push_back((uint16_t)cp);
+  }
+  return u;
+}
+
+}  // namespace
+
+CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
+  CompiledRule out;
+  Parser ps;
+  ps.p = utf8_to_units(src, len);
+  ps.icase = flags & 1;
+  try {
+    ps.prescan();
+    int root = ps.parse_disjunction();
+    if (ps.i < ps.p.size()) throw Fail{RULE_ERR_SYNTAX, ps.p[ps.i] == ')' ? "unmatched ')'" : "unexpected character"};
+    if (ps.icase && ps.explicit_nonascii) throw Fail{RULE_ERR_UNSUPPORTED, "flag i with non-ASCII literals"};
+    Compiler c(ps, out);
+    c.check_supported(root);
+    c.gen(root);
+    c.emit(OP_MATCH);
+    out.nullable = c.nullable(root);
+    if (out.nullable) { for (int k = 0; k < 4; k++) out.first_bytes.w[k] = ~0ull; }
+    else {
+      Ranges f; c.first(root, f); normalise(f);
+      for (auto& p : f) { for (int b = p.first; b <= std::min(p.second, 127); b++) out.first_bytes.set(b); if (p.second >= 128) for (int b = 128; b < 256; b++) out.first_bytes.set(b); }
+    }
+    if (!out.nullable) {
+      Compiler::Info I = c.analyse(root);
+      if (I.has_factors) {
+        bool ok = !I.factors.empty(); for (auto& s : I.factors) if (s.empty()) ok = false;
+        if (ok) {
+          out.factors = I.factors;
+          out.factors_exact = I.has_exact && I.is_exact_tight && I.exact == I.factors;
+        }
+      }
+    }
+  } catch (const Fail& f) {
+    out = CompiledRule();
+    out.status = f.status; out.error = f.msg;
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------ prefilter DFA
+
+namespace {
+struct Item { uint32_t seq; uint16_t k; bool operator<(const Item& o) const { return seq != o.seq ? seq < o.seq : k < o.k; } bool operator==(const Item& o) const { return seq == o.seq && k == o.k; } };
+struct StateKey { std::vector<Item> items; std::vector<uint32_t> done; bool operator<(const StateKey& o) const { return items != o.items ? items < o.items : done < o.done; } };
+}
+
+bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* pf, std::string* err) {
+  Prefilter& P = *pf;
+  P = Prefilter();
+  P.mode = opt.mode;
+  // gather factors
+  struct Seq { FactorSeq s; uint32_t rule; };
+  std::vector<Seq> all;
+  for (size_t r = 0; r < rules.size(); r++) {
+    if (rules[r].status != RULE_OK) continue;
+    if (rules[r].factors.empty()) { P.always_rules.push_back((uint32_t)r); continue; }
+    for (auto& f : rules[r].factors) all.push_back({f, (uint32_t)r});
+  }
+  // column mapping
+  int ncols;
+  uint8_t colmap[256];
+  if (opt.mode == 0) {
+    ncols = 128; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)(b & 0x7f);
+  } else {
+    // partition refinement of the byte alphabet by every distinct element set
+    std::set<ByteSet> distinct; for (auto& q : all) for (auto& e : q.s) distinct.insert(e);
+    std::vector<int> cls(256, 0); int ncls = 1;
+    for (auto& bs : distinct) {
+      std::map<std::pair<int, bool>, int> remap; std::vector<int> nc(256);
+      for (int b = 0; b < 256; b++) { auto key = std::make_pair(cls[b], bs.has(b)); auto it = remap.find(key); if (it == remap.end()) it = remap.emplace(key, (int)remap.size()).first; nc[b] = it->second; }
+      cls.swap(nc); ncls = (int)remap.size();
+    }
+    // merge the lightest classes until they fit (merging only ever widens element sets => still sound)
+    while (ncls > opt.max_classes) {
+      std::vector<double> w(ncls, 0); for (int b = 0; b < 256; b++) w[cls[b]] += Compiler::byte_weight(b);
+      int a = -1, c = -1; for (int k = 0; k < ncls; k++) { if (a < 0 || w[k] < w[a]) { c = a; a = k; } else if (c < 0 || w[k] < w[c]) c = k; }
+      for (int b = 0; b < 256; b++) { if (cls[b] == c) cls[b] = a; }
+      for (int b = 0; b < 256; b++) { if (cls[b] == ncls - 1 && c != ncls - 1) cls[b] = c; }
+      ncls--;
+    }
+    ncols = 32; while (ncols < ncls) ncols *= 2;
+    for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)cls[b];
+  }
+  memcpy(P.lut, colmap, 256);
+  P.ncols = ncols;
+
+  for (int flen = std::min(opt.max_factor_len, kMaxFactorLen); flen >= 1; flen--) {
+    // truncate factors (a prefix of a necessary factor is still necessary), map elements to column sets, dedupe
+    struct CSeq { std::vector<std::vector<bool>> cols; std::vector<uint32_t> rules; };
+    std::map<std::vector<std::vector<bool>>, std::vector<uint32_t>> uniq;
+    for (auto& q : all) {
+      std::vector<std::vector<bool>> cs;
+      for (size_t k = 0; k < q.s.size() && (int)k < flen; k++) { std::vector<bool> c(ncols, false); for (int b = 0; b < 256; b++) if (q.s[k].has(b)) c[colmap[b]] = true; cs.push_back(c); }
+      uniq[cs].push_back(q.rule);
+    }
+    std::vector<CSeq> seqs; for (auto& kv : uniq) seqs.push_back({kv.first, kv.second});
+    std::vector<std::vector<uint32_t>> start_by_col(ncols);
+    for (uint32_t q = 0; q < seqs.size(); q++) for (int c = 0; c < ncols; c++) if (seqs[q].cols[0][c]) start_by_col[c].push_back(q);
+    // subset construction
+    std::map<StateKey, int> ids; std::vector<StateKey> states; std::vector<std::vector<int>> trans;
+    auto intern = [&](StateKey&& k) { auto it = ids.find(k); if (it != ids.end()) return it->second; int id = (int)states.size(); ids.emplace(k, id); states.push_back(std::move(k)); return id; };
+    intern(StateKey());
+    bool overflow = false;
+    for (size_t s = 0; s < states.size() && !overflow; s++) {
+      std::vector<int> row(ncols);
+      for (int c = 0; c < ncols; c++) {
+        StateKey nk; StateKey cur = states[s];
+        for (auto& it : cur.items) if (seqs[it.seq].cols[it.k][c]) { if (it.k + 1u == seqs[it.seq].cols.size()) nk.done.push_back(it.seq); else nk.items.push_back({it.seq, (uint16_t)(it.k + 1)}); }
+        for (uint32_t q : start_by_col[c]) { if (seqs[q].cols.size() == 1) nk.done.push_back(q); else nk.items.push_back({q, 1}); }
+        std::sort(nk.items.begin(), nk.items.end()); nk.items.erase(std::unique(nk.items.begin(), nk.items.end()), nk.items.end());
+        std::sort(nk.done.begin(), nk.done.end()); nk.done.erase(std::unique(nk.done.begin(), nk.done.end()), nk.done.end());
+        row[c] = intern(std::move(nk));
+        if ((int)states.size() > opt.max_states || states.size() > 65000) { overflow = true; break; }
+      }
+      trans.push_back(row);
+    }
+    if (overflow) continue;
+    // renumber: non-accepting first (state 0 stays 0), accepting last
+    int n = (int)states.size(); std::vector<int> newid(n); int na = 0, nn = 0;
+    for (int s = 0; s < n; s++) if (states[s].done.empty()) nn++;
+    int a = nn, b = 0;
+    for (int s = 0; s < n; s++) { if (states[s].done.empty()) newid[s] = b++; else { newid[s] = a++; na++; } }
+    P.nstates = n; P.first_accept = nn; P.factor_len = flen;
+    P.table.assign((size_t)n * ncols, 0);
+    for (int s = 0; s < n; s++) for (int c = 0; c < ncols; c++) P.table[(size_t)newid[s] * ncols + c] = (uint16_t)newid[trans[s][c]];
+    P.out_offsets.assign(na + 1, 0); P.out_rules.clear();
+    std::vector<int> old_of(n); for (int s = 0; s < n; s++) old_of[newid[s]] = s;
+    for (int t = 0; t < na; t++) {
+      std::set<uint32_t> rs; for (uint32_t q : states[old_of[nn + t]].done) for (uint32_t r : seqs[q].rules) rs.insert(r);
+      P.out_offsets[t] = (uint32_t)P.out_rules.size(); P.out_rules.insert(P.out_rules.end(), rs.begin(), rs.end());
+    }
+    P.out_offsets[na] = (uint32_t)P.out_rules.size();
+    return true;
+  }
+  // even single-element factors do not fit: every factored rule becomes an always-candidate
+  for (size_t r = 0; r < rules.size(); r++) if (rules[r].status == RULE_OK && !rules[r].factors.empty()) P.always_rules.push_back((uint32_t)r);
+  std::sort(P.always_rules.begin(), P.always_rules.end());
+  P.nstates = 1; P.first_accept = 1; P.factor_len = 0; P.table.assign(ncols, 0); P.out_offsets.assign(1, 0);
+  if (err) *err = "prefilter did not fit the state budget; all rules verified on every message";
+  return true;
+}
+
+}  // namespace cg

@@ -1,0 +1,50 @@
+// ruleset_image.cpp -- see ruleset_image.h
+#include "ruleset_image.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace cg {
+
+bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, HostImage* out, std::string* err) {
+  HostImage& H = *out;
+  H = HostImage();
+  H.rules.resize(n);
+  for (uint32_t i = 0; i < n; i++) H.rules[i] = compile_rule(src[i].src ? src[i].src : "", src[i].len, src[i].flags);
+  H.prog_off.assign((size_t)n + 1, 0);
+  H.first.assign(8 * (size_t)std::max<uint32_t>(n, 1), 0);
+  for (uint32_t i = 0; i < n; i++) {
+    H.prog_off[i] = (uint32_t)H.prog.size();
+    CompiledRule& r = H.rules[i];
+    if (r.status != RULE_OK) continue;     // empty program: never matches, no factors
+    uint32_t base = (uint32_t)(H.sets.size() / 6);
+    for (auto& s : r.sets) {
+      for (int k = 0; k < 4; k++) H.sets.push_back(s.ascii[k]);
+      H.sets.push_back((uint32_t)H.ranges.size());            // element offset of the first lo,hi pair
+      H.sets.push_back((uint32_t)(s.ranges.size() / 2));
+      H.ranges.insert(H.ranges.end(), s.ranges.begin(), s.ranges.end());
+    }
+    for (uint32_t ins : r.prog) {
+      uint32_t op = ins & 0xff, arg = ins >> 8;
+      if (op == OP_SET || op == OP_LOOKAHEAD || op == OP_NLOOKAHEAD || op == OP_LOOKBEHIND || op == OP_NLOOKBEHIND) arg += base;
+      H.prog.push_back(op | (arg << 8));
+    }
+    for (int k = 0; k < 8; k++) H.first[(size_t)i * 8 + k] = (uint32_t)(r.first_bytes.w[k >> 1] >> (32 * (k & 1)));
+  }
+  H.prog_off[n] = (uint32_t)H.prog.size();
+  H.n_sets = (uint32_t)(H.sets.size() / 6);
+
+  PrefilterOptions po;
+  po.mode = opt.mode; po.max_classes = opt.max_classes; po.max_factor_len = opt.max_factor_len;
+  int cols = po.mode == 0 ? 128 : (po.max_classes <= 32 ? 32 : 64);
+  size_t budget = std::max<size_t>(opt.budget_bytes, 256 + (size_t)cols * 2 * 2);
+  po.max_states = (int)std::min<size_t>((budget - 256) / ((size_t)cols * 2), 65000);
+  if (!build_prefilter(H.rules, po, &H.pf, err)) return false;
+  H.image.assign(256 + H.pf.table.size() * 2, 0);
+  memcpy(H.image.data(), H.pf.lut, 256);
+  memcpy(H.image.data() + 256, H.pf.table.data(), H.pf.table.size() * 2);
+  while (H.image.size() % 16) H.image.push_back(0);
+  return true;
+}
+
+}  // namespace cg

@@ -1,0 +1,222 @@
+// sha256_kernels.cu -- batched SHA-256 and the Proof-of-Guardrails Merkle tree (sm_100a).
+//
+// Replaces createHash("sha256").update(s).digest() (gov/src/util.ts:77-79, gov/src/redaction/
+// vault.ts:26-28, nats/src/hooks.ts:90-94) for batches, and builds the Merkle tree the reference
+// only describes (README "Proof-of-Guardrails"; RFC.md:782-800 specifies a hash chain that was
+// never implemented).  Convention (frozen in oracle/sha256_merkle.c, restated in DESIGN.md):
+//   leaf = SHA-256(0x00 || bytes), node = SHA-256(0x01 || L || R), unpaired node promoted.
+// All 64 rounds run in registers; digests are stored in HBM as the canonical 32 big-endian bytes.
+#include "kernels.h"
+
+namespace cg {
+
+__constant__ uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__device__ __forceinline__ void sha_init(uint32_t h[8]) {
+  h[0] = 0x6a09e667; h[1] = 0xbb67ae85; h[2] = 0x3c6ef372; h[3] = 0xa54ff53a;
+  h[4] = 0x510e527f; h[5] = 0x9b05688c; h[6] = 0x1f83d9ab; h[7] = 0x5be0cd19;
+}
+
+// one compression; w[16] is clobbered (rolling message schedule, all in registers)
+__device__ __forceinline__ void sha_compress(uint32_t h[8], uint32_t w[16]) {
+  uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+  for (int t = 0; t < 64; t++) {
+    uint32_t wt;
+    if (t < 16) wt = w[t];
+    else {
+      uint32_t w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
+      uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+      uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+      wt = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
+      w[t & 15] = wt;
+    }
+    uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+    uint32_t ch = (e & f) ^ (~e & g);
+    uint32_t t1 = hh + S1 + ch + K256[t] + wt;
+    uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+    uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+    uint32_t t2 = S0 + mj;
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+__device__ __forceinline__ void store_digest(uint32_t* out, const uint32_t h[8]) {
+  uint4 a = make_uint4(bswap(h[0]), bswap(h[1]), bswap(h[2]), bswap(h[3]));
+  uint4 b = make_uint4(bswap(h[4]), bswap(h[5]), bswap(h[6]), bswap(h[7]));
+  reinterpret_cast<uint4*>(out)[0] = a; reinterpret_cast<uint4*>(out)[1] = b;
+}
+
+// generic: SHA-256 of [prefix byte if prefix >= 0] || data[0,len) ; byte-granular, any alignment
+__device__ void sha_bytes(int prefix, const uint8_t* __restrict__ data, uint64_t len, uint32_t h[8]) {
+  sha_init(h);
+  const uint64_t p = prefix >= 0 ? 1 : 0, total = p + len;
+  const uint64_t nblk = (total + 9 + 63) / 64;
+  for (uint64_t blk = 0; blk < nblk; blk++) {
+    uint32_t w[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint64_t idx = blk * 64 + t * 4 + k;   // index in the padded message
+        uint32_t byte;
+        if (idx < p) byte = (uint32_t)prefix;
+        else if (idx < total) byte = data[idx - p];
+        else if (idx == total) byte = 0x80;
+        else byte = 0;
+        v = (v << 8) | byte;
+      }
+      w[t] = v;
+    }
+    if (blk == nblk - 1) { uint64_t bits = total * 8; w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+    sha_compress(h, w);
+  }
+}
+
+__global__ void __launch_bounds__(128) sha256_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ off,
+                                                            uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t h[8];
+  sha_bytes(-1, bytes + off[i], off[i + 1] - off[i], h);
+  store_digest(out + (size_t)i * 8, h);
+}
+
+__global__ void __launch_bounds__(128) merkle_leaves_var_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ off,
+                                                                 uint64_t n, uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t h[8];
+  sha_bytes(0x00, bytes + off[i], off[i + 1] - off[i], h);
+  store_digest(out + i * 8, h);
+}
+
+// fixed-size leaves whose length is a multiple of 4 and whose base is 4-byte aligned:
+// word loads, the 0x00 domain-separation byte shifts every message word by one byte.
+__global__ void __launch_bounds__(128) merkle_leaves_fixed_kernel(const uint8_t* __restrict__ bytes, uint32_t leaf_words,
+                                                                   uint64_t n, uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* leaf = reinterpret_cast<const uint32_t*>(bytes) + i * leaf_words;
+  uint32_t h[8]; sha_init(h);
+  const uint32_t total = 1 + leaf_words * 4;           // bytes incl. prefix
+  const uint32_t nblk = (total + 9 + 63) / 64;
+  uint32_t prev = 0;                                   // big-endian word preceding the current one (prefix 0x00 in its low byte)
+  uint32_t widx = 0;                                   // next leaf word to consume
+  for (uint32_t blk = 0; blk < nblk; blk++) {
+    uint32_t w[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+      // message word m = blk*16+t covers message bytes [4m, 4m+4) = leaf bytes [4m-1, 4m+3)
+      uint32_t m = blk * 16 + t;
+      uint32_t cur;
+      if (m < leaf_words) { cur = bswap(__ldg(leaf + widx)); widx++; }
+      else if (m == leaf_words) cur = 0x80000000u >> 0;  // leaf exhausted: next byte after data is 0x80
+      else cur = 0;
+      // bytes: low byte of prev, then top three bytes of cur
+      uint32_t v = (prev << 24) | (cur >> 8);
+      if (m == leaf_words) v = (prev << 24) | 0x00800000u;
+      else if (m > leaf_words) v = 0;
+      w[t] = v;
+      prev = cur;
+    }
+    if (blk == nblk - 1) { w[14] = 0; w[15] = total * 8; }
+    sha_compress(h, w);
+  }
+  store_digest(out + i * 8, h);
+}
+
+// node = SHA-256(0x01 || L || R): 65 bytes = two blocks
+__device__ __forceinline__ void merkle_node(const uint32_t l[8], const uint32_t r[8], uint32_t h[8]) {
+  // l, r hold big-endian digest words (i.e. the SHA state words)
+  uint32_t w[16];
+  w[0] = 0x01000000u | (l[0] >> 8);
+#pragma unroll
+  for (int t = 1; t < 8; t++) w[t] = (l[t - 1] << 24) | (l[t] >> 8);
+  w[8] = (l[7] << 24) | (r[0] >> 8);
+#pragma unroll
+  for (int t = 1; t < 8; t++) w[8 + t] = (r[t - 1] << 24) | (r[t] >> 8);
+  sha_init(h);
+  sha_compress(h, w);
+  w[0] = (r[7] << 24) | 0x00800000u;
+#pragma unroll
+  for (int t = 1; t < 15; t++) w[t] = 0;
+  w[15] = 65 * 8;
+  sha_compress(h, w);
+}
+
+__device__ __forceinline__ void load_digest(const uint32_t* p, uint32_t d[8]) {
+  uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  d[0] = bswap(a.x); d[1] = bswap(a.y); d[2] = bswap(a.z); d[3] = bswap(a.w);
+  d[4] = bswap(b.x); d[5] = bswap(b.y); d[6] = bswap(b.z); d[7] = bswap(b.w);
+}
+
+__global__ void __launch_bounds__(128) merkle_level_kernel(const uint32_t* __restrict__ in, uint64_t n_in, uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t n_out = (n_in + 1) / 2;
+  if (i >= n_out) return;
+  if (2 * i + 1 < n_in) {
+    uint32_t l[8], r[8], h[8];
+    load_digest(in + 16 * i, l); load_digest(in + 16 * i + 8, r);
+    merkle_node(l, r, h);
+    store_digest(out + 8 * i, h);
+  } else {
+    reinterpret_cast<uint4*>(out + 8 * i)[0] = reinterpret_cast<const uint4*>(in + 16 * i)[0];
+    reinterpret_cast<uint4*>(out + 8 * i)[1] = reinterpret_cast<const uint4*>(in + 16 * i)[1];
+  }
+}
+
+int launch_sha256_batch(const uint8_t* d_bytes, const uint64_t* d_off, uint32_t n, uint8_t* d_out, cudaStream_t stream) {
+  if (!n) return 0;
+  sha256_batch_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_bytes, d_off, n, reinterpret_cast<uint32_t*>(d_out));
+  return 1;
+}
+// fixed-size leaves of any length / alignment (byte-granular path)
+__global__ void __launch_bounds__(128) merkle_leaves_fixed_generic_kernel(const uint8_t* __restrict__ bytes, uint64_t leaf_len,
+                                                                           uint64_t n, uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t h[8];
+  sha_bytes(0x00, bytes + i * leaf_len, leaf_len, h);
+  store_digest(out + i * 8, h);
+}
+
+int launch_merkle_leaves_fixed(const uint8_t* d_bytes, uint64_t leaf_len, uint64_t n, uint32_t* d_out, cudaStream_t stream) {
+  if (!n) return 0;
+  if (leaf_len == 0 || (leaf_len & 3) || (reinterpret_cast<uintptr_t>(d_bytes) & 3) || leaf_len > (1u << 28)) {
+    merkle_leaves_fixed_generic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_bytes, leaf_len, n, d_out);
+    return 1;
+  }
+  merkle_leaves_fixed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_bytes, (uint32_t)(leaf_len / 4), n, d_out);
+  return 1;
+}
+int launch_merkle_leaves_var(const uint8_t* d_bytes, const uint64_t* d_off, uint64_t n, uint32_t* d_out, cudaStream_t stream) {
+  if (!n) return 0;
+  merkle_leaves_var_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_bytes, d_off, n, d_out);
+  return 1;
+}
+int launch_merkle_level(const uint32_t* d_in, uint64_t n_in, uint32_t* d_out, cudaStream_t stream) {
+  uint64_t n_out = (n_in + 1) / 2;
+  if (!n_out) return 0;
+  merkle_level_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, stream>>>(d_in, n_in, d_out);
+  return 1;
+}
+int launch_merkle_reduce(const uint32_t* d_in, uint64_t n_in, uint32_t levels, uint32_t* d_out, cudaStream_t stream) {
+  (void)d_in; (void)n_in; (void)levels; (void)d_out; (void)stream;
+  return 0;   // fused multi-level reduction: see merkle v2
+}
+
+}  // namespace cg
