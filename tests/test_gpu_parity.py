@@ -1,0 +1,197 @@
+"""GPU tier: the real kernels through the C ABI (ctypes) against the oracle and the golden vectors.
+Bit-exact everywhere (integer / byte / index work).  Run on the B200 box: pytest -m gpu."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import oracle_regexes
+from vainplex_openclaw_b200 import workload as W
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+VECTORS = json.load(open(os.path.join(HERE, "golden", "registry_vectors.json")))["vectors"]
+CATS = ["credential", "financial", "pii", "custom"]
+
+
+@pytest.fixture(scope="module")
+def N():
+    from vainplex_openclaw_b200 import _native
+    _native.init()
+    return _native
+
+
+def oracle_policy(O, rules, data, off):
+    regs = oracle_regexes(O, rules)
+    assert all(r is not None for r in regs)
+    bits, words = O.scan_policy(regs, data, off.astype(np.uint64))
+    hits = []
+    for m in range(bits.shape[0]):
+        row = np.unpackbits(bits[m], bitorder="little")[:len(rules)]
+        hits += [(m, int(r)) for r in np.nonzero(row)[0]]
+    return words, hits
+
+
+def oracle_spans(O, rules, data, off):
+    regs = oracle_regexes(O, rules)
+    pats = [(regs[i], CATS[rules[i][2]]) for i in range(len(rules))]
+    return [tuple(x) for x in O.find_matches_batch(pats, data, off.astype(np.uint64)).tolist()]
+
+
+def test_native_library_is_the_cuda_one(N):
+    assert N.load().cg_device_count() >= 1
+    assert os.path.basename(N.lib_path()) == "libopenclaw_gov.so"
+
+
+def test_reference_vectors_through_the_kernels(N, oracle):
+    """every golden input x the reference's registry configurations, spans == oracle, checks hold"""
+    from test_oracle_golden import run_checks
+    configs = {}
+    for v in VECTORS:
+        key = json.dumps([v["categories"], v["custom"]])
+        configs.setdefault(key, []).append(v)
+    for key, vs in configs.items():
+        cats, custom = json.loads(key)
+        reg = oracle.builtin_registry(cats, custom)           # (Regex, category, id) storage order
+        rules = [(r[0].source, 1 if "i" in r[0].flags else 0, CATS.index(r[1])) for r in reg]
+        if not rules:
+            continue
+        rs = N.Ruleset(rules, strict=True)
+        msgs = [N.js_utf8(v["input"]) for v in vs]
+        data, off = N.pack(msgs)
+        spans = rs.find_matches_batch(data, off)
+        exp = oracle_spans(oracle, rules, data, off)
+        got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+        assert got == exp
+        for mi, v in enumerate(vs):
+            u = oracle.js_units(v["input"])
+            ms = [{"id": reg[r][2], "match": u[s:e].tobytes().decode("utf-16-le", "surrogatepass")} for (m, r, s, e) in got if m == mi]
+            run_checks(ms, v["checks"])
+        rs.close()
+
+
+@pytest.mark.parametrize("n_rules,mode", [(17, 0), (64, 1), (500, 0), (500, 1)])
+def test_policy_scan_equals_oracle(N, oracle, n_rules, mode):
+    rl = W.make_rules(n_rules)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, options=mode, strict=True)
+    n = 6000
+    data_t, off_t, inj = W.make_messages(n, 256, rl, p_hit=0.05, seed=4242 + n_rules)
+    data = data_t.numpy()
+    off = off_t.numpy().astype(np.uint32)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits
+    assert np.array_equal(words, ewords)
+    assert len(ehits) >= len(inj)          # every injected token is a true hit
+    rs.close()
+
+
+@pytest.mark.parametrize("utf8_frac,length", [(0.2, 190), (0.0, 64), (0.1, 1024)])
+def test_redaction_spans_equal_oracle(N, oracle, utf8_frac, length):
+    rl = W.make_rules(120)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    data_t, off_t, _ = W.make_messages(2500, length, rl, p_hit=0.2, utf8_frac=utf8_frac, seed=99 + length)
+    data, off = data_t.numpy(), off_t.numpy().astype(np.uint32)
+    spans = rs.find_matches_batch(data, off)
+    got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+    assert got == oracle_spans(oracle, rules, data, off)
+    # byte offsets delimit the same text as the UTF-16 offsets
+    for s in spans[:200]:
+        m = bytes(data[off[s["msg"]]:off[s["msg"] + 1]])
+        txt = m.decode("utf-8", "replace")
+        u = oracle.js_units(txt)
+        a = m[s["start_byte"]:s["end_byte"]].decode("utf-8", "replace")
+        b = u[s["start16"]:s["end16"]].tobytes().decode("utf-16-le", "replace")
+        assert a == b
+    rs.close()
+
+
+def test_ragged_empty_and_edge_inputs(N, oracle):
+    rules = [(r"sk-[a-zA-Z0-9]{20,}", 0, 0), (r"\d+", 0, 3), (r"", 0, 3), (r"^$", 0, 3), (r"a*?b", 0, 3), (r"x\b", 0, 3), (r"(?:a??)?", 0, 3)]
+    rs = N.Ruleset(rules, strict=True)
+    rng = np.random.default_rng(3)
+    msgs = [b"", b"a", b"sk-" + b"a" * 25, b"", b"12 345", "😀".encode(), b"aab xb", b"x" * 700 + b" 9"]
+    msgs += [bytes(rng.integers(32, 127, int(k), dtype=np.uint8)) for k in rng.integers(0, 90, 300)]
+    msgs += [bytes(rng.integers(0, 256, int(k), dtype=np.uint8)) for k in rng.integers(0, 40, 200)]   # invalid UTF-8 too
+    data, off = N.pack(msgs)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits
+    assert np.array_equal(words, ewords)
+    spans = rs.find_matches_batch(data, off)
+    got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+    assert got == oracle_spans(oracle, rules, data, off)
+    # n = 0
+    d0, o0 = N.pack([])
+    w0, h0 = rs.scan_batch(d0, o0)
+    assert len(w0) == 0 and len(h0) == 0
+    rs.close()
+
+
+def test_failed_rules_never_match_and_report_status(N):
+    rs = N.Ruleset([("ok+", 0, 3), ("a(b", 0, 3), (r"(x)\1", 0, 3)])
+    assert list(rs.status) == [0, N.CG_ERR_SYNTAX, N.CG_ERR_UNSUPPORTED]
+    data, off = N.pack([b"okkk a(b xx"])
+    words, hits = rs.scan_batch(data, off)
+    assert [(int(h["msg"]), int(h["rule"])) for h in hits] == [(0, 0)]
+    with pytest.raises(N.GovError):
+        N.Ruleset([("a(b", 0, 3)], strict=True)
+    rs.close()
+
+
+def test_single_long_message(N, oracle):
+    rl = W.make_rules(40)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    data_t, off_t, _ = W.make_messages(1, 65536, rl, p_hit=1.0, seed=5)
+    data, off = data_t.numpy(), off_t.numpy().astype(np.uint32)
+    spans = rs.find_matches_batch(data, off)
+    got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+    assert got == oracle_spans(oracle, rules, data, off)
+    rs.close()
+
+
+# ------------------------------------------------------------------------------ SHA-256 / Merkle
+
+def test_sha256_batch_equals_hashlib_and_oracle(N, oracle):
+    rng = np.random.default_rng(11)
+    msgs = [bytes(rng.integers(0, 256, int(k), dtype=np.uint8)) for k in list(range(0, 140)) + [255, 256, 257, 1000, 5000]]
+    msgs += [b"abc", b"", b"Hello World!"]
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    data = np.frombuffer(b"".join(msgs) + b"\0" * 64, dtype=np.uint8).copy()
+    out = N.sha256_batch(data, off)
+    for i, m in enumerate(msgs):
+        assert out[i].tobytes() == hashlib.sha256(m).digest()
+    assert np.array_equal(out, oracle.sha256_batch(data, off))
+    assert out[-1].tobytes().hex() == "7f83b1657ff1fc53b92dc18148a1d65dfc2d4b1fa3d677284addd200126d9069"  # gov/RFC.md:1562
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 8, 33, 1000, 4097, 100003])
+def test_merkle_root_variable_leaves(N, oracle, n):
+    rng = np.random.default_rng(n + 1)
+    lens = rng.integers(0, 300, n)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    data = rng.integers(0, 256, int(off[-1]) + 64, dtype=np.uint8)
+    assert N.merkle_root(data, off) == oracle.merkle_root(data, off)
+
+
+@pytest.mark.parametrize("n,leaf", [(1 << 16, 256), (100003, 256), (50000, 32), (7777, 64), (999, 1024), (1234, 37)])
+def test_merkle_root_fixed_leaves(N, oracle, n, leaf):
+    data = W.make_leaves(n, leaf).numpy()
+    assert N.merkle_root_fixed(data, leaf, n) == oracle.merkle_root_fixed(data, leaf, n)
+
+
+def test_merkle_fold_of_block_roots(N, oracle):
+    n, leaf, k = 10000, 64, 8
+    data = W.make_leaves(n, leaf).numpy()
+    roots = []
+    for s in range(0, n, 1 << k):
+        e = min(n, s + (1 << k))
+        roots.append(np.frombuffer(N.merkle_root_fixed(data[s * leaf:], leaf, e - s), dtype=np.uint8))
+    assert N.merkle_fold(np.stack(roots)) == oracle.merkle_root_fixed(data, leaf, n)
