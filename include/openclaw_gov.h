@@ -48,8 +48,10 @@ extern "C" {
 #define CG_CAT_CUSTOM     3u
 
 /* ---- ruleset options */
-#define CG_OPT_PREFILTER_DIRECT7 0u /* 128-column table indexed by byte&0x7f (default) */
-#define CG_OPT_PREFILTER_LUT     1u /* byte->class LUT + compact table */
+#define CG_OPT_PREFILTER_DIRECT7 0u /* level-1 table with 128 columns indexed by byte & 0x7f */
+#define CG_OPT_PREFILTER_LUT     1u /* byte->class LUT (<= 64 classes) + compact table */
+#define CG_OPT_PREFILTER_FOLD6   2u /* 64 columns from SWAR-folded 6-bit byte classes (default) */
+#define CG_OPT_PREFILTER_FOLD5   3u /* 32 columns (byte & 0x1f): twice the states, deeper windows */
 
 typedef struct cg_ruleset cg_ruleset;
 
@@ -74,8 +76,8 @@ typedef struct cg_span {    /* one element of PatternRegistry.findMatches()'s re
 
 typedef struct cg_ruleset_info {
   uint32_t n_rules, n_ok, n_always_candidate, n_sets;
-  uint32_t prefilter_mode, prefilter_states, prefilter_cols, prefilter_factor_len, prefilter_bytes;
-  uint32_t program_words;
+  uint32_t prefilter_mode, prefilter_states, prefilter_cols, prefilter_factor_len /* window min | max<<8 */, prefilter_bytes;
+  uint32_t program_words, n_factors, prefilter_hot_states;
 } cg_ruleset_info;
 
 typedef struct cg_stats {   /* cumulative since cg_init; surfaced by governance.status (index.ts:103-114) */
@@ -93,6 +95,11 @@ CG_API int cg_version(void);
 CG_API int cg_device_count(void);
 CG_API int cg_get_stats(cg_stats *out);
 CG_API uint64_t cg_launch_count(void);   /* kernels launched by this library so far */
+/* measurement hooks (the reference's ScanResult.elapsedMs / evaluationUs, src/redaction/engine.ts:54,65):
+ * with profiling on, CUDA events bracket each kernel of a scan step on its stream. */
+CG_API int cg_set_profiling(int on);
+CG_API int cg_last_kernel_ms(float out_ms[4]);          /* scan, confirm, verify, finalize of the last completed step */
+CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out5[5]); /* slots, VM pairs, spans, flags, level-1 events */
 
 /* ---- rule-set compile.  Replaces `new RegExp(pattern)` in buildPolicyIndex
  * (src/policy-loader.ts:119-128), compileCustomPattern (src/redaction/registry.ts:249-281) and

@@ -7,7 +7,7 @@ import numpy as np
 class Harness:
     """Host-compiled product compiler + VM (tests/native/vm_harness.cpp)."""
 
-    def __init__(self, L, rules, mode=0, budget_kb=0, max_factor_len=0):
+    def __init__(self, L, rules, mode=2, budget_kb=0, max_factor_len=0):
         self.L = L
         self.srcs = [r[0] if isinstance(r[0], bytes) else r[0].encode("utf-8", "surrogatepass") for r in rules]
         arr = (C.c_char_p * max(1, len(rules)))(*self.srcs)
@@ -23,8 +23,8 @@ class Harness:
     def info(self):
         o = np.zeros(8, dtype=np.uint32)
         self.L.harness_info(self.h, o.ctypes.data)
-        return dict(nstates=int(o[0]), first_accept=int(o[1]), ncols=int(o[2]), factor_len=int(o[3]),
-                    n_always=int(o[4]), image_bytes=int(o[5]), prog_words=int(o[6]))
+        return dict(nstates=int(o[0]), n_factors=int(o[1]), ncols=int(o[2]), window_min=int(o[3]) & 0xff,
+                    window_max=int(o[3]) >> 8, n_always=int(o[4]), image_bytes=int(o[5]), prog_words=int(o[6]))
 
     def find_all(self, rule, msg: bytes):
         cap = 64
@@ -41,10 +41,18 @@ class Harness:
         assert r >= 0
         return bool(r)
 
+    def candidates2(self, msg: bytes, want_spans=False):
+        """-> (queued-for-VM rules, direct-hit rules, number of level-1 accepting transitions)"""
+        c = np.zeros(self.rw, dtype=np.uint32)
+        d = np.zeros(self.rw, dtype=np.uint32)
+        l1 = np.zeros(1, dtype=np.uint32)
+        self.L.harness_candidates(self.h, msg, len(msg), c.ctypes.data, d.ctypes.data, 1 if want_spans else 0, l1.ctypes.data)
+        f = lambda bits: {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
+        return f(c), f(d), int(l1[0])
+
     def candidates(self, msg: bytes):
-        bits = np.zeros(self.rw, dtype=np.uint32)
-        self.L.harness_candidates(self.h, msg, len(msg), bits.ctypes.data)
-        return {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
+        c, d, _ = self.candidates2(msg)
+        return c | d
 
     def close(self):
         if self.h:

@@ -7,11 +7,14 @@
 //   * exact spans of the VM == oracle/jsre.c spans
 // The product path never links this file; libopenclaw_gov.so only runs the VM inside verify_kernel.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../vainplex_openclaw_b200/csrc/pike_vm.h"
+#include "../../vainplex_openclaw_b200/csrc/prefilter_dev.h"
 #include "../../vainplex_openclaw_b200/csrc/ruleset_image.h"
 
 using namespace cg;
@@ -34,30 +37,35 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   Harness* h = new Harness();
   std::vector<RuleSrc> src(n);
   for (uint32_t i = 0; i < n; i++) src[i] = RuleSrc{srcs[i], lens[i], flags[i]};
-  ImageOptions io; io.mode = mode; if (budget_kb) io.budget_bytes = (size_t)budget_kb * 1024; if (max_factor_len) io.max_factor_len = max_factor_len;
+  ImageOptions io; io.mode = mode; if (budget_kb) io.budget_bytes = (size_t)budget_kb * 1024; if (getenv("CG_MAX_STATES")) io.max_states = atoi(getenv("CG_MAX_STATES")); if (max_factor_len) io.max_window = max_factor_len;
   std::string err;
   if (!build_host_image(src.data(), n, io, &h->H, &err)) { delete h; return nullptr; }
   for (uint32_t i = 0; i < n; i++) if (status) status[i] = h->H.rules[i].status;
   HostImage& H = h->H; DevRuleset& d = h->d;
   // pad host vectors the same way capi.cu pads the device copies
   H.sets.resize(H.sets.size() + 8, 0); H.ranges.resize(H.ranges.size() + 8, 0); H.first.resize(H.first.size() + 8, 0);
-  H.pf.out_offsets.resize(H.pf.out_offsets.size() + 4, 0); H.pf.out_rules.resize(H.pf.out_rules.size() + 4, 0);
+  H.pf.acc_index.resize(H.pf.acc_index.size() + 4, 0xffffffffu); H.pf.acc_offsets.resize(H.pf.acc_offsets.size() + 4, 0);
+  H.pf.acc_factors.resize(H.pf.acc_factors.size() + 4, 0); H.factor_words.resize(H.factor_words.size() + 16, 0);
+  H.pf.bytesets.resize(H.pf.bytesets.size() + 8, 0);
+  uint32_t n_always = (uint32_t)H.pf.always_rules.size();
   H.pf.always_rules.resize(H.pf.always_rules.size() + 4, 0);
   d.image = H.image.data(); d.image_bytes = (uint32_t)H.image.size(); d.mode = (uint32_t)H.pf.mode;
   d.ncols_log2 = 0; while ((1 << d.ncols_log2) < H.pf.ncols) d.ncols_log2++;
-  d.nstates = (uint32_t)H.pf.nstates; d.first_accept = (uint32_t)H.pf.first_accept;
-  d.out_offsets = H.pf.out_offsets.data(); d.out_rules = H.pf.out_rules.data();
-  d.always_rules = H.pf.always_rules.data(); d.n_always = (uint32_t)(H.pf.always_rules.size() - 4);
+  d.nstates = (uint32_t)H.pf.nstates; d.hot_states = H.hot_states; d.table_full = H.pf.table.data();
+  d.acc_index = H.pf.acc_index.data(); d.acc_offsets = H.pf.acc_offsets.data(); d.acc_factors = H.pf.acc_factors.data();
+  d.factors = H.factor_words.data(); d.bytesets = H.pf.bytesets.data();
+  d.always_rules = H.pf.always_rules.data(); d.n_always = n_always;
   d.prog = H.prog.data(); d.rule_prog_off = H.prog_off.data(); d.sets = H.sets.data(); d.set_ranges = H.ranges.data();
   d.rule_first = H.first.data(); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
   return h;
 }
 void harness_destroy(void* p) { delete (Harness*)p; }
 
-// info: [0]=nstates [1]=first_accept [2]=ncols [3]=factor_len [4]=n_always [5]=image_bytes [6]=program words
+// info: [0]=nstates [1]=n_factors [2]=ncols [3]=window_min|window_max<<8 [4]=n_always [5]=image_bytes [6]=program words
 void harness_info(void* p, uint32_t* out) {
   Harness* h = (Harness*)p;
-  out[0] = h->d.nstates; out[1] = h->d.first_accept; out[2] = (uint32_t)h->H.pf.ncols; out[3] = (uint32_t)h->H.pf.factor_len;
+  out[0] = h->d.nstates; out[1] = (uint32_t)h->H.pf.factors.size(); out[2] = (uint32_t)h->H.pf.ncols;
+  out[3] = (uint32_t)h->H.pf.window_min | ((uint32_t)h->H.pf.window_max << 8);
   out[4] = h->d.n_always; out[5] = h->d.image_bytes; out[6] = (uint32_t)h->H.prog.size();
 }
 const char* harness_rule_error(void* p, uint32_t rule) { return ((Harness*)p)->H.rules[rule].error.c_str(); }
@@ -84,20 +92,54 @@ int harness_test(void* p, uint32_t rule, const uint8_t* m, uint32_t len) {
   return any ? 1 : 0;
 }
 
-// the scan kernel's table walk, restated on the host: candidate bitmap (rw words) for one message
-void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* bits) {
+// the scan kernel's candidate logic (level-1 walk + level-2 confirm, same device/host code),
+// restated for one message: bitmaps (rw words each) of queued candidates and of direct hits
+struct BitSink {
+  uint32_t* cand; uint32_t* direct_;
+  void candidate(uint32_t r) { cand[r >> 5] |= 1u << (r & 31); }
+  void direct(uint32_t r) { direct_[r >> 5] |= 1u << (r & 31); }
+};
+void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand, uint32_t* direct, int want_spans, uint32_t* l1_hits) {
   Harness* h = (Harness*)p; const DevRuleset& d = h->d;
-  for (uint32_t k = 0; k < d.rw; k++) bits[k] = 0;
-  for (uint32_t k = 0; k < d.n_always; k++) { uint32_t r = d.always_rules[k]; bits[r >> 5] |= 1u << (r & 31); }
-  const uint8_t* lut = d.image; const uint16_t* table = (const uint16_t*)(d.image + 256);
+  for (uint32_t k = 0; k < d.rw; k++) { cand[k] = 0; direct[k] = 0; }
+  BitSink sink{cand, direct};
+  for (uint32_t k = 0; k < d.n_always; k++) sink.candidate(d.always_rules[k]);
+  const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
+  uint32_t state = 0, hits = 0;
+  for (uint32_t i = 0; i < len; i++) {
+    uint32_t col = l1_col(d.mode, lut, m[i]);
+    uint32_t ent = table[(state << d.ncols_log2) + col];
+    if (ent & 0x8000u) { hits++; l1_accept(d, state, col, m, len, i, want_spans != 0, sink); }
+    state = ent & 0x7fffu;
+  }
+  if (l1_hits) *l1_hits = hits;
+}
+
+
+// debug: level-1 accepting transitions per factor over one message (adds into counts[n_factors])
+void harness_l1_factor_counts(void* p, const uint8_t* m, uint32_t len, uint32_t* counts) {
+  Harness* h = (Harness*)p; const DevRuleset& d = h->d;
+  const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0;
   for (uint32_t i = 0; i < len; i++) {
-    uint32_t col = d.mode == 0 ? (m[i] & 0x7fu) : lut[m[i]];
-    state = table[(state << d.ncols_log2) + col];
-    if (state >= d.first_accept) {
-      uint32_t a = state - d.first_accept;
-      for (uint32_t k = d.out_offsets[a]; k < d.out_offsets[a + 1]; k++) { uint32_t r = d.out_rules[k]; bits[r >> 5] |= 1u << (r & 31); }
+    uint32_t col = l1_col(d.mode, lut, m[i]);
+    uint32_t ent = table[(state << d.ncols_log2) + col];
+    if (ent & 0x8000u) { uint32_t aid = d.acc_index[((size_t)state << d.ncols_log2) + col]; for (uint32_t k = d.acc_offsets[aid]; k < d.acc_offsets[aid + 1]; k++) counts[d.acc_factors[k]]++; }
+    state = ent & 0x7fffu;
+  }
+}
+
+// debug: print every full factor with its level-1 window
+void harness_dump_factors(void* p) {
+  Harness* h = (Harness*)p; const Prefilter& P = h->H.pf;
+  for (size_t f = 0; f < P.factors.size(); f++) {
+    const FullFactor& ff = P.factors[f];
+    printf("rule %u len %d win [%d,%d) exact %d : ", ff.rule, ff.len, ff.win_off, ff.win_off + ff.win_len, ff.exact);
+    for (int k = 0; k < ff.len; k++) {
+      int cnt = 0, last = -1; for (int b = 0; b < 256; b++) if ((P.bytesets[(size_t)ff.elem[k] * 8 + (b >> 5)] >> (b & 31)) & 1) { cnt++; last = b; }
+      if (cnt == 1) { if (last >= 33 && last < 127) printf("%c", last); else printf("\\x%02x", last); } else printf("[%d]", cnt);
     }
+    printf("\n");
   }
 }
 

@@ -59,7 +59,7 @@ def test_builtins_on_reference_vectors(oracle, harness_lib):
     h.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("utf8_frac", [0.0, 0.15])
 def test_synthetic_rules_spans_and_prefilter_soundness(oracle, harness_lib, mode, utf8_frac):
     rl = W.make_rules(160)
@@ -70,7 +70,9 @@ def test_synthetic_rules_spans_and_prefilter_soundness(oracle, harness_lib, mode
     buf = data.numpy()
     msgs = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(1200)]
     n_hits = 0
-    cands = [h.candidates(m) for m in msgs]
+    c2 = [h.candidates2(m) for m in msgs]
+    cands = [c[0] | c[1] for c in c2]
+    direct = [c[1] for c in c2]
     for ri, r in enumerate(rules):
         exp = oracle_spans(oracle, oracle.Regex(r[0], "i" if r[1] else ""), msgs)
         for mi, m in enumerate(msgs):
@@ -81,6 +83,8 @@ def test_synthetic_rules_spans_and_prefilter_soundness(oracle, harness_lib, mode
                 if e:
                     n_hits += 1
                     assert ri in cands[mi], ("prefilter missed", r[0], m)
+                else:
+                    assert ri not in direct[mi], ("direct hit without a match", r[0], m)
     assert n_hits >= 200          # the injected tokens were really found
     h.close()
 

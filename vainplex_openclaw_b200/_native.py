@@ -18,7 +18,7 @@ ERR_NAMES = {-1: "INVALID_ARG", -2: "NOT_INITIALIZED", -3: "CUDA", -4: "SYNTAX",
 CG_ERR_SYNTAX, CG_ERR_UNSUPPORTED, CG_ERR_TOO_LARGE, CG_ERR_CAPACITY = -4, -5, -6, -7
 FLAG_ICASE = 1
 CAT = {"credential": 0, "financial": 1, "pii": 2, "custom": 3}
-OPT_DIRECT7, OPT_LUT = 0, 1
+OPT_DIRECT7, OPT_LUT, OPT_FOLD6, OPT_FOLD5 = 0, 1, 2, 3
 
 
 class GovError(RuntimeError):
@@ -34,7 +34,7 @@ class cg_rule(C.Structure):
 class cg_ruleset_info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_rules", "n_ok", "n_always_candidate", "n_sets", "prefilter_mode",
                                           "prefilter_states", "prefilter_cols", "prefilter_factor_len",
-                                          "prefilter_bytes", "program_words")]
+                                          "prefilter_bytes", "program_words", "n_factors", "prefilter_hot_states")]
 
 
 class cg_stats(C.Structure):
@@ -48,6 +48,7 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
                        ("start16", np.uint32), ("end16", np.uint32)])
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
+           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -78,6 +79,9 @@ def load():
     L.cg_device_count.restype = i32
     L.cg_get_stats.argtypes = [C.POINTER(cg_stats)]; L.cg_get_stats.restype = i32
     L.cg_launch_count.restype = u64
+    L.cg_set_profiling.argtypes = [i32]; L.cg_set_profiling.restype = i32
+    L.cg_last_kernel_ms.argtypes = [vp]; L.cg_last_kernel_ms.restype = i32
+    L.cg_scan_work_counters.argtypes = [vp, vp]; L.cg_scan_work_counters.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
     L.cg_ruleset_destroy.argtypes = [vp]; L.cg_ruleset_destroy.restype = None
     L.cg_ruleset_get_info.argtypes = [vp, C.POINTER(cg_ruleset_info)]; L.cg_ruleset_get_info.restype = i32
@@ -137,7 +141,7 @@ def pack(messages) -> tuple[np.ndarray, np.ndarray]:
 class Ruleset:
     """cg_ruleset handle.  rules: iterable of (source:str|bytes, flags:int, category:int)."""
 
-    def __init__(self, rules, options: int = OPT_DIRECT7, strict: bool = False):
+    def __init__(self, rules, options: int = OPT_FOLD6, strict: bool = False):
         L = load()
         if not _inited:
             init()
@@ -196,6 +200,12 @@ class Ruleset:
             check(rc)
             return spans[:ns.value]
 
+    def work_counters(self):
+        """(slots, VM pairs, spans, error flags, level-1 events) of the last completed step."""
+        out = np.zeros(5, dtype=np.uint32)
+        check(load().cg_scan_work_counters(self.handle, out.ctypes.data))
+        return tuple(int(x) for x in out)
+
     def scan_batch_device(self, d_bytes: int, d_off: int, n: int, d_words: int, stream: int = 0):
         check(load().cg_scan_batch_device(self.handle, d_bytes, d_off, n, d_words, stream))
 
@@ -238,6 +248,17 @@ def stats() -> cg_stats:
     s = cg_stats()
     check(load().cg_get_stats(C.byref(s)))
     return s
+
+
+def set_profiling(on: bool):
+    check(load().cg_set_profiling(1 if on else 0))
+
+
+def last_kernel_ms():
+    """(scan_ms, confirm_ms, verify_ms, finalize_ms) of the last completed scan step (profiling must be on)."""
+    out = np.zeros(4, dtype=np.float32)
+    check(load().cg_last_kernel_ms(out.ctypes.data))
+    return tuple(float(x) for x in out)
 
 
 def launch_count() -> int:

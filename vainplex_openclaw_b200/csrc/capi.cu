@@ -28,6 +28,8 @@ struct Ctx {
   int device = 0, sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool profiling = false;
   cg_stats stats{};
   uint64_t launches = 0;
   // grow-only staging in HBM
@@ -68,6 +70,7 @@ struct cg_ruleset {
   ScanWork work{};
   ~cg_ruleset() {
     for (void* p : allocs) cudaFree(p);
+    cudaFree(work.l1_msg); cudaFree(work.l1_pos); cudaFree(work.l1_sc); cudaFree(work.slot_of_msg);
     cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.spans);
   }
 };
@@ -86,9 +89,15 @@ int upload(cg_ruleset* rs, const std::vector<T>& v, const T** out, size_t pad_el
   return CG_OK;
 }
 
-int ensure_work(cg_ruleset* rs, uint32_t slot_cap, uint32_t event_cap, uint32_t span_cap) {
+int ensure_work(cg_ruleset* rs, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_cap, uint32_t event_cap, uint32_t span_cap) {
   ScanWork& w = rs->work;
   if (!w.counters) { CU(cudaMalloc((void**)&w.counters, 16 * sizeof(uint32_t))); }
+  if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
+  if (l1_cap > w.l1_cap) {
+    cudaFree(w.l1_msg); cudaFree(w.l1_pos); cudaFree(w.l1_sc); w.l1_msg = w.l1_pos = w.l1_sc = nullptr; w.l1_cap = 0;
+    CU(cudaMalloc((void**)&w.l1_msg, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_sc, (size_t)l1_cap * 4));
+    w.l1_cap = l1_cap;
+  }
   if (slot_cap > w.slot_cap) {
     cudaFree(w.slot_msg); cudaFree(w.cand); cudaFree(w.hit); w.slot_msg = w.cand = w.hit = nullptr; w.slot_cap = 0;
     size_t rw = rs->dev.rw ? rs->dev.rw : 1;
@@ -102,14 +111,21 @@ int ensure_work(cg_ruleset* rs, uint32_t slot_cap, uint32_t event_cap, uint32_t 
   return CG_OK;
 }
 
-// scan + verify + finalize on device-resident input; asynchronous
+// scan + confirm + verify + finalize on device-resident input; asynchronous
 int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words,
                     bool spans, cudaStream_t st) {
   CU(cudaMemsetAsync(rs->work.counters, 0, 16 * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(rs->work.slot_of_msg, 0xff, (size_t)n * 4, st));
   int k = 0;
-  k += launch_scan(rs->dev, rs->work, d_bytes, d_off, n, d_words, G.sm_count, st);
+  if (G.profiling) cudaEventRecord(G.pev[0], st);
+  k += launch_scan(rs->dev, rs->work, d_bytes, d_off, n, d_words, spans, G.sm_count, st);
+  if (G.profiling) cudaEventRecord(G.pev[1], st);
+  k += launch_confirm(rs->dev, rs->work, d_bytes, d_off, spans, G.sm_count, st);
+  if (G.profiling) cudaEventRecord(G.pev[2], st);
   k += launch_verify(rs->dev, rs->work, d_bytes, d_off, spans, G.sm_count, st);
+  if (G.profiling) cudaEventRecord(G.pev[3], st);
   k += launch_finalize(rs->dev, rs->work, d_words, G.sm_count, st);
+  if (G.profiling) cudaEventRecord(G.pev[4], st);
   G.launches += k; G.stats.kernel_launches += k;
   CU(cudaGetLastError());
   return CG_OK;
@@ -134,10 +150,13 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
     CU(cudaMemsetAsync(G.d_bytes + total, 0, 64, st));
     CU(cudaMemcpyAsync(G.d_off32, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
   }
-  uint32_t slot_cap = std::max<uint32_t>(n, 1), event_cap = std::max<uint32_t>(4 * n, 4096), span_cap = spans ? std::max<uint32_t>(4 * n, 4096) : 1;
+  uint32_t slot_cap = std::max<uint32_t>(n / 4, 4096), event_cap = std::max<uint32_t>(n, 4096), span_cap = spans ? std::max<uint32_t>(n, 4096) : 1;
+  uint32_t l1_cap = std::max<uint32_t>(4 * n, 1u << 16);
+  // keep whatever an earlier step of this rule set needed
+  slot_cap = std::max(slot_cap, rs->work.slot_cap); event_cap = std::max(event_cap, rs->work.event_cap); l1_cap = std::max(l1_cap, rs->work.l1_cap);
   hs->counters.assign(16, 0);
-  for (int attempt = 0; attempt < 8; attempt++) {
-    if ((rc = ensure_work(rs, slot_cap, event_cap, span_cap))) return rc;
+  for (int attempt = 0; attempt < 10; attempt++) {
+    if ((rc = ensure_work(rs, std::max<uint32_t>(n, 1), l1_cap, slot_cap, event_cap, span_cap))) return rc;
     CU(cudaEventRecord(G.ev0, st));
     if (n) { if ((rc = run_scan_device(rs, G.d_bytes, G.d_off32, n, G.d_words, spans, st))) return rc; }
     else CU(cudaMemsetAsync(rs->work.counters, 0, 64, st));
@@ -147,14 +166,15 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
     float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_scan_ms = ms;
     uint32_t flags = hs->counters[3];
     if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
-    if (flags & ERR_EVENT_OVERFLOW) { event_cap = std::max(event_cap * 4, hs->counters[1] + 1024); continue; }
-    if (flags & ERR_SPAN_OVERFLOW) { span_cap = std::max(span_cap * 4, hs->counters[2] + 1024); continue; }
-    if (flags & ERR_SLOT_OVERFLOW) { slot_cap = slot_cap * 2; continue; }
+    if (flags & ERR_L1_OVERFLOW) { l1_cap = std::max<uint32_t>(l1_cap * 2, hs->counters[4] + 1024); continue; }
+    if (flags & ERR_SLOT_OVERFLOW) { slot_cap = std::max<uint32_t>(slot_cap * 4, hs->counters[0] + 1024); continue; }
+    if (flags & ERR_EVENT_OVERFLOW) { event_cap = std::max<uint32_t>(event_cap * 4, hs->counters[1] + 1024); continue; }
+    if (flags & ERR_SPAN_OVERFLOW) { span_cap = std::max<uint32_t>(span_cap * 4, hs->counters[2] + 1024); continue; }
     G.stats.messages_scanned += n; G.stats.bytes_scanned += total;
     G.stats.candidate_events += hs->counters[1]; G.stats.verified_pairs += hs->counters[1];
     return CG_OK;
   }
-  return fail(CG_ERR_CAPACITY, "candidate queue kept overflowing");
+  return fail(CG_ERR_CAPACITY, "candidate queues kept overflowing");
 }
 
 }  // namespace
@@ -183,6 +203,7 @@ int cg_init(int device) {
   G.sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&G.ev0)); CU(cudaEventCreate(&G.ev1));
+  for (int i = 0; i < 5; i++) CU(cudaEventCreate(&G.pev[i]));
   G.ready = true;
   return CG_OK;
 }
@@ -192,8 +213,25 @@ void cg_shutdown(void) {
   if (!G.ready) return;
   cudaStreamSynchronize(G.stream);
   cudaFree(G.d_bytes); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
-  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); cudaStreamDestroy(G.stream);
+  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); cudaStreamDestroy(G.stream);
   G = Ctx();
+}
+
+int cg_set_profiling(int on) { G.profiling = on != 0; return CG_OK; }
+
+int cg_last_kernel_ms(float out_ms[4]) {
+  // device time of scan / confirm / verify / finalize of the most recent *completed* scan step
+  if (!G.ready || !out_ms) return fail(CG_ERR_INVALID_ARG, "not initialised");
+  for (int i = 0; i < 4; i++) { out_ms[i] = 0; if (cudaEventElapsedTime(&out_ms[i], G.pev[i], G.pev[i + 1]) != cudaSuccess) { cudaGetLastError(); return fail(CG_ERR_CUDA, "profiling events not recorded / not complete"); } }
+  return CG_OK;
+}
+
+int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out5[5]) {
+  // [0] slots (messages with confirmed candidates), [1] (message, rule) pairs sent to the VM, [2] spans,
+  // [3] error flags, [4] level-1 accept events -- of the last completed step
+  if (!rs || !out5 || !rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
+  CU(cudaMemcpy(out5, rs->work.counters, 20, cudaMemcpyDeviceToHost));
+  return CG_OK;
 }
 
 int cg_get_stats(cg_stats* out) { if (!out) return fail(CG_ERR_INVALID_ARG, "null"); *out = G.stats; return CG_OK; }
@@ -216,11 +254,12 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   rs->category.resize(n_rules);
   for (uint32_t i = 0; i < n_rules; i++) { src[i] = RuleSrc{rules[i].source, rules[i].source_len, rules[i].flags}; rs->category[i] = rules[i].category; }
   ImageOptions io;
-  io.mode = (options & CG_OPT_PREFILTER_LUT) ? 1 : 0;
-  if (const char* e = getenv("CG_PREFILTER_MODE")) io.mode = atoi(e) ? 1 : 0;
+  io.mode = (int)(options & 3u);
+  if (const char* e = getenv("CG_PREFILTER_MODE")) io.mode = atoi(e);
   if (const char* e = getenv("CG_PREFILTER_KB")) io.budget_bytes = (size_t)atoi(e) * 1024;
   if (const char* e = getenv("CG_PREFILTER_CLASSES")) io.max_classes = atoi(e);
-  if (const char* e = getenv("CG_FACTOR_LEN")) io.max_factor_len = atoi(e);
+  if (const char* e = getenv("CG_WINDOW")) io.max_window = atoi(e);
+  if (const char* e = getenv("CG_MAX_STATES")) io.max_states = atoi(e);
   std::string perr;
   if (!build_host_image(src.data(), n_rules, io, &rs->host, &perr)) return fail(CG_ERR_TOO_LARGE, perr);
   HostImage& H = rs->host;
@@ -241,9 +280,13 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   const uint8_t* d_image; if ((rc = upload(rs.get(), image, &d_image, 16))) return rc;
   d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode;
   d.ncols_log2 = 0; while ((1 << d.ncols_log2) < P.ncols) d.ncols_log2++;
-  d.nstates = (uint32_t)P.nstates; d.first_accept = (uint32_t)P.first_accept;
-  if ((rc = upload(rs.get(), P.out_offsets, &d.out_offsets))) return rc;
-  if ((rc = upload(rs.get(), P.out_rules, &d.out_rules))) return rc;
+  d.nstates = (uint32_t)P.nstates; d.hot_states = H.hot_states;
+  if ((rc = upload(rs.get(), P.table, &d.table_full, 64))) return rc;
+  if ((rc = upload(rs.get(), P.acc_index, &d.acc_index))) return rc;
+  if ((rc = upload(rs.get(), P.acc_offsets, &d.acc_offsets))) return rc;
+  if ((rc = upload(rs.get(), P.acc_factors, &d.acc_factors))) return rc;
+  if ((rc = upload(rs.get(), H.factor_words, &d.factors, 16))) return rc;
+  if ((rc = upload(rs.get(), P.bytesets, &d.bytesets, 8))) return rc;
   if ((rc = upload(rs.get(), P.always_rules, &d.always_rules))) return rc;
   d.n_always = (uint32_t)P.always_rules.size();
   if ((rc = upload(rs.get(), prog, &d.prog))) return rc;
@@ -252,6 +295,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), ranges, &d.set_ranges, 8))) return rc;
   if ((rc = upload(rs.get(), first, &d.rule_first, 8))) return rc;
   d.n_rules = n_rules; d.rw = (n_rules + 31) / 32; if (d.rw == 0) d.rw = 1;
+  d.max_prog_len = 0; for (uint32_t i = 0; i < n_rules; i++) d.max_prog_len = std::max(d.max_prog_len, prog_off[i + 1] - prog_off[i]);
   *out = rs.release();
   return CG_OK;
 }
@@ -264,8 +308,8 @@ int cg_ruleset_get_info(const cg_ruleset* rs, cg_ruleset_info* o) {
   o->n_rules = (uint32_t)rs->host.rules.size();
   for (auto& r : rs->host.rules) if (r.status == RULE_OK) o->n_ok++;
   o->n_always_candidate = (uint32_t)rs->host.pf.always_rules.size(); o->n_sets = rs->n_sets;
-  o->prefilter_mode = (uint32_t)rs->host.pf.mode; o->prefilter_states = (uint32_t)rs->host.pf.nstates; o->prefilter_cols = (uint32_t)rs->host.pf.ncols;
-  o->prefilter_factor_len = (uint32_t)rs->host.pf.factor_len; o->prefilter_bytes = rs->dev.image_bytes; o->program_words = rs->program_words;
+  o->prefilter_mode = (uint32_t)rs->host.pf.mode; o->prefilter_states = (uint32_t)rs->host.pf.nstates; o->prefilter_hot_states = rs->host.hot_states; o->prefilter_cols = (uint32_t)rs->host.pf.ncols;
+  o->prefilter_factor_len = (uint32_t)rs->host.pf.window_min | ((uint32_t)rs->host.pf.window_max << 8); o->n_factors = (uint32_t)rs->host.pf.factors.size(); o->prefilter_bytes = rs->dev.image_bytes; o->program_words = rs->program_words;
   return CG_OK;
 }
 
@@ -291,6 +335,7 @@ int cg_scan_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets,
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hs.slot_msg[a] < hs.slot_msg[b]; });
     for (uint32_t oi = 0; oi < n_slots; oi++) {
       uint32_t s = order[oi];
+      if (hs.slot_msg[s] == 0xffffffffu) continue;
       for (uint32_t k = 0; k < rw; k++) {
         uint32_t v = hs.hit[(size_t)s * rw + k];
         while (v) { uint32_t b = __builtin_ctz(v); v &= v - 1; if (out_hits && nh < hits_cap) { out_hits[nh].msg = hs.slot_msg[s]; out_hits[nh].rule = k * 32 + b; } nh++; }
@@ -354,7 +399,8 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
   if (!rs || !d_bytes || !d_offsets || !d_out_words) return fail(CG_ERR_INVALID_ARG, "null argument");
-  int rc = ensure_work(rs, std::max<uint32_t>(n, 1), std::max<uint32_t>(4 * n, 4096), 1);
+  int rc = ensure_work(rs, std::max<uint32_t>(n, 1), std::max<uint32_t>(std::max<uint32_t>(4 * n, 1u << 16), rs->work.l1_cap), std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), rs->work.slot_cap),
+                       std::max<uint32_t>(std::max<uint32_t>(n, 4096), rs->work.event_cap), 1);
   if (rc) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
   if (!n) return CG_OK;

@@ -7,40 +7,52 @@ namespace cg {
 
 // Everything the scan / verify kernels need to know about a compiled rule set (device pointers).
 struct DevRuleset {
-  const uint8_t* image;          // [lut 256 B][table nstates*ncols u16], 16-byte aligned, size % 16 == 0
+  const uint8_t* image;          // [lut 256 B][level-1 table nstates*ncols u16], 16-byte aligned, size % 16 == 0
   uint32_t image_bytes;
-  uint32_t mode;                 // 0 = direct 7-bit columns, 1 = LUT columns
+  uint32_t mode;                 // 0 = direct 7-bit columns, 1 = LUT columns, 2 = folded 6-bit, 3 = folded 5-bit columns
+  uint32_t max_prog_len;         // longest Pike program of the set (picks the VM capacity)
   uint32_t ncols_log2;
-  uint32_t nstates, first_accept;
-  const uint32_t* out_offsets;   // CSR over accept states
-  const uint32_t* out_rules;
+  uint32_t nstates;
+  uint32_t hot_states;           // rows [0, hot_states) are in the shared-memory image, the rest only in table_full
+  const uint16_t* table_full;    // complete level-1 table in HBM (L2-resident)
+  const uint32_t* acc_index;     // nstates*ncols: accept id of an accepting transition
+  const uint32_t* acc_offsets;   // CSR over accept ids -> factor ids
+  const uint32_t* acc_factors;
+  const uint32_t* factors;       // 10 words per full factor: rule, len|win_off<<8|win_len<<16|exact<<24, 16 x u16 set ids
+  const uint32_t* bytesets;      // 8 words per 256-bit byte set
   const uint32_t* always_rules;  // candidates for every message
   uint32_t n_always;
   const uint32_t* prog;          // all Pike programs, concatenated
   const uint32_t* rule_prog_off; // n_rules + 1
-  const uint32_t* sets;          // 6 words per set: ascii[4], range_off, n_ranges
+  const uint32_t* sets;          // 6 words per unit set: ascii[4], range_off, n_ranges
   const uint16_t* set_ranges;    // inclusive lo,hi pairs
   const uint32_t* rule_first;    // 8 words per rule: first-byte bitmap
   uint32_t n_rules;
   uint32_t rw;                   // bitmap words per slot = ceil(n_rules / 32)
 };
 
-// Per-call scratch in HBM.  A "slot" is one message that produced at least one candidate.
+// Per-call scratch in HBM.  A "slot" is one message with at least one confirmed candidate.
 struct ScanWork {
-  uint32_t* counters;            // [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags
+  uint32_t* counters;            // [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (level-1 accept events)
+  uint32_t* l1_msg;              // [l1_cap] level-1 accept events queued by scan_kernel: message,
+  uint32_t* l1_pos;              //          byte offset of the accepting byte inside the message,
+  uint32_t* l1_sc;               //          state << 8 | column of the accepting transition (0xffffffff = "always" rules)
+  uint32_t* slot_of_msg;         // [n] 0xffffffff = none yet (reset per step)
   uint32_t* slot_msg;            // [slot_cap]
   uint32_t* cand;                // [slot_cap * rw]  candidate (msg,rule) pairs already queued
   uint32_t* hit;                 // [slot_cap * rw]  verified pairs
-  uint2* events;                 // [event_cap]  (slot, rule)
+  uint2* events;                 // [event_cap]  (slot, rule) for the Pike VM
   uint32_t* spans;               // [span_cap * 6] msg, rule, start_byte, end_byte, start16, end16
-  uint32_t slot_cap, event_cap, span_cap;
+  uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap;
 };
 
-enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16 };
+enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32 };
 
 // launchers (all asynchronous on `stream`); return the number of kernels launched
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
-                uint64_t* d_words, int sm_count, cudaStream_t stream);
+                uint64_t* d_words, bool want_spans, int sm_count, cudaStream_t stream);
+int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
+                   bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream);
 int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, int sm_count, cudaStream_t stream);

@@ -59,18 +59,31 @@ CG_HD bool is_word(int u) { return (u >= '0' && u <= '9') || (u >= 'A' && u <= '
 
 constexpr int kVmStack = 192;
 
-struct VM {
+// VM working storage.  LocalStore: plain per-thread arrays (host harness, large programs).
+// SmemStore (scan_kernels.cu): thread-interleaved shared memory for the common small programs.
+template <int CAP>
+struct LocalStore {
+  static constexpr uint32_t cap = CAP;
+  uint16_t mark_[CAP]; uint16_t pcs_[2][CAP]; uint32_t sts_[2][CAP]; uint16_t stk_[kVmStack];
+  CG_HD uint16_t& mark(uint32_t i) { return mark_[i]; }
+  CG_HD uint16_t& pc(int L, uint32_t i) { return pcs_[L][i]; }
+  CG_HD uint32_t& st(int L, uint32_t i) { return sts_[L][i]; }
+  CG_HD uint16_t& stk(uint32_t i) { return stk_[i]; }
+};
+
+template <class Store>
+struct VMS {
   const DevRuleset& rs; const uint32_t* prog; uint32_t plen;
-  uint16_t mark[kMaxProgLen]; uint16_t gen;
-  uint16_t pcs[2][kMaxProgLen]; uint32_t sts[2][kMaxProgLen]; uint32_t cnt[2];
-  uint16_t stk[kVmStack];
+  Store S; uint16_t gen; uint32_t cnt[2];
   uint32_t err;
   // best match of the current search
   bool matched; uint32_t m_start, m_end, m_end16; int m_prev;
 
-  CG_HD_NOINLINE VM(const DevRuleset& r) : rs(r), gen(0), err(0) {}
+  static CG_HD uint32_t capacity() { return Store::cap; }
+  CG_HD_NOINLINE VMS(const DevRuleset& r) : rs(r), gen(0), err(0) {}
+  CG_HD_NOINLINE VMS(const DevRuleset& r, const Store& s) : rs(r), S(s), gen(0), err(0) {}
 
-  CG_HD_NOINLINE void bump_gen() { if (++gen >= 0x7fff) { for (uint32_t k = 0; k < plen; k++) mark[k] = 0; gen = 1; } }
+  CG_HD_NOINLINE void bump_gen() { if (++gen >= 0x7fff) { for (uint32_t k = 0; k < plen; k++) S.mark(k) = 0; gen = 1; } }
 
   // Closure from pc0 at a position whose context is (prev, next, byte `pos`, unit index `upos`):
   // a depth-first walk in priority order.  SPLIT nodes carry a per-step mark that is IN-PROGRESS
@@ -84,24 +97,24 @@ struct VM {
   // then cut every lower-priority thread).
   CG_HD_NOINLINE bool add(int L, uint32_t pc0, uint32_t start, int prev, int next, uint32_t pos, uint32_t upos) {
     const uint16_t INPROG = (uint16_t)(gen * 2), DONE = (uint16_t)(gen * 2 + 1);
-    int sp = 0; stk[sp++] = (uint16_t)pc0;
+    int sp = 0; S.stk(sp++) = (uint16_t)pc0;
     while (sp) {
-      uint32_t x = stk[--sp];
-      if (x & 0x8000u) { mark[x & 0x7fffu] = DONE; continue; }
+      uint32_t x = S.stk(--sp);
+      if (x & 0x8000u) { S.mark(x & 0x7fffu) = DONE; continue; }
       uint32_t pc = x;
       for (;;) {
         uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
         bool go = false;
         switch (op) {
           case OP_SPLIT_NEXT: case OP_SPLIT_JUMP:
-            if (mark[pc] == DONE) break;
-            mark[pc] = INPROG;
-            if (sp + 2 <= kVmStack) { stk[sp++] = (uint16_t)(0x8000u | pc); stk[sp++] = (uint16_t)(op == OP_SPLIT_NEXT ? arg : pc + 1); }
+            if (S.mark(pc) == DONE) break;
+            S.mark(pc) = INPROG;
+            if (sp + 2 <= kVmStack) { S.stk(sp++) = (uint16_t)(0x8000u | pc); S.stk(sp++) = (uint16_t)(op == OP_SPLIT_NEXT ? arg : pc + 1); }
             else err |= ERR_VM_STACK;
             pc = op == OP_SPLIT_NEXT ? pc + 1 : arg; go = true; break;
           case OP_JMP: pc = arg; go = true; break;
-          case OP_JMP_BACK: if (mark[arg] != INPROG) { pc = arg; go = true; } break;
-          case OP_EMPTYCHK: if (mark[arg] != INPROG) { pc++; go = true; } break;
+          case OP_JMP_BACK: if (S.mark(arg) != INPROG) { pc = arg; go = true; } break;
+          case OP_EMPTYCHK: if (S.mark(arg) != INPROG) { pc++; go = true; } break;
           case OP_BOL: if (pos == 0) { pc++; go = true; } break;
           case OP_EOL: if (next < 0) { pc++; go = true; } break;
           case OP_WORDB: if (is_word(prev) != is_word(next)) { pc++; go = true; } break;
@@ -114,10 +127,10 @@ struct VM {
             matched = true; m_start = start; m_end = pos; m_end16 = upos; m_prev = prev;
             return true;
           default:   // consuming instruction: queue the thread once per step
-            if (mark[pc] != DONE) {
-              mark[pc] = DONE;
+            if (S.mark(pc) != DONE) {
+              S.mark(pc) = DONE;
               uint32_t k = cnt[L];
-              if (k < kMaxProgLen) { pcs[L][k] = (uint16_t)pc; sts[L][k] = start; cnt[L] = k + 1; } else err |= ERR_VM_LIST;
+              if (k < Store::cap) { S.pc(L, k) = (uint16_t)pc; S.st(L, k) = start; cnt[L] = k + 1; } else err |= ERR_VM_LIST;
             }
             break;
         }
@@ -153,18 +166,25 @@ struct VM {
       uint32_t npos = cn.pos, nupos = upos + 1;
       bool cut = false;
       for (uint32_t k = 0; k < cnt[L] && !cut; k++) {
-        uint32_t pc = pcs[L][k]; uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
+        uint32_t pc = S.pc(L, k); uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
         bool ok = op == OP_CHAR ? ((uint32_t)cur == arg)
                 : op == OP_ANY ? !(cur == 0x0a || cur == 0x0d || cur == 0x2028 || cur == 0x2029)
                 : in_set(rs, arg, cur);
-        if (ok) cut = add(N, pc + 1, sts[L][k], cur, nxt, npos, nupos);
+        if (ok) cut = add(N, pc + 1, S.st(L, k), cur, nxt, npos, nupos);
       }
-      if (!cut && !matched) add(N, 0, npos, cur, nxt, npos, nupos);   // new lowest-priority start
+      // new lowest-priority start at npos -- skipped when the unit there cannot begin a match
+      // (first-unit filter; a start thread that cannot consume its first unit dies immediately,
+      // and rules that can match the empty string have an all-ones filter)
+      if (!cut && !matched && !(nxt >= 0 && nxt < 128 && !((first[nxt >> 5] >> (nxt & 31)) & 1u)))
+        add(N, 0, npos, cur, nxt, npos, nupos);
       L = N; prev = cur; pos = npos; upos = nupos; c = cn; cn = cnn; cur = nxt;
     }
     return matched;
   }
 };
+
+template <int CAP> using VMT = VMS<LocalStore<CAP>>;
+using VM = VMT<kMaxProgLen>;
 
 // number of UTF-16 units in m[0, upto)
 CG_HD_NOINLINE uint32_t count_units(const uint8_t* __restrict__ m, uint32_t len, uint32_t upto) {
@@ -185,11 +205,12 @@ CG_HD_NOINLINE Cursor cursor_at(const uint8_t* __restrict__ m, uint32_t len, uin
 
 // All matches of one rule in one message -- the exec loop of registry.ts:225-236 (SPANS) or just
 // RegExp.test (context.ts:9-25, !SPANS).  sink.span(start_byte, end_byte, start16, end16).
-template <bool SPANS, class Sink>
-CG_HD_NOINLINE bool run_rule(VM& vm, const DevRuleset& rs, uint32_t rule, const uint8_t* __restrict__ m, uint32_t len, Sink& sink) {
+template <bool SPANS, class VMX, class Sink>
+CG_HD_NOINLINE bool run_rule(VMX& vm, const DevRuleset& rs, uint32_t rule, const uint8_t* __restrict__ m, uint32_t len, Sink& sink) {
   vm.prog = rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
   if (vm.plen == 0) return false;                     // rule failed to compile: never matches
-  for (uint32_t k = 0; k < vm.plen; k++) vm.mark[k] = 0;
+  if (vm.plen > VMX::capacity()) { vm.err |= ERR_VM_LIST; return false; }
+  for (uint32_t k = 0; k < vm.plen; k++) vm.S.mark(k) = 0;
   vm.gen = 0;
   const uint32_t* first = rs.rule_first + (size_t)rule * 8;
   uint32_t from = 0, from16 = 0; int prev = -1; Cursor c{0, 0};

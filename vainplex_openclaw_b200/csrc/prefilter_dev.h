@@ -1,0 +1,50 @@
+// prefilter_dev.h -- level-2 of the prefilter: exact confirmation of a full factor at a position
+// flagged by the level-1 DFA.  CG_HD so that tests/native/vm_harness.cpp restates the scan
+// kernel's candidate logic with the very same code.
+#pragma once
+#include <cstdint>
+#include "kernels.h"
+#include "pike_vm.h"   // CG_HD macros
+
+namespace cg {
+
+CG_HD uint32_t l1_col(uint32_t mode, const uint8_t* __restrict__ lut, uint32_t b) {
+  return mode == 0 ? (b & 0x7fu) : mode == 2 ? ((b & 0x1fu) | ((b >> 1) & 0x20u)) : mode == 3 ? (b & 0x1fu) : (uint32_t)lut[b];
+}
+
+CG_HD bool byte_in_set(const DevRuleset& rs, uint32_t sid, uint32_t b) {
+  return (rs.bytesets[(size_t)sid * 8 + (b >> 5)] >> (b & 31)) & 1u;
+}
+
+// Does factor `fw` occur in message m[0,len) with its level-1 window ending at byte `pend`?
+CG_HD_NOINLINE bool confirm_factor(const DevRuleset& rs, const uint32_t* __restrict__ fw, const uint8_t* __restrict__ m,
+                                   uint32_t len, uint32_t pend) {
+  const uint32_t meta = fw[1], flen = meta & 0xff, wend = ((meta >> 8) & 0xff) + ((meta >> 16) & 0xff);   // window end (exclusive) inside the factor
+  if (pend + 1 < wend) return false;
+  const uint32_t t0 = pend + 1 - wend;                 // message offset of factor element 0
+  if (t0 + flen > len) return false;
+  // elements after the window first (most likely to fail), then the rest (the window was only
+  // matched through the folded level-1 alphabet, so it is re-checked exactly as well)
+  for (uint32_t i = 0; i < flen; i++) {
+    uint32_t k = wend + i; if (k >= flen) k -= flen;
+    uint32_t sid = (fw[2 + (k >> 1)] >> (16 * (k & 1))) & 0xffffu;
+    if (!byte_in_set(rs, sid, m[t0 + k])) return false;
+  }
+  return true;
+}
+
+// An accepting level-1 transition (state, col) was taken on the byte at message offset `pend`.
+template <class Sink>
+CG_HD_NOINLINE void l1_accept(const DevRuleset& rs, uint32_t state, uint32_t col, const uint8_t* __restrict__ m, uint32_t len,
+                              uint32_t pend, bool want_spans, Sink& sink) {
+  const uint32_t aid = rs.acc_index[((size_t)state << rs.ncols_log2) + col];
+  if (aid == 0xffffffffu) return;
+  for (uint32_t k = rs.acc_offsets[aid]; k < rs.acc_offsets[aid + 1]; k++) {
+    const uint32_t* fw = rs.factors + (size_t)rs.acc_factors[k] * 10;
+    if (confirm_factor(rs, fw, m, len, pend)) {
+      if ((fw[1] >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0]);
+    }
+  }
+}
+
+}  // namespace cg

@@ -457,20 +457,33 @@ struct Compiler {
     double s = 0; for (auto& q : f) { if (q.empty()) return 1.0; s += seq_prob(q); } return std::min(s, 1.0);
   }
 
-  // byte-level view of one unit node; returns false when the node has non-ASCII members (no byte info)
-  bool unit_bytes(int n, std::vector<FactorSeq>* seqs) const {
+  // byte-level view of one unit node.  ASCII-only sets are one exact byte set; a single non-ASCII
+  // literal is its UTF-8 bytes; any other set with members >= 0x80 is over-approximated by the three
+  // byte shapes one decoded unit can have (1 byte; 2 bytes incl. half an astral pair or a truncated
+  // sequence; 3 bytes) -- sound for ill-formed input too, since every U+FFFD the decoder emits
+  // covers 1-3 bytes of exactly these shapes.  *tight is cleared when the view over-approximates.
+  bool unit_bytes(int n, std::vector<FactorSeq>* seqs, bool* tight) const {
     Ranges r = unit_ranges(n);
+    *tight = true;
     bool ascii_only = true; for (auto& p : r) if (p.second >= 128) ascii_only = false;
-    if (ascii_only) { ByteSet b; for (auto& p : r) for (int c = p.first; c <= p.second; c++) b.set(c); if (b.empty()) return false; seqs->push_back({b}); return true; }
+    ByteSet lo; for (auto& p : r) for (int c = p.first; c <= std::min(p.second, 127); c++) lo.set(c);
+    if (ascii_only) { if (lo.empty()) return false; seqs->push_back({lo}); return true; }
     if (r.size() == 1 && r[0].first == r[0].second) {      // single non-ASCII literal: its UTF-8 bytes
       int c = r[0].first;
-      if (c >= 0xd800 && c <= 0xdfff) return false;
-      FactorSeq s; ByteSet b0, b1, b2;
-      if (c < 0x800) { b0.set(0xc0 | (c >> 6)); b1.set(0x80 | (c & 0x3f)); s = {b0, b1}; }
-      else { b0.set(0xe0 | (c >> 12)); b1.set(0x80 | ((c >> 6) & 0x3f)); b2.set(0x80 | (c & 0x3f)); s = {b0, b1, b2}; }
-      seqs->push_back(s); return true;
+      if (!(c >= 0xd800 && c <= 0xdfff)) {
+        FactorSeq s; ByteSet b0, b1, b2;
+        if (c < 0x800) { b0.set(0xc0 | (c >> 6)); b1.set(0x80 | (c & 0x3f)); s = {b0, b1}; }
+        else { b0.set(0xe0 | (c >> 12)); b1.set(0x80 | ((c >> 6) & 0x3f)); b2.set(0x80 | (c & 0x3f)); s = {b0, b1, b2}; }
+        seqs->push_back(s); return true;
+      }
     }
-    return false;
+    *tight = false;
+    ByteSet one = lo, hi, cont, lead3;
+    for (int b = 0x80; b < 0x100; b++) { one.set(b); hi.set(b); }
+    for (int b = 0x80; b < 0xc0; b++) cont.set(b);
+    for (int b = 0xe0; b <= 0xf4; b++) lead3.set(b);
+    seqs->push_back({one}); seqs->push_back({hi, cont}); seqs->push_back({lead3, cont, cont});
+    return true;
   }
 
   static void consider(std::vector<FactorSeq>& best, bool& have, const std::vector<FactorSeq>& cand) {
@@ -484,8 +497,8 @@ struct Compiler {
     Info I;
     switch (nd.type) {
       case T_CHAR: case T_ANY: case T_SET: {
-        std::vector<FactorSeq> s;
-        if (unit_bytes(n, &s)) { I.has_exact = true; I.exact = s; I.is_exact_tight = true; I.has_factors = true; I.factors = s; }
+        std::vector<FactorSeq> s; bool tight = true;
+        if (unit_bytes(n, &s, &tight)) { I.has_exact = true; I.exact = s; I.is_exact_tight = tight; I.has_factors = true; I.factors = s; }
         return I;
       }
       case T_EMPTY: I.has_exact = true; I.exact = {FactorSeq{}}; I.is_exact_tight = true; return I;
@@ -552,21 +565,28 @@ struct Compiler {
                 piece = {FactorSeq{}}; has_piece = true; breaks_after = true;
                 int copies = std::min(N(kk).min, (int)kMaxRunLen);
                 for (int q = 0; q < copies && has_piece; q++) {
-                  std::vector<FactorSeq> nx;
-                  for (auto& a : piece) for (auto& e : b.exact) { FactorSeq s = a; s.insert(s.end(), e.begin(), e.end()); nx.push_back(s); }
-                  if (nx.size() > kMaxSeqs || (!nx.empty() && nx[0].size() > kMaxRunLen)) { breaks_after = true; break; }
+                  std::vector<FactorSeq> nx; bool full = false;
+                  for (auto& a : piece) for (auto& e : b.exact) { FactorSeq s = a; s.insert(s.end(), e.begin(), e.end()); if (s.size() >= kMaxRunLen) { s.resize(kMaxRunLen); full = true; } nx.push_back(s); }
+                  if (nx.size() > kMaxSeqs) break;
                   piece.swap(nx);
+                  if (full) break;
                 }
               }
             }
             (void)kn;
           }
           if (!has_piece) { close_run(); run_tight = false; continue; }
-          // extend the run by the cross product, or restart it when it would grow too much
-          std::vector<FactorSeq> nx; bool ok = true;
-          for (auto& a : run) { for (auto& e : piece) { FactorSeq s = a; s.insert(s.end(), e.begin(), e.end()); if (s.size() > kMaxRunLen) { ok = false; break; } nx.push_back(s); } if (!ok) break; }
-          if (!ok || nx.size() > kMaxSeqs) { all_exact = false; close_run(); run = piece; if (run.size() > kMaxSeqs) run = {FactorSeq{}}; }
+          // extend the run by the cross product; a piece that would overflow the element limit is
+          // cut (a prefix of a necessary factor is still necessary) and the run is closed there
+          std::vector<FactorSeq> nx; bool cut = false;
+          for (auto& a : run) for (auto& e : piece) {
+            FactorSeq s = a; s.insert(s.end(), e.begin(), e.end());
+            if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; }
+            nx.push_back(s);
+          }
+          if (nx.size() > kMaxSeqs) { all_exact = false; close_run(); run = piece; if (run.size() > kMaxSeqs) run = {FactorSeq{}}; for (auto& s : run) if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; } }
           else run.swap(nx);
+          if (cut) { all_exact = false; close_run(); }
           if (breaks_after) { all_exact = false; close_run(); }
         }
         if (all_exact) { I.has_exact = true; I.exact = run; I.is_exact_tight = tight && run_tight; }
@@ -640,106 +660,168 @@ CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
   return out;
 }
 
-// ------------------------------------------------------------------ prefilter DFA
+// ------------------------------------------------------------------ prefilter (level-1 Mealy DFA + full factors)
 
 namespace {
-struct Item { uint32_t seq; uint16_t k; bool operator<(const Item& o) const { return seq != o.seq ? seq < o.seq : k < o.k; } bool operator==(const Item& o) const { return seq == o.seq && k == o.k; } };
-struct StateKey { std::vector<Item> items; std::vector<uint32_t> done; bool operator<(const StateKey& o) const { return items != o.items ? items < o.items : done < o.done; } };
+struct Item { uint32_t pat; uint16_t k; bool operator<(const Item& o) const { return pat != o.pat ? pat < o.pat : k < o.k; } bool operator==(const Item& o) const { return pat == o.pat && k == o.k; } };
+using ColSeq = std::vector<uint64_t>;    // one 64-bit column mask per element (ncols <= 64) or two words for 128 columns
+
+struct L1Pattern { std::vector<std::vector<bool>> cols; std::vector<uint32_t> factors; };
+
+struct Dfa {
+  int nstates = 0;
+  std::vector<uint16_t> table; std::vector<uint32_t> acc_index, acc_offsets, acc_factors;
+};
+
+// subset construction; returns false when the state budget is exceeded
+static bool build_dfa(const std::vector<L1Pattern>& pats, int ncols, int max_states, Dfa* out) {
+  std::map<std::vector<Item>, int> ids; std::vector<std::vector<Item>> states;
+  auto intern = [&](std::vector<Item>&& k) { auto it = ids.find(k); if (it != ids.end()) return it->second; int id = (int)states.size(); ids.emplace(k, id); states.push_back(std::move(k)); return id; };
+  std::vector<std::vector<uint32_t>> start_by_col(ncols);
+  for (uint32_t q = 0; q < pats.size(); q++) for (int c = 0; c < ncols; c++) if (pats[q].cols[0][c]) start_by_col[c].push_back(q);
+  std::map<std::vector<uint32_t>, uint32_t> acc_ids; std::vector<std::vector<uint32_t>> acc_sets;
+  std::vector<uint16_t> table; std::vector<uint32_t> acc_index;
+  intern({});
+  for (size_t s = 0; s < states.size(); s++) {
+    std::vector<Item> cur = states[s];
+    for (int c = 0; c < ncols; c++) {
+      std::vector<Item> nk; std::vector<uint32_t> done;
+      for (auto& it : cur) if (pats[it.pat].cols[it.k][c]) { if (it.k + 1u == pats[it.pat].cols.size()) done.push_back(it.pat); else nk.push_back({it.pat, (uint16_t)(it.k + 1)}); }
+      for (uint32_t q : start_by_col[c]) { if (pats[q].cols.size() == 1) done.push_back(q); else nk.push_back({q, 1}); }
+      std::sort(nk.begin(), nk.end()); nk.erase(std::unique(nk.begin(), nk.end()), nk.end());
+      int nid = intern(std::move(nk));
+      if ((int)states.size() > max_states || states.size() > 32767) return false;
+      uint32_t aid = 0xffffffffu;
+      if (!done.empty()) {
+        std::vector<uint32_t> fs; for (uint32_t q : done) fs.insert(fs.end(), pats[q].factors.begin(), pats[q].factors.end());
+        std::sort(fs.begin(), fs.end()); fs.erase(std::unique(fs.begin(), fs.end()), fs.end());
+        auto it = acc_ids.find(fs);
+        if (it == acc_ids.end()) { it = acc_ids.emplace(fs, (uint32_t)acc_sets.size()).first; acc_sets.push_back(fs); }
+        aid = it->second;
+      }
+      table.push_back((uint16_t)(nid | (aid != 0xffffffffu ? 0x8000 : 0)));
+      acc_index.push_back(aid);
+    }
+  }
+  out->nstates = (int)states.size(); out->table.swap(table); out->acc_index.swap(acc_index);
+  out->acc_offsets.assign(1, 0); out->acc_factors.clear();
+  for (auto& fs : acc_sets) { out->acc_factors.insert(out->acc_factors.end(), fs.begin(), fs.end()); out->acc_offsets.push_back((uint32_t)out->acc_factors.size()); }
+  return true;
 }
+}  // namespace
 
 bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* pf, std::string* err) {
   Prefilter& P = *pf;
   P = Prefilter();
   P.mode = opt.mode;
-  // gather factors
-  struct Seq { FactorSeq s; uint32_t rule; };
-  std::vector<Seq> all;
+  // ---- full factors + deduplicated byte sets
+  std::map<ByteSet, uint16_t> set_ids;
+  auto set_id = [&](const ByteSet& b) {
+    auto it = set_ids.find(b); if (it != set_ids.end()) return it->second;
+    uint16_t id = (uint16_t)set_ids.size(); set_ids.emplace(b, id);
+    for (int k = 0; k < 8; k++) P.bytesets.push_back((uint32_t)(b.w[k >> 1] >> (32 * (k & 1))));
+    return id;
+  };
+  std::vector<FactorSeq> seqs;          // parallel to P.factors
   for (size_t r = 0; r < rules.size(); r++) {
     if (rules[r].status != RULE_OK) continue;
     if (rules[r].factors.empty()) { P.always_rules.push_back((uint32_t)r); continue; }
-    for (auto& f : rules[r].factors) all.push_back({f, (uint32_t)r});
+    for (auto& f : rules[r].factors) {
+      FullFactor ff{}; ff.rule = (uint32_t)r; ff.len = (uint8_t)std::min<size_t>(f.size(), kMaxFactorElems);
+      ff.exact = (rules[r].factors_exact && f.size() <= (size_t)kMaxFactorElems) ? 1 : 0;
+      for (int k = 0; k < ff.len; k++) ff.elem[k] = set_id(f[k]);
+      P.factors.push_back(ff); seqs.push_back(FactorSeq(f.begin(), f.begin() + ff.len));
+    }
   }
-  // column mapping
-  int ncols;
-  uint8_t colmap[256];
-  if (opt.mode == 0) {
-    ncols = 128; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)(b & 0x7f);
-  } else {
-    // partition refinement of the byte alphabet by every distinct element set
-    std::set<ByteSet> distinct; for (auto& q : all) for (auto& e : q.s) distinct.insert(e);
+  // ---- column mapping
+  int ncols; uint8_t colmap[256];
+  if (opt.mode == 0) { ncols = 128; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)(b & 0x7f); }
+  else if (opt.mode == 2) { ncols = 64; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)((b & 0x1f) | ((b >> 1) & 0x20)); }
+  else if (opt.mode == 3) { ncols = 32; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)(b & 0x1f); }
+  else {
+    std::set<ByteSet> distinct; for (auto& q : seqs) for (auto& e : q) distinct.insert(e);
     std::vector<int> cls(256, 0); int ncls = 1;
     for (auto& bs : distinct) {
       std::map<std::pair<int, bool>, int> remap; std::vector<int> nc(256);
       for (int b = 0; b < 256; b++) { auto key = std::make_pair(cls[b], bs.has(b)); auto it = remap.find(key); if (it == remap.end()) it = remap.emplace(key, (int)remap.size()).first; nc[b] = it->second; }
       cls.swap(nc); ncls = (int)remap.size();
     }
-    // merge the lightest classes until they fit (merging only ever widens element sets => still sound)
-    while (ncls > opt.max_classes) {
+    while (ncls > opt.max_classes) {   // merge the two lightest classes (only ever widens sets => still sound)
       std::vector<double> w(ncls, 0); for (int b = 0; b < 256; b++) w[cls[b]] += Compiler::byte_weight(b);
-      int a = -1, c = -1; for (int k = 0; k < ncls; k++) { if (a < 0 || w[k] < w[a]) { c = a; a = k; } else if (c < 0 || w[k] < w[c]) c = k; }
-      for (int b = 0; b < 256; b++) { if (cls[b] == c) cls[b] = a; }
-      for (int b = 0; b < 256; b++) { if (cls[b] == ncls - 1 && c != ncls - 1) cls[b] = c; }
+      int a = -1, c2 = -1; for (int k = 0; k < ncls; k++) { if (a < 0 || w[k] < w[a]) { c2 = a; a = k; } else if (c2 < 0 || w[k] < w[c2]) c2 = k; }
+      for (int b = 0; b < 256; b++) if (cls[b] == c2) cls[b] = a;
+      for (int b = 0; b < 256; b++) if (cls[b] == ncls - 1 && c2 != ncls - 1) cls[b] = c2;
       ncls--;
     }
     ncols = 32; while (ncols < ncls) ncols *= 2;
     for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)cls[b];
   }
-  memcpy(P.lut, colmap, 256);
-  P.ncols = ncols;
+  memcpy(P.lut, colmap, 256); P.ncols = ncols;
+  // probability that a text byte lands in a column (for ranking windows)
+  std::vector<double> colw(ncols, 0); for (int b = 0; b < 256; b++) colw[colmap[b]] += Compiler::byte_weight(b);
+  auto elem_cols = [&](const ByteSet& e) { std::vector<bool> c(ncols, false); for (int b = 0; b < 256; b++) if (e.has(b)) c[colmap[b]] = true; return c; };
+  auto elem_prob = [&](const ByteSet& e) { std::vector<bool> c = elem_cols(e); double p = 0; for (int k = 0; k < ncols; k++) if (c[k]) p += colw[k]; return std::min(p, 1.0); };
 
-  for (int flen = std::min(opt.max_factor_len, kMaxFactorLen); flen >= 1; flen--) {
-    // truncate factors (a prefix of a necessary factor is still necessary), map elements to column sets, dedupe
-    struct CSeq { std::vector<std::vector<bool>> cols; std::vector<uint32_t> rules; };
+  const size_t nf = seqs.size();
+  std::vector<std::vector<double>> eprob(nf);
+  for (size_t f = 0; f < nf; f++) for (auto& e : seqs[f]) eprob[f].push_back(elem_prob(e));
+  // best window of length w for factor f (lowest probability); returns offset
+  auto best_window = [&](size_t f, int w, double* prob) {
+    int len = (int)seqs[f].size(); if (w > len) w = len;
+    int bo = 0; double bp = 2;
+    for (int o = 0; o + w <= len; o++) { double p = 1; for (int k = 0; k < w; k++) p *= eprob[f][o + k]; if (p < bp) { bp = p; bo = o; } }
+    *prob = bp; return bo;
+  };
+  auto try_build = [&](const std::vector<int>& wl, Dfa* dfa) {
     std::map<std::vector<std::vector<bool>>, std::vector<uint32_t>> uniq;
-    for (auto& q : all) {
-      std::vector<std::vector<bool>> cs;
-      for (size_t k = 0; k < q.s.size() && (int)k < flen; k++) { std::vector<bool> c(ncols, false); for (int b = 0; b < 256; b++) if (q.s[k].has(b)) c[colmap[b]] = true; cs.push_back(c); }
-      uniq[cs].push_back(q.rule);
+    for (size_t f = 0; f < nf; f++) {
+      double p; int w = std::min<int>(wl[f], (int)seqs[f].size()); int o = best_window(f, w, &p);
+      std::vector<std::vector<bool>> cs; for (int k = 0; k < w; k++) cs.push_back(elem_cols(seqs[f][o + k]));
+      uniq[cs].push_back((uint32_t)f);
     }
-    std::vector<CSeq> seqs; for (auto& kv : uniq) seqs.push_back({kv.first, kv.second});
-    std::vector<std::vector<uint32_t>> start_by_col(ncols);
-    for (uint32_t q = 0; q < seqs.size(); q++) for (int c = 0; c < ncols; c++) if (seqs[q].cols[0][c]) start_by_col[c].push_back(q);
-    // subset construction
-    std::map<StateKey, int> ids; std::vector<StateKey> states; std::vector<std::vector<int>> trans;
-    auto intern = [&](StateKey&& k) { auto it = ids.find(k); if (it != ids.end()) return it->second; int id = (int)states.size(); ids.emplace(k, id); states.push_back(std::move(k)); return id; };
-    intern(StateKey());
-    bool overflow = false;
-    for (size_t s = 0; s < states.size() && !overflow; s++) {
-      std::vector<int> row(ncols);
-      for (int c = 0; c < ncols; c++) {
-        StateKey nk; StateKey cur = states[s];
-        for (auto& it : cur.items) if (seqs[it.seq].cols[it.k][c]) { if (it.k + 1u == seqs[it.seq].cols.size()) nk.done.push_back(it.seq); else nk.items.push_back({it.seq, (uint16_t)(it.k + 1)}); }
-        for (uint32_t q : start_by_col[c]) { if (seqs[q].cols.size() == 1) nk.done.push_back(q); else nk.items.push_back({q, 1}); }
-        std::sort(nk.items.begin(), nk.items.end()); nk.items.erase(std::unique(nk.items.begin(), nk.items.end()), nk.items.end());
-        std::sort(nk.done.begin(), nk.done.end()); nk.done.erase(std::unique(nk.done.begin(), nk.done.end()), nk.done.end());
-        row[c] = intern(std::move(nk));
-        if ((int)states.size() > opt.max_states || states.size() > 65000) { overflow = true; break; }
-      }
-      trans.push_back(row);
-    }
-    if (overflow) continue;
-    // renumber: non-accepting first (state 0 stays 0), accepting last
-    int n = (int)states.size(); std::vector<int> newid(n); int na = 0, nn = 0;
-    for (int s = 0; s < n; s++) if (states[s].done.empty()) nn++;
-    int a = nn, b = 0;
-    for (int s = 0; s < n; s++) { if (states[s].done.empty()) newid[s] = b++; else { newid[s] = a++; na++; } }
-    P.nstates = n; P.first_accept = nn; P.factor_len = flen;
-    P.table.assign((size_t)n * ncols, 0);
-    for (int s = 0; s < n; s++) for (int c = 0; c < ncols; c++) P.table[(size_t)newid[s] * ncols + c] = (uint16_t)newid[trans[s][c]];
-    P.out_offsets.assign(na + 1, 0); P.out_rules.clear();
-    std::vector<int> old_of(n); for (int s = 0; s < n; s++) old_of[newid[s]] = s;
-    for (int t = 0; t < na; t++) {
-      std::set<uint32_t> rs; for (uint32_t q : states[old_of[nn + t]].done) for (uint32_t r : seqs[q].rules) rs.insert(r);
-      P.out_offsets[t] = (uint32_t)P.out_rules.size(); P.out_rules.insert(P.out_rules.end(), rs.begin(), rs.end());
-    }
-    P.out_offsets[na] = (uint32_t)P.out_rules.size();
-    return true;
+    std::vector<L1Pattern> pats; for (auto& kv : uniq) pats.push_back({kv.first, kv.second});
+    return build_dfa(pats, ncols, opt.max_states, dfa);
+  };
+
+  Dfa best; bool have = false; std::vector<int> wl(nf, 0);
+  if (nf == 0) { have = true; best.nstates = 1; best.table.assign(ncols, 0); best.acc_index.assign(ncols, 0xffffffffu); best.acc_offsets.assign(1, 0); }
+  int base = 0;
+  for (int w = std::min(opt.max_window, kMaxWindow); w >= 1 && !have; w--) {
+    std::vector<int> t(nf, w); Dfa d;
+    if (try_build(t, &d)) { best = std::move(d); wl = t; have = true; base = w; }
   }
-  // even single-element factors do not fit: every factored rule becomes an always-candidate
-  for (size_t r = 0; r < rules.size(); r++) if (rules[r].status == RULE_OK && !rules[r].factors.empty()) P.always_rules.push_back((uint32_t)r);
-  std::sort(P.always_rules.begin(), P.always_rules.end());
-  P.nstates = 1; P.first_accept = 1; P.factor_len = 0; P.table.assign(ncols, 0); P.out_offsets.assign(1, 0);
-  if (err) *err = "prefilter did not fit the state budget; all rules verified on every message";
+  if (!have) {
+    // not even 1-element windows fit: every factored rule becomes an always-candidate
+    for (auto& ff : P.factors) P.always_rules.push_back(ff.rule);
+    std::sort(P.always_rules.begin(), P.always_rules.end()); P.always_rules.erase(std::unique(P.always_rules.begin(), P.always_rules.end()), P.always_rules.end());
+    P.factors.clear(); best.nstates = 1; best.table.assign(ncols, 0); best.acc_index.assign(ncols, 0xffffffffu); best.acc_offsets.assign(1, 0); best.acc_factors.clear();
+    if (err) *err = "prefilter did not fit the state budget; all rules verified on every message";
+  } else if (nf && base < std::min(opt.max_window, kMaxWindow)) {
+    // spend the remaining rows on the most frequent windows: extend the top fraction by one element, repeatedly
+    for (int round = 0; round < 3; round++) {
+      std::vector<std::pair<double, size_t>> order;
+      for (size_t f = 0; f < nf; f++) if ((int)seqs[f].size() > wl[f] && wl[f] < kMaxWindow) { double p; best_window(f, wl[f], &p); order.push_back({-p, f}); }
+      if (order.empty()) break;
+      std::sort(order.begin(), order.end());
+      bool grew = false;
+      for (double frac : {1.0, 0.5, 0.25, 0.125, 0.0625}) {
+        size_t cnt = std::max<size_t>(1, (size_t)(order.size() * frac));
+        std::vector<int> t = wl; for (size_t k = 0; k < cnt; k++) t[order[k].second]++;
+        Dfa d;
+        if (try_build(t, &d)) { best = std::move(d); wl = t; grew = true; break; }
+      }
+      if (!grew) break;
+    }
+  }
+  // record the windows that were used
+  P.window_min = 255; P.window_max = 0;
+  for (size_t f = 0; f < P.factors.size(); f++) {
+    double p; int w = std::min<int>(wl[f], (int)seqs[f].size()); int o = best_window(f, w, &p);
+    P.factors[f].win_off = (uint8_t)o; P.factors[f].win_len = (uint8_t)w;
+    P.window_min = std::min(P.window_min, w); P.window_max = std::max(P.window_max, w);
+  }
+  if (P.factors.empty()) P.window_min = P.window_max = 0;
+  P.nstates = best.nstates; P.table = best.table; P.acc_index = best.acc_index; P.acc_offsets = best.acc_offsets; P.acc_factors = best.acc_factors;
   return true;
 }
 

@@ -17,7 +17,6 @@
 namespace cg {
 
 constexpr int kMaxProgLen = 1024;        // Pike instructions per rule (verify-kernel list bound)
-constexpr int kMaxFactorLen = 8;         // elements per prefilter factor
 
 // ---- Pike program encoding: one uint32 per instruction = op | arg << 8
 enum Op : uint32_t {
@@ -76,23 +75,35 @@ struct CompiledRule {
 // flags: bit0 = ignoreCase ("i").  `src` is the JS pattern source encoded as UTF-8.
 CompiledRule compile_rule(const char* src, size_t len, uint32_t flags);
 
-// ---- prefilter DFA over all rules' factors
+// ---- prefilter: level 1 = Mealy DFA over short *windows* of every rule's necessary factors
+// (shared memory, one lookup per byte); level 2 = exact confirmation of the full factor (up to 16
+// byte-set elements) at the flagged position; only confirmed (message, rule) pairs reach the VM.
+constexpr int kMaxWindow = 8;
+constexpr int kMaxFactorElems = 16;
+
 struct PrefilterOptions {
-  int mode = 0;              // 0 = direct 7-bit index (128 columns, no LUT), 1 = byte->class LUT
-  int max_states = 640;      // rows that fit the shared-memory budget
+  int mode = 2;              // 0 = direct 7-bit (128 cols), 1 = byte->class LUT (<=64), 2 = folded 6-bit (64, SWAR), 3 = folded 5-bit (32, SWAR)
+  int max_states = 24576;    // total level-1 states (rows beyond the shared-memory budget stay in L2-resident HBM)
   int max_classes = 64;      // LUT mode only
-  int max_factor_len = kMaxFactorLen;
+  int max_window = kMaxWindow;
+};
+struct FullFactor {
+  uint32_t rule;
+  uint8_t len, win_off, win_len, exact;   // exact: a confirmed occurrence proves the rule matches (RegExp.test)
+  uint16_t elem[kMaxFactorElems];         // byte-set ids
 };
 struct Prefilter {
-  int mode = 0;
-  int ncols = 128;                    // columns per row (power of two)
-  int nstates = 1;
-  int first_accept = 1;               // states >= first_accept have outputs
-  int factor_len = 0;                 // truncation that was needed to fit
-  std::vector<uint16_t> table;        // nstates * ncols
-  uint8_t lut[256];                   // LUT mode: byte -> column ; direct mode: b & 0x7f
-  std::vector<uint32_t> out_offsets;  // per accept state (index s - first_accept): CSR into out_rules, size naccept+1
-  std::vector<uint32_t> out_rules;    // rule ids
+  int mode = 2;
+  int ncols = 64;                     // columns per row (power of two)
+  int nstates = 1;                    // states are numbered breadth-first: shallow (hot) states first
+  int window_min = 0, window_max = 0; // level-1 window lengths actually used
+  std::vector<uint16_t> table;        // nstates * ncols; bit 15 = accepting transition, bits 0-14 = next state
+  uint8_t lut[256];                   // byte -> column (used by the device only in LUT mode)
+  std::vector<uint32_t> acc_index;    // nstates * ncols: accept id of an accepting transition, else 0xffffffff
+  std::vector<uint32_t> acc_offsets;  // CSR over accept ids -> factor ids
+  std::vector<uint32_t> acc_factors;
+  std::vector<FullFactor> factors;
+  std::vector<uint32_t> bytesets;     // 8 words per 256-bit set
   std::vector<uint32_t> always_rules; // rules without usable factors: candidates for every message
 };
 bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* out, std::string* err);

@@ -35,14 +35,21 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   H.n_sets = (uint32_t)(H.sets.size() / 6);
 
   PrefilterOptions po;
-  po.mode = opt.mode; po.max_classes = opt.max_classes; po.max_factor_len = opt.max_factor_len;
-  int cols = po.mode == 0 ? 128 : (po.max_classes <= 32 ? 32 : 64);
+  po.mode = opt.mode; po.max_classes = opt.max_classes; po.max_window = opt.max_window;
+  int cols = po.mode == 0 ? 128 : po.mode == 2 ? 64 : po.mode == 3 ? 32 : (po.max_classes <= 32 ? 32 : 64);
   size_t budget = std::max<size_t>(opt.budget_bytes, 256 + (size_t)cols * 2 * 2);
-  po.max_states = (int)std::min<size_t>((budget - 256) / ((size_t)cols * 2), 65000);
+  size_t hot_rows = std::min<size_t>((budget - 256) / ((size_t)cols * 2), 32767);
+  po.max_states = std::max<int>((int)std::min<size_t>((size_t)std::max(opt.max_states, 1), 32767), 1);
   if (!build_prefilter(H.rules, po, &H.pf, err)) return false;
-  H.image.assign(256 + H.pf.table.size() * 2, 0);
+  H.hot_states = (uint32_t)std::min<size_t>(hot_rows, (size_t)H.pf.nstates);
+  for (auto& f : H.pf.factors) {
+    H.factor_words.push_back(f.rule);
+    H.factor_words.push_back((uint32_t)f.len | ((uint32_t)f.win_off << 8) | ((uint32_t)f.win_len << 16) | ((uint32_t)f.exact << 24));
+    for (int k = 0; k < kMaxFactorElems; k += 2) H.factor_words.push_back((uint32_t)f.elem[k] | ((uint32_t)f.elem[k + 1] << 16));
+  }
+  H.image.assign(256 + (size_t)H.hot_states * H.pf.ncols * 2, 0);
   memcpy(H.image.data(), H.pf.lut, 256);
-  memcpy(H.image.data() + 256, H.pf.table.data(), H.pf.table.size() * 2);
+  memcpy(H.image.data() + 256, H.pf.table.data(), (size_t)H.hot_states * H.pf.ncols * 2);
   while (H.image.size() % 16) H.image.push_back(0);
   return true;
 }

@@ -10,17 +10,20 @@ namespace cg {
 struct HostImage {
   std::vector<CompiledRule> rules;
   Prefilter pf;
-  std::vector<uint8_t> image;          // [lut 256][table], padded to 16 bytes
+  std::vector<uint8_t> image;          // [lut 256][first hot_states rows of the table], padded to 16 bytes
+  uint32_t hot_states = 0;             // rows resident in shared memory
   std::vector<uint32_t> prog, prog_off, sets, first;
+  std::vector<uint32_t> factor_words;  // 10 words per full factor (device layout)
   std::vector<uint16_t> ranges;
   uint32_t n_sets = 0;
 };
 
 struct ImageOptions {
-  int mode = 0;                 // prefilter column mode (0 direct7, 1 LUT)
-  size_t budget_bytes = 192 * 1024;
+  int mode = 2;                 // level-1 column mode (0 direct7, 1 LUT, 2 folded 6-bit)
+  size_t budget_bytes = 200 * 1024;   // shared-memory budget of the hot rows
+  int max_states = 16384;             // total states (cold rows are read from L2-resident HBM)
   int max_classes = 64;
-  int max_factor_len = kMaxFactorLen;
+  int max_window = kMaxWindow;
 };
 
 struct RuleSrc { const char* src; uint32_t len; uint32_t flags; };

@@ -1,10 +1,13 @@
 // scan_kernels.cu -- sm_100a kernels of the message-scan hot path.
 //
-//   scan_kernel     every byte of every message through the prefilter DFA that lives in shared
-//                   memory (image staged with one TMA bulk copy per CTA, completion on an mbarrier).
-//                   One lane owns one message; candidates (message, rule) are queued in HBM.
-//   verify_kernel   exact ECMAScript semantics for the queued candidates: a Pike VM over UTF-16
-//                   units decoded on the fly from the UTF-8 bytes (leftmost-first, global-exec
+//   scan_kernel     every byte of every message through the level-1 prefilter DFA that lives in
+//                   shared memory (image staged with TMA bulk copies, completion on an mbarrier).
+//                   One lane owns one message; accepting transitions are compacted with warp
+//                   ballots into an event queue in HBM (one atomic per warp and word).
+//   confirm_kernel  level 2: one thread per level-1 event confirms the full factor exactly and
+//                   queues the surviving (message, rule) pairs (or records a direct hit).
+//   verify_kernel   exact ECMAScript semantics for the queued pairs: a Pike VM over UTF-16 units
+//                   decoded on the fly from the UTF-8 bytes (leftmost-first, global-exec
 //                   iteration of registry.ts:225-236, RegExp.test of context.ts:9-25).
 //   finalize_kernel per-message result words from the verified-hit bitmaps.
 //
@@ -13,6 +16,7 @@
 #include "kernels.h"
 #include "rulec.h"
 #include "pike_vm.h"
+#include "prefilter_dev.h"
 
 namespace cg {
 
@@ -50,44 +54,34 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// candidate queue (lane-private slot; cand bitmap dedupes (message, rule) at the source)
+// level 1: prefilter scan.  lane-per-message, streaming 16-byte loads, table in shared memory
 // ------------------------------------------------------------------------------------------
-struct Emitter {
-  const DevRuleset& rs; const ScanWork& w; uint32_t msg; uint32_t slot;
-  __device__ Emitter(const DevRuleset& r, const ScanWork& wk, uint32_t m) : rs(r), w(wk), msg(m), slot(0xffffffffu) {}
-  __device__ bool ensure_slot() {
-    if (slot != 0xffffffffu) return slot < w.slot_cap;
-    slot = atomicAdd(&w.counters[0], 1u);
-    if (slot >= w.slot_cap) { atomicOr(&w.counters[3], ERR_SLOT_OVERFLOW); return false; }
-    w.slot_msg[slot] = msg;
-    for (uint32_t k = 0; k < rs.rw; k++) { w.cand[(size_t)slot * rs.rw + k] = 0; w.hit[(size_t)slot * rs.rw + k] = 0; }
-    return true;
-  }
-  __device__ void rule(uint32_t r) {
-    if (!ensure_slot()) return;
-    uint32_t* cw = &w.cand[(size_t)slot * rs.rw + (r >> 5)];
-    uint32_t v = *cw, bit = 1u << (r & 31);
-    if (v & bit) return;
-    *cw = v | bit;
-    uint32_t e = atomicAdd(&w.counters[1], 1u);
-    if (e < w.event_cap) w.events[e] = make_uint2(slot, r); else atomicOr(&w.counters[3], ERR_EVENT_OVERFLOW);
-  }
-  __device__ void accept_state(uint32_t s) {
-    uint32_t a = s - rs.first_accept;
-    for (uint32_t k = rs.out_offsets[a]; k < rs.out_offsets[a + 1]; k++) rule(rs.out_rules[k]);
-  }
-};
+constexpr int kScanThreads = 1024;
+constexpr uint32_t kL1Always = 0xffffffffu;
 
-// ------------------------------------------------------------------------------------------
-// prefilter scan, v1: lane-per-message, streaming 16-byte loads, table in shared memory
-// ------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 512;
+// pre-doubled column indices of the four bytes of a word (one byte each), SWAR
+template <int MODE> __device__ __forceinline__ uint32_t cols2_of_word(uint32_t w);
+template <> __device__ __forceinline__ uint32_t cols2_of_word<0>(uint32_t w) { return (w + w) & 0xfefefefeu; }
+template <> __device__ __forceinline__ uint32_t cols2_of_word<2>(uint32_t w) { return ((w & 0x1f1f1f1fu) | ((w >> 1) & 0x20202020u)) << 1; }
+template <> __device__ __forceinline__ uint32_t cols2_of_word<3>(uint32_t w) { return (w & 0x1f1f1f1fu) << 1; }
+template <> __device__ __forceinline__ uint32_t cols2_of_word<1>(uint32_t w) { return w; }   // LUT mode resolves per byte
 
+template <int MODE> struct RowBytes { static constexpr uint32_t v = MODE == 0 ? 256u : MODE == 3 ? 64u : 128u; };
+
+// one level-1 transition: the raw table entry (bit 15 = accepting transition).  Rows of the shallow
+// (hot) states come from shared memory; the rare deep states read their row from the L2-resident copy.
 template <int MODE>
-__device__ __forceinline__ uint32_t dfa_step(const uint16_t* __restrict__ table, const uint8_t* __restrict__ lut,
-                                             uint32_t state, uint32_t b, uint32_t ncols_log2) {
-  if (MODE == 0) return table[(state << 7) + (b & 0x7fu)];
-  return table[(state << ncols_log2) + lut[b]];
+__device__ __forceinline__ uint32_t l1_step(const uint8_t* __restrict__ tbl, const uint8_t* __restrict__ gtbl, const uint8_t* __restrict__ lut,
+                                            uint32_t row_shift, uint32_t hot, uint32_t state, uint32_t c2) {
+  uint32_t o;
+  if (MODE == 1) o = (state << row_shift) + 2u * lut[c2]; else o = state * RowBytes<MODE>::v + c2;
+  if (state < hot) return *reinterpret_cast<const uint16_t*>(tbl + o);
+  return __ldg(reinterpret_cast<const uint16_t*>(gtbl + o));
+}
+
+__device__ __forceinline__ void l1_push_one(const ScanWork& w, uint32_t msg, uint32_t pos, uint32_t sc) {
+  uint32_t k = atomicAdd(&w.counters[4], 1u);
+  if (k < w.l1_cap) { w.l1_msg[k] = msg; w.l1_pos[k] = pos; w.l1_sc[k] = sc; } else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
 }
 
 template <int MODE>
@@ -107,48 +101,142 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
   }
   mbar_wait(&bar, 0);
   const uint8_t* lut = smem;
-  const uint16_t* table = reinterpret_cast<const uint16_t*>(smem + 256);
-  const uint32_t ncl = rs.ncols_log2, first_accept = rs.first_accept;
+  const uint8_t* tbl = smem + 256;
+  const uint8_t* gtbl = reinterpret_cast<const uint8_t*>(rs.table_full);
+  const uint32_t row_shift = rs.ncols_log2 + 1, hot = rs.hot_states;
+  const uint32_t FULL = 0xffffffffu;
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kScanThreads / 32;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t ntiles = (n + 31) / 32;
   for (uint32_t tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
-    uint32_t msg = tile * 32 + lane;
-    if (msg >= n) continue;
-    uint32_t b = off[msg], e = off[msg + 1];
-    uint32_t state = 0, acc = 0, p = b;
-    while (p < e && (p & 15u)) { state = dfa_step<MODE>(table, lut, state, bytes[p], ncl); acc = max(acc, state); p++; }
-    while (p + 16 <= e) {
-      uint4 v = ldg_stream(bytes + p);
-      uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t msg = tile * 32 + lane;
+    const bool valid = msg < n;
+    const uint32_t b = valid ? off[msg] : 0u, e = valid ? off[msg + 1] : 0u;
+    if (valid && rs.n_always) l1_push_one(w, msg, 0, kL1Always);
+    uint32_t state = 0, p = b;
+    // byte-wise, checked: the unaligned head and the tail of a message
+    auto checked = [&](uint32_t upto) {
+      for (; p < upto; p++) {
+        uint32_t col = l1_col(rs.mode, lut, bytes[p]);
+        uint32_t ent = state < hot ? *reinterpret_cast<const uint16_t*>(tbl + (state << row_shift) + 2u * col)
+                          : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(gtbl + (state << row_shift) + 2u * col));
+        if (ent & 0x8000u) l1_push_one(w, msg, p - b, (state << 8) | col);
+        state = ent & 0x7fffu;
+      }
+    };
+    uint32_t head_end = (b + 15u) & ~15u; if (head_end > e) head_end = e;
+    checked(head_end);
+    // warp-uniform main loop over 16-byte chunks
+    uint32_t nch = (e - p) >> 4, maxch = nch;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxch = max(maxch, __shfl_xor_sync(FULL, maxch, d));
+    for (uint32_t c = 0; c < maxch; c++) {
+      const bool act = c < nch;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (act) v = ldg_stream(bytes + p);
+      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int q = 0; q < 4; q++) {
+        const uint32_t s0 = state;
+        uint32_t acc = 0;
+        if (act) {
+          const uint32_t c2 = cols2_of_word<MODE>(wd[q]);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          state = dfa_step<MODE>(table, lut, state, (wd[q] >> (8 * k)) & 0xffu, ncl);
-          acc = max(acc, state);
+          for (int k = 0; k < 4; k++) {
+            uint32_t ent = l1_step<MODE>(tbl, gtbl, lut, row_shift, hot, state, (c2 >> (8 * k)) & 0xffu);
+            acc |= ent; state = ent & 0x7fffu;
+          }
+        }
+        // rare: some lane took an accepting transition in this word -> compact the events with ballots
+        if (__ballot_sync(FULL, (acc & 0x8000u) != 0)) {
+          uint32_t cnt = 0, ev_pos[4], ev_sc[4];
+          if (acc & 0x8000u) {
+            uint32_t st = s0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              uint32_t col = l1_col(rs.mode, lut, (wd[q] >> (8 * k)) & 0xffu);
+              uint32_t ent = st < hot ? *reinterpret_cast<const uint16_t*>(tbl + (st << row_shift) + 2u * col)
+                                      : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(gtbl + (st << row_shift) + 2u * col));
+              if (ent & 0x8000u) { ev_pos[cnt] = p + 4 * q + k - b; ev_sc[cnt] = (st << 8) | col; cnt++; }
+              st = ent & 0x7fffu;
+            }
+          }
+          uint32_t idx = 0, total = 0;
+#pragma unroll
+          for (uint32_t j = 1; j <= 4; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&w.counters[4], total);
+          base = __shfl_sync(FULL, base, 0);
+          if (base + total > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
+          else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t k = base + idx + j; w.l1_msg[k] = msg; w.l1_pos[k] = ev_pos[j]; w.l1_sc[k] = ev_sc[j]; }
+          }
         }
       }
-      p += 16;
+      if (act) p += 16;
     }
-    while (p < e) { state = dfa_step<MODE>(table, lut, state, bytes[p], ncl); acc = max(acc, state); p++; }
-
-    if (acc >= first_accept || rs.n_always) {
-      Emitter em(rs, w, msg);
-      for (uint32_t k = 0; k < rs.n_always; k++) em.rule(rs.always_rules[k]);
-      if (acc >= first_accept) {
-        state = 0;
-        for (p = b; p < e; p++) {
-          state = dfa_step<MODE>(table, lut, state, bytes[p], ncl);
-          if (state >= first_accept) em.accept_state(state);
-        }
-      }
-    }
-    words[msg] = 0ull;
+    checked(e);
+    if (valid) words[msg] = 0ull;
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// level 2: confirm the full factor for every level-1 event; queue survivors for the VM
+// ------------------------------------------------------------------------------------------
+struct SlotSink {
+  const DevRuleset& rs; const ScanWork& w; uint32_t msg; uint32_t slot;
+  __device__ SlotSink(const DevRuleset& r, const ScanWork& wk, uint32_t m) : rs(r), w(wk), msg(m), slot(0xffffffffu) {}
+  __device__ bool ensure_slot() {
+    if (slot != 0xffffffffu) return slot < w.slot_cap;
+    uint32_t s = *reinterpret_cast<volatile uint32_t*>(&w.slot_of_msg[msg]);
+    if (s == 0xffffffffu) {
+      uint32_t mine = atomicAdd(&w.counters[0], 1u);
+      if (mine >= w.slot_cap) { atomicOr(&w.counters[3], ERR_SLOT_OVERFLOW); slot = mine; return false; }
+      for (uint32_t k = 0; k < rs.rw; k++) { w.cand[(size_t)mine * rs.rw + k] = 0; w.hit[(size_t)mine * rs.rw + k] = 0; }
+      w.slot_msg[mine] = msg;
+      __threadfence();                                   // rows are zero before the slot becomes visible
+      uint32_t old = atomicCAS(&w.slot_of_msg[msg], 0xffffffffu, mine);
+      if (old == 0xffffffffu) s = mine; else { s = old; w.slot_msg[mine] = 0xffffffffu; }   // lost the race: slot stays unused
+    }
+    slot = s;
+    return true;
+  }
+  __device__ void candidate(uint32_t r) {
+    if (!ensure_slot()) return;
+    uint32_t bit = 1u << (r & 31);
+    uint32_t old = atomicOr(&w.cand[(size_t)slot * rs.rw + (r >> 5)], bit);
+    if (old & bit) return;
+    uint32_t e = atomicAdd(&w.counters[1], 1u);
+    if (e < w.event_cap) w.events[e] = make_uint2(slot, r); else atomicOr(&w.counters[3], ERR_EVENT_OVERFLOW);
+  }
+  // a confirmed exact factor already proves RegExp.test(message) for this rule
+  __device__ void direct(uint32_t r) {
+    if (!ensure_slot()) return;
+    uint32_t bit = 1u << (r & 31);
+    atomicOr(&w.cand[(size_t)slot * rs.rw + (r >> 5)], bit);
+    atomicOr(&w.hit[(size_t)slot * rs.rw + (r >> 5)], bit);
+  }
+};
+
+__global__ void __launch_bounds__(256)
+confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, int want_spans) {
+  const uint32_t n1 = min(w.counters[4], w.l1_cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
+    const uint32_t msg = w.l1_msg[i], pos = w.l1_pos[i], sc = w.l1_sc[i];
+    SlotSink sink(rs, w, msg);
+    if (sc == kL1Always) { for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate(rs.always_rules[k]); continue; }
+    const uint32_t b = off[msg];
+    l1_accept(rs, sc >> 8, sc & 0xffu, bytes + b, off[msg + 1] - b, pos, want_spans != 0, sink);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// level 3: exact verification by the Pike VM
+// ------------------------------------------------------------------------------------------
 constexpr int kVerifyThreads = 64;
+constexpr int kSmallProg = 160;          // VM capacity that covers every built-in rule (longest: 133 instructions)
 
 struct GlobalSpanSink {
   const ScanWork& w; uint32_t msg, rule;
@@ -159,14 +247,55 @@ struct GlobalSpanSink {
   }
 };
 
+// thread-interleaved shared-memory VM storage: element i of thread t lives at base[i * blockDim + t]
+struct SmemStore {
+  static constexpr uint32_t cap = kSmallProg;
+  uint16_t* mark_; uint16_t* pcs_; uint32_t* sts_; uint16_t* stk_; uint32_t stride, t;
+  __device__ __forceinline__ uint16_t& mark(uint32_t i) { return mark_[i * stride + t]; }
+  __device__ __forceinline__ uint16_t& pc(int L, uint32_t i) { return pcs_[(L * cap + i) * stride + t]; }
+  __device__ __forceinline__ uint32_t& st(int L, uint32_t i) { return sts_[(L * cap + i) * stride + t]; }
+  __device__ __forceinline__ uint16_t& stk(uint32_t i) { return stk_[i * stride + t]; }
+};
+constexpr size_t kVerifySmem = (size_t)kVerifyThreads * (kSmallProg * 2 + 2 * kSmallProg * 2 + 2 * kSmallProg * 4 + kVmStack * 2);
+
+// small programs (<= kSmallProg instructions): VM state in shared memory
 template <bool SPANS>
 __global__ void __launch_bounds__(kVerifyThreads)
-verify_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off) {
+verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off) {
+  extern __shared__ __align__(16) uint8_t vsm[];
   const uint32_t n_events = min(w.counters[1], w.event_cap);
-  VM vm(rs);
+  SmemStore st;
+  st.stride = kVerifyThreads; st.t = threadIdx.x;
+  st.sts_ = reinterpret_cast<uint32_t*>(vsm);
+  st.pcs_ = reinterpret_cast<uint16_t*>(vsm + (size_t)kVerifyThreads * 2 * kSmallProg * 4);
+  st.mark_ = st.pcs_ + (size_t)kVerifyThreads * 2 * kSmallProg;
+  st.stk_ = st.mark_ + (size_t)kVerifyThreads * kSmallProg;
+  VMS<SmemStore> vm(rs, st);
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
     uint2 ev = w.events[e];
-    uint32_t slot = ev.x, rule = ev.y, msg = w.slot_msg[slot];
+    uint32_t slot = ev.x, rule = ev.y;
+    uint32_t plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
+    if (plen > (uint32_t)kSmallProg) continue;          // handled by verify_large_kernel
+    uint32_t msg = w.slot_msg[slot];
+    GlobalSpanSink sink{w, msg, rule};
+    bool any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
+    if (any) atomicOr(&w.hit[(size_t)slot * rs.rw + (rule >> 5)], 1u << (rule & 31));
+  }
+  if (vm.err) atomicOr(&w.counters[3], vm.err);
+}
+
+// programs longer than kSmallProg: per-thread local arrays
+template <bool SPANS>
+__global__ void __launch_bounds__(kVerifyThreads)
+verify_large_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off) {
+  const uint32_t n_events = min(w.counters[1], w.event_cap);
+  VMT<kMaxProgLen> vm(rs);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
+    uint2 ev = w.events[e];
+    uint32_t slot = ev.x, rule = ev.y;
+    uint32_t plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
+    if (plen <= (uint32_t)kSmallProg) continue;
+    uint32_t msg = w.slot_msg[slot];
     GlobalSpanSink sink{w, msg, rule};
     bool any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
     if (any) atomicOr(&w.hit[(size_t)slot * rs.rw + (rule >> 5)], 1u << (rule & 31));
@@ -177,12 +306,14 @@ verify_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, cons
 __global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict__ words) {
   const uint32_t n_slots = min(w.counters[0], w.slot_cap);
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+    const uint32_t msg = w.slot_msg[s];
+    if (msg == 0xffffffffu) continue;                    // slot lost an allocation race: unused
     uint32_t count = 0, first = 0xffffffffu;
     for (uint32_t k = 0; k < rs.rw; k++) {
       uint32_t v = w.hit[(size_t)s * rs.rw + k];
       if (v) { if (first == 0xffffffffu) first = k * 32 + (__ffs(v) - 1); count += __popc(v); }
     }
-    if (count) words[w.slot_msg[s]] = (1ull << 63) | ((uint64_t)count << 32) | first;
+    if (count) words[msg] = (1ull << 63) | ((uint64_t)count << 32) | first;
   }
 }
 
@@ -190,27 +321,41 @@ __global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict_
 // launchers
 // ------------------------------------------------------------------------------------------
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
-                uint64_t* d_words, int sm_count, cudaStream_t stream) {
+                uint64_t* d_words, bool want_spans, int sm_count, cudaStream_t stream) {
+  (void)want_spans;
   if (n == 0) return 0;
   size_t smem = rs.image_bytes;
   uint32_t ntiles = (n + 31) / 32, wpb = kScanThreads / 32;
   uint32_t grid = (ntiles + wpb - 1) / wpb; if (grid > (uint32_t)sm_count) grid = sm_count;
-  if (rs.mode == 0) {
-    cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<0><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words);
-  } else {
-    cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<1><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words);
-  }
+#define CG_LAUNCH_SCAN(M) do { cudaFuncSetAttribute(scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    scan_kernel<M><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); } while (0)
+  switch (rs.mode) { case 0: CG_LAUNCH_SCAN(0); break; case 2: CG_LAUNCH_SCAN(2); break; case 3: CG_LAUNCH_SCAN(3); break; default: CG_LAUNCH_SCAN(1); break; }
+#undef CG_LAUNCH_SCAN
+  return 1;
+}
+
+int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
+                   bool want_spans, int sm_count, cudaStream_t stream) {
+  confirm_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_bytes, d_off, want_spans ? 1 : 0);
   return 1;
 }
 
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream) {
-  int grid = sm_count * 8;
-  if (want_spans) verify_kernel<true><<<grid, kVerifyThreads, 0, stream>>>(rs, w, d_bytes, d_off);
-  else verify_kernel<false><<<grid, kVerifyThreads, 0, stream>>>(rs, w, d_bytes, d_off);
-  return 1;
+  int k = 1;
+  if (want_spans) {
+    cudaFuncSetAttribute(verify_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
+    verify_small_kernel<true><<<sm_count, kVerifyThreads, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+  } else {
+    cudaFuncSetAttribute(verify_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
+    verify_small_kernel<false><<<sm_count, kVerifyThreads, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+  }
+  if (rs.max_prog_len > (uint32_t)kSmallProg) {
+    k++;
+    if (want_spans) verify_large_kernel<true><<<sm_count * 4, kVerifyThreads, 0, stream>>>(rs, w, d_bytes, d_off);
+    else verify_large_kernel<false><<<sm_count * 4, kVerifyThreads, 0, stream>>>(rs, w, d_bytes, d_off);
+  }
+  return k;
 }
 
 int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, int sm_count, cudaStream_t stream) {

@@ -87,19 +87,21 @@ def make_rules(n_rules: int, seed: int = SEED_RULES, include_builtins: bool = Tr
             rules.append({"id": rid, "source": src, "flags": 0, "category": CAT_CUSTOM, "sample": smp})
         elif u < 0.90:      # prefix + class run tokens
             form = int(rng.integers(0, 4))
-            pre = _word(rng, 2, 4) + ("-", "_", "", ".")[int(rng.integers(0, 4))]
+            # like sk- / ghp_ / glpat- / AIza: a distinctive prefix of >= 3 characters, usually with a separator
+            pre = _word(rng, 3, 5) + ("-", "_", "", ".")[int(rng.integers(0, 4))]
             cnt = int(rng.integers(16, 41))
             body = "".join(_ALNUM[int(x)] for x in rng.integers(0, len(_ALNUM), cnt + 4))
+            esc = pre.replace(".", "\\.")
             if form == 0:
-                src, smp = "%s[a-zA-Z0-9]{%d,}" % (pre, cnt), pre + body
+                src, smp = "%s[a-zA-Z0-9]{%d,}" % (esc, cnt), pre + body
             elif form == 1:
-                src, smp = "%s[a-zA-Z0-9]{%d}" % (pre, cnt), pre + body[:cnt]
+                src, smp = "%s[a-zA-Z0-9]{%d}" % (esc, cnt), pre + body[:cnt]
             elif form == 2:
                 up = pre.upper().replace("-", "X").replace("_", "Y").replace(".", "Z") + "Q"
                 ub = "".join("ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"[int(x)] for x in rng.integers(0, 36, 16))
                 src, smp = "(?<![A-Z0-9])%s[0-9A-Z]{16}(?![A-Z0-9])" % up, up + ub
             else:
-                src, smp = "%s[a-zA-Z0-9_-]{%d,}" % (pre, cnt), pre + body
+                src, smp = "%s[a-zA-Z0-9_-]{%d,}" % (esc, cnt), pre + body
             rules.append({"id": rid, "source": src, "flags": 0, "category": CAT_CREDENTIAL, "sample": smp})
         else:               # structured
             form = int(rng.integers(0, 4))
