@@ -46,4 +46,5 @@ def harness_lib():
     L.harness_find_all.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32]
     L.harness_test.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]
     L.harness_candidates.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.harness_policy_hits.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p]
     return L

@@ -50,6 +50,12 @@ class Harness:
         f = lambda bits: {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
         return f(c), f(d), int(l1[0])
 
+    def policy_hits(self, msg: bytes):
+        """rules with RegExp.test(msg) true, computed the way the device pipeline does (level 1 -> confirm -> island VM)"""
+        bits = np.zeros(self.rw, dtype=np.uint32)
+        self.L.harness_policy_hits(self.h, msg, len(msg), bits.ctypes.data)
+        return {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
+
     def candidates(self, msg: bytes):
         c, d, _ = self.candidates2(msg)
         return c | d

@@ -45,7 +45,7 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   // pad host vectors the same way capi.cu pads the device copies
   H.sets.resize(H.sets.size() + 8, 0); H.ranges.resize(H.ranges.size() + 8, 0); H.first.resize(H.first.size() + 8, 0);
   H.pf.acc_index.resize(H.pf.acc_index.size() + 4, 0xffffffffu); H.pf.acc_offsets.resize(H.pf.acc_offsets.size() + 4, 0);
-  H.pf.acc_factors.resize(H.pf.acc_factors.size() + 4, 0); H.factor_words.resize(H.factor_words.size() + 16, 0);
+  H.pf.acc_factors.resize(H.pf.acc_factors.size() + 4, 0); H.factor_words.resize(H.factor_words.size() + 24, 0);
   H.pf.bytesets.resize(H.pf.bytesets.size() + 8, 0);
   uint32_t n_always = (uint32_t)H.pf.always_rules.size();
   H.pf.always_rules.resize(H.pf.always_rules.size() + 4, 0);
@@ -56,7 +56,8 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   d.factors = H.factor_words.data(); d.bytesets = H.pf.bytesets.data();
   d.always_rules = H.pf.always_rules.data(); d.n_always = n_always;
   d.prog = H.prog.data(); d.rule_prog_off = H.prog_off.data(); d.sets = H.sets.data(); d.set_ranges = H.ranges.data();
-  d.rule_first = H.first.data(); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
+  H.alpha.resize(H.alpha.size() + 8, 0);
+  d.rule_first = H.first.data(); d.rule_alpha = H.alpha.data(); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
   return h;
 }
 void harness_destroy(void* p) { delete (Harness*)p; }
@@ -96,13 +97,14 @@ int harness_test(void* p, uint32_t rule, const uint8_t* m, uint32_t len) {
 // restated for one message: bitmaps (rw words each) of queued candidates and of direct hits
 struct BitSink {
   uint32_t* cand; uint32_t* direct_;
-  void candidate(uint32_t r) { cand[r >> 5] |= 1u << (r & 31); }
+  std::vector<uint32_t>* occ;   // (rule, t0, pre) triples of confirmed occurrences
+  void candidate(uint32_t r, uint32_t t0 = 0xffffffffu, uint32_t pre = 0xffff) { cand[r >> 5] |= 1u << (r & 31); if (occ) { occ->push_back(r); occ->push_back(t0); occ->push_back(pre); } }
   void direct(uint32_t r) { direct_[r >> 5] |= 1u << (r & 31); }
 };
 void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand, uint32_t* direct, int want_spans, uint32_t* l1_hits) {
   Harness* h = (Harness*)p; const DevRuleset& d = h->d;
   for (uint32_t k = 0; k < d.rw; k++) { cand[k] = 0; direct[k] = 0; }
-  BitSink sink{cand, direct};
+  BitSink sink{cand, direct, nullptr};
   for (uint32_t k = 0; k < d.n_always; k++) sink.candidate(d.always_rules[k]);
   const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0, hits = 0;
@@ -115,6 +117,32 @@ void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand,
   if (l1_hits) *l1_hits = hits;
 }
 
+
+// policy-mode verification exactly as verify_*_kernel does it: for every confirmed factor occurrence
+// run test_at_factor; returns the bitmap of rules that hit (direct hits included)
+void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits) {
+  Harness* h = (Harness*)p; const DevRuleset& d = h->d;
+  std::vector<uint32_t> cand(d.rw, 0), occ;
+  for (uint32_t k = 0; k < d.rw; k++) hits[k] = 0;
+  BitSink sink{cand.data(), hits, &occ};
+  for (uint32_t k = 0; k < d.n_always; k++) sink.candidate(d.always_rules[k]);
+  const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
+  uint32_t state = 0;
+  for (uint32_t i = 0; i < len; i++) {
+    uint32_t col = l1_col(d.mode, lut, m[i]);
+    uint32_t ent = table[(state << d.ncols_log2) + col];
+    if (ent & 0x8000u) l1_accept(d, state, col, m, len, i, false, sink);
+    state = ent & 0x7fffu;
+  }
+  VM vm(d);
+  struct Null { void span(uint32_t, uint32_t, uint32_t, uint32_t) {} } ns;
+  for (size_t k = 0; k + 2 < occ.size(); k += 3) {
+    uint32_t r = occ[k], t0 = occ[k + 1], pre = occ[k + 2];
+    if ((hits[r >> 5] >> (r & 31)) & 1u) continue;
+    bool any = t0 == 0xffffffffu ? run_rule<false>(vm, d, r, m, len, ns) : test_at_factor(vm, d, r, m, len, t0, pre);
+    if (any) hits[r >> 5] |= 1u << (r & 31);
+  }
+}
 
 // debug: level-1 accepting transitions per factor over one message (adds into counts[n_factors])
 void harness_l1_factor_counts(void* p, const uint8_t* m, uint32_t len, uint32_t* counts) {

@@ -86,6 +86,13 @@ def test_synthetic_rules_spans_and_prefilter_soundness(oracle, harness_lib, mode
                 else:
                     assert ri not in direct[mi], ("direct hit without a match", r[0], m)
     assert n_hits >= 200          # the injected tokens were really found
+    # policy semantics through the pipeline's own logic (level 1 -> confirm -> island-restricted VM)
+    hits_by_msg = {}
+    for ri, r in enumerate(rules):
+        for mi in oracle_spans(oracle, oracle.Regex(r[0], "i" if r[1] else ""), msgs):
+            hits_by_msg.setdefault(mi, set()).add(ri)
+    for mi, m in enumerate(msgs):
+        assert h.policy_hits(m) == hits_by_msg.get(mi, set()), (mi, m)
     h.close()
 
 
@@ -189,6 +196,7 @@ def test_random_regex_differential(oracle, harness_lib):
             assert got == exp.get(mi, []), (src, fl, texts[mi])
             if exp.get(mi):
                 assert 0 in h.candidates(m), ("prefilter missed", src, texts[mi])
+            assert (0 in h.policy_hits(m)) == bool(exp.get(mi)), ("policy pipeline differs", src, fl, texts[mi])
         checked += 1
         h.close()
     assert checked > 400

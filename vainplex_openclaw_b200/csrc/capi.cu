@@ -71,7 +71,7 @@ struct cg_ruleset {
   ~cg_ruleset() {
     for (void* p : allocs) cudaFree(p);
     cudaFree(work.l1_msg); cudaFree(work.l1_pos); cudaFree(work.l1_sc); cudaFree(work.slot_of_msg);
-    cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.spans);
+    cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
   }
 };
 
@@ -106,7 +106,7 @@ int ensure_work(cg_ruleset* rs, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_
     CU(cudaMalloc((void**)&w.hit, (size_t)slot_cap * rw * 4));
     w.slot_cap = slot_cap;
   }
-  if (event_cap > w.event_cap) { cudaFree(w.events); w.events = nullptr; w.event_cap = 0; CU(cudaMalloc((void**)&w.events, (size_t)event_cap * sizeof(uint2))); w.event_cap = event_cap; }
+  if (event_cap > w.event_cap) { cudaFree(w.events); cudaFree(w.event_pos); cudaFree(w.event_pre); w.events = nullptr; w.event_pos = w.event_pre = nullptr; w.event_cap = 0; CU(cudaMalloc((void**)&w.events, (size_t)event_cap * sizeof(uint2))); CU(cudaMalloc((void**)&w.event_pos, (size_t)event_cap * 4)); CU(cudaMalloc((void**)&w.event_pre, (size_t)event_cap * 4)); w.event_cap = event_cap; }
   if (span_cap > w.span_cap) { cudaFree(w.spans); w.spans = nullptr; w.span_cap = 0; CU(cudaMalloc((void**)&w.spans, (size_t)span_cap * 24)); w.span_cap = span_cap; }
   return CG_OK;
 }
@@ -294,6 +294,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), sets, &d.sets, 8))) return rc;
   if ((rc = upload(rs.get(), ranges, &d.set_ranges, 8))) return rc;
   if ((rc = upload(rs.get(), first, &d.rule_first, 8))) return rc;
+  if ((rc = upload(rs.get(), H.alpha, &d.rule_alpha, 8))) return rc;
   d.n_rules = n_rules; d.rw = (n_rules + 31) / 32; if (d.rw == 0) d.rw = 1;
   d.max_prog_len = 0; for (uint32_t i = 0; i < n_rules; i++) d.max_prog_len = std::max(d.max_prog_len, prog_off[i + 1] - prog_off[i]);
   *out = rs.release();

@@ -18,7 +18,7 @@ struct DevRuleset {
   const uint32_t* acc_index;     // nstates*ncols: accept id of an accepting transition
   const uint32_t* acc_offsets;   // CSR over accept ids -> factor ids
   const uint32_t* acc_factors;
-  const uint32_t* factors;       // 10 words per full factor: rule, len|win_off<<8|win_len<<16|exact<<24, 16 x u16 set ids
+  const uint32_t* factors;       // 12 words per full factor: rule, len|win_off<<8|win_len<<16|exact<<24, 16 x u16 set ids, max prefix units, pad
   const uint32_t* bytesets;      // 8 words per 256-bit byte set
   const uint32_t* always_rules;  // candidates for every message
   uint32_t n_always;
@@ -27,6 +27,7 @@ struct DevRuleset {
   const uint32_t* sets;          // 6 words per unit set: ascii[4], range_off, n_ranges
   const uint16_t* set_ranges;    // inclusive lo,hi pairs
   const uint32_t* rule_first;    // 8 words per rule: first-byte bitmap
+  const uint32_t* rule_alpha;    // 8 words per rule: alphabet bitmap (bytes a match can contain)
   uint32_t n_rules;
   uint32_t rw;                   // bitmap words per slot = ceil(n_rules / 32)
 };
@@ -42,6 +43,8 @@ struct ScanWork {
   uint32_t* cand;                // [slot_cap * rw]  candidate (msg,rule) pairs already queued
   uint32_t* hit;                 // [slot_cap * rw]  verified pairs
   uint2* events;                 // [event_cap]  (slot, rule) for the Pike VM
+  uint32_t* event_pos;           // [event_cap]  policy mode: message offset of the confirmed factor's first byte
+  uint32_t* event_pre;           // [event_cap]  policy mode: max units of a match before that factor (0xffff = unbounded)
   uint32_t* spans;               // [span_cap * 6] msg, rule, start_byte, end_byte, start16, end16
   uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap;
 };

@@ -142,7 +142,7 @@ struct VMS {
 
   // One leftmost-first search starting at byte `from` (unit index from16, unit before it `prev`).
   CG_HD_NOINLINE bool search(const uint8_t* __restrict__ m, uint32_t len, uint32_t from, uint32_t from16, int prev,
-                         const uint32_t* __restrict__ first, Cursor cur_c) {
+                         const uint32_t* __restrict__ first, Cursor cur_c, uint32_t start_limit = 0xffffffffu, bool first_match_only = false) {
     matched = false;
     Cursor c = cur_c;                 // cursor sits at `from`
     uint32_t pos = from, upos = from16;
@@ -150,12 +150,14 @@ struct VMS {
     int L = 0; cnt[0] = 0; bump_gen();
     add(L, 0, pos, prev, cur, pos, upos);
     for (;;) {
+      if (matched && first_match_only) break;
       if (cnt[L] == 0) {
         if (matched || cur < 0) break;
         // Nothing alive and the start at `pos` has already failed: move on, skipping ASCII units
         // that cannot begin a match (first-unit filter; nullable rules have an all-ones filter).
         do { prev = cur; pos = cn.pos; upos++; c = cn; cur = next_unit(m, len, cn); }
         while (cur >= 0 && cur < 128 && !((first[cur >> 5] >> (cur & 31)) & 1u));
+        if (pos > start_limit) break;
         bump_gen();
         add(L, 0, pos, prev, cur, pos, upos);
         continue;
@@ -175,7 +177,7 @@ struct VMS {
       // new lowest-priority start at npos -- skipped when the unit there cannot begin a match
       // (first-unit filter; a start thread that cannot consume its first unit dies immediately,
       // and rules that can match the empty string have an all-ones filter)
-      if (!cut && !matched && !(nxt >= 0 && nxt < 128 && !((first[nxt >> 5] >> (nxt & 31)) & 1u)))
+      if (!cut && !matched && npos <= start_limit && !(nxt >= 0 && nxt < 128 && !((first[nxt >> 5] >> (nxt & 31)) & 1u)))
         add(N, 0, npos, cur, nxt, npos, nupos);
       L = N; prev = cur; pos = npos; upos = nupos; c = cn; cn = cnn; cur = nxt;
     }
@@ -229,6 +231,45 @@ CG_HD_NOINLINE bool run_rule(VMX& vm, const DevRuleset& rs, uint32_t rule, const
     }
   }
   return any;
+}
+
+// the unit that ends at byte `at` (a unit boundary), or -1 at the start of the message
+CG_HD_NOINLINE int unit_before(const uint8_t* __restrict__ m, uint32_t len, uint32_t at) {
+  if (at == 0) return -1;
+  uint32_t q = at - 1; int back = 0;
+  while (q > 0 && back < 3 && (m[q] & 0xc0) == 0x80) { q--; back++; }
+  Cursor c{q, 0}; int last = -1;
+  while (c.pos < at || (c.pending && c.pos + 2 <= at)) { int u = next_unit(m, len, c); if (u < 0) break; last = u; }
+  return last;
+}
+
+// RegExp.test restricted to the matches that contain the confirmed factor occurrence m[t0, t0+flen):
+// such a match lies inside the "island" of bytes from the rule's alphabet around the factor, so the
+// search starts at the island's first byte, spawns no start thread beyond t0 and stops at the first
+// MATCH.  Every true match contains some confirmed occurrence of a factor, hence testing every
+// occurrence this way is exactly RegExp.test(message).
+template <class VMX>
+CG_HD_NOINLINE bool test_at_factor(VMX& vm, const DevRuleset& rs, uint32_t rule, const uint8_t* __restrict__ m, uint32_t len,
+                                   uint32_t t0, uint32_t pre_units) {
+  vm.prog = rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
+  if (vm.plen == 0) return false;
+  if (vm.plen > VMX::capacity()) { vm.err |= ERR_VM_LIST; return false; }
+  for (uint32_t k = 0; k < vm.plen; k++) vm.S.mark(k) = 0;
+  vm.gen = 0;
+  const uint32_t* first = rs.rule_first + (size_t)rule * 8;
+  const uint32_t* alpha = rs.rule_alpha + (size_t)rule * 8;
+  if (t0 > len) t0 = len;
+  uint32_t s = t0;
+  while (s > 0 && ((alpha[m[s - 1] >> 5] >> (m[s - 1] & 31)) & 1u)) s--;
+  // s is a unit boundary: it is 0 or follows a byte outside the alphabet
+  if (pre_units < 0xffffu) {
+    // the pattern puts at most pre_units units (<= 3 bytes each) before the factor
+    uint32_t sb = t0 > 3u * pre_units ? t0 - 3u * pre_units : 0u;
+    for (int k = 0; k < 3 && sb > 0 && (m[sb] & 0xc0) == 0x80; k++) sb--;     // back to the start of a character
+    if (sb > s) s = sb;
+  }
+  Cursor c = cursor_at(m, len, s);
+  return vm.search(m, len, s, 0, unit_before(m, len, s), first, c, t0, true);
 }
 
 }  // namespace cg

@@ -40,9 +40,10 @@ CG_HD_NOINLINE void l1_accept(const DevRuleset& rs, uint32_t state, uint32_t col
   const uint32_t aid = rs.acc_index[((size_t)state << rs.ncols_log2) + col];
   if (aid == 0xffffffffu) return;
   for (uint32_t k = rs.acc_offsets[aid]; k < rs.acc_offsets[aid + 1]; k++) {
-    const uint32_t* fw = rs.factors + (size_t)rs.acc_factors[k] * 10;
+    const uint32_t* fw = rs.factors + (size_t)rs.acc_factors[k] * 12;
     if (confirm_factor(rs, fw, m, len, pend)) {
-      if ((fw[1] >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0]);
+      const uint32_t meta = fw[1], t0 = pend + 1 - (((meta >> 8) & 0xff) + ((meta >> 16) & 0xff));   // factor start in the message
+      if ((meta >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0], t0, fw[10]);
     }
   }
 }

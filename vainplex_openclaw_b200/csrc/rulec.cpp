@@ -432,7 +432,20 @@ struct Compiler {
     bool is_exact_tight = false;        // `exact` IS the language (no over-approximation, no assertions)
     bool has_factors = false;           // every match contains one of `factors` as a substring
     std::vector<FactorSeq> factors;
+    int fpre = 0;                       // max units of the node's match that can precede that factor occurrence (kPreInf = unbounded)
   };
+  static constexpr int kPreInf = 1 << 20;
+  int maxlen(int n) const {
+    const Node& nd = N(n); long v = 0;
+    switch (nd.type) {
+      case T_CHAR: case T_ANY: case T_SET: return 1;
+      case T_CAT: for (int k : nd.kids) { v += maxlen(k); if (v >= kPreInf) return kPreInf; } return (int)v;
+      case T_ALT: for (int k : nd.kids) v = std::max<long>(v, maxlen(k)); return (int)v;
+      case T_GROUP: return maxlen(nd.kids[0]);
+      case T_REPEAT: { if (nd.max == INF) return maxlen(nd.kids[0]) ? kPreInf : 0; long m = (long)nd.max * maxlen(nd.kids[0]); return m >= kPreInf ? kPreInf : (int)m; }
+      default: return 0;
+    }
+  }
   static constexpr size_t kMaxSeqs = 24;
   static constexpr size_t kMaxRunLen = 16;
 
@@ -486,10 +499,10 @@ struct Compiler {
     return true;
   }
 
-  static void consider(std::vector<FactorSeq>& best, bool& have, const std::vector<FactorSeq>& cand) {
+  static void consider(std::vector<FactorSeq>& best, bool& have, int& best_pre, const std::vector<FactorSeq>& cand, int cand_pre) {
     if (cand.empty()) return;
     for (auto& s : cand) if (s.empty()) return;
-    if (!have || score(cand) < score(best)) { best = cand; have = true; }
+    if (!have || score(cand) < score(best)) { best = cand; have = true; best_pre = std::min(cand_pre, kPreInf); }
   }
 
   Info analyse(int n) const {
@@ -511,7 +524,7 @@ struct Compiler {
           Info c = analyse(k);
           if (c.has_exact) ex.insert(ex.end(), c.exact.begin(), c.exact.end()); else all_exact = false;
           tight = tight && c.is_exact_tight;
-          if (c.has_factors) fa.insert(fa.end(), c.factors.begin(), c.factors.end()); else all_fact = false;
+          if (c.has_factors) { fa.insert(fa.end(), c.factors.begin(), c.factors.end()); I.fpre = std::max(I.fpre, c.fpre); } else all_fact = false;
         }
         if (all_exact && ex.size() <= kMaxSeqs) { I.has_exact = true; I.exact = ex; I.is_exact_tight = tight; }
         if (all_fact && fa.size() <= 4 * kMaxSeqs) { I.has_factors = true; I.factors = fa; }
@@ -537,20 +550,29 @@ struct Compiler {
             if (ok && nd.min == nd.max && copies == nd.min) { I.has_exact = true; I.exact = run; I.is_exact_tight = b.is_exact_tight; }
           }
         }
-        std::vector<FactorSeq> best; bool hb = false;
-        if (have) consider(best, hb, run);
-        if (b.has_factors) consider(best, hb, b.factors);
-        if (hb) { I.has_factors = true; I.factors = best; }
+        std::vector<FactorSeq> best; bool hb = false; int bpre = 0;
+        if (have) consider(best, hb, bpre, run, 0);
+        if (b.has_factors) {
+          int ml = maxlen(nd.kids[0]);
+          long before = nd.max == INF ? (ml ? kPreInf : 0) : (long)(nd.max - 1) * ml;
+          consider(best, hb, bpre, b.factors, (int)std::min<long>(before + b.fpre, kPreInf));
+        }
+        if (hb) { I.has_factors = true; I.factors = best; I.fpre = bpre; }
         return I;
       }
       case T_CAT: {
         std::vector<FactorSeq> run = {FactorSeq{}}; bool run_tight = true;
-        std::vector<FactorSeq> best; bool hb = false;
+        std::vector<FactorSeq> best; bool hb = false; int bpre = 0;
         bool all_exact = true, tight = true;
-        auto close_run = [&]() { bool nonempty = false; for (auto& s : run) if (!s.empty()) nonempty = true; bool allne = true; for (auto& s : run) if (s.empty()) allne = false; if (nonempty && allne) consider(best, hb, run); run = {FactorSeq{}}; };
+        long pos = 0; int run_pre = 0;      // pos: max units consumed by the children before the current one
+        auto run_is_empty = [&]() { return run.size() == 1 && run[0].empty(); };
+        auto close_run = [&]() { bool nonempty = false; for (auto& s : run) if (!s.empty()) nonempty = true; bool allne = true; for (auto& s : run) if (s.empty()) allne = false; if (nonempty && allne) consider(best, hb, bpre, run, run_pre); run = {FactorSeq{}}; };
         for (int k : nd.kids) {
           Info c = analyse(k);
-          if (c.has_factors) consider(best, hb, c.factors);
+          const int pre_k = (int)std::min<long>(pos, kPreInf);
+          pos = std::min<long>(pos + maxlen(k), kPreInf);
+          if (c.has_factors) consider(best, hb, bpre, c.factors, (int)std::min<long>((long)pre_k + c.fpre, kPreInf));
+          if (run_is_empty()) run_pre = pre_k;
           // a REPEAT with min>=1 contributes its required prefix to the run and then breaks it
           const Node& kn = N(k);
           bool breaks_after = false;
@@ -584,15 +606,15 @@ struct Compiler {
             if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; }
             nx.push_back(s);
           }
-          if (nx.size() > kMaxSeqs) { all_exact = false; close_run(); run = piece; if (run.size() > kMaxSeqs) run = {FactorSeq{}}; for (auto& s : run) if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; } }
+          if (nx.size() > kMaxSeqs) { all_exact = false; close_run(); run = piece; run_pre = pre_k; if (run.size() > kMaxSeqs) run = {FactorSeq{}}; for (auto& s : run) if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; } }
           else run.swap(nx);
           if (cut) { all_exact = false; close_run(); }
           if (breaks_after) { all_exact = false; close_run(); }
         }
         if (all_exact) { I.has_exact = true; I.exact = run; I.is_exact_tight = tight && run_tight; }
         close_run();
-        if (hb) { I.has_factors = true; I.factors = best; }
-        if (I.has_exact && !I.has_factors) { bool allne = true; for (auto& s : I.exact) if (s.empty()) allne = false; if (allne && !I.exact.empty()) { I.has_factors = true; I.factors = I.exact; } }
+        if (hb) { I.has_factors = true; I.factors = best; I.fpre = bpre; }
+        if (I.has_exact && !I.has_factors) { bool allne = true; for (auto& s : I.exact) if (s.empty()) allne = false; if (allne && !I.exact.empty()) { I.has_factors = true; I.factors = I.exact; I.fpre = 0; } }
         return I;
       }
     }
@@ -643,12 +665,19 @@ CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
       Ranges f; c.first(root, f); normalise(f);
       for (auto& p : f) { for (int b = p.first; b <= std::min(p.second, 127); b++) out.first_bytes.set(b); if (p.second >= 128) for (int b = 128; b < 256; b++) out.first_bytes.set(b); }
     }
+    // alphabet: union of everything the pattern can consume (a match never contains other bytes)
+    for (const Node& nd : ps.nodes) {
+      if (nd.type != T_CHAR && nd.type != T_ANY && nd.type != T_SET) continue;
+      Ranges r = nd.type == T_CHAR ? Ranges{{nd.ch, nd.ch}} : nd.type == T_ANY ? Compiler::any_set() : nd.set;
+      for (auto& p : r) { for (int b = p.first; b <= std::min(p.second, 127); b++) out.alphabet.set(b); if (p.second >= 128) for (int b = 128; b < 256; b++) out.alphabet.set(b); }
+    }
     if (!out.nullable) {
       Compiler::Info I = c.analyse(root);
       if (I.has_factors) {
         bool ok = !I.factors.empty(); for (auto& s : I.factors) if (s.empty()) ok = false;
         if (ok) {
           out.factors = I.factors;
+          out.factor_pre = I.fpre;
           out.factors_exact = I.has_exact && I.is_exact_tight && I.exact == I.factors;
         }
       }
@@ -729,6 +758,7 @@ bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOpti
     for (auto& f : rules[r].factors) {
       FullFactor ff{}; ff.rule = (uint32_t)r; ff.len = (uint8_t)std::min<size_t>(f.size(), kMaxFactorElems);
       ff.exact = (rules[r].factors_exact && f.size() <= (size_t)kMaxFactorElems) ? 1 : 0;
+      ff.pre = rules[r].factor_pre >= 0xffff ? 0xffff : (uint16_t)rules[r].factor_pre;
       for (int k = 0; k < ff.len; k++) ff.elem[k] = set_id(f[k]);
       P.factors.push_back(ff); seqs.push_back(FactorSeq(f.begin(), f.begin() + ff.len));
     }

@@ -68,7 +68,9 @@ struct CompiledRule {
   std::vector<UnitSet> sets;        // rule-local sets; OP_SET args index this (remapped globally later)
   bool nullable = false;            // matches the empty string somewhere
   ByteSet first_bytes;              // bytes that can start a match (all-ones when nullable)
+  ByteSet alphabet;                 // every byte any consuming instruction could accept (over-approximation)
   std::vector<FactorSeq> factors;   // necessary factors; empty => rule is an "always candidate"
+  int factor_pre = 1 << 20;         // max units of a match that can precede the factor occurrence (>= 0xffff: unbounded)
   bool factors_exact = false;       // every match IS one of the factors (pure literal alternation, no assertions)
 };
 
@@ -91,6 +93,7 @@ struct FullFactor {
   uint32_t rule;
   uint8_t len, win_off, win_len, exact;   // exact: a confirmed occurrence proves the rule matches (RegExp.test)
   uint16_t elem[kMaxFactorElems];         // byte-set ids
+  uint16_t pre;                           // max units of a match before the factor (0xffff = unbounded)
 };
 struct Prefilter {
   int mode = 2;

@@ -13,6 +13,7 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   for (uint32_t i = 0; i < n; i++) H.rules[i] = compile_rule(src[i].src ? src[i].src : "", src[i].len, src[i].flags);
   H.prog_off.assign((size_t)n + 1, 0);
   H.first.assign(8 * (size_t)std::max<uint32_t>(n, 1), 0);
+  H.alpha.assign(8 * (size_t)std::max<uint32_t>(n, 1), 0);
   for (uint32_t i = 0; i < n; i++) {
     H.prog_off[i] = (uint32_t)H.prog.size();
     CompiledRule& r = H.rules[i];
@@ -30,6 +31,7 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
       H.prog.push_back(op | (arg << 8));
     }
     for (int k = 0; k < 8; k++) H.first[(size_t)i * 8 + k] = (uint32_t)(r.first_bytes.w[k >> 1] >> (32 * (k & 1)));
+    for (int k = 0; k < 8; k++) H.alpha[(size_t)i * 8 + k] = (uint32_t)(r.alphabet.w[k >> 1] >> (32 * (k & 1)));
   }
   H.prog_off[n] = (uint32_t)H.prog.size();
   H.n_sets = (uint32_t)(H.sets.size() / 6);
@@ -46,6 +48,7 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     H.factor_words.push_back(f.rule);
     H.factor_words.push_back((uint32_t)f.len | ((uint32_t)f.win_off << 8) | ((uint32_t)f.win_len << 16) | ((uint32_t)f.exact << 24));
     for (int k = 0; k < kMaxFactorElems; k += 2) H.factor_words.push_back((uint32_t)f.elem[k] | ((uint32_t)f.elem[k + 1] << 16));
+    H.factor_words.push_back(f.pre); H.factor_words.push_back(0);
   }
   H.image.assign(256 + (size_t)H.hot_states * H.pf.ncols * 2, 0);
   memcpy(H.image.data(), H.pf.lut, 256);

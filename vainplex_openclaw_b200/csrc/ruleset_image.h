@@ -12,8 +12,8 @@ struct HostImage {
   Prefilter pf;
   std::vector<uint8_t> image;          // [lut 256][first hot_states rows of the table], padded to 16 bytes
   uint32_t hot_states = 0;             // rows resident in shared memory
-  std::vector<uint32_t> prog, prog_off, sets, first;
-  std::vector<uint32_t> factor_words;  // 10 words per full factor (device layout)
+  std::vector<uint32_t> prog, prog_off, sets, first, alpha;
+  std::vector<uint32_t> factor_words;  // 12 words per full factor (device layout)
   std::vector<uint16_t> ranges;
   uint32_t n_sets = 0;
 };

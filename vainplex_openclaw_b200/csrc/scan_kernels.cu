@@ -187,7 +187,7 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
 // ------------------------------------------------------------------------------------------
 struct SlotSink {
   const DevRuleset& rs; const ScanWork& w; uint32_t msg; uint32_t slot;
-  __device__ SlotSink(const DevRuleset& r, const ScanWork& wk, uint32_t m) : rs(r), w(wk), msg(m), slot(0xffffffffu) {}
+  __device__ SlotSink(const DevRuleset& r, const ScanWork& wk, uint32_t m, bool ws) : rs(r), w(wk), msg(m), slot(0xffffffffu), want_spans(ws) {}
   __device__ bool ensure_slot() {
     if (slot != 0xffffffffu) return slot < w.slot_cap;
     uint32_t s = *reinterpret_cast<volatile uint32_t*>(&w.slot_of_msg[msg]);
@@ -203,13 +203,25 @@ struct SlotSink {
     slot = s;
     return true;
   }
-  __device__ void candidate(uint32_t r) {
+  // spans mode: one VM run per (message, rule), over the whole message (cand bitmap dedupes).
+  // policy mode: one VM run per confirmed factor occurrence, restricted to its island.
+  bool want_spans;
+  __device__ void candidate(uint32_t r, uint32_t t0, uint32_t pre) {
+    if (!ensure_slot()) return;
+    uint32_t bit = 1u << (r & 31);
+    uint32_t old = atomicOr(&w.cand[(size_t)slot * rs.rw + (r >> 5)], bit);
+    if (want_spans && (old & bit)) return;
+    uint32_t e = atomicAdd(&w.counters[1], 1u);
+    if (e < w.event_cap) { w.events[e] = make_uint2(slot, r); w.event_pos[e] = t0; w.event_pre[e] = pre; } else atomicOr(&w.counters[3], ERR_EVENT_OVERFLOW);
+  }
+  // rules without factors: one whole-message run (event_pos = 0xffffffff)
+  __device__ void candidate_always(uint32_t r) {
     if (!ensure_slot()) return;
     uint32_t bit = 1u << (r & 31);
     uint32_t old = atomicOr(&w.cand[(size_t)slot * rs.rw + (r >> 5)], bit);
     if (old & bit) return;
     uint32_t e = atomicAdd(&w.counters[1], 1u);
-    if (e < w.event_cap) w.events[e] = make_uint2(slot, r); else atomicOr(&w.counters[3], ERR_EVENT_OVERFLOW);
+    if (e < w.event_cap) { w.events[e] = make_uint2(slot, r); w.event_pos[e] = 0xffffffffu; } else atomicOr(&w.counters[3], ERR_EVENT_OVERFLOW);
   }
   // a confirmed exact factor already proves RegExp.test(message) for this rule
   __device__ void direct(uint32_t r) {
@@ -225,8 +237,8 @@ confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, con
   const uint32_t n1 = min(w.counters[4], w.l1_cap);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
     const uint32_t msg = w.l1_msg[i], pos = w.l1_pos[i], sc = w.l1_sc[i];
-    SlotSink sink(rs, w, msg);
-    if (sc == kL1Always) { for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate(rs.always_rules[k]); continue; }
+    SlotSink sink(rs, w, msg, want_spans != 0);
+    if (sc == kL1Always) { for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate_always(rs.always_rules[k]); continue; }
     const uint32_t b = off[msg];
     l1_accept(rs, sc >> 8, sc & 0xffu, bytes + b, off[msg + 1] - b, pos, want_spans != 0, sink);
   }
@@ -278,7 +290,13 @@ verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
     if (plen > (uint32_t)kSmallProg) continue;          // handled by verify_large_kernel
     uint32_t msg = w.slot_msg[slot];
     GlobalSpanSink sink{w, msg, rule};
-    bool any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
+    const uint32_t t0 = w.event_pos[e];
+    bool any;
+    if (SPANS || t0 == 0xffffffffu) any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
+    else {
+      if ((w.hit[(size_t)slot * rs.rw + (rule >> 5)] >> (rule & 31)) & 1u) continue;     // another occurrence already proved it
+      any = test_at_factor(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], t0, w.event_pre[e]);
+    }
     if (any) atomicOr(&w.hit[(size_t)slot * rs.rw + (rule >> 5)], 1u << (rule & 31));
   }
   if (vm.err) atomicOr(&w.counters[3], vm.err);
@@ -297,7 +315,13 @@ verify_large_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
     if (plen <= (uint32_t)kSmallProg) continue;
     uint32_t msg = w.slot_msg[slot];
     GlobalSpanSink sink{w, msg, rule};
-    bool any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
+    const uint32_t t0 = w.event_pos[e];
+    bool any;
+    if (SPANS || t0 == 0xffffffffu) any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
+    else {
+      if ((w.hit[(size_t)slot * rs.rw + (rule >> 5)] >> (rule & 31)) & 1u) continue;     // another occurrence already proved it
+      any = test_at_factor(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], t0, w.event_pre[e]);
+    }
     if (any) atomicOr(&w.hit[(size_t)slot * rs.rw + (rule >> 5)], 1u << (rule & 31));
   }
   if (vm.err) atomicOr(&w.counters[3], vm.err);
