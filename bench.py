@@ -133,6 +133,8 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from vainplex_openclaw_b200 import _native as N, workload as W
@@ -185,10 +187,13 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = N.launch_count() - l0
     clocks = sampler.stop() if sampler else None
+    per_rank_ms = [ms / args.steps]
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        allt = torch.zeros(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allt, t)
+        per_rank_ms = [float(x) / args.steps for x in allt.tolist()]
+        ms = float(allt.max().item())
         dist.barrier()
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
@@ -316,7 +321,7 @@ def main():
                 "steps": e2e_steps, "words_equal_device_path": same},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "extra": {"merkle": merkle},
+        "extra": {"merkle": merkle, "per_rank_ms_per_step": per_rank_ms},
     }
     print(json.dumps(line))
     if world > 1:

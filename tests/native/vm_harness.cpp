@@ -112,7 +112,7 @@ void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand,
     uint32_t col = l1_col(d.mode, lut, m[i]);
     uint32_t ent = table[(state << d.ncols_log2) + col];
     if (ent & 0x8000u) { hits++; l1_accept(d, state, col, m, len, i, want_spans != 0, sink); }
-    state = ent & 0x7fffu;
+    state = ent & 0x3fffu;
   }
   if (l1_hits) *l1_hits = hits;
 }
@@ -132,7 +132,7 @@ void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits
     uint32_t col = l1_col(d.mode, lut, m[i]);
     uint32_t ent = table[(state << d.ncols_log2) + col];
     if (ent & 0x8000u) l1_accept(d, state, col, m, len, i, false, sink);
-    state = ent & 0x7fffu;
+    state = ent & 0x3fffu;
   }
   VM vm(d);
   struct Null { void span(uint32_t, uint32_t, uint32_t, uint32_t) {} } ns;
@@ -153,7 +153,7 @@ void harness_l1_factor_counts(void* p, const uint8_t* m, uint32_t len, uint32_t*
     uint32_t col = l1_col(d.mode, lut, m[i]);
     uint32_t ent = table[(state << d.ncols_log2) + col];
     if (ent & 0x8000u) { uint32_t aid = d.acc_index[((size_t)state << d.ncols_log2) + col]; for (uint32_t k = d.acc_offsets[aid]; k < d.acc_offsets[aid + 1]; k++) counts[d.acc_factors[k]]++; }
-    state = ent & 0x7fffu;
+    state = ent & 0x3fffu;
   }
 }
 

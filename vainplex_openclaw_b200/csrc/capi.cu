@@ -68,7 +68,11 @@ struct cg_ruleset {
   std::vector<void*> allocs;
   uint32_t n_sets = 0, program_words = 0;
   ScanWork work{};
+  // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
+  cudaGraphExec_t graph = nullptr;
+  const void* g_bytes = nullptr; const void* g_off = nullptr; void* g_words = nullptr; uint32_t g_n = 0; uint32_t g_caps[4] = {0, 0, 0, 0};
   ~cg_ruleset() {
+    if (graph) cudaGraphExecDestroy(graph);
     for (void* p : allocs) cudaFree(p);
     cudaFree(work.l1_msg); cudaFree(work.l1_pos); cudaFree(work.l1_sc); cudaFree(work.slot_of_msg);
     cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
@@ -130,6 +134,8 @@ int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_of
   CU(cudaGetLastError());
   return CG_OK;
 }
+
+void prepare_kernels() { static bool done = false; if (!done) { prepare_scan_kernels(); done = true; } }
 
 struct HostScan {
   std::vector<uint32_t> counters, slot_msg, hit, spans;
@@ -281,6 +287,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode;
   d.ncols_log2 = 0; while ((1 << d.ncols_log2) < P.ncols) d.ncols_log2++;
   d.nstates = (uint32_t)P.nstates; d.hot_states = H.hot_states;
+  d.scan_streams = 1; if (const char* e = getenv("CG_SCAN_STREAMS")) d.scan_streams = (uint32_t)atoi(e);
   if ((rc = upload(rs.get(), P.table, &d.table_full, 64))) return rc;
   if ((rc = upload(rs.get(), P.acc_index, &d.acc_index))) return rc;
   if ((rc = upload(rs.get(), P.acc_offsets, &d.acc_offsets))) return rc;
@@ -297,6 +304,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), H.alpha, &d.rule_alpha, 8))) return rc;
   d.n_rules = n_rules; d.rw = (n_rules + 31) / 32; if (d.rw == 0) d.rw = 1;
   d.max_prog_len = 0; for (uint32_t i = 0; i < n_rules; i++) d.max_prog_len = std::max(d.max_prog_len, prog_off[i + 1] - prog_off[i]);
+  prepare_kernels();
   *out = rs.release();
   return CG_OK;
 }
@@ -405,7 +413,29 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   if (rc) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
   if (!n) return CG_OK;
-  rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
+  static const bool use_graph = !(getenv("CG_NO_GRAPH") && atoi(getenv("CG_NO_GRAPH")));
+  if (!use_graph || G.profiling) {
+    rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
+  } else {
+    // memset + scan + confirm + verify + finalize captured once per (arguments, capacities), then replayed:
+    // one launch per step instead of seven, so the host never becomes the bottleneck
+    const ScanWork& w = rs->work;
+    const uint32_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
+    if (!rs->graph || rs->g_bytes != d_bytes || rs->g_off != d_offsets || rs->g_words != d_out_words || rs->g_n != n || memcmp(caps, rs->g_caps, sizeof caps)) {
+      if (rs->graph) { cudaGraphExecDestroy(rs->graph); rs->graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
+      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (rc != CG_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc != CG_OK ? rc : cuda_fail(e, "cudaStreamEndCapture"); }
+      e = cudaGraphInstantiate(&rs->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) { rs->graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
+      rs->g_bytes = d_bytes; rs->g_off = d_offsets; rs->g_words = d_out_words; rs->g_n = n; memcpy(rs->g_caps, caps, sizeof caps);
+    }
+    CU(cudaGraphLaunch(rs->graph, st));
+    G.launches += 5; G.stats.kernel_launches += 5;       // kernels inside the graph (scan, confirm, verify, finalize + optional large-VM)
+  }
   if (rc == CG_OK) { G.stats.messages_scanned += n; }
   return rc;
 }

@@ -13,7 +13,8 @@ struct DevRuleset {
   uint32_t max_prog_len;         // longest Pike program of the set (picks the VM capacity)
   uint32_t ncols_log2;
   uint32_t nstates;
-  uint32_t hot_states;           // rows [0, hot_states) are in the shared-memory image, the rest only in table_full
+  uint32_t hot_states;           // rows [0, hot_states) + one trap row are in the shared-memory image, the rest only in table_full
+  uint32_t scan_streams;         // message streams per lane in scan_kernel (1 or 2)
   const uint16_t* table_full;    // complete level-1 table in HBM (L2-resident)
   const uint32_t* acc_index;     // nstates*ncols: accept id of an accepting transition
   const uint32_t* acc_offsets;   // CSR over accept ids -> factor ids
@@ -59,6 +60,9 @@ int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byt
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream);
 int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, int sm_count, cudaStream_t stream);
+
+// raises the dynamic shared-memory limits of every kernel once (not legal inside stream capture)
+void prepare_scan_kernels();
 
 // SHA-256 / Merkle
 int launch_sha256_batch(const uint8_t* d_bytes, const uint64_t* d_off, uint32_t n, uint8_t* d_out, cudaStream_t stream);

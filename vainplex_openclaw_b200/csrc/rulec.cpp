@@ -719,7 +719,7 @@ static bool build_dfa(const std::vector<L1Pattern>& pats, int ncols, int max_sta
       for (uint32_t q : start_by_col[c]) { if (pats[q].cols.size() == 1) done.push_back(q); else nk.push_back({q, 1}); }
       std::sort(nk.begin(), nk.end()); nk.erase(std::unique(nk.begin(), nk.end()), nk.end());
       int nid = intern(std::move(nk));
-      if ((int)states.size() > max_states || states.size() > 32767) return false;
+      if ((int)states.size() > max_states || states.size() > 16383) return false;
       uint32_t aid = 0xffffffffu;
       if (!done.empty()) {
         std::vector<uint32_t> fs; for (uint32_t q : done) fs.insert(fs.end(), pats[q].factors.begin(), pats[q].factors.end());

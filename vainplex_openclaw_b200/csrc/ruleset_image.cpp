@@ -41,18 +41,28 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   int cols = po.mode == 0 ? 128 : po.mode == 2 ? 64 : po.mode == 3 ? 32 : (po.max_classes <= 32 ? 32 : 64);
   size_t budget = std::max<size_t>(opt.budget_bytes, 256 + (size_t)cols * 2 * 2);
   size_t hot_rows = std::min<size_t>((budget - 256) / ((size_t)cols * 2), 32767);
-  po.max_states = std::max<int>((int)std::min<size_t>((size_t)std::max(opt.max_states, 1), 32767), 1);
+  po.max_states = std::max<int>((int)std::min<size_t>((size_t)std::max(opt.max_states, 1), 16383), 1);
   if (!build_prefilter(H.rules, po, &H.pf, err)) return false;
-  H.hot_states = (uint32_t)std::min<size_t>(hot_rows, (size_t)H.pf.nstates);
   for (auto& f : H.pf.factors) {
     H.factor_words.push_back(f.rule);
     H.factor_words.push_back((uint32_t)f.len | ((uint32_t)f.win_off << 8) | ((uint32_t)f.win_len << 16) | ((uint32_t)f.exact << 24));
     for (int k = 0; k < kMaxFactorElems; k += 2) H.factor_words.push_back((uint32_t)f.elem[k] | ((uint32_t)f.elem[k + 1] << 16));
     H.factor_words.push_back(f.pre); H.factor_words.push_back(0);
   }
-  H.image.assign(256 + (size_t)H.hot_states * H.pf.ncols * 2, 0);
+  // shared-memory image: rows [0, hot) with every transition into a deeper state redirected to the
+  // trap row `hot` (flag 0x4000), followed by the trap row itself
+  H.hot_states = (uint32_t)std::min<size_t>(hot_rows > 1 ? hot_rows - 1 : 1, (size_t)H.pf.nstates);
+  const uint32_t hot = H.hot_states; const size_t nc = (size_t)H.pf.ncols;
+  std::vector<uint16_t> img((size_t)(hot + 1) * nc);
+  for (uint32_t s = 0; s < hot; s++) for (size_t c = 0; c < nc; c++) {
+    uint16_t e = H.pf.table[(size_t)s * nc + c];
+    if ((uint32_t)(e & 0x3fff) >= hot) e = (uint16_t)((e & 0x8000) | 0x4000 | hot);
+    img[(size_t)s * nc + c] = e;
+  }
+  for (size_t c = 0; c < nc; c++) img[(size_t)hot * nc + c] = (uint16_t)(0x4000 | hot);
+  H.image.assign(256 + img.size() * 2, 0);
   memcpy(H.image.data(), H.pf.lut, 256);
-  memcpy(H.image.data() + 256, H.pf.table.data(), (size_t)H.hot_states * H.pf.ncols * 2);
+  memcpy(H.image.data() + 256, img.data(), img.size() * 2);
   while (H.image.size() % 16) H.image.push_back(0);
   return true;
 }

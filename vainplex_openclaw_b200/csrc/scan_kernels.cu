@@ -54,10 +54,12 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// level 1: prefilter scan.  lane-per-message, streaming 16-byte loads, table in shared memory
+// level 1: prefilter scan.  lane-per-message (NS interleaved message streams per lane), streaming
+// 16-byte loads, table in shared memory
 // ------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 1024;
 constexpr uint32_t kL1Always = 0xffffffffu;
+constexpr uint32_t kAccept = 0x8000u, kCold = 0x4000u, kStateMask = 0x3fffu;
 
 // pre-doubled column indices of the four bytes of a word (one byte each), SWAR
 template <int MODE> __device__ __forceinline__ uint32_t cols2_of_word(uint32_t w);
@@ -68,15 +70,23 @@ template <> __device__ __forceinline__ uint32_t cols2_of_word<1>(uint32_t w) { r
 
 template <int MODE> struct RowBytes { static constexpr uint32_t v = MODE == 0 ? 256u : MODE == 3 ? 64u : 128u; };
 
-// one level-1 transition: the raw table entry (bit 15 = accepting transition).  Rows of the shallow
-// (hot) states come from shared memory; the rare deep states read their row from the L2-resident copy.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+
+// One level-1 transition out of the shared-memory image (32-bit shared addresses, no generic
+// loads).  Rows [0, hot) are real; row `hot` is a trap row (every entry = hot | kCold) and every
+// hot-row transition into a deep state is stored as hot | kCold, so the fast path never leaves
+// shared memory: an excursion into deep states only raises kCold, and the flagged word is then
+// re-walked on the full table in HBM/L2 by the (rare) slow path, which also restores the state.
 template <int MODE>
-__device__ __forceinline__ uint32_t l1_step(const uint8_t* __restrict__ tbl, const uint8_t* __restrict__ gtbl, const uint8_t* __restrict__ lut,
-                                            uint32_t row_shift, uint32_t hot, uint32_t state, uint32_t c2) {
-  uint32_t o;
-  if (MODE == 1) o = (state << row_shift) + 2u * lut[c2]; else o = state * RowBytes<MODE>::v + c2;
-  if (state < hot) return *reinterpret_cast<const uint16_t*>(tbl + o);
-  return __ldg(reinterpret_cast<const uint16_t*>(gtbl + o));
+__device__ __forceinline__ uint32_t l1_fast(uint32_t tbl_s, uint32_t lut_s, uint32_t row_shift, uint32_t state, uint32_t c2) {
+  if (MODE == 1) return lds_u16(tbl_s + (state << row_shift) + 2u * lds_u8(lut_s + c2));
+  return lds_u16(tbl_s + state * RowBytes<MODE>::v + c2);
+}
+
+// the complete table (deep states included), L2-resident
+__device__ __forceinline__ uint32_t l1_full(const DevRuleset& rs, uint32_t state, uint32_t col) {
+  return __ldg(rs.table_full + ((size_t)state << rs.ncols_log2) + col);
 }
 
 __device__ __forceinline__ void l1_push_one(const ScanWork& w, uint32_t msg, uint32_t pos, uint32_t sc) {
@@ -84,7 +94,7 @@ __device__ __forceinline__ void l1_push_one(const ScanWork& w, uint32_t msg, uin
   if (k < w.l1_cap) { w.l1_msg[k] = msg; w.l1_pos[k] = pos; w.l1_sc[k] = sc; } else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
 }
 
-template <int MODE>
+template <int MODE, int NS>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
             uint64_t* __restrict__ words) {
@@ -101,84 +111,126 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
   }
   mbar_wait(&bar, 0);
   const uint8_t* lut = smem;
-  const uint8_t* tbl = smem + 256;
-  const uint8_t* gtbl = reinterpret_cast<const uint8_t*>(rs.table_full);
+  const uint32_t lut_s = smem_u32(smem), tbl_s = lut_s + 256u;
   const uint32_t row_shift = rs.ncols_log2 + 1, hot = rs.hot_states;
   const uint32_t FULL = 0xffffffffu;
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kScanThreads / 32;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t ntiles = (n + 31) / 32;
+  const uint32_t per_tile = 32u * NS;
+  const uint32_t ntiles = (n + per_tile - 1) / per_tile;
   for (uint32_t tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
-    const uint32_t msg = tile * 32 + lane;
-    const bool valid = msg < n;
-    const uint32_t b = valid ? off[msg] : 0u, e = valid ? off[msg + 1] : 0u;
-    if (valid && rs.n_always) l1_push_one(w, msg, 0, kL1Always);
-    uint32_t state = 0, p = b;
-    // byte-wise, checked: the unaligned head and the tail of a message
-    auto checked = [&](uint32_t upto) {
-      for (; p < upto; p++) {
-        uint32_t col = l1_col(rs.mode, lut, bytes[p]);
-        uint32_t ent = state < hot ? *reinterpret_cast<const uint16_t*>(tbl + (state << row_shift) + 2u * col)
-                          : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(gtbl + (state << row_shift) + 2u * col));
-        if (ent & 0x8000u) l1_push_one(w, msg, p - b, (state << 8) | col);
-        state = ent & 0x7fffu;
+    uint32_t msg[NS], b[NS], e[NS], p[NS], state[NS], nch[NS];
+    uint32_t maxch = 0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      msg[s] = tile * per_tile + s * 32 + lane;
+      const bool valid = msg[s] < n;
+      b[s] = valid ? off[msg[s]] : 0u; e[s] = valid ? off[msg[s] + 1] : 0u;
+      if (valid && rs.n_always) l1_push_one(w, msg[s], 0, kL1Always);
+      state[s] = 0; p[s] = b[s];
+      // unaligned head: byte-wise on the full table
+      uint32_t head_end = (b[s] + 15u) & ~15u; if (head_end > e[s]) head_end = e[s];
+      for (; p[s] < head_end; p[s]++) {
+        uint32_t col = l1_col(rs.mode, lut, bytes[p[s]]);
+        uint32_t ent = l1_full(rs, state[s], col);
+        if (ent & kAccept) l1_push_one(w, msg[s], p[s] - b[s], (state[s] << 8) | col);
+        state[s] = ent & kStateMask;
       }
-    };
-    uint32_t head_end = (b + 15u) & ~15u; if (head_end > e) head_end = e;
-    checked(head_end);
-    // warp-uniform main loop over 16-byte chunks
-    uint32_t nch = (e - p) >> 4, maxch = nch;
+      nch[s] = (e[s] - p[s]) >> 4;
+      maxch = max(maxch, nch[s]);
+    }
 #pragma unroll
     for (int d = 16; d; d >>= 1) maxch = max(maxch, __shfl_xor_sync(FULL, maxch, d));
+
+    // warp-uniform main loop over 16-byte chunks of NS message streams; the chunks are software-
+    // pipelined kPrefetch deep in registers so the HBM latency of chunk c+kPrefetch hides behind
+    // the table walk of chunk c
+    constexpr int kPrefetch = 3;
+    uint4 buf[NS][kPrefetch];
+#pragma unroll
+    for (int s = 0; s < NS; s++)
+#pragma unroll
+      for (int d = 0; d < kPrefetch; d++) { buf[s][d] = make_uint4(0, 0, 0, 0); if ((uint32_t)d < nch[s]) buf[s][d] = ldg_stream(bytes + p[s] + 16 * d); }
     for (uint32_t c = 0; c < maxch; c++) {
-      const bool act = c < nch;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (act) v = ldg_stream(bytes + p);
-      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+      uint4 v[NS]; bool act[NS];
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        act[s] = c < nch[s]; v[s] = buf[s][0];
+#pragma unroll
+        for (int d = 0; d + 1 < kPrefetch; d++) buf[s][d] = buf[s][d + 1];
+        buf[s][kPrefetch - 1] = make_uint4(0, 0, 0, 0);
+        if (c + kPrefetch < nch[s]) buf[s][kPrefetch - 1] = ldg_stream(bytes + p[s] + 16 * kPrefetch);
+      }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const uint32_t s0 = state;
-        uint32_t acc = 0;
-        if (act) {
-          const uint32_t c2 = cols2_of_word<MODE>(wd[q]);
+        uint32_t s0[NS], acc[NS], wd[NS], fs[NS];
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            uint32_t ent = l1_step<MODE>(tbl, gtbl, lut, row_shift, hot, state, (c2 >> (8 * k)) & 0xffu);
-            acc |= ent; state = ent & 0x7fffu;
+        for (int s = 0; s < NS; s++) {
+          wd[s] = q == 0 ? v[s].x : q == 1 ? v[s].y : q == 2 ? v[s].z : v[s].w;
+          s0[s] = state[s];
+          acc[s] = state[s] >= hot ? kCold : 0u;          // a deep state at word start: this word goes the slow way
+          fs[s] = min(state[s], hot);
+        }
+        uint32_t c2[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) c2[s] = cols2_of_word<MODE>(wd[s]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+          for (int s = 0; s < NS; s++) {
+            uint32_t ent = l1_fast<MODE>(tbl_s, lut_s, row_shift, fs[s], __byte_perm(c2[s], 0, 0x4440 + k));
+            acc[s] |= ent; fs[s] = ent & kStateMask;
           }
         }
-        // rare: some lane took an accepting transition in this word -> compact the events with ballots
-        if (__ballot_sync(FULL, (acc & 0x8000u) != 0)) {
-          uint32_t cnt = 0, ev_pos[4], ev_sc[4];
-          if (acc & 0x8000u) {
-            uint32_t st = s0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              uint32_t col = l1_col(rs.mode, lut, (wd[q] >> (8 * k)) & 0xffu);
-              uint32_t ent = st < hot ? *reinterpret_cast<const uint16_t*>(tbl + (st << row_shift) + 2u * col)
-                                      : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(gtbl + (st << row_shift) + 2u * col));
-              if (ent & 0x8000u) { ev_pos[cnt] = p + 4 * q + k - b; ev_sc[cnt] = (st << 8) | col; cnt++; }
-              st = ent & 0x7fffu;
+        for (int s = 0; s < NS; s++) {
+          const bool flagged = act[s] && (acc[s] & (kAccept | kCold));
+          if (act[s]) state[s] = fs[s];
+          // rare: an accepting transition or an excursion into deep states in this word
+          if (__ballot_sync(FULL, flagged)) {
+            uint32_t cnt = 0, ev_pos[4], ev_sc[4];
+            if (flagged) {
+              uint32_t st = s0[s];
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                uint32_t col = l1_col(rs.mode, lut, (wd[s] >> (8 * k)) & 0xffu);
+                uint32_t ent = l1_full(rs, st, col);
+                if (ent & kAccept) { ev_pos[cnt] = p[s] + 4 * q + k - b[s]; ev_sc[cnt] = (st << 8) | col; cnt++; }
+                st = ent & kStateMask;
+              }
+              state[s] = st;                                 // the true state (may be a deep one)
             }
-          }
-          uint32_t idx = 0, total = 0;
+            uint32_t idx = 0, total = 0;
 #pragma unroll
-          for (uint32_t j = 1; j <= 4; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(&w.counters[4], total);
-          base = __shfl_sync(FULL, base, 0);
-          if (base + total > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
-          else {
+            for (uint32_t j = 1; j <= 4; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
+            if (total) {
+              uint32_t base = 0;
+              if (lane == 0) base = atomicAdd(&w.counters[4], total);
+              base = __shfl_sync(FULL, base, 0);
+              if (base + total > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
+              else {
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t k = base + idx + j; w.l1_msg[k] = msg; w.l1_pos[k] = ev_pos[j]; w.l1_sc[k] = ev_sc[j]; }
+                for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t k2 = base + idx + j; w.l1_msg[k2] = msg[s]; w.l1_pos[k2] = ev_pos[j]; w.l1_sc[k2] = ev_sc[j]; }
+              }
+            }
           }
         }
       }
-      if (act) p += 16;
+#pragma unroll
+      for (int s = 0; s < NS; s++) if (act[s]) p[s] += 16;
     }
-    checked(e);
-    if (valid) words[msg] = 0ull;
+    // tails
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      for (; p[s] < e[s]; p[s]++) {
+        uint32_t col = l1_col(rs.mode, lut, bytes[p[s]]);
+        uint32_t ent = l1_full(rs, state[s], col);
+        if (ent & kAccept) l1_push_one(w, msg[s], p[s] - b[s], (state[s] << 8) | col);
+        state[s] = ent & kStateMask;
+      }
+      if (msg[s] < n) words[msg[s]] = 0ull;
+    }
   }
 }
 
@@ -344,6 +396,16 @@ __global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict_
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+void prepare_scan_kernels() {
+  int dev = 0, optin = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int kMaxSmem = (optin > 0 ? optin : 227 * 1024) - 1024;     // leave room for the kernels' static shared memory
+#define CG_PREP(M) cudaFuncSetAttribute(scan_kernel<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); cudaFuncSetAttribute(scan_kernel<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
+  CG_PREP(0); CG_PREP(1); CG_PREP(2); CG_PREP(3);
+#undef CG_PREP
+  cudaFuncSetAttribute(verify_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
+  cudaFuncSetAttribute(verify_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
+}
+
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, bool want_spans, int sm_count, cudaStream_t stream) {
   (void)want_spans;
@@ -351,8 +413,11 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   size_t smem = rs.image_bytes;
   uint32_t ntiles = (n + 31) / 32, wpb = kScanThreads / 32;
   uint32_t grid = (ntiles + wpb - 1) / wpb; if (grid > (uint32_t)sm_count) grid = sm_count;
-#define CG_LAUNCH_SCAN(M) do { cudaFuncSetAttribute(scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    scan_kernel<M><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); } while (0)
+  const int ns = rs.scan_streams == 1 ? 1 : 2;
+#define CG_LAUNCH_SCAN(M) do { if (ns == 1) { \
+      scan_kernel<M, 1><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); } \
+    else { \
+      scan_kernel<M, 2><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); } } while (0)
   switch (rs.mode) { case 0: CG_LAUNCH_SCAN(0); break; case 2: CG_LAUNCH_SCAN(2); break; case 3: CG_LAUNCH_SCAN(3); break; default: CG_LAUNCH_SCAN(1); break; }
 #undef CG_LAUNCH_SCAN
   return 1;
@@ -368,10 +433,8 @@ int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byte
                   bool want_spans, int sm_count, cudaStream_t stream) {
   int k = 1;
   if (want_spans) {
-    cudaFuncSetAttribute(verify_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
     verify_small_kernel<true><<<sm_count, kVerifyThreads, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   } else {
-    cudaFuncSetAttribute(verify_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
     verify_small_kernel<false><<<sm_count, kVerifyThreads, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   }
   if (rs.max_prog_len > (uint32_t)kSmallProg) {
