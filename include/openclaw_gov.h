@@ -50,8 +50,9 @@ extern "C" {
 /* ---- ruleset options */
 #define CG_OPT_PREFILTER_DIRECT7 0u /* level-1 table with 128 columns indexed by byte & 0x7f */
 #define CG_OPT_PREFILTER_LUT     1u /* byte->class LUT (<= 64 classes) + compact table */
-#define CG_OPT_PREFILTER_FOLD6   2u /* 64 columns from SWAR-folded 6-bit byte classes (default) */
-#define CG_OPT_PREFILTER_FOLD5   3u /* 32 columns (byte & 0x1f): twice the states, deeper windows */
+#define CG_OPT_PREFILTER_FOLD6   2u /* DFA with 64 columns from SWAR-folded 6-bit byte classes (default) */
+#define CG_OPT_PREFILTER_FOLD5   3u /* DFA with 32 columns (byte & 0x1f) */
+#define CG_OPT_PREFILTER_FP      4u /* lane-private fingerprint table over 4-byte windows (small rule sets; falls back to FOLD6) */
 
 typedef struct cg_ruleset cg_ruleset;
 

@@ -24,7 +24,7 @@ class Harness:
         o = np.zeros(8, dtype=np.uint32)
         self.L.harness_info(self.h, o.ctypes.data)
         return dict(nstates=int(o[0]), n_factors=int(o[1]), ncols=int(o[2]), window_min=int(o[3]) & 0xff,
-                    window_max=int(o[3]) >> 8, n_always=int(o[4]), image_bytes=int(o[5]), prog_words=int(o[6]))
+                    window_max=int(o[3]) >> 8, n_always=int(o[4]), image_bytes=int(o[5]), prog_words=int(o[6]), mode=int(o[7]))
 
     def find_all(self, rule, msg: bytes):
         cap = 64

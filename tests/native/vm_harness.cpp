@@ -55,6 +55,9 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   d.acc_index = H.pf.acc_index.data(); d.acc_offsets = H.pf.acc_offsets.data(); d.acc_factors = H.pf.acc_factors.data();
   d.factors = H.factor_words.data(); d.bytesets = H.pf.bytesets.data();
   d.always_rules = H.pf.always_rules.data(); d.n_always = n_always;
+  H.pf.fp_table.resize(H.pf.fp_table.size() + 4, 0); H.pf.fp_acc.resize(H.pf.fp_acc.size() + 4, 0xffffffffu);
+  d.n_trig = (uint32_t)H.pf.trig_bytes.size(); for (uint32_t q = 0; q < 2; q++) { d.trig_byte[q] = q < d.n_trig ? H.pf.trig_bytes[q] : 0; d.trig_acc[q] = q < d.n_trig ? H.pf.trig_acc[q] : 0xffffffffu; }
+  d.fp_buckets = H.pf.fp_buckets; d.fp_mult = H.pf.fp_mult; d.fp_table = H.pf.fp_table.data(); d.fp_acc = H.pf.fp_acc.data();
   d.prog = H.prog.data(); d.rule_prog_off = H.prog_off.data(); d.sets = H.sets.data(); d.set_ranges = H.ranges.data();
   H.alpha.resize(H.alpha.size() + 8, 0);
   d.rule_first = H.first.data(); d.rule_alpha = H.alpha.data(); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
@@ -65,7 +68,7 @@ void harness_destroy(void* p) { delete (Harness*)p; }
 // info: [0]=nstates [1]=n_factors [2]=ncols [3]=window_min|window_max<<8 [4]=n_always [5]=image_bytes [6]=program words
 void harness_info(void* p, uint32_t* out) {
   Harness* h = (Harness*)p;
-  out[0] = h->d.nstates; out[1] = (uint32_t)h->H.pf.factors.size(); out[2] = (uint32_t)h->H.pf.ncols;
+  out[0] = h->H.pf.mode == 4 ? h->H.pf.fp_keys : h->d.nstates; out[7] = (uint32_t)h->H.pf.mode; out[1] = (uint32_t)h->H.pf.factors.size(); out[2] = (uint32_t)h->H.pf.ncols;
   out[3] = (uint32_t)h->H.pf.window_min | ((uint32_t)h->H.pf.window_max << 8);
   out[4] = h->d.n_always; out[5] = h->d.image_bytes; out[6] = (uint32_t)h->H.prog.size();
 }
@@ -108,6 +111,17 @@ void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand,
   for (uint32_t k = 0; k < d.n_always; k++) sink.candidate(d.always_rules[k]);
   const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0, hits = 0;
+  if (d.mode == 4) {        // the fingerprint scan restated: rolling 4-symbol window, hash, 2-way bucket
+    uint32_t win = 0;
+    for (uint32_t i = 0; i < len; i++) {
+      win = (win >> 8) | (fp_fold(m[i]) << 24);
+      uint32_t hsh = win * d.fp_mult, b = (uint32_t)(((uint64_t)hsh * d.fp_buckets) >> 32), val = d.fp_table[b], fp = (hsh >> 8) & 0xffffu;
+      if ((val & 0xffffu) == fp || (val >> 16) == fp) { hits++; if (getenv("CG_FP_DEBUG")) fprintf(stderr, "hit win %08x h %08x b %u val %08x fp %04x acc %d %d\n", win, hsh, b, val, fp, (int)d.fp_acc[2*b], (int)d.fp_acc[2*b+1]); fp_accept(d, hsh, m, len, i, want_spans != 0, sink); }
+      for (uint32_t q = 0; q < d.n_trig; q++) if (m[i] == d.trig_byte[q]) { hits++; accept_id(d, d.trig_acc[q], m, len, i, want_spans != 0, sink); }
+    }
+    if (l1_hits) *l1_hits = hits;
+    return;
+  }
   for (uint32_t i = 0; i < len; i++) {
     uint32_t col = l1_col(d.mode, lut, m[i]);
     uint32_t ent = table[(state << d.ncols_log2) + col];
@@ -128,6 +142,15 @@ void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits
   for (uint32_t k = 0; k < d.n_always; k++) sink.candidate(d.always_rules[k]);
   const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0;
+  if (d.mode == 4) {
+    uint32_t win = 0;
+    for (uint32_t i = 0; i < len; i++) {
+      win = (win >> 8) | (fp_fold(m[i]) << 24);
+      uint32_t hsh = win * d.fp_mult, b = (uint32_t)(((uint64_t)hsh * d.fp_buckets) >> 32), val = d.fp_table[b], fp = (hsh >> 8) & 0xffffu;
+      if ((val & 0xffffu) == fp || (val >> 16) == fp) fp_accept(d, hsh, m, len, i, false, sink);
+      for (uint32_t q = 0; q < d.n_trig; q++) if (m[i] == d.trig_byte[q]) accept_id(d, d.trig_acc[q], m, len, i, false, sink);
+    }
+  } else
   for (uint32_t i = 0; i < len; i++) {
     uint32_t col = l1_col(d.mode, lut, m[i]);
     uint32_t ent = table[(state << d.ncols_log2) + col];
@@ -149,6 +172,15 @@ void harness_l1_factor_counts(void* p, const uint8_t* m, uint32_t len, uint32_t*
   Harness* h = (Harness*)p; const DevRuleset& d = h->d;
   const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0;
+  if (d.mode == 4) {
+    uint32_t win = 0;
+    for (uint32_t i = 0; i < len; i++) {
+      win = (win >> 8) | (fp_fold(m[i]) << 24);
+      uint32_t hsh = win * d.fp_mult, b = (uint32_t)(((uint64_t)hsh * d.fp_buckets) >> 32), val = d.fp_table[b], fp = (hsh >> 8) & 0xffffu;
+      for (uint32_t way = 0; way < 2; way++) if (((val >> (16 * way)) & 0xffffu) == fp) { uint32_t aid = d.fp_acc[2 * b + way]; if (aid != 0xffffffffu) for (uint32_t k = d.acc_offsets[aid]; k < d.acc_offsets[aid + 1]; k++) counts[d.acc_factors[k]]++; }
+    }
+    return;
+  }
   for (uint32_t i = 0; i < len; i++) {
     uint32_t col = l1_col(d.mode, lut, m[i]);
     uint32_t ent = table[(state << d.ncols_log2) + col];

@@ -59,7 +59,7 @@ def test_builtins_on_reference_vectors(oracle, harness_lib):
     h.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("utf8_frac", [0.0, 0.15])
 def test_synthetic_rules_spans_and_prefilter_soundness(oracle, harness_lib, mode, utf8_frac):
     rl = W.make_rules(160)

@@ -72,7 +72,7 @@ def test_reference_vectors_through_the_kernels(N, oracle):
         rs.close()
 
 
-@pytest.mark.parametrize("n_rules,mode", [(17, 0), (64, 1), (500, 0), (500, 1), (500, 2), (500, 3), (2000, 2), (2000, 3)])
+@pytest.mark.parametrize("n_rules,mode", [(17, 0), (64, 1), (500, 0), (500, 1), (500, 2), (500, 3), (2000, 2), (2000, 3), (17, 4), (120, 4), (500, 4)])
 def test_policy_scan_equals_oracle(N, oracle, n_rules, mode):
     rl = W.make_rules(n_rules)
     rules = W.rules_as_tuples(rl)

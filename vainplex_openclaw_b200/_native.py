@@ -18,7 +18,7 @@ ERR_NAMES = {-1: "INVALID_ARG", -2: "NOT_INITIALIZED", -3: "CUDA", -4: "SYNTAX",
 CG_ERR_SYNTAX, CG_ERR_UNSUPPORTED, CG_ERR_TOO_LARGE, CG_ERR_CAPACITY = -4, -5, -6, -7
 FLAG_ICASE = 1
 CAT = {"credential": 0, "financial": 1, "pii": 2, "custom": 3}
-OPT_DIRECT7, OPT_LUT, OPT_FOLD6, OPT_FOLD5 = 0, 1, 2, 3
+OPT_DIRECT7, OPT_LUT, OPT_FOLD6, OPT_FOLD5, OPT_FP = 0, 1, 2, 3, 4
 
 
 class GovError(RuntimeError):

@@ -260,7 +260,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   rs->category.resize(n_rules);
   for (uint32_t i = 0; i < n_rules; i++) { src[i] = RuleSrc{rules[i].source, rules[i].source_len, rules[i].flags}; rs->category[i] = rules[i].category; }
   ImageOptions io;
-  io.mode = (int)(options & 3u);
+  io.mode = (int)(options & 7u); if (io.mode > 4) io.mode = 4;
   if (const char* e = getenv("CG_PREFILTER_MODE")) io.mode = atoi(e);
   if (const char* e = getenv("CG_PREFILTER_KB")) io.budget_bytes = (size_t)atoi(e) * 1024;
   if (const char* e = getenv("CG_PREFILTER_CLASSES")) io.max_classes = atoi(e);
@@ -295,6 +295,10 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), H.factor_words, &d.factors, 16))) return rc;
   if ((rc = upload(rs.get(), P.bytesets, &d.bytesets, 8))) return rc;
   if ((rc = upload(rs.get(), P.always_rules, &d.always_rules))) return rc;
+  d.fp_buckets = P.fp_buckets; d.fp_mult = P.fp_mult;
+  d.n_trig = (uint32_t)P.trig_bytes.size(); for (uint32_t t = 0; t < 2; t++) { d.trig_byte[t] = t < d.n_trig ? P.trig_bytes[t] : 0; d.trig_acc[t] = t < d.n_trig ? P.trig_acc[t] : 0xffffffffu; }
+  if ((rc = upload(rs.get(), P.fp_table, &d.fp_table))) return rc;
+  if ((rc = upload(rs.get(), P.fp_acc, &d.fp_acc))) return rc;
   d.n_always = (uint32_t)P.always_rules.size();
   if ((rc = upload(rs.get(), prog, &d.prog))) return rc;
   if ((rc = upload(rs.get(), prog_off, &d.rule_prog_off))) return rc;
@@ -317,7 +321,7 @@ int cg_ruleset_get_info(const cg_ruleset* rs, cg_ruleset_info* o) {
   o->n_rules = (uint32_t)rs->host.rules.size();
   for (auto& r : rs->host.rules) if (r.status == RULE_OK) o->n_ok++;
   o->n_always_candidate = (uint32_t)rs->host.pf.always_rules.size(); o->n_sets = rs->n_sets;
-  o->prefilter_mode = (uint32_t)rs->host.pf.mode; o->prefilter_states = (uint32_t)rs->host.pf.nstates; o->prefilter_hot_states = rs->host.hot_states; o->prefilter_cols = (uint32_t)rs->host.pf.ncols;
+  o->prefilter_mode = (uint32_t)rs->host.pf.mode; o->prefilter_states = rs->host.pf.mode == 4 ? rs->host.pf.fp_keys : (uint32_t)rs->host.pf.nstates; o->prefilter_hot_states = rs->host.hot_states; o->prefilter_cols = (uint32_t)rs->host.pf.ncols;
   o->prefilter_factor_len = (uint32_t)rs->host.pf.window_min | ((uint32_t)rs->host.pf.window_max << 8); o->n_factors = (uint32_t)rs->host.pf.factors.size(); o->prefilter_bytes = rs->dev.image_bytes; o->program_words = rs->program_words;
   return CG_OK;
 }

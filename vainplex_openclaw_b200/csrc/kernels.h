@@ -9,7 +9,7 @@ namespace cg {
 struct DevRuleset {
   const uint8_t* image;          // [lut 256 B][level-1 table nstates*ncols u16], 16-byte aligned, size % 16 == 0
   uint32_t image_bytes;
-  uint32_t mode;                 // 0 = direct 7-bit columns, 1 = LUT columns, 2 = folded 6-bit, 3 = folded 5-bit columns
+  uint32_t mode;                 // 0 = direct 7-bit columns, 1 = LUT columns, 2 = folded 6-bit, 3 = folded 5-bit columns, 4 = fingerprint table
   uint32_t max_prog_len;         // longest Pike program of the set (picks the VM capacity)
   uint32_t ncols_log2;
   uint32_t nstates;
@@ -21,6 +21,11 @@ struct DevRuleset {
   const uint32_t* acc_factors;
   const uint32_t* factors;       // 12 words per full factor: rule, len|win_off<<8|win_len<<16|exact<<24, 16 x u16 set ids, max prefix units, pad
   const uint32_t* bytesets;      // 8 words per 256-bit byte set
+  // mode 4 (fingerprint level 1): bucket = umulhi(window * fp_mult, fp_buckets); image = [256 B][fp_buckets x 32 replicated words]
+  uint32_t fp_buckets, fp_mult;
+  const uint32_t* fp_table;      // fp_buckets words (two 16-bit fingerprints each)
+  const uint32_t* fp_acc;        // 2 * fp_buckets accept ids
+  uint32_t n_trig, trig_byte[2], trig_acc[2];   // single-byte triggers (events carry pos | 0x80000000, sc = trigger index)
   const uint32_t* always_rules;  // candidates for every message
   uint32_t n_always;
   const uint32_t* prog;          // all Pike programs, concatenated

@@ -9,7 +9,7 @@
 namespace cg {
 
 CG_HD uint32_t l1_col(uint32_t mode, const uint8_t* __restrict__ lut, uint32_t b) {
-  return mode == 0 ? (b & 0x7fu) : mode == 2 ? ((b & 0x1fu) | ((b >> 1) & 0x20u)) : mode == 3 ? (b & 0x1fu) : (uint32_t)lut[b];
+  return mode == 0 ? (b & 0x7fu) : mode == 2 ? ((b & 0x1fu) | ((b >> 1) & 0x20u)) : mode == 3 ? (b & 0x1fu) : (uint32_t)lut[b];   // mode 4: lut = fp_fold
 }
 
 CG_HD bool byte_in_set(const DevRuleset& rs, uint32_t sid, uint32_t b) {
@@ -33,11 +33,10 @@ CG_HD_NOINLINE bool confirm_factor(const DevRuleset& rs, const uint32_t* __restr
   return true;
 }
 
-// An accepting level-1 transition (state, col) was taken on the byte at message offset `pend`.
+// the factors of accept id `aid` are confirmed at message offset `pend` (window's last byte)
 template <class Sink>
-CG_HD_NOINLINE void l1_accept(const DevRuleset& rs, uint32_t state, uint32_t col, const uint8_t* __restrict__ m, uint32_t len,
-                              uint32_t pend, bool want_spans, Sink& sink) {
-  const uint32_t aid = rs.acc_index[((size_t)state << rs.ncols_log2) + col];
+CG_HD_NOINLINE void accept_id(const DevRuleset& rs, uint32_t aid, const uint8_t* __restrict__ m, uint32_t len, uint32_t pend,
+                              bool want_spans, Sink& sink) {
   if (aid == 0xffffffffu) return;
   for (uint32_t k = rs.acc_offsets[aid]; k < rs.acc_offsets[aid + 1]; k++) {
     const uint32_t* fw = rs.factors + (size_t)rs.acc_factors[k] * 12;
@@ -46,6 +45,22 @@ CG_HD_NOINLINE void l1_accept(const DevRuleset& rs, uint32_t state, uint32_t col
       if ((meta >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0], t0, fw[10]);
     }
   }
+}
+
+// DFA modes: an accepting level-1 transition (state, col) was taken on the byte at message offset `pend`.
+template <class Sink>
+CG_HD_NOINLINE void l1_accept(const DevRuleset& rs, uint32_t state, uint32_t col, const uint8_t* __restrict__ m, uint32_t len,
+                              uint32_t pend, bool want_spans, Sink& sink) {
+  accept_id(rs, rs.acc_index[((size_t)state << rs.ncols_log2) + col], m, len, pend, want_spans, sink);
+}
+
+// mode 4: the window hash `h` hit a fingerprint at message offset `pend`
+template <class Sink>
+CG_HD_NOINLINE void fp_accept(const DevRuleset& rs, uint32_t h, const uint8_t* __restrict__ m, uint32_t len, uint32_t pend,
+                              bool want_spans, Sink& sink) {
+  const uint32_t b = (uint32_t)(((uint64_t)h * rs.fp_buckets) >> 32), fp = (h >> 8) & 0xffffu, val = rs.fp_table[b];
+  for (uint32_t way = 0; way < 2; way++)
+    if (((val >> (16 * way)) & 0xffffu) == fp) accept_id(rs, rs.fp_acc[2 * b + way], m, len, pend, want_spans, sink);
 }
 
 }  // namespace cg

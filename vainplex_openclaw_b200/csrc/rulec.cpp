@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -739,7 +741,131 @@ static bool build_dfa(const std::vector<L1Pattern>& pats, int ncols, int max_sta
 }
 }  // namespace
 
-bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* pf, std::string* err) {
+// ---- mode 4: stateless level 1.  For every factor one window of 4 consecutive symbols (mode-4
+// alphabet, see fp_fold) is enumerated; hash(window) selects a 2-way bucket of 16-bit fingerprints.
+// The table is replicated once per shared-memory bank, so lane i only ever reads bank i: every
+// probe is a single conflict-free wavefront.  Returns false when the rule set is not eligible.
+static void collect_full_factors(const std::vector<CompiledRule>& rules, Prefilter& P, std::vector<FactorSeq>& seqs) {
+  std::map<ByteSet, uint16_t> set_ids;
+  auto set_id = [&](const ByteSet& b) {
+    auto it = set_ids.find(b); if (it != set_ids.end()) return it->second;
+    uint16_t id = (uint16_t)set_ids.size(); set_ids.emplace(b, id);
+    for (int k = 0; k < 8; k++) P.bytesets.push_back((uint32_t)(b.w[k >> 1] >> (32 * (k & 1))));
+    return id;
+  };
+  for (size_t r = 0; r < rules.size(); r++) {
+    if (rules[r].status != RULE_OK) continue;
+    if (rules[r].factors.empty()) { P.always_rules.push_back((uint32_t)r); continue; }
+    for (auto& f : rules[r].factors) {
+      FullFactor ff{}; ff.rule = (uint32_t)r; ff.len = (uint8_t)std::min<size_t>(f.size(), kMaxFactorElems);
+      ff.exact = (rules[r].factors_exact && f.size() <= (size_t)kMaxFactorElems) ? 1 : 0;
+      ff.pre = rules[r].factor_pre >= 0xffff ? 0xffff : (uint16_t)rules[r].factor_pre;
+      for (int k = 0; k < ff.len; k++) ff.elem[k] = set_id(f[k]);
+      P.factors.push_back(ff); seqs.push_back(FactorSeq(f.begin(), f.begin() + ff.len));
+    }
+  }
+}
+
+static bool build_fp_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* pf) {
+  Prefilter& P = *pf;
+  P = Prefilter();
+  P.mode = 4; P.ncols = 64; P.nstates = 1;
+  for (int b = 0; b < 256; b++) P.lut[b] = (uint8_t)fp_fold((uint32_t)b);
+  std::vector<FactorSeq> seqs;
+  collect_full_factors(rules, P, seqs);
+  const uint32_t B = (uint32_t)std::max(opt.fp_buckets, 16);
+  std::set<uint32_t> all_syms; for (int b = 0; b < 256; b++) all_syms.insert(fp_fold((uint32_t)b));
+  const size_t kMaxVariants = 256;
+  // windows: key -> factor ids
+  std::map<uint32_t, std::vector<uint32_t>> keys;
+  std::vector<uint32_t> trig_bytes; std::vector<std::vector<uint32_t>> trig_factors;
+  for (size_t f = 0; f < seqs.size(); f++) {
+    const FactorSeq& s = seqs[f]; const int len = (int)s.size();
+    std::vector<std::vector<uint32_t>> syms(len);
+    for (int k = 0; k < len; k++) { std::set<uint32_t> u; for (int b = 0; b < 256; b++) if (s[k].has(b)) u.insert(fp_fold((uint32_t)b)); syms[k].assign(u.begin(), u.end()); }
+    // candidate windows: 4 symbols ending at factor element `wend-1`; positions before the factor are wildcards
+    int best_wend = -1; double best_cnt = 1e30, best_p = 2;
+    for (int wend = std::min(len, 4); wend <= len; wend++) {
+      double cnt = 1, p = 1;
+      for (int j = 0; j < 4; j++) { int k = wend - 4 + j; if (k < 0) { cnt *= (double)all_syms.size(); } else { cnt *= (double)syms[k].size(); double q = 0; for (int b = 0; b < 256; b++) if (s[k].has(b)) q += Compiler::byte_weight(b); p *= std::min(q, 1.0); } }
+      if (cnt < best_cnt || (cnt == best_cnt && p < best_p)) { best_cnt = cnt; best_p = p; best_wend = wend; }
+    }
+    if (best_wend < 0 || best_cnt > (double)kMaxVariants) {
+      // not enumerable as a 4-symbol window (e.g. '@' + classes): fall back to a single-byte trigger,
+      // compared SWAR-style in registers by the scan kernel (at most two distinct trigger bytes per set)
+      int tk = -1; double tp = 2; int tb = -1;
+      for (int k = 0; k < len; k++) {
+        int cnt = 0, last = -1; for (int b = 0; b < 256; b++) if (s[k].has(b)) { cnt++; last = b; }
+        if (cnt == 1 && Compiler::byte_weight(last) < tp) { tp = Compiler::byte_weight(last); tk = k; tb = last; }
+      }
+      size_t ti = 0;
+      if (tk >= 0) { for (; ti < trig_bytes.size(); ti++) if (trig_bytes[ti] == (uint32_t)tb) break; }
+      if (tk < 0 || (ti == trig_bytes.size() && trig_bytes.size() >= 2)) {
+        if (getenv("CG_FP_DEBUG")) fprintf(stderr, "fp: factor %zu of rule %u not enumerable (len %d, best %g variants)\n", f, P.factors[f].rule, len, best_cnt);
+        return false;
+      }
+      if (ti == trig_bytes.size()) { trig_bytes.push_back((uint32_t)tb); trig_factors.emplace_back(); }
+      trig_factors[ti].push_back((uint32_t)f);
+      P.factors[f].win_off = (uint8_t)tk; P.factors[f].win_len = 1;
+      continue;
+    }
+    P.factors[f].win_len = (uint8_t)std::min(best_wend, 4); P.factors[f].win_off = (uint8_t)(best_wend - P.factors[f].win_len);
+    // enumerate: symbol j of the window sits in bits 8j..8j+7 (oldest symbol lowest)
+    std::vector<uint32_t> cur = {0};
+    for (int j = 0; j < 4; j++) {
+      int k = best_wend - 4 + j; std::vector<uint32_t> nx;
+      const std::vector<uint32_t> wild(all_syms.begin(), all_syms.end());
+      const std::vector<uint32_t>& opts = k < 0 ? wild : syms[k];
+      for (uint32_t base : cur) for (uint32_t v : opts) nx.push_back(base | (v << (8 * j)));
+      cur.swap(nx);
+    }
+    for (uint32_t key : cur) keys[key].push_back((uint32_t)f);
+  }
+  P.fp_keys = (uint32_t)keys.size();
+  if (keys.size() > (size_t)B * 2 * 3 / 4) { if (getenv("CG_FP_DEBUG")) fprintf(stderr, "fp: %zu keys exceed the capacity of %u buckets\n", keys.size(), B); return false; }              // keep the load factor below 75 %
+  // find a multiplier under which no bucket overflows and no key has fingerprint 0
+  uint64_t sm = 0x9E3779B97F4A7C15ull;
+  for (int attempt = 0; attempt < 512; attempt++) {
+    sm += 0x9E3779B97F4A7C15ull; uint64_t z = sm; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    const uint32_t mult = (uint32_t)z | 1u;
+    std::vector<uint32_t> table(B, 0xffffffffu); std::vector<std::vector<uint32_t>> slot_f((size_t)B * 2);     // 0xffff = empty way
+    bool ok = true;
+    for (auto& kv : keys) {
+      uint32_t hsh = kv.first * mult, fp = (hsh >> 8) & 0xffffu, b = (uint32_t)(((uint64_t)hsh * B) >> 32);
+      if (fp == 0xffffu) { ok = false; break; }
+      int way = -1;
+      for (int w2 = 0; w2 < 2; w2++) { uint32_t cur_fp = (table[b] >> (16 * w2)) & 0xffffu; if (cur_fp == fp) { way = w2; break; } }
+      if (way < 0) for (int w2 = 0; w2 < 2; w2++) if (((table[b] >> (16 * w2)) & 0xffffu) == 0xffffu) { way = w2; table[b] = (table[b] & ~(0xffffu << (16 * w2))) | (fp << (16 * w2)); break; }
+      if (way < 0) { ok = false; break; }
+      auto& dst = slot_f[(size_t)b * 2 + way]; dst.insert(dst.end(), kv.second.begin(), kv.second.end());
+    }
+    if (!ok) continue;
+    P.fp_buckets = B; P.fp_mult = mult; P.fp_table = table;
+    P.fp_acc.assign((size_t)B * 2, 0xffffffffu); P.acc_offsets.assign(1, 0); P.acc_factors.clear();
+    for (size_t sidx = 0; sidx < slot_f.size(); sidx++) {
+      if (slot_f[sidx].empty()) continue;
+      std::sort(slot_f[sidx].begin(), slot_f[sidx].end()); slot_f[sidx].erase(std::unique(slot_f[sidx].begin(), slot_f[sidx].end()), slot_f[sidx].end());
+      P.fp_acc[sidx] = (uint32_t)(P.acc_offsets.size() - 1);
+      P.acc_factors.insert(P.acc_factors.end(), slot_f[sidx].begin(), slot_f[sidx].end());
+      P.acc_offsets.push_back((uint32_t)P.acc_factors.size());
+    }
+    P.trig_bytes = trig_bytes; P.trig_acc.clear();
+    for (auto& tf : trig_factors) { P.trig_acc.push_back((uint32_t)(P.acc_offsets.size() - 1)); P.acc_factors.insert(P.acc_factors.end(), tf.begin(), tf.end()); P.acc_offsets.push_back((uint32_t)P.acc_factors.size()); }
+    P.window_min = 255; P.window_max = 0;
+    for (auto& ff : P.factors) { P.window_min = std::min<int>(P.window_min, ff.win_len); P.window_max = std::max<int>(P.window_max, ff.win_len); }
+    if (P.factors.empty()) P.window_min = P.window_max = 0;
+    P.table.assign(64, 0); P.acc_index.assign(64, 0xffffffffu);        // unused DFA part (kept non-empty)
+    return true;
+  }
+  return false;
+}
+
+bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt_in, Prefilter* pf, std::string* err) {
+  PrefilterOptions opt = opt_in;
+  if (opt.mode == 4) {
+    if (build_fp_prefilter(rules, opt, pf)) return true;
+    opt.mode = 2;                       // windows not enumerable / table full: the general DFA takes over
+  }
   Prefilter& P = *pf;
   P = Prefilter();
   P.mode = opt.mode;

@@ -84,7 +84,9 @@ constexpr int kMaxWindow = 8;
 constexpr int kMaxFactorElems = 16;
 
 struct PrefilterOptions {
-  int mode = 2;              // 0 = direct 7-bit (128 cols), 1 = byte->class LUT (<=64), 2 = folded 6-bit (64, SWAR), 3 = folded 5-bit (32, SWAR)
+  int mode = 2;              // 0 = direct 7-bit (128 cols), 1 = byte->class LUT (<=64), 2 = folded 6-bit (64, SWAR), 3 = folded 5-bit (32, SWAR),
+                             // 4 = lane-private fingerprint table over 4-byte windows (falls back to 2 when a rule set does not fit)
+  int fp_buckets = 1024;     // mode 4: 2-way buckets per lane-bank replica
   int max_states = 24576;    // total level-1 states (rows beyond the shared-memory budget stay in L2-resident HBM)
   int max_classes = 64;      // LUT mode only
   int max_window = kMaxWindow;
@@ -108,7 +110,16 @@ struct Prefilter {
   std::vector<FullFactor> factors;
   std::vector<uint32_t> bytesets;     // 8 words per 256-bit set
   std::vector<uint32_t> always_rules; // rules without usable factors: candidates for every message
+  // mode 4: fingerprint table.  bucket = umulhi(h, fp_buckets), fingerprint = (h >> 8) & 0xffff, h = window * fp_mult
+  uint32_t fp_buckets = 0, fp_mult = 0, fp_keys = 0;
+  std::vector<uint32_t> fp_table;     // fp_buckets words: two 16-bit fingerprints (0xffff = empty)
+  std::vector<uint32_t> fp_acc;       // 2 * fp_buckets accept ids (0xffffffff = empty)
+  std::vector<uint32_t> trig_bytes;   // mode 4: up to two single-byte triggers for factors without an enumerable window
+  std::vector<uint32_t> trig_acc;     //         their accept ids
 };
+
+// the byte -> 6-bit symbol map of mode 4: fold6 with the digit columns collapsed to two symbols
+inline uint32_t fp_fold(uint32_t b) { uint32_t c = (b & 0x1fu) | ((b >> 1) & 0x20u); if ((c & 0x30u) == 0x10u) c &= 0x38u; return c; }
 bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* out, std::string* err);
 
 }  // namespace cg

@@ -38,10 +38,11 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
 
   PrefilterOptions po;
   po.mode = opt.mode; po.max_classes = opt.max_classes; po.max_window = opt.max_window;
-  int cols = po.mode == 0 ? 128 : po.mode == 2 ? 64 : po.mode == 3 ? 32 : (po.max_classes <= 32 ? 32 : 64);
+  int cols = po.mode == 0 ? 128 : po.mode == 2 ? 64 : po.mode == 3 ? 32 : po.mode == 4 ? 64 : (po.max_classes <= 32 ? 32 : 64);
   size_t budget = std::max<size_t>(opt.budget_bytes, 256 + (size_t)cols * 2 * 2);
   size_t hot_rows = std::min<size_t>((budget - 256) / ((size_t)cols * 2), 32767);
   po.max_states = std::max<int>((int)std::min<size_t>((size_t)std::max(opt.max_states, 1), 16383), 1);
+  po.fp_buckets = (int)std::max<size_t>((budget - 256) / 128, 16);
   if (!build_prefilter(H.rules, po, &H.pf, err)) return false;
   for (auto& f : H.pf.factors) {
     H.factor_words.push_back(f.rule);
@@ -49,15 +50,27 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     for (int k = 0; k < kMaxFactorElems; k += 2) H.factor_words.push_back((uint32_t)f.elem[k] | ((uint32_t)f.elem[k + 1] << 16));
     H.factor_words.push_back(f.pre); H.factor_words.push_back(0);
   }
+  if (H.pf.mode == 4) {
+    // fingerprint table replicated once per bank: word (bucket * 32 + lane) holds bucket's two fingerprints
+    H.hot_states = 0;
+    H.image.assign(256 + (size_t)H.pf.fp_buckets * 128, 0);
+    memcpy(H.image.data(), H.pf.lut, 256);
+    uint32_t* t = reinterpret_cast<uint32_t*>(H.image.data() + 256);
+    for (uint32_t b = 0; b < H.pf.fp_buckets; b++) for (int l = 0; l < 32; l++) t[(size_t)b * 32 + l] = H.pf.fp_table[b];
+    while (H.image.size() % 16) H.image.push_back(0);
+    return true;
+  }
   // shared-memory image: rows [0, hot) with every transition into a deeper state redirected to the
   // trap row `hot` (flag 0x4000), followed by the trap row itself
   H.hot_states = (uint32_t)std::min<size_t>(hot_rows > 1 ? hot_rows - 1 : 1, (size_t)H.pf.nstates);
   const uint32_t hot = H.hot_states; const size_t nc = (size_t)H.pf.ncols;
   std::vector<uint16_t> img((size_t)(hot + 1) * nc);
+  // mode 2: entry (row, col) lives at byte offset (2*col) ^ ((row << 2) & 0x7c) of its row (see l1_fast)
+  auto swz = [&](uint32_t row, size_t col) { return H.pf.mode == 2 ? (size_t)(((2 * col) ^ ((row << 2) & 0x7c)) / 2) : col; };
   for (uint32_t s = 0; s < hot; s++) for (size_t c = 0; c < nc; c++) {
     uint16_t e = H.pf.table[(size_t)s * nc + c];
     if ((uint32_t)(e & 0x3fff) >= hot) e = (uint16_t)((e & 0x8000) | 0x4000 | hot);
-    img[(size_t)s * nc + c] = e;
+    img[(size_t)s * nc + swz(s, c)] = e;
   }
   for (size_t c = 0; c < nc; c++) img[(size_t)hot * nc + c] = (uint16_t)(0x4000 | hot);
   H.image.assign(256 + img.size() * 2, 0);

@@ -19,7 +19,7 @@ struct HostImage {
 };
 
 struct ImageOptions {
-  int mode = 2;                 // level-1 column mode (0 direct7, 1 LUT, 2 folded 6-bit)
+  int mode = 2;                 // level-1 mode (0 direct7, 1 LUT, 2 folded 6-bit, 3 folded 5-bit DFA; 4 fingerprint table, falls back to 2)
   size_t budget_bytes = 200 * 1024;   // shared-memory budget of the hot rows
   int max_states = 16384;             // total states (cold rows are read from L2-resident HBM)
   int max_classes = 64;

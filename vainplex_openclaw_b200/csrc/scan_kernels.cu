@@ -17,6 +17,7 @@
 #include "rulec.h"
 #include "pike_vm.h"
 #include "prefilter_dev.h"
+#include <algorithm>
 
 namespace cg {
 
@@ -78,9 +79,13 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) { uint32_t v; asm("ld
 // hot-row transition into a deep state is stored as hot | kCold, so the fast path never leaves
 // shared memory: an excursion into deep states only raises kCold, and the flagged word is then
 // re-walked on the full table in HBM/L2 by the (rare) slow path, which also restores the state.
+// In mode 2 the 32 words of a row are XOR-swizzled by the low five bits of the row index (the image is
+// stored that way): lanes sitting in different states but reading the same frequent column (' ', 'e',
+// ...) then land in different banks instead of all colliding in one.
 template <int MODE>
 __device__ __forceinline__ uint32_t l1_fast(uint32_t tbl_s, uint32_t lut_s, uint32_t row_shift, uint32_t state, uint32_t c2) {
   if (MODE == 1) return lds_u16(tbl_s + (state << row_shift) + 2u * lds_u8(lut_s + c2));
+  if (MODE == 2) return lds_u16(tbl_s + state * 128u + (c2 ^ ((state << 2) & 0x7cu)));
   return lds_u16(tbl_s + state * RowBytes<MODE>::v + c2);
 }
 
@@ -235,6 +240,119 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// level 1, mode 4: stateless fingerprint probe.  Every byte position hashes the last four symbols
+// (fold6 + digit collapse, SWAR) and reads ONE word from the lane's own bank of the replicated table
+// -- conflict-free by construction -- and compares two 16-bit fingerprints.  Up to two single-byte
+// triggers (e.g. '@') are matched SWAR-style in registers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fp_fold_word(uint32_t w) {
+  uint32_t f = (w & 0x1f1f1f1fu) | ((w >> 1) & 0x20202020u);
+  uint32_t t = (f >> 4) & ~(f >> 5) & 0x01010101u;        // digit columns 0x10..0x19 -> 0x10 / 0x18
+  return f & ~(t * 7u);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t fp_probe(uint32_t tabs, uint32_t buckets, uint32_t mult, uint32_t win) {
+  uint32_t h = win * mult;
+  uint32_t x = lds_u32(tabs + (__umulhi(h, buckets) << 7)) ^ __byte_perm(h, 0, 0x2121);        // fingerprint = bits 8..23 of h, in both halves
+  return (x - 0x00010001u) & ~x & 0x80008000u;              // non-zero <=> one half equals the fingerprint
+}
+__device__ __forceinline__ uint32_t has_byte(uint32_t w, uint32_t splat) { uint32_t x = w ^ splat; return (x - 0x01010101u) & ~x & 0x80808080u; }
+
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_fp_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
+               uint64_t* __restrict__ words) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, rs.image_bytes);
+    for (uint32_t o = 0; o < rs.image_bytes; o += 32768u) {
+      uint32_t len = rs.image_bytes - o < 32768u ? rs.image_bytes - o : 32768u;
+      tma_bulk_g2s(smem + o, rs.image + o, len, &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kScanThreads / 32;
+  const uint32_t tabs = smem_u32(smem) + 256u + lane * 4u;      // this lane's bank
+  const uint32_t B = rs.fp_buckets, mult = rs.fp_mult, ntrig = rs.n_trig;
+  const uint32_t sp0 = rs.trig_byte[0] * 0x01010101u, sp1 = rs.trig_byte[1] * 0x01010101u;
+  const uint32_t FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+  const uint32_t ntiles = (n + 31) / 32;
+  for (uint32_t tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
+    const uint32_t msg = tile * 32 + lane;
+    const bool valid = msg < n;
+    const uint32_t b = valid ? off[msg] : 0u, e = valid ? off[msg + 1] : 0u;
+    if (valid && rs.n_always) l1_push_one(w, msg, 0, kL1Always);
+    uint32_t p = b, win = 0;                                 // win: last four symbols, oldest in the low byte
+    auto bytewise = [&](uint32_t upto) {
+      for (; p < upto; p++) {
+        const uint32_t byte = bytes[p];
+        win = (win >> 8) | (fp_fold_word(byte) << 24);
+        if (fp_probe(tabs, B, mult, win)) l1_push_one(w, msg, p - b, win * mult);
+        for (uint32_t t = 0; t < ntrig; t++) if (byte == rs.trig_byte[t]) l1_push_one(w, msg, (p - b) | 0x80000000u, t);
+      }
+    };
+    uint32_t head_end = (b + 15u) & ~15u; if (head_end > e) head_end = e;
+    bytewise(head_end);
+    uint32_t nch = (e - p) >> 4, maxch = nch;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxch = max(maxch, __shfl_xor_sync(FULL, maxch, d));
+    constexpr int kPrefetch = 3;
+    uint4 buf[kPrefetch];
+#pragma unroll
+    for (int d = 0; d < kPrefetch; d++) { buf[d] = make_uint4(0, 0, 0, 0); if ((uint32_t)d < nch) buf[d] = ldg_stream(bytes + p + 16 * d); }
+    for (uint32_t c = 0; c < maxch; c++) {
+      const bool act = c < nch;
+      const uint4 v = buf[0];
+#pragma unroll
+      for (int d = 0; d + 1 < kPrefetch; d++) buf[d] = buf[d + 1];
+      buf[kPrefetch - 1] = make_uint4(0, 0, 0, 0);
+      if (c + kPrefetch < nch) buf[kPrefetch - 1] = ldg_stream(bytes + p + 16 * kPrefetch);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t wd = q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w;
+        const uint32_t P = win, F = fp_fold_word(wd);
+        uint32_t acc = fp_probe(tabs, B, mult, __funnelshift_r(P, F, 8)) | fp_probe(tabs, B, mult, __funnelshift_r(P, F, 16)) |
+                       fp_probe(tabs, B, mult, __funnelshift_r(P, F, 24)) | fp_probe(tabs, B, mult, F);
+        if (ntrig) { acc |= has_byte(wd, sp0); if (ntrig > 1) acc |= has_byte(wd, sp1); }
+        const bool flagged = act && acc != 0;
+        if (act) win = F;
+        if (__ballot_sync(FULL, flagged)) {
+          uint32_t cnt = 0, ev_pos[6], ev_sc[6];
+          if (flagged) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint32_t wk = k == 3 ? F : __funnelshift_r(P, F, 8 * (k + 1));
+              const uint32_t pos = p + 4 * q + k - b;
+              if (fp_probe(tabs, B, mult, wk) && cnt < 6) { ev_pos[cnt] = pos; ev_sc[cnt] = wk * mult; cnt++; }
+              const uint32_t byte = (wd >> (8 * k)) & 0xffu;
+              for (uint32_t t = 0; t < ntrig; t++) if (byte == rs.trig_byte[t] && cnt < 6) { ev_pos[cnt] = pos | 0x80000000u; ev_sc[cnt] = t; cnt++; }
+            }
+          }
+          uint32_t idx = 0, total = 0;
+#pragma unroll
+          for (uint32_t j = 1; j <= 6; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
+          if (total) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&w.counters[4], total);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + total > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
+            else {
+#pragma unroll
+              for (uint32_t j = 0; j < 6; j++) if (j < cnt) { uint32_t k2 = base + idx + j; w.l1_msg[k2] = msg; w.l1_pos[k2] = ev_pos[j]; w.l1_sc[k2] = ev_sc[j]; }
+            }
+          }
+        }
+      }
+      if (act) p += 16;
+    }
+    bytewise(e);
+    if (valid) words[msg] = 0ull;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // level 2: confirm the full factor for every level-1 event; queue survivors for the VM
 // ------------------------------------------------------------------------------------------
 struct SlotSink {
@@ -291,8 +409,11 @@ confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, con
     const uint32_t msg = w.l1_msg[i], pos = w.l1_pos[i], sc = w.l1_sc[i];
     SlotSink sink(rs, w, msg, want_spans != 0);
     if (sc == kL1Always) { for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate_always(rs.always_rules[k]); continue; }
-    const uint32_t b = off[msg];
-    l1_accept(rs, sc >> 8, sc & 0xffu, bytes + b, off[msg + 1] - b, pos, want_spans != 0, sink);
+    const uint32_t b = off[msg], len = off[msg + 1] - b;
+    if (rs.mode == 4) {
+      if (pos & 0x80000000u) accept_id(rs, rs.trig_acc[sc & 1u], bytes + b, len, pos & 0x7fffffffu, want_spans != 0, sink);
+      else fp_accept(rs, sc, bytes + b, len, pos, want_spans != 0, sink);
+    } else l1_accept(rs, sc >> 8, sc & 0xffu, bytes + b, len, pos, want_spans != 0, sink);
   }
 }
 
@@ -402,6 +523,7 @@ void prepare_scan_kernels() {
 #define CG_PREP(M) cudaFuncSetAttribute(scan_kernel<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); cudaFuncSetAttribute(scan_kernel<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
   CG_PREP(0); CG_PREP(1); CG_PREP(2); CG_PREP(3);
 #undef CG_PREP
+  cudaFuncSetAttribute(scan_fp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(verify_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
   cudaFuncSetAttribute(verify_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
 }
@@ -413,6 +535,7 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   size_t smem = rs.image_bytes;
   uint32_t ntiles = (n + 31) / 32, wpb = kScanThreads / 32;
   uint32_t grid = (ntiles + wpb - 1) / wpb; if (grid > (uint32_t)sm_count) grid = sm_count;
+  if (rs.mode == 4) { scan_fp_kernel<<<std::min<uint32_t>((n + 32 * wpb - 1) / (32 * wpb), (uint32_t)sm_count), kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); return 1; }
   const int ns = rs.scan_streams == 1 ? 1 : 2;
 #define CG_LAUNCH_SCAN(M) do { if (ns == 1) { \
       scan_kernel<M, 1><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); } \
