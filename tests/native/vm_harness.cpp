@@ -101,7 +101,7 @@ int harness_test(void* p, uint32_t rule, const uint8_t* m, uint32_t len) {
 struct BitSink {
   uint32_t* cand; uint32_t* direct_;
   std::vector<uint32_t>* occ;   // (rule, t0, pre) triples of confirmed occurrences
-  void candidate(uint32_t r, uint32_t t0 = 0xffffffffu, uint32_t pre = 0xffff) { cand[r >> 5] |= 1u << (r & 31); if (occ) { occ->push_back(r); occ->push_back(t0); occ->push_back(pre); } }
+  void candidate(uint32_t r, uint32_t t0 = 0xffffffffu, uint32_t pre = 0xffffffffu) { cand[r >> 5] |= 1u << (r & 31); if (occ) { occ->push_back(r); occ->push_back(t0); occ->push_back(pre); } }
   void direct(uint32_t r) { direct_[r >> 5] |= 1u << (r & 31); }
 };
 void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand, uint32_t* direct, int want_spans, uint32_t* l1_hits) {

@@ -74,6 +74,7 @@ struct LocalStore {
 template <class Store>
 struct VMS {
   const DevRuleset& rs; const uint32_t* prog; uint32_t plen;
+  const uint32_t* prog_override = nullptr;    // the caller's staged copy of the current rule's program (shared memory), if any
   Store S; uint16_t gen; uint32_t cnt[2];
   uint32_t err;
   // best match of the current search
@@ -209,7 +210,7 @@ CG_HD_NOINLINE Cursor cursor_at(const uint8_t* __restrict__ m, uint32_t len, uin
 // RegExp.test (context.ts:9-25, !SPANS).  sink.span(start_byte, end_byte, start16, end16).
 template <bool SPANS, class VMX, class Sink>
 CG_HD_NOINLINE bool run_rule(VMX& vm, const DevRuleset& rs, uint32_t rule, const uint8_t* __restrict__ m, uint32_t len, Sink& sink) {
-  vm.prog = rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
+  vm.prog = vm.prog_override ? vm.prog_override : rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
   if (vm.plen == 0) return false;                     // rule failed to compile: never matches
   if (vm.plen > VMX::capacity()) { vm.err |= ERR_VM_LIST; return false; }
   for (uint32_t k = 0; k < vm.plen; k++) vm.S.mark(k) = 0;
@@ -251,13 +252,15 @@ CG_HD_NOINLINE int unit_before(const uint8_t* __restrict__ m, uint32_t len, uint
 template <class VMX>
 CG_HD_NOINLINE bool test_at_factor(VMX& vm, const DevRuleset& rs, uint32_t rule, const uint8_t* __restrict__ m, uint32_t len,
                                    uint32_t t0, uint32_t pre_units) {
-  vm.prog = rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
+  vm.prog = vm.prog_override ? vm.prog_override : rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
   if (vm.plen == 0) return false;
   if (vm.plen > VMX::capacity()) { vm.err |= ERR_VM_LIST; return false; }
   for (uint32_t k = 0; k < vm.plen; k++) vm.S.mark(k) = 0;
   vm.gen = 0;
   const uint32_t* first = rs.rule_first + (size_t)rule * 8;
-  const uint32_t* alpha = rs.rule_alpha + (size_t)rule * 8;
+  // bytes the part of a match BEFORE this factor can consist of (per factor; falls back to the rule's alphabet)
+  const uint32_t pa = pre_units >> 16; pre_units &= 0xffffu;
+  const uint32_t* alpha = pa != 0xffffu ? rs.bytesets + (size_t)pa * 8 : rs.rule_alpha + (size_t)rule * 8;
   if (t0 > len) t0 = len;
   uint32_t s = t0;
   while (s > 0 && ((alpha[m[s - 1] >> 5] >> (m[s - 1] & 31)) & 1u)) s--;
@@ -268,6 +271,9 @@ CG_HD_NOINLINE bool test_at_factor(VMX& vm, const DevRuleset& rs, uint32_t rule,
     for (int k = 0; k < 3 && sb > 0 && (m[sb] & 0xc0) == 0x80; k++) sb--;     // back to the start of a character
     if (sb > s) s = sb;
   }
+  // a factor occurrence may begin in the middle of a character (byte-level wildcard shapes): start at the
+  // character's first byte -- that only adds earlier, legitimate start positions
+  for (int k = 0; k < 3 && s > 0 && s < len && (m[s] & 0xc0) == 0x80; k++) s--;
   Cursor c = cursor_at(m, len, s);
   return vm.search(m, len, s, 0, unit_before(m, len, s), first, c, t0, true);
 }

@@ -42,7 +42,7 @@ CG_HD_NOINLINE void accept_id(const DevRuleset& rs, uint32_t aid, const uint8_t*
     const uint32_t* fw = rs.factors + (size_t)rs.acc_factors[k] * 12;
     if (confirm_factor(rs, fw, m, len, pend)) {
       const uint32_t meta = fw[1], t0 = pend + 1 - (((meta >> 8) & 0xff) + ((meta >> 16) & 0xff));   // factor start in the message
-      if ((meta >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0], t0, fw[10]);
+      if ((meta >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0], t0, fw[10] | (fw[11] << 16));     // max prefix units | prefix-alphabet set id << 16
     }
   }
 }

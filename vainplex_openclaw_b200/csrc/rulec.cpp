@@ -435,7 +435,21 @@ struct Compiler {
     bool has_factors = false;           // every match contains one of `factors` as a substring
     std::vector<FactorSeq> factors;
     int fpre = 0;                       // max units of the node's match that can precede that factor occurrence (kPreInf = unbounded)
+    ByteSet fpre_alpha;                 // bytes that part of the match before the factor can consist of (over-approximation)
   };
+  // every byte the sub-pattern can consume
+  ByteSet alpha_of(int n) const {
+    const Node& nd = N(n); ByteSet a;
+    if (nd.type == T_CHAR || nd.type == T_ANY || nd.type == T_SET) {
+      Ranges r = unit_ranges(n);
+      for (auto& p : r) { for (int b = p.first; b <= std::min(p.second, 127); b++) a.set(b); if (p.second >= 128) for (int b = 128; b < 256; b++) a.set(b); }
+      return a;
+    }
+    if (nd.type == T_LOOK) return a;
+    for (int k : nd.kids) { ByteSet s = alpha_of(k); for (int i = 0; i < 4; i++) a.w[i] |= s.w[i]; }
+    return a;
+  }
+  static void or_into(ByteSet& a, const ByteSet& b) { for (int i = 0; i < 4; i++) a.w[i] |= b.w[i]; }
   static constexpr int kPreInf = 1 << 20;
   int maxlen(int n) const {
     const Node& nd = N(n); long v = 0;
@@ -501,10 +515,11 @@ struct Compiler {
     return true;
   }
 
-  static void consider(std::vector<FactorSeq>& best, bool& have, int& best_pre, const std::vector<FactorSeq>& cand, int cand_pre) {
+  static void consider(std::vector<FactorSeq>& best, bool& have, int& best_pre, ByteSet& best_alpha, const std::vector<FactorSeq>& cand, int cand_pre,
+                       const ByteSet& cand_alpha) {
     if (cand.empty()) return;
     for (auto& s : cand) if (s.empty()) return;
-    if (!have || score(cand) < score(best)) { best = cand; have = true; best_pre = std::min(cand_pre, kPreInf); }
+    if (!have || score(cand) < score(best)) { best = cand; have = true; best_pre = std::min(cand_pre, kPreInf); best_alpha = cand_alpha; }
   }
 
   Info analyse(int n) const {
@@ -526,7 +541,7 @@ struct Compiler {
           Info c = analyse(k);
           if (c.has_exact) ex.insert(ex.end(), c.exact.begin(), c.exact.end()); else all_exact = false;
           tight = tight && c.is_exact_tight;
-          if (c.has_factors) { fa.insert(fa.end(), c.factors.begin(), c.factors.end()); I.fpre = std::max(I.fpre, c.fpre); } else all_fact = false;
+          if (c.has_factors) { fa.insert(fa.end(), c.factors.begin(), c.factors.end()); I.fpre = std::max(I.fpre, c.fpre); or_into(I.fpre_alpha, c.fpre_alpha); } else all_fact = false;
         }
         if (all_exact && ex.size() <= kMaxSeqs) { I.has_exact = true; I.exact = ex; I.is_exact_tight = tight; }
         if (all_fact && fa.size() <= 4 * kMaxSeqs) { I.has_factors = true; I.factors = fa; }
@@ -552,29 +567,33 @@ struct Compiler {
             if (ok && nd.min == nd.max && copies == nd.min) { I.has_exact = true; I.exact = run; I.is_exact_tight = b.is_exact_tight; }
           }
         }
-        std::vector<FactorSeq> best; bool hb = false; int bpre = 0;
-        if (have) consider(best, hb, bpre, run, 0);
+        std::vector<FactorSeq> best; bool hb = false; int bpre = 0; ByteSet balpha;
+        if (have) consider(best, hb, bpre, balpha, run, 0, ByteSet());
         if (b.has_factors) {
           int ml = maxlen(nd.kids[0]);
           long before = nd.max == INF ? (ml ? kPreInf : 0) : (long)(nd.max - 1) * ml;
-          consider(best, hb, bpre, b.factors, (int)std::min<long>(before + b.fpre, kPreInf));
+          ByteSet al = b.fpre_alpha; if (nd.max != 1) or_into(al, alpha_of(nd.kids[0]));     // earlier iterations of the body
+          consider(best, hb, bpre, balpha, b.factors, (int)std::min<long>(before + b.fpre, kPreInf), al);
         }
-        if (hb) { I.has_factors = true; I.factors = best; I.fpre = bpre; }
+        if (hb) { I.has_factors = true; I.factors = best; I.fpre = bpre; I.fpre_alpha = balpha; }
         return I;
       }
       case T_CAT: {
         std::vector<FactorSeq> run = {FactorSeq{}}; bool run_tight = true;
-        std::vector<FactorSeq> best; bool hb = false; int bpre = 0;
+        std::vector<FactorSeq> best; bool hb = false; int bpre = 0; ByteSet balpha;
         bool all_exact = true, tight = true;
         long pos = 0; int run_pre = 0;      // pos: max units consumed by the children before the current one
+        ByteSet alpha_before, run_alpha;    // bytes the children before the current one / before the run can consume
         auto run_is_empty = [&]() { return run.size() == 1 && run[0].empty(); };
-        auto close_run = [&]() { bool nonempty = false; for (auto& s : run) if (!s.empty()) nonempty = true; bool allne = true; for (auto& s : run) if (s.empty()) allne = false; if (nonempty && allne) consider(best, hb, bpre, run, run_pre); run = {FactorSeq{}}; };
+        auto close_run = [&]() { bool nonempty = false; for (auto& s : run) if (!s.empty()) nonempty = true; bool allne = true; for (auto& s : run) if (s.empty()) allne = false; if (nonempty && allne) consider(best, hb, bpre, balpha, run, run_pre, run_alpha); run = {FactorSeq{}}; };
         for (int k : nd.kids) {
           Info c = analyse(k);
           const int pre_k = (int)std::min<long>(pos, kPreInf);
           pos = std::min<long>(pos + maxlen(k), kPreInf);
-          if (c.has_factors) consider(best, hb, bpre, c.factors, (int)std::min<long>((long)pre_k + c.fpre, kPreInf));
-          if (run_is_empty()) run_pre = pre_k;
+          const ByteSet alpha_k = alpha_before;
+          or_into(alpha_before, alpha_of(k));
+          if (c.has_factors) { ByteSet al = alpha_k; or_into(al, c.fpre_alpha); consider(best, hb, bpre, balpha, c.factors, (int)std::min<long>((long)pre_k + c.fpre, kPreInf), al); }
+          if (run_is_empty()) { run_pre = pre_k; run_alpha = alpha_k; }
           // a REPEAT with min>=1 contributes its required prefix to the run and then breaks it
           const Node& kn = N(k);
           bool breaks_after = false;
@@ -608,14 +627,14 @@ struct Compiler {
             if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; }
             nx.push_back(s);
           }
-          if (nx.size() > kMaxSeqs) { all_exact = false; close_run(); run = piece; run_pre = pre_k; if (run.size() > kMaxSeqs) run = {FactorSeq{}}; for (auto& s : run) if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; } }
+          if (nx.size() > kMaxSeqs) { all_exact = false; close_run(); run = piece; run_pre = pre_k; run_alpha = alpha_k; if (run.size() > kMaxSeqs) run = {FactorSeq{}}; for (auto& s : run) if (s.size() > kMaxRunLen) { s.resize(kMaxRunLen); cut = true; } }
           else run.swap(nx);
           if (cut) { all_exact = false; close_run(); }
           if (breaks_after) { all_exact = false; close_run(); }
         }
         if (all_exact) { I.has_exact = true; I.exact = run; I.is_exact_tight = tight && run_tight; }
         close_run();
-        if (hb) { I.has_factors = true; I.factors = best; I.fpre = bpre; }
+        if (hb) { I.has_factors = true; I.factors = best; I.fpre = bpre; I.fpre_alpha = balpha; }
         if (I.has_exact && !I.has_factors) { bool allne = true; for (auto& s : I.exact) if (s.empty()) allne = false; if (allne && !I.exact.empty()) { I.has_factors = true; I.factors = I.exact; I.fpre = 0; } }
         return I;
       }
@@ -680,6 +699,7 @@ CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
         if (ok) {
           out.factors = I.factors;
           out.factor_pre = I.fpre;
+          out.factor_pre_alpha = I.fpre_alpha;
           out.factors_exact = I.has_exact && I.is_exact_tight && I.exact == I.factors;
         }
       }
@@ -760,6 +780,7 @@ static void collect_full_factors(const std::vector<CompiledRule>& rules, Prefilt
       FullFactor ff{}; ff.rule = (uint32_t)r; ff.len = (uint8_t)std::min<size_t>(f.size(), kMaxFactorElems);
       ff.exact = (rules[r].factors_exact && f.size() <= (size_t)kMaxFactorElems) ? 1 : 0;
       ff.pre = rules[r].factor_pre >= 0xffff ? 0xffff : (uint16_t)rules[r].factor_pre;
+      ff.pre_alpha = set_id(rules[r].factor_pre_alpha);
       for (int k = 0; k < ff.len; k++) ff.elem[k] = set_id(f[k]);
       P.factors.push_back(ff); seqs.push_back(FactorSeq(f.begin(), f.begin() + ff.len));
     }
@@ -885,6 +906,7 @@ bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOpti
       FullFactor ff{}; ff.rule = (uint32_t)r; ff.len = (uint8_t)std::min<size_t>(f.size(), kMaxFactorElems);
       ff.exact = (rules[r].factors_exact && f.size() <= (size_t)kMaxFactorElems) ? 1 : 0;
       ff.pre = rules[r].factor_pre >= 0xffff ? 0xffff : (uint16_t)rules[r].factor_pre;
+      ff.pre_alpha = set_id(rules[r].factor_pre_alpha);
       for (int k = 0; k < ff.len; k++) ff.elem[k] = set_id(f[k]);
       P.factors.push_back(ff); seqs.push_back(FactorSeq(f.begin(), f.begin() + ff.len));
     }

@@ -71,6 +71,7 @@ struct CompiledRule {
   ByteSet alphabet;                 // every byte any consuming instruction could accept (over-approximation)
   std::vector<FactorSeq> factors;   // necessary factors; empty => rule is an "always candidate"
   int factor_pre = 1 << 20;         // max units of a match that can precede the factor occurrence (>= 0xffff: unbounded)
+  ByteSet factor_pre_alpha;         // bytes the part of a match before the factor can consist of
   bool factors_exact = false;       // every match IS one of the factors (pure literal alternation, no assertions)
 };
 
@@ -96,6 +97,7 @@ struct FullFactor {
   uint8_t len, win_off, win_len, exact;   // exact: a confirmed occurrence proves the rule matches (RegExp.test)
   uint16_t elem[kMaxFactorElems];         // byte-set ids
   uint16_t pre;                           // max units of a match before the factor (0xffff = unbounded)
+  uint16_t pre_alpha;                     // byte-set id: what the part of a match before the factor can consist of
 };
 struct Prefilter {
   int mode = 2;

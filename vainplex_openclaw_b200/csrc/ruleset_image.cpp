@@ -48,7 +48,7 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     H.factor_words.push_back(f.rule);
     H.factor_words.push_back((uint32_t)f.len | ((uint32_t)f.win_off << 8) | ((uint32_t)f.win_len << 16) | ((uint32_t)f.exact << 24));
     for (int k = 0; k < kMaxFactorElems; k += 2) H.factor_words.push_back((uint32_t)f.elem[k] | ((uint32_t)f.elem[k + 1] << 16));
-    H.factor_words.push_back(f.pre); H.factor_words.push_back(0);
+    H.factor_words.push_back(f.pre); H.factor_words.push_back(f.pre_alpha);
   }
   if (H.pf.mode == 4) {
     // fingerprint table replicated once per bank: word (bucket * 32 + lane) holds bucket's two fingerprints

@@ -420,8 +420,11 @@ confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, con
 // ------------------------------------------------------------------------------------------
 // level 3: exact verification by the Pike VM
 // ------------------------------------------------------------------------------------------
-constexpr int kVerifyThreads = 64;
-constexpr int kSmallProg = 160;          // VM capacity that covers every built-in rule (longest: 133 instructions)
+constexpr int kVerifyThreads = 64;            // verify_large_kernel
+// verify_small_kernel: VM runs diverge completely (different program, different text per lane), so a warp
+// pays the SUM of its lanes' instruction streams.  Only kVerifyLanes lanes per warp carry a run.
+constexpr int kVerifyBlock = 256, kVerifyLanes = 3, kVerifySlots = (kVerifyBlock / 32) * kVerifyLanes;
+constexpr int kSmallProg = 192;          // VM capacity that covers every built-in rule (longest: key-value-credential, 183 instructions)
 
 struct GlobalSpanSink {
   const ScanWork& w; uint32_t msg, rule;
@@ -441,35 +444,48 @@ struct SmemStore {
   __device__ __forceinline__ uint32_t& st(int L, uint32_t i) { return sts_[(L * cap + i) * stride + t]; }
   __device__ __forceinline__ uint16_t& stk(uint32_t i) { return stk_[i * stride + t]; }
 };
-constexpr size_t kVerifySmem = (size_t)kVerifyThreads * (kSmallProg * 2 + 2 * kSmallProg * 2 + 2 * kSmallProg * 4 + kVmStack * 2);
+constexpr int kStageMsg = 256;                       // messages up to this many bytes are staged into shared memory
+constexpr size_t kVerifyVmBytes = (size_t)kVerifySlots * (kSmallProg * 2 + 2 * kSmallProg * 2 + 2 * kSmallProg * 4 + kVmStack * 2);
+constexpr size_t kVerifyProgBytes = (size_t)kVerifySlots * (kSmallProg + 1) * 4;     // odd word stride per slot: conflict-free
+constexpr size_t kVerifyMsgBytes = (size_t)kVerifySlots * (kStageMsg + 4);
+constexpr size_t kVerifySmem = kVerifyVmBytes + kVerifyProgBytes + kVerifyMsgBytes;
 
 // small programs (<= kSmallProg instructions): VM state in shared memory
 template <bool SPANS>
-__global__ void __launch_bounds__(kVerifyThreads)
+__global__ void __launch_bounds__(kVerifyBlock)
 verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off) {
   extern __shared__ __align__(16) uint8_t vsm[];
   const uint32_t n_events = min(w.counters[1], w.event_cap);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane >= (uint32_t)kVerifyLanes) return;
+  const uint32_t slot_id = warp * kVerifyLanes + lane;                 // this thread's VM slot inside the block
   SmemStore st;
-  st.stride = kVerifyThreads; st.t = threadIdx.x;
+  st.stride = kVerifySlots; st.t = slot_id;
   st.sts_ = reinterpret_cast<uint32_t*>(vsm);
-  st.pcs_ = reinterpret_cast<uint16_t*>(vsm + (size_t)kVerifyThreads * 2 * kSmallProg * 4);
-  st.mark_ = st.pcs_ + (size_t)kVerifyThreads * 2 * kSmallProg;
-  st.stk_ = st.mark_ + (size_t)kVerifyThreads * kSmallProg;
+  st.pcs_ = reinterpret_cast<uint16_t*>(vsm + (size_t)kVerifySlots * 2 * kSmallProg * 4);
+  st.mark_ = st.pcs_ + (size_t)kVerifySlots * 2 * kSmallProg;
+  st.stk_ = st.mark_ + (size_t)kVerifySlots * kSmallProg;
   VMS<SmemStore> vm(rs, st);
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
+  // per-thread staging areas: the rule's program and (for short messages) the message bytes, so the
+  // VM's dependent loads hit shared memory instead of chains of L2 round trips
+  uint32_t* my_prog = reinterpret_cast<uint32_t*>(vsm + kVerifyVmBytes) + (size_t)slot_id * (kSmallProg + 1);
+  uint8_t* my_msg = vsm + kVerifyVmBytes + kVerifyProgBytes + (size_t)slot_id * (kStageMsg + 4);
+  for (uint32_t e = blockIdx.x * kVerifySlots + slot_id; e < n_events; e += gridDim.x * kVerifySlots) {
     uint2 ev = w.events[e];
     uint32_t slot = ev.x, rule = ev.y;
-    uint32_t plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
+    const uint32_t poff = rs.rule_prog_off[rule], plen = rs.rule_prog_off[rule + 1] - poff;
     if (plen > (uint32_t)kSmallProg) continue;          // handled by verify_large_kernel
     uint32_t msg = w.slot_msg[slot];
     GlobalSpanSink sink{w, msg, rule};
     const uint32_t t0 = w.event_pos[e];
+    if (!SPANS && t0 != 0xffffffffu && ((w.hit[(size_t)slot * rs.rw + (rule >> 5)] >> (rule & 31)) & 1u)) continue;   // another occurrence already proved it
+    for (uint32_t k = 0; k < plen; k++) my_prog[k] = rs.prog[poff + k];
+    vm.prog_override = my_prog;
+    const uint8_t* m = bytes + off[msg]; const uint32_t len = off[msg + 1] - off[msg];
+    if (len <= (uint32_t)kStageMsg) { for (uint32_t k = 0; k < len; k++) my_msg[k] = m[k]; m = my_msg; }
     bool any;
-    if (SPANS || t0 == 0xffffffffu) any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
-    else {
-      if ((w.hit[(size_t)slot * rs.rw + (rule >> 5)] >> (rule & 31)) & 1u) continue;     // another occurrence already proved it
-      any = test_at_factor(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], t0, w.event_pre[e]);
-    }
+    if (SPANS || t0 == 0xffffffffu) any = run_rule<SPANS>(vm, rs, rule, m, len, sink);
+    else any = test_at_factor(vm, rs, rule, m, len, t0, w.event_pre[e]);
     if (any) atomicOr(&w.hit[(size_t)slot * rs.rw + (rule >> 5)], 1u << (rule & 31));
   }
   if (vm.err) atomicOr(&w.counters[3], vm.err);
@@ -556,9 +572,9 @@ int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byte
                   bool want_spans, int sm_count, cudaStream_t stream) {
   int k = 1;
   if (want_spans) {
-    verify_small_kernel<true><<<sm_count, kVerifyThreads, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+    verify_small_kernel<true><<<sm_count * 2, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   } else {
-    verify_small_kernel<false><<<sm_count, kVerifyThreads, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+    verify_small_kernel<false><<<sm_count * 2, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   }
   if (rs.max_prog_len > (uint32_t)kSmallProg) {
     k++;
