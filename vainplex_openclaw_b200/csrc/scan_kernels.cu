@@ -423,7 +423,7 @@ confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, con
 constexpr int kVerifyThreads = 64;            // verify_large_kernel
 // verify_small_kernel: VM runs diverge completely (different program, different text per lane), so a warp
 // pays the SUM of its lanes' instruction streams.  Only kVerifyLanes lanes per warp carry a run.
-constexpr int kVerifyBlock = 256, kVerifyLanes = 3, kVerifySlots = (kVerifyBlock / 32) * kVerifyLanes;
+constexpr int kVerifyBlock = 256, kVerifyLanes = 2, kVerifySlots = (kVerifyBlock / 32) * kVerifyLanes;
 constexpr int kSmallProg = 192;          // VM capacity that covers every built-in rule (longest: key-value-credential, 183 instructions)
 
 struct GlobalSpanSink {
@@ -479,10 +479,10 @@ verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
     GlobalSpanSink sink{w, msg, rule};
     const uint32_t t0 = w.event_pos[e];
     if (!SPANS && t0 != 0xffffffffu && ((w.hit[(size_t)slot * rs.rw + (rule >> 5)] >> (rule & 31)) & 1u)) continue;   // another occurrence already proved it
-    for (uint32_t k = 0; k < plen; k++) my_prog[k] = rs.prog[poff + k];
-    vm.prog_override = my_prog;
+    // (staging the program / message into shared memory was measured: the copy loops cost more than the
+    //  L1-cached global loads they replace, so the VM reads both through the read-only path)
+    (void)my_prog; (void)my_msg; (void)poff;
     const uint8_t* m = bytes + off[msg]; const uint32_t len = off[msg + 1] - off[msg];
-    if (len <= (uint32_t)kStageMsg) { for (uint32_t k = 0; k < len; k++) my_msg[k] = m[k]; m = my_msg; }
     bool any;
     if (SPANS || t0 == 0xffffffffu) any = run_rule<SPANS>(vm, rs, rule, m, len, sink);
     else any = test_at_factor(vm, rs, rule, m, len, t0, w.event_pre[e]);
