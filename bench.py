@@ -314,7 +314,7 @@ def main():
                      "traffic": traffic, "kernel": "scan_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms},
         "kernel_ms": {"scan": scan_ms, "confirm": float(np.median(kms[:, 1])), "verify": float(np.median(kms[:, 2])), "finalize": float(np.median(kms[:, 3]))},
-        "candidates": {"level1_events": counters[4], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
+        "candidates": {"level1_events": counters[4], "slow_chunks": counters[5], "slow_warp_entries": counters[6], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
                        "hit_messages": int((words != 0).sum().item()), "injected": len(inj)},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "msgs/s", "h2d_bytes_per_step": int(n * L + 4 * (n + 1)), "d2h_bytes_per_step": int(8 * n + 64),

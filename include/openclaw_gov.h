@@ -100,7 +100,7 @@ CG_API uint64_t cg_launch_count(void);   /* kernels launched by this library so 
  * with profiling on, CUDA events bracket each kernel of a scan step on its stream. */
 CG_API int cg_set_profiling(int on);
 CG_API int cg_last_kernel_ms(float out_ms[4]);          /* scan, confirm, verify, finalize of the last completed step */
-CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out5[5]); /* slots, VM pairs, spans, flags, level-1 events */
+CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out8[8]); /* slots, VM pairs, spans, flags, level-1 events, slow-path chunks, slow-path warp entries, reserved */
 
 /* ---- rule-set compile.  Replaces `new RegExp(pattern)` in buildPolicyIndex
  * (src/policy-loader.ts:119-128), compileCustomPattern (src/redaction/registry.ts:249-281) and

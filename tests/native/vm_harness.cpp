@@ -51,7 +51,7 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   H.pf.always_rules.resize(H.pf.always_rules.size() + 4, 0);
   d.image = H.image.data(); d.image_bytes = (uint32_t)H.image.size(); d.mode = (uint32_t)H.pf.mode;
   d.ncols_log2 = 0; while ((1 << d.ncols_log2) < H.pf.ncols) d.ncols_log2++;
-  d.nstates = (uint32_t)H.pf.nstates; d.hot_states = H.hot_states; d.table_full = H.pf.table.data();
+  d.nstates = (uint32_t)H.pf.nstates; d.hot_states = H.hot_states; d.lut_off = H.lut_off; d.row_stride = H.row_stride; d.table_full = H.pf.table.data();
   d.acc_index = H.pf.acc_index.data(); d.acc_offsets = H.pf.acc_offsets.data(); d.acc_factors = H.pf.acc_factors.data();
   d.factors = H.factor_words.data(); d.bytesets = H.pf.bytesets.data();
   d.always_rules = H.pf.always_rules.data(); d.n_always = n_always;
@@ -109,7 +109,7 @@ void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand,
   for (uint32_t k = 0; k < d.rw; k++) { cand[k] = 0; direct[k] = 0; }
   BitSink sink{cand, direct, nullptr};
   for (uint32_t k = 0; k < d.n_always; k++) sink.candidate(d.always_rules[k]);
-  const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
+  const uint8_t* lut = d.image + d.lut_off; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0, hits = 0;
   if (d.mode == 4) {        // the fingerprint scan restated: rolling 4-symbol window, hash, 2-way bucket
     uint32_t win = 0;
@@ -140,7 +140,7 @@ void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits
   for (uint32_t k = 0; k < d.rw; k++) hits[k] = 0;
   BitSink sink{cand.data(), hits, &occ};
   for (uint32_t k = 0; k < d.n_always; k++) sink.candidate(d.always_rules[k]);
-  const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
+  const uint8_t* lut = d.image + d.lut_off; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0;
   if (d.mode == 4) {
     uint32_t win = 0;
@@ -170,7 +170,7 @@ void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits
 // debug: level-1 accepting transitions per factor over one message (adds into counts[n_factors])
 void harness_l1_factor_counts(void* p, const uint8_t* m, uint32_t len, uint32_t* counts) {
   Harness* h = (Harness*)p; const DevRuleset& d = h->d;
-  const uint8_t* lut = d.image; const uint16_t* table = h->H.pf.table.data();
+  const uint8_t* lut = d.image + d.lut_off; const uint16_t* table = h->H.pf.table.data();
   uint32_t state = 0;
   if (d.mode == 4) {
     uint32_t win = 0;

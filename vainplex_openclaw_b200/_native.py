@@ -201,8 +201,8 @@ class Ruleset:
             return spans[:ns.value]
 
     def work_counters(self):
-        """(slots, VM pairs, spans, error flags, level-1 events) of the last completed step."""
-        out = np.zeros(5, dtype=np.uint32)
+        """(slots, VM pairs, spans, error flags, level-1 events, slow-path chunks, slow-path warp entries, 0) of the last completed step."""
+        out = np.zeros(8, dtype=np.uint32)
         check(load().cg_scan_work_counters(self.handle, out.ctypes.data))
         return tuple(int(x) for x in out)
 

@@ -232,11 +232,12 @@ int cg_last_kernel_ms(float out_ms[4]) {
   return CG_OK;
 }
 
-int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out5[5]) {
+int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out8[8]) {
   // [0] slots (messages with confirmed candidates), [1] (message, rule) pairs sent to the VM, [2] spans,
-  // [3] error flags, [4] level-1 accept events -- of the last completed step
-  if (!rs || !out5 || !rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
-  CU(cudaMemcpy(out5, rs->work.counters, 20, cudaMemcpyDeviceToHost));
+  // [3] error flags, [4] level-1 accept events, [5] 16-byte chunks re-walked by the scan kernel's slow path,
+  // [6] warp-level entries into that slow path, [7] reserved -- of the last completed step
+  if (!rs || !out8 || !rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
+  CU(cudaMemcpy(out8, rs->work.counters, 32, cudaMemcpyDeviceToHost));
   return CG_OK;
 }
 
@@ -286,8 +287,9 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   const uint8_t* d_image; if ((rc = upload(rs.get(), image, &d_image, 16))) return rc;
   d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode;
   d.ncols_log2 = 0; while ((1 << d.ncols_log2) < P.ncols) d.ncols_log2++;
-  d.nstates = (uint32_t)P.nstates; d.hot_states = H.hot_states;
+  d.nstates = (uint32_t)P.nstates; d.hot_states = H.hot_states; d.lut_off = H.lut_off; d.row_stride = H.row_stride;
   d.scan_streams = 1; if (const char* e = getenv("CG_SCAN_STREAMS")) d.scan_streams = (uint32_t)atoi(e);
+  d.debug_flags = 0; if (const char* e = getenv("CG_SCAN_DEBUG")) d.debug_flags = (uint32_t)atoi(e);   // 1: skip the slow path (timing experiments only, results wrong)
   if ((rc = upload(rs.get(), P.table, &d.table_full, 64))) return rc;
   if ((rc = upload(rs.get(), P.acc_index, &d.acc_index))) return rc;
   if ((rc = upload(rs.get(), P.acc_offsets, &d.acc_offsets))) return rc;

@@ -7,7 +7,8 @@ namespace cg {
 
 // Everything the scan / verify kernels need to know about a compiled rule set (device pointers).
 struct DevRuleset {
-  const uint8_t* image;          // [lut 256 B][level-1 table nstates*ncols u16], 16-byte aligned, size % 16 == 0
+  const uint8_t* image;          // shared-memory image (layout: ruleset_image.h), 16-byte aligned, size % 16 == 0
+  uint32_t lut_off, row_stride;  // DFA modes: byte offset of the 256-byte LUT inside the image; bytes between table rows
   uint32_t image_bytes;
   uint32_t mode;                 // 0 = direct 7-bit columns, 1 = LUT columns, 2 = folded 6-bit, 3 = folded 5-bit columns, 4 = fingerprint table
   uint32_t max_prog_len;         // longest Pike program of the set (picks the VM capacity)
@@ -15,6 +16,7 @@ struct DevRuleset {
   uint32_t nstates;
   uint32_t hot_states;           // rows [0, hot_states) + one trap row are in the shared-memory image, the rest only in table_full
   uint32_t scan_streams;         // message streams per lane in scan_kernel (1 or 2)
+  uint32_t debug_flags;          // CG_SCAN_DEBUG (timing experiments): bit 0 = skip the scan kernel's slow path
   const uint16_t* table_full;    // complete level-1 table in HBM (L2-resident)
   const uint32_t* acc_index;     // nstates*ncols: accept id of an accepting transition
   const uint32_t* acc_offsets;   // CSR over accept ids -> factor ids

@@ -52,7 +52,7 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   }
   if (H.pf.mode == 4) {
     // fingerprint table replicated once per bank: word (bucket * 32 + lane) holds bucket's two fingerprints
-    H.hot_states = 0;
+    H.hot_states = 0; H.lut_off = 0; H.row_stride = 0;
     H.image.assign(256 + (size_t)H.pf.fp_buckets * 128, 0);
     memcpy(H.image.data(), H.pf.lut, 256);
     uint32_t* t = reinterpret_cast<uint32_t*>(H.image.data() + 256);
@@ -60,23 +60,27 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     while (H.image.size() % 16) H.image.push_back(0);
     return true;
   }
-  // shared-memory image: rows [0, hot) with every transition into a deeper state redirected to the
-  // trap row `hot` (flag 0x4000), followed by the trap row itself
+  // shared-memory image: [rows 0..hot of the table, `row_stride` bytes apart][pad to 16][lut 256 B].
+  // Entries are plain u16 state indices.  Every transition that is accepting, or leads to a state that is
+  // not resident (>= hot), is stored as `hot`, the index of an absorbing trap row: the fast path of
+  // scan_kernel then needs no flag bits -- a chunk that ends in the trap row is re-walked on the full table.
+  // row_stride = 2 * ncols + 4: the 4 pad bytes rotate consecutive rows by one bank, so lanes sitting in
+  // different states but reading the same frequent column (' ', 'e', ...) land in different banks.
+  H.row_stride = (uint32_t)cols * 2 + 4;
+  budget = std::min<size_t>(budget, 155 * 1024);            // + 64 KB staging + 6 KB event buffers + static shared memory <= 227 KB per CTA
+  hot_rows = std::min<size_t>((budget - 256 - 16) / H.row_stride, 16383);
   H.hot_states = (uint32_t)std::min<size_t>(hot_rows > 1 ? hot_rows - 1 : 1, (size_t)H.pf.nstates);
   const uint32_t hot = H.hot_states; const size_t nc = (size_t)H.pf.ncols;
-  std::vector<uint16_t> img((size_t)(hot + 1) * nc);
-  // mode 2: entry (row, col) lives at byte offset (2*col) ^ ((row << 2) & 0x7c) of its row (see l1_fast)
-  auto swz = [&](uint32_t row, size_t col) { return H.pf.mode == 2 ? (size_t)(((2 * col) ^ ((row << 2) & 0x7c)) / 2) : col; };
+  size_t tbl_bytes = ((size_t)(hot + 1) * H.row_stride + 15) & ~(size_t)15;
+  H.lut_off = (uint32_t)tbl_bytes;
+  H.image.assign(tbl_bytes + 256, 0);
+  auto put = [&](uint32_t row, size_t col, uint16_t v) { memcpy(H.image.data() + (size_t)row * H.row_stride + 2 * col, &v, 2); };
   for (uint32_t s = 0; s < hot; s++) for (size_t c = 0; c < nc; c++) {
     uint16_t e = H.pf.table[(size_t)s * nc + c];
-    if ((uint32_t)(e & 0x3fff) >= hot) e = (uint16_t)((e & 0x8000) | 0x4000 | hot);
-    img[(size_t)s * nc + swz(s, c)] = e;
+    put(s, c, ((e & 0x8000) || (uint32_t)(e & 0x3fff) >= hot) ? (uint16_t)hot : (uint16_t)(e & 0x3fff));
   }
-  for (size_t c = 0; c < nc; c++) img[(size_t)hot * nc + c] = (uint16_t)(0x4000 | hot);
-  H.image.assign(256 + img.size() * 2, 0);
-  memcpy(H.image.data(), H.pf.lut, 256);
-  memcpy(H.image.data() + 256, img.data(), img.size() * 2);
-  while (H.image.size() % 16) H.image.push_back(0);
+  for (size_t c = 0; c < (size_t)cols; c++) put(hot, c, (uint16_t)hot);
+  memcpy(H.image.data() + H.lut_off, H.pf.lut, 256);
   return true;
 }
 

@@ -10,8 +10,9 @@ namespace cg {
 struct HostImage {
   std::vector<CompiledRule> rules;
   Prefilter pf;
-  std::vector<uint8_t> image;          // [lut 256][first hot_states rows of the table], padded to 16 bytes
-  uint32_t hot_states = 0;             // rows resident in shared memory
+  std::vector<uint8_t> image;          // DFA modes: [rows 0..hot_states, row_stride bytes apart][lut 256]; mode 4: [lut 256][replicated buckets]
+  uint32_t hot_states = 0;             // rows resident in shared memory (row `hot_states` itself is the trap row)
+  uint32_t lut_off = 0, row_stride = 0;
   std::vector<uint32_t> prog, prog_off, sets, first, alpha;
   std::vector<uint32_t> factor_words;  // 12 words per full factor (device layout)
   std::vector<uint16_t> ranges;
@@ -20,7 +21,7 @@ struct HostImage {
 
 struct ImageOptions {
   int mode = 2;                 // level-1 mode (0 direct7, 1 LUT, 2 folded 6-bit, 3 folded 5-bit DFA; 4 fingerprint table, falls back to 2)
-  size_t budget_bytes = 200 * 1024;   // shared-memory budget of the hot rows
+  size_t budget_bytes = 155 * 1024;   // shared-memory budget of the image (scan_kernel adds 64 KB of staging buffers; 227 KB per CTA)
   int max_states = 16384;             // total states (cold rows are read from L2-resident HBM)
   int max_classes = 64;
   int max_window = kMaxWindow;

@@ -65,31 +65,14 @@ constexpr uint32_t kAccept = 0x8000u, kCold = 0x4000u, kStateMask = 0x3fffu;
 // pre-doubled column indices of the four bytes of a word (one byte each), SWAR
 template <int MODE> __device__ __forceinline__ uint32_t cols2_of_word(uint32_t w);
 template <> __device__ __forceinline__ uint32_t cols2_of_word<0>(uint32_t w) { return (w + w) & 0xfefefefeu; }
-template <> __device__ __forceinline__ uint32_t cols2_of_word<2>(uint32_t w) { return ((w & 0x1f1f1f1fu) | ((w >> 1) & 0x20202020u)) << 1; }
-template <> __device__ __forceinline__ uint32_t cols2_of_word<3>(uint32_t w) { return (w & 0x1f1f1f1fu) << 1; }
+template <> __device__ __forceinline__ uint32_t cols2_of_word<2>(uint32_t w) { return ((w << 1) & 0x3e3e3e3eu) | (w & 0x40404040u); }
+template <> __device__ __forceinline__ uint32_t cols2_of_word<3>(uint32_t w) { return (w << 1) & 0x3e3e3e3eu; }
 template <> __device__ __forceinline__ uint32_t cols2_of_word<1>(uint32_t w) { return w; }   // LUT mode resolves per byte
 
-template <int MODE> struct RowBytes { static constexpr uint32_t v = MODE == 0 ? 256u : MODE == 3 ? 64u : 128u; };
+// bytes between two rows of the shared-memory table: 2 * ncols + 4 (ruleset_image.cpp)
+template <int MODE> struct RowStride { static constexpr uint32_t v = (MODE == 0 ? 256u : MODE == 3 ? 64u : 128u) + 4u; };
 
-__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
-
-// One level-1 transition out of the shared-memory image (32-bit shared addresses, no generic
-// loads).  Rows [0, hot) are real; row `hot` is a trap row (every entry = hot | kCold) and every
-// hot-row transition into a deep state is stored as hot | kCold, so the fast path never leaves
-// shared memory: an excursion into deep states only raises kCold, and the flagged word is then
-// re-walked on the full table in HBM/L2 by the (rare) slow path, which also restores the state.
-// In mode 2 the 32 words of a row are XOR-swizzled by the low five bits of the row index (the image is
-// stored that way): lanes sitting in different states but reading the same frequent column (' ', 'e',
-// ...) then land in different banks instead of all colliding in one.
-template <int MODE>
-__device__ __forceinline__ uint32_t l1_fast(uint32_t tbl_s, uint32_t lut_s, uint32_t row_shift, uint32_t state, uint32_t c2) {
-  if (MODE == 1) return lds_u16(tbl_s + (state << row_shift) + 2u * lds_u8(lut_s + c2));
-  if (MODE == 2) return lds_u16(tbl_s + state * 128u + (c2 ^ ((state << 2) & 0x7cu)));
-  return lds_u16(tbl_s + state * RowBytes<MODE>::v + c2);
-}
-
-// the complete table (deep states included), L2-resident
+// the complete table (deep states and accept flags included), L2-resident
 __device__ __forceinline__ uint32_t l1_full(const DevRuleset& rs, uint32_t state, uint32_t col) {
   return __ldg(rs.table_full + ((size_t)state << rs.ncols_log2) + col);
 }
@@ -99,7 +82,34 @@ __device__ __forceinline__ void l1_push_one(const ScanWork& w, uint32_t msg, uin
   if (k < w.l1_cap) { w.l1_msg[k] = msg; w.l1_pos[k] = pos; w.l1_sc[k] = sc; } else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
 }
 
-template <int MODE, int NS>
+// One level-1 transition out of the shared-memory table: entries are plain state indices, so the whole
+// step is  PRMT (column of byte k) ; IMAD (row * stride + column) ; LDS.U16.  Rows [0, hot) are real, row
+// `hot` is an absorbing trap row that every accepting transition and every transition into a non-resident
+// state leads to: the fast path never tests a flag, it only looks where it ended up after 16 bytes.
+template <int MODE>
+__device__ __forceinline__ uint32_t l1_step(const uint8_t* __restrict__ tbl, const uint8_t* __restrict__ lut, uint32_t stride, uint32_t state, uint32_t c2w, int k) {
+  uint32_t c2 = __byte_perm(c2w, 0, 0x4440 + k);
+  if (MODE == 1) c2 = 2u * lut[c2];
+  return *reinterpret_cast<const uint16_t*>(tbl + state * stride + c2);
+}
+
+// Staging buffer of one warp: 64 bytes (four 16-byte units) of each of its 32 messages.  Unit u of message m
+// lives at m * 64 + ((u ^ ((m >> 1) & 3)) << 4): with that XOR both the loader's STS.128 (lane -> message
+// lane/4 + 8j, unit lane%4) and the walker's LDS.128 (lane -> its own message, unit cc) are bank-conflict free.
+constexpr uint32_t kStageBytesPerWarp = 32u * 64u;
+constexpr uint32_t kScanStageBytes = (kScanThreads / 32) * kStageBytesPerWarp;
+constexpr uint32_t kEvBuf = 16;                                 // events per warp buffered in shared memory (3 words each)
+constexpr uint32_t kScanEvBytes = (kScanThreads / 32) * kEvBuf * 12u;
+__device__ __forceinline__ uint32_t stage_off(uint32_t m, uint32_t u) { return m * 64u + ((u ^ ((m >> 1) & 3u)) << 4); }
+
+// Lane-per-message walk, but the message bytes do not arrive lane-per-message: a lane reading 16 bytes of its
+// own message makes every LDG.128 touch 32 different 128-byte lines (32 L1 wavefronts per instruction, more
+// load/store-pipe time than the table walk itself).  Instead the warp fetches "group g" = 64 bytes of each of
+// its 32 messages with four LDG.128 whose lanes cover 8 messages x 64 contiguous bytes each (8 lines per
+// instruction, every 32-byte sector fully used), transposes through the staging buffer, and each lane then
+// pulls its own 16-byte chunks out of shared memory.  The loads of group g+1 are in flight while group g is
+// walked.
+template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
             uint64_t* __restrict__ words) {
@@ -115,128 +125,147 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
     }
   }
   mbar_wait(&bar, 0);
-  const uint8_t* lut = smem;
-  const uint32_t lut_s = smem_u32(smem), tbl_s = lut_s + 256u;
-  const uint32_t row_shift = rs.ncols_log2 + 1, hot = rs.hot_states;
+  const uint8_t* tbl = smem;
+  const uint8_t* lut = smem + rs.lut_off;
+  const uint32_t hot = rs.hot_states;
+  const uint32_t stride = MODE == 1 ? rs.row_stride : RowStride<MODE>::v;     // compile-time constant except in LUT mode
   const uint32_t FULL = 0xffffffffu;
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kScanThreads / 32;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t per_tile = 32u * NS;
-  const uint32_t ntiles = (n + per_tile - 1) / per_tile;
+  uint8_t* stage = smem + ((rs.image_bytes + 127u) & ~127u) + warp * kStageBytesPerWarp;
+  const uint32_t ld_unit = lane & 3u;                          // loader role: unit of the group this lane fetches
+  // Level-1 accept events are collected in a small per-warp buffer in shared memory and appended to the global
+  // queue kEvBuf at a time: one returning atomic (a ~1 us round trip to L2 that stalls the whole warp) per
+  // flush instead of one per flagged word.
+  uint32_t* evb = reinterpret_cast<uint32_t*>(smem + ((rs.image_bytes + 127u) & ~127u) + kScanStageBytes) + warp * (3u * kEvBuf);
+  uint32_t evn = 0;                                            // warp-uniform fill level
+  auto flush_events = [&]() {
+    if (evn == 0) return;
+    __syncwarp();
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&w.counters[4], evn);
+    base = __shfl_sync(FULL, base, 0);
+    if (base + evn > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
+    else if (lane < evn) { w.l1_msg[base + lane] = evb[3u * lane]; w.l1_pos[base + lane] = evb[3u * lane + 1]; w.l1_sc[base + lane] = evb[3u * lane + 2]; }
+    evn = 0;
+    __syncwarp();
+  };
+  const uint32_t ntiles = (n + 31u) / 32u;
   for (uint32_t tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
-    uint32_t msg[NS], b[NS], e[NS], p[NS], state[NS], nch[NS];
-    uint32_t maxch = 0;
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      msg[s] = tile * per_tile + s * 32 + lane;
-      const bool valid = msg[s] < n;
-      b[s] = valid ? off[msg[s]] : 0u; e[s] = valid ? off[msg[s] + 1] : 0u;
-      if (valid && rs.n_always) l1_push_one(w, msg[s], 0, kL1Always);
-      state[s] = 0; p[s] = b[s];
-      // unaligned head: byte-wise on the full table
-      uint32_t head_end = (b[s] + 15u) & ~15u; if (head_end > e[s]) head_end = e[s];
-      for (; p[s] < head_end; p[s]++) {
-        uint32_t col = l1_col(rs.mode, lut, bytes[p[s]]);
-        uint32_t ent = l1_full(rs, state[s], col);
-        if (ent & kAccept) l1_push_one(w, msg[s], p[s] - b[s], (state[s] << 8) | col);
-        state[s] = ent & kStateMask;
-      }
-      nch[s] = (e[s] - p[s]) >> 4;
-      maxch = max(maxch, nch[s]);
+    const uint32_t msg = tile * 32u + lane;
+    const bool valid = msg < n;
+    const uint32_t b = valid ? off[msg] : 0u, e = valid ? off[msg + 1] : 0u;
+    if (valid && rs.n_always) l1_push_one(w, msg, 0, kL1Always);
+    uint32_t state = 0, p = b;
+    // unaligned head: byte-wise on the full table
+    uint32_t head_end = (b + 15u) & ~15u; if (head_end > e) head_end = e;
+    for (; p < head_end; p++) {
+      uint32_t col = l1_col(rs.mode, lut, bytes[p]);
+      uint32_t ent = l1_full(rs, state, col);
+      if (ent & kAccept) l1_push_one(w, msg, p - b, (state << 8) | col);
+      state = ent & kStateMask;
     }
+    const uint32_t nch = (e - p) >> 4;
+    uint32_t maxch = nch;
 #pragma unroll
     for (int d = 16; d; d >>= 1) maxch = max(maxch, __shfl_xor_sync(FULL, maxch, d));
+    const uint32_t ngroups = (maxch + 3u) >> 2;
 
-    // warp-uniform main loop over 16-byte chunks of NS message streams; the chunks are software-
-    // pipelined kPrefetch deep in registers so the HBM latency of chunk c+kPrefetch hides behind
-    // the table walk of chunk c
-    constexpr int kPrefetch = 3;
-    uint4 buf[NS][kPrefetch];
+    // loader role: this lane fetches unit ld_unit of messages (lane / 4) + 8 j, j = 0..3
+    uint32_t lp[4], ln[4];
 #pragma unroll
-    for (int s = 0; s < NS; s++)
+    for (int j = 0; j < 4; j++) { lp[j] = __shfl_sync(FULL, p, (lane >> 2) + 8 * j); ln[j] = __shfl_sync(FULL, nch, (lane >> 2) + 8 * j); }
+    uint4 r[4];
+    auto load_group = [&](uint32_t g) {
+      const uint32_t cidx = 4u * g + ld_unit;
 #pragma unroll
-      for (int d = 0; d < kPrefetch; d++) { buf[s][d] = make_uint4(0, 0, 0, 0); if ((uint32_t)d < nch[s]) buf[s][d] = ldg_stream(bytes + p[s] + 16 * d); }
-    for (uint32_t c = 0; c < maxch; c++) {
-      uint4 v[NS]; bool act[NS];
+      for (int j = 0; j < 4; j++) { r[j] = make_uint4(0, 0, 0, 0); if (cidx < ln[j]) r[j] = ldg_stream(bytes + lp[j] + 16u * cidx); }
+    };
+    auto store_group = [&]() {
 #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        act[s] = c < nch[s]; v[s] = buf[s][0];
+      for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(stage + stage_off((lane >> 2) + 8 * j, ld_unit)) = r[j];
+    };
+    if (ngroups) { load_group(0); __syncwarp(); store_group(); __syncwarp(); if (ngroups > 1) load_group(1); }
+    for (uint32_t g = 0; g < ngroups; g++) {
+#pragma unroll 1
+      for (uint32_t cc = 0; cc < 4; cc++) {
+        const bool act = 4u * g + cc < nch;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(lane, cc));
 #pragma unroll
-        for (int d = 0; d + 1 < kPrefetch; d++) buf[s][d] = buf[s][d + 1];
-        buf[s][kPrefetch - 1] = make_uint4(0, 0, 0, 0);
-        if (c + kPrefetch < nch[s]) buf[s][kPrefetch - 1] = ldg_stream(bytes + p[s] + 16 * kPrefetch);
-      }
+        for (int q = 0; q < 4; q++) {
+          const uint32_t c2 = cols2_of_word<MODE>(q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w);
+          uint32_t fs = min(state, hot);                     // a non-resident state at word start: straight into the trap row
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint32_t s0[NS], acc[NS], wd[NS], fs[NS];
+          for (int k = 0; k < 4; k++) fs = l1_step<MODE>(tbl, lut, stride, fs, c2, k);
+          const bool flagged = act && fs == hot;
+          const uint32_t fl = __ballot_sync(FULL, flagged);
+          if (fl == 0) { if (act) state = fs; continue; }
+          // rare: an accepting transition or an excursion into non-resident states somewhere in this word.
+          // Flagged lanes re-walk the four bytes from the word's start state: resident transitions from shared
+          // memory, trapped ones from the full table in L2 (accept flag + true successor).
+          if (rs.debug_flags & 1u) continue;
+          if (lane == 0) { atomicAdd(&w.counters[5], (uint32_t)__popc(fl)); atomicAdd(&w.counters[6], 1u); }
+          uint32_t cnt = 0, ev_pos[4], ev_sc[4];
+          if (flagged) {
+            uint32_t st = state;
 #pragma unroll
-        for (int s = 0; s < NS; s++) {
-          wd[s] = q == 0 ? v[s].x : q == 1 ? v[s].y : q == 2 ? v[s].z : v[s].w;
-          s0[s] = state[s];
-          acc[s] = state[s] >= hot ? kCold : 0u;          // a deep state at word start: this word goes the slow way
-          fs[s] = min(state[s], hot);
-        }
-        uint32_t c2[NS];
+            for (int k = 0; k < 4; k++) {
+              uint32_t c2k = __byte_perm(c2, 0, 0x4440 + k);
+              if (MODE == 1) c2k = 2u * lut[c2k];
+              uint32_t nx = hot;
+              if (st < hot) nx = *reinterpret_cast<const uint16_t*>(tbl + st * stride + c2k);
+              if (nx == hot) {
+                const uint32_t ent = l1_full(rs, st, c2k >> 1);
+                if (ent & kAccept) {
 #pragma unroll
-        for (int s = 0; s < NS; s++) c2[s] = cols2_of_word<MODE>(wd[s]);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-#pragma unroll
-          for (int s = 0; s < NS; s++) {
-            uint32_t ent = l1_fast<MODE>(tbl_s, lut_s, row_shift, fs[s], __byte_perm(c2[s], 0, 0x4440 + k));
-            acc[s] |= ent; fs[s] = ent & kStateMask;
-          }
-        }
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-          const bool flagged = act[s] && (acc[s] & (kAccept | kCold));
-          if (act[s]) state[s] = fs[s];
-          // rare: an accepting transition or an excursion into deep states in this word
-          if (__ballot_sync(FULL, flagged)) {
-            uint32_t cnt = 0, ev_pos[4], ev_sc[4];
-            if (flagged) {
-              uint32_t st = s0[s];
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                uint32_t col = l1_col(rs.mode, lut, (wd[s] >> (8 * k)) & 0xffu);
-                uint32_t ent = l1_full(rs, st, col);
-                if (ent & kAccept) { ev_pos[cnt] = p[s] + 4 * q + k - b[s]; ev_sc[cnt] = (st << 8) | col; cnt++; }
-                st = ent & kStateMask;
+                  for (int j = 0; j <= k; j++) if (cnt == (uint32_t)j) { ev_pos[j] = p + 4 * q + k - b; ev_sc[j] = (st << 8) | (c2k >> 1); }
+                  cnt++;
+                }
+                nx = ent & kStateMask;
               }
-              state[s] = st;                                 // the true state (may be a deep one)
+              st = nx;
             }
-            uint32_t idx = 0, total = 0;
+            state = st;                                      // the true state (may be a non-resident one)
+          } else if (act) state = fs;
+          uint32_t idx = 0, total = 0;
 #pragma unroll
-            for (uint32_t j = 1; j <= 4; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
-            if (total) {
+          for (uint32_t j = 1; j <= 4; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
+          if (total) {
+            if (evn + total > kEvBuf) flush_events();
+            if (total > kEvBuf) {                              // more events in one word than the buffer holds: straight to the queue
               uint32_t base = 0;
               if (lane == 0) base = atomicAdd(&w.counters[4], total);
               base = __shfl_sync(FULL, base, 0);
               if (base + total > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
               else {
 #pragma unroll
-                for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t k2 = base + idx + j; w.l1_msg[k2] = msg[s]; w.l1_pos[k2] = ev_pos[j]; w.l1_sc[k2] = ev_sc[j]; }
+                for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t k2 = base + idx + j; w.l1_msg[k2] = msg; w.l1_pos[k2] = ev_pos[j]; w.l1_sc[k2] = ev_sc[j]; }
               }
+            } else {
+#pragma unroll
+              for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t* d = evb + 3u * (evn + idx + j); d[0] = msg; d[1] = ev_pos[j]; d[2] = ev_sc[j]; }
+              evn += total;
             }
           }
         }
+        if (act) p += 16;
       }
-#pragma unroll
-      for (int s = 0; s < NS; s++) if (act[s]) p[s] += 16;
-    }
-    // tails
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      for (; p[s] < e[s]; p[s]++) {
-        uint32_t col = l1_col(rs.mode, lut, bytes[p[s]]);
-        uint32_t ent = l1_full(rs, state[s], col);
-        if (ent & kAccept) l1_push_one(w, msg[s], p[s] - b[s], (state[s] << 8) | col);
-        state[s] = ent & kStateMask;
+      if (g + 1 < ngroups) {
+        __syncwarp(); store_group(); __syncwarp();
+        if (g + 2 < ngroups) load_group(g + 2);
       }
-      if (msg[s] < n) words[msg[s]] = 0ull;
     }
+    // tail
+    for (; p < e; p++) {
+      uint32_t col = l1_col(rs.mode, lut, bytes[p]);
+      uint32_t ent = l1_full(rs, state, col);
+      if (ent & kAccept) l1_push_one(w, msg, p - b, (state << 8) | col);
+      state = ent & kStateMask;
+    }
+    if (valid) words[msg] = 0ull;
   }
+  flush_events();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -536,7 +565,7 @@ __global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict_
 void prepare_scan_kernels() {
   int dev = 0, optin = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int kMaxSmem = (optin > 0 ? optin : 227 * 1024) - 1024;     // leave room for the kernels' static shared memory
-#define CG_PREP(M) cudaFuncSetAttribute(scan_kernel<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); cudaFuncSetAttribute(scan_kernel<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
+#define CG_PREP(M) cudaFuncSetAttribute(scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
   CG_PREP(0); CG_PREP(1); CG_PREP(2); CG_PREP(3);
 #undef CG_PREP
   cudaFuncSetAttribute(scan_fp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -552,11 +581,8 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   uint32_t ntiles = (n + 31) / 32, wpb = kScanThreads / 32;
   uint32_t grid = (ntiles + wpb - 1) / wpb; if (grid > (uint32_t)sm_count) grid = sm_count;
   if (rs.mode == 4) { scan_fp_kernel<<<std::min<uint32_t>((n + 32 * wpb - 1) / (32 * wpb), (uint32_t)sm_count), kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); return 1; }
-  const int ns = rs.scan_streams == 1 ? 1 : 2;
-#define CG_LAUNCH_SCAN(M) do { if (ns == 1) { \
-      scan_kernel<M, 1><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); } \
-    else { \
-      scan_kernel<M, 2><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); } } while (0)
+  smem = ((smem + 127) & ~(size_t)127) + kScanStageBytes + kScanEvBytes;      // image + per warp: 2 KB staging buffer, event buffer
+#define CG_LAUNCH_SCAN(M) scan_kernel<M><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words)
   switch (rs.mode) { case 0: CG_LAUNCH_SCAN(0); break; case 2: CG_LAUNCH_SCAN(2); break; case 3: CG_LAUNCH_SCAN(3); break; default: CG_LAUNCH_SCAN(1); break; }
 #undef CG_LAUNCH_SCAN
   return 1;
