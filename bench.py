@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--len", type=int, default=MSG_LEN, dest="msg_len")
     ap.add_argument("--rules", type=int, default=N_RULES)
     ap.add_argument("--mode", type=int, default=int(os.environ.get("CG_PREFILTER_MODE", "2")))
+    ap.add_argument("--seed-offset", type=int, default=0, help="shift the synthetic data seed (rank r of an N-GPU run uses offset r)")
     ap.add_argument("--no-merkle", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--merkle-leaves", type=int, default=MERKLE_LEAVES)
@@ -150,7 +151,8 @@ def main():
     rs = N.Ruleset(rules, options=args.mode, strict=True)
     compile_s = time.perf_counter() - t0
     info = rs.info()
-    data, off64, inj = W.make_messages(n, L, rl, p_hit=P_HIT, seed=W.SEED_MSG + rank, device=dev)
+    data, off64, inj = W.make_messages(n, L, rl, p_hit=P_HIT, seed=W.SEED_MSG + rank + args.seed_offset, device=dev,
+                                        vocab_seed=W.SEED_MSG + args.seed_offset)
     off = off64.to(torch.int32)              # uint32 offsets (bit pattern) as the C ABI expects; n*L < 2^31 here
     words = torch.zeros(n, dtype=torch.int64, device=dev)
     stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: handle 0 would mean "library stream" to the C ABI
@@ -314,7 +316,7 @@ def main():
                      "traffic": traffic, "kernel": "scan_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms},
         "kernel_ms": {"scan": scan_ms, "confirm": float(np.median(kms[:, 1])), "verify": float(np.median(kms[:, 2])), "finalize": float(np.median(kms[:, 3]))},
-        "candidates": {"level1_events": counters[4], "slow_chunks": counters[5], "slow_warp_entries": counters[6], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
+        "candidates": {"level1_events": counters[4], "slow_warp_entries": counters[6], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
                        "hit_messages": int((words != 0).sum().item()), "injected": len(inj)},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "msgs/s", "h2d_bytes_per_step": int(n * L + 4 * (n + 1)), "d2h_bytes_per_step": int(8 * n + 64),

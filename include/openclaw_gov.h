@@ -100,7 +100,7 @@ CG_API uint64_t cg_launch_count(void);   /* kernels launched by this library so 
  * with profiling on, CUDA events bracket each kernel of a scan step on its stream. */
 CG_API int cg_set_profiling(int on);
 CG_API int cg_last_kernel_ms(float out_ms[4]);          /* scan, confirm, verify, finalize of the last completed step */
-CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out8[8]); /* slots, VM pairs, spans, flags, level-1 events, slow-path chunks, slow-path warp entries, reserved */
+CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out8[8]); /* slots, VM pairs, spans, flags, level-1 events, reserved, slow-path warp entries, reserved */
 
 /* ---- rule-set compile.  Replaces `new RegExp(pattern)` in buildPolicyIndex
  * (src/policy-loader.ts:119-128), compileCustomPattern (src/redaction/registry.ts:249-281) and
@@ -141,6 +141,13 @@ CG_API int cg_find_matches_batch(cg_ruleset *rs, const uint8_t *bytes, const uin
  * d_bytes must be readable for 16 bytes past offsets[n] (padding). */
 CG_API int cg_scan_batch_device(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n,
                                 void *d_out_words, void *stream);
+
+/* Profile-guided residency.  The level-1 automaton usually has more states than fit into shared memory; which
+ * rows are resident is decided from a state-visit histogram over a sample of real messages.  The first scan of a
+ * rule set does this by itself on (a sample of) its own batch; call this to re-profile when the traffic changes.
+ * Device pointers as for cg_scan_batch_device.  Results never depend on it, only the scan kernel's speed.
+ * No counterpart in the reference (V8 compiles each RegExp on its own). */
+CG_API int cg_ruleset_adapt(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n, void *stream);
 
 /* ---- SHA-256.  Replaces createHash("sha256").update(s).digest() at src/util.ts:77-79,
  * src/redaction/vault.ts:26-28 (and nats/src/hooks.ts:90-94) for a batch of n byte strings. */

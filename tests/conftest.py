@@ -47,4 +47,11 @@ def harness_lib():
     L.harness_test.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]
     L.harness_candidates.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.harness_policy_hits.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p]
+    L.harness_l1_hist.restype = C.c_uint64
+    L.harness_l1_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    L.harness_rank.argtypes = [C.c_void_p, C.c_void_p]
+    L.harness_image.restype = C.c_void_p
+    L.harness_image.argtypes = [C.c_void_p, C.c_void_p]
+    L.harness_table.restype = C.c_void_p
+    L.harness_table.argtypes = [C.c_void_p]
     return L

@@ -56,6 +56,26 @@ class Harness:
         self.L.harness_policy_hits(self.h, msg, len(msg), bits.ctypes.data)
         return {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
 
+    def l1_hist(self, data: np.ndarray, n_msgs: int, msg_len: int):
+        """(visits per level-1 state, accepting transitions) over n_msgs fixed-length messages"""
+        hist = np.zeros(self.info()["nstates"], dtype=np.uint64)
+        acc = self.L.harness_l1_hist(self.h, data.ctypes.data, n_msgs, msg_len, hist.ctypes.data)
+        return hist, int(acc)
+
+    def rank(self, visits: np.ndarray):
+        """profile-guided residency: renumber the states, most visited first"""
+        v = np.ascontiguousarray(visits, dtype=np.uint32)
+        self.L.harness_rank(self.h, v.ctypes.data)
+
+    def image(self):
+        """-> (image bytes, hot_states, row_stride, lut_off, full table [nstates, ncols] u16)"""
+        o = np.zeros(4, dtype=np.uint32)
+        ptr = self.L.harness_image(self.h, o.ctypes.data)
+        img = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(int(o[0]),)).copy()
+        inf = self.info()
+        tab = np.ctypeslib.as_array(C.cast(self.L.harness_table(self.h), C.POINTER(C.c_uint16)), shape=(inf["nstates"], inf["ncols"])).copy()
+        return img, int(o[1]), int(o[2]), int(o[3]), tab
+
     def candidates(self, msg: bytes):
         c, d, _ = self.candidates2(msg)
         return c | d

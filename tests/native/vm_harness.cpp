@@ -204,3 +204,38 @@ void harness_dump_factors(void* p) {
 }
 
 }  // extern "C"
+
+// level-1 state visit histogram over a batch of fixed-length messages (state resets per message):
+// hist[s] += 1 for every transition taken out of state s; returns the number of accepting transitions
+extern "C" uint64_t harness_l1_hist(void* p, const uint8_t* data, uint64_t n_msgs, uint32_t msg_len, uint64_t* hist) {
+  Harness* h = (Harness*)p; const DevRuleset& d = h->d;
+  const uint8_t* lut = d.image + d.lut_off; const uint16_t* table = h->H.pf.table.data();
+  uint64_t acc = 0;
+  for (uint64_t m = 0; m < n_msgs; m++) {
+    uint32_t state = 0;
+    const uint8_t* s = data + m * msg_len;
+    for (uint32_t i = 0; i < msg_len; i++) {
+      uint32_t col = l1_col(d.mode, lut, s[i]);
+      uint32_t ent = table[(state << d.ncols_log2) + col];
+      hist[state]++;
+      if (ent & 0x8000u) acc++;
+      state = ent & 0x3fffu;
+    }
+  }
+  return acc;
+}
+
+// profile-guided residency on the host copy: renumber the states by `visits` (see rank_states_by_visits)
+extern "C" void harness_rank(void* p, const uint32_t* visits) {
+  Harness* h = (Harness*)p; HostImage& H = h->H; DevRuleset& d = h->d;
+  rank_states_by_visits(&H, visits);
+  d.image = H.image.data(); d.image_bytes = (uint32_t)H.image.size(); d.hot_states = H.hot_states; d.lut_off = H.lut_off; d.row_stride = H.row_stride;
+  d.table_full = H.pf.table.data(); d.acc_index = H.pf.acc_index.data();
+}
+// the shared-memory image as the scan kernel sees it (tests check the trap-table invariants)
+extern "C" const uint8_t* harness_image(void* p, uint32_t* out4) {
+  Harness* h = (Harness*)p;
+  out4[0] = h->d.image_bytes; out4[1] = h->d.hot_states; out4[2] = h->d.row_stride; out4[3] = h->d.lut_off;
+  return h->d.image;
+}
+extern "C" const uint16_t* harness_table(void* p) { return ((Harness*)p)->H.pf.table.data(); }

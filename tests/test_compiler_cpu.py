@@ -202,6 +202,44 @@ def test_random_regex_differential(oracle, harness_lib):
     assert checked > 400
 
 
+def test_trap_table_image_and_profile_guided_ranking(harness_lib):
+    """The shared-memory image of scan_kernel: plain state indices, accepting / non-resident transitions -> the absorbing
+    trap row; and profile-guided residency (rank_states_by_visits) is a pure renumbering: same candidates, same hits,
+    fewer visits to non-resident rows."""
+    rl = W.make_rules(500)
+    rules = W.rules_as_tuples(rl)
+    h = Harness(harness_lib, rules, mode=2, budget_kb=48)          # small budget: most states are not resident
+    data, off, _ = W.make_messages(400, 256, rl, p_hit=0.2, seed=77)
+    buf = data.numpy()
+    msgs = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(400)]
+
+    def check_image():
+        img, hot, stride, lut_off, tab = h.image()
+        ns, nc = tab.shape
+        assert stride == 2 * nc + 4 and hot < ns and lut_off % 16 == 0 and len(img) == lut_off + 256
+        rows = np.stack([np.frombuffer(img[r * stride:r * stride + 2 * nc].tobytes(), dtype=np.uint16) for r in range(hot + 1)])
+        assert (rows[hot] == hot).all()                              # absorbing trap row
+        nxt, acc = tab[:hot] & 0x3fff, (tab[:hot] & 0x8000) != 0
+        trapped = acc | (nxt >= hot)
+        assert (rows[:hot][trapped] == hot).all() and (rows[:hot][~trapped] == nxt[~trapped]).all()
+        return hot
+
+    hot = check_image()
+    before = [(h.candidates2(m), h.policy_hits(m)) for m in msgs]
+    hist, _ = h.l1_hist(buf, 400, 256)
+    cold_before = int(hist[hot:].sum())
+    h.rank(np.minimum(hist, 0xffffffff))
+    assert check_image() == hot
+    after = [(h.candidates2(m), h.policy_hits(m)) for m in msgs]
+    assert before == after
+    hist2, _ = h.l1_hist(buf, 400, 256)
+    assert int(hist2.sum()) == int(hist.sum()) and hist2[0] == hist[0]      # the start state stays state 0
+    cold_after = int(hist2[hot:].sum())
+    assert cold_after <= cold_before and (cold_before == 0 or cold_after < cold_before)
+    assert (np.diff(hist2[1:].astype(np.int64)) <= 0).all()                  # most visited first
+    h.close()
+
+
 def test_abi_exports_every_declared_symbol():
     """every CG_API symbol of include/openclaw_gov.h is exported by the built library (no compute calls)."""
     from vainplex_openclaw_b200 import _native as N

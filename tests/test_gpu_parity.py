@@ -89,6 +89,37 @@ def test_policy_scan_equals_oracle(N, oracle, n_rules, mode):
     rs.close()
 
 
+def test_residency_adaptation_never_changes_results(N, oracle):
+    """Profile-guided residency (cg_ruleset_adapt / first scan) only renumbers level-1 states: words and hits of batches
+    with different vocabularies stay equal to the oracle before and after re-profiling on either batch."""
+    import torch
+    rl = W.make_rules(1200)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    info = rs.info()
+    assert info.prefilter_states > info.prefilter_hot_states          # otherwise there is nothing to adapt
+    batches = []
+    for seed in (31, 32):
+        data_t, off_t, _ = W.make_messages(3000, 256, rl, p_hit=0.05, seed=seed)
+        data, off = data_t.numpy(), off_t.numpy().astype(np.uint32)
+        batches.append((data, off, oracle_policy(oracle, rules, data, off)))
+
+    def check_all():
+        for data, off, (ewords, ehits) in batches:
+            words, hits = rs.scan_batch(data, off)
+            assert np.array_equal(words, ewords)
+            assert [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits
+
+    check_all()                                   # the first scan adapted to batch 0
+    for data, off, _ in reversed(batches):        # re-profile on batch 1, then on batch 0 again
+        d = torch.from_numpy(np.concatenate([data, np.zeros(64, np.uint8)])).cuda()
+        o = torch.from_numpy(off.astype(np.int32)).cuda()
+        rs.adapt(d.data_ptr(), o.data_ptr(), len(off) - 1)
+        torch.cuda.synchronize()
+        check_all()
+    rs.close()
+
+
 @pytest.mark.parametrize("utf8_frac,length", [(0.2, 190), (0.0, 64), (0.1, 1024)])
 def test_redaction_spans_equal_oracle(N, oracle, utf8_frac, length):
     rl = W.make_rules(120)

@@ -48,7 +48,7 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
                        ("start16", np.uint32), ("end16", np.uint32)])
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
-           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters",
+           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -82,6 +82,7 @@ def load():
     L.cg_set_profiling.argtypes = [i32]; L.cg_set_profiling.restype = i32
     L.cg_last_kernel_ms.argtypes = [vp]; L.cg_last_kernel_ms.restype = i32
     L.cg_scan_work_counters.argtypes = [vp, vp]; L.cg_scan_work_counters.restype = i32
+    L.cg_ruleset_adapt.argtypes = [vp, vp, vp, u32, vp]; L.cg_ruleset_adapt.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
     L.cg_ruleset_destroy.argtypes = [vp]; L.cg_ruleset_destroy.restype = None
     L.cg_ruleset_get_info.argtypes = [vp, C.POINTER(cg_ruleset_info)]; L.cg_ruleset_get_info.restype = i32
@@ -201,10 +202,14 @@ class Ruleset:
             return spans[:ns.value]
 
     def work_counters(self):
-        """(slots, VM pairs, spans, error flags, level-1 events, slow-path chunks, slow-path warp entries, 0) of the last completed step."""
+        """(slots, VM pairs, spans, error flags, level-1 events, 0, slow-path warp entries, 0) of the last completed step."""
         out = np.zeros(8, dtype=np.uint32)
         check(load().cg_scan_work_counters(self.handle, out.ctypes.data))
         return tuple(int(x) for x in out)
+
+    def adapt(self, d_bytes: int, d_off: int, n: int, stream: int = 0):
+        """Re-profile which level-1 rows are shared-memory resident on a sample of this (device-resident) batch."""
+        check(load().cg_ruleset_adapt(self.handle, d_bytes, d_off, n, stream))
 
     def scan_batch_device(self, d_bytes: int, d_off: int, n: int, d_words: int, stream: int = 0):
         check(load().cg_scan_batch_device(self.handle, d_bytes, d_off, n, d_words, stream))

@@ -71,6 +71,8 @@ struct cg_ruleset {
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
   cudaGraphExec_t graph = nullptr;
   const void* g_bytes = nullptr; const void* g_off = nullptr; void* g_words = nullptr; uint32_t g_n = 0; uint32_t g_caps[4] = {0, 0, 0, 0};
+  bool adapted = false;           // profile-guided residency has run (first scan, or cg_ruleset_adapt)
+  uint8_t* d_image_rw = nullptr; uint16_t* d_table_rw = nullptr; uint32_t* d_acc_index_rw = nullptr;   // writable aliases of dev.image / table_full / acc_index
   ~cg_ruleset() {
     if (graph) cudaGraphExecDestroy(graph);
     for (void* p : allocs) cudaFree(p);
@@ -116,6 +118,34 @@ int ensure_work(cg_ruleset* rs, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_
 }
 
 // scan + confirm + verify + finalize on device-resident input; asynchronous
+// Profile-guided residency: sample the batch, count level-1 state visits, renumber the states so the
+// most visited ones are the shared-memory resident ones, and overwrite the device tables in place (same sizes, same
+// pointers: a captured graph stays valid).  Results never depend on this, only how often the scan's slow path runs.
+int adapt_ruleset(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, cudaStream_t st) {
+  rs->adapted = true;
+  HostImage& H = rs->host;
+  if (H.pf.mode == 4 || !n || (uint32_t)H.pf.nstates <= H.hot_states) return CG_OK;      // everything is resident already
+  if (getenv("CG_NO_ADAPT") && atoi(getenv("CG_NO_ADAPT"))) return CG_OK;
+  const uint32_t ns = (uint32_t)H.pf.nstates, n_sample = std::min<uint32_t>(n, 8192);
+  uint32_t* d_visits = nullptr;
+  CU(cudaMalloc((void**)&d_visits, (size_t)ns * 4));
+  cudaError_t e = cudaMemsetAsync(d_visits, 0, (size_t)ns * 4, st);
+  if (e == cudaSuccess) { launch_l1_profile(rs->dev, d_bytes, d_off, n, n_sample, d_visits, st); G.launches++; G.stats.kernel_launches++; }
+  std::vector<uint32_t> visits(ns);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(visits.data(), d_visits, (size_t)ns * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_visits);
+  if (e != cudaSuccess) return cuda_fail(e, "level-1 profile");
+  const size_t image_bytes = H.image.size();
+  rank_states_by_visits(&H, visits.data());
+  if (H.image.size() != image_bytes) return fail(CG_ERR_CUDA, "internal: image size changed on re-ranking");
+  CU(cudaMemcpyAsync(rs->d_image_rw, H.image.data(), H.image.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rs->d_table_rw, H.pf.table.data(), H.pf.table.size() * 2, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rs->d_acc_index_rw, H.pf.acc_index.data(), H.pf.acc_index.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return CG_OK;
+}
+
 int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words,
                     bool spans, cudaStream_t st) {
   CU(cudaMemsetAsync(rs->work.counters, 0, 16 * sizeof(uint32_t), st));
@@ -161,6 +191,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
   // keep whatever an earlier step of this rule set needed
   slot_cap = std::max(slot_cap, rs->work.slot_cap); event_cap = std::max(event_cap, rs->work.event_cap); l1_cap = std::max(l1_cap, rs->work.l1_cap);
   hs->counters.assign(16, 0);
+  if (n && !rs->adapted && (rc = adapt_ruleset(rs, G.d_bytes, G.d_off32, n, st))) return rc;
   for (int attempt = 0; attempt < 10; attempt++) {
     if ((rc = ensure_work(rs, std::max<uint32_t>(n, 1), l1_cap, slot_cap, event_cap, span_cap))) return rc;
     CU(cudaEventRecord(G.ev0, st));
@@ -234,8 +265,8 @@ int cg_last_kernel_ms(float out_ms[4]) {
 
 int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out8[8]) {
   // [0] slots (messages with confirmed candidates), [1] (message, rule) pairs sent to the VM, [2] spans,
-  // [3] error flags, [4] level-1 accept events, [5] 16-byte chunks re-walked by the scan kernel's slow path,
-  // [6] warp-level entries into that slow path, [7] reserved -- of the last completed step
+  // [3] error flags, [4] level-1 accept events, [5] reserved, [6] warp-level entries into the scan kernel's slow path
+  // (4-byte words some lane had to re-walk on the full table), [7] reserved -- of the last completed step
   if (!rs || !out8 || !rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
   CU(cudaMemcpy(out8, rs->work.counters, 32, cudaMemcpyDeviceToHost));
   return CG_OK;
@@ -285,13 +316,14 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   DevRuleset& d = rs->dev;
   int rc;
   const uint8_t* d_image; if ((rc = upload(rs.get(), image, &d_image, 16))) return rc;
-  d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode;
+  d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode; rs->d_image_rw = const_cast<uint8_t*>(d_image);
   d.ncols_log2 = 0; while ((1 << d.ncols_log2) < P.ncols) d.ncols_log2++;
   d.nstates = (uint32_t)P.nstates; d.hot_states = H.hot_states; d.lut_off = H.lut_off; d.row_stride = H.row_stride;
   d.scan_streams = 1; if (const char* e = getenv("CG_SCAN_STREAMS")) d.scan_streams = (uint32_t)atoi(e);
   d.debug_flags = 0; if (const char* e = getenv("CG_SCAN_DEBUG")) d.debug_flags = (uint32_t)atoi(e);   // 1: skip the slow path (timing experiments only, results wrong)
   if ((rc = upload(rs.get(), P.table, &d.table_full, 64))) return rc;
   if ((rc = upload(rs.get(), P.acc_index, &d.acc_index))) return rc;
+  rs->d_table_rw = const_cast<uint16_t*>(d.table_full); rs->d_acc_index_rw = const_cast<uint32_t*>(d.acc_index);
   if ((rc = upload(rs.get(), P.acc_offsets, &d.acc_offsets))) return rc;
   if ((rc = upload(rs.get(), P.acc_factors, &d.acc_factors))) return rc;
   if ((rc = upload(rs.get(), H.factor_words, &d.factors, 16))) return rc;
@@ -419,6 +451,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   if (rc) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
   if (!n) return CG_OK;
+  if (!rs->adapted && (rc = adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st))) return rc;
   static const bool use_graph = !(getenv("CG_NO_GRAPH") && atoi(getenv("CG_NO_GRAPH")));
   if (!use_graph || G.profiling) {
     rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
@@ -444,6 +477,15 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   }
   if (rc == CG_OK) { G.stats.messages_scanned += n; }
   return rc;
+}
+
+int cg_ruleset_adapt(cg_ruleset* rs, const void* d_bytes, const void* d_offsets, uint32_t n, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!rs || !d_bytes || !d_offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
+  cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+  CU(cudaStreamSynchronize(st));                         // nothing may still be reading the tables
+  return adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st);
 }
 
 // ---------------------------------------------------------------------------------- SHA / Merkle

@@ -62,6 +62,9 @@ enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 
 // launchers (all asynchronous on `stream`); return the number of kernels launched
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, bool want_spans, int sm_count, cudaStream_t stream);
+// state visit histogram over n_sample evenly spaced messages (profile-guided residency)
+int launch_l1_profile(const DevRuleset& rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint32_t n_sample,
+                      uint32_t* d_visits, cudaStream_t stream);
 int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                    bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,

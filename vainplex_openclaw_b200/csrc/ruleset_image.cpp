@@ -6,6 +6,58 @@
 
 namespace cg {
 
+// (Re)builds the shared-memory image of a DFA-mode rule set from H.pf.table: see the layout comment below.
+void build_dfa_image(HostImage* out) {
+  // shared-memory image: [rows 0..hot of the table, `row_stride` bytes apart][pad to 16][lut 256 B].
+  // Entries are plain u16 state indices.  Every transition that is accepting, or leads to a state that is
+  // not resident (>= hot), is stored as `hot`, the index of an absorbing trap row: the fast path of
+  // scan_kernel then needs no flag bits -- a chunk that ends in the trap row is re-walked on the full table.
+  // row_stride = 2 * ncols + 4: the 4 pad bytes rotate consecutive rows by one bank, so lanes sitting in
+  // different states but reading the same frequent column (' ', 'e', ...) land in different banks.
+  HostImage& H = *out; size_t budget = H.budget_bytes; const uint32_t cols = H.image_cols; size_t hot_rows;
+  H.row_stride = cols * 2 + 4;
+  budget = std::min<size_t>(budget, (size_t)155 * 1024);            // + 64 KB staging + 6 KB event buffers + static shared memory <= 227 KB per CTA
+  hot_rows = std::min<size_t>((budget - 256 - 16) / H.row_stride, 16383);
+  H.hot_states = (uint32_t)std::min<size_t>(hot_rows > 1 ? hot_rows - 1 : 1, (size_t)H.pf.nstates);
+  const uint32_t hot = H.hot_states; const size_t nc = (size_t)H.pf.ncols;
+  size_t tbl_bytes = ((size_t)(hot + 1) * H.row_stride + 15) & ~(size_t)15;
+  H.lut_off = (uint32_t)tbl_bytes;
+  H.image.assign(tbl_bytes + 256, 0);
+  auto put = [&](uint32_t row, size_t col, uint16_t v) { memcpy(H.image.data() + (size_t)row * H.row_stride + 2 * col, &v, 2); };
+  for (uint32_t s = 0; s < hot; s++) for (size_t c = 0; c < nc; c++) {
+    uint16_t e = H.pf.table[(size_t)s * nc + c];
+    put(s, c, ((e & 0x8000) || (uint32_t)(e & 0x3fff) >= hot) ? (uint16_t)hot : (uint16_t)(e & 0x3fff));
+  }
+  for (size_t c = 0; c < (size_t)cols; c++) put(hot, c, (uint16_t)hot);
+  memcpy(H.image.data() + H.lut_off, H.pf.lut, 256);
+}
+
+// Profile-guided residency: renumber the level-1 states so that the most visited ones get the lowest indices
+// (= the rows that are resident in shared memory), keeping the start state at index 0.  `visits[s]` is how often
+// state s was left on a sample of real traffic.  Everything indexed by state (table, acc_index) is permuted and
+// the image rebuilt; the matcher's results do not depend on the numbering, only how often its slow path runs.
+void rank_states_by_visits(HostImage* out, const uint32_t* visits) {
+  HostImage& H = *out; Prefilter& P = H.pf;
+  if (P.mode == 4 || P.nstates <= 1) return;
+  const uint32_t ns = (uint32_t)P.nstates; const size_t nc = (size_t)P.ncols;
+  std::vector<uint32_t> order(ns);
+  for (uint32_t i = 0; i < ns; i++) order[i] = i;
+  std::stable_sort(order.begin() + 1, order.end(), [&](uint32_t a, uint32_t b) { return visits[a] > visits[b]; });
+  std::vector<uint32_t> new_of_old(ns);
+  for (uint32_t i = 0; i < ns; i++) new_of_old[order[i]] = i;
+  std::vector<uint16_t> table(P.table.size()); std::vector<uint32_t> acc(P.acc_index.size(), 0xffffffffu);
+  for (uint32_t i = 0; i < ns; i++) {
+    const uint32_t o = order[i];
+    for (size_t c = 0; c < nc; c++) {
+      const uint16_t e = P.table[(size_t)o * nc + c];
+      table[(size_t)i * nc + c] = (uint16_t)((e & 0xc000) | new_of_old[e & 0x3fff]);
+      acc[(size_t)i * nc + c] = P.acc_index[(size_t)o * nc + c];
+    }
+  }
+  P.table.swap(table); P.acc_index.swap(acc);
+  build_dfa_image(out);
+}
+
 bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, HostImage* out, std::string* err) {
   HostImage& H = *out;
   H = HostImage();
@@ -60,27 +112,8 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     while (H.image.size() % 16) H.image.push_back(0);
     return true;
   }
-  // shared-memory image: [rows 0..hot of the table, `row_stride` bytes apart][pad to 16][lut 256 B].
-  // Entries are plain u16 state indices.  Every transition that is accepting, or leads to a state that is
-  // not resident (>= hot), is stored as `hot`, the index of an absorbing trap row: the fast path of
-  // scan_kernel then needs no flag bits -- a chunk that ends in the trap row is re-walked on the full table.
-  // row_stride = 2 * ncols + 4: the 4 pad bytes rotate consecutive rows by one bank, so lanes sitting in
-  // different states but reading the same frequent column (' ', 'e', ...) land in different banks.
-  H.row_stride = (uint32_t)cols * 2 + 4;
-  budget = std::min<size_t>(budget, 155 * 1024);            // + 64 KB staging + 6 KB event buffers + static shared memory <= 227 KB per CTA
-  hot_rows = std::min<size_t>((budget - 256 - 16) / H.row_stride, 16383);
-  H.hot_states = (uint32_t)std::min<size_t>(hot_rows > 1 ? hot_rows - 1 : 1, (size_t)H.pf.nstates);
-  const uint32_t hot = H.hot_states; const size_t nc = (size_t)H.pf.ncols;
-  size_t tbl_bytes = ((size_t)(hot + 1) * H.row_stride + 15) & ~(size_t)15;
-  H.lut_off = (uint32_t)tbl_bytes;
-  H.image.assign(tbl_bytes + 256, 0);
-  auto put = [&](uint32_t row, size_t col, uint16_t v) { memcpy(H.image.data() + (size_t)row * H.row_stride + 2 * col, &v, 2); };
-  for (uint32_t s = 0; s < hot; s++) for (size_t c = 0; c < nc; c++) {
-    uint16_t e = H.pf.table[(size_t)s * nc + c];
-    put(s, c, ((e & 0x8000) || (uint32_t)(e & 0x3fff) >= hot) ? (uint16_t)hot : (uint16_t)(e & 0x3fff));
-  }
-  for (size_t c = 0; c < (size_t)cols; c++) put(hot, c, (uint16_t)hot);
-  memcpy(H.image.data() + H.lut_off, H.pf.lut, 256);
+  H.budget_bytes = budget; H.image_cols = (uint32_t)cols;
+  build_dfa_image(&H);
   return true;
 }
 

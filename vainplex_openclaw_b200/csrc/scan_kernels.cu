@@ -140,6 +140,7 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
   // flush instead of one per flagged word.
   uint32_t* evb = reinterpret_cast<uint32_t*>(smem + ((rs.image_bytes + 127u) & ~127u) + kScanStageBytes) + warp * (3u * kEvBuf);
   uint32_t evn = 0;                                            // warp-uniform fill level
+  uint32_t slow_entries = 0;                                   // (same-address atomics from every slow-path entry would serialise in L2)
   auto flush_events = [&]() {
     if (evn == 0) return;
     __syncwarp();
@@ -172,15 +173,18 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
     for (int d = 16; d; d >>= 1) maxch = max(maxch, __shfl_xor_sync(FULL, maxch, d));
     const uint32_t ngroups = (maxch + 3u) >> 2;
 
-    // loader role: this lane fetches unit ld_unit of messages (lane / 4) + 8 j, j = 0..3
-    uint32_t lp[4], ln[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) { lp[j] = __shfl_sync(FULL, p, (lane >> 2) + 8 * j); ln[j] = __shfl_sync(FULL, nch, (lane >> 2) + 8 * j); }
+    // loader role: this lane fetches unit ld_unit of messages (lane / 4) + 8 j, j = 0..3 (their chunk base and
+    // count come by shuffle each time: eight registers less than keeping them)
+    const uint32_t p0 = p;
     uint4 r[4];
     auto load_group = [&](uint32_t g) {
       const uint32_t cidx = 4u * g + ld_unit;
 #pragma unroll
-      for (int j = 0; j < 4; j++) { r[j] = make_uint4(0, 0, 0, 0); if (cidx < ln[j]) r[j] = ldg_stream(bytes + lp[j] + 16u * cidx); }
+      for (int j = 0; j < 4; j++) {
+        const uint32_t lp = __shfl_sync(FULL, p0, (lane >> 2) + 8 * j), ln = __shfl_sync(FULL, nch, (lane >> 2) + 8 * j);
+        r[j] = make_uint4(0, 0, 0, 0);
+        if (cidx < ln) r[j] = ldg_stream(bytes + lp + 16u * cidx);
+      }
     };
     auto store_group = [&]() {
 #pragma unroll
@@ -205,7 +209,7 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
           // Flagged lanes re-walk the four bytes from the word's start state: resident transitions from shared
           // memory, trapped ones from the full table in L2 (accept flag + true successor).
           if (rs.debug_flags & 1u) continue;
-          if (lane == 0) { atomicAdd(&w.counters[5], (uint32_t)__popc(fl)); atomicAdd(&w.counters[6], 1u); }
+          slow_entries++;                                    // folded into counters[6] once per warp
           uint32_t cnt = 0, ev_pos[4], ev_sc[4];
           if (flagged) {
             uint32_t st = state;
@@ -266,6 +270,7 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
     if (valid) words[msg] = 0ull;
   }
   flush_events();
+  if (lane == 0 && slow_entries) atomicAdd(&w.counters[6], slow_entries);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -378,6 +383,24 @@ scan_fp_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, con
     }
     bytewise(e);
     if (valid) words[msg] = 0ull;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// profile-guided residency: how often is each level-1 state visited on a sample of the traffic?
+// One thread per sampled message walks the full table (L2) and counts; run once per rule set (and on request),
+// the host then renumbers the states so the most visited ones are the shared-memory resident ones.
+// ------------------------------------------------------------------------------------------
+__global__ void l1_profile_kernel(DevRuleset rs, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
+                                  uint32_t n_sample, uint32_t* __restrict__ visits) {
+  const uint8_t* lut = rs.image + rs.lut_off;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_sample; i += gridDim.x * blockDim.x) {
+    const uint32_t msg = (uint32_t)(((uint64_t)i * n) / n_sample);
+    uint32_t state = 0;
+    for (uint32_t p = off[msg], e = off[msg + 1]; p < e; p++) {
+      atomicAdd(&visits[state], 1u);
+      state = l1_full(rs, state, l1_col(rs.mode, lut, bytes[p])) & kStateMask;
+    }
   }
 }
 
@@ -585,6 +608,13 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
 #define CG_LAUNCH_SCAN(M) scan_kernel<M><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words)
   switch (rs.mode) { case 0: CG_LAUNCH_SCAN(0); break; case 2: CG_LAUNCH_SCAN(2); break; case 3: CG_LAUNCH_SCAN(3); break; default: CG_LAUNCH_SCAN(1); break; }
 #undef CG_LAUNCH_SCAN
+  return 1;
+}
+
+int launch_l1_profile(const DevRuleset& rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint32_t n_sample,
+                      uint32_t* d_visits, cudaStream_t stream) {
+  if (!n || !n_sample) return 0;
+  l1_profile_kernel<<<(n_sample + 127) / 128, 128, 0, stream>>>(rs, d_bytes, d_off, n, n_sample, d_visits);
   return 1;
 }
 

@@ -148,7 +148,7 @@ def _vocab(rng, n_words: int, utf8_frac: float):
 
 
 def make_messages(n: int, length: int, n_rules_for_hits=None, p_hit: float = 0.01, utf8_frac: float = 0.0,
-                  seed: int = SEED_MSG, device="cpu", chunk_msgs: int = 1 << 16):
+                  seed: int = SEED_MSG, device="cpu", chunk_msgs: int = 1 << 16, vocab_seed=None):
     """Fixed-length batch.  Returns (bytes uint8 tensor [n*length + 64], offsets uint32-valued int64
     tensor [n+1] as torch tensors on `device`, injected list of (msg, rule_index) on the host).
 
@@ -157,7 +157,8 @@ def make_messages(n: int, length: int, n_rules_for_hits=None, p_hit: float = 0.0
     and the device decoder treat that as U+FFFD, exactly like Buffer.toString() would."""
     import torch
     rng = np.random.default_rng(seed)
-    words = _vocab(rng, 4096, utf8_frac)
+    # the vocabulary is the "language" of the traffic: shards of one workload (ranks) share it and draw different messages
+    words = _vocab(rng if vocab_seed is None else np.random.default_rng(vocab_seed), 4096, utf8_frac)
     # zipf-ish word frequencies
     wprob = 1.0 / np.arange(1, len(words) + 1) ** 0.9
     wprob /= wprob.sum()
