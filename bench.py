@@ -154,16 +154,23 @@ def main():
     data, off64, inj = W.make_messages(n, L, rl, p_hit=P_HIT, seed=W.SEED_MSG + rank + args.seed_offset, device=dev,
                                         vocab_seed=W.SEED_MSG + args.seed_offset)
     off = off64.to(torch.int32)              # uint32 offsets (bit pattern) as the C ABI expects; n*L < 2^31 here
-    words = torch.zeros(n, dtype=torch.int64, device=dev)
+    # two result buffers: the library keeps two batches in flight (batch k's verify overlaps batch k+1's scan), so a
+    # buffer may only be reused two calls later
+    words2 = [torch.zeros(n, dtype=torch.int64, device=dev) for _ in range(2)]
+    words = words2[0]
     stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: handle 0 would mean "library stream" to the C ABI
     torch.cuda.synchronize()
     torch.cuda.set_stream(stream)
 
+    step_no = [0]
+
     def step():
-        rs.scan_batch_device(data.data_ptr(), off.data_ptr(), n, words.data_ptr(), stream.cuda_stream)
+        rs.scan_batch_device(data.data_ptr(), off.data_ptr(), n, words2[step_no[0] & 1].data_ptr(), stream.cuda_stream)
+        step_no[0] += 1
 
     for _ in range(args.warmup):
         step()
+    rs.scan_join(stream.cuda_stream)
     torch.cuda.synchronize()
     # kernel breakdown (profiling events inside the library, one sync per step; not the headline timing)
     N.set_profiling(True)
@@ -173,6 +180,8 @@ def main():
     N.set_profiling(False)
     kms = np.array(kms)
     counters = rs.work_counters()
+    words = words2[(step_no[0] - 1) & 1]             # results of the last (sequential, profiled) step: checked against the e2e path below
+    words_seq = words.clone()
 
     # ---- headline: K steps, device-resident inputs (256 MiB per step > 126 MB L2), barrier + sync both sides
     if world > 1:
@@ -184,9 +193,11 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    rs.scan_join(stream.cuda_stream)                 # the stream waits for the tails of the last two batches
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    pipelined_equal = bool(torch.equal(words2[0], words_seq) and torch.equal(words2[1], words_seq))
     launches = N.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     per_rank_ms = [ms / args.steps]
@@ -311,12 +322,15 @@ def main():
                    "prefilter": {"mode": int(info.prefilter_mode), "states": int(info.prefilter_states), "cols": int(info.prefilter_cols),
                                  "window_min": int(info.prefilter_factor_len) & 0xff, "window_max": int(info.prefilter_factor_len) >> 8, "factors": int(info.n_factors), "smem_bytes": int(info.prefilter_bytes),
                                  "always_candidate_rules": int(info.n_always_candidate)},
+                   "pipeline": ("CG_PIPELINE=1: two batches in flight" if os.environ.get("CG_PIPELINE") == "1" else "off: in-order step replayed as one CUDA graph") +
+                               "; results of the timed steps equal the profiled step: %s" % pipelined_equal,
                    "compile_s": compile_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "kernel": "scan_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms},
+        "kernel_ms_note": "kernel_ms: CUDA events inside the library around each kernel of one step (profiling mode, no graph); ms_per_step: the graph-replayed steady state",
         "kernel_ms": {"scan": scan_ms, "confirm": float(np.median(kms[:, 1])), "verify": float(np.median(kms[:, 2])), "finalize": float(np.median(kms[:, 3]))},
-        "candidates": {"level1_events": counters[4], "slow_warp_entries": counters[6], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
+        "candidates": {"level1_events": counters[4], **({"vm_cycle_hist_2^11..": list(counters[8:16]), "vm_cycle_max": counters[7]} if os.environ.get("CG_SCAN_DEBUG") == "2" else {}), "slow_warp_entries": counters[6], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
                        "hit_messages": int((words != 0).sum().item()), "injected": len(inj)},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "msgs/s", "h2d_bytes_per_step": int(n * L + 4 * (n + 1)), "d2h_bytes_per_step": int(8 * n + 64),

@@ -100,7 +100,7 @@ CG_API uint64_t cg_launch_count(void);   /* kernels launched by this library so 
  * with profiling on, CUDA events bracket each kernel of a scan step on its stream. */
 CG_API int cg_set_profiling(int on);
 CG_API int cg_last_kernel_ms(float out_ms[4]);          /* scan, confirm, verify, finalize of the last completed step */
-CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out8[8]); /* slots, VM pairs, spans, flags, level-1 events, reserved, slow-path warp entries, reserved */
+CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out16[16]); /* slots, VM pairs, spans, flags, level-1 events, (internal), slow-path warp entries, reserved */
 
 /* ---- rule-set compile.  Replaces `new RegExp(pattern)` in buildPolicyIndex
  * (src/policy-loader.ts:119-128), compileCustomPattern (src/redaction/registry.ts:249-281) and
@@ -141,6 +141,16 @@ CG_API int cg_find_matches_batch(cg_ruleset *rs, const uint8_t *bytes, const uin
  * d_bytes must be readable for 16 bytes past offsets[n] (padding). */
 CG_API int cg_scan_batch_device(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n,
                                 void *d_out_words, void *stream);
+
+/* With CG_PIPELINE=1 in the environment cg_scan_batch_device keeps up to two batches in flight: batch k's confirm /
+ * verify / finalize run on a stream of the library's own while `stream` already scans batch k+1.  Then
+ *   - the results of a batch are complete on `stream` only after the NEXT BUT ONE call on the same rule set, or after
+ *     cg_scan_join(rs, stream) (which makes `stream` wait for everything still in flight; it does not block the host);
+ *   - d_out_words and the input buffers of a batch must not be reused for writing before that point (alternate two
+ *     output buffers, as bench.py does).
+ * By default (no pipelining) every call is strictly in order on `stream` and cg_scan_join is a no-op; callers that
+ * always join before reading results work in both modes. */
+CG_API int cg_scan_join(cg_ruleset *rs, void *stream);
 
 /* Profile-guided residency.  The level-1 automaton usually has more states than fit into shared memory; which
  * rows are resident is decided from a state-visit histogram over a sample of real messages.  The first scan of a

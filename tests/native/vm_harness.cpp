@@ -239,3 +239,37 @@ extern "C" const uint8_t* harness_image(void* p, uint32_t* out4) {
   return h->d.image;
 }
 extern "C" const uint16_t* harness_table(void* p) { return ((Harness*)p)->H.pf.table.data(); }
+
+// VM work statistics per rule over a batch (built with -DCG_VM_STATS only): for every confirmed occurrence that reaches
+// the VM, accumulate the counters of pike_vm.h into out[rule * 8 + i], i = 0..4; out[rule * 8 + 5] = events, [6] = island start distance
+#ifdef CG_VM_STATS
+extern "C" unsigned long long cg_vm_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+extern "C" void harness_vm_stats(void* p, const uint8_t* data, uint64_t n_msgs, uint32_t msg_len, unsigned long long* out) {
+  Harness* h = (Harness*)p; const DevRuleset& d = h->d;
+  const uint8_t* lut = d.image + d.lut_off; const uint16_t* table = h->H.pf.table.data();
+  VM vm(d);
+  for (uint64_t mi = 0; mi < n_msgs; mi++) {
+    const uint8_t* m = data + mi * msg_len; uint32_t len = msg_len;
+    std::vector<uint32_t> cand(d.rw, 0), hits(d.rw, 0), occ;
+    BitSink sink{cand.data(), hits.data(), &occ};
+    uint32_t state = 0;
+    for (uint32_t i = 0; i < len; i++) {
+      uint32_t col = l1_col(d.mode, lut, m[i]);
+      uint32_t ent = table[(state << d.ncols_log2) + col];
+      if (ent & 0x8000u) l1_accept(d, state, col, m, len, i, false, sink);
+      state = ent & 0x3fffu;
+    }
+    for (size_t k = 0; k + 2 < occ.size(); k += 3) {
+      uint32_t r = occ[k], t0 = occ[k + 1], pre = occ[k + 2];
+      if ((hits[r >> 5] >> (r & 31)) & 1u) continue;
+      if (t0 == 0xffffffffu) continue;
+      for (int i = 0; i < 8; i++) cg_vm_stats[i] = 0;
+      bool any = test_at_factor(vm, d, r, m, len, t0, pre);
+      if (any) hits[r >> 5] |= 1u << (r & 31);
+      for (int i = 0; i < 5; i++) out[(size_t)r * 8 + i] += cg_vm_stats[i];
+      out[(size_t)r * 8 + 5]++;
+      out[(size_t)r * 8 + 6] += (pre & 0xffffu);
+    }
+  }
+}
+#endif

@@ -89,6 +89,46 @@ def test_policy_scan_equals_oracle(N, oracle, n_rules, mode):
     rs.close()
 
 
+@pytest.mark.parametrize("pipeline", ["0", "1"])
+def test_device_scan_equals_host_path(N, oracle, pipeline, monkeypatch):
+    """cg_scan_batch_device (in order, or with CG_PIPELINE=1 two batches in flight: tail of batch k beside the scan of
+    batch k+1): a run of different batches into separate output buffers equals the host path, batch by batch."""
+    import subprocess, sys
+    if pipeline == "1" and os.environ.get("CG_PIPELINE") != "1":
+        # the library reads CG_PIPELINE once per process: run this very test in a child with the variable set
+        env = dict(os.environ, CG_PIPELINE="1")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__ + "::test_device_scan_equals_host_path[1]"],
+                           env=env, capture_output=True, text=True, cwd=os.path.dirname(HERE))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    import torch
+    rl = W.make_rules(500)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    n = 20000
+    batches = []
+    for seed in range(5):
+        data_t, off_t, _ = W.make_messages(n, 256, rl, p_hit=0.03, seed=900 + seed)
+        batches.append((data_t.numpy(), off_t.numpy().astype(np.uint32)))
+    expect = [rs.scan_batch(d, o, want_hits=False)[0] for d, o in batches]
+    ewords, _ = oracle_policy(oracle, rules, batches[0][0][:2000 * 256 + 64], batches[0][1][:2001])
+    assert np.array_equal(expect[0][:2000], ewords)
+    stream = torch.cuda.Stream()
+    dev = [(torch.from_numpy(d).cuda(), torch.from_numpy(o.astype(np.int32)).cuda()) for d, o in batches]
+    outs = [torch.full((n,), -1, dtype=torch.int64, device="cuda") for _ in batches]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for (d, o), out in zip(dev, outs):
+            rs.scan_batch_device(d.data_ptr(), o.data_ptr(), n, out.data_ptr(), stream.cuda_stream)
+        rs.scan_join(stream.cuda_stream)
+        stream.synchronize()
+        for out, e in zip(outs, expect):
+            assert np.array_equal(out.cpu().numpy().view(np.uint64), e)
+            out.fill_(-1)
+        torch.cuda.synchronize()
+    rs.close()
+
+
 def test_residency_adaptation_never_changes_results(N, oracle):
     """Profile-guided residency (cg_ruleset_adapt / first scan) only renumbers level-1 states: words and hits of batches
     with different vocabularies stay equal to the oracle before and after re-profiling on either batch."""

@@ -48,7 +48,7 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
                        ("start16", np.uint32), ("end16", np.uint32)])
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
-           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt",
+           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt", "cg_scan_join",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -83,6 +83,7 @@ def load():
     L.cg_last_kernel_ms.argtypes = [vp]; L.cg_last_kernel_ms.restype = i32
     L.cg_scan_work_counters.argtypes = [vp, vp]; L.cg_scan_work_counters.restype = i32
     L.cg_ruleset_adapt.argtypes = [vp, vp, vp, u32, vp]; L.cg_ruleset_adapt.restype = i32
+    L.cg_scan_join.argtypes = [vp, vp]; L.cg_scan_join.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
     L.cg_ruleset_destroy.argtypes = [vp]; L.cg_ruleset_destroy.restype = None
     L.cg_ruleset_get_info.argtypes = [vp, C.POINTER(cg_ruleset_info)]; L.cg_ruleset_get_info.restype = i32
@@ -203,9 +204,13 @@ class Ruleset:
 
     def work_counters(self):
         """(slots, VM pairs, spans, error flags, level-1 events, 0, slow-path warp entries, 0) of the last completed step."""
-        out = np.zeros(8, dtype=np.uint32)
+        out = np.zeros(16, dtype=np.uint32)
         check(load().cg_scan_work_counters(self.handle, out.ctypes.data))
         return tuple(int(x) for x in out)
+
+    def scan_join(self, stream: int = 0):
+        """Make `stream` wait for every batch scan_batch_device still has in flight (does not block the host)."""
+        check(load().cg_scan_join(self.handle, stream))
 
     def adapt(self, d_bytes: int, d_off: int, n: int, stream: int = 0):
         """Re-profile which level-1 rows are shared-memory resident on a sample of this (device-resident) batch."""

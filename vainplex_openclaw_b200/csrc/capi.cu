@@ -67,7 +67,12 @@ struct cg_ruleset {
   DevRuleset dev{};
   std::vector<void*> allocs;
   uint32_t n_sets = 0, program_words = 0;
-  ScanWork work{};
+  ScanWork work{};                // scratch of the (sequential) host path and of even pipelined steps
+  ScanWork work2{};               // scratch of odd pipelined steps (cg_scan_batch_device keeps two batches in flight)
+  uint64_t seq = 0;               // pipelined steps issued so far
+  cudaStream_t side = nullptr;    // confirm / verify / finalize of batch k run here while the caller's stream scans batch k+1
+  cudaEvent_t e_scan[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr};
+  bool inflight[2] = {false, false};
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
   cudaGraphExec_t graph = nullptr;
   const void* g_bytes = nullptr; const void* g_off = nullptr; void* g_words = nullptr; uint32_t g_n = 0; uint32_t g_caps[4] = {0, 0, 0, 0};
@@ -75,6 +80,9 @@ struct cg_ruleset {
   uint8_t* d_image_rw = nullptr; uint16_t* d_table_rw = nullptr; uint32_t* d_acc_index_rw = nullptr;   // writable aliases of dev.image / table_full / acc_index
   ~cg_ruleset() {
     if (graph) cudaGraphExecDestroy(graph);
+    if (side) cudaStreamDestroy(side);
+    for (int i = 0; i < 2; i++) { if (e_scan[i]) cudaEventDestroy(e_scan[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); }
+    for (ScanWork* w2 : {&work2}) { cudaFree(w2->l1_msg); cudaFree(w2->l1_pos); cudaFree(w2->l1_sc); cudaFree(w2->slot_of_msg); cudaFree(w2->counters); cudaFree(w2->slot_msg); cudaFree(w2->cand); cudaFree(w2->hit); cudaFree(w2->events); cudaFree(w2->event_pos); cudaFree(w2->event_pre); cudaFree(w2->spans); }
     for (void* p : allocs) cudaFree(p);
     cudaFree(work.l1_msg); cudaFree(work.l1_pos); cudaFree(work.l1_sc); cudaFree(work.slot_of_msg);
     cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
@@ -95,8 +103,7 @@ int upload(cg_ruleset* rs, const std::vector<T>& v, const T** out, size_t pad_el
   return CG_OK;
 }
 
-int ensure_work(cg_ruleset* rs, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_cap, uint32_t event_cap, uint32_t span_cap) {
-  ScanWork& w = rs->work;
+int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_cap, uint32_t event_cap, uint32_t span_cap) {
   if (!w.counters) { CU(cudaMalloc((void**)&w.counters, 16 * sizeof(uint32_t))); }
   if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
   if (l1_cap > w.l1_cap) {
@@ -117,7 +124,6 @@ int ensure_work(cg_ruleset* rs, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_
   return CG_OK;
 }
 
-// scan + confirm + verify + finalize on device-resident input; asynchronous
 // Profile-guided residency: sample the batch, count level-1 state visits, renumber the states so the
 // most visited ones are the shared-memory resident ones, and overwrite the device tables in place (same sizes, same
 // pointers: a captured graph stays valid).  Results never depend on this, only how often the scan's slow path runs.
@@ -146,22 +152,39 @@ int adapt_ruleset(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off,
   return CG_OK;
 }
 
-int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words,
-                    bool spans, cudaStream_t st) {
-  CU(cudaMemsetAsync(rs->work.counters, 0, 16 * sizeof(uint32_t), st));
-  CU(cudaMemsetAsync(rs->work.slot_of_msg, 0xff, (size_t)n * 4, st));
-  int k = 0;
+// head: scratch reset + level-1 scan; tail: confirm + verify + finalize.  Both asynchronous.
+int scan_head(cg_ruleset* rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words, bool spans, cudaStream_t st) {
+  CU(cudaMemsetAsync(w.counters, 0, 16 * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(w.slot_of_msg, 0xff, (size_t)n * 4, st));
   if (G.profiling) cudaEventRecord(G.pev[0], st);
-  k += launch_scan(rs->dev, rs->work, d_bytes, d_off, n, d_words, spans, G.sm_count, st);
+  int k = launch_scan(rs->dev, w, d_bytes, d_off, n, d_words, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[1], st);
-  k += launch_confirm(rs->dev, rs->work, d_bytes, d_off, spans, G.sm_count, st);
+  G.launches += k; G.stats.kernel_launches += k;
+  CU(cudaGetLastError());
+  return CG_OK;
+}
+int scan_tail(cg_ruleset* rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint64_t* d_words, bool spans, cudaStream_t st) {
+  int k = launch_confirm(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[2], st);
-  k += launch_verify(rs->dev, rs->work, d_bytes, d_off, spans, G.sm_count, st);
+  k += launch_verify(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[3], st);
-  k += launch_finalize(rs->dev, rs->work, d_words, G.sm_count, st);
+  k += launch_finalize(rs->dev, w, d_words, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[4], st);
   G.launches += k; G.stats.kernel_launches += k;
   CU(cudaGetLastError());
+  return CG_OK;
+}
+// scan + confirm + verify + finalize on device-resident input, one stream; asynchronous
+int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words,
+                    bool spans, cudaStream_t st) {
+  int rc = scan_head(rs, rs->work, d_bytes, d_off, n, d_words, spans, st);
+  if (rc) return rc;
+  return scan_tail(rs, rs->work, d_bytes, d_off, d_words, spans, st);
+}
+
+// every pipelined batch still in flight joins `st` (st waits for their tails)
+int join_pipeline(cg_ruleset* rs, cudaStream_t st) {
+  for (int i = 0; i < 2; i++) if (rs->inflight[i]) { CU(cudaStreamWaitEvent(st, rs->e_done[i], 0)); rs->inflight[i] = false; }
   return CG_OK;
 }
 
@@ -191,9 +214,10 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
   // keep whatever an earlier step of this rule set needed
   slot_cap = std::max(slot_cap, rs->work.slot_cap); event_cap = std::max(event_cap, rs->work.event_cap); l1_cap = std::max(l1_cap, rs->work.l1_cap);
   hs->counters.assign(16, 0);
+  if ((rc = join_pipeline(rs, st))) return rc;
   if (n && !rs->adapted && (rc = adapt_ruleset(rs, G.d_bytes, G.d_off32, n, st))) return rc;
   for (int attempt = 0; attempt < 10; attempt++) {
-    if ((rc = ensure_work(rs, std::max<uint32_t>(n, 1), l1_cap, slot_cap, event_cap, span_cap))) return rc;
+    if ((rc = ensure_work(rs, rs->work, std::max<uint32_t>(n, 1), l1_cap, slot_cap, event_cap, span_cap))) return rc;
     CU(cudaEventRecord(G.ev0, st));
     if (n) { if ((rc = run_scan_device(rs, G.d_bytes, G.d_off32, n, G.d_words, spans, st))) return rc; }
     else CU(cudaMemsetAsync(rs->work.counters, 0, 64, st));
@@ -263,12 +287,14 @@ int cg_last_kernel_ms(float out_ms[4]) {
   return CG_OK;
 }
 
-int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out8[8]) {
+int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out8[16]) {
   // [0] slots (messages with confirmed candidates), [1] (message, rule) pairs sent to the VM, [2] spans,
-  // [3] error flags, [4] level-1 accept events, [5] reserved, [6] warp-level entries into the scan kernel's slow path
+  // [3] error flags, [4] level-1 accept events, [5] verify kernel's event cursor, [6] warp-level entries into the scan kernel's slow path
   // (4-byte words some lane had to re-walk on the full table), [7] reserved -- of the last completed step
-  if (!rs || !out8 || !rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
-  CU(cudaMemcpy(out8, rs->work.counters, 32, cudaMemcpyDeviceToHost));
+  const ScanWork& lw = (rs && rs->seq && ((rs->seq - 1) & 1u)) ? rs->work2 : rs->work;     // the most recent pipelined batch, else the sequential scratch
+  if (!rs || !out8 || !lw.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out8, lw.counters, 64, cudaMemcpyDeviceToHost));     // [7..15]: CG_SCAN_DEBUG=2 VM cycle histogram
   return CG_OK;
 }
 
@@ -347,7 +373,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   return CG_OK;
 }
 
-void cg_ruleset_destroy(cg_ruleset* rs) { std::lock_guard<std::mutex> lk(g_mu); if (rs) { if (G.ready) cudaStreamSynchronize(G.stream); delete rs; } }
+void cg_ruleset_destroy(cg_ruleset* rs) { std::lock_guard<std::mutex> lk(g_mu); if (rs) { if (G.ready) cudaDeviceSynchronize(); delete rs; } }
 
 int cg_ruleset_get_info(const cg_ruleset* rs, cg_ruleset_info* o) {
   if (!rs || !o) return fail(CG_ERR_INVALID_ARG, "null argument");
@@ -446,19 +472,53 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
   if (!rs || !d_bytes || !d_offsets || !d_out_words) return fail(CG_ERR_INVALID_ARG, "null argument");
-  int rc = ensure_work(rs, std::max<uint32_t>(n, 1), std::max<uint32_t>(std::max<uint32_t>(4 * n, 1u << 16), rs->work.l1_cap), std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), rs->work.slot_cap),
-                       std::max<uint32_t>(std::max<uint32_t>(n, 4096), rs->work.event_cap), 1);
-  if (rc) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
   if (!n) return CG_OK;
-  if (!rs->adapted && (rc = adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st))) return rc;
   static const bool use_graph = !(getenv("CG_NO_GRAPH") && atoi(getenv("CG_NO_GRAPH")));
+  // opt-in (CG_PIPELINE=1): measured on B200, the tail kernels squeezed next to the scan kernel run ~4x slower and the
+  // step time does not improve; the default is the in-order step replayed as one CUDA graph
+  static const bool use_pipeline = getenv("CG_PIPELINE") && atoi(getenv("CG_PIPELINE"));
+  const bool pipelined = use_pipeline && !G.profiling;
+  // which scratch set this batch uses: pipelined batches alternate between two
+  const int idx = pipelined ? (int)(rs->seq & 1u) : 0;
+  ScanWork& w = idx ? rs->work2 : rs->work;
+  const uint32_t want_l1 = std::max<uint32_t>(std::max<uint32_t>(4 * n, 1u << 16), w.l1_cap), want_slot = std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), w.slot_cap),
+                 want_ev = std::max<uint32_t>(std::max<uint32_t>(n, 4096), w.event_cap);
+  int rc;
+  if (n > w.msg_cap || want_l1 > w.l1_cap || want_slot > w.slot_cap || want_ev > w.event_cap || !w.counters || !w.spans) {
+    // (re)allocation: nothing may still be using the old buffers
+    CU(cudaStreamSynchronize(st)); if (rs->side) CU(cudaStreamSynchronize(rs->side));
+    if (rs->graph) { cudaGraphExecDestroy(rs->graph); rs->graph = nullptr; }
+    if ((rc = ensure_work(rs, w, std::max<uint32_t>(n, 1), want_l1, want_slot, want_ev, 1))) return rc;
+  }
+  if (!rs->adapted) {
+    if ((rc = join_pipeline(rs, st))) return rc;
+    if ((rc = adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st))) return rc;
+  }
+  if (pipelined) {
+    // Two batches in flight: the caller's stream runs scratch reset + scan of batch k, the side stream runs confirm +
+    // verify + finalize of batch k while the caller's stream already scans batch k+1.  The tail kernels are small
+    // latency-bound grids; whether they actually run beside the scan kernel depends on what its CTAs leave free.
+    if (!rs->side) {
+      CU(cudaStreamCreateWithFlags(&rs->side, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) { CU(cudaEventCreateWithFlags(&rs->e_scan[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&rs->e_done[i], cudaEventDisableTiming)); }
+    }
+    if (rs->inflight[idx]) { CU(cudaStreamWaitEvent(st, rs->e_done[idx], 0)); rs->inflight[idx] = false; }   // batch k-2 is done with this scratch set
+    if ((rc = scan_head(rs, w, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st))) return rc;
+    CU(cudaEventRecord(rs->e_scan[idx], st));
+    CU(cudaStreamWaitEvent(rs->side, rs->e_scan[idx], 0));
+    if ((rc = scan_tail(rs, w, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, (uint64_t*)d_out_words, false, rs->side))) return rc;
+    CU(cudaEventRecord(rs->e_done[idx], rs->side));
+    rs->inflight[idx] = true; rs->seq++;
+    G.stats.messages_scanned += n;
+    return CG_OK;
+  }
+  if ((rc = join_pipeline(rs, st))) return rc;
   if (!use_graph || G.profiling) {
     rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
   } else {
     // memset + scan + confirm + verify + finalize captured once per (arguments, capacities), then replayed:
     // one launch per step instead of seven, so the host never becomes the bottleneck
-    const ScanWork& w = rs->work;
     const uint32_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
     if (!rs->graph || rs->g_bytes != d_bytes || rs->g_off != d_offsets || rs->g_words != d_out_words || rs->g_n != n || memcmp(caps, rs->g_caps, sizeof caps)) {
       if (rs->graph) { cudaGraphExecDestroy(rs->graph); rs->graph = nullptr; }
@@ -479,11 +539,19 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   return rc;
 }
 
+int cg_scan_join(cg_ruleset* rs, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!rs) return fail(CG_ERR_INVALID_ARG, "null argument");
+  return join_pipeline(rs, stream ? (cudaStream_t)stream : G.stream);
+}
+
 int cg_ruleset_adapt(cg_ruleset* rs, const void* d_bytes, const void* d_offsets, uint32_t n, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
   if (!rs || !d_bytes || !d_offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
   cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+  if (int jr = join_pipeline(rs, st)) return jr;
   CU(cudaStreamSynchronize(st));                         // nothing may still be reading the tables
   return adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st);
 }

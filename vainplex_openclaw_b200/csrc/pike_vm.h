@@ -19,6 +19,13 @@
 #define CG_HD_NOINLINE inline
 #endif
 
+#if defined(CG_VM_STATS) && !defined(__CUDA_ARCH__)
+#define CG_VM_STAT(i) (++cg_vm_stats[i])
+extern "C" unsigned long long cg_vm_stats[8];     // [0] closure (add) calls, [1] closure instructions, [2] list-thread steps, [3] search steps, [4] stretch units
+#else
+#define CG_VM_STAT(i) ((void)0)
+#endif
+
 namespace cg {
 
 struct Cursor { uint32_t pos; uint32_t pending; };   // pending = low surrogate still to deliver (0 = none)
@@ -64,6 +71,7 @@ constexpr int kVmStack = 192;
 template <int CAP>
 struct LocalStore {
   static constexpr uint32_t cap = CAP;
+  static constexpr bool coop = false;      // one run per thread
   uint16_t mark_[CAP]; uint16_t pcs_[2][CAP]; uint32_t sts_[2][CAP]; uint16_t stk_[kVmStack];
   CG_HD uint16_t& mark(uint32_t i) { return mark_[i]; }
   CG_HD uint16_t& pc(int L, uint32_t i) { return pcs_[L][i]; }
@@ -84,6 +92,14 @@ struct VMS {
   CG_HD_NOINLINE VMS(const DevRuleset& r) : rs(r), gen(0), err(0) {}
   CG_HD_NOINLINE VMS(const DevRuleset& r, const Store& s) : rs(r), S(s), gen(0), err(0) {}
 
+  // all marks to zero, generation restarted (cooperative stores: the warp's lanes split the array)
+  CG_HD void clear_marks() {
+#if defined(__CUDA_ARCH__)
+    if (Store::coop) { for (uint32_t k = threadIdx.x & 31u; k < plen; k += 32u) S.mark(k) = 0; __syncwarp(); gen = 0; return; }
+#endif
+    for (uint32_t k = 0; k < plen; k++) S.mark(k) = 0;
+    gen = 0;
+  }
   CG_HD_NOINLINE void bump_gen() { if (++gen >= 0x7fff) { for (uint32_t k = 0; k < plen; k++) S.mark(k) = 0; gen = 1; } }
 
   // Closure from pc0 at a position whose context is (prev, next, byte `pos`, unit index `upos`):
@@ -98,6 +114,7 @@ struct VMS {
   // then cut every lower-priority thread).
   CG_HD_NOINLINE bool add(int L, uint32_t pc0, uint32_t start, int prev, int next, uint32_t pos, uint32_t upos) {
     const uint16_t INPROG = (uint16_t)(gen * 2), DONE = (uint16_t)(gen * 2 + 1);
+    CG_VM_STAT(0);
     int sp = 0; S.stk(sp++) = (uint16_t)pc0;
     while (sp) {
       uint32_t x = S.stk(--sp);
@@ -105,7 +122,7 @@ struct VMS {
       uint32_t pc = x;
       for (;;) {
         uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
-        bool go = false;
+        bool go = false; CG_VM_STAT(1);
         switch (op) {
           case OP_SPLIT_NEXT: case OP_SPLIT_JUMP:
             if (S.mark(pc) == DONE) break;
@@ -157,23 +174,92 @@ struct VMS {
         // Nothing alive and the start at `pos` has already failed: move on, skipping ASCII units
         // that cannot begin a match (first-unit filter; nullable rules have an all-ones filter).
         do { prev = cur; pos = cn.pos; upos++; c = cn; cur = next_unit(m, len, cn); }
-        while (cur >= 0 && cur < 128 && !((first[cur >> 5] >> (cur & 31)) & 1u));
+        while (pos <= start_limit && cur >= 0 && cur < 128 && !((first[cur >> 5] >> (cur & 31)) & 1u));
         if (pos > start_limit) break;
         bump_gen();
         add(L, 0, pos, prev, cur, pos, upos);
         continue;
       }
       if (cur < 0) break;
+      // Deterministic stretch: one live thread, no further start positions, and straight-line consuming
+      // instructions ahead (a literal, an expanded x{36}): walk it without the list / closure machinery.  The
+      // last unit of the stretch -- the one whose successor instruction needs a closure -- is left to the
+      // general step below.
+      if (cnt[L] == 1 && !matched && cn.pos > start_limit) {
+        uint32_t pc = S.pc(L, 0);
+#if defined(__CUDA_ARCH__)
+        if (Store::coop) {
+          // Warp-cooperative form (verify_small_kernel: the 32 lanes of a warp execute ONE run redundantly, with
+          // identical registers): lane j tests byte pos+j against instruction pc+j, a ballot finds how far the
+          // stretch holds, and 32 units cost one round of loads instead of 32 dependent ones.  ASCII only -- a
+          // byte >= 0x80 ends the batch and goes through the general step (full UTF-8 decode).
+          const uint32_t lane = threadIdx.x & 31u;
+          while (!c.pending) {
+            const uint32_t bj = pos + lane < len ? (uint32_t)m[pos + lane] : 0x100u;
+            const uint32_t ij = pc + lane < plen ? prog[pc + lane] : (uint32_t)OP_MATCH;
+            const uint32_t nj = pc + lane + 1 < plen ? prog[pc + lane + 1] & 0xffu : (uint32_t)OP_MATCH;
+            const uint32_t op = ij & 0xffu, arg = ij >> 8;
+            const bool cons = op == OP_CHAR || op == OP_SET || op == OP_ANY;
+            bool ok = false;
+            if (cons && bj < 0x80u)
+              ok = op == OP_CHAR ? bj == arg : op == OP_ANY ? !(bj == 0x0au || bj == 0x0du) : ((rs.sets[(size_t)arg * 6 + (bj >> 5)] >> (bj & 31u)) & 1u) != 0;
+            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+            const uint32_t good = okm & __ballot_sync(0xffffffffu, nj == OP_CHAR || nj == OP_SET || nj == OP_ANY);
+            const uint32_t J = good == 0xffffffffu ? 32u : (uint32_t)__ffs(~good) - 1u;      // units consumed by this batch
+            const uint32_t bJ = __shfl_sync(0xffffffffu, bj, J & 31u), bP = __shfl_sync(0xffffffffu, bj, (J + 31u) & 31u);
+            if (J) { prev = (int)bP; pos += J; upos += J; pc += J; }
+            if (J == 32u) {                                   // all 32 held: reload and go on (cur is fixed up on exit)
+              c.pos = pos; c.pending = 0; cn = c; cur = next_unit(m, len, cn);
+              if (cur < 0) { cnt[L] = 0; break; }
+              continue;
+            }
+            // position J: its instruction is consuming (instruction pc + J - 1 said so, or it is the thread's own)
+            c.pos = pos; c.pending = 0; cn = c;
+            if (bJ == 0x100u) { cur = -1; cnt[L] = 0; break; }                      // end of message: the thread dies
+            if (bJ < 0x80u) { cur = (int)bJ; cn.pos = pos + 1; if (!((okm >> J) & 1u)) cnt[L] = 0; }   // ASCII mismatch: dies
+            else cur = next_unit(m, len, cn);                                       // non-ASCII: the general step decides
+            break;
+          }
+          if (c.pending) {}                                   // (mid-surrogate: nothing done, general step)
+        } else
+#endif
+        for (;;) {
+          const uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
+          const bool ok = op == OP_CHAR ? ((uint32_t)cur == arg)
+                        : op == OP_ANY ? !(cur == 0x0a || cur == 0x0d || cur == 0x2028 || cur == 0x2029)
+                        : in_set(rs, arg, cur);
+          if (!ok) { cnt[L] = 0; break; }
+          const uint32_t nop = prog[pc + 1] & 0xff;
+          if (nop != OP_CHAR && nop != OP_SET && nop != OP_ANY) break;
+          prev = cur; pos = cn.pos; upos++; c = cn; cur = next_unit(m, len, cn); pc++; CG_VM_STAT(4);
+          if (cur < 0) { cnt[L] = 0; break; }
+        }
+        if (cnt[L] == 0) continue;                          // the thread died: the loop head ends the search
+        S.pc(L, 0) = (uint16_t)pc;
+      }
       Cursor cnn = cn; int nxt = next_unit(m, len, cnn);  // unit after cur
       int N = L ^ 1; cnt[N] = 0; bump_gen();
       uint32_t npos = cn.pos, nupos = upos + 1;
       bool cut = false;
+      CG_VM_STAT(3);
       for (uint32_t k = 0; k < cnt[L] && !cut; k++) {
+        CG_VM_STAT(2);
         uint32_t pc = S.pc(L, k); uint32_t ins = prog[pc], op = ins & 0xff, arg = ins >> 8;
         bool ok = op == OP_CHAR ? ((uint32_t)cur == arg)
                 : op == OP_ANY ? !(cur == 0x0a || cur == 0x0d || cur == 0x2028 || cur == 0x2029)
                 : in_set(rs, arg, cur);
-        if (ok) cut = add(N, pc + 1, S.st(L, k), cur, nxt, npos, nupos);
+        if (ok) {
+          // successor is itself a consuming instruction (inside a literal / class run): queue it directly, no closure walk
+          const uint32_t npc = pc + 1, nop = prog[npc] & 0xff;
+          if (nop == OP_CHAR || nop == OP_SET || nop == OP_ANY) {
+            const uint16_t DONE = (uint16_t)(gen * 2 + 1);
+            if (S.mark(npc) != DONE) {
+              S.mark(npc) = DONE;
+              const uint32_t q = cnt[N];
+              if (q < Store::cap) { S.pc(N, q) = (uint16_t)npc; S.st(N, q) = S.st(L, k); cnt[N] = q + 1; } else err |= ERR_VM_LIST;
+            }
+          } else cut = add(N, npc, S.st(L, k), cur, nxt, npos, nupos);
+        }
       }
       // new lowest-priority start at npos -- skipped when the unit there cannot begin a match
       // (first-unit filter; a start thread that cannot consume its first unit dies immediately,
@@ -213,8 +299,7 @@ CG_HD_NOINLINE bool run_rule(VMX& vm, const DevRuleset& rs, uint32_t rule, const
   vm.prog = vm.prog_override ? vm.prog_override : rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
   if (vm.plen == 0) return false;                     // rule failed to compile: never matches
   if (vm.plen > VMX::capacity()) { vm.err |= ERR_VM_LIST; return false; }
-  for (uint32_t k = 0; k < vm.plen; k++) vm.S.mark(k) = 0;
-  vm.gen = 0;
+  vm.clear_marks();
   const uint32_t* first = rs.rule_first + (size_t)rule * 8;
   uint32_t from = 0, from16 = 0; int prev = -1; Cursor c{0, 0};
   bool any = false;
@@ -255,8 +340,7 @@ CG_HD_NOINLINE bool test_at_factor(VMX& vm, const DevRuleset& rs, uint32_t rule,
   vm.prog = vm.prog_override ? vm.prog_override : rs.prog + rs.rule_prog_off[rule]; vm.plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
   if (vm.plen == 0) return false;
   if (vm.plen > VMX::capacity()) { vm.err |= ERR_VM_LIST; return false; }
-  for (uint32_t k = 0; k < vm.plen; k++) vm.S.mark(k) = 0;
-  vm.gen = 0;
+  vm.clear_marks();
   const uint32_t* first = rs.rule_first + (size_t)rule * 8;
   // bytes the part of a match BEFORE this factor can consist of (per factor; falls back to the rule's alphabet)
   const uint32_t pa = pre_units >> 16; pre_units &= 0xffffu;

@@ -58,7 +58,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {
 // level 1: prefilter scan.  lane-per-message (NS interleaved message streams per lane), streaming
 // 16-byte loads, table in shared memory
 // ------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 1024;
+constexpr int kScanThreads = 1024;      // 32 warps, one CTA per SM (768 threads next to a co-resident verify CTA was measured: scan 10% slower, no overlap gain)
 constexpr uint32_t kL1Always = 0xffffffffu;
 constexpr uint32_t kAccept = 0x8000u, kCold = 0x4000u, kStateMask = 0x3fffu;
 
@@ -473,14 +473,15 @@ confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, con
 // level 3: exact verification by the Pike VM
 // ------------------------------------------------------------------------------------------
 constexpr int kVerifyThreads = 64;            // verify_large_kernel
-// verify_small_kernel: VM runs diverge completely (different program, different text per lane), so a warp
-// pays the SUM of its lanes' instruction streams.  Only kVerifyLanes lanes per warp carry a run.
-constexpr int kVerifyBlock = 256, kVerifyLanes = 2, kVerifySlots = (kVerifyBlock / 32) * kVerifyLanes;
+// verify_small_kernel: VM runs diverge completely (different program, different text), so two runs in one warp cost the
+// SUM of their instruction streams: one run per warp, whose lanes cooperate inside the run instead.
+constexpr int kVerifyBlock = 256, kVerifyCtasPerSm = 4, kVerifySlots = kVerifyBlock / 32;     // one VM run per warp
 constexpr int kSmallProg = 192;          // VM capacity that covers every built-in rule (longest: key-value-credential, 183 instructions)
 
 struct GlobalSpanSink {
-  const ScanWork& w; uint32_t msg, rule;
+  const ScanWork& w; uint32_t msg, rule; bool lane0_only;
   __device__ void span(uint32_t sb, uint32_t eb, uint32_t s16, uint32_t e16) {
+    if (lane0_only && (threadIdx.x & 31u)) return;         // warp-redundant runs (verify_small_kernel): one lane reports
     uint32_t k = atomicAdd(&w.counters[2], 1u);
     if (k < w.span_cap) { uint32_t* o = w.spans + (size_t)k * 6; o[0] = msg; o[1] = rule; o[2] = sb; o[3] = eb; o[4] = s16; o[5] = e16; }
     else atomicOr(&w.counters[3], ERR_SPAN_OVERFLOW);
@@ -490,6 +491,7 @@ struct GlobalSpanSink {
 // thread-interleaved shared-memory VM storage: element i of thread t lives at base[i * blockDim + t]
 struct SmemStore {
   static constexpr uint32_t cap = kSmallProg;
+  static constexpr bool coop = true;       // one run per WARP: every lane executes it redundantly and helps where it can (pike_vm.h)
   uint16_t* mark_; uint16_t* pcs_; uint32_t* sts_; uint16_t* stk_; uint32_t stride, t;
   __device__ __forceinline__ uint16_t& mark(uint32_t i) { return mark_[i * stride + t]; }
   __device__ __forceinline__ uint16_t& pc(int L, uint32_t i) { return pcs_[(L * cap + i) * stride + t]; }
@@ -498,19 +500,21 @@ struct SmemStore {
 };
 constexpr int kStageMsg = 256;                       // messages up to this many bytes are staged into shared memory
 constexpr size_t kVerifyVmBytes = (size_t)kVerifySlots * (kSmallProg * 2 + 2 * kSmallProg * 2 + 2 * kSmallProg * 4 + kVmStack * 2);
-constexpr size_t kVerifyProgBytes = (size_t)kVerifySlots * (kSmallProg + 1) * 4;     // odd word stride per slot: conflict-free
-constexpr size_t kVerifyMsgBytes = (size_t)kVerifySlots * (kStageMsg + 4);
+constexpr size_t kVerifyProgBytes = 0;      // (staging areas: measured, not worth their copy loops)
+constexpr size_t kVerifyMsgBytes = 0;
 constexpr size_t kVerifySmem = kVerifyVmBytes + kVerifyProgBytes + kVerifyMsgBytes;
 
 // small programs (<= kSmallProg instructions): VM state in shared memory
 template <bool SPANS>
-__global__ void __launch_bounds__(kVerifyBlock)
+__global__ void __launch_bounds__(kVerifyBlock, kVerifyCtasPerSm)
 verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off) {
   extern __shared__ __align__(16) uint8_t vsm[];
   const uint32_t n_events = min(w.counters[1], w.event_cap);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane >= (uint32_t)kVerifyLanes) return;
-  const uint32_t slot_id = warp * kVerifyLanes + lane;                 // this thread's VM slot inside the block
+  // One run per warp.  All 32 lanes execute it redundantly -- identical registers, uniform control flow, the VM
+  // state in shared memory written with identical values -- so that the lanes can split the work wherever a step
+  // is data-parallel (SIMD literal / class stretches, mark clearing; see pike_vm.h).  Only lane 0 reports.
+  const uint32_t slot_id = warp;
   SmemStore st;
   st.stride = kVerifySlots; st.t = slot_id;
   st.sts_ = reinterpret_cast<uint32_t*>(vsm);
@@ -518,29 +522,40 @@ verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
   st.mark_ = st.pcs_ + (size_t)kVerifySlots * 2 * kSmallProg;
   st.stk_ = st.mark_ + (size_t)kVerifySlots * kSmallProg;
   VMS<SmemStore> vm(rs, st);
-  // per-thread staging areas: the rule's program and (for short messages) the message bytes, so the
-  // VM's dependent loads hit shared memory instead of chains of L2 round trips
-  uint32_t* my_prog = reinterpret_cast<uint32_t*>(vsm + kVerifyVmBytes) + (size_t)slot_id * (kSmallProg + 1);
-  uint8_t* my_msg = vsm + kVerifyVmBytes + kVerifyProgBytes + (size_t)slot_id * (kStageMsg + 4);
-  for (uint32_t e = blockIdx.x * kVerifySlots + slot_id; e < n_events; e += gridDim.x * kVerifySlots) {
+  // events are handed out one at a time (their cost varies by two orders of magnitude): a static split leaves most
+  // warps idle while a few finish their second or third long run
+  for (;;) {
+    uint32_t e = 0;
+    if (lane == 0) e = atomicAdd(&w.counters[5], 1u);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e >= n_events) break;
     uint2 ev = w.events[e];
     uint32_t slot = ev.x, rule = ev.y;
-    const uint32_t poff = rs.rule_prog_off[rule], plen = rs.rule_prog_off[rule + 1] - poff;
+    const uint32_t plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
     if (plen > (uint32_t)kSmallProg) continue;          // handled by verify_large_kernel
     uint32_t msg = w.slot_msg[slot];
-    GlobalSpanSink sink{w, msg, rule};
+    GlobalSpanSink sink{w, msg, rule, true};
     const uint32_t t0 = w.event_pos[e];
-    if (!SPANS && t0 != 0xffffffffu && ((w.hit[(size_t)slot * rs.rw + (rule >> 5)] >> (rule & 31)) & 1u)) continue;   // another occurrence already proved it
-    // (staging the program / message into shared memory was measured: the copy loops cost more than the
-    //  L1-cached global loads they replace, so the VM reads both through the read-only path)
-    (void)my_prog; (void)my_msg; (void)poff;
+    if (!SPANS && t0 != 0xffffffffu) {                  // another occurrence already proved it?  (one read, broadcast: the warp must agree)
+      uint32_t hv = 0;
+      if (lane == 0) hv = w.hit[(size_t)slot * rs.rw + (rule >> 5)];
+      hv = __shfl_sync(0xffffffffu, hv, 0);
+      if ((hv >> (rule & 31)) & 1u) continue;
+    }
     const uint8_t* m = bytes + off[msg]; const uint32_t len = off[msg + 1] - off[msg];
     bool any;
+    const long long tc0 = (rs.debug_flags & 2u) ? clock64() : 0;
     if (SPANS || t0 == 0xffffffffu) any = run_rule<SPANS>(vm, rs, rule, m, len, sink);
     else any = test_at_factor(vm, rs, rule, m, len, t0, w.event_pre[e]);
-    if (any) atomicOr(&w.hit[(size_t)slot * rs.rw + (rule >> 5)], 1u << (rule & 31));
+    __syncwarp();
+    if (any && lane == 0) atomicOr(&w.hit[(size_t)slot * rs.rw + (rule >> 5)], 1u << (rule & 31));
+    if ((rs.debug_flags & 2u) && lane == 0) {       // CG_SCAN_DEBUG=2: histogram of VM cycles per event in counters[8..15] (<2^11, <2^12, ... >=2^17), max in [7]
+      const uint32_t cyc = (uint32_t)(clock64() - tc0);
+      int bkt = 31 - __clz(cyc | 1u) - 10; bkt = bkt < 0 ? 0 : bkt > 7 ? 7 : bkt;
+      atomicAdd(&w.counters[8 + bkt], 1u); atomicMax(&w.counters[7], cyc);
+    }
   }
-  if (vm.err) atomicOr(&w.counters[3], vm.err);
+  if (vm.err && lane == 0) atomicOr(&w.counters[3], vm.err);
 }
 
 // programs longer than kSmallProg: per-thread local arrays
@@ -555,7 +570,7 @@ verify_large_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
     uint32_t plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
     if (plen <= (uint32_t)kSmallProg) continue;
     uint32_t msg = w.slot_msg[slot];
-    GlobalSpanSink sink{w, msg, rule};
+    GlobalSpanSink sink{w, msg, rule, false};
     const uint32_t t0 = w.event_pos[e];
     bool any;
     if (SPANS || t0 == 0xffffffffu) any = run_rule<SPANS>(vm, rs, rule, bytes + off[msg], off[msg + 1] - off[msg], sink);
@@ -628,9 +643,9 @@ int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byte
                   bool want_spans, int sm_count, cudaStream_t stream) {
   int k = 1;
   if (want_spans) {
-    verify_small_kernel<true><<<sm_count * 2, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+    verify_small_kernel<true><<<sm_count * kVerifyCtasPerSm, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   } else {
-    verify_small_kernel<false><<<sm_count * 2, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+    verify_small_kernel<false><<<sm_count * kVerifyCtasPerSm, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   }
   if (rs.max_prog_len > (uint32_t)kSmallProg) {
     k++;
