@@ -16,6 +16,8 @@ CG_HD bool byte_in_set(const DevRuleset& rs, uint32_t sid, uint32_t b) {
   return (rs.bytesets[(size_t)sid * 8 + (b >> 5)] >> (b & 31)) & 1u;
 }
 
+constexpr int kMaxFactorElemsDev = 16;      // = kMaxFactorElems (rulec.h): elements per full factor
+
 // Does factor `fw` occur in message m[0,len) with its level-1 window ending at byte `pend`?
 CG_HD_NOINLINE bool confirm_factor(const DevRuleset& rs, const uint32_t* __restrict__ fw, const uint8_t* __restrict__ m,
                                    uint32_t len, uint32_t pend) {
@@ -23,14 +25,18 @@ CG_HD_NOINLINE bool confirm_factor(const DevRuleset& rs, const uint32_t* __restr
   if (pend + 1 < wend) return false;
   const uint32_t t0 = pend + 1 - wend;                 // message offset of factor element 0
   if (t0 + flen > len) return false;
-  // elements after the window first (most likely to fail), then the rest (the window was only
-  // matched through the folded level-1 alphabet, so it is re-checked exactly as well)
-  for (uint32_t i = 0; i < flen; i++) {
-    uint32_t k = wend + i; if (k >= flen) k -= flen;
-    uint32_t sid = (fw[2 + (k >> 1)] >> (16 * (k & 1))) & 0xffffu;
-    if (!byte_in_set(rs, sid, m[t0 + k])) return false;
+  // No early exit on purpose: with all (up to 16) element checks unrolled and independent, their loads -- the factor's
+  // set ids, the message bytes, one byte-set word each -- are issued back to back and overlap, instead of forming a
+  // chain of 2 x flen dependent L2 round trips (this kernel is pure latency).
+  bool ok = true;
+#pragma unroll
+  for (uint32_t k = 0; k < (uint32_t)kMaxFactorElemsDev; k++) {
+    if (k < flen) {
+      const uint32_t sid = (fw[2 + (k >> 1)] >> (16 * (k & 1))) & 0xffffu;
+      ok = ok & byte_in_set(rs, sid, m[t0 + k]);
+    }
   }
-  return true;
+  return ok;
 }
 
 // the factors of accept id `aid` are confirmed at message offset `pend` (window's last byte)
