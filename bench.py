@@ -83,7 +83,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, emit=None):
     """The reference's own CPU implementation of the path, restated (oracle/): policy-semantics scan
     (matchesAny: RegExp.test per rule, gov/src/conditions/context.ts:9-25) on all host threads."""
     if rank != 0:
@@ -93,11 +93,21 @@ def reference_arm(args, rank, world):
     rl = W.make_rules(N_RULES)
     regs = [O.Regex(r["source"], "i" if r["flags"] else "") for r in rl]
     threads = os.cpu_count() or 1
-    sample = int(os.environ.get("CG_REF_SAMPLE", 65536))
-    data_t, off_t, _ = W.make_messages(sample, MSG_LEN, rl, p_hit=P_HIT)
+    # bounded sample per step, sized from a short calibration so that the whole --steps K --warmup W run stays near two
+    # minutes whatever K and W the caller picks (CG_REF_SAMPLE pins it)
+    cal_n = 4096
+    data_t, off_t, _ = W.make_messages(65536, MSG_LEN, rl, p_hit=P_HIT)
     data, off = data_t.numpy(), off_t.numpy().astype(np.uint64)
+    O.scan_policy(regs, data[: cal_n * MSG_LEN + 64], off[:cal_n + 1], threads=threads, want_bits=False)       # untimed: page in, spawn threads
+    t0 = time.perf_counter()
+    O.scan_policy(regs, data[: cal_n * MSG_LEN + 64], off[:cal_n + 1], threads=threads, want_bits=False)
+    rate = cal_n / max(time.perf_counter() - t0, 1e-6)
+    budget_s = float(os.environ.get("CG_REF_SECONDS", 120.0))
+    sample = int(os.environ.get("CG_REF_SAMPLE", 0)) or int(rate * budget_s / max(args.steps + args.warmup, 1))
+    sample = max(1024, min(65536, sample))
+    data, off = data[: sample * MSG_LEN + 64], off[: sample + 1]
     for _ in range(args.warmup):
-        O.scan_policy(regs, data[: 4096 * MSG_LEN + 64], off[:4097], threads=threads, want_bits=False)
+        O.scan_policy(regs, data, off, threads=threads, want_bits=False)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         O.scan_policy(regs, data, off, threads=threads, want_bits=False)
@@ -111,10 +121,21 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "msgs/s", "cores": threads, "kind": "port",
                              "sample": "%d messages x %d rules per step, oracle/jsre.c backtracking matcher, %d threads (Node.js absent: restated oracle, not Node)" % (sample, N_RULES, threads)},
             "e2e": {"value": v, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    (emit or (lambda o: print(json.dumps(o))))(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner, ...)
+    # goes to stderr instead; the real stdout is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -132,7 +153,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        return reference_arm(args, rank, world)
+        return reference_arm(args, rank, world, emit)
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
@@ -339,7 +360,7 @@ def main():
         "clocks": clocks,
         "extra": {"merkle": merkle, "per_rank_ms_per_step": per_rank_ms},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -74,12 +74,13 @@ struct cg_ruleset {
   cudaEvent_t e_scan[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr};
   bool inflight[2] = {false, false};
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
-  cudaGraphExec_t graph = nullptr;
-  const void* g_bytes = nullptr; const void* g_off = nullptr; void* g_words = nullptr; uint32_t g_n = 0; uint32_t g_caps[4] = {0, 0, 0, 0};
+  struct CachedGraph { cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint32_t caps[4] = {0, 0, 0, 0}; uint64_t used = 0; };
+  CachedGraph graphs[2];          // two entries: callers that alternate between two input/output buffer sets replay, never re-capture
+  uint64_t graph_clock = 0;
   bool adapted = false;           // profile-guided residency has run (first scan, or cg_ruleset_adapt)
   uint8_t* d_image_rw = nullptr; uint16_t* d_table_rw = nullptr; uint32_t* d_acc_index_rw = nullptr;   // writable aliases of dev.image / table_full / acc_index
   ~cg_ruleset() {
-    if (graph) cudaGraphExecDestroy(graph);
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (side) cudaStreamDestroy(side);
     for (int i = 0; i < 2; i++) { if (e_scan[i]) cudaEventDestroy(e_scan[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); }
     for (ScanWork* w2 : {&work2}) { cudaFree(w2->l1_msg); cudaFree(w2->l1_pos); cudaFree(w2->l1_sc); cudaFree(w2->slot_of_msg); cudaFree(w2->counters); cudaFree(w2->slot_msg); cudaFree(w2->cand); cudaFree(w2->hit); cudaFree(w2->events); cudaFree(w2->event_pos); cudaFree(w2->event_pre); cudaFree(w2->spans); }
@@ -488,7 +489,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   if (n > w.msg_cap || want_l1 > w.l1_cap || want_slot > w.slot_cap || want_ev > w.event_cap || !w.counters || !w.spans) {
     // (re)allocation: nothing may still be using the old buffers
     CU(cudaStreamSynchronize(st)); if (rs->side) CU(cudaStreamSynchronize(rs->side));
-    if (rs->graph) { cudaGraphExecDestroy(rs->graph); rs->graph = nullptr; }
+    for (auto& g : rs->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if ((rc = ensure_work(rs, w, std::max<uint32_t>(n, 1), want_l1, want_slot, want_ev, 1))) return rc;
   }
   if (!rs->adapted) {
@@ -520,19 +521,23 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     // memset + scan + confirm + verify + finalize captured once per (arguments, capacities), then replayed:
     // one launch per step instead of seven, so the host never becomes the bottleneck
     const uint32_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
-    if (!rs->graph || rs->g_bytes != d_bytes || rs->g_off != d_offsets || rs->g_words != d_out_words || rs->g_n != n || memcmp(caps, rs->g_caps, sizeof caps)) {
-      if (rs->graph) { cudaGraphExecDestroy(rs->graph); rs->graph = nullptr; }
+    cg_ruleset::CachedGraph* hit = nullptr;
+    for (auto& g : rs->graphs) if (g.exec && g.bytes == d_bytes && g.off == d_offsets && g.words == d_out_words && g.n == n && !memcmp(caps, g.caps, sizeof caps)) hit = &g;
+    if (!hit) {
+      hit = rs->graphs[0].used <= rs->graphs[1].used ? &rs->graphs[0] : &rs->graphs[1];       // least recently used entry
+      if (hit->exec) { cudaGraphExecDestroy(hit->exec); hit->exec = nullptr; }
       cudaGraph_t g = nullptr;
       CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
       cudaError_t e = cudaStreamEndCapture(st, &g);
       if (rc != CG_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc != CG_OK ? rc : cuda_fail(e, "cudaStreamEndCapture"); }
-      e = cudaGraphInstantiate(&rs->graph, g, 0);
+      e = cudaGraphInstantiate(&hit->exec, g, 0);
       cudaGraphDestroy(g);
-      if (e != cudaSuccess) { rs->graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
-      rs->g_bytes = d_bytes; rs->g_off = d_offsets; rs->g_words = d_out_words; rs->g_n = n; memcpy(rs->g_caps, caps, sizeof caps);
+      if (e != cudaSuccess) { hit->exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
+      hit->bytes = d_bytes; hit->off = d_offsets; hit->words = d_out_words; hit->n = n; memcpy(hit->caps, caps, sizeof caps);
     }
-    CU(cudaGraphLaunch(rs->graph, st));
+    hit->used = ++rs->graph_clock;
+    CU(cudaGraphLaunch(hit->exec, st));
     G.launches += 5; G.stats.kernel_launches += 5;       // kernels inside the graph (scan, confirm, verify, finalize + optional large-VM)
   }
   if (rc == CG_OK) { G.stats.messages_scanned += n; }
