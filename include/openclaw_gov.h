@@ -138,7 +138,10 @@ CG_API int cg_find_matches_batch(cg_ruleset *rs, const uint8_t *bytes, const uin
 /* ---- device-resident variants (inputs/outputs already in HBM; used by bench.py `value` and by
  * callers that pipeline their own copies).  Pointers are CUDA device pointers; `stream` is a
  * cudaStream_t (NULL = the library's own stream); asynchronous w.r.t. the host.
- * d_bytes must be readable for 16 bytes past offsets[n] (padding). */
+ * d_bytes must be readable for 16 bytes past offsets[n] (padding).
+ * Queue capacities: a batch that overflows an internal queue (far more level-1 events / candidates than usual) sets a
+ * flag in cg_scan_work_counters()[3] and its result words are incomplete; the library sees the flag at the next call
+ * and grows the scratch before that call runs.  (cg_scan_batch, the host-buffer call, retries by itself.) */
 CG_API int cg_scan_batch_device(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n,
                                 void *d_out_words, void *stream);
 

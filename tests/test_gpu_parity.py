@@ -226,6 +226,54 @@ def test_single_long_message(N, oracle):
     rs.close()
 
 
+def test_long_messages_are_cut_into_units(N, oracle):
+    """Messages longer than 2 KB are scanned as 1 KB units (16 bytes of warm-up each): tokens placed on and around every
+    unit boundary must be found exactly once, for ragged lengths, through the host path and the device path."""
+    import torch
+    rl = W.make_rules(120)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    rng = np.random.default_rng(99)
+    lens = [5000, 3 * 1024 + 5, 2049, 100, 70000, 0, 1024, 2048, 4096 + 17, 33, 9000]
+    filler_t, _, _ = W.make_messages(1, sum(lens) + 64, rl, p_hit=0.0, seed=17)
+    filler = filler_t.numpy()
+    msgs, pos = [], 0
+    for L in lens:
+        m = bytearray(filler[pos:pos + L].tobytes()); pos += L
+        for b in range(1024, L, 1024):                       # a token ending / starting / straddling each boundary
+            r = rl[int(rng.integers(17, len(rl)))]
+            tok = (" " + r["sample"] + " ").encode()
+            at = b + int(rng.integers(-len(tok) - 2, 3))
+            if 0 <= at and at + len(tok) <= L:
+                m[at:at + len(tok)] = tok
+        msgs.append(bytes(m))
+    data, off = N.pack(msgs)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert len(ehits) >= 60
+    for rep in range(2):                                     # second round: the unit table already exists
+        words, hits = rs.scan_batch(data, off)
+        assert np.array_equal(words, ewords)
+        assert [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits
+    d = torch.from_numpy(np.concatenate([data, np.zeros(64, np.uint8)])).cuda()
+    o = torch.from_numpy(off.astype(np.int32)).cuda()
+    out = torch.full((len(msgs),), -1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    for rep in range(3):
+        rs.scan_batch_device(d.data_ptr(), o.data_ptr(), len(msgs), out.data_ptr(), st.cuda_stream)
+        rs.scan_join(st.cuda_stream)
+        st.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), ewords)
+    spans = rs.find_matches_batch(data, off)
+    got = [(int(x["msg"]), int(x["rule"]), int(x["start16"]), int(x["end16"])) for x in spans]
+    assert got == oracle_spans(oracle, rules, data, off)
+    # and back to a short-message batch on the same rule set (unit table dropped again)
+    data2_t, off2_t, _ = W.make_messages(3000, 200, rl, p_hit=0.1, seed=18)
+    data2, off2 = data2_t.numpy(), off2_t.numpy().astype(np.uint32)
+    w2, _ = rs.scan_batch(data2, off2)
+    assert np.array_equal(w2, oracle_policy(oracle, rules, data2, off2)[0])
+    rs.close()
+
+
 # ------------------------------------------------------------------------------ SHA-256 / Merkle
 
 def test_sha256_batch_equals_hashlib_and_oracle(N, oracle):

@@ -73,8 +73,14 @@ struct cg_ruleset {
   cudaStream_t side = nullptr;    // confirm / verify / finalize of batch k run here while the caller's stream scans batch k+1
   cudaEvent_t e_scan[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr};
   bool inflight[2] = {false, false};
+  // device path: the step's counters are mirrored into pinned host memory after every batch, so the NEXT call can see
+  // that a queue overflowed (results of that batch incomplete, flagged in counters[3]) and grow the scratch before it runs
+  uint32_t* h_counters = nullptr; cudaEvent_t e_cnt = nullptr; bool cnt_pending = false;
+  uint32_t grow_l1 = 0, grow_slot = 0, grow_ev = 0, grow_units = 0;     // capacities learnt from overflows
+  bool segmented = false;         // long messages seen (first scan / cg_ruleset_adapt): scans cut them into units (kernels.h)
+  uint32_t want_units = 0;        // unit-table capacity for the batches seen so far
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
-  struct CachedGraph { cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint32_t caps[4] = {0, 0, 0, 0}; uint64_t used = 0; };
+  struct CachedGraph { cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint64_t caps[6] = {0, 0, 0, 0, 0, 0}; uint64_t used = 0; };
   CachedGraph graphs[2];          // two entries: callers that alternate between two input/output buffer sets replay, never re-capture
   uint64_t graph_clock = 0;
   bool adapted = false;           // profile-guided residency has run (first scan, or cg_ruleset_adapt)
@@ -82,7 +88,10 @@ struct cg_ruleset {
   ~cg_ruleset() {
     for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (side) cudaStreamDestroy(side);
+    if (h_counters) cudaFreeHost(h_counters);
+    if (e_cnt) cudaEventDestroy(e_cnt);
     for (int i = 0; i < 2; i++) { if (e_scan[i]) cudaEventDestroy(e_scan[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); }
+    cudaFree(work.units); cudaFree(work2.units);
     for (ScanWork* w2 : {&work2}) { cudaFree(w2->l1_msg); cudaFree(w2->l1_pos); cudaFree(w2->l1_sc); cudaFree(w2->slot_of_msg); cudaFree(w2->counters); cudaFree(w2->slot_msg); cudaFree(w2->cand); cudaFree(w2->hit); cudaFree(w2->events); cudaFree(w2->event_pos); cudaFree(w2->event_pre); cudaFree(w2->spans); }
     for (void* p : allocs) cudaFree(p);
     cudaFree(work.l1_msg); cudaFree(work.l1_pos); cudaFree(work.l1_sc); cudaFree(work.slot_of_msg);
@@ -105,7 +114,7 @@ int upload(cg_ruleset* rs, const std::vector<T>& v, const T** out, size_t pad_el
 }
 
 int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_cap, uint32_t event_cap, uint32_t span_cap) {
-  if (!w.counters) { CU(cudaMalloc((void**)&w.counters, 16 * sizeof(uint32_t))); }
+  if (!w.counters) { CU(cudaMalloc((void**)&w.counters, kCounterWords * sizeof(uint32_t))); }
   if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
   if (l1_cap > w.l1_cap) {
     cudaFree(w.l1_msg); cudaFree(w.l1_pos); cudaFree(w.l1_sc); w.l1_msg = w.l1_pos = w.l1_sc = nullptr; w.l1_cap = 0;
@@ -125,12 +134,40 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
   return CG_OK;
 }
 
+// unit table of segmented scans: allocate / grow / drop to match rs->segmented
+int ensure_units(cg_ruleset* rs, ScanWork& w) {
+  if (!rs->segmented || rs->host.pf.mode == 4) { if (w.units) { cudaFree(w.units); w.units = nullptr; w.unit_cap = 0; } return CG_OK; }
+  const uint32_t want = std::max(rs->want_units, rs->grow_units);
+  if (w.units && w.unit_cap >= want) return CG_OK;
+  if (w.units) { cudaFree(w.units); w.units = nullptr; w.unit_cap = 0; }
+  CU(cudaMalloc((void**)&w.units, (size_t)want * sizeof(uint2)));
+  w.unit_cap = want;
+  return CG_OK;
+}
+
+// Long messages?  (device-resident batch: one reduction over the offsets, then the total size from offsets[n])
+int decide_segmentation(cg_ruleset* rs, const uint32_t* d_off, uint32_t n, cudaStream_t st) {
+  uint32_t* d_max = nullptr; uint32_t h[2] = {0, 0};
+  CU(cudaMalloc((void**)&d_max, 4));
+  cudaError_t e = cudaMemsetAsync(d_max, 0, 4, st);
+  if (e == cudaSuccess) { launch_max_len(d_off, n, d_max, st); G.launches++; G.stats.kernel_launches++; }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h[0], d_max, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h[1], d_off + n, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_max);
+  if (e != cudaSuccess) return cuda_fail(e, "message length scan");
+  rs->segmented = h[0] > 2 * kSegBytes;
+  rs->want_units = n + h[1] / kSegBytes + 64;
+  return CG_OK;
+}
+
 // Profile-guided residency: sample the batch, count level-1 state visits, renumber the states so the
 // most visited ones are the shared-memory resident ones, and overwrite the device tables in place (same sizes, same
 // pointers: a captured graph stays valid).  Results never depend on this, only how often the scan's slow path runs.
 int adapt_ruleset(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, cudaStream_t st) {
   rs->adapted = true;
   HostImage& H = rs->host;
+  if (n) { int rc = decide_segmentation(rs, d_off, n, st); if (rc) return rc; }
   if (H.pf.mode == 4 || !n || (uint32_t)H.pf.nstates <= H.hot_states) return CG_OK;      // everything is resident already
   if (getenv("CG_NO_ADAPT") && atoi(getenv("CG_NO_ADAPT"))) return CG_OK;
   const uint32_t ns = (uint32_t)H.pf.nstates, n_sample = std::min<uint32_t>(n, 8192);
@@ -155,8 +192,9 @@ int adapt_ruleset(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off,
 
 // head: scratch reset + level-1 scan; tail: confirm + verify + finalize.  Both asynchronous.
 int scan_head(cg_ruleset* rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words, bool spans, cudaStream_t st) {
-  CU(cudaMemsetAsync(w.counters, 0, 16 * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(w.counters, 0, kCounterWords * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(w.slot_of_msg, 0xff, (size_t)n * 4, st));
+  if (w.units) { int kk = launch_plan_units(w, d_off, n, st); G.launches += kk; G.stats.kernel_launches += kk; }
   if (G.profiling) cudaEventRecord(G.pev[0], st);
   int k = launch_scan(rs->dev, w, d_bytes, d_off, n, d_words, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[1], st);
@@ -216,12 +254,20 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
   slot_cap = std::max(slot_cap, rs->work.slot_cap); event_cap = std::max(event_cap, rs->work.event_cap); l1_cap = std::max(l1_cap, rs->work.l1_cap);
   hs->counters.assign(16, 0);
   if ((rc = join_pipeline(rs, st))) return rc;
+  {
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < n; i++) max_len = std::max(max_len, offsets[i + 1] - offsets[i]);
+    const bool seg = max_len > 2 * kSegBytes;
+    const uint32_t want = n + (uint32_t)(total / kSegBytes) + 64;
+    if (seg != rs->segmented || (seg && want > rs->want_units)) { CU(cudaStreamSynchronize(st)); rs->segmented = seg; rs->want_units = std::max(rs->want_units, want); }
+    if ((rc = ensure_units(rs, rs->work))) return rc;
+  }
   if (n && !rs->adapted && (rc = adapt_ruleset(rs, G.d_bytes, G.d_off32, n, st))) return rc;
   for (int attempt = 0; attempt < 10; attempt++) {
     if ((rc = ensure_work(rs, rs->work, std::max<uint32_t>(n, 1), l1_cap, slot_cap, event_cap, span_cap))) return rc;
     CU(cudaEventRecord(G.ev0, st));
     if (n) { if ((rc = run_scan_device(rs, G.d_bytes, G.d_off32, n, G.d_words, spans, st))) return rc; }
-    else CU(cudaMemsetAsync(rs->work.counters, 0, 64, st));
+    else CU(cudaMemsetAsync(rs->work.counters, 0, kCounterWords * sizeof(uint32_t), st));
     CU(cudaEventRecord(G.ev1, st));
     CU(cudaMemcpyAsync(hs->counters.data(), rs->work.counters, 64, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -483,9 +529,19 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   // which scratch set this batch uses: pipelined batches alternate between two
   const int idx = pipelined ? (int)(rs->seq & 1u) : 0;
   ScanWork& w = idx ? rs->work2 : rs->work;
-  const uint32_t want_l1 = std::max<uint32_t>(std::max<uint32_t>(4 * n, 1u << 16), w.l1_cap), want_slot = std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), w.slot_cap),
-                 want_ev = std::max<uint32_t>(std::max<uint32_t>(n, 4096), w.event_cap);
   int rc;
+  // did the previous batch overflow a queue?  (its counters were copied to pinned memory; the copy is normally long done)
+  if (rs->cnt_pending && cudaEventQuery(rs->e_cnt) == cudaSuccess) {
+    rs->cnt_pending = false;
+    const uint32_t* hc = rs->h_counters; const uint32_t flags = hc[3];
+    if (flags & ERR_L1_OVERFLOW) rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * hc[4], hc[4] + 65536));
+    if (flags & ERR_SLOT_OVERFLOW) rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096));
+    if (flags & ERR_EVENT_OVERFLOW) rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096));
+    if (flags & ERR_UNIT_OVERFLOW) rs->grow_units = std::max<uint32_t>(rs->grow_units, hc[16] + hc[16] / 8 + 64);
+  }
+  const uint32_t want_l1 = std::max(std::max<uint32_t>(std::max<uint32_t>(4 * n, 1u << 16), w.l1_cap), rs->grow_l1),
+                 want_slot = std::max(std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), w.slot_cap), rs->grow_slot),
+                 want_ev = std::max(std::max<uint32_t>(std::max<uint32_t>(n, 4096), w.event_cap), rs->grow_ev);
   if (n > w.msg_cap || want_l1 > w.l1_cap || want_slot > w.slot_cap || want_ev > w.event_cap || !w.counters || !w.spans) {
     // (re)allocation: nothing may still be using the old buffers
     CU(cudaStreamSynchronize(st)); if (rs->side) CU(cudaStreamSynchronize(rs->side));
@@ -495,6 +551,13 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   if (!rs->adapted) {
     if ((rc = join_pipeline(rs, st))) return rc;
     if ((rc = adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st))) return rc;
+  }
+  {
+    const bool want_tbl = rs->segmented && rs->host.pf.mode != 4;
+    if (want_tbl != (w.units != nullptr) || (want_tbl && w.unit_cap < std::max(rs->want_units, rs->grow_units))) {
+      CU(cudaStreamSynchronize(st)); if (rs->side) CU(cudaStreamSynchronize(rs->side));
+      if ((rc = ensure_units(rs, w))) return rc;
+    }
   }
   if (pipelined) {
     // Two batches in flight: the caller's stream runs scratch reset + scan of batch k, the side stream runs confirm +
@@ -520,7 +583,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   } else {
     // memset + scan + confirm + verify + finalize captured once per (arguments, capacities), then replayed:
     // one launch per step instead of seven, so the host never becomes the bottleneck
-    const uint32_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
+    const uint64_t caps[6] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap, w.unit_cap, (uint64_t)(uintptr_t)w.units};
     cg_ruleset::CachedGraph* hit = nullptr;
     for (auto& g : rs->graphs) if (g.exec && g.bytes == d_bytes && g.off == d_offsets && g.words == d_out_words && g.n == n && !memcmp(caps, g.caps, sizeof caps)) hit = &g;
     if (!hit) {
@@ -540,7 +603,15 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     CU(cudaGraphLaunch(hit->exec, st));
     G.launches += 5; G.stats.kernel_launches += 5;       // kernels inside the graph (scan, confirm, verify, finalize + optional large-VM)
   }
-  if (rc == CG_OK) { G.stats.messages_scanned += n; }
+  if (rc == CG_OK) {
+    G.stats.messages_scanned += n;
+    if (!rs->h_counters) { CU(cudaMallocHost((void**)&rs->h_counters, kCounterWords * 4)); CU(cudaEventCreateWithFlags(&rs->e_cnt, cudaEventDisableTiming)); }
+    if (!rs->cnt_pending) {                                 // (one mirror copy in flight at a time)
+      CU(cudaMemcpyAsync(rs->h_counters, w.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaEventRecord(rs->e_cnt, st));
+      rs->cnt_pending = true;
+    }
+  }
   return rc;
 }
 

@@ -42,7 +42,8 @@ struct DevRuleset {
 
 // Per-call scratch in HBM.  A "slot" is one message with at least one confirmed candidate.
 struct ScanWork {
-  uint32_t* counters;            // [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (level-1 accept events)
+  uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (level-1 accept events) [5]=verify cursor
+                                 //           [6]=slow-path entries [7..15]=debug [16]=n_units (segmented scans)
   uint32_t* l1_msg;              // [l1_cap] level-1 accept events queued by scan_kernel: message,
   uint32_t* l1_pos;              //          byte offset of the accepting byte inside the message,
   uint32_t* l1_sc;               //          state << 8 | column of the accepting transition (0xffffffff = "always" rules)
@@ -54,14 +55,23 @@ struct ScanWork {
   uint32_t* event_pos;           // [event_cap]  policy mode: message offset of the confirmed factor's first byte
   uint32_t* event_pre;           // [event_cap]  policy mode: max units of a match before that factor (0xffff = unbounded)
   uint32_t* spans;               // [span_cap * 6] msg, rule, start_byte, end_byte, start16, end16
-  uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap;
+  // Long messages are cut into units of kSegBytes (+ kSegWarm bytes of warm-up) so that every lane has about the same
+  // amount to walk: units[u] = (message, segment).  nullptr = one unit per message (short-message batches).
+  uint2* units;
+  uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap, unit_cap;
 };
 
-enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32 };
+enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32,
+                  ERR_UNIT_OVERFLOW = 64 /* not an error: the scan falls back to one unit per message */ };
+constexpr uint32_t kSegBytes = 1024, kSegWarm = 16;     // kSegWarm >= longest level-1 window - 1 (kMaxWindow = 8), multiple of 16
+constexpr uint32_t kCounterWords = 32;
 
 // launchers (all asynchronous on `stream`); return the number of kernels launched
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, bool want_spans, int sm_count, cudaStream_t stream);
+// unit table of a segmented scan (counters[16] = number of units) and the longest message of a batch
+int launch_plan_units(const ScanWork& w, const uint32_t* d_off, uint32_t n, cudaStream_t stream);
+int launch_max_len(const uint32_t* d_off, uint32_t n, uint32_t* d_out_max, cudaStream_t stream);
 // state visit histogram over n_sample evenly spaced messages (profile-guided residency)
 int launch_l1_profile(const DevRuleset& rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint32_t n_sample,
                       uint32_t* d_visits, cudaStream_t stream);

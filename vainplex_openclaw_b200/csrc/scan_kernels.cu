@@ -152,19 +152,29 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
     evn = 0;
     __syncwarp();
   };
-  const uint32_t ntiles = (n + 31u) / 32u;
+  // units: one per message, or (segmented scans) kSegBytes-sized pieces of long messages.  A piece other than the
+  // first starts kSegWarm bytes early in state 0 and reports nothing before its own first byte: the level-1 automaton
+  // is definite (its state depends on the last kMaxWindow - 1 bytes only), so by then it is in the true state.
+  const bool segmented = w.units != nullptr && !(w.counters[3] & ERR_UNIT_OVERFLOW);
+  const uint32_t n_units = segmented ? min(w.counters[16], w.unit_cap) : n;
+  const uint32_t ntiles = (n_units + 31u) / 32u;
   for (uint32_t tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
-    const uint32_t msg = tile * 32u + lane;
-    const bool valid = msg < n;
-    const uint32_t b = valid ? off[msg] : 0u, e = valid ? off[msg + 1] : 0u;
-    if (valid && rs.n_always) l1_push_one(w, msg, 0, kL1Always);
+    const uint32_t unit = tile * 32u + lane;
+    const bool valid = unit < n_units;
+    uint32_t msg = unit, seg = 0;
+    if (segmented && valid) { const uint2 un = w.units[unit]; msg = un.x; seg = un.y; }
+    const uint32_t mb = valid ? off[msg] : 0u, me = valid ? off[msg + 1] : 0u;      // the message; p - mb = event position
+    const uint32_t lo = seg * kSegBytes;                                            // first position this unit reports
+    const uint32_t b = seg ? mb + lo - kSegWarm : mb;                               // first byte walked
+    const uint32_t e = segmented ? min(me, mb + lo + kSegBytes) : me;
+    if (valid && rs.n_always && lo == 0) l1_push_one(w, msg, 0, kL1Always);
     uint32_t state = 0, p = b;
     // unaligned head: byte-wise on the full table
     uint32_t head_end = (b + 15u) & ~15u; if (head_end > e) head_end = e;
     for (; p < head_end; p++) {
       uint32_t col = l1_col(rs.mode, lut, bytes[p]);
       uint32_t ent = l1_full(rs, state, col);
-      if (ent & kAccept) l1_push_one(w, msg, p - b, (state << 8) | col);
+      if ((ent & kAccept) && p - mb >= lo) l1_push_one(w, msg, p - mb, (state << 8) | col);
       state = ent & kStateMask;
     }
     const uint32_t nch = (e - p) >> 4;
@@ -221,9 +231,9 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
               if (st < hot) nx = *reinterpret_cast<const uint16_t*>(tbl + st * stride + c2k);
               if (nx == hot) {
                 const uint32_t ent = l1_full(rs, st, c2k >> 1);
-                if (ent & kAccept) {
+                if ((ent & kAccept) && p + 4 * q + k - mb >= lo) {
 #pragma unroll
-                  for (int j = 0; j <= k; j++) if (cnt == (uint32_t)j) { ev_pos[j] = p + 4 * q + k - b; ev_sc[j] = (st << 8) | (c2k >> 1); }
+                  for (int j = 0; j <= k; j++) if (cnt == (uint32_t)j) { ev_pos[j] = p + 4 * q + k - mb; ev_sc[j] = (st << 8) | (c2k >> 1); }
                   cnt++;
                 }
                 nx = ent & kStateMask;
@@ -264,10 +274,10 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
     for (; p < e; p++) {
       uint32_t col = l1_col(rs.mode, lut, bytes[p]);
       uint32_t ent = l1_full(rs, state, col);
-      if (ent & kAccept) l1_push_one(w, msg, p - b, (state << 8) | col);
+      if ((ent & kAccept) && p - mb >= lo) l1_push_one(w, msg, p - mb, (state << 8) | col);
       state = ent & kStateMask;
     }
-    if (valid) words[msg] = 0ull;
+    if (valid && lo == 0) words[msg] = 0ull;
   }
   flush_events();
   if (lane == 0 && slow_entries) atomicAdd(&w.counters[6], slow_entries);
@@ -384,6 +394,36 @@ scan_fp_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, con
     bytewise(e);
     if (valid) words[msg] = 0ull;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// segmented scans: the unit table.  A message of len bytes becomes max(1, ceil(len / kSegBytes)) units; slots are
+// reserved with one atomic per warp (the order of units does not matter).  counters[16] = units needed; if that
+// exceeds unit_cap the scan falls back to one unit per message (ERR_UNIT_OVERFLOW) and the host grows the table.
+// ------------------------------------------------------------------------------------------
+__global__ void plan_units_kernel(ScanWork w, const uint32_t* __restrict__ off, uint32_t n) {
+  const uint32_t FULL = 0xffffffffu, lane = threadIdx.x & 31u;
+  for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const uint32_t msg = i0 + threadIdx.x;
+    uint32_t k = 0;
+    if (msg < n) { const uint32_t len = off[msg + 1] - off[msg]; k = len <= kSegBytes ? 1u : (len + kSegBytes - 1u) / kSegBytes; }
+    uint32_t incl = k;                                      // inclusive warp prefix sum
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    uint32_t base = 0;
+    if (lane == 0 && total) base = atomicAdd(&w.counters[16], total);
+    base = __shfl_sync(FULL, base, 0) + incl - k;
+    if (base + k > w.unit_cap) { if (k) atomicOr(&w.counters[3], ERR_UNIT_OVERFLOW); }
+    else for (uint32_t j = 0; j < k; j++) w.units[base + j] = make_uint2(msg, j);
+  }
+}
+__global__ void max_len_kernel(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, off[i + 1] - off[i]);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -617,12 +657,23 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   if (n == 0) return 0;
   size_t smem = rs.image_bytes;
   uint32_t ntiles = (n + 31) / 32, wpb = kScanThreads / 32;
-  uint32_t grid = (ntiles + wpb - 1) / wpb; if (grid > (uint32_t)sm_count) grid = sm_count;
+  uint32_t grid = (ntiles + wpb - 1) / wpb; if (grid > (uint32_t)sm_count || w.units) grid = sm_count;      // segmented: unit count is only known on the device
   if (rs.mode == 4) { scan_fp_kernel<<<std::min<uint32_t>((n + 32 * wpb - 1) / (32 * wpb), (uint32_t)sm_count), kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); return 1; }
   smem = ((smem + 127) & ~(size_t)127) + kScanStageBytes + kScanEvBytes;      // image + per warp: 2 KB staging buffer, event buffer
 #define CG_LAUNCH_SCAN(M) scan_kernel<M><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words)
   switch (rs.mode) { case 0: CG_LAUNCH_SCAN(0); break; case 2: CG_LAUNCH_SCAN(2); break; case 3: CG_LAUNCH_SCAN(3); break; default: CG_LAUNCH_SCAN(1); break; }
 #undef CG_LAUNCH_SCAN
+  return 1;
+}
+
+int launch_plan_units(const ScanWork& w, const uint32_t* d_off, uint32_t n, cudaStream_t stream) {
+  if (!n || !w.units) return 0;
+  plan_units_kernel<<<std::min<uint32_t>((n + 255) / 256, 1184u), 256, 0, stream>>>(w, d_off, n);
+  return 1;
+}
+int launch_max_len(const uint32_t* d_off, uint32_t n, uint32_t* d_out_max, cudaStream_t stream) {
+  if (!n) return 0;
+  max_len_kernel<<<std::min<uint32_t>((n + 255) / 256, 1184u), 256, 0, stream>>>(d_off, n, d_out_max);
   return 1;
 }
 
