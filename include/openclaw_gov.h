@@ -135,6 +135,18 @@ CG_API int cg_scan_one(cg_ruleset *rs, const uint8_t *bytes, uint32_t len, uint6
 CG_API int cg_find_matches_batch(cg_ruleset *rs, const uint8_t *bytes, const uint32_t *offsets, uint32_t n,
                                  cg_span *out_spans, uint32_t spans_cap, uint32_t *out_nspans);
 
+/* ---- redacted output of a batch: RedactionEngine.scanString (src/redaction/engine.ts:74-85) = findMatches +
+ * applyReplacements (engine.ts:165-181), every match replaced by the vault's default placeholder
+ * "[REDACTED:<category>:<first 8 hex digits of SHA-256(match)>]" (src/redaction/vault.ts:33-35,75-104).
+ *   out_bytes / out_offsets[n+1] : redacted messages, same packing as the input; *out_need = bytes needed
+ *   out_spans / out_digests32    : the resolved spans (as cg_find_matches_batch) and SHA-256 of each matched text, so that
+ *                                  the caller's vault can store the originals and detect the 2^-32 case in which two live
+ *                                  values share hash8 and vault.store switches to the 12-digit form (vault.ts:85-104).
+ * CG_ERR_CAPACITY when out_cap / spans_cap are too small (sizes in *out_need / *out_nspans). */
+CG_API int cg_redact_batch(cg_ruleset *rs, const uint8_t *bytes, const uint32_t *offsets, uint32_t n,
+                           uint8_t *out_bytes, uint64_t out_cap, uint64_t *out_need, uint32_t *out_offsets,
+                           cg_span *out_spans, uint32_t spans_cap, uint32_t *out_nspans, uint8_t *out_digests32);
+
 /* ---- device-resident variants (inputs/outputs already in HBM; used by bench.py `value` and by
  * callers that pipeline their own copies).  Pointers are CUDA device pointers; `stream` is a
  * cudaStream_t (NULL = the library's own stream); asynchronous w.r.t. the host.

@@ -274,6 +274,37 @@ def test_long_messages_are_cut_into_units(N, oracle):
     rs.close()
 
 
+def test_redact_batch_equals_oracle_splice(N, oracle):
+    """cg_redact_batch: findMatches + applyReplacements with [REDACTED:<category>:<hash8>] (engine.ts:165-181,
+    vault.ts:33-35), bytes and digests exact, on ragged UTF-8 messages."""
+    import hashlib
+    rl = W.make_rules(200)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    data_t, off_t, _ = W.make_messages(4000, 180, rl, p_hit=0.3, utf8_frac=0.15, seed=77)
+    buf = data_t.numpy()
+    off0 = off_t.numpy()
+    rng = np.random.default_rng(5)
+    msgs = [bytes(buf[int(off0[i]):int(off0[i]) + int(rng.integers(0, 181))]) for i in range(4000)]     # ragged, may cut a character
+    data, off = N.pack(msgs)
+    out, out_off, spans, dig = rs.redact_batch(data, off)
+    exp_spans = oracle_spans(oracle, rules, data, off)
+    got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+    assert got == exp_spans and len(got) >= 300
+    by_msg = {}
+    for s, d in zip(spans, dig):
+        m = msgs[int(s["msg"])][int(s["start_byte"]):int(s["end_byte"])]
+        assert bytes(d) == hashlib.sha256(m).digest()
+        by_msg.setdefault(int(s["msg"]), []).append((int(s["start_byte"]), int(s["end_byte"]), CATS[rules[int(s["rule"])][2]], bytes(d).hex()[:8]))
+    assert int(out_off[0]) == 0 and len(out) == int(out_off[-1])
+    for i, m in enumerate(msgs):
+        e = bytearray(m)
+        for a, b, cat, h8 in sorted(by_msg.get(i, []), reverse=True):                 # right to left, as applyReplacements
+            e[a:b] = ("[REDACTED:%s:%s]" % (cat, h8)).encode()
+        assert bytes(out[int(out_off[i]):int(out_off[i + 1])]) == bytes(e), i
+    rs.close()
+
+
 # ------------------------------------------------------------------------------ SHA-256 / Merkle
 
 def test_sha256_batch_equals_hashlib_and_oracle(N, oracle):

@@ -76,6 +76,26 @@ def test_vault_and_engine(P):
     assert vault.store(secret, "pii") == "[REDACTED:credential:%s]" % h8
 
 
+def test_batch_redaction_spliced_on_the_device(P):
+    """RedactionEngine.scan_strings (cg_redact_batch): same outputs, counts, categories and vault contents as the
+    per-string scan_string path, including multi-byte text around the matches and strings without any match."""
+    import json, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    vectors = json.load(open(os.path.join(here, "golden", "registry_vectors.json")))["vectors"]
+    inputs = [v["input"] for v in vectors][:120]
+    inputs += ["", "nothing to see", "päss ✓ sk-" + "b" * 24 + " ünd 😀 bob@example.com 😀", "x" * 3000 + " ghp_" + "q" * 36 + " " + "y" * 3000]
+    cats = ["credential", "pii", "financial"]
+    v1, v2 = P.RedactionVault(), P.RedactionVault()
+    e1, e2 = P.RedactionEngine(P.PatternRegistry(cats), v1), P.RedactionEngine(P.PatternRegistry(cats), v2)
+    one = [e1.scan_string(s) for s in inputs]
+    many = e2.scan_strings(inputs)
+    assert sum(r["redactionCount"] for r in one) >= 60
+    for s, a, b in zip(inputs, one, many):
+        assert a["output"] == b["output"], s
+        assert a["redactionCount"] == b["redactionCount"] and a["categories"] == b["categories"]
+        assert v2.resolve_all(b["output"])["resolved"] == v1.resolve_all(a["output"])["resolved"] == s
+
+
 def test_matches_any_and_policy(P):
     assert P.matches_any("secret\\d+", ["my secret42"])
     assert not P.matches_any("secret\\d+", ["my secret"])

@@ -48,7 +48,7 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
                        ("start16", np.uint32), ("end16", np.uint32)])
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
-           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt", "cg_scan_join",
+           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt", "cg_scan_join", "cg_redact_batch",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -84,6 +84,7 @@ def load():
     L.cg_scan_work_counters.argtypes = [vp, vp]; L.cg_scan_work_counters.restype = i32
     L.cg_ruleset_adapt.argtypes = [vp, vp, vp, u32, vp]; L.cg_ruleset_adapt.restype = i32
     L.cg_scan_join.argtypes = [vp, vp]; L.cg_scan_join.restype = i32
+    L.cg_redact_batch.argtypes = [vp, vp, vp, u32, vp, u64, vp, vp, vp, u32, vp, vp]; L.cg_redact_batch.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
     L.cg_ruleset_destroy.argtypes = [vp]; L.cg_ruleset_destroy.restype = None
     L.cg_ruleset_get_info.argtypes = [vp, C.POINTER(cg_ruleset_info)]; L.cg_ruleset_get_info.restype = i32
@@ -201,6 +202,26 @@ class Ruleset:
                 continue
             check(rc)
             return spans[:ns.value]
+
+    def redact_batch(self, data: np.ndarray, off: np.ndarray):
+        """RedactionEngine.scanString for a batch, spliced on the device.
+        -> (out_bytes uint8[..], out_offsets uint32[n+1], resolved spans, digests uint8[ns, 32])"""
+        n = len(off) - 1
+        total = int(off[n]) if n else 0
+        out_off = np.zeros(n + 1, dtype=np.uint32)
+        need, ns = C.c_uint64(0), C.c_uint32(0)
+        cap_bytes, cap_spans = total + 4096, 1024
+        while True:
+            out = np.zeros(cap_bytes + 64, dtype=np.uint8)
+            spans = np.zeros(cap_spans, dtype=SPAN_DTYPE)
+            dig = np.zeros((cap_spans, 32), dtype=np.uint8)
+            rc = load().cg_redact_batch(self.handle, data.ctypes.data, off.ctypes.data, n, out.ctypes.data, cap_bytes, C.byref(need),
+                                        out_off.ctypes.data, spans.ctypes.data, cap_spans, C.byref(ns), dig.ctypes.data)
+            if rc == CG_ERR_CAPACITY and (need.value > cap_bytes or ns.value > cap_spans):
+                cap_bytes, cap_spans = max(cap_bytes, need.value), max(cap_spans, ns.value)
+                continue
+            check(rc)
+            return out[:need.value], out_off, spans[:ns.value], dig[:ns.value]
 
     def work_counters(self):
         """(slots, VM pairs, spans, error flags, level-1 events, 0, slow-path warp entries, 0) of the last completed step."""

@@ -479,8 +479,9 @@ int cg_scan_one(cg_ruleset* rs, const uint8_t* bytes, uint32_t len, uint64_t* ou
   return rc;
 }
 
-int cg_find_matches_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, cg_span* out_spans, uint32_t spans_cap, uint32_t* out_nspans) {
-  std::lock_guard<std::mutex> lk(g_mu);
+namespace {
+// findMatches + resolveOverlaps for a batch: resolved spans sorted by (msg, start).  Leaves the input in G.d_bytes / G.d_off32.
+int find_matches_resolved(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, std::vector<cg_span>* out) {
   HostScan hs;
   int rc = scan_host(rs, bytes, offsets, n, true, &hs);
   if (rc) return rc;
@@ -496,7 +497,7 @@ int cg_find_matches_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* 
     return a.start16 < b.start16;
   });
   // resolveOverlaps (registry.ts:288-316): stable sort by start asc, length desc, category order; greedy keep
-  uint32_t outn = 0;
+  out->clear();
   for (size_t i = 0; i < raw.size();) {
     size_t j = i; while (j < raw.size() && raw[j].msg == raw[i].msg) j++;
     std::stable_sort(raw.begin() + i, raw.begin() + j, [&](const cg_span& a, const cg_span& b) {
@@ -506,12 +507,74 @@ int cg_find_matches_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* 
       return cat[a.rule] < cat[b.rule];
     });
     int64_t last_end = -1;
-    for (size_t k = i; k < j; k++) if ((int64_t)raw[k].start16 >= last_end) { if (out_spans && outn < spans_cap) out_spans[outn] = raw[k]; outn++; last_end = raw[k].end16; }
+    for (size_t k = i; k < j; k++) if ((int64_t)raw[k].start16 >= last_end) { out->push_back(raw[k]); last_end = raw[k].end16; }
     i = j;
   }
+  G.stats.spans += out->size();
+  return CG_OK;
+}
+}  // namespace
+
+int cg_find_matches_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, cg_span* out_spans, uint32_t spans_cap, uint32_t* out_nspans) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::vector<cg_span> res;
+  int rc = find_matches_resolved(rs, bytes, offsets, n, &res);
+  if (rc) return rc;
+  const uint32_t outn = (uint32_t)res.size();
+  if (out_spans) memcpy(out_spans, res.data(), (size_t)std::min(outn, spans_cap) * sizeof(cg_span));
   if (out_nspans) *out_nspans = outn;
-  G.stats.spans += outn;
   if (out_spans && outn > spans_cap) return fail(CG_ERR_CAPACITY, "out_spans too small");
+  return CG_OK;
+}
+
+int cg_redact_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint8_t* out_bytes, uint64_t out_cap,
+                    uint64_t* out_need, uint32_t* out_offsets, cg_span* out_spans, uint32_t spans_cap, uint32_t* out_nspans, uint8_t* out_digests32) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out_offsets || (n && (!bytes || !offsets))) return fail(CG_ERR_INVALID_ARG, "null argument");
+  std::vector<cg_span> res;
+  int rc = find_matches_resolved(rs, bytes, offsets, n, &res);            // input bytes / offsets stay in G.d_bytes / G.d_off32
+  if (rc) return rc;
+  const uint32_t ns = (uint32_t)res.size();
+  static const uint32_t kCatLen[4] = {10, 9, 3, 6};                         // credential, financial, pii, custom
+  // host: output offsets and the per-message span index (O(n + spans)); device: digests and the splice itself
+  std::vector<uint32_t> span_begin((size_t)n + 1), span_start(ns), span_len(ns), span_cat(ns);
+  uint64_t pos = 0; uint32_t k = 0;
+  for (uint32_t m = 0; m < n; m++) {
+    span_begin[m] = k; out_offsets[m] = (uint32_t)pos;
+    uint64_t len = offsets[m + 1] - offsets[m];
+    for (; k < ns && res[k].msg == m; k++) {
+      span_start[k] = offsets[m] + res[k].start_byte; span_len[k] = res[k].end_byte - res[k].start_byte; span_cat[k] = rs->category[res[k].rule] & 3u;
+      len = len - span_len[k] + 20u + kCatLen[span_cat[k]];
+    }
+    pos += len;
+  }
+  span_begin[n] = k; out_offsets[n] = (uint32_t)pos;
+  if (out_need) *out_need = pos;
+  if (out_nspans) *out_nspans = ns;
+  if (pos >> 32) return fail(CG_ERR_TOO_LARGE, "redacted batch exceeds 4 GiB");
+  if ((out_spans && ns > spans_cap) || pos > out_cap || !out_bytes) return fail(CG_ERR_CAPACITY, "output buffer too small (see *out_need / *out_nspans)");
+  if (out_spans) memcpy(out_spans, res.data(), (size_t)ns * sizeof(cg_span));
+  cudaStream_t st = G.stream;
+  static uint8_t* d_out = nullptr; static size_t cap_out = 0; static uint32_t* d_meta = nullptr; static size_t cap_meta = 0;
+  if ((rc = grow(&d_out, &cap_out, (size_t)pos + 64))) return rc;
+  const size_t meta_words = 2 * ((size_t)n + 1) + 3 * (size_t)ns + 8 * (size_t)ns + 16;
+  if ((rc = grow(&d_meta, &cap_meta, meta_words))) return rc;
+  uint32_t* d_out_off = d_meta; uint32_t* d_span_begin = d_out_off + n + 1; uint32_t* d_start = d_span_begin + n + 1;
+  uint32_t* d_len = d_start + ns; uint32_t* d_cat = d_len + ns; uint32_t* d_dig = d_cat + ns; d_dig += (8 - ((d_dig - d_meta) & 7)) & 7;   // 32-byte aligned digests
+  CU(cudaMemcpyAsync(d_out_off, out_offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_span_begin, span_begin.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (ns) {
+    CU(cudaMemcpyAsync(d_start, span_start.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_len, span_len.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_cat, span_cat.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+  }
+  int kl = launch_redact_digests(G.d_bytes, d_start, d_len, ns, d_dig, st);
+  kl += launch_redact_splice(G.d_bytes, G.d_off32, d_out_off, d_span_begin, d_start, d_len, d_cat, d_dig, d_out, n, G.sm_count, st);
+  G.launches += kl; G.stats.kernel_launches += kl; G.stats.sha256_items += ns;
+  CU(cudaGetLastError());
+  if (pos) CU(cudaMemcpyAsync(out_bytes, d_out, (size_t)pos, cudaMemcpyDeviceToHost, st));
+  if (ns && out_digests32) CU(cudaMemcpyAsync(out_digests32, d_dig, (size_t)ns * 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return CG_OK;
 }
 

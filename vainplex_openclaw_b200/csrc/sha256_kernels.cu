@@ -7,6 +7,7 @@
 //   leaf = SHA-256(0x00 || bytes), node = SHA-256(0x01 || L || R), unpaired node promoted.
 // All 64 rounds run in registers; digests are stored in HBM as the canonical 32 big-endian bytes.
 #include "kernels.h"
+#include <algorithm>
 
 namespace cg {
 
@@ -177,6 +178,75 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const uint32_t* __res
     reinterpret_cast<uint4*>(out + 8 * i)[0] = reinterpret_cast<const uint4*>(in + 16 * i)[0];
     reinterpret_cast<uint4*>(out + 8 * i)[1] = reinterpret_cast<const uint4*>(in + 16 * i)[1];
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// redacted-output assembly (RedactionEngine.applyReplacements, engine.ts:165-181, with the vault's placeholder
+// "[REDACTED:<category>:<first 8 hex digits of SHA-256(match)>]", vault.ts:33-35,75-104)
+// ------------------------------------------------------------------------------------------
+// SHA-256 of every matched text: span i = bytes[start[i], start[i] + len[i])
+__global__ void __launch_bounds__(128) redact_digest_kernel(const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ start,
+                                                             const uint32_t* __restrict__ len, uint32_t ns, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  uint32_t h[8];
+  sha_bytes(-1, bytes + start[i], len[i], h);
+  store_digest(out + (size_t)i * 8, h);
+}
+
+__constant__ char kCatName[4][12] = {"credential", "financial", "pii", "custom"};       // CATEGORY_ORDER, registry.ts:17-22
+__constant__ uint8_t kCatLen[4] = {10, 9, 3, 6};
+
+// One warp per message: the text between spans is copied, every span is replaced by its placeholder.
+// span_begin[msg] .. span_begin[msg+1] index the (position-sorted, non-overlapping) spans of the message.
+__global__ void __launch_bounds__(256) redact_splice_kernel(const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off,
+                                                             const uint32_t* __restrict__ out_off, const uint32_t* __restrict__ span_begin,
+                                                             const uint32_t* __restrict__ span_start, const uint32_t* __restrict__ span_len,
+                                                             const uint32_t* __restrict__ span_cat, const uint32_t* __restrict__ digests,
+                                                             uint8_t* __restrict__ out, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
+  for (uint32_t msg = blockIdx.x * wpb + (threadIdx.x >> 5); msg < n; msg += gridDim.x * wpb) {
+    const uint32_t b = off[msg], e = off[msg + 1];
+    uint32_t src = b, dst = out_off[msg];
+    for (uint32_t k = span_begin[msg], ke = span_begin[msg + 1]; k <= ke; k++) {
+      const uint32_t stop = k < ke ? span_start[k] : e;          // copy bytes[src, stop)
+      for (uint32_t i = lane; i < stop - src; i += 32u) out[dst + i] = bytes[src + i];
+      dst += stop - src;
+      if (k == ke) break;
+      const uint32_t cat = span_cat[k] & 3u, cl = kCatLen[cat];
+      // "[REDACTED:" cat ":" hhhhhhhh "]"   = 10 + cl + 1 + 8 + 1 bytes, one byte per lane
+      const uint32_t plen = 20u + cl;
+      if (lane < plen) {
+        uint8_t ch;
+        if (lane < 10u) ch = (uint8_t)"[REDACTED:"[lane];
+        else if (lane < 10u + cl) ch = (uint8_t)kCatName[cat][lane - 10u];
+        else if (lane == 10u + cl) ch = ':';
+        else if (lane < 19u + cl) {
+          const uint32_t d = lane - (11u + cl);                   // hex digit 0..7 of the digest (bytes 0..3)
+          const uint32_t word = digests[(size_t)k * 8];           // stored big-endian byte order in memory: byte j = (word >> 8j) & 0xff
+          const uint32_t byte = (word >> (8u * (d >> 1))) & 0xffu, nib = (d & 1u) ? (byte & 15u) : (byte >> 4);
+          ch = (uint8_t)(nib < 10u ? '0' + nib : 'a' + nib - 10u);
+        } else ch = ']';
+        out[dst + lane] = ch;
+      }
+      dst += plen;
+      src = span_start[k] + span_len[k];
+    }
+  }
+}
+
+int launch_redact_digests(const uint8_t* d_bytes, const uint32_t* d_start, const uint32_t* d_len, uint32_t ns, uint32_t* d_out, cudaStream_t stream) {
+  if (!ns) return 0;
+  redact_digest_kernel<<<(ns + 127) / 128, 128, 0, stream>>>(d_bytes, d_start, d_len, ns, d_out);
+  return 1;
+}
+int launch_redact_splice(const uint8_t* d_bytes, const uint32_t* d_off, const uint32_t* d_out_off, const uint32_t* d_span_begin,
+                         const uint32_t* d_span_start, const uint32_t* d_span_len, const uint32_t* d_span_cat, const uint32_t* d_digests,
+                         uint8_t* d_out, uint32_t n, int sm_count, cudaStream_t stream) {
+  if (!n) return 0;
+  const uint32_t grid = std::min<uint32_t>((n + 7) / 8, (uint32_t)sm_count * 8u);
+  redact_splice_kernel<<<grid, 256, 0, stream>>>(d_bytes, d_off, d_out_off, d_span_begin, d_span_start, d_span_len, d_span_cat, d_digests, d_out, n);
+  return 1;
 }
 
 int launch_sha256_batch(const uint8_t* d_bytes, const uint64_t* d_off, uint32_t n, uint8_t* d_out, cudaStream_t stream) {

@@ -258,6 +258,36 @@ class RedactionEngine:
                 pass
         return self._redact_string(value, cats, count)
 
+    def scan_strings(self, inputs: Sequence[str]) -> List[dict]:
+        """scanString (engine.ts:74-85) for many strings with the splice done on the device (cg_redact_batch): matches,
+        SHA-256 of every match and the redacted text come back from one call; the vault learns the originals here.
+        A string whose placeholder the vault would issue in its 12-digit form (another live value shares hash8,
+        vault.ts:85-104) is re-spliced on the host."""
+        rs = self.registry._rs()
+        if rs is None or not inputs:
+            return [{"output": s, "redactionCount": 0, "categories": set()} for s in inputs]
+        data, off = N.pack([N.js_utf8(s) for s in inputs])
+        out, out_off, spans, digests = rs.redact_batch(data, off)
+        res = [{"output": s, "redactionCount": 0, "categories": set()} for s in inputs]
+        by_msg: Dict[int, list] = {}
+        for sp, dg in zip(spans, digests):
+            by_msg.setdefault(int(sp["msg"]), []).append((sp, bytes(dg).hex()))
+        for m, lst in by_msg.items():
+            s = inputs[m]
+            short = True
+            for sp, h in reversed(lst):                          # vault.store order of applyReplacements: last match first
+                cat = self.registry.patterns[int(sp["rule"])]["category"]
+                ph = self.vault.store(_slice16(s, int(sp["start16"]), int(sp["end16"])), cat, h)
+                short = short and ph == "[REDACTED:%s:%s]" % (cat, h[:8])
+                res[m]["redactionCount"] += 1
+                res[m]["categories"].add(cat)
+            if short:
+                res[m]["output"] = bytes(out[int(out_off[m]):int(out_off[m + 1])]).decode("utf-8", "surrogatepass")
+            else:
+                cats, count = set(), [0]
+                res[m]["output"] = self._redact_string(s, cats, count)
+        return res
+
     def _redact_string(self, input: str, cats, count) -> str:
         matches = self.registry.find_matches(input)
         if not matches:
