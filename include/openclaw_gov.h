@@ -193,6 +193,26 @@ CG_API int cg_merkle_block_roots_device(const void *d_bytes, uint64_t leaf_len, 
 CG_API int cg_merkle_fold(const uint8_t *nodes32, uint64_t m, uint8_t out_root[32]);
 CG_API int cg_merkle_fold_device(const void *d_nodes32, uint64_t m, void *d_out_root32, void *stream);
 
+/* ---- append-only Merkle log over the event log (audit JSONL lines of src/audit-trail.ts:151-179
+ * as leaves, same convention as cg_merkle_root).  The log keeps the *frontier* -- the root of one perfect subtree per
+ * set bit of its size, at most 64 digests -- so that appending a batch costs O(batch) and the state that has to be
+ * persisted next to the YYYY-MM-DD.jsonl file is a few hundred bytes.  With keep_leaf_digests the leaf digests stay
+ * in HBM (32 bytes per leaf) and RFC 6962 audit paths can be produced.  No counterpart in the reference. */
+typedef struct cg_merkle_log cg_merkle_log;
+CG_API int cg_merkle_log_create(cg_merkle_log **out, int keep_leaf_digests);
+CG_API void cg_merkle_log_destroy(cg_merkle_log *log);
+CG_API int cg_merkle_log_append(cg_merkle_log *log, const uint8_t *bytes, const uint64_t *offsets, uint64_t n);   /* host buffers */
+CG_API int cg_merkle_log_size(const cg_merkle_log *log, uint64_t *out_n);
+CG_API int cg_merkle_log_root(cg_merkle_log *log, uint8_t out_root[32]);      /* == cg_merkle_root over every leaf appended so far */
+/* frontier: one digest per set bit of the size, largest subtree first; restore() resumes a log from it (no proofs) */
+CG_API int cg_merkle_log_frontier(cg_merkle_log *log, uint8_t *out_frontier32, uint32_t *out_count);
+CG_API int cg_merkle_log_restore(cg_merkle_log **out, uint64_t n, const uint8_t *frontier32, uint32_t count);
+/* RFC 6962 2.1.1 audit path of leaf `index` in the current tree (leaf level first); needs keep_leaf_digests */
+CG_API int cg_merkle_log_proof(cg_merkle_log *log, uint64_t index, uint8_t *out_path32, uint32_t path_cap, uint32_t *out_len);
+/* RFC 9162 2.1.3.2: *out_ok = 1 iff `path` proves that leaf_bytes is entry `index` of the tree of tree_size leaves with this root */
+CG_API int cg_merkle_verify_proof(const uint8_t *leaf_bytes, uint64_t leaf_len, uint64_t index, uint64_t tree_size,
+                                  const uint8_t *path32, uint32_t path_len, const uint8_t root[32], int *out_ok);
+
 #ifdef __cplusplus
 }
 #endif

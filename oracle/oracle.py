@@ -292,3 +292,61 @@ def merkle_fold(nodes: np.ndarray) -> bytes:
     out = np.zeros(32, dtype=np.uint8)
     lib().oracle_merkle_fold(buf.ctypes.data, buf.shape[0], out.ctypes.data)
     return out.tobytes()
+
+
+# ---------------------------------------------------------------- Merkle log: audit paths (RFC 6962 2.1.1 / RFC 9162 2.1.3.2)
+# Restated from the RFC text on top of the oracle's own SHA-256; small inputs only (pure Python recursion).
+
+def merkle_leaf_hash(leaf: bytes) -> bytes:
+    return sha256(b"\x00" + leaf)
+
+
+def merkle_node_hash(left: bytes, right: bytes) -> bytes:
+    return sha256(b"\x01" + left + right)
+
+
+def _mth(hashes):
+    """MTH over a list of leaf hashes, RFC 6962 2.1: split at the largest power of two smaller than n."""
+    n = len(hashes)
+    if n == 1:
+        return hashes[0]
+    k = 1
+    while k * 2 < n:
+        k *= 2
+    return merkle_node_hash(_mth(hashes[:k]), _mth(hashes[k:]))
+
+
+def merkle_audit_path(leaves, index: int):
+    """PATH(m, D[n]) of RFC 6962 2.1.1 (leaf level first)."""
+    def path(m, hs):
+        n = len(hs)
+        if n == 1:
+            return []
+        k = 1
+        while k * 2 < n:
+            k *= 2
+        if m < k:
+            return path(m, hs[:k]) + [_mth(hs[k:])]
+        return path(m - k, hs[k:]) + [_mth(hs[:k])]
+    return path(index, [merkle_leaf_hash(x) for x in leaves])
+
+
+def merkle_verify_path(leaf: bytes, index: int, tree_size: int, path, root: bytes) -> bool:
+    """RFC 9162 2.1.3.2."""
+    if index >= tree_size:
+        return False
+    fn, sn, r = index, tree_size - 1, merkle_leaf_hash(leaf)
+    for p in path:
+        if sn == 0:
+            return False
+        if (fn & 1) or fn == sn:
+            r = merkle_node_hash(p, r)
+            if not (fn & 1):
+                while not (fn & 1) and fn != 0:
+                    fn >>= 1
+                    sn >>= 1
+        else:
+            r = merkle_node_hash(r, p)
+        fn >>= 1
+        sn >>= 1
+    return sn == 0 and r == root

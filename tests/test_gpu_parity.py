@@ -345,3 +345,46 @@ def test_merkle_fold_of_block_roots(N, oracle):
         e = min(n, s + (1 << k))
         roots.append(np.frombuffer(N.merkle_root_fixed(data[s * leaf:], leaf, e - s), dtype=np.uint8))
     assert N.merkle_fold(np.stack(roots)) == oracle.merkle_root_fixed(data, leaf, n)
+
+
+def test_merkle_log_append_frontier_and_proofs(N, oracle):
+    """Append-only log: the root after every append equals the one-shot tree over all leaves so far (device and oracle),
+    the persisted frontier resumes the log, and RFC 6962 audit paths equal the oracle's and verify (RFC 9162 2.1.3.2)."""
+    rng = np.random.default_rng(2024)
+    leaves = [bytes(rng.integers(0, 256, int(rng.integers(0, 300)), dtype=np.uint8)) for _ in range(2500)]
+    log = N.MerkleLog(keep_leaf_digests=True)
+    assert log.root() == hashlib.sha256(b"").digest() and log.size() == 0
+    done = 0
+    for chunk in [1, 1, 2, 3, 5, 64, 63, 1, 256, 700, 1, 1000, 403]:
+        log.append(leaves[done:done + chunk]); done += chunk
+        data, off = N.pack(leaves[:done])
+        assert log.size() == done
+        assert log.root() == oracle.merkle_root(data, off.astype(np.uint64)) == N.merkle_root(data, off.astype(np.uint64))
+        assert len(log.frontier()) == bin(done).count("1")
+    assert done == 2500
+    root = log.root()
+    # persisted frontier -> resumed log keeps producing the same roots
+    resumed = N.MerkleLog.restore(done, log.frontier())
+    extra = [b"event-%d" % i for i in range(37)]
+    log.append(extra); resumed.append(extra)
+    assert resumed.root() == log.root() and resumed.size() == done + 37
+    all_leaves = leaves + extra
+    root2 = log.root()
+    small = all_leaves[:77]                                  # the pure-Python oracle paths are for small trees
+    slog = N.MerkleLog()
+    slog.append(small)
+    sroot = slog.root()
+    for i in [0, 1, 31, 32, 63, 64, 75, 76]:
+        p = slog.proof(i)
+        assert p == oracle.merkle_audit_path(small, i)
+        assert oracle.merkle_verify_path(small[i], i, len(small), p, sroot) and N.merkle_verify_proof(small[i], i, len(small), p, sroot)
+    for i in [0, 1, 1234, 2047, 2048, 2499, 2500, 2536]:
+        p = log.proof(i)
+        assert oracle.merkle_verify_path(all_leaves[i], i, len(all_leaves), p, root2)
+        assert N.merkle_verify_proof(all_leaves[i], i, len(all_leaves), p, root2)
+        assert not N.merkle_verify_proof(all_leaves[i] + b"x", i, len(all_leaves), p, root2)
+        assert not N.merkle_verify_proof(all_leaves[i], i, len(all_leaves), p, root)          # an older root
+        if p:
+            assert not N.merkle_verify_proof(all_leaves[i], i ^ 1, len(all_leaves), p, root2)
+    for lg in (log, resumed, slog):
+        lg.close()

@@ -197,3 +197,25 @@ def test_python_re_agrees_on_builtins(oracle):
             s = m.decode("utf-8", "replace")
             exp += [(mi, 0, x.start(), x.end()) for x in py.finditer(s)]
         assert [tuple(x) for x in got.tolist()] == exp, r["id"]
+
+
+def test_merkle_audit_paths_of_the_oracle(oracle):
+    """RFC 6962 2.1.1 paths restated in the oracle verify against the oracle's root for every leaf of every tree size
+    1..40 (RFC 9162 2.1.3.2), have the expected lengths, and reject a wrong leaf / index / size."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    leaves = [bytes(rng.integers(0, 256, int(rng.integers(0, 90)), dtype=np.uint8)) for _ in range(40)]
+    for n in range(1, 41):
+        ls = leaves[:n]
+        off = np.zeros(n + 1, dtype=np.uint64); off[1:] = np.cumsum([len(x) for x in ls])
+        data = np.frombuffer(b"".join(ls) + b"\0" * 64, dtype=np.uint8).copy()
+        root = oracle.merkle_root(data, off)
+        assert root == oracle.merkle_root_rfc6962(data, off)
+        for i in range(n):
+            p = oracle.merkle_audit_path(ls, i)
+            assert len(p) <= max(1, (n - 1).bit_length())
+            assert oracle.merkle_verify_path(ls[i], i, n, p, root)
+            assert not oracle.merkle_verify_path(ls[i] + b"!", i, n, p, root)
+            if n > 1:
+                assert not oracle.merkle_verify_path(ls[i], (i + 1) % n, n, p, root) or ls[i] == ls[(i + 1) % n]
+                assert not oracle.merkle_verify_path(ls[i], i, n + 1, p, root)

@@ -49,6 +49,8 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
            "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt", "cg_scan_join", "cg_redact_batch",
+           "cg_merkle_log_create", "cg_merkle_log_destroy", "cg_merkle_log_append", "cg_merkle_log_size", "cg_merkle_log_root",
+           "cg_merkle_log_frontier", "cg_merkle_log_restore", "cg_merkle_log_proof", "cg_merkle_verify_proof",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -85,6 +87,15 @@ def load():
     L.cg_ruleset_adapt.argtypes = [vp, vp, vp, u32, vp]; L.cg_ruleset_adapt.restype = i32
     L.cg_scan_join.argtypes = [vp, vp]; L.cg_scan_join.restype = i32
     L.cg_redact_batch.argtypes = [vp, vp, vp, u32, vp, u64, vp, vp, vp, u32, vp, vp]; L.cg_redact_batch.restype = i32
+    L.cg_merkle_log_create.argtypes = [vp, i32]; L.cg_merkle_log_create.restype = i32
+    L.cg_merkle_log_destroy.argtypes = [vp]; L.cg_merkle_log_destroy.restype = None
+    L.cg_merkle_log_append.argtypes = [vp, vp, vp, u64]; L.cg_merkle_log_append.restype = i32
+    L.cg_merkle_log_size.argtypes = [vp, vp]; L.cg_merkle_log_size.restype = i32
+    L.cg_merkle_log_root.argtypes = [vp, vp]; L.cg_merkle_log_root.restype = i32
+    L.cg_merkle_log_frontier.argtypes = [vp, vp, vp]; L.cg_merkle_log_frontier.restype = i32
+    L.cg_merkle_log_restore.argtypes = [vp, u64, vp, u32]; L.cg_merkle_log_restore.restype = i32
+    L.cg_merkle_log_proof.argtypes = [vp, u64, vp, u32, vp]; L.cg_merkle_log_proof.restype = i32
+    L.cg_merkle_verify_proof.argtypes = [vp, u64, u64, u64, vp, u32, vp, vp]; L.cg_merkle_verify_proof.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
     L.cg_ruleset_destroy.argtypes = [vp]; L.cg_ruleset_destroy.restype = None
     L.cg_ruleset_get_info.argtypes = [vp, C.POINTER(cg_ruleset_info)]; L.cg_ruleset_get_info.restype = i32
@@ -294,3 +305,67 @@ def last_kernel_ms():
 
 def launch_count() -> int:
     return int(load().cg_launch_count())
+
+
+class MerkleLog:
+    """cg_merkle_log: append-only Merkle tree over event-log leaves (frontier state, optional audit paths)."""
+
+    def __init__(self, keep_leaf_digests: bool = True, _handle=None):
+        if _handle is not None:
+            self.handle = _handle
+            return
+        h = C.c_void_p()
+        check(load().cg_merkle_log_create(C.byref(h), 1 if keep_leaf_digests else 0))
+        self.handle = h
+
+    @classmethod
+    def restore(cls, n: int, frontier: np.ndarray):
+        f = np.ascontiguousarray(frontier, dtype=np.uint8)
+        h = C.c_void_p()
+        check(load().cg_merkle_log_restore(C.byref(h), n, f.ctypes.data, f.shape[0] if f.size else 0))
+        return cls(_handle=h)
+
+    def append(self, leaves):
+        """leaves: list of bytes."""
+        if not leaves:
+            return
+        off = np.zeros(len(leaves) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in leaves])
+        data = np.frombuffer(b"".join(leaves) + b"\0" * 64, dtype=np.uint8).copy()
+        check(load().cg_merkle_log_append(self.handle, data.ctypes.data, off.ctypes.data, len(leaves)))
+
+    def size(self) -> int:
+        n = C.c_uint64(0)
+        check(load().cg_merkle_log_size(self.handle, C.byref(n)))
+        return n.value
+
+    def root(self) -> bytes:
+        out = np.zeros(32, dtype=np.uint8)
+        check(load().cg_merkle_log_root(self.handle, out.ctypes.data))
+        return out.tobytes()
+
+    def frontier(self) -> np.ndarray:
+        out = np.zeros((64, 32), dtype=np.uint8)
+        k = C.c_uint32(0)
+        check(load().cg_merkle_log_frontier(self.handle, out.ctypes.data, C.byref(k)))
+        return out[:k.value].copy()
+
+    def proof(self, index: int):
+        out = np.zeros((64, 32), dtype=np.uint8)
+        k = C.c_uint32(0)
+        check(load().cg_merkle_log_proof(self.handle, index, out.ctypes.data, 64, C.byref(k)))
+        return [out[i].tobytes() for i in range(k.value)]
+
+    def close(self):
+        if self.handle:
+            load().cg_merkle_log_destroy(self.handle)
+            self.handle = None
+
+
+def merkle_verify_proof(leaf: bytes, index: int, tree_size: int, path, root: bytes) -> bool:
+    p = np.frombuffer(b"".join(path) + b"\0" * 32, dtype=np.uint8).copy()
+    lb = np.frombuffer(leaf + b"\0", dtype=np.uint8).copy()
+    r = np.frombuffer(root, dtype=np.uint8).copy()
+    ok = C.c_int(0)
+    check(load().cg_merkle_verify_proof(lb.ctypes.data, len(leaf), index, tree_size, p.ctypes.data, len(path), r.ctypes.data, C.byref(ok)))
+    return bool(ok.value)

@@ -810,6 +810,201 @@ int cg_merkle_block_roots_device(const void* d_bytes, uint64_t leaf_len, uint64_
   return CG_OK;
 }
 
+// ---------------------------------------------------------------------------------- Merkle log (append, frontier, proofs)
+struct cg_merkle_log {
+  uint64_t n = 0;                 // leaves so far; bit h of n set <=> slot h holds the root of a perfect 2^h subtree
+  bool keep = false;              // keep every leaf digest in HBM (needed for inclusion proofs)
+  uint32_t* d_slots = nullptr;    // 64 x 8 words
+  uint32_t* d_tmp = nullptr;      // 66 x 8 words: [0..63] gathered left operands, [64] accumulator, [65] result
+  uint32_t* d_leaves = nullptr; uint64_t cap_leaves = 0;     // keep: n leaf digests
+  uint32_t* d_new = nullptr; size_t cap_new = 0;             // !keep: the current batch's leaf digests
+  uint32_t* d_a = nullptr; size_t cap_a = 0; uint32_t* d_b = nullptr; size_t cap_b = 0;   // level ping-pong
+  ~cg_merkle_log() { cudaFree(d_slots); cudaFree(d_tmp); cudaFree(d_leaves); cudaFree(d_new); cudaFree(d_a); cudaFree(d_b); }
+};
+
+namespace {
+// MTH of `cnt` consecutive leaf digests starting at d_in (level-wise, unpaired node promoted) -> d_out (32 bytes)
+int log_range_root(cg_merkle_log* L, const uint32_t* d_in, uint64_t cnt, uint32_t* d_out, cudaStream_t st) {
+  int rc;
+  if (cnt == 1) { CU(cudaMemcpyAsync(d_out, d_in, 32, cudaMemcpyDeviceToDevice, st)); return CG_OK; }
+  if ((rc = grow(&L->d_a, &L->cap_a, (size_t)(cnt + 1) / 2 * 8 + 8))) return rc;
+  if ((rc = grow(&L->d_b, &L->cap_b, (size_t)(cnt + 3) / 4 * 8 + 8))) return rc;
+  const uint32_t* src = d_in; uint32_t* dst = L->d_a; uint64_t m = cnt;
+  while (m > 1) {
+    int k = launch_merkle_level(src, m, dst, st); G.launches += k; G.stats.kernel_launches += k;
+    m = (m + 1) / 2; src = dst; dst = dst == L->d_a ? L->d_b : L->d_a;
+  }
+  CU(cudaMemcpyAsync(d_out, src, 32, cudaMemcpyDeviceToDevice, st));
+  return CG_OK;
+}
+int log_check(cg_merkle_log* L) {
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!L) return fail(CG_ERR_INVALID_ARG, "null argument");
+  return CG_OK;
+}
+// root of the current tree -> d_tmp[65]
+int log_root_device(cg_merkle_log* L, cudaStream_t st) {
+  // fold the frontier from the smallest subtree upwards: r = slot[lowest]; r = node(slot[h], r) for every higher set bit
+  uint32_t nl = 0; int lowest = -1;
+  for (int h = 0; h < 64; h++) if ((L->n >> h) & 1ull) {
+    if (lowest < 0) { lowest = h; continue; }
+    CU(cudaMemcpyAsync(L->d_tmp + 8 * nl, L->d_slots + 8 * h, 32, cudaMemcpyDeviceToDevice, st)); nl++;
+  }
+  int k = launch_merkle_chain(L->d_tmp, nl, L->d_slots + 8 * lowest, L->d_tmp + 8 * 65, st);
+  G.launches += k; G.stats.kernel_launches += k;
+  return CG_OK;
+}
+}  // namespace
+
+int cg_merkle_log_create(cg_merkle_log** out, int keep_leaf_digests) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!out) return fail(CG_ERR_INVALID_ARG, "null argument");
+  std::unique_ptr<cg_merkle_log> L(new cg_merkle_log());
+  L->keep = keep_leaf_digests != 0;
+  CU(cudaMalloc((void**)&L->d_slots, 64 * 32)); CU(cudaMalloc((void**)&L->d_tmp, 66 * 32));
+  CU(cudaMemset(L->d_slots, 0, 64 * 32));
+  *out = L.release();
+  return CG_OK;
+}
+void cg_merkle_log_destroy(cg_merkle_log* L) { std::lock_guard<std::mutex> lk(g_mu); if (L) { if (G.ready) cudaStreamSynchronize(G.stream); delete L; } }
+int cg_merkle_log_size(const cg_merkle_log* L, uint64_t* out_n) { if (!L || !out_n) return fail(CG_ERR_INVALID_ARG, "null argument"); *out_n = L->n; return CG_OK; }
+
+int cg_merkle_log_restore(cg_merkle_log** out, uint64_t n, const uint8_t* frontier32, uint32_t count) {
+  if (!out || (count && !frontier32) || count != (uint32_t)__builtin_popcountll(n)) return fail(CG_ERR_INVALID_ARG, "frontier must hold one digest per set bit of n");
+  int rc = cg_merkle_log_create(out, 0);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_mu);
+  cg_merkle_log* L = *out; uint32_t k = 0;
+  for (int h = 63; h >= 0; h--) if ((n >> h) & 1ull) { CU(cudaMemcpy(L->d_slots + 8 * h, frontier32 + 32 * (size_t)k, 32, cudaMemcpyHostToDevice)); k++; }
+  L->n = n;
+  return CG_OK;
+}
+
+int cg_merkle_log_frontier(cg_merkle_log* L, uint8_t* out_frontier32, uint32_t* out_count) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = log_check(L); if (rc) return rc;
+  if (!out_count) return fail(CG_ERR_INVALID_ARG, "null argument");
+  uint32_t k = 0;
+  for (int h = 63; h >= 0; h--) if ((L->n >> h) & 1ull) { if (out_frontier32) CU(cudaMemcpyAsync(out_frontier32 + 32 * (size_t)k, L->d_slots + 8 * h, 32, cudaMemcpyDeviceToHost, G.stream)); k++; }
+  CU(cudaStreamSynchronize(G.stream));
+  *out_count = k;
+  return CG_OK;
+}
+
+int cg_merkle_log_append(cg_merkle_log* L, const uint8_t* bytes, const uint64_t* offsets, uint64_t m) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = log_check(L); if (rc) return rc;
+  if (!m) return CG_OK;
+  if (!offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (L->n + m < L->n) return fail(CG_ERR_TOO_LARGE, "log size overflows 64 bits");
+  cudaStream_t st = G.stream;
+  const size_t total = offsets[m];
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)m + 1))) return rc;
+  uint32_t* d_dig;                                          // where this batch's leaf digests go
+  if (L->keep) {
+    if (L->n + m > L->cap_leaves) {                         // grow the digest store (amortised doubling), keeping what is there
+      uint64_t cap = std::max<uint64_t>(L->n + m, L->cap_leaves * 2); uint32_t* nd = nullptr;
+      CU(cudaMalloc((void**)&nd, (size_t)cap * 32));
+      if (L->n) CU(cudaMemcpyAsync(nd, L->d_leaves, (size_t)L->n * 32, cudaMemcpyDeviceToDevice, st));
+      CU(cudaStreamSynchronize(st)); cudaFree(L->d_leaves); L->d_leaves = nd; L->cap_leaves = cap;
+    }
+    d_dig = L->d_leaves + (size_t)L->n * 8;
+  } else {
+    if ((rc = grow(&L->d_new, &L->cap_new, (size_t)m * 8))) return rc;
+    d_dig = L->d_new;
+  }
+  if (total) CU(cudaMemcpyAsync(G.d_bytes, bytes, total, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(G.d_off64, offsets, ((size_t)m + 1) * 8, cudaMemcpyHostToDevice, st));
+  int k = launch_merkle_leaves_var(G.d_bytes, G.d_off64, m, d_dig, st);
+  G.launches += k; G.stats.kernel_launches += k; G.stats.merkle_leaves += m;
+  // cut [n, n+m) into aligned perfect blocks (block size <= lowest set bit of its position), reduce each, carry into the frontier
+  uint64_t pos = L->n, rem = m;
+  while (rem) {
+    uint64_t s = pos ? (pos & (~pos + 1)) : (1ull << 63);
+    while (s > rem) s >>= 1;
+    uint32_t* acc = L->d_tmp + 8 * 64;
+    if ((rc = log_range_root(L, d_dig + (size_t)(pos - L->n) * 8, s, acc, st))) return rc;
+    int h = 0; while ((1ull << h) < s) h++;
+    uint32_t nl = 0; int top = h;                           // slots h, h+1, ... that are occupied merge into the new subtree
+    while ((pos >> top) & 1ull) { CU(cudaMemcpyAsync(L->d_tmp + 8 * nl, L->d_slots + 8 * top, 32, cudaMemcpyDeviceToDevice, st)); nl++; top++; }
+    if (nl) { k = launch_merkle_chain(L->d_tmp, nl, acc, L->d_slots + 8 * top, st); G.launches += k; G.stats.kernel_launches += k; }
+    else CU(cudaMemcpyAsync(L->d_slots + 8 * top, acc, 32, cudaMemcpyDeviceToDevice, st));
+    pos += s; rem -= s;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  L->n += m;
+  return CG_OK;
+}
+
+int cg_merkle_log_root(cg_merkle_log* L, uint8_t out_root[32]) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = log_check(L); if (rc) return rc;
+    if (!out_root) return fail(CG_ERR_INVALID_ARG, "null argument");
+    if (L->n) {
+      if ((rc = log_root_device(L, G.stream))) return rc;
+      CU(cudaMemcpyAsync(out_root, L->d_tmp + 8 * 65, 32, cudaMemcpyDeviceToHost, G.stream));
+      CU(cudaStreamSynchronize(G.stream));
+      return CG_OK;
+    }
+    return empty_root(out_root);
+  }
+}
+
+int cg_merkle_log_proof(cg_merkle_log* L, uint64_t index, uint8_t* out_path32, uint32_t path_cap, uint32_t* out_len) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = log_check(L); if (rc) return rc;
+  if (!out_len) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (!L->keep) return fail(CG_ERR_UNSUPPORTED, "log was created without leaf digests (or restored from a frontier): no proofs");
+  if (index >= L->n) return fail(CG_ERR_INVALID_ARG, "leaf index out of range");
+  // RFC 6962 2.1.1: PATH(m, D[n]) -- the sibling subtree at every split on the way down, returned leaf level first
+  std::vector<std::pair<uint64_t, uint64_t>> sib;
+  uint64_t lo = 0, hi = L->n;
+  while (hi - lo > 1) {
+    uint64_t k = 1; while (k * 2 < hi - lo) k *= 2;       // largest power of two < hi - lo
+    if (index < lo + k) { sib.push_back({lo + k, hi}); hi = lo + k; } else { sib.push_back({lo, lo + k}); lo = lo + k; }
+  }
+  *out_len = (uint32_t)sib.size();
+  if (sib.size() > path_cap || (sib.size() && !out_path32)) return fail(CG_ERR_CAPACITY, "path buffer too small");
+  cudaStream_t st = G.stream;
+  for (size_t i = 0; i < sib.size(); i++) {
+    const auto& r = sib[sib.size() - 1 - i];
+    if ((rc = log_range_root(L, L->d_leaves + (size_t)r.first * 8, r.second - r.first, L->d_tmp + 8 * i, st))) return rc;
+  }
+  if (!sib.empty()) CU(cudaMemcpyAsync(out_path32, L->d_tmp, sib.size() * 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return CG_OK;
+}
+
+int cg_merkle_verify_proof(const uint8_t* leaf_bytes, uint64_t leaf_len, uint64_t index, uint64_t tree_size, const uint8_t* path32, uint32_t path_len,
+                           const uint8_t root[32], int* out_ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!out_ok || !root || (leaf_len && !leaf_bytes) || (path_len && !path32) || path_len > 64) return fail(CG_ERR_INVALID_ARG, "bad argument");
+  int rc; cudaStream_t st = G.stream;
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, (size_t)leaf_len + 64))) return rc;
+  if ((rc = grow(&G.d_off64, &G.cap_off64, 2))) return rc;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)(path_len + 4) * 8))) return rc;
+  uint64_t off[2] = {0, leaf_len};
+  if (leaf_len) CU(cudaMemcpyAsync(G.d_bytes, leaf_bytes, leaf_len, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(G.d_off64, off, 16, cudaMemcpyHostToDevice, st));
+  uint32_t* d_leaf = G.d_dig[0]; uint32_t* d_root = d_leaf + 8; uint32_t* d_ok = d_root + 8; uint32_t* d_path = d_ok + 8;
+  int k = launch_merkle_leaves_var(G.d_bytes, G.d_off64, 1, d_leaf, st);
+  CU(cudaMemcpyAsync(d_root, root, 32, cudaMemcpyHostToDevice, st));
+  if (path_len) CU(cudaMemcpyAsync(d_path, path32, (size_t)path_len * 32, cudaMemcpyHostToDevice, st));
+  k += launch_merkle_verify(d_leaf, index, tree_size, d_path, path_len, d_root, d_ok, st);
+  G.launches += k; G.stats.kernel_launches += k;
+  uint32_t ok = 0;
+  CU(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  *out_ok = (int)ok;
+  return CG_OK;
+}
+
 int cg_merkle_fold_device(const void* d_nodes32, uint64_t m, void* d_out_root32, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");

@@ -181,6 +181,54 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const uint32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// Merkle log helpers (append-only log: frontier carries, root fold, audit-path check) -- a handful of node hashes
+// per call, run by one thread on the device (the product computes no hash on the CPU)
+// ------------------------------------------------------------------------------------------
+// acc = node(left[k], acc) for k = 0..n_left-1 : frontier carry chains and the root fold.  left: n_left digests.
+__global__ void merkle_chain_kernel(const uint32_t* __restrict__ left, uint32_t n_left, const uint32_t* __restrict__ acc_in, uint32_t* __restrict__ acc_out) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint32_t r[8]; load_digest(acc_in, r);
+  for (uint32_t k = 0; k < n_left; k++) { uint32_t l[8], h[8]; load_digest(left + 8 * k, l); merkle_node(l, r, h);
+#pragma unroll
+    for (int t = 0; t < 8; t++) r[t] = h[t]; }
+  store_digest(acc_out, r);
+}
+// RFC 9162 2.1.3.2: does `path` prove that the leaf with digest leaf32 is entry `index` of the tree of `size` leaves with root `root32`?
+__global__ void merkle_verify_kernel(const uint32_t* __restrict__ leaf32, unsigned long long index, unsigned long long size,
+                                     const uint32_t* __restrict__ path, uint32_t path_len, const uint32_t* __restrict__ root32, uint32_t* __restrict__ ok) {
+  if (threadIdx.x || blockIdx.x) return;
+  *ok = 0;
+  if (index >= size) return;
+  unsigned long long fn = index, sn = size - 1;
+  uint32_t r[8]; load_digest(leaf32, r);
+  for (uint32_t k = 0; k < path_len; k++) {
+    if (sn == 0) return;
+    uint32_t p[8], h[8]; load_digest(path + 8 * k, p);
+    if ((fn & 1ull) || fn == sn) {
+      merkle_node(p, r, h);
+      if (!(fn & 1ull)) while (!(fn & 1ull) && fn != 0) { fn >>= 1; sn >>= 1; }
+    } else merkle_node(r, p, h);
+#pragma unroll
+    for (int t = 0; t < 8; t++) r[t] = h[t];
+    fn >>= 1; sn >>= 1;
+  }
+  if (sn != 0) return;
+  uint32_t q[8]; load_digest(root32, q);
+  bool eq = true;
+#pragma unroll
+  for (int t = 0; t < 8; t++) eq = eq && q[t] == r[t];
+  *ok = eq ? 1u : 0u;
+}
+int launch_merkle_chain(const uint32_t* d_left, uint32_t n_left, const uint32_t* d_acc_in, uint32_t* d_acc_out, cudaStream_t stream) {
+  merkle_chain_kernel<<<1, 32, 0, stream>>>(d_left, n_left, d_acc_in, d_acc_out);
+  return 1;
+}
+int launch_merkle_verify(const uint32_t* d_leaf32, uint64_t index, uint64_t size, const uint32_t* d_path, uint32_t path_len, const uint32_t* d_root32, uint32_t* d_ok, cudaStream_t stream) {
+  merkle_verify_kernel<<<1, 32, 0, stream>>>(d_leaf32, index, size, d_path, path_len, d_root32, d_ok);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // redacted-output assembly (RedactionEngine.applyReplacements, engine.ts:165-181, with the vault's placeholder
 // "[REDACTED:<category>:<first 8 hex digits of SHA-256(match)>]", vault.ts:33-35,75-104)
 // ------------------------------------------------------------------------------------------
