@@ -258,6 +258,16 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * n * e2e_steps / e2e_s
     same = bool(torch.equal(h_words.to(dev), words))
+    # (f1) redacted output through cg_redact_batch (findMatches semantics + digests + splice on the device), host buffers
+    redact = None
+    if world == 1:
+        nr = min(n, 1 << 18)
+        hd, ho = h_data.numpy()[: nr * L + 64], h_off.numpy()[: nr + 1].view(np.uint32)
+        rs.redact_batch(hd, ho)
+        t0 = time.perf_counter()
+        r_out, r_off, r_spans, r_dig = rs.redact_batch(hd, ho)
+        dt = time.perf_counter() - t0
+        redact = {"msgs": nr, "msgs_per_s_from_host": nr / dt, "spans": int(len(r_spans)), "out_bytes": int(len(r_out)), "in_bytes": int(nr * L)}
 
     # ---- Merkle (C3): leaves/s; block roots all-gathered over NCCL, folded on every rank
     merkle = None
@@ -299,6 +309,26 @@ def main():
                   "root_hex": bytes(root.cpu().numpy()).hex(), "collective": "all_gather of %d block roots/rank (NCCL)" % nblk if world > 1 else "none (1 rank)",
                   "hbm_frac_of_measured": (nl * MERKLE_LEAF / (mms * 1e-3)) / (peak * 1e9),
                   "sha256_compressions_per_s": world * (nl * ((MERKLE_LEAF + 1 + 9 + 63) // 64) + 2 * (nl - 1)) / (mms * 1e-3)}
+        # (f2) the same leaves through the append-only log in 16 appends from host memory (H2D inside), rank 0, N = 1 only
+        if world == 1 and rank == 0:
+            nlog = min(nl, 1 << 20)
+            h_leaves = leaves[: nlog * MERKLE_LEAF].cpu().numpy()
+            offs = (np.arange(nlog // 16 + 1, dtype=np.uint64) * MERKLE_LEAF)
+            lg = N.MerkleLog(keep_leaf_digests=True)
+            t0 = time.perf_counter()
+            for c in range(16):
+                part = h_leaves[c * (nlog // 16) * MERKLE_LEAF:]
+                N.check(lib.cg_merkle_log_append(lg.handle, part.ctypes.data, offs.ctypes.data, nlog // 16))
+            log_root = lg.root()
+            dt = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            path = lg.proof(nlog // 3)
+            proof_ms = (time.perf_counter() - t1) * 1e3
+            one_shot = N.merkle_root_fixed(h_leaves, MERKLE_LEAF, nlog)
+            merkle["log"] = {"leaves": nlog, "appends": 16, "leaves_per_s_from_host": nlog / dt, "root_equals_one_shot_tree": log_root == one_shot,
+                             "proof_len": len(path), "proof_ms": proof_ms,
+                             "proof_verifies": N.merkle_verify_proof(bytes(h_leaves[(nlog // 3) * MERKLE_LEAF:(nlog // 3 + 1) * MERKLE_LEAF]), nlog // 3, nlog, path, log_root)}
+            lg.close()
         del leaves
 
     if rank != 0:
@@ -358,7 +388,7 @@ def main():
                 "steps": e2e_steps, "words_equal_device_path": same},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "extra": {"merkle": merkle, "per_rank_ms_per_step": per_rank_ms},
+        "extra": {"merkle": merkle, "redact": redact, "per_rank_ms_per_step": per_rank_ms},
     }
     emit(line)
     if world > 1:

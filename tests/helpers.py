@@ -100,3 +100,30 @@ def oracle_regexes(O, rules):
 def words_to_tuple(w):
     w = int(w)
     return (w >> 63, (w >> 32) & 0x7fffffff, w & 0xffffffff) if w else (0, 0, 0xffffffff)
+
+# Rule packs in the FORMS of the reference's other packs: alternations of CJK / Cyrillic literals,
+# classes mixing CJK ranges with \w, a greedy wildcard between literals, a capture group after optional blanks
+# (cortex/src/patterns/lang-*.ts), and the lazy PEM block of cortex/src/trace-analyzer/redactor.ts.  The words are ours.
+PACK_RULES = [
+    (r"(?:已经决定|方案确定|我们选用|就这样办)", 0, 3),
+    (r"(?:关于|回到|讨论一下)\s*([\u4e00-\u9fff\w]{2,20})", 0, 3),
+    (r"(?:等待|被.*卡住|需要.*才可以)", 0, 3),
+    (r"(?:решили|договорились|утвердили план)", 0, 3),
+    (r"(?:насчёт|по поводу)\s+([а-яёА-ЯЁ\w]{3,24})", 0, 3),
+    (r"(?:결정했|확정했|하기로 했)", 0, 3),
+    (r"(?:すごい|完璧|やった)[!！]*", 0, 3),
+    (r"-----BEGIN [A-Z ]+-----[\s\S]*?-----END [A-Z ]+-----", 0, 0),
+    (r"(?:schluessel|geheimnis)\s*[:=]\s*\S{6,}", 1, 0),
+]
+PACK_TEXTS = [
+    "今天开会，我们选用新的部署流程，关于 数据库迁移_v2 的事情稍后再说。",
+    "被上游的评审卡住了，需要安全团队签字才可以继续；讨论一下预算",
+    "Вчера договорились и утвердили план, а насчёт  бюджета2025 решим позже",
+    "по поводу релиза: решили выкатывать в пятницу",
+    "우리는 금요일에 배포하기로 했습니다. 확정했어요",
+    "すごい！！ 完璧 やった!",
+    "key follows\n-----BEGIN RSA PRIVATE KEY-----\nMIIB\n😀\n-----END RSA PRIVATE KEY-----\ntrailer -----END X-----",
+    "Schluessel = abc123def and GEHEIMNIS:xyz (short) ünd GeheimNis=лмнопрст",
+    "nothing here 😀 plain ascii and ünïcödé",
+    "",
+]

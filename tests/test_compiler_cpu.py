@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from helpers import Harness
+from helpers import Harness, PACK_RULES, PACK_TEXTS
 from vainplex_openclaw_b200 import workload as W
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -237,6 +237,28 @@ def test_trap_table_image_and_profile_guided_ranking(harness_lib):
     cold_after = int(hist2[hot:].sum())
     assert cold_after <= cold_before and (cold_before == 0 or cold_after < cold_before)
     assert (np.diff(hist2[1:].astype(np.int64)) <= 0).all()                  # most visited first
+    h.close()
+
+
+def test_non_ascii_rule_packs_and_lazy_block(oracle, harness_lib):
+    """the forms of the reference's other rule packs -- CJK / Cyrillic / Hangul literal alternations, classes
+    mixing CJK ranges with \\w, `.*` between literals, the lazy PEM block -- through the product compiler + VM on the host."""
+    h = Harness(harness_lib, PACK_RULES, mode=2)
+    assert (h.status == 0).all(), [h.L.harness_rule_error(h.h, i) for i in np.nonzero(h.status)[0]]
+    msgs = [t.encode("utf-8") for t in PACK_TEXTS]
+    total = 0
+    for ri, r in enumerate(PACK_RULES):
+        reg = oracle.Regex(r[0], "i" if r[1] else "")
+        exp = oracle_spans(oracle, reg, msgs)
+        for mi, m in enumerate(msgs):
+            got = h.find_all(ri, m)
+            assert [(g[2], g[3]) for g in got] == exp.get(mi, []), (r[0], PACK_TEXTS[mi])
+            total += len(got)
+            if exp.get(mi):
+                assert ri in h.candidates(m) and ri in h.policy_hits(m)
+            else:
+                assert ri not in h.policy_hits(m)
+    assert total >= 14
     h.close()
 
 

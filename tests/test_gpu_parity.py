@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import oracle_regexes
+from helpers import oracle_regexes, PACK_RULES, PACK_TEXTS
 from vainplex_openclaw_b200 import workload as W
 
 pytestmark = pytest.mark.gpu
@@ -388,3 +388,43 @@ def test_merkle_log_append_frontier_and_proofs(N, oracle):
             assert not N.merkle_verify_proof(all_leaves[i], i ^ 1, len(all_leaves), p, root2)
     for lg in (log, resumed, slog):
         lg.close()
+
+
+def test_non_ascii_rule_packs_on_the_kernels(N, oracle):
+    """CJK / Cyrillic / Hangul literal alternations, classes with CJK ranges, `.*` between literals and the
+    lazy PEM block: policy words, hits and resolved spans equal the oracle's."""
+    rs = N.Ruleset(PACK_RULES, strict=True)
+    msgs = [t.encode("utf-8") for t in PACK_TEXTS] * 40
+    data, off = N.pack(msgs)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, PACK_RULES, data, off)
+    assert np.array_equal(words, ewords) and [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits and len(ehits) >= 400
+    spans = rs.find_matches_batch(data, off)
+    got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+    assert got == oracle_spans(oracle, PACK_RULES, data, off)
+    rs.close()
+
+
+def test_chunked_host_scan_equals_one_piece_scan(N, oracle):
+    """Large words-only host batches go through the chunked path (copies overlapped with the kernels): same words as
+    the one-piece path, ragged lengths, and the hit count derived from the words equals the hit list's length."""
+    rl = W.make_rules(120)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    n = 90000
+    data_t, off_t, _ = W.make_messages(n, 96, rl, p_hit=0.05, seed=321)
+    buf, off0 = data_t.numpy(), off_t.numpy()
+    rng = np.random.default_rng(8)
+    lens = rng.integers(0, 97, n)
+    off = np.zeros(n + 1, dtype=np.uint32); off[1:] = np.cumsum(lens)
+    data = np.zeros(int(off[-1]) + 64, dtype=np.uint8)
+    src = np.repeat(off0[:-1].astype(np.int64), lens) + (np.arange(int(off[-1])) - np.repeat(off[:-1].astype(np.int64), lens))
+    data[:int(off[-1])] = buf[src]
+    w_one, hits = rs.scan_batch(data, off, want_hits=True)              # one piece (hit list requested); also adapts the rule set
+    w_chunk, _ = rs.scan_batch(data, off, want_hits=False)              # chunked
+    assert np.array_equal(w_one, w_chunk)
+    assert int(((w_chunk >> np.uint64(32)) & np.uint64(0x7fffffff))[w_chunk >> np.uint64(63) == 1].sum()) == len(hits) >= 1000
+    sub = 3000
+    ewords, _ = oracle_policy(oracle, rules, data[: int(off[sub]) + 64], off[: sub + 1])
+    assert np.array_equal(w_chunk[:sub], ewords)
+    rs.close()

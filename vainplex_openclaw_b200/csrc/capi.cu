@@ -38,6 +38,9 @@ struct Ctx {
   uint64_t* d_off64 = nullptr; size_t cap_off64 = 0;
   uint64_t* d_words = nullptr; size_t cap_words = 0;
   uint32_t* d_dig[2] = {nullptr, nullptr}; size_t cap_dig[2] = {0, 0};
+  // chunked host-buffer scans: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c
+  static constexpr int kChunks = 8;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr; cudaEvent_t e_h2d[kChunks] = {}, e_done[kChunks] = {}; uint32_t* h_chunk_counters = nullptr;
 } G;
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -251,7 +254,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
   uint32_t slot_cap = std::max<uint32_t>(n / 4, 4096), event_cap = std::max<uint32_t>(n, 4096), span_cap = spans ? std::max<uint32_t>(n, 4096) : 1;
   uint32_t l1_cap = std::max<uint32_t>(4 * n, 1u << 16);
   // keep whatever an earlier step of this rule set needed
-  slot_cap = std::max(slot_cap, rs->work.slot_cap); event_cap = std::max(event_cap, rs->work.event_cap); l1_cap = std::max(l1_cap, rs->work.l1_cap);
+  slot_cap = std::max(std::max(slot_cap, rs->work.slot_cap), rs->grow_slot); event_cap = std::max(std::max(event_cap, rs->work.event_cap), rs->grow_ev); l1_cap = std::max(std::max(l1_cap, rs->work.l1_cap), rs->grow_l1);
   hs->counters.assign(16, 0);
   if ((rc = join_pipeline(rs, st))) return rc;
   {
@@ -283,6 +286,73 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
     return CG_OK;
   }
   return fail(CG_ERR_CAPACITY, "candidate queues kept overflowing");
+}
+
+// Words-only scan of a large host batch in kChunks pieces: the H2D copy of piece c+1 and the D2H copy of piece c-1 run
+// on their own streams while the kernels of piece c run -- end to end the call then costs little more than the H2D copy
+// alone.  Returns 1 when a queue overflowed somewhere (capacities have been grown; the caller re-runs in one piece).
+int scan_host_chunked(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint64_t* out_words) {
+  const int C = Ctx::kChunks;
+  const size_t total = offsets[n];
+  int rc;
+  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
+  if ((rc = grow(&G.d_words, &G.cap_words, (size_t)n + 1))) return rc;
+  if (!G.s_h2d) {
+    CU(cudaStreamCreateWithFlags(&G.s_h2d, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&G.s_d2h, cudaStreamNonBlocking));
+    for (int c = 0; c < C; c++) { CU(cudaEventCreateWithFlags(&G.e_h2d[c], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&G.e_done[c], cudaEventDisableTiming)); }
+    CU(cudaMallocHost((void**)&G.h_chunk_counters, (size_t)C * kCounterWords * 4));
+  }
+  cudaStream_t st = G.stream;
+  if ((rc = join_pipeline(rs, st))) return rc;
+  {   // segmentation decision from the host offsets (as scan_host)
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < n; i++) max_len = std::max(max_len, offsets[i + 1] - offsets[i]);
+    const bool seg = max_len > 2 * kSegBytes;
+    const uint32_t want = n + (uint32_t)(total / kSegBytes) + 64;
+    if (seg != rs->segmented || (seg && want > rs->want_units)) { CU(cudaStreamSynchronize(st)); rs->segmented = seg; rs->want_units = std::max(rs->want_units, want); }
+    if ((rc = ensure_units(rs, rs->work))) return rc;
+  }
+  const uint32_t per = (n + C - 1) / C;
+  const uint32_t l1_cap = std::max(std::max<uint32_t>(std::max<uint32_t>(4 * per, 1u << 16), rs->work.l1_cap), rs->grow_l1),
+                 slot_cap = std::max(std::max<uint32_t>(std::max<uint32_t>(per / 4, 4096), rs->work.slot_cap), rs->grow_slot),
+                 event_cap = std::max(std::max<uint32_t>(std::max<uint32_t>(per, 4096), rs->work.event_cap), rs->grow_ev);
+  CU(cudaStreamSynchronize(st));
+  if ((rc = ensure_work(rs, rs->work, std::max<uint32_t>(per, 1), l1_cap, slot_cap, event_cap, 1))) return rc;
+  CU(cudaMemcpyAsync(G.d_off32, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, G.s_h2d));
+  CU(cudaMemsetAsync(G.d_bytes + total, 0, 64, G.s_h2d));
+  CU(cudaEventRecord(G.ev0, st));
+  int used = 0;
+  for (int c = 0; c < C; c++) {
+    const uint32_t m0 = std::min<uint64_t>((uint64_t)c * per, n), m1 = std::min<uint64_t>((uint64_t)(c + 1) * per, n);
+    if (m1 <= m0) break;
+    used = c + 1;
+    const size_t b0 = offsets[m0], b1 = offsets[m1];
+    if (b1 > b0) CU(cudaMemcpyAsync(G.d_bytes + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, G.s_h2d));
+    CU(cudaEventRecord(G.e_h2d[c], G.s_h2d));
+    CU(cudaStreamWaitEvent(st, G.e_h2d[c], 0));
+    if ((rc = run_scan_device(rs, G.d_bytes, G.d_off32 + m0, m1 - m0, G.d_words + m0, false, st))) return rc;
+    CU(cudaMemcpyAsync(G.h_chunk_counters + (size_t)c * kCounterWords, rs->work.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(G.e_done[c], st));
+    CU(cudaStreamWaitEvent(G.s_d2h, G.e_done[c], 0));
+    if (out_words) CU(cudaMemcpyAsync(out_words + m0, G.d_words + m0, (size_t)(m1 - m0) * 8, cudaMemcpyDeviceToHost, G.s_d2h));
+  }
+  CU(cudaEventRecord(G.ev1, st));
+  CU(cudaStreamSynchronize(st)); CU(cudaStreamSynchronize(G.s_d2h)); CU(cudaStreamSynchronize(G.s_h2d));
+  float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_scan_ms = ms;
+  bool overflow = false;
+  for (int c = 0; c < used; c++) {
+    const uint32_t* hc = G.h_chunk_counters + (size_t)c * kCounterWords; const uint32_t flags = hc[3];
+    if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
+    if (flags & ERR_L1_OVERFLOW) { rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * hc[4], hc[4] + 65536)); overflow = true; }
+    if (flags & ERR_SLOT_OVERFLOW) { rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096)); overflow = true; }
+    if (flags & ERR_EVENT_OVERFLOW) { rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096)); overflow = true; }
+    if (flags & ERR_UNIT_OVERFLOW) rs->grow_units = std::max<uint32_t>(rs->grow_units, hc[16] + hc[16] / 8 + 64);      // not an error: that piece ran unsegmented
+    G.stats.candidate_events += hc[1]; G.stats.verified_pairs += hc[1];
+  }
+  if (overflow) return 1;
+  G.stats.messages_scanned += n; G.stats.bytes_scanned += total;
+  return CG_OK;
 }
 
 }  // namespace
@@ -437,7 +507,19 @@ int cg_scan_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets,
                   cg_hit* out_hits, uint32_t hits_cap, uint32_t* out_nhits) {
   std::lock_guard<std::mutex> lk(g_mu);
   HostScan hs;
-  int rc = scan_host(rs, bytes, offsets, n, false, &hs);
+  int rc;
+  // large words-only batches: chunked, copies overlapped with the kernels (the hit list needs the per-batch slot tables)
+  static const bool no_chunks = getenv("CG_NO_CHUNKS") && atoi(getenv("CG_NO_CHUNKS"));
+  if (!no_chunks && !out_hits && out_words && n >= (1u << 16) && G.ready && rs && bytes && offsets && rs->adapted) {
+    rc = scan_host_chunked(rs, bytes, offsets, n, out_words);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (out_nhits) { uint64_t nh = 0; for (uint32_t i = 0; i < n; i++) if (out_words[i] >> 63) nh += (out_words[i] >> 32) & 0x7fffffffu; *out_nhits = (uint32_t)nh; G.stats.hits += nh; }
+      return CG_OK;
+    }
+    // rc == 1: a queue overflowed in some piece; capacities have been raised -- run the batch in one piece below
+  }
+  rc = scan_host(rs, bytes, offsets, n, false, &hs);
   if (rc) return rc;
   cudaStream_t st = G.stream;
   if (out_words && n) CU(cudaMemcpyAsync(out_words, G.d_words, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
