@@ -258,6 +258,21 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * n * e2e_steps / e2e_s
     same = bool(torch.equal(h_words.to(dev), words))
+    # C1: one message through the blocking single-message entry point (the synchronous hooks' path), 17 built-in rules
+    one = None
+    if world == 1:
+        rs17 = N.Ruleset(W.rules_as_tuples(W.make_rules(17)), strict=True)
+        m1 = bytes(h_data.numpy()[:L])
+        tok = b"please use key sk-" + b"a" * 24 + b" for bob@example.com"
+        for _ in range(20):
+            rs17.scan_one(m1)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            rs17.scan_one(m1)
+        lat = (time.perf_counter() - t0) / 200
+        w1, r1 = rs17.scan_one(tok)
+        one = {"latency_us": lat * 1e6, "rules": 17, "msg_bytes": L, "hit_rules_of_probe": r1}
+        rs17.close()
     # (f1) redacted output through cg_redact_batch (findMatches semantics + digests + splice on the device), host buffers
     redact = None
     if world == 1:
@@ -388,7 +403,7 @@ def main():
                 "steps": e2e_steps, "words_equal_device_path": same},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "extra": {"merkle": merkle, "redact": redact, "per_rank_ms_per_step": per_rank_ms},
+        "extra": {"merkle": merkle, "redact": redact, "scan_one": one, "per_rank_ms_per_step": per_rank_ms},
     }
     emit(line)
     if world > 1:

@@ -135,6 +135,15 @@ CG_API int cg_scan_one(cg_ruleset *rs, const uint8_t *bytes, uint32_t len, uint6
 CG_API int cg_find_matches_batch(cg_ruleset *rs, const uint8_t *bytes, const uint32_t *offsets, uint32_t n,
                                  cg_span *out_spans, uint32_t spans_cap, uint32_t *out_nspans);
 
+/* ---- verdicts instead of hit bits: aggregateMatches / matchPolicy of src/policy-evaluator.ts:44-146
+ * for rule sets whose rules are the messageContains patterns of a policy list.  rule_policy[i] = index of rule i's policy
+ * in evaluation order (priority descending; rules stored policy by policy), rule_action[i] = 0 allow / 1 audit / 2 deny.
+ * Per message: per policy the first matching rule counts; deny beats audit beats allow; the first policy that produced the
+ * winning action is reported.  out_verdicts[i] = action | (matched policies, saturating at 1023) << 2 | deciding rule << 12
+ * (deciding rule = 0xfffff when no deny / audit rule matched; 0 = no policy matched: allow). */
+CG_API int cg_ruleset_set_policy(cg_ruleset *rs, const uint32_t *rule_policy, const uint8_t *rule_action, uint32_t n_rules);
+CG_API int cg_policy_verdict_batch(cg_ruleset *rs, const uint8_t *bytes, const uint32_t *offsets, uint32_t n, uint32_t *out_verdicts);
+
 /* ---- redacted output of a batch: RedactionEngine.scanString (src/redaction/engine.ts:74-85) = findMatches +
  * applyReplacements (engine.ts:165-181), every match replaced by the vault's default placeholder
  * "[REDACTED:<category>:<first 8 hex digits of SHA-256(match)>]" (src/redaction/vault.ts:33-35,75-104).

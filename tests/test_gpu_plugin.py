@@ -96,6 +96,32 @@ def test_batch_redaction_spliced_on_the_device(P):
         assert v2.resolve_all(b["output"])["resolved"] == v1.resolve_all(a["output"])["resolved"] == s
 
 
+def test_verdicts_aggregated_on_the_device(P):
+    """MessagePolicy.verdict_batch (cg_policy_verdict_batch) == evaluate_batch (host aggregation of the hit list):
+    priority order, first matching rule per policy, deny > audit > allow, first policy's reason."""
+    import random
+    rnd = random.Random(4)
+    words = ["alpha", "bravo", "charlie", "delta", "echo", "foxtrot", "golf", "hotel", "india", "juliet", "kilo", "lima"]
+    policies = []
+    for pi in range(9):
+        rules = []
+        for ri in range(rnd.randint(1, 4)):
+            pats = [rnd.choice(words) + (r"\s+" + rnd.choice(words) if rnd.random() < 0.3 else "") for _ in range(rnd.randint(1, 3))]
+            act = rnd.choice(["deny", "audit", "allow", "deny"])
+            eff = {"action": act}
+            if rnd.random() < 0.7:
+                eff["reason"] = "p%d r%d %s" % (pi, ri, act)
+            rules.append({"messageContains": pats, "effect": eff})
+        policies.append({"id": "pol%d" % pi, "priority": rnd.randint(0, 5) * 10, "rules": rules, "enabled": pi != 4})
+    mp = P.MessagePolicy(policies)
+    texts = [" ".join(rnd.choice(words + ["zulu", "yankee", "xray"] * 3) for _ in range(rnd.randint(0, 9))) for _ in range(600)] + ["", "no keywords here"]
+    a = mp.evaluate_batch(texts)
+    b = mp.verdict_batch(texts)
+    assert {x["action"] for x in a} == {"allow", "audit", "deny"}
+    for t, x, y in zip(texts, a, b):
+        assert (x["action"], x["reason"], len(x["matches"])) == (y["action"], y["reason"], y["matchedPolicies"]), t
+
+
 def test_matches_any_and_policy(P):
     assert P.matches_any("secret\\d+", ["my secret42"])
     assert not P.matches_any("secret\\d+", ["my secret"])

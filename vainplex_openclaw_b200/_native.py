@@ -48,7 +48,7 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
                        ("start16", np.uint32), ("end16", np.uint32)])
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
-           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt", "cg_scan_join", "cg_redact_batch",
+           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt", "cg_scan_join", "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch",
            "cg_merkle_log_create", "cg_merkle_log_destroy", "cg_merkle_log_append", "cg_merkle_log_size", "cg_merkle_log_root",
            "cg_merkle_log_frontier", "cg_merkle_log_restore", "cg_merkle_log_proof", "cg_merkle_verify_proof",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
@@ -87,6 +87,8 @@ def load():
     L.cg_ruleset_adapt.argtypes = [vp, vp, vp, u32, vp]; L.cg_ruleset_adapt.restype = i32
     L.cg_scan_join.argtypes = [vp, vp]; L.cg_scan_join.restype = i32
     L.cg_redact_batch.argtypes = [vp, vp, vp, u32, vp, u64, vp, vp, vp, u32, vp, vp]; L.cg_redact_batch.restype = i32
+    L.cg_ruleset_set_policy.argtypes = [vp, vp, vp, u32]; L.cg_ruleset_set_policy.restype = i32
+    L.cg_policy_verdict_batch.argtypes = [vp, vp, vp, u32, vp]; L.cg_policy_verdict_batch.restype = i32
     L.cg_merkle_log_create.argtypes = [vp, i32]; L.cg_merkle_log_create.restype = i32
     L.cg_merkle_log_destroy.argtypes = [vp]; L.cg_merkle_log_destroy.restype = None
     L.cg_merkle_log_append.argtypes = [vp, vp, vp, u64]; L.cg_merkle_log_append.restype = i32
@@ -200,6 +202,15 @@ class Ruleset:
             check(rc)
             return words[:n], hits[:nh.value]
 
+    def scan_one(self, msg: bytes):
+        """The synchronous hooks' path (before_message_write / tool_result_persist): one message, blocking.
+        -> (word, [hit rule indices])"""
+        buf = np.frombuffer(msg + b"\0" * 64, dtype=np.uint8)
+        word, nr = C.c_uint64(0), C.c_uint32(0)
+        rules = np.zeros(max(64, self.n_rules), dtype=np.uint32)
+        check(load().cg_scan_one(self.handle, buf.ctypes.data, len(msg), C.byref(word), rules.ctypes.data, len(rules), C.byref(nr)))
+        return word.value, [int(x) for x in rules[:nr.value]]
+
     def find_matches_batch(self, data: np.ndarray, off: np.ndarray):
         """-> spans structured array, resolved per registry.ts:288-316, sorted by (msg, start)."""
         n = len(off) - 1
@@ -213,6 +224,18 @@ class Ruleset:
                 continue
             check(rc)
             return spans[:ns.value]
+
+    def set_policy(self, rule_policy, rule_action):
+        """rule i belongs to policy rule_policy[i] (evaluation order, non-decreasing) with effect rule_action[i] (0 allow, 1 audit, 2 deny)."""
+        pol = np.ascontiguousarray(rule_policy, dtype=np.uint32); act = np.ascontiguousarray(rule_action, dtype=np.uint8)
+        check(load().cg_ruleset_set_policy(self.handle, pol.ctypes.data, act.ctypes.data, len(pol)))
+
+    def verdict_batch(self, data: np.ndarray, off: np.ndarray) -> np.ndarray:
+        """-> uint32 verdict per message: action | matched policies << 2 | deciding rule << 12 (openclaw_gov.h)."""
+        n = len(off) - 1
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        check(load().cg_policy_verdict_batch(self.handle, data.ctypes.data, off.ctypes.data, n, out.ctypes.data))
+        return out[:n]
 
     def redact_batch(self, data: np.ndarray, off: np.ndarray):
         """RedactionEngine.scanString for a batch, spliced on the device.

@@ -483,6 +483,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), ranges, &d.set_ranges, 8))) return rc;
   if ((rc = upload(rs.get(), first, &d.rule_first, 8))) return rc;
   if ((rc = upload(rs.get(), H.alpha, &d.rule_alpha, 8))) return rc;
+  d.rule_policy = nullptr; d.rule_action = nullptr;
   d.n_rules = n_rules; d.rw = (n_rules + 31) / 32; if (d.rw == 0) d.rw = 1;
   d.max_prog_len = 0; for (uint32_t i = 0; i < n_rules; i++) d.max_prog_len = std::max(d.max_prog_len, prog_off[i + 1] - prog_off[i]);
   prepare_kernels();
@@ -606,6 +607,44 @@ int cg_find_matches_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* 
   if (out_spans) memcpy(out_spans, res.data(), (size_t)std::min(outn, spans_cap) * sizeof(cg_span));
   if (out_nspans) *out_nspans = outn;
   if (out_spans && outn > spans_cap) return fail(CG_ERR_CAPACITY, "out_spans too small");
+  return CG_OK;
+}
+
+int cg_ruleset_set_policy(cg_ruleset* rs, const uint32_t* rule_policy, const uint8_t* rule_action, uint32_t n_rules) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!rs || !rule_policy || !rule_action || n_rules != rs->dev.n_rules) return fail(CG_ERR_INVALID_ARG, "one (policy, action) pair per rule of the set");
+  std::vector<uint32_t> pol(rule_policy, rule_policy + n_rules), act(n_rules);
+  for (uint32_t i = 0; i < n_rules; i++) {
+    if (rule_action[i] > 2) return fail(CG_ERR_INVALID_ARG, "action must be 0 (allow), 1 (audit) or 2 (deny)");
+    if (i && pol[i] < pol[i - 1]) return fail(CG_ERR_INVALID_ARG, "rules must be stored policy by policy (policy index non-decreasing)");
+    act[i] = rule_action[i];
+  }
+  CU(cudaStreamSynchronize(G.stream));
+  int rc;
+  if ((rc = upload(rs, pol, &rs->dev.rule_policy))) return rc;
+  if ((rc = upload(rs, act, &rs->dev.rule_action))) return rc;
+  for (auto& g : rs->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }      // DevRuleset is captured by value
+  return CG_OK;
+}
+
+int cg_policy_verdict_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint32_t* out_verdicts) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!rs || !out_verdicts) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (!rs->dev.rule_policy) return fail(CG_ERR_INVALID_ARG, "cg_ruleset_set_policy has not been called");
+  HostScan hs;
+  int rc = scan_host(rs, bytes, offsets, n, false, &hs);
+  if (rc) return rc;
+  if (!n) return CG_OK;
+  static uint32_t* d_verdicts = nullptr; static size_t cap_verdicts = 0;
+  if ((rc = grow(&d_verdicts, &cap_verdicts, (size_t)n))) return rc;
+  cudaStream_t st = G.stream;
+  CU(cudaMemsetAsync(d_verdicts, 0, (size_t)n * 4, st));
+  int k = launch_verdicts(rs->dev, rs->work, d_verdicts, G.sm_count, st);
+  G.launches += k; G.stats.kernel_launches += k;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_verdicts, d_verdicts, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return CG_OK;
 }
 

@@ -36,6 +36,9 @@ struct DevRuleset {
   const uint16_t* set_ranges;    // inclusive lo,hi pairs
   const uint32_t* rule_first;    // 8 words per rule: first-byte bitmap
   const uint32_t* rule_alpha;    // 8 words per rule: alphabet bitmap (bytes a match can contain)
+  // verdict aggregation (policy-evaluator.ts:44-146, messageContains slice): per rule its policy (index in priority order,
+  // non-decreasing with the rule index) and its effect (0 allow, 1 audit, 2 deny); nullptr until cg_ruleset_set_policy
+  const uint32_t* rule_policy; const uint32_t* rule_action;
   uint32_t n_rules;
   uint32_t rw;                   // bitmap words per slot = ceil(n_rules / 32)
 };
@@ -79,6 +82,8 @@ int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byt
                    bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream);
+// one verdict word per hit message: action | matched policies << 2 | deciding rule << 12 (cg_policy_verdict_batch)
+int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdicts, int sm_count, cudaStream_t stream);
 int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, int sm_count, cudaStream_t stream);
 
 // raises the dynamic shared-memory limits of every kernel once (not legal inside stream capture)

@@ -637,6 +637,31 @@ __global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict_
   }
 }
 
+// Verdict of a message from its hit bitmap (aggregateMatches, policy-evaluator.ts:110-146, for messageContains rules):
+// policies in priority order, per policy the FIRST matching rule counts, deny beats audit beats allow, and the first
+// policy that produced the winning action is the one whose reason is reported.  Rules are stored policy by policy, so an
+// ascending walk over the hit bits meets every policy's deciding rule first.
+__global__ void verdict_kernel(DevRuleset rs, ScanWork w, uint32_t* __restrict__ verdicts) {
+  const uint32_t n_slots = min(w.counters[0], w.slot_cap);
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+    const uint32_t msg = w.slot_msg[s];
+    if (msg == 0xffffffffu) continue;
+    uint32_t prev = 0xffffffffu, best = 0, decide = 0xfffffu, matched = 0;
+    for (uint32_t k = 0; k < rs.rw; k++) {
+      uint32_t v = w.hit[(size_t)s * rs.rw + k];
+      while (v) {
+        const uint32_t r = k * 32 + (__ffs(v) - 1); v &= v - 1;
+        const uint32_t p = rs.rule_policy[r];
+        if (p == prev) continue;
+        prev = p; matched++;
+        const uint32_t a = rs.rule_action[r];
+        if (a == 2u && best != 2u) { best = 2u; decide = r; } else if (a == 1u && best == 0u) { best = 1u; decide = r; }
+      }
+    }
+    if (matched) verdicts[msg] = best | (min(matched, 1023u) << 2) | (decide << 12);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -704,6 +729,11 @@ int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byte
     else verify_large_kernel<false><<<sm_count * 4, kVerifyThreads, 0, stream>>>(rs, w, d_bytes, d_off);
   }
   return k;
+}
+
+int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdicts, int sm_count, cudaStream_t stream) {
+  verdict_kernel<<<sm_count * 2, 256, 0, stream>>>(rs, w, d_verdicts);
+  return 1;
 }
 
 int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, int sm_count, cudaStream_t stream) {

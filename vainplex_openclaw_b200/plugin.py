@@ -428,6 +428,34 @@ class MessagePolicy:
     def evaluate(self, text: str) -> dict:
         return self.evaluate_batch([text])[0]
 
+    ACTIONS = ("allow", "audit", "deny")
+
+    def verdict_batch(self, texts: Sequence[str]) -> List[dict]:
+        """Same action / reason as evaluate_batch, aggregated on the device (cg_policy_verdict_batch): one verdict word
+        per message comes back instead of the hit list (the `matches` list is not materialised)."""
+        rs = self.scanner.ruleset
+        if rs is None or not texts:
+            return [{"action": "allow", "reason": "No matching policies", "matchedPolicies": 0} for _ in texts]
+        if not getattr(self, "_policy_set", False):
+            pol, act = [], []
+            for pat_rule in self.scanner.rule_of_pattern:
+                pi, ri = self.index[pat_rule]
+                eff = self.policies[pi]["rules"][ri].get("effect", {"action": "deny"})
+                pol.append(pi); act.append(self.ACTIONS.index(eff["action"]))
+            rs.set_policy(pol, act)
+            self._policy_set = True
+        data, off = N.pack([N.js_utf8(t) for t in texts])
+        out = []
+        for v in rs.verdict_batch(data, off).tolist():
+            action, matched, decide = self.ACTIONS[v & 3], (v >> 2) & 1023, v >> 12
+            reason = "No matching policies" if action == "allow" else ""
+            if decide != 0xfffff and action != "allow":
+                pi, ri = self.index[self.scanner.rule_of_pattern[decide]]
+                eff = self.policies[pi]["rules"][ri].get("effect", {"action": "deny"})
+                reason = eff.get("reason", "Denied by policy %s" % self.policies[pi]["id"]) if action == "deny" else eff.get("reason", "")
+            out.append({"action": action, "reason": reason, "matchedPolicies": matched})
+        return out
+
 
 # ------------------------------------------------------------------------------------- plugin entry
 
