@@ -94,7 +94,7 @@ struct cg_ruleset {
     if (h_counters) cudaFreeHost(h_counters);
     if (e_cnt) cudaEventDestroy(e_cnt);
     for (int i = 0; i < 2; i++) { if (e_scan[i]) cudaEventDestroy(e_scan[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); }
-    cudaFree(work.units); cudaFree(work2.units);
+    cudaFree(work.units); cudaFree(work2.units); cudaFree(work.heavy_idx); cudaFree(work2.heavy_idx);
     for (ScanWork* w2 : {&work2}) { cudaFree(w2->l1_msg); cudaFree(w2->l1_pos); cudaFree(w2->l1_sc); cudaFree(w2->slot_of_msg); cudaFree(w2->counters); cudaFree(w2->slot_msg); cudaFree(w2->cand); cudaFree(w2->hit); cudaFree(w2->events); cudaFree(w2->event_pos); cudaFree(w2->event_pre); cudaFree(w2->spans); }
     for (void* p : allocs) cudaFree(p);
     cudaFree(work.l1_msg); cudaFree(work.l1_pos); cudaFree(work.l1_sc); cudaFree(work.slot_of_msg);
@@ -132,7 +132,7 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
     CU(cudaMalloc((void**)&w.hit, (size_t)slot_cap * rw * 4));
     w.slot_cap = slot_cap;
   }
-  if (event_cap > w.event_cap) { cudaFree(w.events); cudaFree(w.event_pos); cudaFree(w.event_pre); w.events = nullptr; w.event_pos = w.event_pre = nullptr; w.event_cap = 0; CU(cudaMalloc((void**)&w.events, (size_t)event_cap * sizeof(uint2))); CU(cudaMalloc((void**)&w.event_pos, (size_t)event_cap * 4)); CU(cudaMalloc((void**)&w.event_pre, (size_t)event_cap * 4)); w.event_cap = event_cap; }
+  if (event_cap > w.event_cap) { cudaFree(w.events); cudaFree(w.event_pos); cudaFree(w.event_pre); cudaFree(w.heavy_idx); w.events = nullptr; w.event_pos = w.event_pre = w.heavy_idx = nullptr; w.event_cap = 0; CU(cudaMalloc((void**)&w.events, (size_t)event_cap * sizeof(uint2))); CU(cudaMalloc((void**)&w.heavy_idx, (size_t)event_cap * 4)); CU(cudaMalloc((void**)&w.event_pos, (size_t)event_cap * 4)); CU(cudaMalloc((void**)&w.event_pre, (size_t)event_cap * 4)); w.event_cap = event_cap; }
   if (span_cap > w.span_cap) { cudaFree(w.spans); w.spans = nullptr; w.span_cap = 0; CU(cudaMalloc((void**)&w.spans, (size_t)span_cap * 24)); w.span_cap = span_cap; }
   return CG_OK;
 }

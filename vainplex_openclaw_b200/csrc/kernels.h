@@ -46,7 +46,7 @@ struct DevRuleset {
 // Per-call scratch in HBM.  A "slot" is one message with at least one confirmed candidate.
 struct ScanWork {
   uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (level-1 accept events) [5]=verify cursor
-                                 //           [6]=slow-path entries [7..15]=debug [16]=n_units (segmented scans)
+                                 //           [6]=slow-path entries [7..15]=debug [16]=n_units (segmented scans) [17]=n_heavy [18]=verify cursor (light events)
   uint32_t* l1_msg;              // [l1_cap] level-1 accept events queued by scan_kernel: message,
   uint32_t* l1_pos;              //          byte offset of the accepting byte inside the message,
   uint32_t* l1_sc;               //          state << 8 | column of the accepting transition (0xffffffff = "always" rules)
@@ -54,7 +54,8 @@ struct ScanWork {
   uint32_t* slot_msg;            // [slot_cap]
   uint32_t* cand;                // [slot_cap * rw]  candidate (msg,rule) pairs already queued
   uint32_t* hit;                 // [slot_cap * rw]  verified pairs
-  uint2* events;                 // [event_cap]  (slot, rule) for the Pike VM
+  uint2* events;                 // [event_cap]  (slot, rule | heavy << 31) for the Pike VM
+  uint32_t* heavy_idx;           // [event_cap]  indices of the events expected to run long (counters[17] of them): verified first
   uint32_t* event_pos;           // [event_cap]  policy mode: message offset of the confirmed factor's first byte
   uint32_t* event_pre;           // [event_cap]  policy mode: max units of a match before that factor (0xffff = unbounded)
   uint32_t* spans;               // [span_cap * 6] msg, rule, start_byte, end_byte, start16, end16

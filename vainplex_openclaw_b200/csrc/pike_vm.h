@@ -112,7 +112,7 @@ struct VMS {
   // *fresh* entry into an in-progress SPLIT (an inner loop re-entered by a new outer iteration) is
   // explored again at its higher priority.  Returns true when MATCH was reached (the caller must
   // then cut every lower-priority thread).
-  CG_HD_NOINLINE bool add(int L, uint32_t pc0, uint32_t start, int prev, int next, uint32_t pos, uint32_t upos) {
+  CG_HD bool add(int L, uint32_t pc0, uint32_t start, int prev, int next, uint32_t pos, uint32_t upos) {
     const uint16_t INPROG = (uint16_t)(gen * 2), DONE = (uint16_t)(gen * 2 + 1);
     CG_VM_STAT(0);
     int sp = 0; S.stk(sp++) = (uint16_t)pc0;

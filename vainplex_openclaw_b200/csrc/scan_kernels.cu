@@ -474,7 +474,13 @@ struct SlotSink {
     uint32_t old = atomicOr(&w.cand[(size_t)slot * rs.rw + (r >> 5)], bit);
     if (want_spans && (old & bit)) return;
     uint32_t e = atomicAdd(&w.counters[1], 1u);
-    if (e < w.event_cap) { w.events[e] = make_uint2(slot, r); w.event_pos[e] = t0; w.event_pre[e] = pre; } else atomicOr(&w.counters[3], ERR_EVENT_OVERFLOW);
+    if (e < w.event_cap) {
+      // a long stretch of pattern before the factor (or an unbounded one) means many start positions for the VM: such
+      // runs are an order of magnitude longer than the rest and are handed out first, so that none of them starts last
+      const bool heavy = !want_spans && (pre & 0xffffu) >= 24u;
+      w.events[e] = make_uint2(slot, r | (heavy ? 0x80000000u : 0u)); w.event_pos[e] = t0; w.event_pre[e] = pre;
+      if (heavy) w.heavy_idx[atomicAdd(&w.counters[17], 1u)] = e;
+    } else atomicOr(&w.counters[3], ERR_EVENT_OVERFLOW);
   }
   // rules without factors: one whole-message run (event_pos = 0xffffffff)
   __device__ void candidate_always(uint32_t r) {
@@ -564,13 +570,19 @@ verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
   VMS<SmemStore> vm(rs, st);
   // events are handed out one at a time (their cost varies by two orders of magnitude): a static split leaves most
   // warps idle while a few finish their second or third long run
+  const uint32_t n_heavy = min(w.counters[17], n_events);
+  bool heavy_phase = true;
   for (;;) {
     uint32_t e = 0;
-    if (lane == 0) e = atomicAdd(&w.counters[5], 1u);
+    if (lane == 0) e = atomicAdd(&w.counters[heavy_phase ? 5 : 18], 1u);
     e = __shfl_sync(0xffffffffu, e, 0);
-    if (e >= n_events) break;
+    if (heavy_phase) {
+      if (e >= n_heavy) { heavy_phase = false; continue; }
+      e = w.heavy_idx[e];
+    } else if (e >= n_events) break;
     uint2 ev = w.events[e];
-    uint32_t slot = ev.x, rule = ev.y;
+    if (!heavy_phase && (ev.y >> 31)) continue;             // done (or being done) by the heavy phase
+    uint32_t slot = ev.x, rule = ev.y & 0x7fffffffu;
     const uint32_t plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
     if (plen > (uint32_t)kSmallProg) continue;          // handled by verify_large_kernel
     uint32_t msg = w.slot_msg[slot];
@@ -606,7 +618,7 @@ verify_large_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
   VMT<kMaxProgLen> vm(rs);
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
     uint2 ev = w.events[e];
-    uint32_t slot = ev.x, rule = ev.y;
+    uint32_t slot = ev.x, rule = ev.y & 0x7fffffffu;
     uint32_t plen = rs.rule_prog_off[rule + 1] - rs.rule_prog_off[rule];
     if (plen <= (uint32_t)kSmallProg) continue;
     uint32_t msg = w.slot_msg[slot];
