@@ -127,3 +127,32 @@ PACK_TEXTS = [
     "nothing here 😀 plain ascii and ünïcödé",
     "",
 ]
+
+
+# random ECMAScript patterns over a tiny alphabet (dense matches, empty matches, astral characters, lazy quantifiers, look-arounds)
+ATOMS = ["a", "b", "c", "1", " ", "é", "😀", ".", r"\d", r"\w", r"\s", r"\S", r"\W", "[ab]", "[^a]", "[a-c1]", r"[^\s1]", r"\b", r"\B",
+         "^", "$", "(?!a)", "(?=b)", "(?<!a)", "(?<=b)", "(?<![a1])", r"(?!\d)"]
+QUANTS = ["", "", "", "*", "+", "?", "{2}", "{1,2}", "{2,}", "*?", "+?", "??", "{1,3}?"]
+
+
+def random_regex(rng, depth=0):
+    n = int(rng.integers(1, 5))
+    parts = []
+    for _ in range(n):
+        u = rng.random()
+        if depth < 2 and u < 0.25:
+            inner = random_regex(rng, depth + 1)
+            if rng.random() < 0.5:
+                inner = inner + "|" + random_regex(rng, depth + 1)
+            atom = ("(?:%s)" if rng.random() < 0.6 else "(%s)") % inner
+        else:
+            atom = ATOMS[int(rng.integers(0, len(ATOMS)))]
+        q = QUANTS[int(rng.integers(0, len(QUANTS)))]
+        if atom in ("^", "$", r"\b", r"\B") or atom.startswith("(?<") :
+            q = ""
+        if atom.startswith("(?=") or atom.startswith("(?!"):
+            q = ""
+        parts.append(atom + q)
+    return "".join(parts)
+
+

@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from helpers import Harness, PACK_RULES, PACK_TEXTS
+from helpers import Harness, PACK_RULES, PACK_TEXTS, random_regex
 from vainplex_openclaw_b200 import workload as W
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -130,32 +130,6 @@ def test_syntax_and_support_classification(oracle, harness_lib):
         oracle.Regex(s)
     assert N.rule_check("[a-z]{2000}") == N.CG_ERR_TOO_LARGE
     assert N.rule_check("É", N.FLAG_ICASE) == N.CG_ERR_UNSUPPORTED
-
-
-ATOMS = ["a", "b", "c", "1", " ", "é", "😀", ".", r"\d", r"\w", r"\s", r"\S", r"\W", "[ab]", "[^a]", "[a-c1]", r"[^\s1]", r"\b", r"\B",
-         "^", "$", "(?!a)", "(?=b)", "(?<!a)", "(?<=b)", "(?<![a1])", r"(?!\d)"]
-QUANTS = ["", "", "", "*", "+", "?", "{2}", "{1,2}", "{2,}", "*?", "+?", "??", "{1,3}?"]
-
-
-def random_regex(rng, depth=0):
-    n = int(rng.integers(1, 5))
-    parts = []
-    for _ in range(n):
-        u = rng.random()
-        if depth < 2 and u < 0.25:
-            inner = random_regex(rng, depth + 1)
-            if rng.random() < 0.5:
-                inner = inner + "|" + random_regex(rng, depth + 1)
-            atom = ("(?:%s)" if rng.random() < 0.6 else "(%s)") % inner
-        else:
-            atom = ATOMS[int(rng.integers(0, len(ATOMS)))]
-        q = QUANTS[int(rng.integers(0, len(QUANTS)))]
-        if atom in ("^", "$", r"\b", r"\B") or atom.startswith("(?<") :
-            q = ""
-        if atom.startswith("(?=") or atom.startswith("(?!"):
-            q = ""
-        parts.append(atom + q)
-    return "".join(parts)
 
 
 def test_random_regex_differential(oracle, harness_lib):

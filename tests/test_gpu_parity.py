@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import oracle_regexes, PACK_RULES, PACK_TEXTS
+from helpers import oracle_regexes, PACK_RULES, PACK_TEXTS, random_regex
 from vainplex_openclaw_b200 import workload as W
 
 pytestmark = pytest.mark.gpu
@@ -427,4 +427,39 @@ def test_chunked_host_scan_equals_one_piece_scan(N, oracle):
     sub = 3000
     ewords, _ = oracle_policy(oracle, rules, data[: int(off[sub]) + 64], off[: sub + 1])
     assert np.array_equal(w_chunk[:sub], ewords)
+    rs.close()
+
+
+def test_random_regex_differential_on_the_kernels(N, oracle):
+    """The CPU tier fuzzes the compiler + VM on the host; this is the same differential through the real kernels:
+    ~250 random patterns (those both sides accept) as ONE rule set, dense / empty / astral matches, policy words + hits
+    and resolved spans against the oracle."""
+    rng = np.random.default_rng(777)
+    alphabet = ["a", "b", "c", "1", " ", "é", "😀", "\n", "A"]
+    texts = ["".join(alphabet[int(k)] for k in rng.integers(0, len(alphabet), int(rng.integers(0, 24)))) for _ in range(80)]
+    texts += ["", "a", "aaaa", "abcabc", "😀", "a😀b", "1 a1"]
+    msgs = [t.encode("utf-8") for t in texts]
+    data, off = N.pack(msgs)
+    rules = []
+    for _ in range(700):
+        src = random_regex(rng)
+        fl = 1 if rng.random() < 0.2 else 0
+        try:
+            rx = oracle.Regex(src, "i" if fl else "")
+            oracle.find_matches_batch([(rx, "custom")], data, off.astype(np.uint64))      # exponential backtracking -> RuntimeError
+        except (oracle.RegexSyntaxError, oracle.OracleUnsupported, RuntimeError):
+            continue
+        if N.rule_check(src, fl) != 0:
+            continue
+        rules.append((src, fl, int(rng.integers(0, 4))))
+        if len(rules) == 250:
+            break
+    assert len(rules) >= 200
+    rs = N.Ruleset(rules, strict=True)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits and np.array_equal(words, ewords) and len(ehits) > 3000
+    spans = rs.find_matches_batch(data, off)
+    got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+    assert got == oracle_spans(oracle, rules, data, off)
     rs.close()
