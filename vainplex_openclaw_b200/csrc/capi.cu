@@ -41,6 +41,9 @@ struct Ctx {
   // chunked host-buffer scans: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c
   static constexpr int kChunks = 8;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr; cudaEvent_t e_h2d[kChunks] = {}, e_done[kChunks] = {}; uint32_t* h_chunk_counters = nullptr;
+  // cg_redact_batch / cg_policy_verdict_batch staging (grow-only)
+  uint8_t* d_redact_out = nullptr; size_t cap_redact_out = 0; uint32_t* d_redact_meta = nullptr; size_t cap_redact_meta = 0;
+  uint32_t* d_verdicts = nullptr; size_t cap_verdicts = 0;
 } G;
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -389,7 +392,10 @@ int cg_init(int device) {
 void cg_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return;
-  cudaStreamSynchronize(G.stream);
+  cudaDeviceSynchronize();
+  cudaFree(G.d_redact_out); cudaFree(G.d_redact_meta); cudaFree(G.d_verdicts);
+  if (G.h_chunk_counters) cudaFreeHost(G.h_chunk_counters);
+  if (G.s_h2d) { cudaStreamDestroy(G.s_h2d); cudaStreamDestroy(G.s_d2h); for (int c = 0; c < Ctx::kChunks; c++) { cudaEventDestroy(G.e_h2d[c]); cudaEventDestroy(G.e_done[c]); } }
   cudaFree(G.d_bytes); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
   cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); cudaStreamDestroy(G.stream);
   G = Ctx();
@@ -462,7 +468,6 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode; rs->d_image_rw = const_cast<uint8_t*>(d_image);
   d.ncols_log2 = 0; while ((1 << d.ncols_log2) < P.ncols) d.ncols_log2++;
   d.nstates = (uint32_t)P.nstates; d.hot_states = H.hot_states; d.lut_off = H.lut_off; d.row_stride = H.row_stride;
-  d.scan_streams = 1; if (const char* e = getenv("CG_SCAN_STREAMS")) d.scan_streams = (uint32_t)atoi(e);
   d.debug_flags = 0; if (const char* e = getenv("CG_SCAN_DEBUG")) d.debug_flags = (uint32_t)atoi(e);   // 1: skip the slow path (timing experiments only, results wrong)
   if ((rc = upload(rs.get(), P.table, &d.table_full, 64))) return rc;
   if ((rc = upload(rs.get(), P.acc_index, &d.acc_index))) return rc;
@@ -636,8 +641,8 @@ int cg_policy_verdict_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t
   int rc = scan_host(rs, bytes, offsets, n, false, &hs);
   if (rc) return rc;
   if (!n) return CG_OK;
-  static uint32_t* d_verdicts = nullptr; static size_t cap_verdicts = 0;
-  if ((rc = grow(&d_verdicts, &cap_verdicts, (size_t)n))) return rc;
+  if ((rc = grow(&G.d_verdicts, &G.cap_verdicts, (size_t)n))) return rc;
+  uint32_t* d_verdicts = G.d_verdicts;
   cudaStream_t st = G.stream;
   CU(cudaMemsetAsync(d_verdicts, 0, (size_t)n * 4, st));
   int k = launch_verdicts(rs->dev, rs->work, d_verdicts, G.sm_count, st);
@@ -676,10 +681,11 @@ int cg_redact_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offset
   if ((out_spans && ns > spans_cap) || pos > out_cap || !out_bytes) return fail(CG_ERR_CAPACITY, "output buffer too small (see *out_need / *out_nspans)");
   if (out_spans) memcpy(out_spans, res.data(), (size_t)ns * sizeof(cg_span));
   cudaStream_t st = G.stream;
-  static uint8_t* d_out = nullptr; static size_t cap_out = 0; static uint32_t* d_meta = nullptr; static size_t cap_meta = 0;
-  if ((rc = grow(&d_out, &cap_out, (size_t)pos + 64))) return rc;
+  if ((rc = grow(&G.d_redact_out, &G.cap_redact_out, (size_t)pos + 64))) return rc;
+  uint8_t* d_out = G.d_redact_out;
   const size_t meta_words = 2 * ((size_t)n + 1) + 3 * (size_t)ns + 8 * (size_t)ns + 16;
-  if ((rc = grow(&d_meta, &cap_meta, meta_words))) return rc;
+  if ((rc = grow(&G.d_redact_meta, &G.cap_redact_meta, meta_words))) return rc;
+  uint32_t* d_meta = G.d_redact_meta;
   uint32_t* d_out_off = d_meta; uint32_t* d_span_begin = d_out_off + n + 1; uint32_t* d_start = d_span_begin + n + 1;
   uint32_t* d_len = d_start + ns; uint32_t* d_cat = d_len + ns; uint32_t* d_dig = d_cat + ns; d_dig += (8 - ((d_dig - d_meta) & 7)) & 7;   // 32-byte aligned digests
   CU(cudaMemcpyAsync(d_out_off, out_offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));

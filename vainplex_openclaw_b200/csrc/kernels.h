@@ -15,8 +15,8 @@ struct DevRuleset {
   uint32_t ncols_log2;
   uint32_t nstates;
   uint32_t hot_states;           // rows [0, hot_states) + one trap row are in the shared-memory image, the rest only in table_full
-  uint32_t scan_streams;         // message streams per lane in scan_kernel (1 or 2)
-  uint32_t debug_flags;          // CG_SCAN_DEBUG (timing experiments): bit 0 = skip the scan kernel's slow path
+  uint32_t debug_flags;          // CG_SCAN_DEBUG (experiments only): bit 0 = skip the scan kernel's slow path (results wrong),
+                                 //   bit 1 = histogram of VM cycles per event in counters[7..15]
   const uint16_t* table_full;    // complete level-1 table in HBM (L2-resident)
   const uint32_t* acc_index;     // nstates*ncols: accept id of an accepting transition
   const uint32_t* acc_offsets;   // CSR over accept ids -> factor ids
