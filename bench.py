@@ -145,11 +145,15 @@ def main():
     ap.add_argument("--len", type=int, default=MSG_LEN, dest="msg_len")
     ap.add_argument("--rules", type=int, default=N_RULES)
     ap.add_argument("--mode", type=int, default=int(os.environ.get("CG_PREFILTER_MODE", "2")))
+    ap.add_argument("--p-hit", type=float, default=None, help="fraction of messages with an injected rule-matching token (default 0.01; SURVEY 8d also names 0 and 0.10)")
     ap.add_argument("--seed-offset", type=int, default=0, help="shift the synthetic data seed (rank r of an N-GPU run uses offset r)")
     ap.add_argument("--no-merkle", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--merkle-leaves", type=int, default=MERKLE_LEAVES)
     args = ap.parse_args()
+    global P_HIT
+    if args.p_hit is not None:
+        P_HIT = args.p_hit
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
