@@ -89,6 +89,14 @@ struct VMS {
   bool matched; uint32_t m_start, m_end, m_end16; int m_prev;
 
   static CG_HD uint32_t capacity() { return Store::cap; }
+  static constexpr bool coop = Store::coop;
+  // warp-redundant runs: after any section only some lanes execute (lane 0 reporting a span, ...) the warp must be back
+  // together before the next shared-memory access -- every lane reads what every lane wrote
+  static CG_HD void rejoin() {
+#if defined(__CUDA_ARCH__)
+    if (Store::coop) __syncwarp();
+#endif
+  }
   CG_HD_NOINLINE VMS(const DevRuleset& r) : rs(r), gen(0), err(0) {}
   CG_HD_NOINLINE VMS(const DevRuleset& r, const Store& s) : rs(r), S(s), gen(0), err(0) {}
 
@@ -308,6 +316,7 @@ CG_HD_NOINLINE bool run_rule(VMX& vm, const DevRuleset& rs, uint32_t rule, const
     any = true;
     if (!SPANS) break;
     sink.span(vm.m_start, vm.m_end, count_units(m, len, vm.m_start), vm.m_end16);
+    VMX::rejoin();
     // lastIndex = end; after an empty match advance one code unit
     from = vm.m_end; from16 = vm.m_end16; prev = vm.m_prev; c = cursor_at(m, len, from);
     if (vm.m_end == vm.m_start) {

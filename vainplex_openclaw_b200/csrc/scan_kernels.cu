@@ -606,6 +606,7 @@ verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
       int bkt = 31 - __clz(cyc | 1u) - 10; bkt = bkt < 0 ? 0 : bkt > 7 ? 7 : bkt;
       atomicAdd(&w.counters[8 + bkt], 1u); atomicMax(&w.counters[7], cyc);
     }
+    __syncwarp();                                          // lane 0 reported; everyone together again before the next run touches shared memory
   }
   if (vm.err && lane == 0) atomicOr(&w.counters[3], vm.err);
 }
