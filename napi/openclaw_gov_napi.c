@@ -140,12 +140,44 @@ static napi_value js_merkle_root(napi_env env, napi_callback_info info) {
   return arr;
 }
 
+/* redactBatch(handle, bytes, offsets) -> { bytes: Uint8Array, offsets: Uint32Array, spans: Uint32Array (6 per span), digests: Uint8Array (32 per span) }
+ * = RedactionEngine.scanString for a batch (engine.ts:74-85,165-181) with the vault's default placeholder; the TS side
+ * stores the originals in the vault from spans + digests (vault.ts:75-128). */
+static napi_value js_redact_batch(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value argv[3]; cg_ruleset *rs; uint8_t *bytes, *offp; size_t nb, no;
+  NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+  NAPI_CALL(env, napi_get_value_external(env, argv[0], (void **)&rs));
+  if (!get_u8(env, argv[1], &bytes, &nb) || !get_u8(env, argv[2], &offp, &no) || no == 0) { napi_throw_type_error(env, NULL, "redactBatch(handle, Uint8Array, Uint32Array)"); return NULL; }
+  uint32_t n = (uint32_t)(no - 1), ns = 0, cap_spans = 256; uint64_t need = 0, cap_bytes = nb + 4096;
+  napi_value off_ab, off_arr; void *off_data;
+  napi_create_arraybuffer(env, (size_t)(n + 1) * 4, &off_data, &off_ab);
+  uint8_t *out = NULL, *dig = NULL; cg_span *spans = NULL; int rc;
+  for (;;) {
+    out = (uint8_t *)realloc(out, cap_bytes + 64); spans = (cg_span *)realloc(spans, sizeof(cg_span) * cap_spans); dig = (uint8_t *)realloc(dig, (size_t)cap_spans * 32);
+    rc = cg_redact_batch(rs, bytes, (const uint32_t *)offp, n, out, cap_bytes, &need, (uint32_t *)off_data, spans, cap_spans, &ns, dig);
+    if (rc == CG_ERR_CAPACITY && (need > cap_bytes || ns > cap_spans)) { if (need > cap_bytes) cap_bytes = need; if (ns > cap_spans) cap_spans = ns; continue; }
+    break;
+  }
+  if (rc != CG_OK) { free(out); free(spans); free(dig); napi_throw_error(env, NULL, cg_last_error()); return NULL; }
+  napi_value res, b_ab, b_arr, s_ab, s_arr, d_ab, d_arr; void *p;
+  napi_create_arraybuffer(env, (size_t)need, &p, &b_ab); memcpy(p, out, (size_t)need); napi_create_typedarray(env, napi_uint8_array, (size_t)need, b_ab, 0, &b_arr);
+  napi_create_arraybuffer(env, (size_t)ns * sizeof(cg_span), &p, &s_ab); memcpy(p, spans, (size_t)ns * sizeof(cg_span)); napi_create_typedarray(env, napi_uint32_array, (size_t)ns * 6, s_ab, 0, &s_arr);
+  napi_create_arraybuffer(env, (size_t)ns * 32, &p, &d_ab); memcpy(p, dig, (size_t)ns * 32); napi_create_typedarray(env, napi_uint8_array, (size_t)ns * 32, d_ab, 0, &d_arr);
+  napi_create_typedarray(env, napi_uint32_array, (size_t)n + 1, off_ab, 0, &off_arr);
+  free(out); free(spans); free(dig);
+  napi_create_object(env, &res);
+  napi_set_named_property(env, res, "bytes", b_arr); napi_set_named_property(env, res, "offsets", off_arr);
+  napi_set_named_property(env, res, "spans", s_arr); napi_set_named_property(env, res, "digests", d_arr);
+  return res;
+}
+
 static napi_value module_init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
     {"init", NULL, js_init, NULL, NULL, NULL, napi_default, NULL},
     {"createRuleset", NULL, js_create_ruleset, NULL, NULL, NULL, napi_default, NULL},
     {"scanBatch", NULL, js_scan_batch, NULL, NULL, NULL, napi_default, NULL},
     {"findMatchesBatch", NULL, js_find_matches_batch, NULL, NULL, NULL, napi_default, NULL},
+    {"redactBatch", NULL, js_redact_batch, NULL, NULL, NULL, napi_default, NULL},
     {"sha256Batch", NULL, js_sha256_batch, NULL, NULL, NULL, napi_default, NULL},
     {"merkleRoot", NULL, js_merkle_root, NULL, NULL, NULL, napi_default, NULL},
   };
