@@ -14,8 +14,9 @@
  * await, src/hooks.ts:360-365; the async bulk path wraps scanBatch in a libuv worker on the JS side):
  *   init(device?: number): void
  *   createRuleset(rules: {source: string, flags?: number, category?: number}[]): {handle: External, status: Int32Array}
- *   scanBatch(handle, bytes: Uint8Array, offsets: Uint32Array): {words: BigUint64Array, hits: Uint32Array /* msg,rule pairs */}
+ *   scanBatch(handle, bytes: Uint8Array, offsets: Uint32Array): {words: BigUint64Array, hits: Uint32Array}  // hits: msg,rule pairs
  *   findMatchesBatch(handle, bytes, offsets): Uint32Array  // 6 words per span: msg, rule, startByte, endByte, start16, end16
+ *   redactBatch(handle, bytes, offsets): {bytes, offsets, spans, digests}  // scanString for a batch, spliced on the device
  *   sha256Batch(bytes: Uint8Array, offsets: BigUint64Array): Uint8Array  // 32 bytes per item
  *   merkleRoot(bytes: Uint8Array, offsets: BigUint64Array): Uint8Array   // 32 bytes
  * Every failure throws a JS Error carrying cg_last_error(); the reference's try/catch + failMode
