@@ -29,6 +29,12 @@ __device__ __forceinline__ void sha_init(uint32_t h[8]) {
   h[4] = 0x510e527f; h[5] = 0x9b05688c; h[6] = 0x1f83d9ab; h[7] = 0x5be0cd19;
 }
 
+// a + b on the FMA pipe: IMAD a, ONE, b with ONE = 1 read from constant memory at run time (a literal 1 is folded back
+// into IADD3 by ptxas).  The kernels are bound by the integer ALU pipe (ncu: 95 % active, FMA pipe 6 %): SHF and LOP3 have
+// to run there, additions do not.
+__constant__ uint32_t kRuntimeOne = 1;
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b) { return a * kRuntimeOne + b; }
+
 // one compression; w[16] is clobbered (rolling message schedule, all in registers)
 __device__ __forceinline__ void sha_compress(uint32_t h[8], uint32_t w[16]) {
   uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
@@ -40,16 +46,16 @@ __device__ __forceinline__ void sha_compress(uint32_t h[8], uint32_t w[16]) {
       uint32_t w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
       uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
       uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-      wt = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
+      wt = add_fma(add_fma(w[t & 15], s0), add_fma(w[(t - 7) & 15], s1));
       w[t & 15] = wt;
     }
     uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
     uint32_t ch = (e & f) ^ (~e & g);
-    uint32_t t1 = hh + S1 + ch + K256[t] + wt;
+    uint32_t t1 = add_fma(add_fma(add_fma(hh, S1), add_fma(ch, K256[t])), wt);
     uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
     uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-    uint32_t t2 = S0 + mj;
-    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    uint32_t t2 = add_fma(S0, mj);
+    hh = g; g = f; f = e; e = add_fma(d, t1); d = c; c = b; b = a; a = add_fma(t1, t2);
   }
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
