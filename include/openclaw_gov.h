@@ -178,7 +178,9 @@ CG_API int cg_scan_join(cg_ruleset *rs, void *stream);
 
 /* Profile-guided residency.  The level-1 automaton usually has more states than fit into shared memory; which
  * rows are resident is decided from a state-visit histogram over a sample of real messages.  The first scan of a
- * rule set does this by itself on (a sample of) its own batch; call this to re-profile when the traffic changes.
+ * rule set does this by itself on (a sample of) its own batch, and cg_scan_batch_device repeats it when the slow-path
+ * rate of three consecutive batches is far above what it was right after the last profile (traffic drift); call this
+ * to force a re-profile.
  * Device pointers as for cg_scan_batch_device.  Results never depend on it, only the scan kernel's speed.
  * No counterpart in the reference (V8 compiles each RegExp on its own). */
 CG_API int cg_ruleset_adapt(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n, void *stream);

@@ -463,3 +463,36 @@ def test_random_regex_differential_on_the_kernels(N, oracle):
     got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
     assert got == oracle_spans(oracle, rules, data, off)
     rs.close()
+
+
+def test_residency_follows_traffic_drift(N):
+    """The device path re-profiles by itself: after the rule set adapted to one vocabulary, a few batches of another
+    vocabulary bring the scan kernel's slow-path entries down again (results unchanged throughout)."""
+    import torch
+    rl = W.make_rules(500)
+    rs = N.Ruleset(W.rules_as_tuples(rl), strict=True)
+    n = 200000
+    st = torch.cuda.Stream()
+    def dev_batch(seed):
+        d, o, _ = W.make_messages(n, 256, rl, p_hit=0.01, seed=seed, device="cuda")
+        return d, o.to(torch.int32)
+    out = torch.zeros(n, dtype=torch.int64, device="cuda")
+    def run(d, o):
+        rs.scan_batch_device(d.data_ptr(), o.data_ptr(), n, out.data_ptr(), st.cuda_stream)
+        rs.scan_join(st.cuda_stream); st.synchronize()
+        return out.clone(), rs.work_counters()
+    a = dev_batch(W.SEED_MSG)
+    b = dev_batch(W.SEED_MSG + 1)                        # another vocabulary: other level-1 states are hot
+    for _ in range(3):
+        run(*a)
+    first_words, first = run(*b)
+    entries = [first[6]]
+    for _ in range(8):
+        words, c = run(*b)
+        assert torch.equal(words, first_words)
+        entries.append(c[6])
+    cold = [max(0, e - first[4]) for e in entries]     # entries not explained by accepting transitions
+    assert cold[-1] * 3 < cold[0], entries              # re-profiled on the new traffic
+    host_words, _ = rs.scan_batch(b[0].cpu().numpy(), b[1].cpu().numpy().astype(np.uint32), want_hits=True)
+    assert np.array_equal(first_words.cpu().numpy().view(np.uint64), host_words)
+    rs.close()
