@@ -47,40 +47,58 @@ def measured_peaks():
 
 
 class ClockSampler:
-    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML poll every ~0.5 ms between
+    start (construction) and stop() -- the region is only a few milliseconds long, an `nvidia-smi -lms` child would
+    mostly report the idle GPU after it.  Falls back to one nvidia-smi query if NVML is unavailable."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("hw_power_brake", 0x80))
 
     def __init__(self, index: int):
-        self.p = None
+        import threading
+        self.samples, self.reasons, self.max_mhz, self._stop, self.t = [], set(), None, False, None
+        self.index = index
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            h = None
+            try:
+                pr = torch.cuda.get_device_properties(index)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop:
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        for name, bit in self.REASONS:
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.0005)
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
         except Exception:
-            self.p = None
+            self.t = None
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            out = self.p.communicate(timeout=5)[0]
-        except Exception:
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
+        if self.t is None:
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        load = [s for s in sm if s > 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "source": "nvidia-smi after the region (NVML unavailable)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        self._stop = True
+        self.t.join(timeout=2)
+        sm = self.samples
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "NVML polled inside the timed region"}
 
 
 def reference_arm(args, rank, world, emit=None):
@@ -221,10 +239,10 @@ def main():
     rs.scan_join(stream.cuda_stream)                 # the stream waits for the tails of the last two batches
     e1.record(stream)
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
     pipelined_equal = bool(torch.equal(words2[0], words_seq) and torch.equal(words2[1], words_seq))
     launches = N.launch_count() - l0
-    clocks = sampler.stop() if sampler else None
     per_rank_ms = [ms / args.steps]
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
