@@ -70,17 +70,22 @@ class ClockSampler:
                 h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM); pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)   # first calls are slow: not inside the region
+
             def loop():
+                k = 0
                 while not self._stop:
                     try:
                         self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                        for name, bit in self.REASONS:
-                            if r & bit:
-                                self.reasons.add(name)
+                        if k % 3 == 0:
+                            r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                            for name, bit in self.REASONS:
+                                if r & bit:
+                                    self.reasons.add(name)
                     except Exception:
                         pass
-                    time.sleep(0.0005)
+                    k += 1
+                    time.sleep(0.0003)
             self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()
         except Exception:

@@ -85,7 +85,7 @@ struct cg_ruleset {
   uint32_t grow_l1 = 0, grow_slot = 0, grow_ev = 0, grow_units = 0;     // capacities learnt from overflows
   // drift detection: slow-path entries that are not explained by accepting transitions ("cold" entries), right after the
   // last adaptation and now; three batches in a row far above the baseline trigger a new adaptation
-  uint32_t cold_baseline = 0xffffffffu; int cold_strikes = 0; uint32_t adaptations = 0;
+  double cold_baseline = -1.0; int cold_strikes = 0; uint32_t adaptations = 0; uint32_t mirrored_n = 0;   // rates are per message of the mirrored batch
   bool segmented = false;         // long messages seen (first scan / cg_ruleset_adapt): scans cut them into units (kernels.h)
   uint32_t want_units = 0;        // unit-table capacity for the batches seen so far
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
@@ -175,7 +175,7 @@ int decide_segmentation(cg_ruleset* rs, const uint32_t* d_off, uint32_t n, cudaS
 // pointers: a captured graph stays valid).  Results never depend on this, only how often the scan's slow path runs.
 int adapt_ruleset(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, cudaStream_t st) {
   rs->adapted = true; rs->adaptations++;
-  rs->cold_baseline = 0xffffffffu; rs->cold_strikes = 0; rs->cnt_pending = false;      // the next mirrored step sets the new baseline
+  rs->cold_baseline = -1.0; rs->cold_strikes = 0; rs->cnt_pending = false;      // the next mirrored step sets the new baseline
   HostImage& H = rs->host;
   if (n) { int rc = decide_segmentation(rs, d_off, n, st); if (rc) return rc; }
   if (H.pf.mode == 4 || !n || (uint32_t)H.pf.nstates <= H.hot_states) return CG_OK;      // everything is resident already
@@ -733,9 +733,9 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     if (flags & ERR_EVENT_OVERFLOW) rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096));
     if (flags & ERR_UNIT_OVERFLOW) rs->grow_units = std::max<uint32_t>(rs->grow_units, hc[16] + hc[16] / 8 + 64);
     // has the traffic drifted away from what the resident rows were chosen for?
-    const uint32_t cold = hc[6] > hc[4] ? hc[6] - hc[4] : 0u;
-    if (rs->cold_baseline == 0xffffffffu) rs->cold_baseline = cold;
-    else if (cold > 4u * std::max(rs->cold_baseline, 4096u)) { if (++rs->cold_strikes >= 3) { rs->adapted = false; rs->cold_strikes = 0; } }
+    const double cold = (hc[6] > hc[4] ? hc[6] - hc[4] : 0u) / (double)std::max<uint32_t>(rs->mirrored_n, 1u);
+    if (rs->cold_baseline < 0) rs->cold_baseline = cold;
+    else if (cold > 4.0 * std::max(rs->cold_baseline, 0.004)) { if (++rs->cold_strikes >= 3) { rs->adapted = false; rs->cold_strikes = 0; } }
     else rs->cold_strikes = 0;
   }
   const uint32_t want_l1 = std::max(std::max<uint32_t>(std::max<uint32_t>(4 * n, 1u << 16), w.l1_cap), rs->grow_l1),
@@ -808,7 +808,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     if (!rs->cnt_pending) {                                 // (one mirror copy in flight at a time)
       CU(cudaMemcpyAsync(rs->h_counters, w.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, st));
       CU(cudaEventRecord(rs->e_cnt, st));
-      rs->cnt_pending = true;
+      rs->cnt_pending = true; rs->mirrored_n = n;
     }
   }
   return rc;
