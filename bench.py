@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--msgs", type=int, default=N_MSGS)
     ap.add_argument("--len", type=int, default=MSG_LEN, dest="msg_len")
     ap.add_argument("--rules", type=int, default=N_RULES)
-    ap.add_argument("--mode", type=int, default=int(os.environ.get("CG_PREFILTER_MODE", "2")))
+    ap.add_argument("--stride", type=int, default=0, help="gram filter stride: 0 = the compiler's choice, 2 or 4")
     ap.add_argument("--p-hit", type=float, default=None, help="fraction of messages with an injected rule-matching token (default 0.01; SURVEY 8d also names 0 and 0.10)")
     ap.add_argument("--seed-offset", type=int, default=0, help="shift the synthetic data seed (rank r of an N-GPU run uses offset r)")
     ap.add_argument("--no-merkle", action="store_true")
@@ -196,7 +196,7 @@ def main():
     rl = W.make_rules(R)
     rules = W.rules_as_tuples(rl)
     t0 = time.perf_counter()
-    rs = N.Ruleset(rules, options=args.mode, strict=True)
+    rs = N.Ruleset(rules, options=args.stride, strict=True)
     compile_s = time.perf_counter() - t0
     info = rs.info()
     data, off64, inj = W.make_messages(n, L, rl, p_hit=P_HIT, seed=W.SEED_MSG + rank + args.seed_offset, device=dev,
@@ -227,6 +227,7 @@ def main():
         step(); torch.cuda.synchronize(); kms.append(N.last_kernel_ms())
     N.set_profiling(False)
     kms = np.array(kms)
+    rs.scan_join(stream.cuda_stream)
     counters = rs.work_counters()
     words = words2[(step_no[0] - 1) & 1]             # results of the last (sequential, profiled) step: checked against the e2e path below
     words_seq = words.clone()
@@ -241,8 +242,8 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
-    rs.scan_join(stream.cuda_stream)                 # the stream waits for the tails of the last two batches
     e1.record(stream)
+    rs.scan_join(stream.cuda_stream)                 # waits for the stream; raises if a batch overflowed a queue
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
@@ -412,18 +413,18 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "%d x %dB synthetic msgs x %d-rule firewall scan per GPU (BASELINE configs[1]), policy semantics (RegExp.test per rule), p_hit=%.2f" % (n, L, R, P_HIT),
                    "rules": R, "msg_len": L, "msgs_per_gpu": n, "l2": "inputs (%.0f MB/step) larger than the 126 MB L2" % (n * L / 1e6),
-                   "prefilter": {"mode": int(info.prefilter_mode), "states": int(info.prefilter_states), "cols": int(info.prefilter_cols),
-                                 "window_min": int(info.prefilter_factor_len) & 0xff, "window_max": int(info.prefilter_factor_len) >> 8, "factors": int(info.n_factors), "smem_bytes": int(info.prefilter_bytes),
-                                 "always_candidate_rules": int(info.n_always_candidate)},
-                   "pipeline": ("CG_PIPELINE=1: two batches in flight" if os.environ.get("CG_PIPELINE") == "1" else "off: in-order step replayed as one CUDA graph") +
-                               "; results of the timed steps equal the profiled step: %s" % pipelined_equal,
+                   "prefilter": {"stride": int(info.stride), "gram_keys": int(info.gram_keys), "level1b_entries": int(info.gram_entries),
+                                 "factor_len_min": int(info.factor_len) & 0xff, "factor_len_max": int(info.factor_len) >> 8, "factors": int(info.n_factors),
+                                 "bitmap_bytes": int(info.bitmap_bytes), "smem_image_bytes": int(info.image_bytes), "tables_resident": bool(info.tables_resident),
+                                 "trigger_bytes": int(info.n_triggers), "always_candidate_rules": int(info.n_always_candidate)},
+                   "step": "in-order step replayed as one CUDA graph; results of the timed steps equal the profiled step: %s" % pipelined_equal,
                    "compile_s": compile_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "kernel": "scan_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms},
         "kernel_ms_note": "kernel_ms: CUDA events inside the library around each kernel of one step (profiling mode, no graph); ms_per_step: the graph-replayed steady state",
-        "kernel_ms": {"scan": scan_ms, "confirm": float(np.median(kms[:, 1])), "verify": float(np.median(kms[:, 2])), "finalize": float(np.median(kms[:, 3]))},
-        "candidates": {"level1_events": counters[4], **({"vm_cycle_hist_2^11..": list(counters[8:16]), "vm_cycle_max": counters[7]} if os.environ.get("CG_SCAN_DEBUG") == "2" else {}), "slow_warp_entries": counters[6], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
+        "kernel_ms": {"scan": scan_ms, "resolve": float(np.median(kms[:, 1])), "verify": float(np.median(kms[:, 2])), "finalize": float(np.median(kms[:, 3]))},
+        "candidates": {"confirmed_factor_occurrences": counters[4], **({"vm_cycle_hist_2^11..": list(counters[8:16]), "vm_cycle_max": counters[7]} if os.environ.get("CG_SCAN_DEBUG") == "2" else {}), "flagged_grams": counters[6], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
                        "hit_messages": int((words != 0).sum().item()), "injected": len(inj)},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "msgs/s", "h2d_bytes_per_step": int(n * L + 4 * (n + 1)), "d2h_bytes_per_step": int(8 * n + 64),

@@ -47,12 +47,10 @@ extern "C" {
 #define CG_CAT_PII        2u
 #define CG_CAT_CUSTOM     3u
 
-/* ---- ruleset options */
-#define CG_OPT_PREFILTER_DIRECT7 0u /* level-1 table with 128 columns indexed by byte & 0x7f */
-#define CG_OPT_PREFILTER_LUT     1u /* byte->class LUT (<= 64 classes) + compact table */
-#define CG_OPT_PREFILTER_FOLD6   2u /* DFA with 64 columns from SWAR-folded 6-bit byte classes (default) */
-#define CG_OPT_PREFILTER_FOLD5   3u /* DFA with 32 columns (byte & 0x1f) */
-#define CG_OPT_PREFILTER_FP      4u /* lane-private fingerprint table over 4-byte windows (small rule sets; falls back to FOLD6) */
+/* ---- ruleset options: stride of the gram filter */
+#define CG_OPT_STRIDE_AUTO 0u /* 4 when every factor of the set can be covered at four alignments, else 2 (default) */
+#define CG_OPT_STRIDE2     2u /* probe the gram at every even byte offset */
+#define CG_OPT_STRIDE4     4u /* probe every aligned 4-byte word only (rule sets of long literals) */
 
 typedef struct cg_ruleset cg_ruleset;
 
@@ -77,8 +75,8 @@ typedef struct cg_span {    /* one element of PatternRegistry.findMatches()'s re
 
 typedef struct cg_ruleset_info {
   uint32_t n_rules, n_ok, n_always_candidate, n_sets;
-  uint32_t prefilter_mode, prefilter_states, prefilter_cols, prefilter_factor_len /* window min | max<<8 */, prefilter_bytes;
-  uint32_t program_words, n_factors, prefilter_hot_states;
+  uint32_t stride, gram_keys, gram_entries, factor_len /* min | max<<8 */, image_bytes /* staged into shared memory per CTA */;
+  uint32_t program_words, n_factors, bitmap_bytes, n_triggers, tables_resident;
 } cg_ruleset_info;
 
 typedef struct cg_stats {   /* cumulative since cg_init; surfaced by governance.status (index.ts:103-114) */
@@ -99,8 +97,8 @@ CG_API uint64_t cg_launch_count(void);   /* kernels launched by this library so 
 /* measurement hooks (the reference's ScanResult.elapsedMs / evaluationUs, src/redaction/engine.ts:54,65):
  * with profiling on, CUDA events bracket each kernel of a scan step on its stream. */
 CG_API int cg_set_profiling(int on);
-CG_API int cg_last_kernel_ms(float out_ms[4]);          /* scan, confirm, verify, finalize of the last completed step */
-CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out16[16]); /* slots, VM pairs, spans, flags, level-1 events, (internal), slow-path warp entries, reserved */
+CG_API int cg_last_kernel_ms(float out_ms[4]);          /* scan, resolve, verify, finalize of the last completed step */
+CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out16[16]); /* slots, VM pairs, spans, flags, confirmed factor occurrences, (internal), flagged grams, reserved */
 
 /* ---- rule-set compile.  Replaces `new RegExp(pattern)` in buildPolicyIndex
  * (src/policy-loader.ts:119-128), compileCustomPattern (src/redaction/registry.ts:249-281) and
@@ -156,34 +154,19 @@ CG_API int cg_redact_batch(cg_ruleset *rs, const uint8_t *bytes, const uint32_t 
                            uint8_t *out_bytes, uint64_t out_cap, uint64_t *out_need, uint32_t *out_offsets,
                            cg_span *out_spans, uint32_t spans_cap, uint32_t *out_nspans, uint8_t *out_digests32);
 
-/* ---- device-resident variants (inputs/outputs already in HBM; used by bench.py `value` and by
- * callers that pipeline their own copies).  Pointers are CUDA device pointers; `stream` is a
- * cudaStream_t (NULL = the library's own stream); asynchronous w.r.t. the host.
- * d_bytes must be readable for 16 bytes past offsets[n] (padding).
- * Queue capacities: a batch that overflows an internal queue (far more level-1 events / candidates than usual) sets a
- * flag in cg_scan_work_counters()[3] and its result words are incomplete; the library sees the flag at the next call
- * and grows the scratch before that call runs.  (cg_scan_batch, the host-buffer call, retries by itself.) */
+/* ---- device-resident variant (inputs/outputs already in HBM; used by bench.py `value` and by callers that pipeline
+ * their own copies).  Pointers are CUDA device pointers; `stream` is a cudaStream_t (NULL = the library's own stream);
+ * asynchronous w.r.t. the host, strictly in order on `stream`.
+ * d_bytes must be 16-byte aligned and readable for 16 bytes past offsets[n] (padding; any content).
+ * Queue capacities: a batch that overflows an internal queue (far more candidates than usual) cannot be re-run by the
+ * library (the call has long returned).  Instead EVERY result word of that batch is set to 0xffffffffffffffff
+ * ("incomplete") by the device, the scratch is grown before the next call runs, and cg_scan_join reports
+ * CG_ERR_CAPACITY once: scan that batch again.  (cg_scan_batch, the host-buffer call, retries by itself.) */
 CG_API int cg_scan_batch_device(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n,
                                 void *d_out_words, void *stream);
-
-/* With CG_PIPELINE=1 in the environment cg_scan_batch_device keeps up to two batches in flight: batch k's confirm /
- * verify / finalize run on a stream of the library's own while `stream` already scans batch k+1.  Then
- *   - the results of a batch are complete on `stream` only after the NEXT BUT ONE call on the same rule set, or after
- *     cg_scan_join(rs, stream) (which makes `stream` wait for everything still in flight; it does not block the host);
- *   - d_out_words and the input buffers of a batch must not be reused for writing before that point (alternate two
- *     output buffers, as bench.py does).
- * By default (no pipelining) every call is strictly in order on `stream` and cg_scan_join is a no-op; callers that
- * always join before reading results work in both modes. */
+/* Waits for `stream` and returns the status of every device-path batch issued since the previous join: CG_OK,
+ * CG_ERR_CAPACITY (see above) or CG_ERR_TOO_LARGE (the VM ran out of thread-list space; words all ones as well). */
 CG_API int cg_scan_join(cg_ruleset *rs, void *stream);
-
-/* Profile-guided residency.  The level-1 automaton usually has more states than fit into shared memory; which
- * rows are resident is decided from a state-visit histogram over a sample of real messages.  The first scan of a
- * rule set does this by itself on (a sample of) its own batch, and cg_scan_batch_device repeats it when the slow-path
- * rate of three consecutive batches is far above what it was right after the last profile (traffic drift); call this
- * to force a re-profile.
- * Device pointers as for cg_scan_batch_device.  Results never depend on it, only the scan kernel's speed.
- * No counterpart in the reference (V8 compiles each RegExp on its own). */
-CG_API int cg_ruleset_adapt(cg_ruleset *rs, const void *d_bytes, const void *d_offsets, uint32_t n, void *stream);
 
 /* ---- SHA-256.  Replaces createHash("sha256").update(s).digest() at src/util.ts:77-79,
  * src/redaction/vault.ts:26-28 (and nats/src/hooks.ts:90-94) for a batch of n byte strings. */

@@ -63,7 +63,7 @@ static napi_value js_create_ruleset(napi_env env, napi_callback_info info) {
   napi_create_arraybuffer(env, (size_t)n * 4, &status_data, &status_ab);
   napi_create_typedarray(env, napi_int32_array, n, status_ab, 0, &status);
   cg_ruleset *rs = NULL;
-  int rc = cg_ruleset_create(rules, n, CG_OPT_PREFILTER_FOLD6, &rs, (int32_t *)status_data);
+  int rc = cg_ruleset_create(rules, n, CG_OPT_STRIDE_AUTO, &rs, (int32_t *)status_data);
   for (uint32_t i = 0; i < n; i++) free(bufs[i]);
   free(bufs); free(rules);
   if (rc != CG_OK) { napi_throw_error(env, NULL, cg_last_error()); return NULL; }

@@ -32,12 +32,12 @@ def harness_lib():
     csrc = os.path.join(ROOT, "vainplex_openclaw_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "native", "vm_harness.cpp"), os.path.join(csrc, "rulec.cpp"),
             os.path.join(csrc, "ruleset_image.cpp")]
-    deps = srcs + [os.path.join(csrc, h) for h in ("pike_vm.h", "prefilter_dev.h", "rulec.h", "kernels.h", "ruleset_image.h")]
+    deps = srcs + [os.path.join(csrc, h) for h in ("pike_vm.h", "gram_filter.h", "rulec.h", "kernels.h", "ruleset_image.h")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-o", lib] + srcs)
     L = C.CDLL(lib)
     L.harness_create.restype = C.c_void_p
-    L.harness_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
+    L.harness_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
     L.harness_destroy.argtypes = [C.c_void_p]
     L.harness_info.argtypes = [C.c_void_p, C.c_void_p]
     L.harness_rule_error.restype = C.c_char_p
@@ -45,13 +45,11 @@ def harness_lib():
     L.harness_rule_nfactors.argtypes = [C.c_void_p, C.c_uint32]
     L.harness_find_all.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32]
     L.harness_test.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]
-    L.harness_candidates.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-    L.harness_policy_hits.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p]
-    L.harness_l1_hist.restype = C.c_uint64
-    L.harness_l1_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
-    L.harness_rank.argtypes = [C.c_void_p, C.c_void_p]
-    L.harness_image.restype = C.c_void_p
-    L.harness_image.argtypes = [C.c_void_p, C.c_void_p]
-    L.harness_table.restype = C.c_void_p
-    L.harness_table.argtypes = [C.c_void_p]
+    L.harness_candidates.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.harness_policy_hits.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.harness_policy_hits_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.harness_batch_rates.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    L.harness_l1_factor_counts.restype = C.c_uint32
+    L.harness_l1_factor_counts.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p]
+    L.harness_dump_factors.argtypes = [C.c_void_p]
     return L

@@ -7,24 +7,25 @@ import numpy as np
 class Harness:
     """Host-compiled product compiler + VM (tests/native/vm_harness.cpp)."""
 
-    def __init__(self, L, rules, mode=2, budget_kb=0, max_factor_len=0):
+    def __init__(self, L, rules, stride=0, bitmap_kb=0, max_keys=0):
         self.L = L
         self.srcs = [r[0] if isinstance(r[0], bytes) else r[0].encode("utf-8", "surrogatepass") for r in rules]
         arr = (C.c_char_p * max(1, len(rules)))(*self.srcs)
         lens = np.array([len(s) for s in self.srcs] or [0], dtype=np.uint32)
         flags = np.array([r[1] for r in rules] or [0], dtype=np.uint32)
         self.status = np.zeros(max(1, len(rules)), dtype=np.int32)
-        self.h = L.harness_create(arr, lens.ctypes.data, flags.ctypes.data, len(rules), mode, budget_kb, max_factor_len,
+        self.h = L.harness_create(arr, lens.ctypes.data, flags.ctypes.data, len(rules), stride, bitmap_kb, max_keys,
                                   self.status.ctypes.data)
         assert self.h
         self.n = len(rules)
         self.rw = max(1, (self.n + 31) // 32)
 
     def info(self):
-        o = np.zeros(8, dtype=np.uint32)
+        o = np.zeros(16, dtype=np.uint32)
         self.L.harness_info(self.h, o.ctypes.data)
-        return dict(nstates=int(o[0]), n_factors=int(o[1]), ncols=int(o[2]), window_min=int(o[3]) & 0xff,
-                    window_max=int(o[3]) >> 8, n_always=int(o[4]), image_bytes=int(o[5]), prog_words=int(o[6]), mode=int(o[7]))
+        return dict(keys=int(o[0]), n_factors=int(o[1]), stride=int(o[2]), factor_min=int(o[3]) & 0xff, factor_max=int(o[3]) >> 8,
+                    n_always=int(o[4]), image_bytes=int(o[5]), prog_words=int(o[6]), entries=int(o[7]), shapes=int(o[8]),
+                    triggers=int(o[9]), bitmap_bytes=int(o[10]), tables_resident=int(o[11]))
 
     def find_all(self, rule, msg: bytes):
         cap = 64
@@ -41,45 +42,44 @@ class Harness:
         assert r >= 0
         return bool(r)
 
-    def candidates2(self, msg: bytes, want_spans=False):
-        """-> (queued-for-VM rules, direct-hit rules, number of level-1 accepting transitions)"""
+    def candidates2(self, msg: bytes, want_spans=False, lead=16, seed=1):
+        """-> (queued-for-VM rules, direct-hit rules, number of flagged grams).  The message sits `lead` bytes into a
+        buffer of seeded filler (its neighbours in a batch); lead < 3 exercises the scan kernel's head check."""
         c = np.zeros(self.rw, dtype=np.uint32)
         d = np.zeros(self.rw, dtype=np.uint32)
         l1 = np.zeros(1, dtype=np.uint32)
-        self.L.harness_candidates(self.h, msg, len(msg), c.ctypes.data, d.ctypes.data, 1 if want_spans else 0, l1.ctypes.data)
+        self.L.harness_candidates(self.h, msg, len(msg), c.ctypes.data, d.ctypes.data, 1 if want_spans else 0, l1.ctypes.data, lead, seed)
         f = lambda bits: {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
         return f(c), f(d), int(l1[0])
 
-    def policy_hits(self, msg: bytes):
-        """rules with RegExp.test(msg) true, computed the way the device pipeline does (level 1 -> confirm -> island VM)"""
+    def policy_hits(self, msg: bytes, lead=16, seed=1):
+        """rules with RegExp.test(msg) true, computed the way the device pipeline does (gram filter -> exact factor -> island VM)"""
         bits = np.zeros(self.rw, dtype=np.uint32)
-        self.L.harness_policy_hits(self.h, msg, len(msg), bits.ctypes.data)
+        self.L.harness_policy_hits(self.h, msg, len(msg), bits.ctypes.data, lead, seed)
         return {r for r in range(self.n) if (bits[r >> 5] >> (r & 31)) & 1}
 
-    def l1_hist(self, data: np.ndarray, n_msgs: int, msg_len: int):
-        """(visits per level-1 state, accepting transitions) over n_msgs fixed-length messages"""
-        hist = np.zeros(self.info()["nstates"], dtype=np.uint64)
-        acc = self.L.harness_l1_hist(self.h, data.ctypes.data, n_msgs, msg_len, hist.ctypes.data)
-        return hist, int(acc)
+    def policy_hits_batch(self, data: np.ndarray, off: np.ndarray):
+        """[(msg, rule)] sorted: the device pipeline restated over a packed batch (buffer-relative gram positions, head
+        check, message lookup); data must extend 16 bytes past off[-1]"""
+        n = len(off) - 1
+        o = np.ascontiguousarray(off, dtype=np.uint32)
+        bits = np.zeros(max(1, n) * self.rw, dtype=np.uint32)
+        self.L.harness_policy_hits_batch(self.h, data.ctypes.data, o.ctypes.data, n, bits.ctypes.data)
+        bits = bits.reshape(max(1, n), self.rw)
+        return [(m, r) for m in range(n) for r in range(self.n) if (bits[m, r >> 5] >> (r & 31)) & 1]
 
-    def rank(self, visits: np.ndarray):
-        """profile-guided residency: renumber the states, most visited first"""
-        v = np.ascontiguousarray(visits, dtype=np.uint32)
-        self.L.harness_rank(self.h, v.ctypes.data)
+    def batch_rates(self, data: np.ndarray, n_msgs: int, msg_len: int):
+        """(flagged grams, confirmed factor occurrences) over n_msgs fixed-length messages laid out back to back"""
+        o = np.zeros(2, dtype=np.uint64)
+        self.L.harness_batch_rates(self.h, data.ctypes.data, n_msgs, msg_len, o.ctypes.data)
+        return int(o[0]), int(o[1])
 
-    def image(self):
-        """-> (image bytes, hot_states, row_stride, lut_off, full table [nstates, ncols] u16)"""
-        o = np.zeros(4, dtype=np.uint32)
-        ptr = self.L.harness_image(self.h, o.ctypes.data)
-        img = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(int(o[0]),)).copy()
-        inf = self.info()
-        tab = np.ctypeslib.as_array(C.cast(self.L.harness_table(self.h), C.POINTER(C.c_uint16)), shape=(inf["nstates"], inf["ncols"])).copy()
-        return img, int(o[1]), int(o[2]), int(o[3]), tab
+    def dump(self):
+        self.L.harness_dump_factors(self.h)
 
-    def candidates(self, msg: bytes):
-        c, d, _ = self.candidates2(msg)
+    def candidates(self, msg: bytes, lead=16, seed=1):
+        c, d, _ = self.candidates2(msg, lead=lead, seed=seed)
         return c | d
-
     def close(self):
         if self.h:
             self.L.harness_destroy(self.h)

@@ -18,7 +18,7 @@ ERR_NAMES = {-1: "INVALID_ARG", -2: "NOT_INITIALIZED", -3: "CUDA", -4: "SYNTAX",
 CG_ERR_SYNTAX, CG_ERR_UNSUPPORTED, CG_ERR_TOO_LARGE, CG_ERR_CAPACITY = -4, -5, -6, -7
 FLAG_ICASE = 1
 CAT = {"credential": 0, "financial": 1, "pii": 2, "custom": 3}
-OPT_DIRECT7, OPT_LUT, OPT_FOLD6, OPT_FOLD5, OPT_FP = 0, 1, 2, 3, 4
+OPT_STRIDE_AUTO, OPT_STRIDE2, OPT_STRIDE4 = 0, 2, 4
 
 
 class GovError(RuntimeError):
@@ -32,9 +32,9 @@ class cg_rule(C.Structure):
 
 
 class cg_ruleset_info(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("n_rules", "n_ok", "n_always_candidate", "n_sets", "prefilter_mode",
-                                          "prefilter_states", "prefilter_cols", "prefilter_factor_len",
-                                          "prefilter_bytes", "program_words", "n_factors", "prefilter_hot_states")]
+    _fields_ = [(n, C.c_uint32) for n in ("n_rules", "n_ok", "n_always_candidate", "n_sets", "stride", "gram_keys",
+                                          "gram_entries", "factor_len", "image_bytes", "program_words", "n_factors",
+                                          "bitmap_bytes", "n_triggers", "tables_resident")]
 
 
 class cg_stats(C.Structure):
@@ -48,7 +48,7 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
                        ("start16", np.uint32), ("end16", np.uint32)])
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
-           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_ruleset_adapt", "cg_scan_join", "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch",
+           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_scan_join", "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch",
            "cg_merkle_log_create", "cg_merkle_log_destroy", "cg_merkle_log_append", "cg_merkle_log_size", "cg_merkle_log_root",
            "cg_merkle_log_frontier", "cg_merkle_log_restore", "cg_merkle_log_proof", "cg_merkle_verify_proof",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
@@ -84,7 +84,6 @@ def load():
     L.cg_set_profiling.argtypes = [i32]; L.cg_set_profiling.restype = i32
     L.cg_last_kernel_ms.argtypes = [vp]; L.cg_last_kernel_ms.restype = i32
     L.cg_scan_work_counters.argtypes = [vp, vp]; L.cg_scan_work_counters.restype = i32
-    L.cg_ruleset_adapt.argtypes = [vp, vp, vp, u32, vp]; L.cg_ruleset_adapt.restype = i32
     L.cg_scan_join.argtypes = [vp, vp]; L.cg_scan_join.restype = i32
     L.cg_redact_batch.argtypes = [vp, vp, vp, u32, vp, u64, vp, vp, vp, u32, vp, vp]; L.cg_redact_batch.restype = i32
     L.cg_ruleset_set_policy.argtypes = [vp, vp, vp, u32]; L.cg_ruleset_set_policy.restype = i32
@@ -157,7 +156,7 @@ def pack(messages) -> tuple[np.ndarray, np.ndarray]:
 class Ruleset:
     """cg_ruleset handle.  rules: iterable of (source:str|bytes, flags:int, category:int)."""
 
-    def __init__(self, rules, options: int = OPT_FOLD6, strict: bool = False):
+    def __init__(self, rules, options: int = OPT_STRIDE_AUTO, strict: bool = False):
         L = load()
         if not _inited:
             init()
@@ -258,18 +257,16 @@ class Ruleset:
             return out[:need.value], out_off, spans[:ns.value], dig[:ns.value]
 
     def work_counters(self):
-        """(slots, VM pairs, spans, error flags, level-1 events, 0, slow-path warp entries, 0) of the last completed step."""
+        """(slots, VM pairs, spans, error flags, confirmed factor occurrences, cursor, flagged grams, ...) of the last step whose
+        counters reached the host (device path: after scan_join)."""
         out = np.zeros(16, dtype=np.uint32)
         check(load().cg_scan_work_counters(self.handle, out.ctypes.data))
         return tuple(int(x) for x in out)
 
     def scan_join(self, stream: int = 0):
-        """Make `stream` wait for every batch scan_batch_device still has in flight (does not block the host)."""
+        """Wait for `stream`; raises if a batch issued through scan_batch_device since the last join overflowed a queue
+        (its result words are all ones) -- the scratch has been grown, scan it again."""
         check(load().cg_scan_join(self.handle, stream))
-
-    def adapt(self, d_bytes: int, d_off: int, n: int, stream: int = 0):
-        """Re-profile which level-1 rows are shared-memory resident on a sample of this (device-resident) batch."""
-        check(load().cg_ruleset_adapt(self.handle, d_bytes, d_off, n, stream))
 
     def scan_batch_device(self, d_bytes: int, d_off: int, n: int, d_words: int, stream: int = 0):
         check(load().cg_scan_batch_device(self.handle, d_bytes, d_off, n, d_words, stream))

@@ -73,37 +73,25 @@ struct cg_ruleset {
   DevRuleset dev{};
   std::vector<void*> allocs;
   uint32_t n_sets = 0, program_words = 0;
-  ScanWork work{};                // scratch of the (sequential) host path and of even pipelined steps
-  ScanWork work2{};               // scratch of odd pipelined steps (cg_scan_batch_device keeps two batches in flight)
-  uint64_t seq = 0;               // pipelined steps issued so far
-  cudaStream_t side = nullptr;    // confirm / verify / finalize of batch k run here while the caller's stream scans batch k+1
-  cudaEvent_t e_scan[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr};
-  bool inflight[2] = {false, false};
-  // device path: the step's counters are mirrored into pinned host memory after every batch, so the NEXT call can see
-  // that a queue overflowed (results of that batch incomplete, flagged in counters[3]) and grow the scratch before it runs
-  uint32_t* h_counters = nullptr; cudaEvent_t e_cnt = nullptr; bool cnt_pending = false;
-  uint32_t grow_l1 = 0, grow_slot = 0, grow_ev = 0, grow_units = 0;     // capacities learnt from overflows
-  // drift detection: slow-path entries that are not explained by accepting transitions ("cold" entries), right after the
-  // last adaptation and now; three batches in a row far above the baseline trigger a new adaptation
-  double cold_baseline = -1.0; int cold_strikes = 0; uint32_t adaptations = 0; uint32_t mirrored_n = 0;   // rates are per message of the mirrored batch
-  bool segmented = false;         // long messages seen (first scan / cg_ruleset_adapt): scans cut them into units (kernels.h)
-  uint32_t want_units = 0;        // unit-table capacity for the batches seen so far
+  ScanWork work{};
+  uint64_t seq = 0;               // device-path batches issued so far
+  // device path: every batch's counters are mirrored into a ring of pinned slots, so that a queue overflow (results of
+  // that batch marked incomplete by finalize_kernel) is seen by the next call / by cg_scan_join and the scratch grows
+  static constexpr int kMirror = 16;
+  uint32_t* h_counters = nullptr; cudaEvent_t e_cnt[kMirror] = {}; bool cnt_pending[kMirror] = {};
+  uint32_t grow_l1 = 0, grow_slot = 0, grow_ev = 0;     // capacities learnt from overflows
+  uint32_t sticky_flags = 0;      // error flags of batches since the last cg_scan_join
+  uint32_t last_counters[kCounterWords] = {};
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
-  struct CachedGraph { cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint64_t caps[6] = {0, 0, 0, 0, 0, 0}; uint64_t used = 0; };
+  struct CachedGraph { cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint64_t caps[4] = {0, 0, 0, 0}; uint64_t used = 0; };
   CachedGraph graphs[2];          // two entries: callers that alternate between two input/output buffer sets replay, never re-capture
   uint64_t graph_clock = 0;
-  bool adapted = false;           // profile-guided residency has run (first scan, or cg_ruleset_adapt)
-  uint8_t* d_image_rw = nullptr; uint16_t* d_table_rw = nullptr; uint32_t* d_acc_index_rw = nullptr;   // writable aliases of dev.image / table_full / acc_index
   ~cg_ruleset() {
     for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    if (side) cudaStreamDestroy(side);
     if (h_counters) cudaFreeHost(h_counters);
-    if (e_cnt) cudaEventDestroy(e_cnt);
-    for (int i = 0; i < 2; i++) { if (e_scan[i]) cudaEventDestroy(e_scan[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); }
-    cudaFree(work.units); cudaFree(work2.units); cudaFree(work.heavy_idx); cudaFree(work2.heavy_idx);
-    for (ScanWork* w2 : {&work2}) { cudaFree(w2->l1_msg); cudaFree(w2->l1_pos); cudaFree(w2->l1_sc); cudaFree(w2->slot_of_msg); cudaFree(w2->counters); cudaFree(w2->slot_msg); cudaFree(w2->cand); cudaFree(w2->hit); cudaFree(w2->events); cudaFree(w2->event_pos); cudaFree(w2->event_pre); cudaFree(w2->spans); }
+    for (auto& e : e_cnt) if (e) cudaEventDestroy(e);
     for (void* p : allocs) cudaFree(p);
-    cudaFree(work.l1_msg); cudaFree(work.l1_pos); cudaFree(work.l1_sc); cudaFree(work.slot_of_msg);
+    cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.slot_of_msg);
     cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
   }
 };
@@ -126,8 +114,8 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
   if (!w.counters) { CU(cudaMalloc((void**)&w.counters, kCounterWords * sizeof(uint32_t))); }
   if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
   if (l1_cap > w.l1_cap) {
-    cudaFree(w.l1_msg); cudaFree(w.l1_pos); cudaFree(w.l1_sc); w.l1_msg = w.l1_pos = w.l1_sc = nullptr; w.l1_cap = 0;
-    CU(cudaMalloc((void**)&w.l1_msg, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_sc, (size_t)l1_cap * 4));
+    cudaFree(w.l1_pos); cudaFree(w.l1_fac); w.l1_pos = w.l1_fac = nullptr; w.l1_cap = 0;
+    CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_fac, (size_t)l1_cap * 4));
     w.l1_cap = l1_cap;
   }
   if (slot_cap > w.slot_cap) {
@@ -143,144 +131,78 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
   return CG_OK;
 }
 
-// unit table of segmented scans: allocate / grow / drop to match rs->segmented
-int ensure_units(cg_ruleset* rs, ScanWork& w) {
-  if (!rs->segmented || rs->host.pf.mode == 4) { if (w.units) { cudaFree(w.units); w.units = nullptr; w.unit_cap = 0; } return CG_OK; }
-  const uint32_t want = std::max(rs->want_units, rs->grow_units);
-  if (w.units && w.unit_cap >= want) return CG_OK;
-  if (w.units) { cudaFree(w.units); w.units = nullptr; w.unit_cap = 0; }
-  CU(cudaMalloc((void**)&w.units, (size_t)want * sizeof(uint2)));
-  w.unit_cap = want;
-  return CG_OK;
-}
-
-// Long messages?  (device-resident batch: one reduction over the offsets, then the total size from offsets[n])
-int decide_segmentation(cg_ruleset* rs, const uint32_t* d_off, uint32_t n, cudaStream_t st) {
-  uint32_t* d_max = nullptr; uint32_t h[2] = {0, 0};
-  CU(cudaMalloc((void**)&d_max, 4));
-  cudaError_t e = cudaMemsetAsync(d_max, 0, 4, st);
-  if (e == cudaSuccess) { launch_max_len(d_off, n, d_max, st); G.launches++; G.stats.kernel_launches++; }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h[0], d_max, 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h[1], d_off + n, 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_max);
-  if (e != cudaSuccess) return cuda_fail(e, "message length scan");
-  rs->segmented = h[0] > 2 * kSegBytes;
-  rs->want_units = n + h[1] / kSegBytes + 64;
-  return CG_OK;
-}
-
-// Profile-guided residency: sample the batch, count level-1 state visits, renumber the states so the
-// most visited ones are the shared-memory resident ones, and overwrite the device tables in place (same sizes, same
-// pointers: a captured graph stays valid).  Results never depend on this, only how often the scan's slow path runs.
-int adapt_ruleset(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, cudaStream_t st) {
-  rs->adapted = true; rs->adaptations++;
-  rs->cold_baseline = -1.0; rs->cold_strikes = 0; rs->cnt_pending = false;      // the next mirrored step sets the new baseline
-  HostImage& H = rs->host;
-  if (n) { int rc = decide_segmentation(rs, d_off, n, st); if (rc) return rc; }
-  if (H.pf.mode == 4 || !n || (uint32_t)H.pf.nstates <= H.hot_states) return CG_OK;      // everything is resident already
-  if (getenv("CG_NO_ADAPT") && atoi(getenv("CG_NO_ADAPT"))) return CG_OK;
-  const uint32_t ns = (uint32_t)H.pf.nstates, n_sample = std::min<uint32_t>(n, 8192);
-  uint32_t* d_visits = nullptr;
-  CU(cudaMalloc((void**)&d_visits, (size_t)ns * 4));
-  cudaError_t e = cudaMemsetAsync(d_visits, 0, (size_t)ns * 4, st);
-  if (e == cudaSuccess) { launch_l1_profile(rs->dev, d_bytes, d_off, n, n_sample, d_visits, st); G.launches++; G.stats.kernel_launches++; }
-  std::vector<uint32_t> visits(ns);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(visits.data(), d_visits, (size_t)ns * 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_visits);
-  if (e != cudaSuccess) return cuda_fail(e, "level-1 profile");
-  const size_t image_bytes = H.image.size();
-  rank_states_by_visits(&H, visits.data());
-  if (H.image.size() != image_bytes) return fail(CG_ERR_CUDA, "internal: image size changed on re-ranking");
-  CU(cudaMemcpyAsync(rs->d_image_rw, H.image.data(), H.image.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(rs->d_table_rw, H.pf.table.data(), H.pf.table.size() * 2, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(rs->d_acc_index_rw, H.pf.acc_index.data(), H.pf.acc_index.size() * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaStreamSynchronize(st));
-  return CG_OK;
-}
-
-// head: scratch reset + level-1 scan; tail: confirm + verify + finalize.  Both asynchronous.
-int scan_head(cg_ruleset* rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words, bool spans, cudaStream_t st) {
+// One step on device-resident input: scratch reset, gram scan (+ exact factors), resolve, verify, finalize.  Asynchronous.
+int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words, bool spans, cudaStream_t st) {
+  const ScanWork& w = rs->work;
   CU(cudaMemsetAsync(w.counters, 0, kCounterWords * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(w.slot_of_msg, 0xff, (size_t)n * 4, st));
-  if (w.units) { int kk = launch_plan_units(w, d_off, n, st); G.launches += kk; G.stats.kernel_launches += kk; }
   if (G.profiling) cudaEventRecord(G.pev[0], st);
-  int k = launch_scan(rs->dev, w, d_bytes, d_off, n, d_words, spans, G.sm_count, st);
+  int k = launch_scan(rs->dev, w, d_bytes, d_off, n, d_words, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[1], st);
-  G.launches += k; G.stats.kernel_launches += k;
-  CU(cudaGetLastError());
-  return CG_OK;
-}
-int scan_tail(cg_ruleset* rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint64_t* d_words, bool spans, cudaStream_t st) {
-  int k = launch_confirm(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st);
+  k += launch_resolve(rs->dev, w, d_off, n, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[2], st);
   k += launch_verify(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[3], st);
-  k += launch_finalize(rs->dev, w, d_words, G.sm_count, st);
+  k += launch_finalize(rs->dev, w, d_words, n, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[4], st);
   G.launches += k; G.stats.kernel_launches += k;
   CU(cudaGetLastError());
   return CG_OK;
 }
-// scan + confirm + verify + finalize on device-resident input, one stream; asynchronous
-int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words,
-                    bool spans, cudaStream_t st) {
-  int rc = scan_head(rs, rs->work, d_bytes, d_off, n, d_words, spans, st);
-  if (rc) return rc;
-  return scan_tail(rs, rs->work, d_bytes, d_off, d_words, spans, st);
-}
-
-// every pipelined batch still in flight joins `st` (st waits for their tails)
-int join_pipeline(cg_ruleset* rs, cudaStream_t st) {
-  for (int i = 0; i < 2; i++) if (rs->inflight[i]) { CU(cudaStreamWaitEvent(st, rs->e_done[i], 0)); rs->inflight[i] = false; }
-  return CG_OK;
-}
 
 void prepare_kernels() { static bool done = false; if (!done) { prepare_scan_kernels(); done = true; } }
+
+// capacities a batch of n messages starts with (confirmed occurrences are rare: about one per hundred messages on chat text)
+void default_caps(const cg_ruleset* rs, uint32_t n, uint32_t* l1, uint32_t* slot, uint32_t* ev) {
+  *l1 = std::max(std::max<uint32_t>(std::max<uint32_t>(2 * n, 1u << 16), rs->work.l1_cap), rs->grow_l1);
+  *slot = std::max(std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), rs->work.slot_cap), rs->grow_slot);
+  *ev = std::max(std::max<uint32_t>(std::max<uint32_t>(n, 4096), rs->work.event_cap), rs->grow_ev);
+}
+// what an overflowed step teaches about the capacities the next one needs
+void learn_caps(cg_ruleset* rs, const uint32_t* hc) {
+  const uint32_t flags = hc[3];
+  if (flags & ERR_L1_OVERFLOW) rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * hc[4], hc[4] + 65536));
+  if (flags & ERR_SLOT_OVERFLOW) rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096));
+  if (flags & ERR_EVENT_OVERFLOW) rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096));
+}
 
 struct HostScan {
   std::vector<uint32_t> counters, slot_msg, hit, spans;
 };
 
+int check_offsets(const uint32_t* offsets, uint32_t n) {
+  for (uint32_t i = 0; i < n; i++) if (offsets[i + 1] < offsets[i]) return fail(CG_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  return CG_OK;
+}
+
 // full host-buffer scan with capacity retry; leaves words in G.d_words
 int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, bool spans, HostScan* hs) {
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
   if (!rs || (n && (!bytes || !offsets))) return fail(CG_ERR_INVALID_ARG, "null argument");
-  size_t total = n ? offsets[n] : 0;
   int rc;
+  if (n && (rc = check_offsets(offsets, n))) return rc;
+  const size_t first = n ? offsets[0] : 0, total = n ? offsets[n] : 0;
   if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
   if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
   if ((rc = grow(&G.d_words, &G.cap_words, (size_t)n + 1))) return rc;
   cudaStream_t st = G.stream;
   if (n) {
-    CU(cudaMemcpyAsync(G.d_bytes, bytes, total, cudaMemcpyHostToDevice, st));
+    if (total > first) CU(cudaMemcpyAsync(G.d_bytes + first, bytes + first, total - first, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(G.d_bytes + total, 0, 64, st));
     CU(cudaMemcpyAsync(G.d_off32, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
   }
-  uint32_t slot_cap = std::max<uint32_t>(n / 4, 4096), event_cap = std::max<uint32_t>(n, 4096), span_cap = spans ? std::max<uint32_t>(n, 4096) : 1;
-  uint32_t l1_cap = std::max<uint32_t>(4 * n, 1u << 16);
-  // keep whatever an earlier step of this rule set needed
-  slot_cap = std::max(std::max(slot_cap, rs->work.slot_cap), rs->grow_slot); event_cap = std::max(std::max(event_cap, rs->work.event_cap), rs->grow_ev); l1_cap = std::max(std::max(l1_cap, rs->work.l1_cap), rs->grow_l1);
-  hs->counters.assign(16, 0);
-  if ((rc = join_pipeline(rs, st))) return rc;
-  {
-    uint32_t max_len = 0;
-    for (uint32_t i = 0; i < n; i++) max_len = std::max(max_len, offsets[i + 1] - offsets[i]);
-    const bool seg = max_len > 2 * kSegBytes;
-    const uint32_t want = n + (uint32_t)(total / kSegBytes) + 64;
-    if (seg != rs->segmented || (seg && want > rs->want_units)) { CU(cudaStreamSynchronize(st)); rs->segmented = seg; rs->want_units = std::max(rs->want_units, want); }
-    if ((rc = ensure_units(rs, rs->work))) return rc;
-  }
-  if (n && !rs->adapted && (rc = adapt_ruleset(rs, G.d_bytes, G.d_off32, n, st))) return rc;
+  uint32_t l1_cap, slot_cap, event_cap, span_cap = spans ? std::max<uint32_t>(std::max<uint32_t>(n, 4096), rs->work.span_cap) : 1;
+  default_caps(rs, n, &l1_cap, &slot_cap, &event_cap);
+  hs->counters.assign(kCounterWords, 0);
   for (int attempt = 0; attempt < 10; attempt++) {
     if ((rc = ensure_work(rs, rs->work, std::max<uint32_t>(n, 1), l1_cap, slot_cap, event_cap, span_cap))) return rc;
     CU(cudaEventRecord(G.ev0, st));
     if (n) { if ((rc = run_scan_device(rs, G.d_bytes, G.d_off32, n, G.d_words, spans, st))) return rc; }
     else CU(cudaMemsetAsync(rs->work.counters, 0, kCounterWords * sizeof(uint32_t), st));
     CU(cudaEventRecord(G.ev1, st));
-    CU(cudaMemcpyAsync(hs->counters.data(), rs->work.counters, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hs->counters.data(), rs->work.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    memcpy(rs->last_counters, hs->counters.data(), sizeof rs->last_counters);
     float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_scan_ms = ms;
     uint32_t flags = hs->counters[3];
     if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
@@ -288,7 +210,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
     if (flags & ERR_SLOT_OVERFLOW) { slot_cap = std::max<uint32_t>(slot_cap * 4, hs->counters[0] + 1024); continue; }
     if (flags & ERR_EVENT_OVERFLOW) { event_cap = std::max<uint32_t>(event_cap * 4, hs->counters[1] + 1024); continue; }
     if (flags & ERR_SPAN_OVERFLOW) { span_cap = std::max<uint32_t>(span_cap * 4, hs->counters[2] + 1024); continue; }
-    G.stats.messages_scanned += n; G.stats.bytes_scanned += total;
+    G.stats.messages_scanned += n; G.stats.bytes_scanned += total - first;
     G.stats.candidate_events += hs->counters[1]; G.stats.verified_pairs += hs->counters[1];
     return CG_OK;
   }
@@ -300,8 +222,9 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
 // alone.  Returns 1 when a queue overflowed somewhere (capacities have been grown; the caller re-runs in one piece).
 int scan_host_chunked(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint64_t* out_words) {
   const int C = Ctx::kChunks;
-  const size_t total = offsets[n];
   int rc;
+  if ((rc = check_offsets(offsets, n))) return rc;
+  const size_t total = offsets[n];
   if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
   if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
   if ((rc = grow(&G.d_words, &G.cap_words, (size_t)n + 1))) return rc;
@@ -311,19 +234,9 @@ int scan_host_chunked(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offs
     CU(cudaMallocHost((void**)&G.h_chunk_counters, (size_t)C * kCounterWords * 4));
   }
   cudaStream_t st = G.stream;
-  if ((rc = join_pipeline(rs, st))) return rc;
-  {   // segmentation decision from the host offsets (as scan_host)
-    uint32_t max_len = 0;
-    for (uint32_t i = 0; i < n; i++) max_len = std::max(max_len, offsets[i + 1] - offsets[i]);
-    const bool seg = max_len > 2 * kSegBytes;
-    const uint32_t want = n + (uint32_t)(total / kSegBytes) + 64;
-    if (seg != rs->segmented || (seg && want > rs->want_units)) { CU(cudaStreamSynchronize(st)); rs->segmented = seg; rs->want_units = std::max(rs->want_units, want); }
-    if ((rc = ensure_units(rs, rs->work))) return rc;
-  }
   const uint32_t per = (n + C - 1) / C;
-  const uint32_t l1_cap = std::max(std::max<uint32_t>(std::max<uint32_t>(4 * per, 1u << 16), rs->work.l1_cap), rs->grow_l1),
-                 slot_cap = std::max(std::max<uint32_t>(std::max<uint32_t>(per / 4, 4096), rs->work.slot_cap), rs->grow_slot),
-                 event_cap = std::max(std::max<uint32_t>(std::max<uint32_t>(per, 4096), rs->work.event_cap), rs->grow_ev);
+  uint32_t l1_cap, slot_cap, event_cap;
+  default_caps(rs, per, &l1_cap, &slot_cap, &event_cap);
   CU(cudaStreamSynchronize(st));
   if ((rc = ensure_work(rs, rs->work, std::max<uint32_t>(per, 1), l1_cap, slot_cap, event_cap, 1))) return rc;
   CU(cudaMemcpyAsync(G.d_off32, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, G.s_h2d));
@@ -338,6 +251,8 @@ int scan_host_chunked(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offs
     if (b1 > b0) CU(cudaMemcpyAsync(G.d_bytes + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, G.s_h2d));
     CU(cudaEventRecord(G.e_h2d[c], G.s_h2d));
     CU(cudaStreamWaitEvent(st, G.e_h2d[c], 0));
+    // (a piece reads up to 16 bytes past its last message -- bytes of the next piece that may still be in flight; whatever
+    // it sees there cannot produce an occurrence inside its own range)
     if ((rc = run_scan_device(rs, G.d_bytes, G.d_off32 + m0, m1 - m0, G.d_words + m0, false, st))) return rc;
     CU(cudaMemcpyAsync(G.h_chunk_counters + (size_t)c * kCounterWords, rs->work.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(G.e_done[c], st));
@@ -351,15 +266,26 @@ int scan_host_chunked(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offs
   for (int c = 0; c < used; c++) {
     const uint32_t* hc = G.h_chunk_counters + (size_t)c * kCounterWords; const uint32_t flags = hc[3];
     if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
-    if (flags & ERR_L1_OVERFLOW) { rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * hc[4], hc[4] + 65536)); overflow = true; }
-    if (flags & ERR_SLOT_OVERFLOW) { rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096)); overflow = true; }
-    if (flags & ERR_EVENT_OVERFLOW) { rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096)); overflow = true; }
-    if (flags & ERR_UNIT_OVERFLOW) rs->grow_units = std::max<uint32_t>(rs->grow_units, hc[16] + hc[16] / 8 + 64);      // not an error: that piece ran unsegmented
+    if (flags) { learn_caps(rs, hc); overflow = true; }
     G.stats.candidate_events += hc[1]; G.stats.verified_pairs += hc[1];
   }
+  if (used) memcpy(rs->last_counters, G.h_chunk_counters + (size_t)(used - 1) * kCounterWords, sizeof rs->last_counters);
   if (overflow) return 1;
-  G.stats.messages_scanned += n; G.stats.bytes_scanned += total;
+  G.stats.messages_scanned += n; G.stats.bytes_scanned += total - offsets[0];
   return CG_OK;
+}
+
+// device path: look at every mirrored counter block whose copy has completed
+void poll_mirrors(cg_ruleset* rs, bool wait) {
+  for (int i = 0; i < cg_ruleset::kMirror; i++) {
+    if (!rs->cnt_pending[i]) continue;
+    if (wait) cudaEventSynchronize(rs->e_cnt[i]);
+    else if (cudaEventQuery(rs->e_cnt[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+    rs->cnt_pending[i] = false;
+    const uint32_t* hc = rs->h_counters + (size_t)i * kCounterWords;
+    memcpy(rs->last_counters, hc, sizeof rs->last_counters);
+    if (hc[3]) { rs->sticky_flags |= hc[3]; learn_caps(rs, hc); }
+  }
 }
 
 }  // namespace
@@ -414,14 +340,13 @@ int cg_last_kernel_ms(float out_ms[4]) {
   return CG_OK;
 }
 
-int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out8[16]) {
-  // [0] slots (messages with confirmed candidates), [1] (message, rule) pairs sent to the VM, [2] spans,
-  // [3] error flags, [4] level-1 accept events, [5] verify kernel's event cursor, [6] warp-level entries into the scan kernel's slow path
-  // (4-byte words some lane had to re-walk on the full table), [7] reserved -- of the last completed step
-  const ScanWork& lw = (rs && rs->seq && ((rs->seq - 1) & 1u)) ? rs->work2 : rs->work;     // the most recent pipelined batch, else the sequential scratch
-  if (!rs || !out8 || !lw.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
-  CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(out8, lw.counters, 64, cudaMemcpyDeviceToHost));     // [7..15]: CG_SCAN_DEBUG=2 VM cycle histogram
+int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out16[16]) {
+  // [0] slots (messages with confirmed candidates), [1] (message, rule) pairs sent to the VM, [2] spans, [3] error flags,
+  // [4] confirmed factor occurrences, [5] verify kernel's event cursor, [6] flagged grams (level 1a) -- of the last step
+  // whose counters reached the host (cg_scan_batch: the call itself; device path: after cg_scan_join)
+  if (!rs || !out16) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (!rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
+  memcpy(out16, rs->last_counters, 64);
   return CG_OK;
 }
 
@@ -445,12 +370,11 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   rs->category.resize(n_rules);
   for (uint32_t i = 0; i < n_rules; i++) { src[i] = RuleSrc{rules[i].source, rules[i].source_len, rules[i].flags}; rs->category[i] = rules[i].category; }
   ImageOptions io;
-  io.mode = (int)(options & 7u); if (io.mode > 4) io.mode = 4;
-  if (const char* e = getenv("CG_PREFILTER_MODE")) io.mode = atoi(e);
-  if (const char* e = getenv("CG_PREFILTER_KB")) io.budget_bytes = (size_t)atoi(e) * 1024;
-  if (const char* e = getenv("CG_PREFILTER_CLASSES")) io.max_classes = atoi(e);
-  if (const char* e = getenv("CG_WINDOW")) io.max_window = atoi(e);
-  if (const char* e = getenv("CG_MAX_STATES")) io.max_states = atoi(e);
+  io.stride = (options & 7u) == CG_OPT_STRIDE2 ? 2 : (options & 7u) == CG_OPT_STRIDE4 ? 4 : 0;
+  if (const char* e = getenv("CG_STRIDE")) io.stride = atoi(e);
+  if (const char* e = getenv("CG_BITMAP_KB")) io.bitmap_kb = (uint32_t)atoi(e);
+  if (const char* e = getenv("CG_BLOOM2")) io.bloom2 = atoi(e);
+  if (const char* e = getenv("CG_MAX_KEYS")) io.max_keys = (uint32_t)atoi(e);
   std::string perr;
   if (!build_host_image(src.data(), n_rules, io, &rs->host, &perr)) return fail(CG_ERR_TOO_LARGE, perr);
   HostImage& H = rs->host;
@@ -461,30 +385,29 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
     else if (code != CG_OK) return fail(code, "rule " + std::to_string(i) + ": " + H.rules[i].error);
   }
   const Prefilter& P = H.pf;
-  const std::vector<uint8_t>& image = H.image;
   const std::vector<uint32_t>&prog = H.prog, &prog_off = H.prog_off, &sets = H.sets, &first = H.first;
   const std::vector<uint16_t>& ranges = H.ranges;
   rs->n_sets = H.n_sets; rs->program_words = (uint32_t)H.prog.size();
+  if (P.shapes.size() > 16) return fail(CG_ERR_TOO_LARGE, "internal: more than 16 gram shapes");
 
   DevRuleset& d = rs->dev;
   int rc;
-  const uint8_t* d_image; if ((rc = upload(rs.get(), image, &d_image, 16))) return rc;
-  d.image = d_image; d.image_bytes = (uint32_t)image.size(); d.mode = (uint32_t)P.mode; rs->d_image_rw = const_cast<uint8_t*>(d_image);
-  d.ncols_log2 = 0; while ((1 << d.ncols_log2) < P.ncols) d.ncols_log2++;
-  d.nstates = (uint32_t)P.nstates; d.hot_states = H.hot_states; d.lut_off = H.lut_off; d.row_stride = H.row_stride;
-  d.debug_flags = 0; if (const char* e = getenv("CG_SCAN_DEBUG")) d.debug_flags = (uint32_t)atoi(e);   // 1: skip the slow path (timing experiments only, results wrong)
-  if ((rc = upload(rs.get(), P.table, &d.table_full, 64))) return rc;
-  if ((rc = upload(rs.get(), P.acc_index, &d.acc_index))) return rc;
-  rs->d_table_rw = const_cast<uint16_t*>(d.table_full); rs->d_acc_index_rw = const_cast<uint32_t*>(d.acc_index);
-  if ((rc = upload(rs.get(), P.acc_offsets, &d.acc_offsets))) return rc;
-  if ((rc = upload(rs.get(), P.acc_factors, &d.acc_factors))) return rc;
+  const uint8_t* d_image; if ((rc = upload(rs.get(), H.image, &d_image, 16))) return rc;
+  d.image = d_image; d.image_bytes = (uint32_t)H.image.size(); d.stride = (uint32_t)P.stride;
+  d.bm_mask = H.bm_mask; d.bloom2 = H.bloom2 ? 1u : 0u; d.tables_resident = H.tables_resident ? 1u : 0u;
+  d.dir_off = H.dir_off; d.ent_off = H.ent_off; d.fac_off = H.fac_off; d.set_off = H.set_off; d.nb_shift = H.nb_shift;
+  d.n_shapes = (uint32_t)P.shapes.size(); for (uint32_t k = 0; k < 16; k++) d.shapes[k] = k < d.n_shapes ? P.shapes[k] : 0;
+  d.n_trig = (uint32_t)P.trig_bytes.size(); for (uint32_t t = 0; t < 2; t++) d.trig_byte[t] = t < d.n_trig ? P.trig_bytes[t] : 0;
+  d.hot_c5f = 0x5f5f5f5fu; d.hot_c10 = 0x10101010u; d.hot_one = 1u;
+  d.debug_flags = 0; if (const char* e = getenv("CG_SCAN_DEBUG")) d.debug_flags = (uint32_t)atoi(e);   // 1: drop flagged grams (timing experiments only, results wrong)
+  if ((rc = upload(rs.get(), P.trig_offsets, &d.trig_offsets))) return rc;
+  if ((rc = upload(rs.get(), P.trig_list, &d.trig_list))) return rc;
+  if ((rc = upload(rs.get(), H.bucket_start, &d.bucket_start))) return rc;
+  { const uint32_t* ew = nullptr; if ((rc = upload(rs.get(), H.entry_words, &ew, 8))) return rc; d.entries = reinterpret_cast<const uint2*>(ew); }
+  d.n_factors = (uint32_t)P.factors.size();
   if ((rc = upload(rs.get(), H.factor_words, &d.factors, 16))) return rc;
   if ((rc = upload(rs.get(), P.bytesets, &d.bytesets, 8))) return rc;
   if ((rc = upload(rs.get(), P.always_rules, &d.always_rules))) return rc;
-  d.fp_buckets = P.fp_buckets; d.fp_mult = P.fp_mult;
-  d.n_trig = (uint32_t)P.trig_bytes.size(); for (uint32_t t = 0; t < 2; t++) { d.trig_byte[t] = t < d.n_trig ? P.trig_bytes[t] : 0; d.trig_acc[t] = t < d.n_trig ? P.trig_acc[t] : 0xffffffffu; }
-  if ((rc = upload(rs.get(), P.fp_table, &d.fp_table))) return rc;
-  if ((rc = upload(rs.get(), P.fp_acc, &d.fp_acc))) return rc;
   d.n_always = (uint32_t)P.always_rules.size();
   if ((rc = upload(rs.get(), prog, &d.prog))) return rc;
   if ((rc = upload(rs.get(), prog_off, &d.rule_prog_off))) return rc;
@@ -507,9 +430,12 @@ int cg_ruleset_get_info(const cg_ruleset* rs, cg_ruleset_info* o) {
   memset(o, 0, sizeof *o);
   o->n_rules = (uint32_t)rs->host.rules.size();
   for (auto& r : rs->host.rules) if (r.status == RULE_OK) o->n_ok++;
-  o->n_always_candidate = (uint32_t)rs->host.pf.always_rules.size(); o->n_sets = rs->n_sets;
-  o->prefilter_mode = (uint32_t)rs->host.pf.mode; o->prefilter_states = rs->host.pf.mode == 4 ? rs->host.pf.fp_keys : (uint32_t)rs->host.pf.nstates; o->prefilter_hot_states = rs->host.hot_states; o->prefilter_cols = (uint32_t)rs->host.pf.ncols;
-  o->prefilter_factor_len = (uint32_t)rs->host.pf.window_min | ((uint32_t)rs->host.pf.window_max << 8); o->n_factors = (uint32_t)rs->host.pf.factors.size(); o->prefilter_bytes = rs->dev.image_bytes; o->program_words = rs->program_words;
+  const Prefilter& P = rs->host.pf;
+  o->n_always_candidate = (uint32_t)P.always_rules.size(); o->n_sets = rs->n_sets;
+  o->stride = (uint32_t)P.stride; o->gram_keys = (uint32_t)P.keys.size(); o->gram_entries = (uint32_t)P.entries.size();
+  o->factor_len = P.min_factor_len | (P.max_factor_len << 8); o->n_factors = (uint32_t)P.factors.size();
+  o->image_bytes = rs->dev.image_bytes; o->bitmap_bytes = rs->host.bm_bytes; o->program_words = rs->program_words;
+  o->n_triggers = (uint32_t)P.trig_bytes.size(); o->tables_resident = rs->host.tables_resident ? 1u : 0u;
   return CG_OK;
 }
 
@@ -520,7 +446,7 @@ int cg_scan_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets,
   int rc;
   // large words-only batches: chunked, copies overlapped with the kernels (the hit list needs the per-batch slot tables)
   static const bool no_chunks = getenv("CG_NO_CHUNKS") && atoi(getenv("CG_NO_CHUNKS"));
-  if (!no_chunks && !out_hits && out_words && n >= (1u << 16) && G.ready && rs && bytes && offsets && rs->adapted) {
+  if (!no_chunks && !out_hits && out_words && n >= (1u << 16) && G.ready && rs && bytes && offsets) {
     rc = scan_host_chunked(rs, bytes, offsets, n, out_words);
     if (rc < 0) return rc;
     if (rc == 0) {
@@ -713,85 +639,43 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
   if (!rs || !d_bytes || !d_offsets || !d_out_words) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if ((uintptr_t)d_bytes & 15u) return fail(CG_ERR_INVALID_ARG, "d_bytes must be 16-byte aligned");
   cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
   if (!n) return CG_OK;
   static const bool use_graph = !(getenv("CG_NO_GRAPH") && atoi(getenv("CG_NO_GRAPH")));
-  // opt-in (CG_PIPELINE=1): measured on B200, the tail kernels squeezed next to the scan kernel run ~4x slower and the
-  // step time does not improve; the default is the in-order step replayed as one CUDA graph
-  static const bool use_pipeline = getenv("CG_PIPELINE") && atoi(getenv("CG_PIPELINE"));
-  const bool pipelined = use_pipeline && !G.profiling;
-  // which scratch set this batch uses: pipelined batches alternate between two
-  const int idx = pipelined ? (int)(rs->seq & 1u) : 0;
-  ScanWork& w = idx ? rs->work2 : rs->work;
+  ScanWork& w = rs->work;
   int rc;
-  // did the previous batch overflow a queue?  (its counters were copied to pinned memory; the copy is normally long done)
-  if (rs->cnt_pending && cudaEventQuery(rs->e_cnt) == cudaSuccess) {
-    rs->cnt_pending = false;
-    const uint32_t* hc = rs->h_counters; const uint32_t flags = hc[3];
-    if (flags & ERR_L1_OVERFLOW) rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * hc[4], hc[4] + 65536));
-    if (flags & ERR_SLOT_OVERFLOW) rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096));
-    if (flags & ERR_EVENT_OVERFLOW) rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096));
-    if (flags & ERR_UNIT_OVERFLOW) rs->grow_units = std::max<uint32_t>(rs->grow_units, hc[16] + hc[16] / 8 + 64);
-    // has the traffic drifted away from what the resident rows were chosen for?
-    const double cold = (hc[6] > hc[4] ? hc[6] - hc[4] : 0u) / (double)std::max<uint32_t>(rs->mirrored_n, 1u);
-    if (rs->cold_baseline < 0) rs->cold_baseline = cold;
-    else if (cold > 4.0 * std::max(rs->cold_baseline, 0.004)) { if (++rs->cold_strikes >= 3) { rs->adapted = false; rs->cold_strikes = 0; } }
-    else rs->cold_strikes = 0;
+  if (!rs->h_counters) {
+    CU(cudaMallocHost((void**)&rs->h_counters, (size_t)cg_ruleset::kMirror * kCounterWords * 4));
+    for (auto& e : rs->e_cnt) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  const uint32_t want_l1 = std::max(std::max<uint32_t>(std::max<uint32_t>(4 * n, 1u << 16), w.l1_cap), rs->grow_l1),
-                 want_slot = std::max(std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), w.slot_cap), rs->grow_slot),
-                 want_ev = std::max(std::max<uint32_t>(std::max<uint32_t>(n, 4096), w.event_cap), rs->grow_ev);
+  // did an earlier batch overflow a queue?  (its result words say "incomplete"; grow the scratch before this one runs)
+  poll_mirrors(rs, false);
+  uint32_t want_l1, want_slot, want_ev;
+  default_caps(rs, n, &want_l1, &want_slot, &want_ev);
   if (n > w.msg_cap || want_l1 > w.l1_cap || want_slot > w.slot_cap || want_ev > w.event_cap || !w.counters || !w.spans) {
     // (re)allocation: nothing may still be using the old buffers
-    CU(cudaStreamSynchronize(st)); if (rs->side) CU(cudaStreamSynchronize(rs->side));
+    CU(cudaStreamSynchronize(st));
     for (auto& g : rs->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if ((rc = ensure_work(rs, w, std::max<uint32_t>(n, 1), want_l1, want_slot, want_ev, 1))) return rc;
   }
-  if (!rs->adapted) {
-    if ((rc = join_pipeline(rs, st))) return rc;
-    if ((rc = adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st))) return rc;
-  }
-  {
-    const bool want_tbl = rs->segmented && rs->host.pf.mode != 4;
-    if (want_tbl != (w.units != nullptr) || (want_tbl && w.unit_cap < std::max(rs->want_units, rs->grow_units))) {
-      CU(cudaStreamSynchronize(st)); if (rs->side) CU(cudaStreamSynchronize(rs->side));
-      if ((rc = ensure_units(rs, w))) return rc;
-    }
-  }
-  if (pipelined) {
-    // Two batches in flight: the caller's stream runs scratch reset + scan of batch k, the side stream runs confirm +
-    // verify + finalize of batch k while the caller's stream already scans batch k+1.  The tail kernels are small
-    // latency-bound grids; whether they actually run beside the scan kernel depends on what its CTAs leave free.
-    if (!rs->side) {
-      CU(cudaStreamCreateWithFlags(&rs->side, cudaStreamNonBlocking));
-      for (int i = 0; i < 2; i++) { CU(cudaEventCreateWithFlags(&rs->e_scan[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&rs->e_done[i], cudaEventDisableTiming)); }
-    }
-    if (rs->inflight[idx]) { CU(cudaStreamWaitEvent(st, rs->e_done[idx], 0)); rs->inflight[idx] = false; }   // batch k-2 is done with this scratch set
-    if ((rc = scan_head(rs, w, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st))) return rc;
-    CU(cudaEventRecord(rs->e_scan[idx], st));
-    CU(cudaStreamWaitEvent(rs->side, rs->e_scan[idx], 0));
-    if ((rc = scan_tail(rs, w, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, (uint64_t*)d_out_words, false, rs->side))) return rc;
-    CU(cudaEventRecord(rs->e_done[idx], rs->side));
-    rs->inflight[idx] = true; rs->seq++;
-    G.stats.messages_scanned += n;
-    return CG_OK;
-  }
-  if ((rc = join_pipeline(rs, st))) return rc;
   if (!use_graph || G.profiling) {
     rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
   } else {
-    // memset + scan + confirm + verify + finalize captured once per (arguments, capacities), then replayed:
-    // one launch per step instead of seven, so the host never becomes the bottleneck
-    const uint64_t caps[6] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap, w.unit_cap, (uint64_t)(uintptr_t)w.units};
+    // memsets + scan + resolve + verify + finalize captured once per (arguments, capacities), then replayed:
+    // one launch per step instead of six, so the host never becomes the bottleneck
+    const uint64_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
     cg_ruleset::CachedGraph* hit = nullptr;
     for (auto& g : rs->graphs) if (g.exec && g.bytes == d_bytes && g.off == d_offsets && g.words == d_out_words && g.n == n && !memcmp(caps, g.caps, sizeof caps)) hit = &g;
     if (!hit) {
       hit = rs->graphs[0].used <= rs->graphs[1].used ? &rs->graphs[0] : &rs->graphs[1];       // least recently used entry
       if (hit->exec) { cudaGraphExecDestroy(hit->exec); hit->exec = nullptr; }
       cudaGraph_t g = nullptr;
+      const uint64_t launches_before = G.launches;
       CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
       cudaError_t e = cudaStreamEndCapture(st, &g);
+      G.stats.kernel_launches -= G.launches - launches_before; G.launches = launches_before;      // counted per replay below
       if (rc != CG_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc != CG_OK ? rc : cuda_fail(e, "cudaStreamEndCapture"); }
       e = cudaGraphInstantiate(&hit->exec, g, 0);
       cudaGraphDestroy(g);
@@ -800,16 +684,16 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     }
     hit->used = ++rs->graph_clock;
     CU(cudaGraphLaunch(hit->exec, st));
-    G.launches += 5; G.stats.kernel_launches += 5;       // kernels inside the graph (scan, confirm, verify, finalize + optional large-VM)
+    const int kk = 4 + (rs->dev.max_prog_len > 192 ? 1 : 0);       // kernels inside the graph: scan, resolve, verify (+ large-VM), finalize
+    G.launches += kk; G.stats.kernel_launches += kk;
   }
   if (rc == CG_OK) {
     G.stats.messages_scanned += n;
-    if (!rs->h_counters) { CU(cudaMallocHost((void**)&rs->h_counters, kCounterWords * 4)); CU(cudaEventCreateWithFlags(&rs->e_cnt, cudaEventDisableTiming)); }
-    if (!rs->cnt_pending) {                                 // (one mirror copy in flight at a time)
-      CU(cudaMemcpyAsync(rs->h_counters, w.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaEventRecord(rs->e_cnt, st));
-      rs->cnt_pending = true; rs->mirrored_n = n;
-    }
+    const int slot = (int)(rs->seq % cg_ruleset::kMirror);
+    if (rs->cnt_pending[slot]) { cudaEventSynchronize(rs->e_cnt[slot]); poll_mirrors(rs, false); }
+    CU(cudaMemcpyAsync(rs->h_counters + (size_t)slot * kCounterWords, w.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(rs->e_cnt[slot], st));
+    rs->cnt_pending[slot] = true; rs->seq++;
   }
   return rc;
 }
@@ -818,17 +702,12 @@ int cg_scan_join(cg_ruleset* rs, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
   if (!rs) return fail(CG_ERR_INVALID_ARG, "null argument");
-  return join_pipeline(rs, stream ? (cudaStream_t)stream : G.stream);
-}
-
-int cg_ruleset_adapt(cg_ruleset* rs, const void* d_bytes, const void* d_offsets, uint32_t n, void* stream) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
-  if (!rs || !d_bytes || !d_offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
-  cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
-  if (int jr = join_pipeline(rs, st)) return jr;
-  CU(cudaStreamSynchronize(st));                         // nothing may still be reading the tables
-  return adapt_ruleset(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, st);
+  CU(cudaStreamSynchronize(stream ? (cudaStream_t)stream : G.stream));
+  poll_mirrors(rs, true);
+  const uint32_t flags = rs->sticky_flags; rs->sticky_flags = 0;
+  if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device (result words of that batch are all ones)");
+  if (flags) return fail(CG_ERR_CAPACITY, "a candidate queue overflowed: the result words of that batch are all ones; the scratch has been grown, scan the batch again");
+  return CG_OK;
 }
 
 // ---------------------------------------------------------------------------------- SHA / Merkle

@@ -7,27 +7,29 @@ namespace cg {
 
 // Everything the scan / verify kernels need to know about a compiled rule set (device pointers).
 struct DevRuleset {
-  const uint8_t* image;          // shared-memory image (layout: ruleset_image.h), 16-byte aligned, size % 16 == 0
-  uint32_t lut_off, row_stride;  // DFA modes: byte offset of the 256-byte LUT inside the image; bytes between table rows
-  uint32_t image_bytes;
-  uint32_t mode;                 // 0 = direct 7-bit columns, 1 = LUT columns, 2 = folded 6-bit, 3 = folded 5-bit columns, 4 = fingerprint table
+  // gram filter (rulec.h): the image is staged into shared memory by the scan kernel with TMA bulk copies.
+  //   [0, bm_mask + 4)  bitmap ; then, when tables_resident: [dir_off] bucket_start (n_buckets + 1 words)
+  //   [ent_off] level-1b entries (8 B each) [fac_off] factor words [set_off] byte sets.  All offsets 16-byte aligned.
+  const uint8_t* image;
+  uint32_t image_bytes;          // bytes staged (multiple of 16)
+  uint32_t stride;               // 4: one probe per aligned word, 2: also the gram at byte offset 2 of every word
+  uint32_t bm_mask, bloom2;      // bitmap word address = hi32(key * kGramMult) & bm_mask; bloom2: keys set / need two bits of the word
+  uint32_t tables_resident;      // level-1b tables are part of the image (else read through the HBM pointers below)
+  uint32_t dir_off, ent_off, fac_off, set_off;
+  uint32_t nb_shift;             // bucket = hash >> nb_shift
+  uint32_t n_shapes, shapes[16]; // distinct key masks of the level-1b entries
+  uint32_t n_trig, trig_byte[2]; // single-byte triggers
+  uint32_t hot_c5f, hot_c10, hot_one;   // 0x5f5f5f5f, 0x10101010, 1: run-time constants of the scan kernel's hot loop (scan_kernels.cu)
+  const uint32_t* trig_offsets;  // CSR over triggers -> trig_list (factor | element index << 20)
+  const uint32_t* trig_list;
+  const uint32_t* bucket_start;  // HBM copies of the level-1b tables
+  const uint2* entries;
+  uint32_t n_factors;
   uint32_t max_prog_len;         // longest Pike program of the set (picks the VM capacity)
-  uint32_t ncols_log2;
-  uint32_t nstates;
-  uint32_t hot_states;           // rows [0, hot_states) + one trap row are in the shared-memory image, the rest only in table_full
-  uint32_t debug_flags;          // CG_SCAN_DEBUG (experiments only): bit 0 = skip the scan kernel's slow path (results wrong),
+  uint32_t debug_flags;          // CG_SCAN_DEBUG (experiments only): bit 0 = drop flagged grams (results wrong),
                                  //   bit 1 = histogram of VM cycles per event in counters[7..15]
-  const uint16_t* table_full;    // complete level-1 table in HBM (L2-resident)
-  const uint32_t* acc_index;     // nstates*ncols: accept id of an accepting transition
-  const uint32_t* acc_offsets;   // CSR over accept ids -> factor ids
-  const uint32_t* acc_factors;
-  const uint32_t* factors;       // 12 words per full factor: rule, len|win_off<<8|win_len<<16|exact<<24, 16 x u16 set ids, max prefix units, pad
+  const uint32_t* factors;       // 12 words per full factor: rule, len | exact<<24, 16 x u16 set ids, max prefix units, prefix-alphabet set id
   const uint32_t* bytesets;      // 8 words per 256-bit byte set
-  // mode 4 (fingerprint level 1): bucket = umulhi(window * fp_mult, fp_buckets); image = [256 B][fp_buckets x 32 replicated words]
-  uint32_t fp_buckets, fp_mult;
-  const uint32_t* fp_table;      // fp_buckets words (two 16-bit fingerprints each)
-  const uint32_t* fp_acc;        // 2 * fp_buckets accept ids
-  uint32_t n_trig, trig_byte[2], trig_acc[2];   // single-byte triggers (events carry pos | 0x80000000, sc = trigger index)
   const uint32_t* always_rules;  // candidates for every message
   uint32_t n_always;
   const uint32_t* prog;          // all Pike programs, concatenated
@@ -45,11 +47,10 @@ struct DevRuleset {
 
 // Per-call scratch in HBM.  A "slot" is one message with at least one confirmed candidate.
 struct ScanWork {
-  uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (level-1 accept events) [5]=verify cursor
-                                 //           [6]=slow-path entries [7..15]=debug [16]=n_units (segmented scans) [17]=n_heavy [18]=verify cursor (light events)
-  uint32_t* l1_msg;              // [l1_cap] level-1 accept events queued by scan_kernel: message,
-  uint32_t* l1_pos;              //          byte offset of the accepting byte inside the message,
-  uint32_t* l1_sc;               //          state << 8 | column of the accepting transition (0xffffffff = "always" rules)
+  uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (confirmed factor occurrences) [5]=verify cursor
+                                 //           [6]=flagged grams (level 1a) [7..15]=debug [17]=n_heavy [18]=verify cursor (light events)
+  uint32_t* l1_pos;              // [l1_cap] confirmed factor occurrences queued by scan_kernel: buffer offset of the factor's first byte,
+  uint32_t* l1_fac;              //          factor id
   uint32_t* slot_of_msg;         // [n] 0xffffffff = none yet (reset per step)
   uint32_t* slot_msg;            // [slot_cap]
   uint32_t* cand;                // [slot_cap * rw]  candidate (msg,rule) pairs already queued
@@ -59,33 +60,25 @@ struct ScanWork {
   uint32_t* event_pos;           // [event_cap]  policy mode: message offset of the confirmed factor's first byte
   uint32_t* event_pre;           // [event_cap]  policy mode: max units of a match before that factor (0xffff = unbounded)
   uint32_t* spans;               // [span_cap * 6] msg, rule, start_byte, end_byte, start16, end16
-  // Long messages are cut into units of kSegBytes (+ kSegWarm bytes of warm-up) so that every lane has about the same
-  // amount to walk: units[u] = (message, segment).  nullptr = one unit per message (short-message batches).
-  uint2* units;
-  uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap, unit_cap;
+  uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap;
 };
 
-enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32,
-                  ERR_UNIT_OVERFLOW = 64 /* not an error: the scan falls back to one unit per message */ };
-constexpr uint32_t kSegBytes = 1024, kSegWarm = 16;     // kSegWarm >= longest level-1 window - 1 (kMaxWindow = 8), multiple of 16
+enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32 };
 constexpr uint32_t kCounterWords = 32;
+constexpr uint64_t kWordIncomplete = ~0ull;      // result word of every message of a batch whose queues overflowed / whose VM failed
 
-// launchers (all asynchronous on `stream`); return the number of kernels launched
+// launchers (all asynchronous on `stream`); return the number of kernels launched.
+// scan: level 1 of the whole buffer range [off[0], off[n]); queues confirmed factor occurrences and zeroes d_words.
+// d_bytes must be 16-byte aligned and readable up to 16 bytes past off[n].
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
-                uint64_t* d_words, bool want_spans, int sm_count, cudaStream_t stream);
-// unit table of a segmented scan (counters[16] = number of units) and the longest message of a batch
-int launch_plan_units(const ScanWork& w, const uint32_t* d_off, uint32_t n, cudaStream_t stream);
-int launch_max_len(const uint32_t* d_off, uint32_t n, uint32_t* d_out_max, cudaStream_t stream);
-// state visit histogram over n_sample evenly spaced messages (profile-guided residency)
-int launch_l1_profile(const DevRuleset& rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint32_t n_sample,
-                      uint32_t* d_visits, cudaStream_t stream);
-int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
-                   bool want_spans, int sm_count, cudaStream_t stream);
+                uint64_t* d_words, int sm_count, cudaStream_t stream);
+// resolve: message of every queued occurrence, slots, candidates for the VM / direct hits
+int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream);
 // one verdict word per hit message: action | matched policies << 2 | deciding rule << 12 (cg_policy_verdict_batch)
 int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdicts, int sm_count, cudaStream_t stream);
-int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, int sm_count, cudaStream_t stream);
+int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, uint32_t n, int sm_count, cudaStream_t stream);
 
 // raises the dynamic shared-memory limits of every kernel once (not legal inside stream capture)
 void prepare_scan_kernels();

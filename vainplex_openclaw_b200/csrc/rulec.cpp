@@ -711,185 +711,15 @@ CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
   return out;
 }
 
-// ------------------------------------------------------------------ prefilter (level-1 Mealy DFA + full factors)
+// ------------------------------------------------------------------ prefilter (gram filter, see rulec.h)
 
 namespace {
-struct Item { uint32_t pat; uint16_t k; bool operator<(const Item& o) const { return pat != o.pat ? pat < o.pat : k < o.k; } bool operator==(const Item& o) const { return pat == o.pat && k == o.k; } };
-using ColSeq = std::vector<uint64_t>;    // one 64-bit column mask per element (ncols <= 64) or two words for 128 columns
-
-struct L1Pattern { std::vector<std::vector<bool>> cols; std::vector<uint32_t> factors; };
-
-struct Dfa {
-  int nstates = 0;
-  std::vector<uint16_t> table; std::vector<uint32_t> acc_index, acc_offsets, acc_factors;
-};
-
-// subset construction; returns false when the state budget is exceeded
-static bool build_dfa(const std::vector<L1Pattern>& pats, int ncols, int max_states, Dfa* out) {
-  std::map<std::vector<Item>, int> ids; std::vector<std::vector<Item>> states;
-  auto intern = [&](std::vector<Item>&& k) { auto it = ids.find(k); if (it != ids.end()) return it->second; int id = (int)states.size(); ids.emplace(k, id); states.push_back(std::move(k)); return id; };
-  std::vector<std::vector<uint32_t>> start_by_col(ncols);
-  for (uint32_t q = 0; q < pats.size(); q++) for (int c = 0; c < ncols; c++) if (pats[q].cols[0][c]) start_by_col[c].push_back(q);
-  std::map<std::vector<uint32_t>, uint32_t> acc_ids; std::vector<std::vector<uint32_t>> acc_sets;
-  std::vector<uint16_t> table; std::vector<uint32_t> acc_index;
-  intern({});
-  for (size_t s = 0; s < states.size(); s++) {
-    std::vector<Item> cur = states[s];
-    for (int c = 0; c < ncols; c++) {
-      std::vector<Item> nk; std::vector<uint32_t> done;
-      for (auto& it : cur) if (pats[it.pat].cols[it.k][c]) { if (it.k + 1u == pats[it.pat].cols.size()) done.push_back(it.pat); else nk.push_back({it.pat, (uint16_t)(it.k + 1)}); }
-      for (uint32_t q : start_by_col[c]) { if (pats[q].cols.size() == 1) done.push_back(q); else nk.push_back({q, 1}); }
-      std::sort(nk.begin(), nk.end()); nk.erase(std::unique(nk.begin(), nk.end()), nk.end());
-      int nid = intern(std::move(nk));
-      if ((int)states.size() > max_states || states.size() > 16383) return false;
-      uint32_t aid = 0xffffffffu;
-      if (!done.empty()) {
-        std::vector<uint32_t> fs; for (uint32_t q : done) fs.insert(fs.end(), pats[q].factors.begin(), pats[q].factors.end());
-        std::sort(fs.begin(), fs.end()); fs.erase(std::unique(fs.begin(), fs.end()), fs.end());
-        auto it = acc_ids.find(fs);
-        if (it == acc_ids.end()) { it = acc_ids.emplace(fs, (uint32_t)acc_sets.size()).first; acc_sets.push_back(fs); }
-        aid = it->second;
-      }
-      table.push_back((uint16_t)(nid | (aid != 0xffffffffu ? 0x8000 : 0)));
-      acc_index.push_back(aid);
-    }
-  }
-  out->nstates = (int)states.size(); out->table.swap(table); out->acc_index.swap(acc_index);
-  out->acc_offsets.assign(1, 0); out->acc_factors.clear();
-  for (auto& fs : acc_sets) { out->acc_factors.insert(out->acc_factors.end(), fs.begin(), fs.end()); out->acc_offsets.push_back((uint32_t)out->acc_factors.size()); }
-  return true;
-}
+struct GramChoice { int off = 0; double count = 1e300, prob = 2; int inside = 0; bool ok = false; };
 }  // namespace
 
-// ---- mode 4: stateless level 1.  For every factor one window of 4 consecutive symbols (mode-4
-// alphabet, see fp_fold) is enumerated; hash(window) selects a 2-way bucket of 16-bit fingerprints.
-// The table is replicated once per shared-memory bank, so lane i only ever reads bank i: every
-// probe is a single conflict-free wavefront.  Returns false when the rule set is not eligible.
-static void collect_full_factors(const std::vector<CompiledRule>& rules, Prefilter& P, std::vector<FactorSeq>& seqs) {
-  std::map<ByteSet, uint16_t> set_ids;
-  auto set_id = [&](const ByteSet& b) {
-    auto it = set_ids.find(b); if (it != set_ids.end()) return it->second;
-    uint16_t id = (uint16_t)set_ids.size(); set_ids.emplace(b, id);
-    for (int k = 0; k < 8; k++) P.bytesets.push_back((uint32_t)(b.w[k >> 1] >> (32 * (k & 1))));
-    return id;
-  };
-  for (size_t r = 0; r < rules.size(); r++) {
-    if (rules[r].status != RULE_OK) continue;
-    if (rules[r].factors.empty()) { P.always_rules.push_back((uint32_t)r); continue; }
-    for (auto& f : rules[r].factors) {
-      FullFactor ff{}; ff.rule = (uint32_t)r; ff.len = (uint8_t)std::min<size_t>(f.size(), kMaxFactorElems);
-      ff.exact = (rules[r].factors_exact && f.size() <= (size_t)kMaxFactorElems) ? 1 : 0;
-      ff.pre = rules[r].factor_pre >= 0xffff ? 0xffff : (uint16_t)rules[r].factor_pre;
-      ff.pre_alpha = set_id(rules[r].factor_pre_alpha);
-      for (int k = 0; k < ff.len; k++) ff.elem[k] = set_id(f[k]);
-      P.factors.push_back(ff); seqs.push_back(FactorSeq(f.begin(), f.begin() + ff.len));
-    }
-  }
-}
-
-static bool build_fp_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* pf) {
+bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* pf, std::string* err) {
   Prefilter& P = *pf;
   P = Prefilter();
-  P.mode = 4; P.ncols = 64; P.nstates = 1;
-  for (int b = 0; b < 256; b++) P.lut[b] = (uint8_t)fp_fold((uint32_t)b);
-  std::vector<FactorSeq> seqs;
-  collect_full_factors(rules, P, seqs);
-  const uint32_t B = (uint32_t)std::max(opt.fp_buckets, 16);
-  std::set<uint32_t> all_syms; for (int b = 0; b < 256; b++) all_syms.insert(fp_fold((uint32_t)b));
-  const size_t kMaxVariants = 256;
-  // windows: key -> factor ids
-  std::map<uint32_t, std::vector<uint32_t>> keys;
-  std::vector<uint32_t> trig_bytes; std::vector<std::vector<uint32_t>> trig_factors;
-  for (size_t f = 0; f < seqs.size(); f++) {
-    const FactorSeq& s = seqs[f]; const int len = (int)s.size();
-    std::vector<std::vector<uint32_t>> syms(len);
-    for (int k = 0; k < len; k++) { std::set<uint32_t> u; for (int b = 0; b < 256; b++) if (s[k].has(b)) u.insert(fp_fold((uint32_t)b)); syms[k].assign(u.begin(), u.end()); }
-    // candidate windows: 4 symbols ending at factor element `wend-1`; positions before the factor are wildcards
-    int best_wend = -1; double best_cnt = 1e30, best_p = 2;
-    for (int wend = std::min(len, 4); wend <= len; wend++) {
-      double cnt = 1, p = 1;
-      for (int j = 0; j < 4; j++) { int k = wend - 4 + j; if (k < 0) { cnt *= (double)all_syms.size(); } else { cnt *= (double)syms[k].size(); double q = 0; for (int b = 0; b < 256; b++) if (s[k].has(b)) q += Compiler::byte_weight(b); p *= std::min(q, 1.0); } }
-      if (cnt < best_cnt || (cnt == best_cnt && p < best_p)) { best_cnt = cnt; best_p = p; best_wend = wend; }
-    }
-    if (best_wend < 0 || best_cnt > (double)kMaxVariants) {
-      // not enumerable as a 4-symbol window (e.g. '@' + classes): fall back to a single-byte trigger,
-      // compared SWAR-style in registers by the scan kernel (at most two distinct trigger bytes per set)
-      int tk = -1; double tp = 2; int tb = -1;
-      for (int k = 0; k < len; k++) {
-        int cnt = 0, last = -1; for (int b = 0; b < 256; b++) if (s[k].has(b)) { cnt++; last = b; }
-        if (cnt == 1 && Compiler::byte_weight(last) < tp) { tp = Compiler::byte_weight(last); tk = k; tb = last; }
-      }
-      size_t ti = 0;
-      if (tk >= 0) { for (; ti < trig_bytes.size(); ti++) if (trig_bytes[ti] == (uint32_t)tb) break; }
-      if (tk < 0 || (ti == trig_bytes.size() && trig_bytes.size() >= 2)) {
-        if (getenv("CG_FP_DEBUG")) fprintf(stderr, "fp: factor %zu of rule %u not enumerable (len %d, best %g variants)\n", f, P.factors[f].rule, len, best_cnt);
-        return false;
-      }
-      if (ti == trig_bytes.size()) { trig_bytes.push_back((uint32_t)tb); trig_factors.emplace_back(); }
-      trig_factors[ti].push_back((uint32_t)f);
-      P.factors[f].win_off = (uint8_t)tk; P.factors[f].win_len = 1;
-      continue;
-    }
-    P.factors[f].win_len = (uint8_t)std::min(best_wend, 4); P.factors[f].win_off = (uint8_t)(best_wend - P.factors[f].win_len);
-    // enumerate: symbol j of the window sits in bits 8j..8j+7 (oldest symbol lowest)
-    std::vector<uint32_t> cur = {0};
-    for (int j = 0; j < 4; j++) {
-      int k = best_wend - 4 + j; std::vector<uint32_t> nx;
-      const std::vector<uint32_t> wild(all_syms.begin(), all_syms.end());
-      const std::vector<uint32_t>& opts = k < 0 ? wild : syms[k];
-      for (uint32_t base : cur) for (uint32_t v : opts) nx.push_back(base | (v << (8 * j)));
-      cur.swap(nx);
-    }
-    for (uint32_t key : cur) keys[key].push_back((uint32_t)f);
-  }
-  P.fp_keys = (uint32_t)keys.size();
-  if (keys.size() > (size_t)B * 2 * 3 / 4) { if (getenv("CG_FP_DEBUG")) fprintf(stderr, "fp: %zu keys exceed the capacity of %u buckets\n", keys.size(), B); return false; }              // keep the load factor below 75 %
-  // find a multiplier under which no bucket overflows and no key has fingerprint 0
-  uint64_t sm = 0x9E3779B97F4A7C15ull;
-  for (int attempt = 0; attempt < 512; attempt++) {
-    sm += 0x9E3779B97F4A7C15ull; uint64_t z = sm; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
-    const uint32_t mult = (uint32_t)z | 1u;
-    std::vector<uint32_t> table(B, 0xffffffffu); std::vector<std::vector<uint32_t>> slot_f((size_t)B * 2);     // 0xffff = empty way
-    bool ok = true;
-    for (auto& kv : keys) {
-      uint32_t hsh = kv.first * mult, fp = (hsh >> 8) & 0xffffu, b = (uint32_t)(((uint64_t)hsh * B) >> 32);
-      if (fp == 0xffffu) { ok = false; break; }
-      int way = -1;
-      for (int w2 = 0; w2 < 2; w2++) { uint32_t cur_fp = (table[b] >> (16 * w2)) & 0xffffu; if (cur_fp == fp) { way = w2; break; } }
-      if (way < 0) for (int w2 = 0; w2 < 2; w2++) if (((table[b] >> (16 * w2)) & 0xffffu) == 0xffffu) { way = w2; table[b] = (table[b] & ~(0xffffu << (16 * w2))) | (fp << (16 * w2)); break; }
-      if (way < 0) { ok = false; break; }
-      auto& dst = slot_f[(size_t)b * 2 + way]; dst.insert(dst.end(), kv.second.begin(), kv.second.end());
-    }
-    if (!ok) continue;
-    P.fp_buckets = B; P.fp_mult = mult; P.fp_table = table;
-    P.fp_acc.assign((size_t)B * 2, 0xffffffffu); P.acc_offsets.assign(1, 0); P.acc_factors.clear();
-    for (size_t sidx = 0; sidx < slot_f.size(); sidx++) {
-      if (slot_f[sidx].empty()) continue;
-      std::sort(slot_f[sidx].begin(), slot_f[sidx].end()); slot_f[sidx].erase(std::unique(slot_f[sidx].begin(), slot_f[sidx].end()), slot_f[sidx].end());
-      P.fp_acc[sidx] = (uint32_t)(P.acc_offsets.size() - 1);
-      P.acc_factors.insert(P.acc_factors.end(), slot_f[sidx].begin(), slot_f[sidx].end());
-      P.acc_offsets.push_back((uint32_t)P.acc_factors.size());
-    }
-    P.trig_bytes = trig_bytes; P.trig_acc.clear();
-    for (auto& tf : trig_factors) { P.trig_acc.push_back((uint32_t)(P.acc_offsets.size() - 1)); P.acc_factors.insert(P.acc_factors.end(), tf.begin(), tf.end()); P.acc_offsets.push_back((uint32_t)P.acc_factors.size()); }
-    P.window_min = 255; P.window_max = 0;
-    for (auto& ff : P.factors) { P.window_min = std::min<int>(P.window_min, ff.win_len); P.window_max = std::max<int>(P.window_max, ff.win_len); }
-    if (P.factors.empty()) P.window_min = P.window_max = 0;
-    P.table.assign(64, 0); P.acc_index.assign(64, 0xffffffffu);        // unused DFA part (kept non-empty)
-    return true;
-  }
-  return false;
-}
-
-bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt_in, Prefilter* pf, std::string* err) {
-  PrefilterOptions opt = opt_in;
-  if (opt.mode == 4) {
-    if (build_fp_prefilter(rules, opt, pf)) return true;
-    opt.mode = 2;                       // windows not enumerable / table full: the general DFA takes over
-  }
-  Prefilter& P = *pf;
-  P = Prefilter();
-  P.mode = opt.mode;
   // ---- full factors + deduplicated byte sets
   std::map<ByteSet, uint16_t> set_ids;
   auto set_id = [&](const ByteSet& b) {
@@ -911,95 +741,108 @@ bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOpti
       P.factors.push_back(ff); seqs.push_back(FactorSeq(f.begin(), f.begin() + ff.len));
     }
   }
-  // ---- column mapping
-  int ncols; uint8_t colmap[256];
-  if (opt.mode == 0) { ncols = 128; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)(b & 0x7f); }
-  else if (opt.mode == 2) { ncols = 64; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)((b & 0x1f) | ((b >> 1) & 0x20)); }
-  else if (opt.mode == 3) { ncols = 32; for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)(b & 0x1f); }
-  else {
-    std::set<ByteSet> distinct; for (auto& q : seqs) for (auto& e : q) distinct.insert(e);
-    std::vector<int> cls(256, 0); int ncls = 1;
-    for (auto& bs : distinct) {
-      std::map<std::pair<int, bool>, int> remap; std::vector<int> nc(256);
-      for (int b = 0; b < 256; b++) { auto key = std::make_pair(cls[b], bs.has(b)); auto it = remap.find(key); if (it == remap.end()) it = remap.emplace(key, (int)remap.size()).first; nc[b] = it->second; }
-      cls.swap(nc); ncls = (int)remap.size();
-    }
-    while (ncls > opt.max_classes) {   // merge the two lightest classes (only ever widens sets => still sound)
-      std::vector<double> w(ncls, 0); for (int b = 0; b < 256; b++) w[cls[b]] += Compiler::byte_weight(b);
-      int a = -1, c2 = -1; for (int k = 0; k < ncls; k++) { if (a < 0 || w[k] < w[a]) { c2 = a; a = k; } else if (c2 < 0 || w[k] < w[c2]) c2 = k; }
-      for (int b = 0; b < 256; b++) if (cls[b] == c2) cls[b] = a;
-      for (int b = 0; b < 256; b++) if (cls[b] == ncls - 1 && c2 != ncls - 1) cls[b] = c2;
-      ncls--;
-    }
-    ncols = 32; while (ncols < ncls) ncols *= 2;
-    for (int b = 0; b < 256; b++) colmap[b] = (uint8_t)cls[b];
-  }
-  memcpy(P.lut, colmap, 256); P.ncols = ncols;
-  // probability that a text byte lands in a column (for ranking windows)
-  std::vector<double> colw(ncols, 0); for (int b = 0; b < 256; b++) colw[colmap[b]] += Compiler::byte_weight(b);
-  auto elem_cols = [&](const ByteSet& e) { std::vector<bool> c(ncols, false); for (int b = 0; b < 256; b++) if (e.has(b)) c[colmap[b]] = true; return c; };
-  auto elem_prob = [&](const ByteSet& e) { std::vector<bool> c = elem_cols(e); double p = 0; for (int k = 0; k < ncols; k++) if (c[k]) p += colw[k]; return std::min(p, 1.0); };
-
+  if (P.factors.size() >= (1u << 20)) { if (err) *err = "too many factors"; return false; }
   const size_t nf = seqs.size();
+  // folded images of every element
+  std::vector<uint32_t> wild; { std::set<uint32_t> u; for (int b = 0; b < 256; b++) u.insert(gram_fold((uint32_t)b)); wild.assign(u.begin(), u.end()); }
+  std::vector<std::vector<std::vector<uint32_t>>> img(nf);
   std::vector<std::vector<double>> eprob(nf);
-  for (size_t f = 0; f < nf; f++) for (auto& e : seqs[f]) eprob[f].push_back(elem_prob(e));
-  // best window of length w for factor f (lowest probability); returns offset
-  auto best_window = [&](size_t f, int w, double* prob) {
-    int len = (int)seqs[f].size(); if (w > len) w = len;
-    int bo = 0; double bp = 2;
-    for (int o = 0; o + w <= len; o++) { double p = 1; for (int k = 0; k < w; k++) p *= eprob[f][o + k]; if (p < bp) { bp = p; bo = o; } }
-    *prob = bp; return bo;
+  for (size_t f = 0; f < nf; f++) for (auto& e : seqs[f]) {
+    std::set<uint32_t> u; double q = 0;
+    for (int b = 0; b < 256; b++) if (e.has(b)) { u.insert(gram_fold((uint32_t)b)); q += Compiler::byte_weight(b); }
+    img[f].push_back(std::vector<uint32_t>(u.begin(), u.end())); eprob[f].push_back(std::min(q, 1.0));
+  }
+  // best gram position of factor f for start residue r at stride S
+  auto choose = [&](size_t f, int S, int r) {
+    GramChoice best; const int L = (int)seqs[f].size();
+    for (int o = -(kGramLen - 1); o <= L - 1; o++) {
+      if ((((o + r) % S) + S) % S != 0) continue;
+      double cnt = 1, p = 1; int inside = 0;
+      for (int j = 0; j < kGramLen; j++) { int k = o + j; if (k < 0 || k >= L) cnt *= (double)wild.size(); else { cnt *= (double)img[f][k].size(); p *= eprob[f][k]; inside++; } }
+      if (cnt < best.count || (cnt == best.count && (p < best.prob || (p == best.prob && inside > best.inside)))) { best.off = o; best.count = cnt; best.prob = p; best.inside = inside; }
+    }
+    best.ok = best.count <= (double)opt.max_keys_per_gram;
+    return best;
   };
-  auto try_build = [&](const std::vector<int>& wl, Dfa* dfa) {
-    std::map<std::vector<std::vector<bool>>, std::vector<uint32_t>> uniq;
+  auto plan = [&](int S, std::vector<std::vector<GramChoice>>* out, std::vector<char>* uncovered) {
+    double total = 0; out->assign(nf, {}); uncovered->assign(nf, 0);
     for (size_t f = 0; f < nf; f++) {
-      double p; int w = std::min<int>(wl[f], (int)seqs[f].size()); int o = best_window(f, w, &p);
-      std::vector<std::vector<bool>> cs; for (int k = 0; k < w; k++) cs.push_back(elem_cols(seqs[f][o + k]));
-      uniq[cs].push_back((uint32_t)f);
+      for (int r = 0; r < S; r++) { GramChoice c = choose(f, S, r); (*out)[f].push_back(c); if (!c.ok) (*uncovered)[f] = 1; }
+      if (!(*uncovered)[f]) for (auto& c : (*out)[f]) total += c.count;
     }
-    std::vector<L1Pattern> pats; for (auto& kv : uniq) pats.push_back({kv.first, kv.second});
-    return build_dfa(pats, ncols, opt.max_states, dfa);
+    return total;
   };
-
-  Dfa best; bool have = false; std::vector<int> wl(nf, 0);
-  if (nf == 0) { have = true; best.nstates = 1; best.table.assign(ncols, 0); best.acc_index.assign(ncols, 0xffffffffu); best.acc_offsets.assign(1, 0); }
-  int base = 0;
-  for (int w = std::min(opt.max_window, kMaxWindow); w >= 1 && !have; w--) {
-    std::vector<int> t(nf, w); Dfa d;
-    if (try_build(t, &d)) { best = std::move(d); wl = t; have = true; base = w; }
-  }
-  if (!have) {
-    // not even 1-element windows fit: every factored rule becomes an always-candidate
-    for (auto& ff : P.factors) P.always_rules.push_back(ff.rule);
-    std::sort(P.always_rules.begin(), P.always_rules.end()); P.always_rules.erase(std::unique(P.always_rules.begin(), P.always_rules.end()), P.always_rules.end());
-    P.factors.clear(); best.nstates = 1; best.table.assign(ncols, 0); best.acc_index.assign(ncols, 0xffffffffu); best.acc_offsets.assign(1, 0); best.acc_factors.clear();
-    if (err) *err = "prefilter did not fit the state budget; all rules verified on every message";
-  } else if (nf && base < std::min(opt.max_window, kMaxWindow)) {
-    // spend the remaining rows on the most frequent windows: extend the top fraction by one element, repeatedly
-    for (int round = 0; round < 3; round++) {
-      std::vector<std::pair<double, size_t>> order;
-      for (size_t f = 0; f < nf; f++) if ((int)seqs[f].size() > wl[f] && wl[f] < kMaxWindow) { double p; best_window(f, wl[f], &p); order.push_back({-p, f}); }
-      if (order.empty()) break;
-      std::sort(order.begin(), order.end());
-      bool grew = false;
-      for (double frac : {1.0, 0.5, 0.25, 0.125, 0.0625}) {
-        size_t cnt = std::max<size_t>(1, (size_t)(order.size() * frac));
-        std::vector<int> t = wl; for (size_t k = 0; k < cnt; k++) t[order[k].second]++;
-        Dfa d;
-        if (try_build(t, &d)) { best = std::move(d); wl = t; grew = true; break; }
-      }
-      if (!grew) break;
+  std::vector<std::vector<GramChoice>> ch; std::vector<char> unc;
+  int S = opt.stride == 2 ? 2 : 4;
+  double total = plan(S, &ch, &unc);
+  if (S == 4 && opt.stride != 4) {
+    // stride 4 needs every factor covered at four residues; one uncoverable short factor (or too many keys) moves the
+    // whole set to stride 2, where the remaining uncoverable ones become triggers / always-candidates
+    bool any_unc = false; for (char u : unc) any_unc |= u != 0;
+    if (any_unc || total > (double)opt.max_keys) {
+      std::vector<std::vector<GramChoice>> ch2; std::vector<char> unc2;
+      double total2 = plan(2, &ch2, &unc2);
+      size_t n4 = 0, n2 = 0; for (char u : unc) n4 += u != 0; for (char u : unc2) n2 += u != 0;
+      if (n2 < n4 || total > (double)opt.max_keys) { S = 2; ch.swap(ch2); unc.swap(unc2); total = total2; }
     }
   }
-  // record the windows that were used
-  P.window_min = 255; P.window_max = 0;
-  for (size_t f = 0; f < P.factors.size(); f++) {
-    double p; int w = std::min<int>(wl[f], (int)seqs[f].size()); int o = best_window(f, w, &p);
-    P.factors[f].win_off = (uint8_t)o; P.factors[f].win_len = (uint8_t)w;
-    P.window_min = std::min(P.window_min, w); P.window_max = std::max(P.window_max, w);
+  P.stride = S;
+  // ---- factors no gram covers: single-byte trigger (rarest singleton element), else every message is a candidate
+  std::vector<std::vector<uint32_t>> trig_lists;
+  std::set<uint32_t> always(P.always_rules.begin(), P.always_rules.end());
+  for (size_t f = 0; f < nf; f++) {
+    if (!unc[f]) continue;
+    int tk = -1, tb = -1; double tp = 2;
+    for (int k = 0; k < (int)seqs[f].size(); k++) {
+      int cnt = 0, last = -1; for (int b = 0; b < 256; b++) if (seqs[f][k].has(b)) { cnt++; last = b; }
+      if (cnt == 1 && Compiler::byte_weight(last) < tp) { tp = Compiler::byte_weight(last); tk = k; tb = last; }
+    }
+    size_t ti = 0;
+    if (tk >= 0) for (; ti < P.trig_bytes.size(); ti++) if (P.trig_bytes[ti] == (uint32_t)tb) break;
+    if (tk < 0 || (ti == P.trig_bytes.size() && P.trig_bytes.size() >= 2)) { always.insert(P.factors[f].rule); continue; }
+    if (ti == P.trig_bytes.size()) { P.trig_bytes.push_back((uint32_t)tb); trig_lists.emplace_back(); }
+    trig_lists[ti].push_back((uint32_t)f | ((uint32_t)tk << 20));
   }
-  if (P.factors.empty()) P.window_min = P.window_max = 0;
-  P.nstates = best.nstates; P.table = best.table; P.acc_index = best.acc_index; P.acc_offsets = best.acc_offsets; P.acc_factors = best.acc_factors;
+  P.always_rules.assign(always.begin(), always.end());
+  // A rule that is a candidate for every message is verified over the whole message anyway: its factors leave the filter
+  // altogether (an occurrence event would only shadow the whole-message run in the per-message candidate bitmap).
+  std::vector<uint32_t> new_id(nf, 0xffffffffu);
+  {
+    std::vector<FullFactor> kept;
+    for (size_t f = 0; f < nf; f++) if (!always.count(P.factors[f].rule)) { new_id[f] = (uint32_t)kept.size(); kept.push_back(P.factors[f]); }
+    P.factors.swap(kept);
+  }
+  P.trig_offsets.assign(1, 0);
+  for (auto& tl : trig_lists) {
+    for (uint32_t e : tl) if (new_id[e & 0xfffffu] != 0xffffffffu) P.trig_list.push_back(new_id[e & 0xfffffu] | (e & 0xfff00000u));
+    P.trig_offsets.push_back((uint32_t)P.trig_list.size());
+  }
+  // ---- keys + level-1b entries
+  std::set<uint32_t> shapes;
+  for (size_t f = 0; f < nf; f++) {
+    if (unc[f] || new_id[f] == 0xffffffffu) continue;
+    const int L = (int)seqs[f].size();
+    for (int r = 0; r < S; r++) {
+      const GramChoice& c = ch[f][r];
+      GramEntry e{}; e.factor = new_id[f]; e.off = c.off;
+      std::vector<uint32_t> cur = {0};
+      for (int j = 0; j < kGramLen; j++) {
+        const int k = c.off + j; const std::vector<uint32_t>& opts = (k < 0 || k >= L) ? wild : img[f][k];
+        if (k >= 0 && k < L && opts.size() == 1) { e.key |= opts[0] << (8 * j); e.mask |= 0xffu << (8 * j); }
+        std::vector<uint32_t> nx; nx.reserve(cur.size() * opts.size());
+        for (uint32_t base : cur) for (uint32_t v : opts) nx.push_back(base | (v << (8 * j)));
+        cur.swap(nx);
+      }
+      P.keys.insert(P.keys.end(), cur.begin(), cur.end());
+      P.entries.push_back(e); shapes.insert(e.mask);
+    }
+  }
+  std::sort(P.keys.begin(), P.keys.end()); P.keys.erase(std::unique(P.keys.begin(), P.keys.end()), P.keys.end());
+  P.shapes.assign(shapes.begin(), shapes.end());
+  P.min_factor_len = 255; P.max_factor_len = 0;
+  for (auto& ff : P.factors) { P.min_factor_len = std::min<uint32_t>(P.min_factor_len, ff.len); P.max_factor_len = std::max<uint32_t>(P.max_factor_len, ff.len); }
+  if (P.factors.empty()) P.min_factor_len = 0;
+  (void)err;
   return true;
 }
 

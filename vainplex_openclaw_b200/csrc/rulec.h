@@ -6,9 +6,9 @@
 // Output is a flat device image with two parts:
 //   1. per rule: a unit-level Pike-VM program (exact ECMAScript leftmost-first semantics on
 //      UTF-16 code units, decoded on the fly from UTF-8 by the verify kernel), and
-//   2. for the whole set: one prefilter DFA over *necessary factors* of every rule
+//   2. for the whole set: one stateless gram filter over *necessary factors* of every rule
 //      (byte-set sequences every match must contain) -- sound over-approximation, every
-//      byte of every message goes through exactly this table from shared memory.
+//      byte of every message is hashed against exactly this bitmap in shared memory.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -78,50 +78,56 @@ struct CompiledRule {
 // flags: bit0 = ignoreCase ("i").  `src` is the JS pattern source encoded as UTF-8.
 CompiledRule compile_rule(const char* src, size_t len, uint32_t flags);
 
-// ---- prefilter: level 1 = Mealy DFA over short *windows* of every rule's necessary factors
-// (shared memory, one lookup per byte); level 2 = exact confirmation of the full factor (up to 16
-// byte-set elements) at the flagged position; only confirmed (message, rule) pairs reach the VM.
-constexpr int kMaxWindow = 8;
+// ---- prefilter: a stateless two-level filter over every rule's *necessary factors* (byte-set sequences every
+// match must contain; <= kMaxFactorElems elements are kept per factor).
+//   level 1a  every aligned 4-byte gram of the batch buffer (stride 4), or every even-offset gram (stride 2), is
+//             folded (gram_fold: case bit and bit 7 dropped, digits collapsed), hashed and tested against a bitmap
+//             in shared memory.  For every factor and every residue r of its start position modulo the stride, ONE
+//             gram position relative to the factor is registered: all folded byte combinations the factor allows
+//             there (bytes outside the factor are wildcards) are set in the bitmap.
+//   level 1b  a flagged gram is looked up in a hash table of (masked key -> factor, gram offset); the factor's byte
+//             sets are then compared exactly at that position (what level 2 used to do in its own kernel).
+// Factors no gram can cover within the key budget fall back to a single-byte trigger (at most two distinct bytes,
+// compared SWAR-style), and rules without any usable factor are candidates for every message.
 constexpr int kMaxFactorElems = 16;
+constexpr int kGramLen = 4;
+
+// byte -> 6-bit-ish symbol of the gram hash (49 distinct values).  z = (b & 0x5f) ^ 0x10; z < 0x10 (digits and
+// : ; < = > ?, plus the C0/C1 bytes sharing those low bits) collapses to 0.  Mirrors gram_fold_word() in gram_filter.h.
+inline uint32_t gram_fold(uint32_t b) { uint32_t z = (b & 0x5fu) ^ 0x10u; return z < 0x10u ? 0u : z; }
+constexpr uint32_t kGramMult = 0x9E3779B1u;          // bitmap hash: h = key * kGramMult
+constexpr uint32_t kGramMult2 = 0x85EBCA77u;         // level-1b bucket hash
 
 struct PrefilterOptions {
-  int mode = 2;              // 0 = direct 7-bit (128 cols), 1 = byte->class LUT (<=64), 2 = folded 6-bit (64, SWAR), 3 = folded 5-bit (32, SWAR),
-                             // 4 = lane-private fingerprint table over 4-byte windows (falls back to 2 when a rule set does not fit)
-  int fp_buckets = 1024;     // mode 4: 2-way buckets per lane-bank replica
-  int max_states = 24576;    // total level-1 states (rows beyond the shared-memory budget stay in L2-resident HBM)
-  int max_classes = 64;      // LUT mode only
-  int max_window = kMaxWindow;
+  int stride = 0;                 // 0 = choose: 4 when every factor is coverable within max_keys, else 2
+  uint32_t max_keys = 24576;      // bitmap keys that still allow stride 4
+  uint32_t max_keys_per_gram = 4096;
 };
 struct FullFactor {
   uint32_t rule;
-  uint8_t len, win_off, win_len, exact;   // exact: a confirmed occurrence proves the rule matches (RegExp.test)
+  uint8_t len, exact;                     // exact: a confirmed occurrence proves the rule matches (RegExp.test)
   uint16_t elem[kMaxFactorElems];         // byte-set ids
   uint16_t pre;                           // max units of a match before the factor (0xffff = unbounded)
   uint16_t pre_alpha;                     // byte-set id: what the part of a match before the factor can consist of
 };
+struct GramEntry {                        // one per (factor, residue of the factor's start modulo the stride)
+  uint32_t key, mask;                     // folded gram with the class / wildcard bytes zeroed; 0xff per byte that is part of the key
+  uint32_t factor; int32_t off;           // gram start - factor start, -3 .. len-1
+};
 struct Prefilter {
-  int mode = 2;
-  int ncols = 64;                     // columns per row (power of two)
-  int nstates = 1;                    // states are numbered breadth-first: shallow (hot) states first
-  int window_min = 0, window_max = 0; // level-1 window lengths actually used
-  std::vector<uint16_t> table;        // nstates * ncols; bit 15 = accepting transition, bits 0-14 = next state
-  uint8_t lut[256];                   // byte -> column (used by the device only in LUT mode)
-  std::vector<uint32_t> acc_index;    // nstates * ncols: accept id of an accepting transition, else 0xffffffff
-  std::vector<uint32_t> acc_offsets;  // CSR over accept ids -> factor ids
-  std::vector<uint32_t> acc_factors;
+  int stride = 4;
+  std::vector<uint32_t> keys;         // every folded gram the bitmap must flag (sorted, unique)
+  std::vector<GramEntry> entries;
+  std::vector<uint32_t> shapes;       // distinct entry masks
   std::vector<FullFactor> factors;
   std::vector<uint32_t> bytesets;     // 8 words per 256-bit set
   std::vector<uint32_t> always_rules; // rules without usable factors: candidates for every message
-  // mode 4: fingerprint table.  bucket = umulhi(h, fp_buckets), fingerprint = (h >> 8) & 0xffff, h = window * fp_mult
-  uint32_t fp_buckets = 0, fp_mult = 0, fp_keys = 0;
-  std::vector<uint32_t> fp_table;     // fp_buckets words: two 16-bit fingerprints (0xffff = empty)
-  std::vector<uint32_t> fp_acc;       // 2 * fp_buckets accept ids (0xffffffff = empty)
-  std::vector<uint32_t> trig_bytes;   // mode 4: up to two single-byte triggers for factors without an enumerable window
-  std::vector<uint32_t> trig_acc;     //         their accept ids
+  std::vector<uint32_t> trig_bytes;   // up to two single-byte triggers for factors no gram covers
+  std::vector<uint32_t> trig_offsets; // CSR over triggers -> trig_list
+  std::vector<uint32_t> trig_list;    // factor | element index of the trigger byte << 20
+  uint32_t min_factor_len = 0, max_factor_len = 0;
 };
 
-// the byte -> 6-bit symbol map of mode 4: fold6 with the digit columns collapsed to two symbols
-inline uint32_t fp_fold(uint32_t b) { uint32_t c = (b & 0x1fu) | ((b >> 1) & 0x20u); if ((c & 0x30u) == 0x10u) c &= 0x38u; return c; }
 bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOptions& opt, Prefilter* out, std::string* err);
 
 }  // namespace cg

@@ -6,58 +6,6 @@
 
 namespace cg {
 
-// (Re)builds the shared-memory image of a DFA-mode rule set from H.pf.table: see the layout comment below.
-void build_dfa_image(HostImage* out) {
-  // shared-memory image: [rows 0..hot of the table, `row_stride` bytes apart][pad to 16][lut 256 B].
-  // Entries are plain u16 state indices.  Every transition that is accepting, or leads to a state that is
-  // not resident (>= hot), is stored as `hot`, the index of an absorbing trap row: the fast path of
-  // scan_kernel then needs no flag bits -- a chunk that ends in the trap row is re-walked on the full table.
-  // row_stride = 2 * ncols + 4: the 4 pad bytes rotate consecutive rows by one bank, so lanes sitting in
-  // different states but reading the same frequent column (' ', 'e', ...) land in different banks.
-  HostImage& H = *out; size_t budget = H.budget_bytes; const uint32_t cols = H.image_cols; size_t hot_rows;
-  H.row_stride = cols * 2 + 4;
-  budget = std::min<size_t>(budget, (size_t)155 * 1024);            // + 64 KB staging + 6 KB event buffers + static shared memory <= 227 KB per CTA
-  hot_rows = std::min<size_t>((budget - 256 - 16) / H.row_stride, 16383);
-  H.hot_states = (uint32_t)std::min<size_t>(hot_rows > 1 ? hot_rows - 1 : 1, (size_t)H.pf.nstates);
-  const uint32_t hot = H.hot_states; const size_t nc = (size_t)H.pf.ncols;
-  size_t tbl_bytes = ((size_t)(hot + 1) * H.row_stride + 15) & ~(size_t)15;
-  H.lut_off = (uint32_t)tbl_bytes;
-  H.image.assign(tbl_bytes + 256, 0);
-  auto put = [&](uint32_t row, size_t col, uint16_t v) { memcpy(H.image.data() + (size_t)row * H.row_stride + 2 * col, &v, 2); };
-  for (uint32_t s = 0; s < hot; s++) for (size_t c = 0; c < nc; c++) {
-    uint16_t e = H.pf.table[(size_t)s * nc + c];
-    put(s, c, ((e & 0x8000) || (uint32_t)(e & 0x3fff) >= hot) ? (uint16_t)hot : (uint16_t)(e & 0x3fff));
-  }
-  for (size_t c = 0; c < (size_t)cols; c++) put(hot, c, (uint16_t)hot);
-  memcpy(H.image.data() + H.lut_off, H.pf.lut, 256);
-}
-
-// Profile-guided residency: renumber the level-1 states so that the most visited ones get the lowest indices
-// (= the rows that are resident in shared memory), keeping the start state at index 0.  `visits[s]` is how often
-// state s was left on a sample of real traffic.  Everything indexed by state (table, acc_index) is permuted and
-// the image rebuilt; the matcher's results do not depend on the numbering, only how often its slow path runs.
-void rank_states_by_visits(HostImage* out, const uint32_t* visits) {
-  HostImage& H = *out; Prefilter& P = H.pf;
-  if (P.mode == 4 || P.nstates <= 1) return;
-  const uint32_t ns = (uint32_t)P.nstates; const size_t nc = (size_t)P.ncols;
-  std::vector<uint32_t> order(ns);
-  for (uint32_t i = 0; i < ns; i++) order[i] = i;
-  std::stable_sort(order.begin() + 1, order.end(), [&](uint32_t a, uint32_t b) { return visits[a] > visits[b]; });
-  std::vector<uint32_t> new_of_old(ns);
-  for (uint32_t i = 0; i < ns; i++) new_of_old[order[i]] = i;
-  std::vector<uint16_t> table(P.table.size()); std::vector<uint32_t> acc(P.acc_index.size(), 0xffffffffu);
-  for (uint32_t i = 0; i < ns; i++) {
-    const uint32_t o = order[i];
-    for (size_t c = 0; c < nc; c++) {
-      const uint16_t e = P.table[(size_t)o * nc + c];
-      table[(size_t)i * nc + c] = (uint16_t)((e & 0xc000) | new_of_old[e & 0x3fff]);
-      acc[(size_t)i * nc + c] = P.acc_index[(size_t)o * nc + c];
-    }
-  }
-  P.table.swap(table); P.acc_index.swap(acc);
-  build_dfa_image(out);
-}
-
 bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, HostImage* out, std::string* err) {
   HostImage& H = *out;
   H = HostImage();
@@ -89,31 +37,56 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   H.n_sets = (uint32_t)(H.sets.size() / 6);
 
   PrefilterOptions po;
-  po.mode = opt.mode; po.max_classes = opt.max_classes; po.max_window = opt.max_window;
-  int cols = po.mode == 0 ? 128 : po.mode == 2 ? 64 : po.mode == 3 ? 32 : po.mode == 4 ? 64 : (po.max_classes <= 32 ? 32 : 64);
-  size_t budget = std::max<size_t>(opt.budget_bytes, 256 + (size_t)cols * 2 * 2);
-  size_t hot_rows = std::min<size_t>((budget - 256) / ((size_t)cols * 2), 32767);
-  po.max_states = std::max<int>((int)std::min<size_t>((size_t)std::max(opt.max_states, 1), 16383), 1);
-  po.fp_buckets = (int)std::max<size_t>((budget - 256) / 128, 16);
+  po.stride = opt.stride; po.max_keys = opt.max_keys;
   if (!build_prefilter(H.rules, po, &H.pf, err)) return false;
-  for (auto& f : H.pf.factors) {
+  const Prefilter& P = H.pf;
+  for (auto& f : P.factors) {
     H.factor_words.push_back(f.rule);
-    H.factor_words.push_back((uint32_t)f.len | ((uint32_t)f.win_off << 8) | ((uint32_t)f.win_len << 16) | ((uint32_t)f.exact << 24));
+    H.factor_words.push_back((uint32_t)f.len | ((uint32_t)f.exact << 24));
     for (int k = 0; k < kMaxFactorElems; k += 2) H.factor_words.push_back((uint32_t)f.elem[k] | ((uint32_t)f.elem[k + 1] << 16));
     H.factor_words.push_back(f.pre); H.factor_words.push_back(f.pre_alpha);
   }
-  if (H.pf.mode == 4) {
-    // fingerprint table replicated once per bank: word (bucket * 32 + lane) holds bucket's two fingerprints
-    H.hot_states = 0; H.lut_off = 0; H.row_stride = 0;
-    H.image.assign(256 + (size_t)H.pf.fp_buckets * 128, 0);
-    memcpy(H.image.data(), H.pf.lut, 256);
-    uint32_t* t = reinterpret_cast<uint32_t*>(H.image.data() + 256);
-    for (uint32_t b = 0; b < H.pf.fp_buckets; b++) for (int l = 0; l < 32; l++) t[(size_t)b * 32 + l] = H.pf.fp_table[b];
-    while (H.image.size() % 16) H.image.push_back(0);
-    return true;
+  // ---- level-1b hash table: entries sorted by bucket
+  uint32_t nb = 16; while (nb < P.entries.size() / 2) nb *= 2;
+  H.n_buckets = nb; H.nb_shift = 32; { uint32_t t = nb; while (t > 1) { t >>= 1; H.nb_shift--; } }
+  std::vector<uint32_t> shape_of(P.entries.size()), bucket_of(P.entries.size()), order(P.entries.size());
+  for (size_t i = 0; i < P.entries.size(); i++) {
+    uint32_t s = 0; while (P.shapes[s] != P.entries[i].mask) s++;
+    shape_of[i] = s; bucket_of[i] = (uint32_t)((((P.entries[i].key & P.entries[i].mask) ^ (s * 0x9E3779B9u)) * kGramMult2) >> H.nb_shift); order[i] = (uint32_t)i;
   }
-  H.budget_bytes = budget; H.image_cols = (uint32_t)cols;
-  build_dfa_image(&H);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return bucket_of[a] < bucket_of[b]; });
+  H.bucket_start.assign((size_t)nb + 1, 0);
+  for (uint32_t i : order) H.bucket_start[bucket_of[i] + 1]++;
+  for (uint32_t b = 0; b < nb; b++) H.bucket_start[b + 1] += H.bucket_start[b];
+  for (uint32_t i : order) {
+    const GramEntry& e = P.entries[i];
+    H.entry_words.push_back(e.key & e.mask);
+    H.entry_words.push_back(e.factor | ((uint32_t)(e.off + 3) << 20) | (shape_of[i] << 25));
+  }
+  // ---- bitmap: one bit per key (optionally two in the same word: blocked Bloom filter); sized for a fill below one per cent
+  uint32_t bm = opt.bitmap_kb ? opt.bitmap_kb * 1024u : 16u * 1024u;
+  if (!opt.bitmap_kb) while (bm < 128u * 1024u && (uint64_t)bm * 8 < (uint64_t)P.keys.size() * 256) bm *= 2;
+  { uint32_t t = 4096; while (t < bm) t *= 2; bm = std::min<uint32_t>(t, 128u * 1024u); }       // power of two
+  auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t tables = a16(H.bucket_start.size() * 4) + a16(H.entry_words.size() * 4) + a16(H.factor_words.size() * 4 + 64) + a16(P.bytesets.size() * 4 + 32);
+  while (bm > 16u * 1024u && (size_t)bm + tables > opt.budget_bytes && (uint64_t)(bm / 2) * 8 >= (uint64_t)P.keys.size() * 32) bm /= 2;   // tables resident beats a sparser bitmap
+  H.tables_resident = (size_t)bm + tables <= opt.budget_bytes;
+  if (!H.tables_resident && !opt.bitmap_kb) bm = 128u * 1024u;
+  H.bm_bytes = bm; H.bm_mask = bm - 4; H.bloom2 = opt.bloom2 != 0;
+  H.image.assign(bm, 0);
+  for (uint32_t key : P.keys) {
+    const uint32_t h = key * kGramMult, addr = (uint32_t)(((uint64_t)key * kGramMult) >> 32) & H.bm_mask;
+    uint32_t wv; memcpy(&wv, H.image.data() + addr, 4);
+    wv |= (0x80000000u >> (h & 31u)) | (H.bloom2 ? (0x80000000u >> ((h >> 5) & 31u)) : 0u);
+    memcpy(H.image.data() + addr, &wv, 4);
+  }
+  if (H.tables_resident) {
+    auto append = [&](const void* p, size_t bytes, size_t pad) { uint32_t o = (uint32_t)H.image.size(); H.image.resize(a16(H.image.size() + bytes + pad), 0); if (bytes) memcpy(H.image.data() + o, p, bytes); return o; };
+    H.dir_off = append(H.bucket_start.data(), H.bucket_start.size() * 4, 0);
+    H.ent_off = append(H.entry_words.data(), H.entry_words.size() * 4, 0);
+    H.fac_off = append(H.factor_words.data(), H.factor_words.size() * 4, 64);
+    H.set_off = append(P.bytesets.data(), P.bytesets.size() * 4, 32);
+  }
   return true;
 }
 

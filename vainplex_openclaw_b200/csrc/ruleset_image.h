@@ -10,10 +10,14 @@ namespace cg {
 struct HostImage {
   std::vector<CompiledRule> rules;
   Prefilter pf;
-  std::vector<uint8_t> image;          // DFA modes: [rows 0..hot_states, row_stride bytes apart][lut 256]; mode 4: [lut 256][replicated buckets]
-  uint32_t hot_states = 0;             // rows resident in shared memory (row `hot_states` itself is the trap row)
-  uint32_t lut_off = 0, row_stride = 0;
-  size_t budget_bytes = 0; uint32_t image_cols = 0;   // what build_dfa_image() was given (kept for rebuilds)
+  // what the scan kernel stages into shared memory: [bitmap][bucket_start][entries][factor words][byte sets]
+  // (the level-1b tables only when they fit the budget: tables_resident)
+  std::vector<uint8_t> image;
+  uint32_t bm_bytes = 0, bm_mask = 0; bool bloom2 = false;
+  bool tables_resident = false;
+  uint32_t dir_off = 0, ent_off = 0, fac_off = 0, set_off = 0, nb_shift = 0, n_buckets = 0;
+  std::vector<uint32_t> bucket_start;  // n_buckets + 1
+  std::vector<uint32_t> entry_words;   // 2 words per level-1b entry, sorted by bucket: masked key, factor | (off + 3) << 20 | shape << 25
   std::vector<uint32_t> prog, prog_off, sets, first, alpha;
   std::vector<uint32_t> factor_words;  // 12 words per full factor (device layout)
   std::vector<uint16_t> ranges;
@@ -21,20 +25,16 @@ struct HostImage {
 };
 
 struct ImageOptions {
-  int mode = 2;                 // level-1 mode (0 direct7, 1 LUT, 2 folded 6-bit, 3 folded 5-bit DFA; 4 fingerprint table, falls back to 2)
-  size_t budget_bytes = 155 * 1024;   // shared-memory budget of the image (scan_kernel adds 64 KB of staging buffers; 227 KB per CTA)
-  int max_states = 16384;             // total states (cold rows are read from L2-resident HBM)
-  int max_classes = 64;
-  int max_window = kMaxWindow;
+  int stride = 0;                       // 0 = choose (rulec.h)
+  size_t budget_bytes = 216 * 1024;     // shared memory the image may take (scan_kernel adds 8 KB of rings; 227 KB per CTA)
+  uint32_t bitmap_kb = 0;               // 0 = sized from the number of keys (16 .. 128 KB)
+  int bloom2 = 0;                       // two bits per key in one bitmap word (costs three more ALU instructions per probe)
+  uint32_t max_keys = 24576;
 };
 
 struct RuleSrc { const char* src; uint32_t len; uint32_t flags; };
 
 // compiles every rule (failures stay in rules[i].status) and builds the prefilter + tables
 bool build_host_image(const RuleSrc* rules, uint32_t n, const ImageOptions& opt, HostImage* out, std::string* err);
-
-void build_dfa_image(HostImage* H);
-// profile-guided residency: most visited level-1 states first (see ruleset_image.cpp)
-void rank_states_by_visits(HostImage* H, const uint32_t* visits);
 
 }  // namespace cg

@@ -1,11 +1,10 @@
 // scan_kernels.cu -- sm_100a kernels of the message-scan hot path.
 //
-//   scan_kernel     every byte of every message through the level-1 prefilter DFA that lives in
-//                   shared memory (image staged with TMA bulk copies, completion on an mbarrier).
-//                   One lane owns one message; accepting transitions are compacted with warp
-//                   ballots into an event queue in HBM (one atomic per warp and word).
-//   confirm_kernel  level 2: one thread per level-1 event confirms the full factor exactly and
-//                   queues the surviving (message, rule) pairs (or records a direct hit).
+//   scan_kernel     every byte of the batch buffer through the gram filter: 4-byte grams folded, hashed and tested against
+//                   a bitmap in shared memory (image staged with TMA bulk copies, completion on an mbarrier); flagged
+//                   grams are compacted with warp ballots and confirmed exactly against the factor tables.
+//   resolve_kernel  level 2: message of every confirmed factor occurrence; queues (message, rule) pairs for the VM
+//                   (or records a direct hit).
 //   verify_kernel   exact ECMAScript semantics for the queued pairs: a Pike VM over UTF-16 units
 //                   decoded on the fly from the UTF-8 bytes (leftmost-first, global-exec
 //                   iteration of registry.ts:225-236, RegExp.test of context.ts:9-25).
@@ -16,7 +15,7 @@
 #include "kernels.h"
 #include "rulec.h"
 #include "pike_vm.h"
-#include "prefilter_dev.h"
+#include "gram_filter.h"
 #include <algorithm>
 
 namespace cg {
@@ -55,63 +54,113 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// level 1: prefilter scan.  lane-per-message (NS interleaved message streams per lane), streaming
-// 16-byte loads, table in shared memory
+// level 1: the gram filter.  Position-parallel: a lane owns 16 consecutive bytes of the batch buffer (LDG.128, the warp
+// reads 512 contiguous bytes), no per-message state, so long and ragged messages need no special handling.
+//   1a  every aligned 4-byte gram (stride 4) or every even-offset gram (stride 2) is folded SWAR-style, hashed with one
+//       IMAD and tested against the bitmap in shared memory (two bits of one word).  Result bits are funnel-shifted
+//       into a per-lane flag word; a warp ballot decides whether anything has to be looked at.
+//   1b  flagged grams are compacted (ballot + popc) into a per-warp ring in shared memory and drained 32 at a time,
+//       one per lane: level-1b table lookup and exact comparison of the factor (gram_filter.h).  Confirmed factor
+//       occurrences go to the queue in HBM, one atomic each (they are rare).
 // ------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 1024;      // 32 warps, one CTA per SM (768 threads next to a co-resident verify CTA was measured: scan 10% slower, no overlap gain)
-constexpr uint32_t kL1Always = 0xffffffffu;
-constexpr uint32_t kAccept = 0x8000u, kCold = 0x4000u, kStateMask = 0x3fffu;
+constexpr int kScanThreads = 1024;      // 32 warps, one CTA per SM
+constexpr uint32_t kRing = 64;          // flagged grams per warp waiting for the drain (a round adds <= 32, a drain leaves < 32)
+constexpr uint32_t kScanRingBytes = (kScanThreads / 32) * kRing * 4;
 
-// pre-doubled column indices of the four bytes of a word (one byte each), SWAR
-template <int MODE> __device__ __forceinline__ uint32_t cols2_of_word(uint32_t w);
-template <> __device__ __forceinline__ uint32_t cols2_of_word<0>(uint32_t w) { return (w + w) & 0xfefefefeu; }
-template <> __device__ __forceinline__ uint32_t cols2_of_word<2>(uint32_t w) { return ((w << 1) & 0x3e3e3e3eu) | (w & 0x40404040u); }
-template <> __device__ __forceinline__ uint32_t cols2_of_word<3>(uint32_t w) { return (w << 1) & 0x3e3e3e3eu; }
-template <> __device__ __forceinline__ uint32_t cols2_of_word<1>(uint32_t w) { return w; }   // LUT mode resolves per byte
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 
-// bytes between two rows of the shared-memory table: 2 * ncols + 4 (ruleset_image.cpp)
-template <int MODE> struct RowStride { static constexpr uint32_t v = (MODE == 0 ? 256u : MODE == 3 ? 64u : 128u) + 4u; };
+struct QueueEmit {
+  const ScanWork& w;
+  __device__ __forceinline__ void operator()(uint32_t t0, uint32_t f) {
+    const uint32_t k = atomicAdd(&w.counters[4], 1u);
+    if (k < w.l1_cap) { w.l1_pos[k] = t0; w.l1_fac[k] = f; } else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
+  }
+};
 
-// the complete table (deep states and accept flags included), L2-resident
-__device__ __forceinline__ uint32_t l1_full(const DevRuleset& rs, uint32_t state, uint32_t col) {
-  return __ldg(rs.table_full + ((size_t)state << rs.ncols_log2) + col);
+// The hot loop is bound by the integer ALU pipe (LOP3 / SHF / PRMT: 16 lanes per SM sub-partition and clock), not by
+// instruction issue: constants that would cost a second LOP3 as immediates sit in registers, and additions go through
+// IMAD (x * one + c, `one` a run-time 1 the compiler cannot fold) so that they execute on the FMA pipe instead.
+struct HotConst { uint32_t c5f, c10, one; };
+// z = (w & 0x5f5f5f5f) ^ 0x10101010 per byte (one LOP3); the gram key drops the low nibble of the digit bytes (z < 0x10)
+__device__ __forceinline__ uint32_t fold_z(uint32_t w, const HotConst& k) {
+  uint32_t z;
+  asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(z) : "r"(w), "r"(k.c5f), "r"(k.c10));
+  return z;
+}
+__device__ __forceinline__ uint32_t fold_key(uint32_t z, const HotConst& k) {
+  uint32_t y, keep, f;
+  asm("mad.lo.u32 %0, %1, %2, 0x70707070;" : "=r"(y) : "r"(z), "r"(k.one));
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(keep) : "r"(y));                                 // sign-replicate: 0xff for non-digit bytes
+  asm("lop3.b32 %0, %1, %2, 0xf0f0f0f0, 0xe0;" : "=r"(f) : "r"(z), "r"(keep));               // z & (keep | 0xf0f0f0f0)
+  return f;
+}
+// one probe of the bitmap: the word at hi32(key * M) & bm_mask, bit 31 - (h & 31) (and, BLOOM2, 31 - ((h >> 5) & 31)), h = lo32;
+// the answer is shifted into the low end of `flags`
+template <int BLOOM2>
+__device__ __forceinline__ void gram_probe(uint32_t bm, uint32_t bm_mask, uint32_t key, uint32_t& flags) {
+  const uint32_t h = key * kGramMult;
+  const uint32_t wv = lds_u32(bm + (__umulhi(key, kGramMult) & bm_mask));
+  uint32_t t = wv << (h & 31u);
+  if (BLOOM2) t &= wv << ((h >> 5) & 31u);
+  flags = __funnelshift_l(t, flags, 1);
+}
+// trigger bytes, compared in the folded domain (z): bit 7 of every byte of the result is CLEAR where z equals the splatted
+// folded trigger byte (z ^ splat <= 0x5f, so adding 0x7f carries into bit 7 exactly when the byte differs; no carry across bytes)
+__device__ __forceinline__ uint32_t differs(uint32_t z, uint32_t splat_z, uint32_t one) {
+  uint32_t y; const uint32_t e = z ^ splat_z;
+  asm("mad.lo.u32 %0, %1, %2, 0x7f7f7f7f;" : "=r"(y) : "r"(e), "r"(one));
+  return y;
 }
 
-__device__ __forceinline__ void l1_push_one(const ScanWork& w, uint32_t msg, uint32_t pos, uint32_t sc) {
-  uint32_t k = atomicAdd(&w.counters[4], 1u);
-  if (k < w.l1_cap) { w.l1_msg[k] = msg; w.l1_pos[k] = pos; w.l1_sc[k] = sc; } else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
+// what the rare paths need (kept out of line: the hot loop must stay small enough for the instruction cache)
+struct ScanCtx { GramTables T; const uint8_t* bytes; uint32_t begin, end; };
+
+// level 1b for up to 32 flagged grams of one warp's ring, one per lane.  `shift`: flagged gram = byte position >> shift.
+__device__ __forceinline__ void drain_ring(const DevRuleset& rs, const ScanWork& w, const ScanCtx& c, uint32_t ring, uint32_t head, uint32_t cnt, uint32_t shift) {
+  const uint32_t lane = threadIdx.x & 31u;
+  if (lane < cnt) {
+    const uint32_t pos = lds_u32(ring + (((head + lane) & (kRing - 1)) << 2)) << shift;
+    if (pos < c.end && !(rs.debug_flags & 1u)) {
+      const uint32_t* p4 = reinterpret_cast<const uint32_t*>(c.bytes + (pos & ~3u));
+      uint32_t g = __ldg(p4);
+      if (pos & 3u) g = __funnelshift_r(g, __ldg(p4 + 1), 8u * (pos & 3u));
+      QueueEmit emit{w};
+      gram_lookup(rs, c.T, gram_fold_word(g), c.bytes, c.begin, c.end, pos, emit);
+    }
+  }
+  __syncwarp();
 }
 
-// One level-1 transition out of the shared-memory table: entries are plain state indices, so the whole
-// step is  PRMT (column of byte k) ; IMAD (row * stride + column) ; LDS.U16.  Rows [0, hot) are real, row
-// `hot` is an absorbing trap row that every accepting transition and every transition into a non-resident
-// state leads to: the fast path never tests a flag, it only looks where it ended up after 16 bytes.
-template <int MODE>
-__device__ __forceinline__ uint32_t l1_step(const uint8_t* __restrict__ tbl, const uint8_t* __restrict__ lut, uint32_t stride, uint32_t state, uint32_t c2w, int k) {
-  uint32_t c2 = __byte_perm(c2w, 0, 0x4440 + k);
-  if (MODE == 1) c2 = 2u * lut[c2];
-  return *reinterpret_cast<const uint16_t*>(tbl + state * stride + c2);
+// trigger bytes inside one 16-byte chunk: bit 8k+7 of mk_j set = byte k of word j equals a trigger byte in the folded
+// domain (which merges case and bit 7), so every marked byte is compared again exactly
+__device__ __forceinline__ void trigger_chunk(const DevRuleset& rs, const ScanWork& w, const ScanCtx& c, uint32_t mk0, uint32_t mk1, uint32_t mk2, uint32_t mk3, uint32_t chunk) {
+  QueueEmit emit{w};
+#pragma unroll 1
+  for (uint32_t j = 0; j < 4; j++) {
+    uint32_t mk = j == 0 ? mk0 : j == 1 ? mk1 : j == 2 ? mk2 : mk3;
+    while (mk) {
+      const uint32_t bitpos = 31u - __clz(mk); mk &= ~(1u << bitpos);
+      const uint32_t pos = chunk * 16u + 4u * j + (bitpos >> 3);
+      if (pos < c.begin || pos >= c.end) continue;
+      const uint32_t by = c.bytes[pos];
+      for (uint32_t t = 0; t < rs.n_trig; t++) if (by == rs.trig_byte[t]) gram_trigger(rs, c.T, t, c.bytes, c.begin, c.end, pos, emit);
+    }
+  }
 }
 
-// Staging buffer of one warp: 64 bytes (four 16-byte units) of each of its 32 messages.  Unit u of message m
-// lives at m * 64 + ((u ^ ((m >> 1) & 3)) << 4): with that XOR both the loader's STS.128 (lane -> message
-// lane/4 + 8j, unit lane%4) and the walker's LDS.128 (lane -> its own message, unit cc) are bank-conflict free.
-constexpr uint32_t kStageBytesPerWarp = 32u * 64u;
-constexpr uint32_t kScanStageBytes = (kScanThreads / 32) * kStageBytesPerWarp;
-constexpr uint32_t kEvBuf = 16;                                 // events per warp buffered in shared memory (3 words each)
-constexpr uint32_t kScanEvBytes = (kScanThreads / 32) * kEvBuf * 12u;
-__device__ __forceinline__ uint32_t stage_off(uint32_t m, uint32_t u) { return m * 64u + ((u ^ ((m >> 1) & 3u)) << 4); }
+// An occurrence that starts less than three bytes into the scanned range has no gram in front of it: compared directly.
+__device__ __noinline__ void head_check(const DevRuleset& rs, const ScanWork& w, const ScanCtx& c) {
+  QueueEmit emit{w};
+  for (uint32_t i = threadIdx.x; i < 3u * rs.n_factors; i += kScanThreads) {
+    const uint32_t f = i / 3u, t0 = c.begin + i % 3u;
+    const uint32_t* fw = c.T.factors + (size_t)f * 12;
+    if (t0 < c.end && t0 + (fw[1] & 0xffu) <= c.end && factor_at(fw, c.T.bytesets, c.bytes + t0)) emit(t0, f);
+  }
+}
 
-// Lane-per-message walk, but the message bytes do not arrive lane-per-message: a lane reading 16 bytes of its
-// own message makes every LDG.128 touch 32 different 128-byte lines (32 L1 wavefronts per instruction, more
-// load/store-pipe time than the table walk itself).  Instead the warp fetches "group g" = 64 bytes of each of
-// its 32 messages with four LDG.128 whose lanes cover 8 messages x 64 contiguous bytes each (8 lines per
-// instruction, every 32-byte sector fully used), transposes through the staging buffer, and each lane then
-// pulls its own 16-byte chunks out of shared memory.  The loads of group g+1 are in flight while group g is
-// walked.
-template <int MODE>
+template <int NPROBE, int NTRIG, int BLOOM2>
 __global__ void __launch_bounds__(kScanThreads, 1)
-scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
+scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
             uint64_t* __restrict__ words) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -124,328 +173,93 @@ scan_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const 
       tma_bulk_g2s(smem + o, rs.image + o, len, &bar);
     }
   }
+  // while the image is in flight: result words start at zero (finalize_kernel fills in the messages that hit)
+  for (uint32_t i = blockIdx.x * kScanThreads + threadIdx.x; i < n; i += gridDim.x * kScanThreads) words[i] = 0ull;
+  ScanCtx ctx;
+  ctx.bytes = bytes; ctx.begin = off[0]; ctx.end = off[n];
+  const uint32_t begin = ctx.begin, end = ctx.end;
   mbar_wait(&bar, 0);
-  const uint8_t* tbl = smem;
-  const uint8_t* lut = smem + rs.lut_off;
-  const uint32_t hot = rs.hot_states;
-  const uint32_t stride = MODE == 1 ? rs.row_stride : RowStride<MODE>::v;     // compile-time constant except in LUT mode
-  const uint32_t FULL = 0xffffffffu;
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kScanThreads / 32;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  uint8_t* stage = smem + ((rs.image_bytes + 127u) & ~127u) + warp * kStageBytesPerWarp;
-  const uint32_t ld_unit = lane & 3u;                          // loader role: unit of the group this lane fetches
-  // Level-1 accept events are collected in a small per-warp buffer in shared memory and appended to the global
-  // queue kEvBuf at a time: one returning atomic (a ~1 us round trip to L2 that stalls the whole warp) per
-  // flush instead of one per flagged word.
-  uint32_t* evb = reinterpret_cast<uint32_t*>(smem + ((rs.image_bytes + 127u) & ~127u) + kScanStageBytes) + warp * (3u * kEvBuf);
-  uint32_t evn = 0;                                            // warp-uniform fill level
-  uint32_t slow_entries = 0;                                   // (same-address atomics from every slow-path entry would serialise in L2)
-  auto flush_events = [&]() {
-    if (evn == 0) return;
-    __syncwarp();
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&w.counters[4], evn);
-    base = __shfl_sync(FULL, base, 0);
-    if (base + evn > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
-    else if (lane < evn) { w.l1_msg[base + lane] = evb[3u * lane]; w.l1_pos[base + lane] = evb[3u * lane + 1]; w.l1_sc[base + lane] = evb[3u * lane + 2]; }
-    evn = 0;
-    __syncwarp();
+  const uint32_t lt = (1u << lane) - 1u, FULL = 0xffffffffu;
+  const uint32_t bm = smem_u32(smem), bm_mask = rs.bm_mask;
+  const uint32_t ring = smem_u32(smem + rs.image_bytes) + warp * (kRing * 4);
+  if (rs.tables_resident) {
+    ctx.T.bucket_start = reinterpret_cast<const uint32_t*>(smem + rs.dir_off); ctx.T.entries = reinterpret_cast<const uint2*>(smem + rs.ent_off);
+    ctx.T.factors = reinterpret_cast<const uint32_t*>(smem + rs.fac_off); ctx.T.bytesets = reinterpret_cast<const uint32_t*>(smem + rs.set_off);
+  } else { ctx.T.bucket_start = rs.bucket_start; ctx.T.entries = rs.entries; ctx.T.factors = rs.factors; ctx.T.bytesets = rs.bytesets; }
+  constexpr uint32_t kShift = NPROBE == 2 ? 1 : 2;             // flagged gram = its byte position >> kShift
+  HotConst hk; hk.c5f = rs.hot_c5f; hk.c10 = rs.hot_c10; hk.one = rs.hot_one;
+  uint32_t ring_n = 0, ring_head = 0, flagged_total = 0;
+  if (blockIdx.x == 0) head_check(rs, w, ctx);
+
+  const uint32_t first_chunk = begin >> 4, end_chunk = (end + 15u) >> 4;       // 16-byte chunks [first, end)
+  // folded (z domain) trigger bytes, splatted
+  const uint32_t splat0 = NTRIG > 0 ? (((rs.trig_byte[0] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u, splat1 = NTRIG > 1 ? (((rs.trig_byte[1] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u;
+  // this lane's chunk in the warp's current tile (32 chunks = 512 bytes); tiles are dealt round-robin to all warps of the grid
+  uint32_t c = first_chunk + (blockIdx.x * wpb + warp) * 32u + lane;
+  const uint32_t cstep = gridDim.x * wpb * 32u;
+
+  // two tiles in flight per warp beyond the one being scanned
+  auto load_chunk = [&](uint4& v, uint32_t& t, uint32_t cc) {
+    v = make_uint4(0, 0, 0, 0); t = 0;
+    if (cc < end_chunk) v = ldg_stream(bytes + (size_t)cc * 16);
+    if (NPROBE == 2 && lane == 31 && cc + 1 < end_chunk) t = __ldg(reinterpret_cast<const uint32_t*>(bytes + (size_t)(cc + 1) * 16));
   };
-  // units: one per message, or (segmented scans) kSegBytes-sized pieces of long messages.  A piece other than the
-  // first starts kSegWarm bytes early in state 0 and reports nothing before its own first byte: the level-1 automaton
-  // is definite (its state depends on the last kMaxWindow - 1 bytes only), so by then it is in the true state.
-  const bool segmented = w.units != nullptr && !(w.counters[3] & ERR_UNIT_OVERFLOW);
-  const uint32_t n_units = segmented ? min(w.counters[16], w.unit_cap) : n;
-  const uint32_t ntiles = (n_units + 31u) / 32u;
-  for (uint32_t tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
-    const uint32_t unit = tile * 32u + lane;
-    const bool valid = unit < n_units;
-    uint32_t msg = unit, seg = 0;
-    if (segmented && valid) { const uint2 un = w.units[unit]; msg = un.x; seg = un.y; }
-    const uint32_t mb = valid ? off[msg] : 0u, me = valid ? off[msg + 1] : 0u;      // the message; p - mb = event position
-    const uint32_t lo = seg * kSegBytes;                                            // first position this unit reports
-    const uint32_t b = seg ? mb + lo - kSegWarm : mb;                               // first byte walked
-    const uint32_t e = segmented ? min(me, mb + lo + kSegBytes) : me;
-    if (valid && rs.n_always && lo == 0) l1_push_one(w, msg, 0, kL1Always);
-    uint32_t state = 0, p = b;
-    // unaligned head: byte-wise on the full table
-    uint32_t head_end = (b + 15u) & ~15u; if (head_end > e) head_end = e;
-    for (; p < head_end; p++) {
-      uint32_t col = l1_col(rs.mode, lut, bytes[p]);
-      uint32_t ent = l1_full(rs, state, col);
-      if ((ent & kAccept) && p - mb >= lo) l1_push_one(w, msg, p - mb, (state << 8) | col);
-      state = ent & kStateMask;
-    }
-    const uint32_t nch = (e - p) >> 4;
-    uint32_t maxch = nch;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) maxch = max(maxch, __shfl_xor_sync(FULL, maxch, d));
-    const uint32_t ngroups = (maxch + 3u) >> 2;
-
-    // loader role: this lane fetches unit ld_unit of messages (lane / 4) + 8 j, j = 0..3 (their chunk base and
-    // count come by shuffle each time: eight registers less than keeping them)
-    const uint32_t p0 = p;
-    uint4 r[4];
-    auto load_group = [&](uint32_t g) {
-      const uint32_t cidx = 4u * g + ld_unit;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t lp = __shfl_sync(FULL, p0, (lane >> 2) + 8 * j), ln = __shfl_sync(FULL, nch, (lane >> 2) + 8 * j);
-        r[j] = make_uint4(0, 0, 0, 0);
-        if (cidx < ln) r[j] = ldg_stream(bytes + lp + 16u * cidx);
-      }
-    };
-    auto store_group = [&]() {
-#pragma unroll
-      for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(stage + stage_off((lane >> 2) + 8 * j, ld_unit)) = r[j];
-    };
-    if (ngroups) { load_group(0); __syncwarp(); store_group(); __syncwarp(); if (ngroups > 1) load_group(1); }
-    for (uint32_t g = 0; g < ngroups; g++) {
+  uint4 b0, b1; uint32_t t0, t1;
+  load_chunk(b0, t0, c); load_chunk(b1, t1, c + cstep);
 #pragma unroll 1
-      for (uint32_t cc = 0; cc < 4; cc++) {
-        const bool act = 4u * g + cc < nch;
-        const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(lane, cc));
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const uint32_t c2 = cols2_of_word<MODE>(q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w);
-          uint32_t fs = min(state, hot);                     // a non-resident state at word start: straight into the trap row
-#pragma unroll
-          for (int k = 0; k < 4; k++) fs = l1_step<MODE>(tbl, lut, stride, fs, c2, k);
-          const bool flagged = act && fs == hot;
-          const uint32_t fl = __ballot_sync(FULL, flagged);
-          if (fl == 0) { if (act) state = fs; continue; }
-          // rare: an accepting transition or an excursion into non-resident states somewhere in this word.
-          // Flagged lanes re-walk the four bytes from the word's start state: resident transitions from shared
-          // memory, trapped ones from the full table in L2 (accept flag + true successor).
-          if (rs.debug_flags & 1u) continue;
-          slow_entries++;                                    // folded into counters[6] once per warp
-          uint32_t cnt = 0, ev_pos[4], ev_sc[4];
-          if (flagged) {
-            uint32_t st = state;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              uint32_t c2k = __byte_perm(c2, 0, 0x4440 + k);
-              if (MODE == 1) c2k = 2u * lut[c2k];
-              uint32_t nx = hot;
-              if (st < hot) nx = *reinterpret_cast<const uint16_t*>(tbl + st * stride + c2k);
-              if (nx == hot) {
-                const uint32_t ent = l1_full(rs, st, c2k >> 1);
-                if ((ent & kAccept) && p + 4 * q + k - mb >= lo) {
-#pragma unroll
-                  for (int j = 0; j <= k; j++) if (cnt == (uint32_t)j) { ev_pos[j] = p + 4 * q + k - mb; ev_sc[j] = (st << 8) | (c2k >> 1); }
-                  cnt++;
-                }
-                nx = ent & kStateMask;
-              }
-              st = nx;
-            }
-            state = st;                                      // the true state (may be a non-resident one)
-          } else if (act) state = fs;
-          uint32_t idx = 0, total = 0;
-#pragma unroll
-          for (uint32_t j = 1; j <= 4; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
-          if (total) {
-            if (evn + total > kEvBuf) flush_events();
-            if (total > kEvBuf) {                              // more events in one word than the buffer holds: straight to the queue
-              uint32_t base = 0;
-              if (lane == 0) base = atomicAdd(&w.counters[4], total);
-              base = __shfl_sync(FULL, base, 0);
-              if (base + total > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
-              else {
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t k2 = base + idx + j; w.l1_msg[k2] = msg; w.l1_pos[k2] = ev_pos[j]; w.l1_sc[k2] = ev_sc[j]; }
-              }
-            } else {
-#pragma unroll
-              for (uint32_t j = 0; j < 4; j++) if (j < cnt) { uint32_t* d = evb + 3u * (evn + idx + j); d[0] = msg; d[1] = ev_pos[j]; d[2] = ev_sc[j]; }
-              evn += total;
-            }
-          }
+  while (c - lane < end_chunk) {
+    const uint4 cur = b0; const uint32_t ct = t0;
+    b0 = b1; t0 = t1;
+    load_chunk(b1, t1, c + 2u * cstep);
+    const uint32_t z0 = fold_z(cur.x, hk), z1 = fold_z(cur.y, hk), z2 = fold_z(cur.z, hk), z3 = fold_z(cur.w, hk);
+    const uint32_t f0 = fold_key(z0, hk), f1 = fold_key(z1, hk), f2 = fold_key(z2, hk), f3 = fold_key(z3, hk);
+    uint32_t flags = 0;
+    if (NPROBE == 2) {
+      uint32_t w4 = __shfl_down_sync(FULL, cur.x, 1); if (lane == 31) w4 = ct;
+      const uint32_t f4 = fold_key(fold_z(w4, hk), hk);
+      gram_probe<BLOOM2>(bm, bm_mask, f0, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f0, f1, 16), flags);
+      gram_probe<BLOOM2>(bm, bm_mask, f1, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f1, f2, 16), flags);
+      gram_probe<BLOOM2>(bm, bm_mask, f2, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f2, f3, 16), flags);
+      gram_probe<BLOOM2>(bm, bm_mask, f3, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f3, f4, 16), flags);
+    } else {
+      gram_probe<BLOOM2>(bm, bm_mask, f0, flags); gram_probe<BLOOM2>(bm, bm_mask, f1, flags);
+      gram_probe<BLOOM2>(bm, bm_mask, f2, flags); gram_probe<BLOOM2>(bm, bm_mask, f3, flags);
+    }
+    // triggers: d_j has bit 7 of a byte clear where it equals a trigger byte (folded domain)
+    uint32_t d0 = 0x80808080u, d1 = 0x80808080u, d2 = 0x80808080u, d3 = 0x80808080u;
+    if (NTRIG > 0) { d0 = differs(z0, splat0, hk.one); d1 = differs(z1, splat0, hk.one); d2 = differs(z2, splat0, hk.one); d3 = differs(z3, splat0, hk.one); }
+    if (NTRIG > 1) { d0 &= differs(z0, splat1, hk.one); d1 &= differs(z1, splat1, hk.one); d2 &= differs(z2, splat1, hk.one); d3 &= differs(z3, splat1, hk.one); }
+    bool trig = NTRIG > 0 && ((d0 & d1 & d2 & d3 & 0x80808080u) != 0x80808080u);
+    if (c >= end_chunk) { flags = 0; trig = false; }
+    if (__any_sync(FULL, flags != 0 || trig)) {
+      // rare from here on.  flags: bit (4 * NPROBE - 1 - j) = probe j of the lane's chunk; flagged grams are compacted into the warp's ring
+      if (NTRIG > 0 && trig) trigger_chunk(rs, w, ctx, ~d0 & 0x80808080u, ~d1 & 0x80808080u, ~d2 & 0x80808080u, ~d3 & 0x80808080u, c);
+      __syncwarp();
+      const uint32_t base = c * (4u * NPROBE);
+      while (__any_sync(FULL, flags != 0)) {
+        const bool has = flags != 0;
+        const uint32_t m = __ballot_sync(FULL, has);
+        if (has) {
+          const uint32_t bit = 31u - __clz(flags);
+          flags &= ~(1u << bit);
+          const uint32_t slot = (ring_head + ring_n + __popc(m & lt)) & (kRing - 1);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring + slot * 4), "r"(base + (4u * NPROBE - 1u - bit)) : "memory");
         }
-        if (act) p += 16;
-      }
-      if (g + 1 < ngroups) {
-        __syncwarp(); store_group(); __syncwarp();
-        if (g + 2 < ngroups) load_group(g + 2);
+        ring_n += __popc(m); flagged_total += __popc(m);
+        if (ring_n >= 32) { __syncwarp(); drain_ring(rs, w, ctx, ring, ring_head, 32, kShift); ring_head += 32; ring_n -= 32; }
       }
     }
-    // tail
-    for (; p < e; p++) {
-      uint32_t col = l1_col(rs.mode, lut, bytes[p]);
-      uint32_t ent = l1_full(rs, state, col);
-      if ((ent & kAccept) && p - mb >= lo) l1_push_one(w, msg, p - mb, (state << 8) | col);
-      state = ent & kStateMask;
-    }
-    if (valid && lo == 0) words[msg] = 0ull;
+    c += cstep;
   }
-  flush_events();
-  if (lane == 0 && slow_entries) atomicAdd(&w.counters[6], slow_entries);
+  __syncwarp();
+  if (ring_n) drain_ring(rs, w, ctx, ring, ring_head, ring_n, kShift);
+  if (lane == 0 && flagged_total) atomicAdd(&w.counters[6], flagged_total);
 }
 
 // ------------------------------------------------------------------------------------------
-// level 1, mode 4: stateless fingerprint probe.  Every byte position hashes the last four symbols
-// (fold6 + digit collapse, SWAR) and reads ONE word from the lane's own bank of the replicated table
-// -- conflict-free by construction -- and compares two 16-bit fingerprints.  Up to two single-byte
-// triggers (e.g. '@') are matched SWAR-style in registers.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fp_fold_word(uint32_t w) {
-  uint32_t f = (w & 0x1f1f1f1fu) | ((w >> 1) & 0x20202020u);
-  uint32_t t = (f >> 4) & ~(f >> 5) & 0x01010101u;        // digit columns 0x10..0x19 -> 0x10 / 0x18
-  return f & ~(t * 7u);
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
-__device__ __forceinline__ uint32_t fp_probe(uint32_t tabs, uint32_t buckets, uint32_t mult, uint32_t win) {
-  uint32_t h = win * mult;
-  uint32_t x = lds_u32(tabs + (__umulhi(h, buckets) << 7)) ^ __byte_perm(h, 0, 0x2121);        // fingerprint = bits 8..23 of h, in both halves
-  return (x - 0x00010001u) & ~x & 0x80008000u;              // non-zero <=> one half equals the fingerprint
-}
-__device__ __forceinline__ uint32_t has_byte(uint32_t w, uint32_t splat) { uint32_t x = w ^ splat; return (x - 0x01010101u) & ~x & 0x80808080u; }
-
-__global__ void __launch_bounds__(kScanThreads, 1)
-scan_fp_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
-               uint64_t* __restrict__ words) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, rs.image_bytes);
-    for (uint32_t o = 0; o < rs.image_bytes; o += 32768u) {
-      uint32_t len = rs.image_bytes - o < 32768u ? rs.image_bytes - o : 32768u;
-      tma_bulk_g2s(smem + o, rs.image + o, len, &bar);
-    }
-  }
-  mbar_wait(&bar, 0);
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kScanThreads / 32;
-  const uint32_t tabs = smem_u32(smem) + 256u + lane * 4u;      // this lane's bank
-  const uint32_t B = rs.fp_buckets, mult = rs.fp_mult, ntrig = rs.n_trig;
-  const uint32_t sp0 = rs.trig_byte[0] * 0x01010101u, sp1 = rs.trig_byte[1] * 0x01010101u;
-  const uint32_t FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
-  const uint32_t ntiles = (n + 31) / 32;
-  for (uint32_t tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
-    const uint32_t msg = tile * 32 + lane;
-    const bool valid = msg < n;
-    const uint32_t b = valid ? off[msg] : 0u, e = valid ? off[msg + 1] : 0u;
-    if (valid && rs.n_always) l1_push_one(w, msg, 0, kL1Always);
-    uint32_t p = b, win = 0;                                 // win: last four symbols, oldest in the low byte
-    auto bytewise = [&](uint32_t upto) {
-      for (; p < upto; p++) {
-        const uint32_t byte = bytes[p];
-        win = (win >> 8) | (fp_fold_word(byte) << 24);
-        if (fp_probe(tabs, B, mult, win)) l1_push_one(w, msg, p - b, win * mult);
-        for (uint32_t t = 0; t < ntrig; t++) if (byte == rs.trig_byte[t]) l1_push_one(w, msg, (p - b) | 0x80000000u, t);
-      }
-    };
-    uint32_t head_end = (b + 15u) & ~15u; if (head_end > e) head_end = e;
-    bytewise(head_end);
-    uint32_t nch = (e - p) >> 4, maxch = nch;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) maxch = max(maxch, __shfl_xor_sync(FULL, maxch, d));
-    constexpr int kPrefetch = 3;
-    uint4 buf[kPrefetch];
-#pragma unroll
-    for (int d = 0; d < kPrefetch; d++) { buf[d] = make_uint4(0, 0, 0, 0); if ((uint32_t)d < nch) buf[d] = ldg_stream(bytes + p + 16 * d); }
-    for (uint32_t c = 0; c < maxch; c++) {
-      const bool act = c < nch;
-      const uint4 v = buf[0];
-#pragma unroll
-      for (int d = 0; d + 1 < kPrefetch; d++) buf[d] = buf[d + 1];
-      buf[kPrefetch - 1] = make_uint4(0, 0, 0, 0);
-      if (c + kPrefetch < nch) buf[kPrefetch - 1] = ldg_stream(bytes + p + 16 * kPrefetch);
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const uint32_t wd = q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w;
-        const uint32_t P = win, F = fp_fold_word(wd);
-        uint32_t acc = fp_probe(tabs, B, mult, __funnelshift_r(P, F, 8)) | fp_probe(tabs, B, mult, __funnelshift_r(P, F, 16)) |
-                       fp_probe(tabs, B, mult, __funnelshift_r(P, F, 24)) | fp_probe(tabs, B, mult, F);
-        if (ntrig) { acc |= has_byte(wd, sp0); if (ntrig > 1) acc |= has_byte(wd, sp1); }
-        const bool flagged = act && acc != 0;
-        if (act) win = F;
-        if (__ballot_sync(FULL, flagged)) {
-          uint32_t cnt = 0, ev_pos[6], ev_sc[6];
-          if (flagged) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const uint32_t wk = k == 3 ? F : __funnelshift_r(P, F, 8 * (k + 1));
-              const uint32_t pos = p + 4 * q + k - b;
-              if (fp_probe(tabs, B, mult, wk) && cnt < 6) { ev_pos[cnt] = pos; ev_sc[cnt] = wk * mult; cnt++; }
-              const uint32_t byte = (wd >> (8 * k)) & 0xffu;
-              for (uint32_t t = 0; t < ntrig; t++) if (byte == rs.trig_byte[t] && cnt < 6) { ev_pos[cnt] = pos | 0x80000000u; ev_sc[cnt] = t; cnt++; }
-            }
-          }
-          uint32_t idx = 0, total = 0;
-#pragma unroll
-          for (uint32_t j = 1; j <= 6; j++) { uint32_t bj = __ballot_sync(FULL, cnt >= j); idx += __popc(bj & lt_mask); total += __popc(bj); }
-          if (total) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&w.counters[4], total);
-            base = __shfl_sync(FULL, base, 0);
-            if (base + total > w.l1_cap) { if (lane == 0) atomicOr(&w.counters[3], ERR_L1_OVERFLOW); }
-            else {
-#pragma unroll
-              for (uint32_t j = 0; j < 6; j++) if (j < cnt) { uint32_t k2 = base + idx + j; w.l1_msg[k2] = msg; w.l1_pos[k2] = ev_pos[j]; w.l1_sc[k2] = ev_sc[j]; }
-            }
-          }
-        }
-      }
-      if (act) p += 16;
-    }
-    bytewise(e);
-    if (valid) words[msg] = 0ull;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// segmented scans: the unit table.  A message of len bytes becomes max(1, ceil(len / kSegBytes)) units; slots are
-// reserved with one atomic per warp (the order of units does not matter).  counters[16] = units needed; if that
-// exceeds unit_cap the scan falls back to one unit per message (ERR_UNIT_OVERFLOW) and the host grows the table.
-// ------------------------------------------------------------------------------------------
-__global__ void plan_units_kernel(ScanWork w, const uint32_t* __restrict__ off, uint32_t n) {
-  const uint32_t FULL = 0xffffffffu, lane = threadIdx.x & 31u;
-  for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
-    const uint32_t msg = i0 + threadIdx.x;
-    uint32_t k = 0;
-    if (msg < n) { const uint32_t len = off[msg + 1] - off[msg]; k = len <= kSegBytes ? 1u : (len + kSegBytes - 1u) / kSegBytes; }
-    uint32_t incl = k;                                      // inclusive warp prefix sum
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    uint32_t base = 0;
-    if (lane == 0 && total) base = atomicAdd(&w.counters[16], total);
-    base = __shfl_sync(FULL, base, 0) + incl - k;
-    if (base + k > w.unit_cap) { if (k) atomicOr(&w.counters[3], ERR_UNIT_OVERFLOW); }
-    else for (uint32_t j = 0; j < k; j++) w.units[base + j] = make_uint2(msg, j);
-  }
-}
-__global__ void max_len_kernel(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ out) {
-  uint32_t m = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, off[i + 1] - off[i]);
-#pragma unroll
-  for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
-}
-
-// ------------------------------------------------------------------------------------------
-// profile-guided residency: how often is each level-1 state visited on a sample of the traffic?
-// One thread per sampled message walks the full table (L2) and counts; run once per rule set (and on request),
-// the host then renumbers the states so the most visited ones are the shared-memory resident ones.
-// ------------------------------------------------------------------------------------------
-__global__ void l1_profile_kernel(DevRuleset rs, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
-                                  uint32_t n_sample, uint32_t* __restrict__ visits) {
-  const uint8_t* lut = rs.image + rs.lut_off;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_sample; i += gridDim.x * blockDim.x) {
-    const uint32_t msg = (uint32_t)(((uint64_t)i * n) / n_sample);
-    uint32_t state = 0;
-    for (uint32_t p = off[msg], e = off[msg + 1]; p < e; p++) {
-      atomicAdd(&visits[state], 1u);
-      state = l1_full(rs, state, l1_col(rs.mode, lut, bytes[p])) & kStateMask;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// level 2: confirm the full factor for every level-1 event; queue survivors for the VM
+// level 2: which message does every confirmed factor occurrence belong to?  Slots, candidates for the VM, direct hits.
 // ------------------------------------------------------------------------------------------
 struct SlotSink {
   const DevRuleset& rs; const ScanWork& w; uint32_t msg; uint32_t slot;
@@ -501,17 +315,19 @@ struct SlotSink {
 };
 
 __global__ void __launch_bounds__(256)
-confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, int want_spans) {
+resolve_kernel(DevRuleset rs, ScanWork w, const uint32_t* __restrict__ off, uint32_t n, int want_spans) {
   const uint32_t n1 = min(w.counters[4], w.l1_cap);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
-    const uint32_t msg = w.l1_msg[i], pos = w.l1_pos[i], sc = w.l1_sc[i];
+  const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t i = tid; i < n1; i += stride) {
+    const uint32_t pos = w.l1_pos[i], f = w.l1_fac[i];
+    const uint32_t msg = message_of(off, n, pos);
+    if (pos + (rs.factors[(size_t)f * 12 + 1] & 0xffu) > off[msg + 1]) continue;     // straddles two messages: not an occurrence
     SlotSink sink(rs, w, msg, want_spans != 0);
-    if (sc == kL1Always) { for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate_always(rs.always_rules[k]); continue; }
-    const uint32_t b = off[msg], len = off[msg + 1] - b;
-    if (rs.mode == 4) {
-      if (pos & 0x80000000u) accept_id(rs, rs.trig_acc[sc & 1u], bytes + b, len, pos & 0x7fffffffu, want_spans != 0, sink);
-      else fp_accept(rs, sc, bytes + b, len, pos, want_spans != 0, sink);
-    } else l1_accept(rs, sc >> 8, sc & 0xffu, bytes + b, len, pos, want_spans != 0, sink);
+    factor_confirmed(rs, f, pos - off[msg], want_spans != 0, sink);
+  }
+  if (rs.n_always) for (uint32_t msg = tid; msg < n; msg += stride) {
+    SlotSink sink(rs, w, msg, want_spans != 0);
+    for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate_always(rs.always_rules[k]);
   }
 }
 
@@ -636,7 +452,13 @@ verify_large_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
   if (vm.err) atomicOr(&w.counters[3], vm.err);
 }
 
-__global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict__ words) {
+__global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict__ words, uint32_t n) {
+  // A step whose queues overflowed or whose VM ran out of space has incomplete results: every word of the batch says so
+  // (in-band, so that a caller of the asynchronous device path cannot mistake them for "no hit").
+  if (w.counters[3]) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) words[i] = kWordIncomplete;
+    return;
+  }
   const uint32_t n_slots = min(w.counters[0], w.slot_cap);
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
     const uint32_t msg = w.slot_msg[s];
@@ -678,53 +500,33 @@ __global__ void verdict_kernel(DevRuleset rs, ScanWork w, uint32_t* __restrict__
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+#define CG_FOR_SCAN_VARIANTS(X) X(1, 0, 1) X(1, 1, 1) X(1, 2, 1) X(2, 0, 1) X(2, 1, 1) X(2, 2, 1) X(1, 0, 0) X(1, 1, 0) X(1, 2, 0) X(2, 0, 0) X(2, 1, 0) X(2, 2, 0)
 void prepare_scan_kernels() {
   int dev = 0, optin = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int kMaxSmem = (optin > 0 ? optin : 227 * 1024) - 1024;     // leave room for the kernels' static shared memory
-#define CG_PREP(M) cudaFuncSetAttribute(scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
-  CG_PREP(0); CG_PREP(1); CG_PREP(2); CG_PREP(3);
+#define CG_PREP(P, T, B) cudaFuncSetAttribute(scan_kernel<P, T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  CG_FOR_SCAN_VARIANTS(CG_PREP)
 #undef CG_PREP
-  cudaFuncSetAttribute(scan_fp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(verify_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
   cudaFuncSetAttribute(verify_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
 }
 
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
-                uint64_t* d_words, bool want_spans, int sm_count, cudaStream_t stream) {
-  (void)want_spans;
+                uint64_t* d_words, int sm_count, cudaStream_t stream) {
   if (n == 0) return 0;
-  size_t smem = rs.image_bytes;
-  uint32_t ntiles = (n + 31) / 32, wpb = kScanThreads / 32;
-  uint32_t grid = (ntiles + wpb - 1) / wpb; if (grid > (uint32_t)sm_count || w.units) grid = sm_count;      // segmented: unit count is only known on the device
-  if (rs.mode == 4) { scan_fp_kernel<<<std::min<uint32_t>((n + 32 * wpb - 1) / (32 * wpb), (uint32_t)sm_count), kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); return 1; }
-  smem = ((smem + 127) & ~(size_t)127) + kScanStageBytes + kScanEvBytes;      // image + per warp: 2 KB staging buffer, event buffer
-#define CG_LAUNCH_SCAN(M) scan_kernel<M><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words)
-  switch (rs.mode) { case 0: CG_LAUNCH_SCAN(0); break; case 2: CG_LAUNCH_SCAN(2); break; case 3: CG_LAUNCH_SCAN(3); break; default: CG_LAUNCH_SCAN(1); break; }
-#undef CG_LAUNCH_SCAN
+  const size_t smem = (size_t)rs.image_bytes + kScanRingBytes;
+  // the scanned range is only known on the device (off[0] .. off[n]); a warp tile is 512 bytes, messages are rarely shorter than 16
+  uint32_t grid = (uint32_t)sm_count;
+  if (n < 4096) grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, n / 32u + 1u));         // tiny batches: fewer image loads
+  const int np = rs.stride == 2 ? 2 : 1, nt = (int)rs.n_trig, bl = rs.bloom2 ? 1 : 0;
+#define CG_LAUNCH(P, T, B) if (np == P && nt == T && bl == B) scan_kernel<P, T, B><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words);
+  CG_FOR_SCAN_VARIANTS(CG_LAUNCH)
+#undef CG_LAUNCH
   return 1;
 }
 
-int launch_plan_units(const ScanWork& w, const uint32_t* d_off, uint32_t n, cudaStream_t stream) {
-  if (!n || !w.units) return 0;
-  plan_units_kernel<<<std::min<uint32_t>((n + 255) / 256, 1184u), 256, 0, stream>>>(w, d_off, n);
-  return 1;
-}
-int launch_max_len(const uint32_t* d_off, uint32_t n, uint32_t* d_out_max, cudaStream_t stream) {
-  if (!n) return 0;
-  max_len_kernel<<<std::min<uint32_t>((n + 255) / 256, 1184u), 256, 0, stream>>>(d_off, n, d_out_max);
-  return 1;
-}
-
-int launch_l1_profile(const DevRuleset& rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint32_t n_sample,
-                      uint32_t* d_visits, cudaStream_t stream) {
-  if (!n || !n_sample) return 0;
-  l1_profile_kernel<<<(n_sample + 127) / 128, 128, 0, stream>>>(rs, d_bytes, d_off, n, n_sample, d_visits);
-  return 1;
-}
-
-int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
-                   bool want_spans, int sm_count, cudaStream_t stream) {
-  confirm_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_bytes, d_off, want_spans ? 1 : 0);
+int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
+  resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_off, n, want_spans ? 1 : 0);
   return 1;
 }
 
@@ -749,8 +551,8 @@ int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdict
   return 1;
 }
 
-int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, int sm_count, cudaStream_t stream) {
-  finalize_kernel<<<sm_count * 2, 256, 0, stream>>>(rs, w, d_words);
+int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, uint32_t n, int sm_count, cudaStream_t stream) {
+  finalize_kernel<<<sm_count * 2, 256, 0, stream>>>(rs, w, d_words, n);
   return 1;
 }
 
