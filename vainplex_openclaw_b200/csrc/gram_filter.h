@@ -27,10 +27,10 @@ CG_HD uint32_t gram_fold_word(uint32_t w) {
   return z & (keep | 0xf0f0f0f0u);
 }
 
-// Bitmap geometry: p = key * kGramMult as a 64-bit product; word at byte address (p >> 32) & bm_mask (bm_mask = bitmap
-// bytes - 4: the high half is one IMAD.HI on the device, no shift), bit 31 - (p & 31) and, for the optional second
-// Bloom bit in the same word, bit 31 - ((p >> 5) & 31).
-CG_HD uint32_t gram_bitmap_addr(uint32_t key, uint32_t bm_mask) { return (uint32_t)(((uint64_t)key * kGramMult) >> 32) & bm_mask; }
+// Bitmap geometry: h = key * kGramMult; word index = the top log2(words) bits of h (on the device hi32(h * words), one
+// IMAD.HI), bit 31 - (h & 31) and, for the optional second Bloom bit in the same word, bit 31 - ((h >> 5) & 31).
+// bm_mask = bitmap bytes - 4 (bitmap bytes a power of two).
+CG_HD uint32_t gram_bitmap_addr(uint32_t key, uint32_t bm_mask) { return (uint32_t)(((uint64_t)(key * kGramMult) * ((bm_mask >> 2) + 1u)) >> 32) << 2; }
 CG_HD uint32_t gram_bitmap_bits(uint32_t key, bool bloom2) {
   const uint32_t h = key * kGramMult;
   return (0x80000000u >> (h & 31u)) | (bloom2 ? (0x80000000u >> ((h >> 5) & 31u)) : 0u);
@@ -83,21 +83,45 @@ CG_HD bool factor_at_gram(const uint32_t* __restrict__ fw, const uint32_t* __res
 // A flagged gram: `key` = folded four bytes at buffer position `pos`.  Every registered (factor, gram offset) whose
 // masked key equals the gram is compared exactly; emit(t0, factor) for each factor that really starts at t0, with
 // [t0, t0 + len) inside [begin, end).
+// Shaped for a draining warp (one flagged gram per lane): the walk over the shapes is uniform and loop-free per bucket
+// (its first two entries), matches are only COLLECTED there; the factor comparison then runs once for every lane's first
+// match and once more for second matches (guarded by warp votes on the device).  Buckets longer than two entries and
+// third matches take the plain loop at the end.
+template <class Emit>
+CG_HD void gram_entry_check(const GramTables& T, uint32_t y, const uint8_t* __restrict__ buf, uint32_t begin, uint32_t end, uint32_t pos, Emit& emit) {
+  const uint32_t f = y & 0xfffffu;
+  const int goff = (int)((y >> 20) & 31u) - 3;
+  const int64_t t0 = (int64_t)pos - goff;
+  const uint32_t* fw = T.factors + (size_t)f * 12;
+  if (t0 >= (int64_t)begin && t0 + (int64_t)(fw[1] & 0xffu) <= (int64_t)end && factor_at_gram(fw, T.bytesets, buf + t0, goff)) emit((uint32_t)t0, f);
+}
 template <class Emit>
 CG_HD void gram_lookup(const DevRuleset& rs, const GramTables& T, uint32_t key, const uint8_t* __restrict__ buf, uint32_t begin, uint32_t end,
-                       uint32_t pos, Emit& emit) {
+                       uint32_t pos, Emit& emit, bool active = true) {
+  uint32_t ya = 0, yb = 0, nmatch = 0; bool spill = false;          // first two matches; spill: this lane has to take the plain loop
   for (uint32_t s = 0; s < rs.n_shapes; s++) {
+    const uint32_t km = key & rs.shapes[s];
+    const uint32_t b = gram_bucket(km, s, rs.nb_shift);
+    const uint32_t e0 = T.bucket_start[b], e1 = active ? T.bucket_start[b + 1] : e0;
+    if (e0 < e1) { const uint2 en = T.entries[e0]; if (en.x == km && (en.y >> 25) == s) { if (nmatch == 0) ya = en.y; else if (nmatch == 1) yb = en.y; nmatch++; } }
+    if (e0 + 1 < e1) { const uint2 en = T.entries[e0 + 1]; if (en.x == km && (en.y >> 25) == s) { if (nmatch == 0) ya = en.y; else if (nmatch == 1) yb = en.y; nmatch++; } }
+    spill = spill || e1 - e0 > 2;
+  }
+  spill = spill || nmatch > 2;
+#ifdef __CUDA_ARCH__
+  if (__any_sync(0xffffffffu, nmatch >= 1 && !spill)) { if (nmatch >= 1 && !spill) gram_entry_check(T, ya, buf, begin, end, pos, emit); }
+  if (__any_sync(0xffffffffu, nmatch >= 2 && !spill)) { if (nmatch >= 2 && !spill) gram_entry_check(T, yb, buf, begin, end, pos, emit); }
+  if (!__any_sync(0xffffffffu, spill)) return;
+#else
+  if (nmatch >= 1 && !spill) gram_entry_check(T, ya, buf, begin, end, pos, emit);
+  if (nmatch >= 2 && !spill) gram_entry_check(T, yb, buf, begin, end, pos, emit);
+#endif
+  if (spill) for (uint32_t s = 0; s < rs.n_shapes; s++) {       // rare: every entry of every bucket
     const uint32_t km = key & rs.shapes[s];
     const uint32_t b = gram_bucket(km, s, rs.nb_shift);
     for (uint32_t e = T.bucket_start[b], e1 = T.bucket_start[b + 1]; e < e1; e++) {
       const uint2 en = T.entries[e];
-      if (en.x != km || (en.y >> 25) != s) continue;
-      const uint32_t f = en.y & 0xfffffu;
-      const int goff = (int)((en.y >> 20) & 31u) - 3;
-      const int64_t t0 = (int64_t)pos - goff;
-      const uint32_t* fw = T.factors + (size_t)f * 12;
-      if (t0 < (int64_t)begin || t0 + (int64_t)(fw[1] & 0xffu) > (int64_t)end) continue;
-      if (factor_at_gram(fw, T.bytesets, buf + t0, goff)) emit((uint32_t)t0, f);
+      if (en.x == km && (en.y >> 25) == s) gram_entry_check(T, en.y, buf, begin, end, pos, emit);
     }
   }
 }

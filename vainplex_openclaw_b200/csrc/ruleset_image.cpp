@@ -47,7 +47,7 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     H.factor_words.push_back(f.pre); H.factor_words.push_back(f.pre_alpha);
   }
   // ---- level-1b hash table: entries sorted by bucket
-  uint32_t nb = 16; while (nb < P.entries.size() / 2) nb *= 2;
+  uint32_t nb = 16; while (nb < P.entries.size() * 2) nb *= 2;      // sparse: the lookup reads a bucket's first two entries without a loop
   H.n_buckets = nb; H.nb_shift = 32; { uint32_t t = nb; while (t > 1) { t >>= 1; H.nb_shift--; } }
   std::vector<uint32_t> shape_of(P.entries.size()), bucket_of(P.entries.size()), order(P.entries.size());
   for (size_t i = 0; i < P.entries.size(); i++) {
@@ -75,7 +75,7 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   H.bm_bytes = bm; H.bm_mask = bm - 4; H.bloom2 = opt.bloom2 != 0;
   H.image.assign(bm, 0);
   for (uint32_t key : P.keys) {
-    const uint32_t h = key * kGramMult, addr = (uint32_t)(((uint64_t)key * kGramMult) >> 32) & H.bm_mask;
+    const uint32_t h = key * kGramMult, addr = (uint32_t)(((uint64_t)h * (bm / 4)) >> 32) << 2;
     uint32_t wv; memcpy(&wv, H.image.data() + addr, 4);
     wv |= (0x80000000u >> (h & 31u)) | (H.bloom2 ? (0x80000000u >> ((h >> 5) & 31u)) : 0u);
     memcpy(H.image.data() + addr, &wv, 4);

@@ -80,7 +80,7 @@ struct QueueEmit {
 // The hot loop is bound by the integer ALU pipe (LOP3 / SHF / PRMT: 16 lanes per SM sub-partition and clock), not by
 // instruction issue: constants that would cost a second LOP3 as immediates sit in registers, and additions go through
 // IMAD (x * one + c, `one` a run-time 1 the compiler cannot fold) so that they execute on the FMA pipe instead.
-struct HotConst { uint32_t c5f, c10, one; };
+struct HotConst { uint32_t c5f, c10, one, four, words; };     // words = bitmap words (a power of two)
 // z = (w & 0x5f5f5f5f) ^ 0x10101010 per byte (one LOP3); the gram key drops the low nibble of the digit bytes (z < 0x10)
 __device__ __forceinline__ uint32_t fold_z(uint32_t w, const HotConst& k) {
   uint32_t z;
@@ -94,12 +94,14 @@ __device__ __forceinline__ uint32_t fold_key(uint32_t z, const HotConst& k) {
   asm("lop3.b32 %0, %1, %2, 0xf0f0f0f0, 0xe0;" : "=r"(f) : "r"(z), "r"(keep));               // z & (keep | 0xf0f0f0f0)
   return f;
 }
-// one probe of the bitmap: the word at hi32(key * M) & bm_mask, bit 31 - (h & 31) (and, BLOOM2, 31 - ((h >> 5) & 31)), h = lo32;
-// the answer is shifted into the low end of `flags`
+// one probe of the bitmap.  h = key * M; word index = hi32(h * words) (= the top bits of h), byte address = index * 4 + base:
+// three IMADs on the FMA pipe instead of shift + mask on the ALU pipe; bit 31 - (h & 31) of the word is shifted into `flags`.
 template <int BLOOM2>
-__device__ __forceinline__ void gram_probe(uint32_t bm, uint32_t bm_mask, uint32_t key, uint32_t& flags) {
+__device__ __forceinline__ void gram_probe(uint32_t bm, const HotConst& k, uint32_t key, uint32_t& flags) {
   const uint32_t h = key * kGramMult;
-  const uint32_t wv = lds_u32(bm + (__umulhi(key, kGramMult) & bm_mask));
+  uint32_t addr;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(__umulhi(h, k.words)), "r"(k.four), "r"(bm));
+  const uint32_t wv = lds_u32(addr);
   uint32_t t = wv << (h & 31u);
   if (BLOOM2) t &= wv << ((h >> 5) & 31u);
   flags = __funnelshift_l(t, flags, 1);
@@ -118,16 +120,20 @@ struct ScanCtx { GramTables T; const uint8_t* bytes; uint32_t begin, end; };
 // level 1b for up to 32 flagged grams of one warp's ring, one per lane.  `shift`: flagged gram = byte position >> shift.
 __device__ __forceinline__ void drain_ring(const DevRuleset& rs, const ScanWork& w, const ScanCtx& c, uint32_t ring, uint32_t head, uint32_t cnt, uint32_t shift) {
   const uint32_t lane = threadIdx.x & 31u;
+  // all 32 lanes walk gram_lookup together (its phases are separated by warp votes); lanes without an event are inactive
+  uint32_t pos = 0, g = 0; bool active = false;
   if (lane < cnt) {
-    const uint32_t pos = lds_u32(ring + (((head + lane) & (kRing - 1)) << 2)) << shift;
-    if (pos < c.end && !(rs.debug_flags & 1u)) {
-      const uint32_t* p4 = reinterpret_cast<const uint32_t*>(c.bytes + (pos & ~3u));
-      uint32_t g = __ldg(p4);
-      if (pos & 3u) g = __funnelshift_r(g, __ldg(p4 + 1), 8u * (pos & 3u));
-      QueueEmit emit{w};
-      gram_lookup(rs, c.T, gram_fold_word(g), c.bytes, c.begin, c.end, pos, emit);
-    }
+    pos = lds_u32(ring + (((head + lane) & (kRing - 1)) << 2)) << shift;
+    active = pos < c.end && !(rs.debug_flags & 1u);
   }
+  if (active) {
+    const uint32_t* p4 = reinterpret_cast<const uint32_t*>(c.bytes + (pos & ~3u));
+    g = __ldg(p4);
+    if (pos & 3u) g = __funnelshift_r(g, __ldg(p4 + 1), 8u * (pos & 3u));
+  }
+  QueueEmit emit{w};
+  __syncwarp();
+  gram_lookup(rs, c.T, gram_fold_word(g), c.bytes, c.begin, c.end, pos, emit, active);
   __syncwarp();
 }
 
@@ -151,15 +157,15 @@ __device__ __forceinline__ void trigger_chunk(const DevRuleset& rs, const ScanWo
 // An occurrence that starts less than three bytes into the scanned range has no gram in front of it: compared directly.
 __device__ __noinline__ void head_check(const DevRuleset& rs, const ScanWork& w, const ScanCtx& c) {
   QueueEmit emit{w};
-  for (uint32_t i = threadIdx.x; i < 3u * rs.n_factors; i += kScanThreads) {
+  for (uint32_t i = threadIdx.x; i < 3u * rs.n_factors; i += blockDim.x) {
     const uint32_t f = i / 3u, t0 = c.begin + i % 3u;
     const uint32_t* fw = c.T.factors + (size_t)f * 12;
     if (t0 < c.end && t0 + (fw[1] & 0xffu) <= c.end && factor_at(fw, c.T.bytesets, c.bytes + t0)) emit(t0, f);
   }
 }
 
-template <int NPROBE, int NTRIG, int BLOOM2>
-__global__ void __launch_bounds__(kScanThreads, 1)
+template <int NPROBE, int NTRIG, int BLOOM2, int NT>
+__global__ void __launch_bounds__(NT, 1)
 scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n,
             uint64_t* __restrict__ words) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -174,88 +180,99 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
     }
   }
   // while the image is in flight: result words start at zero (finalize_kernel fills in the messages that hit)
-  for (uint32_t i = blockIdx.x * kScanThreads + threadIdx.x; i < n; i += gridDim.x * kScanThreads) words[i] = 0ull;
+  for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) words[i] = 0ull;
   ScanCtx ctx;
   ctx.bytes = bytes; ctx.begin = off[0]; ctx.end = off[n];
   const uint32_t begin = ctx.begin, end = ctx.end;
   mbar_wait(&bar, 0);
 
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kScanThreads / 32;
-  const uint32_t lt = (1u << lane) - 1u, FULL = 0xffffffffu;
-  const uint32_t bm = smem_u32(smem), bm_mask = rs.bm_mask;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = NT / 32;
+  uint32_t lt = (1u << lane) - 1u; const uint32_t FULL = 0xffffffffu;
+  asm volatile("" : "+r"(lt));                // (loop invariants the compiler would otherwise recompute in every iteration of the hot loop)
+  const uint32_t bm = smem_u32(smem);
   const uint32_t ring = smem_u32(smem + rs.image_bytes) + warp * (kRing * 4);
   if (rs.tables_resident) {
     ctx.T.bucket_start = reinterpret_cast<const uint32_t*>(smem + rs.dir_off); ctx.T.entries = reinterpret_cast<const uint2*>(smem + rs.ent_off);
     ctx.T.factors = reinterpret_cast<const uint32_t*>(smem + rs.fac_off); ctx.T.bytesets = reinterpret_cast<const uint32_t*>(smem + rs.set_off);
   } else { ctx.T.bucket_start = rs.bucket_start; ctx.T.entries = rs.entries; ctx.T.factors = rs.factors; ctx.T.bytesets = rs.bytesets; }
   constexpr uint32_t kShift = NPROBE == 2 ? 1 : 2;             // flagged gram = its byte position >> kShift
-  HotConst hk; hk.c5f = rs.hot_c5f; hk.c10 = rs.hot_c10; hk.one = rs.hot_one;
-  uint32_t ring_n = 0, ring_head = 0, flagged_total = 0;
+  HotConst hk; hk.c5f = rs.hot_c5f; hk.c10 = rs.hot_c10; hk.one = rs.hot_one; hk.four = rs.hot_one << 2; hk.words = (rs.bm_mask >> 2) + 1u;
+  asm volatile("" : "+r"(hk.c5f), "+r"(hk.c10), "+r"(hk.one), "+r"(hk.four), "+r"(hk.words));
+  uint32_t ring_head = 0, ring_tail = 0;          // flagged grams drained / pushed so far (the ring holds [head, tail))
   if (blockIdx.x == 0) head_check(rs, w, ctx);
 
   const uint32_t first_chunk = begin >> 4, end_chunk = (end + 15u) >> 4;       // 16-byte chunks [first, end)
   // folded (z domain) trigger bytes, splatted
-  const uint32_t splat0 = NTRIG > 0 ? (((rs.trig_byte[0] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u, splat1 = NTRIG > 1 ? (((rs.trig_byte[1] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u;
+  uint32_t splat0 = NTRIG > 0 ? (((rs.trig_byte[0] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u, splat1 = NTRIG > 1 ? (((rs.trig_byte[1] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u;
+  asm volatile("" : "+r"(splat0), "+r"(splat1));
   // this lane's chunk in the warp's current tile (32 chunks = 512 bytes); tiles are dealt round-robin to all warps of the grid
   uint32_t c = first_chunk + (blockIdx.x * wpb + warp) * 32u + lane;
   const uint32_t cstep = gridDim.x * wpb * 32u;
 
-  // two tiles in flight per warp beyond the one being scanned
   auto load_chunk = [&](uint4& v, uint32_t& t, uint32_t cc) {
     v = make_uint4(0, 0, 0, 0); t = 0;
     if (cc < end_chunk) v = ldg_stream(bytes + (size_t)cc * 16);
     if (NPROBE == 2 && lane == 31 && cc + 1 < end_chunk) t = __ldg(reinterpret_cast<const uint32_t*>(bytes + (size_t)(cc + 1) * 16));
   };
-  uint4 b0, b1; uint32_t t0, t1;
-  load_chunk(b0, t0, c); load_chunk(b1, t1, c + cstep);
-#pragma unroll 1
-  while (c - lane < end_chunk) {
-    const uint4 cur = b0; const uint32_t ct = t0;
-    b0 = b1; t0 = t1;
-    load_chunk(b1, t1, c + 2u * cstep);
+  // Three tiles per round, each in its own registers: a buffer is refilled (tile + 3 rounds' worth ahead) right after it
+  // has been consumed, so every load has two tiles' worth of work to hide behind and no register is ever copied.
+  // The probe results of the round's three tiles are collected in one register per lane before anything is done about
+  // them: the compaction below then amortises its warp votes over three tiles.
+  constexpr uint32_t kBits = 4u * NPROBE;
+  uint4 bA, bB, bC; uint32_t tA, tB, tC;
+  load_chunk(bA, tA, c); load_chunk(bB, tB, c + cstep); load_chunk(bC, tC, c + 2u * cstep);
+  uint32_t acc = 0;
+  auto scan_tile = [&](uint4& buf, uint32_t& tl, uint32_t cc) {
+    const uint4 cur = buf; const uint32_t ct = tl;
+    load_chunk(buf, tl, cc + 3u * cstep);
     const uint32_t z0 = fold_z(cur.x, hk), z1 = fold_z(cur.y, hk), z2 = fold_z(cur.z, hk), z3 = fold_z(cur.w, hk);
     const uint32_t f0 = fold_key(z0, hk), f1 = fold_key(z1, hk), f2 = fold_key(z2, hk), f3 = fold_key(z3, hk);
     uint32_t flags = 0;
     if (NPROBE == 2) {
       uint32_t w4 = __shfl_down_sync(FULL, cur.x, 1); if (lane == 31) w4 = ct;
       const uint32_t f4 = fold_key(fold_z(w4, hk), hk);
-      gram_probe<BLOOM2>(bm, bm_mask, f0, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f0, f1, 16), flags);
-      gram_probe<BLOOM2>(bm, bm_mask, f1, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f1, f2, 16), flags);
-      gram_probe<BLOOM2>(bm, bm_mask, f2, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f2, f3, 16), flags);
-      gram_probe<BLOOM2>(bm, bm_mask, f3, flags); gram_probe<BLOOM2>(bm, bm_mask, __funnelshift_r(f3, f4, 16), flags);
+      gram_probe<BLOOM2>(bm, hk, f0, flags); gram_probe<BLOOM2>(bm, hk, __funnelshift_r(f0, f1, 16), flags);
+      gram_probe<BLOOM2>(bm, hk, f1, flags); gram_probe<BLOOM2>(bm, hk, __funnelshift_r(f1, f2, 16), flags);
+      gram_probe<BLOOM2>(bm, hk, f2, flags); gram_probe<BLOOM2>(bm, hk, __funnelshift_r(f2, f3, 16), flags);
+      gram_probe<BLOOM2>(bm, hk, f3, flags); gram_probe<BLOOM2>(bm, hk, __funnelshift_r(f3, f4, 16), flags);
     } else {
-      gram_probe<BLOOM2>(bm, bm_mask, f0, flags); gram_probe<BLOOM2>(bm, bm_mask, f1, flags);
-      gram_probe<BLOOM2>(bm, bm_mask, f2, flags); gram_probe<BLOOM2>(bm, bm_mask, f3, flags);
+      gram_probe<BLOOM2>(bm, hk, f0, flags); gram_probe<BLOOM2>(bm, hk, f1, flags);
+      gram_probe<BLOOM2>(bm, hk, f2, flags); gram_probe<BLOOM2>(bm, hk, f3, flags);
     }
-    // triggers: d_j has bit 7 of a byte clear where it equals a trigger byte (folded domain)
-    uint32_t d0 = 0x80808080u, d1 = 0x80808080u, d2 = 0x80808080u, d3 = 0x80808080u;
-    if (NTRIG > 0) { d0 = differs(z0, splat0, hk.one); d1 = differs(z1, splat0, hk.one); d2 = differs(z2, splat0, hk.one); d3 = differs(z3, splat0, hk.one); }
-    if (NTRIG > 1) { d0 &= differs(z0, splat1, hk.one); d1 &= differs(z1, splat1, hk.one); d2 &= differs(z2, splat1, hk.one); d3 &= differs(z3, splat1, hk.one); }
-    bool trig = NTRIG > 0 && ((d0 & d1 & d2 & d3 & 0x80808080u) != 0x80808080u);
-    if (c >= end_chunk) { flags = 0; trig = false; }
-    if (__any_sync(FULL, flags != 0 || trig)) {
-      // rare from here on.  flags: bit (4 * NPROBE - 1 - j) = probe j of the lane's chunk; flagged grams are compacted into the warp's ring
-      if (NTRIG > 0 && trig) trigger_chunk(rs, w, ctx, ~d0 & 0x80808080u, ~d1 & 0x80808080u, ~d2 & 0x80808080u, ~d3 & 0x80808080u, c);
-      __syncwarp();
-      const uint32_t base = c * (4u * NPROBE);
-      while (__any_sync(FULL, flags != 0)) {
-        const bool has = flags != 0;
-        const uint32_t m = __ballot_sync(FULL, has);
-        if (has) {
-          const uint32_t bit = 31u - __clz(flags);
-          flags &= ~(1u << bit);
-          const uint32_t slot = (ring_head + ring_n + __popc(m & lt)) & (kRing - 1);
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring + slot * 4), "r"(base + (4u * NPROBE - 1u - bit)) : "memory");
-        }
-        ring_n += __popc(m); flagged_total += __popc(m);
-        if (ring_n >= 32) { __syncwarp(); drain_ring(rs, w, ctx, ring, ring_head, 32, kShift); ring_head += 32; ring_n -= 32; }
+    if (cc >= end_chunk) flags = 0;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc), "r"(hk.one << kBits), "r"(flags));      // acc = acc << kBits | flags, on the FMA pipe
+    if (NTRIG > 0) {
+      // triggers: d_j has bit 7 of a byte clear where it equals a trigger byte (folded domain)
+      uint32_t d0 = differs(z0, splat0, hk.one), d1 = differs(z1, splat0, hk.one), d2 = differs(z2, splat0, hk.one), d3 = differs(z3, splat0, hk.one);
+      if (NTRIG > 1) { d0 &= differs(z0, splat1, hk.one); d1 &= differs(z1, splat1, hk.one); d2 &= differs(z2, splat1, hk.one); d3 &= differs(z3, splat1, hk.one); }
+      const bool trig = cc < end_chunk && ((d0 & d1 & d2 & d3 & 0x80808080u) != 0x80808080u);
+      if (__any_sync(FULL, trig)) {
+        if (trig) trigger_chunk(rs, w, ctx, ~d0 & 0x80808080u, ~d1 & 0x80808080u, ~d2 & 0x80808080u, ~d3 & 0x80808080u, cc);
+        __syncwarp();
       }
     }
-    c += cstep;
+  };
+#pragma unroll 1
+  while (c - lane < end_chunk) {                           // warp-uniform: this warp still has a tile
+    scan_tile(bA, tA, c);
+    scan_tile(bB, tB, c + cstep);                          // (tiles past the end load nothing and flag nothing)
+    scan_tile(bC, tC, c + 2u * cstep);
+    c += 3u * cstep;
+    // acc: bit (i * kBits + kBits - 1 - j) = probe j of the tile scanned i tiles ago, whose chunk was c - (i + 1) * cstep
+    for (uint32_t m = __ballot_sync(FULL, acc != 0); m; m = __ballot_sync(FULL, acc != 0)) {
+      if (acc) {
+        const uint32_t bit = 31u - __clz(acc);
+        acc ^= 1u << bit;
+        const uint32_t ev = (c - (bit / kBits + 1u) * cstep) * kBits + (kBits - 1u - bit % kBits);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring + (((ring_tail + __popc(m & lt)) & (kRing - 1)) << 2)), "r"(ev) : "memory");
+      }
+      ring_tail += __popc(m);
+      if (ring_tail - ring_head >= 32) { __syncwarp(); drain_ring(rs, w, ctx, ring, ring_head, 32, kShift); ring_head += 32; }
+    }
   }
   __syncwarp();
-  if (ring_n) drain_ring(rs, w, ctx, ring, ring_head, ring_n, kShift);
-  if (lane == 0 && flagged_total) atomicAdd(&w.counters[6], flagged_total);
+  if (ring_tail != ring_head) drain_ring(rs, w, ctx, ring, ring_head, ring_tail - ring_head, kShift);
+  if (lane == 0 && ring_tail) atomicAdd(&w.counters[6], ring_tail);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -500,11 +517,13 @@ __global__ void verdict_kernel(DevRuleset rs, ScanWork w, uint32_t* __restrict__
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-#define CG_FOR_SCAN_VARIANTS(X) X(1, 0, 1) X(1, 1, 1) X(1, 2, 1) X(2, 0, 1) X(2, 1, 1) X(2, 2, 1) X(1, 0, 0) X(1, 1, 0) X(1, 2, 0) X(2, 0, 0) X(2, 1, 0) X(2, 2, 0)
+#define CG_FOR_SCAN_VARIANTS(X) X(1, 0, 0) X(1, 1, 0) X(1, 2, 0) X(2, 0, 0) X(2, 1, 0) X(2, 2, 0) X(1, 0, 1) X(1, 1, 1) X(1, 2, 1) X(2, 0, 1) X(2, 1, 1) X(2, 2, 1)
+static int scan_threads() { static int t = 0; if (!t) { t = kScanThreads; if (const char* e = getenv("CG_SCAN_THREADS")) { int v = atoi(e); if (v == 512 || v == 768 || v == 1024) t = v; } } return t; }
 void prepare_scan_kernels() {
   int dev = 0, optin = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int kMaxSmem = (optin > 0 ? optin : 227 * 1024) - 1024;     // leave room for the kernels' static shared memory
-#define CG_PREP(P, T, B) cudaFuncSetAttribute(scan_kernel<P, T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+#define CG_PREP(P, T, B) cudaFuncSetAttribute(scan_kernel<P, T, B, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+  cudaFuncSetAttribute(scan_kernel<P, T, B, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); cudaFuncSetAttribute(scan_kernel<P, T, B, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   CG_FOR_SCAN_VARIANTS(CG_PREP)
 #undef CG_PREP
   cudaFuncSetAttribute(verify_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
@@ -518,8 +537,11 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   // the scanned range is only known on the device (off[0] .. off[n]); a warp tile is 512 bytes, messages are rarely shorter than 16
   uint32_t grid = (uint32_t)sm_count;
   if (n < 4096) grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, n / 32u + 1u));         // tiny batches: fewer image loads
-  const int np = rs.stride == 2 ? 2 : 1, nt = (int)rs.n_trig, bl = rs.bloom2 ? 1 : 0;
-#define CG_LAUNCH(P, T, B) if (np == P && nt == T && bl == B) scan_kernel<P, T, B><<<grid, kScanThreads, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words);
+  const int np = rs.stride == 2 ? 2 : 1, nt = (int)rs.n_trig, bl = rs.bloom2 ? 1 : 0, th = scan_threads();
+#define CG_LAUNCH(P, T, B) if (np == P && nt == T && bl == B) { \
+    if (th == 1024) scan_kernel<P, T, B, 1024><<<grid, 1024, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); \
+    else if (th == 768) scan_kernel<P, T, B, 768><<<grid, 768, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); \
+    else scan_kernel<P, T, B, 512><<<grid, 512, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); }
   CG_FOR_SCAN_VARIANTS(CG_LAUNCH)
 #undef CG_LAUNCH
   return 1;
