@@ -27,13 +27,13 @@ CG_HD uint32_t gram_fold_word(uint32_t w) {
   return z & (keep | 0xf0f0f0f0u);
 }
 
-// Bitmap geometry: h = key * kGramMult; word index = the top log2(words) bits of h (on the device hi32(h * words), one
-// IMAD.HI), bit 31 - (h & 31) and, for the optional second Bloom bit in the same word, bit 31 - ((h >> 5) & 31).
-// bm_mask = bitmap bytes - 4 (bitmap bytes a power of two).
-CG_HD uint32_t gram_bitmap_addr(uint32_t key, uint32_t bm_mask) { return (uint32_t)(((uint64_t)(key * kGramMult) * ((bm_mask >> 2) + 1u)) >> 32) << 2; }
+// Bitmap geometry: word at byte address hi32(key * kGramMult) & bm_mask (bm_mask = bitmap bytes - 4, bitmap bytes a
+// power of two); a key sets / needs bit 31 - (key & 31) -- the low five bits of its folded first byte -- and, for the
+// optional second Bloom bit in the same word, bit 31 - ((hi32 >> 17) & 31).
+CG_HD uint32_t gram_bitmap_addr(uint32_t key, uint32_t bm_mask) { return (uint32_t)(((uint64_t)key * kGramMult) >> 32) & bm_mask; }
 CG_HD uint32_t gram_bitmap_bits(uint32_t key, bool bloom2) {
-  const uint32_t h = key * kGramMult;
-  return (0x80000000u >> (h & 31u)) | (bloom2 ? (0x80000000u >> ((h >> 5) & 31u)) : 0u);
+  const uint32_t hi = (uint32_t)(((uint64_t)key * kGramMult) >> 32);
+  return (0x80000000u >> (key & 31u)) | (bloom2 ? (0x80000000u >> ((hi >> 17) & 31u)) : 0u);
 }
 CG_HD bool gram_bitmap_test(const uint8_t* bitmap, uint32_t key, uint32_t bm_mask, bool bloom2) {
   const uint32_t wv = *reinterpret_cast<const uint32_t*>(bitmap + gram_bitmap_addr(key, bm_mask));

@@ -75,9 +75,9 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   H.bm_bytes = bm; H.bm_mask = bm - 4; H.bloom2 = opt.bloom2 != 0;
   H.image.assign(bm, 0);
   for (uint32_t key : P.keys) {
-    const uint32_t h = key * kGramMult, addr = (uint32_t)(((uint64_t)h * (bm / 4)) >> 32) << 2;
+    const uint32_t hi = (uint32_t)(((uint64_t)key * kGramMult) >> 32), addr = hi & H.bm_mask;
     uint32_t wv; memcpy(&wv, H.image.data() + addr, 4);
-    wv |= (0x80000000u >> (h & 31u)) | (H.bloom2 ? (0x80000000u >> ((h >> 5) & 31u)) : 0u);
+    wv |= (0x80000000u >> (key & 31u)) | (H.bloom2 ? (0x80000000u >> ((hi >> 17) & 31u)) : 0u);
     memcpy(H.image.data() + addr, &wv, 4);
   }
   if (H.tables_resident) {

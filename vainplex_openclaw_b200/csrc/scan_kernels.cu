@@ -80,7 +80,7 @@ struct QueueEmit {
 // The hot loop is bound by the integer ALU pipe (LOP3 / SHF / PRMT: 16 lanes per SM sub-partition and clock), not by
 // instruction issue: constants that would cost a second LOP3 as immediates sit in registers, and additions go through
 // IMAD (x * one + c, `one` a run-time 1 the compiler cannot fold) so that they execute on the FMA pipe instead.
-struct HotConst { uint32_t c5f, c10, one, four, words; };     // words = bitmap words (a power of two)
+struct HotConst { uint32_t c5f, c10, one, mask; };            // mask = bitmap bytes - 4
 // z = (w & 0x5f5f5f5f) ^ 0x10101010 per byte (one LOP3); the gram key drops the low nibble of the digit bytes (z < 0x10)
 __device__ __forceinline__ uint32_t fold_z(uint32_t w, const HotConst& k) {
   uint32_t z;
@@ -94,16 +94,15 @@ __device__ __forceinline__ uint32_t fold_key(uint32_t z, const HotConst& k) {
   asm("lop3.b32 %0, %1, %2, 0xf0f0f0f0, 0xe0;" : "=r"(f) : "r"(z), "r"(keep));               // z & (keep | 0xf0f0f0f0)
   return f;
 }
-// one probe of the bitmap.  h = key * M; word index = hi32(h * words) (= the top bits of h), byte address = index * 4 + base:
-// three IMADs on the FMA pipe instead of shift + mask on the ALU pipe; bit 31 - (h & 31) of the word is shifted into `flags`.
+// one probe of the bitmap: word at byte address hi32(key * M) & bm_mask (one IMAD.HI on the FMA pipe, one LOP3), bit
+// 31 - (key & 31) of it -- the bit index comes straight from the folded first byte, the variable shift only looks at the
+// low five bits of its operand -- shifted into `flags`.  Five instructions per probe.
 template <int BLOOM2>
 __device__ __forceinline__ void gram_probe(uint32_t bm, const HotConst& k, uint32_t key, uint32_t& flags) {
-  const uint32_t h = key * kGramMult;
-  uint32_t addr;
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(__umulhi(h, k.words)), "r"(k.four), "r"(bm));
-  const uint32_t wv = lds_u32(addr);
-  uint32_t t = wv << (h & 31u);
-  if (BLOOM2) t &= wv << ((h >> 5) & 31u);
+  const uint32_t hi = __umulhi(key, kGramMult);
+  const uint32_t wv = lds_u32(bm + (hi & k.mask));
+  uint32_t t = wv << (key & 31u);
+  if (BLOOM2) t &= wv << ((hi >> 17) & 31u);
   flags = __funnelshift_l(t, flags, 1);
 }
 // trigger bytes, compared in the folded domain (z): bit 7 of every byte of the result is CLEAR where z equals the splatted
@@ -196,8 +195,8 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
     ctx.T.factors = reinterpret_cast<const uint32_t*>(smem + rs.fac_off); ctx.T.bytesets = reinterpret_cast<const uint32_t*>(smem + rs.set_off);
   } else { ctx.T.bucket_start = rs.bucket_start; ctx.T.entries = rs.entries; ctx.T.factors = rs.factors; ctx.T.bytesets = rs.bytesets; }
   constexpr uint32_t kShift = NPROBE == 2 ? 1 : 2;             // flagged gram = its byte position >> kShift
-  HotConst hk; hk.c5f = rs.hot_c5f; hk.c10 = rs.hot_c10; hk.one = rs.hot_one; hk.four = rs.hot_one << 2; hk.words = (rs.bm_mask >> 2) + 1u;
-  asm volatile("" : "+r"(hk.c5f), "+r"(hk.c10), "+r"(hk.one), "+r"(hk.four), "+r"(hk.words));
+  HotConst hk; hk.c5f = rs.hot_c5f; hk.c10 = rs.hot_c10; hk.one = rs.hot_one; hk.mask = rs.bm_mask;
+  asm volatile("" : "+r"(hk.c5f), "+r"(hk.c10), "+r"(hk.one));
   uint32_t ring_head = 0, ring_tail = 0;          // flagged grams drained / pushed so far (the ring holds [head, tail))
   if (blockIdx.x == 0) head_check(rs, w, ctx);
 
