@@ -88,6 +88,8 @@ def lib():
         L.oracle_merkle_root.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.oracle_merkle_root_fixed.restype = C.c_int
         L.oracle_merkle_root_fixed.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.oracle_merkle_root_fixed_mt.restype = C.c_int
+        L.oracle_merkle_root_fixed_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
         L.oracle_merkle_root_rfc6962.restype = C.c_int
         L.oracle_merkle_root_rfc6962.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.oracle_merkle_fold.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
@@ -154,7 +156,7 @@ def scan_policy(regexes: Sequence[Regex], data: np.ndarray, off: np.ndarray, thr
     """matchesAny semantics per (message, rule): returns (hit_bits[n, ceil(R/8)], words[n])."""
     n = len(off) - 1
     R = len(regexes)
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or host_threads()
     bits = np.zeros((n, (R + 7) // 8), dtype=np.uint8) if want_bits else None
     words = np.zeros(n, dtype=np.uint64)
     rc = lib().oracle_scan_policy(_handles(regexes), R, data.ctypes.data, off.ctypes.data, n, threads,
@@ -174,7 +176,7 @@ def find_matches_batch(patterns: Sequence[tuple], data: np.ndarray, off: np.ndar
     regs = [patterns[i][0] for i in order]
     ranks = np.array([CATEGORY_ORDER.index(patterns[i][1]) for i in order], dtype=np.int32)
     n = len(off) - 1
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or host_threads()
     out = C.c_void_p()
     k = lib().oracle_find_matches_batch(_handles(regs), ranks.ctypes.data, len(regs), data.ctypes.data,
                                         off.ctypes.data, n, threads, C.byref(out))
@@ -273,11 +275,23 @@ def merkle_root(data: np.ndarray, off: np.ndarray) -> bytes:
     return out.tobytes()
 
 
-def merkle_root_fixed(data: np.ndarray, leaf_len: int, n: int) -> bytes:
+def merkle_root_fixed(data: np.ndarray, leaf_len: int, n: int, threads: int = 1) -> bytes:
     out = np.zeros(32, dtype=np.uint8)
-    if lib().oracle_merkle_root_fixed(data.ctypes.data, leaf_len, n, out.ctypes.data) != 0:
+    if threads > 1:
+        rc = lib().oracle_merkle_root_fixed_mt(data.ctypes.data, leaf_len, n, threads, out.ctypes.data)
+    else:
+        rc = lib().oracle_merkle_root_fixed(data.ctypes.data, leaf_len, n, out.ctypes.data)
+    if rc != 0:
         raise MemoryError
     return out.tobytes()
+
+
+def host_threads() -> int:
+    """CPUs this process may run on (its affinity mask -- a cgroup-limited container often has fewer than os.cpu_count())"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def merkle_root_rfc6962(data: np.ndarray, off: np.ndarray) -> bytes:

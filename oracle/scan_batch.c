@@ -12,10 +12,12 @@
  * Messages arrive as UTF-8 (bytes + offsets[n+1]) and are decoded to UTF-16 code
  * units first, because the reference matches JS strings.
  */
+#define _GNU_SOURCE   /* sched_getaffinity, pthread_attr_setaffinity_np */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <sched.h>
 
 typedef struct jsre jsre;
 int jsre_exec(const jsre *re, const uint16_t *s, int n, int last_index, int *start, int *end);
@@ -120,10 +122,15 @@ static int run_jobs(Job *proto, size_t nmsg, int nthreads, Job **out_jobs) {
     if ((size_t)nthreads > nmsg && nmsg > 0) nthreads = (int)nmsg;
     Job *jobs = (Job *)calloc((size_t)nthreads, sizeof(Job));
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+    /* one thread per CPU of the caller's affinity mask, pinned (thread t -> the t-th allowed CPU, round robin): the timing
+     * of the CPU arm should not depend on where the scheduler happens to put 128 threads of a cgroup-limited process */
+    cpu_set_t allowed; int cpus[1024], ncpu = 0;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0) for (int c = 0; c < 1024 && c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
     for (int t = 0; t < nthreads; t++) {
         jobs[t] = *proto;
         jobs[t].lo = nmsg * (size_t)t / (size_t)nthreads; jobs[t].hi = nmsg * (size_t)(t + 1) / (size_t)nthreads;
         pthread_attr_t at; pthread_attr_init(&at); pthread_attr_setstacksize(&at, (size_t)512 << 20);
+        if (ncpu > 0) { cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[t % ncpu], &one); pthread_attr_setaffinity_np(&at, sizeof one, &one); }
         pthread_create(&th[t], &at, worker, &jobs[t]);
         pthread_attr_destroy(&at);
     }

@@ -126,6 +126,37 @@ int oracle_merkle_root_fixed(const uint8_t *bytes, size_t leaf_len, size_t n, ui
     return 0;
 }
 
+/* The same tree with the leaf level spread over threads: aligned blocks of 2^16 leaves are reduced to their roots
+ * independently (level-k nodes of the level-wise tree are exactly the roots of aligned 2^k-leaf blocks), the block roots
+ * are folded at the end.  Only there so that the full-size C3 tree can be checked in seconds. */
+#include <pthread.h>
+typedef struct { const uint8_t *bytes; size_t leaf_len, n, nblocks; uint8_t *roots; volatile long *next; } MtJob;
+static void *mt_worker(void *arg) {
+    MtJob *j = (MtJob *)arg;
+    for (;;) {
+        long b = __sync_fetch_and_add(j->next, 1);
+        if ((size_t)b >= j->nblocks) break;
+        size_t lo = (size_t)b << 16, cnt = j->n - lo < ((size_t)1 << 16) ? j->n - lo : ((size_t)1 << 16);
+        oracle_merkle_root_fixed(j->bytes + j->leaf_len * lo, j->leaf_len, cnt, j->roots + 32 * (size_t)b);
+    }
+    return NULL;
+}
+int oracle_merkle_root_fixed_mt(const uint8_t *bytes, size_t leaf_len, size_t n, int nthreads, uint8_t out[32]) {
+    if (n <= ((size_t)1 << 16) || nthreads <= 1) return oracle_merkle_root_fixed(bytes, leaf_len, n, out);
+    size_t nblocks = (n + 65535) >> 16;
+    uint8_t *roots = (uint8_t *)malloc(32 * nblocks);
+    if (!roots) return -1;
+    volatile long next = 0;
+    MtJob job = { bytes, leaf_len, n, nblocks, roots, &next };
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, mt_worker, &job);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    oracle_merkle_fold(roots, nblocks, out);
+    free(roots);
+    return 0;
+}
+
 /* RFC 6962 2.1 MTH stated recursively (split at the largest power of two < n):
  * used by the tests to show the level-wise fold above has the same tree shape. */
 static void mth_rec(const uint8_t *leaf_hashes, size_t n, uint8_t out[32]) {

@@ -135,6 +135,32 @@ def test_syntax_and_support_classification(oracle, harness_lib):
     assert N.rule_check("É", N.FLAG_ICASE) == N.CG_ERR_UNSUPPORTED
 
 
+def test_closure_stack_is_bounded_at_compile_time(oracle, harness_lib):
+    """A rule either provably fits the VM's closure stack or is rejected when it is compiled (it used to pass the compile
+    step and then fail every batch at scan time).  An alternation keeps one pending branch per alternative on that stack."""
+    import itertools, time
+    from vainplex_openclaw_b200 import _native as N
+    words = ["".join(p) for p in itertools.product("abcdefghijklmnopqrst", repeat=2)]        # 400 two-letter alternatives
+    for n_alt, expect_ok in ((60, True), (150, True), (190, True), (200, False), (240, False)):
+        src = "|".join(words[:n_alt])
+        rc = N.rule_check(src)
+        assert (rc == 0) == expect_ok and rc in (0, N.CG_ERR_TOO_LARGE), (n_alt, rc)
+        if expect_ok:
+            h = Harness(harness_lib, [(src, 0, 3)])
+            assert h.status[0] == 0
+            last = words[n_alt - 1].encode()
+            msgs = [b"xx " + last + b" yy", b"ab0", b"zz zz zz", words[7].encode() + b"7"]
+            exp = oracle_spans(oracle, oracle.Regex(src), msgs)
+            for mi, m in enumerate(msgs):
+                assert h.test(0, m) == bool(exp.get(mi)), (n_alt, m)          # (h.test asserts that the VM did not overflow)
+            h.close()
+    # an empty body repeated two billion times must not stall the compiler (it emits nothing: once is enough)
+    t0 = time.time()
+    for src in ("(?:){2000000000}", "(){2000000000}a", "(?:(?:){2000000000}){2000000000}b"):
+        assert N.rule_check(src) in (0, N.CG_ERR_TOO_LARGE, N.CG_ERR_UNSUPPORTED)
+    assert time.time() - t0 < 2.0
+
+
 def test_random_regex_differential(oracle, harness_lib):
     """product compiler + VM vs oracle on random patterns / texts over a tiny alphabet (dense matches,
     empty matches, astral characters, lazy quantifiers, lookarounds)."""

@@ -64,7 +64,7 @@ CG_HD bool in_set(const DevRuleset& rs, uint32_t sid, int u) {
 }
 CG_HD bool is_word(int u) { return (u >= '0' && u <= '9') || (u >= 'A' && u <= 'Z') || u == '_' || (u >= 'a' && u <= 'z'); }
 
-constexpr int kVmStack = 192;
+constexpr int kVmStack = kVmStackLimit;
 
 // VM working storage.  LocalStore: plain per-thread arrays (host harness, large programs).
 // SmemStore (scan_kernels.cu): thread-interleaved shared memory for the common small programs.

@@ -381,7 +381,8 @@ struct Compiler {
       }
       case T_REPEAT: {
         int body = nd.kids[0];
-        for (int c = 0; c < nd.min; c++) gen(body);
+        // (a body that emits nothing -- `(?:){2000000000}` -- is never stopped by the program-length limit: once is enough)
+        for (int c = 0; c < nd.min; c++) { const size_t before = out.prog.size(); gen(body); if (out.prog.size() == before) break; }
         if (nd.max == INF) {
           size_t L = out.prog.size();
           emit(nd.greedy ? OP_SPLIT_NEXT : OP_SPLIT_JUMP, 0);
@@ -393,6 +394,7 @@ struct Compiler {
           // iteration that consumed nothing; EMPTYCHK tests the visited mark of this iteration's SPLIT.
           std::vector<size_t> splits; bool nb = nullable(body);
           for (int c = nd.min; c < nd.max; c++) {
+            if (out.prog.size() > (size_t)kMaxProgLen) break;                   // (emit() reports the overflow)
             splits.push_back(out.prog.size()); emit(nd.greedy ? OP_SPLIT_NEXT : OP_SPLIT_JUMP, 0);
             gen(body);
             if (nb) emit(OP_EMPTYCHK, (uint32_t)splits.back());
@@ -666,6 +668,52 @@ static std::vector<uint16_t> utf8_to_units(const char* s, size_t n) {
 
 }  // namespace
 
+// Worst-case depth of the VM's closure stack (pike_vm.h, VMS::add) for this program: the closure walk is replayed from
+// every pc a closure can start at, with every zero-width assertion passing and fresh marks (a real run only ever cuts
+// paths: assertions fail, marks of earlier threads are DONE).  The device stack holds kVmStackLimit entries; a rule that
+// could overflow it is rejected at compile time instead of failing every batch it meets at scan time.
+static int closure_stack_bound(const std::vector<uint32_t>& prog) {
+  const size_t n = prog.size();
+  std::vector<char> starts(n, 0);
+  if (n) starts[0] = 1;
+  for (size_t pc = 0; pc + 1 < n; pc++) { uint32_t op = prog[pc] & 0xff; if (op == OP_CHAR || op == OP_SET || op == OP_ANY) starts[pc + 1] = 1; }
+  int worst = 0;
+  std::vector<uint8_t> mark(n); std::vector<uint32_t> stk;
+  for (size_t s0 = 0; s0 < n; s0++) {
+    if (!starts[s0]) continue;
+    std::fill(mark.begin(), mark.end(), 0);           // 0 = untouched, 1 = in progress, 2 = done
+    stk.clear(); stk.push_back((uint32_t)s0);
+    while (!stk.empty()) {
+      worst = std::max<int>(worst, (int)stk.size());
+      uint32_t x = stk.back(); stk.pop_back();
+      if (x & 0x80000000u) { mark[x & 0x7fffffffu] = 2; continue; }
+      uint32_t pc = x;
+      for (;;) {
+        if (pc >= n) break;
+        const uint32_t op = prog[pc] & 0xff, arg = prog[pc] >> 8; bool go = false;
+        switch (op) {
+          case OP_SPLIT_NEXT: case OP_SPLIT_JUMP:
+            if (mark[pc] == 2) break;
+            mark[pc] = 1;
+            stk.push_back(0x80000000u | pc); stk.push_back(op == OP_SPLIT_NEXT ? arg : pc + 1);
+            worst = std::max<int>(worst, (int)stk.size());
+            if (worst > 4 * kVmStackLimit) return worst;
+            pc = op == OP_SPLIT_NEXT ? pc + 1 : arg; go = true; break;
+          case OP_JMP: pc = arg; go = true; break;
+          case OP_JMP_BACK: if (mark[arg] != 1) { pc = arg; go = true; } break;
+          case OP_EMPTYCHK: if (mark[arg] != 1) { pc++; go = true; } break;
+          case OP_BOL: case OP_EOL: case OP_WORDB: case OP_NWORDB: case OP_LOOKAHEAD: case OP_NLOOKAHEAD: case OP_LOOKBEHIND: case OP_NLOOKBEHIND:
+            pc++; go = true; break;
+          case OP_MATCH: break;
+          default: mark[pc] = 2; break;        // consuming instruction: the thread is queued
+        }
+        if (!go) break;
+      }
+    }
+  }
+  return worst;
+}
+
 CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
   CompiledRule out;
   Parser ps;
@@ -680,6 +728,7 @@ CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
     c.check_supported(root);
     c.gen(root);
     c.emit(OP_MATCH);
+    if (closure_stack_bound(out.prog) > kVmStackLimit) throw Fail{RULE_ERR_TOO_LARGE, "pattern nests / alternates too deeply for the matcher's closure stack"};
     out.nullable = c.nullable(root);
     if (out.nullable) { for (int k = 0; k < 4; k++) out.first_bytes.w[k] = ~0ull; }
     else {

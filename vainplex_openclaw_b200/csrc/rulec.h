@@ -17,6 +17,7 @@
 namespace cg {
 
 constexpr int kMaxProgLen = 1024;        // Pike instructions per rule (verify-kernel list bound)
+constexpr int kVmStackLimit = 192;       // entries of the VM's closure stack (pike_vm.h); rules that could exceed it are rejected at compile time
 
 // ---- Pike program encoding: one uint32 per instruction = op | arg << 8
 enum Op : uint32_t {

@@ -135,11 +135,20 @@ def rules_as_tuples(rules):
 
 # ------------------------------------------------------------------------------------------ messages
 
-def _vocab(rng, n_words: int, utf8_frac: float):
+def _vocab(rng, n_words: int, utf8_frac: float, fragments=None, frag_frac: float = 0.0):
+    """n_words random lower-case words; with `fragments` (strings taken from the rule set: literals, samples) a fraction
+    frag_frac of the words is a prefix or a suffix (>= 3 characters) of one of them, optionally continued with random
+    letters -- traffic that shares beginnings and endings with the rules without matching them."""
     words = []
     multi = ["é", "ü", "ß", "€", "你", "好", "пр", "\U0001f600", "\U0001f680"]
+    frags = [f for f in (fragments or []) if len(f) >= 4]
     for i in range(n_words):
         w = _word(rng, 2, 10)
+        if frags and rng.random() < frag_frac:
+            f = frags[int(rng.integers(0, len(frags)))]
+            k = int(rng.integers(3, len(f)))                     # 3 .. len-1 characters: never the whole fragment
+            w = (f[:k] if rng.random() < 0.5 else f[len(f) - k:]) + (_word(rng, 1, 3) if rng.random() < 0.5 else "")
+            w = "".join(ch for ch in w if ch.isalnum() or ch in "-_.") or _word(rng, 2, 10)
         if utf8_frac > 0 and rng.random() < utf8_frac:
             pos = int(rng.integers(0, len(w) + 1))
             w = w[:pos] + multi[int(rng.integers(0, len(multi)))] + w[pos:]
@@ -147,8 +156,21 @@ def _vocab(rng, n_words: int, utf8_frac: float):
     return words
 
 
+def rule_fragments(rules):
+    """strings of a rule set that traffic may share beginnings / endings with: every sample token and every run of four or
+    more word characters in a pattern source"""
+    import re
+    out = []
+    for r in rules:
+        if r.get("sample"):
+            out += [t for t in re.split(r"\s+", r["sample"]) if len(t) >= 4]
+        out += re.findall(r"[A-Za-z][A-Za-z0-9_-]{3,}", r["source"])
+    return out
+
+
 def make_messages(n: int, length: int, n_rules_for_hits=None, p_hit: float = 0.01, utf8_frac: float = 0.0,
-                  seed: int = SEED_MSG, device="cpu", chunk_msgs: int = 1 << 16, vocab_seed=None):
+                  seed: int = SEED_MSG, device="cpu", chunk_msgs: int = 1 << 16, vocab_seed=None, vocab_words: int = 4096,
+                  frag_frac: float = 0.0):
     """Fixed-length batch.  Returns (bytes uint8 tensor [n*length + 64], offsets uint32-valued int64
     tensor [n+1] as torch tensors on `device`, injected list of (msg, rule_index) on the host).
 
@@ -158,7 +180,8 @@ def make_messages(n: int, length: int, n_rules_for_hits=None, p_hit: float = 0.0
     import torch
     rng = np.random.default_rng(seed)
     # the vocabulary is the "language" of the traffic: shards of one workload (ranks) share it and draw different messages
-    words = _vocab(rng if vocab_seed is None else np.random.default_rng(vocab_seed), 4096, utf8_frac)
+    words = _vocab(rng if vocab_seed is None else np.random.default_rng(vocab_seed), vocab_words, utf8_frac,
+                   rule_fragments(n_rules_for_hits) if (n_rules_for_hits and frag_frac > 0) else None, frag_frac)
     # zipf-ish word frequencies
     wprob = 1.0 / np.arange(1, len(words) + 1) ** 0.9
     wprob /= wprob.sum()
