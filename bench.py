@@ -443,25 +443,59 @@ def main():
                   "collective": "all_gather of %d block roots/rank (NCCL)" % nblk if world > 1 else "none (1 rank)",
                   "hbm_frac_of_measured": (nl * MERKLE_LEAF / (mms * 1e-3)) / (peak * 1e9),
                   "sha256_compressions_per_s": world * (nl * ((MERKLE_LEAF + 1 + 9 + 63) // 64) + 2 * (nl - 1)) / (mms * 1e-3)}
-        # (f2) the same leaves through the append-only log in 16 appends from host memory (H2D inside), rank 0, N = 1 only
+        # (f2) the append-only log fed from PINNED host memory (H2D inside the timed region), rank 0, N = 1 only:
+        #      ragged leaves (JSONL-line-like lengths 64..320 B) in 16 appends; then the same bytes as one JSONL buffer
+        #      split at '\n' on the device; consistency proof between the half-way tree and the final one
         if world == 1 and rank == 0:
-            nlog = min(nl, 1 << 20)
-            offs = (np.arange(nlog // 16 + 1, dtype=np.uint64) * MERKLE_LEAF)
+            from oracle import oracle as O
+            nlog = min(nl, 1 << 22)
+            rngl = np.random.default_rng(4242)
+            lens = rngl.integers(64, 321, nlog).astype(np.uint64)
+            offs_all = np.zeros(nlog + 1, dtype=np.uint64); offs_all[1:] = np.cumsum(lens)
+            total = int(offs_all[-1])
+            src = leaves[:total + 64].clone()
+            nlpos = torch.from_numpy((offs_all[1:] - 1).astype(np.int64)).to(src.device)
+            src[nlpos] = 10                                    # every leaf ends in '\n' (and holds none elsewhere: make_leaves' alphabet)
+            h_pin = torch.empty(total + 64, dtype=torch.uint8).pin_memory(); h_pin.copy_(src[:total + 64].cpu())
+            o_pin = torch.empty(nlog + 1, dtype=torch.int64).pin_memory(); o_pin.copy_(torch.from_numpy(offs_all.astype(np.int64)))
+            per = nlog // 16
             lg = N.MerkleLog(keep_leaf_digests=True)
+            lg.append([b"warm-up"]); lg.close()
+            lg = N.MerkleLog(keep_leaf_digests=True)
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
             for c in range(16):
-                part = h_leaves[c * (nlog // 16) * MERKLE_LEAF:]
-                N.check(lib.cg_merkle_log_append(lg.handle, part.ctypes.data, offs.ctypes.data, nlog // 16))
+                # offsets are absolute into the one pinned buffer (the library copies bytes[offsets[0], offsets[m]))
+                N.check(lib.cg_merkle_log_append(lg.handle, h_pin.data_ptr(), o_pin.data_ptr() + 8 * c * per, per))
+                if c == 7:
+                    half_root = lg.root()
             log_root = lg.root()
             dt = time.perf_counter() - t0
+            t1 = time.perf_counter(); path = lg.proof(nlog // 3); proof_ms = (time.perf_counter() - t1) * 1e3
+            t1 = time.perf_counter(); cons = lg.consistency(8 * per); cons_ms = (time.perf_counter() - t1) * 1e3
+            h_np = h_pin.numpy()
+            one_shot = N.merkle_root(h_np, offs_all[:16 * per + 1])
+            leaf3 = bytes(h_np[int(offs_all[nlog // 3]):int(offs_all[nlog // 3 + 1])])
+            # the same bytes as a day file: one buffer, split on the device (leaves = lines WITHOUT their '\n')
+            lj = N.MerkleLog(keep_leaf_digests=False)
             t1 = time.perf_counter()
-            path = lg.proof(nlog // 3)
-            proof_ms = (time.perf_counter() - t1) * 1e3
-            one_shot = N.merkle_root_fixed(h_leaves, MERKLE_LEAF, nlog)
-            merkle["log"] = {"leaves": nlog, "appends": 16, "leaves_per_s_from_host": nlog / dt, "root_equals_one_shot_tree": log_root == one_shot,
-                             "proof_len": len(path), "proof_ms": proof_ms,
-                             "proof_verifies": N.merkle_verify_proof(bytes(h_leaves[(nlog // 3) * MERKLE_LEAF:(nlog // 3 + 1) * MERKLE_LEAF]), nlog // 3, nlog, path, log_root)}
-            lg.close()
+            kl = C.c_uint64(0)
+            N.check(lib.cg_merkle_log_append_jsonl(lj.handle, h_pin.data_ptr(), int(offs_all[16 * per]), C.byref(kl)))
+            jroot = lj.root(); dj = time.perf_counter() - t1
+            sample = min(16 * per, 1 << 16)                    # oracle over a prefix (lines without '\n'), against the same prefix through the library
+            so = np.zeros(sample + 1, dtype=np.uint64); so[1:] = np.cumsum(lens[:sample] - 1)
+            sb = np.concatenate([h_np[int(offs_all[i]):int(offs_all[i + 1]) - 1] for i in range(sample)] + [np.zeros(64, dtype=np.uint8)])
+            ls = N.MerkleLog(keep_leaf_digests=False); ls.append_jsonl(h_np[:int(offs_all[sample])]); sroot = ls.root(); ls.close()
+            merkle["log"] = {"leaves": 16 * per, "appends": 16, "leaf_bytes": "ragged 64..320 (mean %.0f)" % float(lens.mean()), "host_memory": "pinned",
+                             "leaves_per_s_from_host": 16 * per / dt, "GBps_from_host": int(offs_all[16 * per]) / dt / 1e9,
+                             "root_equals_one_shot_tree": log_root == one_shot,
+                             "proof_len": len(path), "proof_ms": proof_ms, "proof_verifies": N.merkle_verify_proof(leaf3, nlog // 3, 16 * per, path, log_root),
+                             "consistency_len": len(cons), "consistency_ms": cons_ms,
+                             "consistency_verifies": N.merkle_verify_consistency(8 * per, 16 * per, half_root, log_root, cons) and O.merkle_verify_consistency(8 * per, 16 * per, half_root, log_root, cons),
+                             "jsonl": {"lines": int(kl.value), "bytes": int(offs_all[16 * per]), "lines_per_s_from_host": kl.value / dj,
+                                       "prefix_root_equals_oracle": sroot == O.merkle_root(sb, so), "prefix_lines": sample}}
+            lg.close(); lj.close()
+            del src, h_pin, o_pin
         del leaves, h_leaves
 
     # ---- C4 (BASELINE configs[3]): 10 M messages split over the ranks + the Merkle tree over the event log of THAT scan

@@ -196,6 +196,9 @@ typedef struct cg_merkle_log cg_merkle_log;
 CG_API int cg_merkle_log_create(cg_merkle_log **out, int keep_leaf_digests);
 CG_API void cg_merkle_log_destroy(cg_merkle_log *log);
 CG_API int cg_merkle_log_append(cg_merkle_log *log, const uint8_t *bytes, const uint64_t *offsets, uint64_t n);   /* host buffers */
+/* the day file itself (src/audit-trail.ts:151-179: JSON lines joined with "\n", trailing "\n" per flush): split at '\n' on the
+ * device, every line without its '\n' is one leaf (an unterminated last line counts); *out_lines = leaves appended */
+CG_API int cg_merkle_log_append_jsonl(cg_merkle_log *log, const uint8_t *bytes, uint64_t len, uint64_t *out_lines);
 CG_API int cg_merkle_log_size(const cg_merkle_log *log, uint64_t *out_n);
 CG_API int cg_merkle_log_root(cg_merkle_log *log, uint8_t out_root[32]);      /* == cg_merkle_root over every leaf appended so far */
 /* frontier: one digest per set bit of the size, largest subtree first; restore() resumes a log from it (no proofs) */
@@ -203,6 +206,11 @@ CG_API int cg_merkle_log_frontier(cg_merkle_log *log, uint8_t *out_frontier32, u
 CG_API int cg_merkle_log_restore(cg_merkle_log **out, uint64_t n, const uint8_t *frontier32, uint32_t count);
 /* RFC 6962 2.1.1 audit path of leaf `index` in the current tree (leaf level first); needs keep_leaf_digests */
 CG_API int cg_merkle_log_proof(cg_merkle_log *log, uint64_t index, uint8_t *out_path32, uint32_t path_cap, uint32_t *out_len);
+/* RFC 6962 2.1.2 consistency proof between the tree of the first first_size leaves and the current tree; needs keep_leaf_digests */
+CG_API int cg_merkle_log_consistency(cg_merkle_log *log, uint64_t first_size, uint8_t *out_path32, uint32_t path_cap, uint32_t *out_len);
+/* RFC 9162 2.1.4.2: *out_ok = 1 iff `path` proves that the tree (root_first, first_size) is a prefix of (root_second, second_size) */
+CG_API int cg_merkle_verify_consistency(uint64_t first_size, uint64_t second_size, const uint8_t root_first[32], const uint8_t root_second[32],
+                                        const uint8_t *path32, uint32_t path_len, int *out_ok);
 /* RFC 9162 2.1.3.2: *out_ok = 1 iff `path` proves that leaf_bytes is entry `index` of the tree of tree_size leaves with this root */
 CG_API int cg_merkle_verify_proof(const uint8_t *leaf_bytes, uint64_t leaf_len, uint64_t index, uint64_t tree_size,
                                   const uint8_t *path32, uint32_t path_len, const uint8_t root[32], int *out_ok);

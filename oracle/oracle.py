@@ -364,3 +364,54 @@ def merkle_verify_path(leaf: bytes, index: int, tree_size: int, path, root: byte
         fn >>= 1
         sn >>= 1
     return sn == 0 and r == root
+
+
+def merkle_consistency_proof(leaves, first_size: int):
+    """PROOF(m, D[n]) of RFC 6962 2.1.2."""
+    hs = [merkle_leaf_hash(x) for x in leaves]
+
+    def sub(m, d, b):
+        n = len(d)
+        if m == n:
+            return [] if b else [_mth(d)]
+        k = 1
+        while k * 2 < n:
+            k *= 2
+        if m <= k:
+            return sub(m, d[:k], b) + [_mth(d[k:])]
+        return sub(m - k, d[k:], False) + [_mth(d[:k])]
+    if not 0 < first_size <= len(hs):
+        raise ValueError("first_size out of range")
+    return sub(first_size, hs, True)
+
+
+def merkle_verify_consistency(first_size: int, second_size: int, root_first: bytes, root_second: bytes, path) -> bool:
+    """RFC 9162 2.1.4.2."""
+    path = list(path)
+    if first_size == 0 or first_size > second_size:
+        return False
+    if first_size == second_size:
+        return not path and root_first == root_second
+    if not path:
+        return False
+    if first_size & (first_size - 1) == 0:
+        path = [root_first] + path
+    fn, sn = first_size - 1, second_size - 1
+    while fn & 1:
+        fn >>= 1
+        sn >>= 1
+    fr = sr = path[0]
+    for c in path[1:]:
+        if sn == 0:
+            return False
+        if (fn & 1) or fn == sn:
+            fr = merkle_node_hash(c, fr)
+            sr = merkle_node_hash(c, sr)
+            while not (fn & 1) and fn != 0:
+                fn >>= 1
+                sn >>= 1
+        else:
+            sr = merkle_node_hash(sr, c)
+        fn >>= 1
+        sn >>= 1
+    return sn == 0 and fr == root_first and sr == root_second

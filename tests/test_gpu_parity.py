@@ -427,6 +427,130 @@ def test_merkle_log_append_frontier_and_proofs(N, oracle):
         lg.close()
 
 
+def test_merkle_ct_reference_vectors_on_the_device(N, oracle):
+    """The Certificate Transparency known answers (tests/golden/ct_merkle_vectors.json) through the C ABI: roots of the
+    first k leaves (one-shot and incremental log), audit paths, consistency proofs, both verifiers."""
+    import json
+    v = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ct_merkle_vectors.json")))
+    leaves = [bytes.fromhex(x) for x in v["leaves_hex"]]
+    roots = [bytes.fromhex(x) for x in v["roots_hex"]]
+    log = N.MerkleLog()
+    for k in range(1, 9):
+        data, off = N.pack(leaves[:k])
+        assert N.merkle_root(data, off.astype(np.uint64)) == roots[k - 1]
+        log.append(leaves[k - 1:k])
+        assert log.root() == roots[k - 1]
+    for c in v["inclusion"]:
+        lg = N.MerkleLog(); lg.append(leaves[:c["size"]])
+        p = lg.proof(c["index"])
+        assert [x.hex() for x in p] == c["path_hex"]
+        assert N.merkle_verify_proof(leaves[c["index"]], c["index"], c["size"], p, roots[c["size"] - 1])
+        lg.close()
+    for c in v["consistency"]:
+        lg = N.MerkleLog(); lg.append(leaves[:c["second"]])
+        p = lg.consistency(c["first"])
+        assert [x.hex() for x in p] == c["path_hex"]
+        assert N.merkle_verify_consistency(c["first"], c["second"], roots[c["first"] - 1], roots[c["second"] - 1], p)
+        lg.close()
+    log.close()
+
+
+def test_merkle_consistency_proofs(N, oracle):
+    """RFC 6962 2.1.2 proofs from the log equal the oracle's for every (m, n) of a small tree, and verify (device verifier,
+    RFC 9162 2.1.4.2, and the oracle's); on a 70k-leaf log the proofs verify against roots recorded along the way and
+    any tampering (root, path length, sizes) is rejected."""
+    rng = np.random.default_rng(62)
+    leaves = [bytes(rng.integers(0, 256, int(rng.integers(0, 120)), dtype=np.uint8)) for _ in range(70)]
+    log = N.MerkleLog(); roots = [None]
+    for x in leaves:
+        log.append([x]); roots.append(log.root())
+    for n in (1, 2, 3, 7, 8, 9, 33, 64, 70):
+        lg = N.MerkleLog(); lg.append(leaves[:n])
+        for m in range(1, n + 1):
+            p = lg.consistency(m)
+            assert p == oracle.merkle_consistency_proof(leaves[:n], m), (m, n)
+            assert N.merkle_verify_consistency(m, n, roots[m], roots[n], p)
+            assert oracle.merkle_verify_consistency(m, n, roots[m], roots[n], p)
+            if m < n:
+                assert not N.merkle_verify_consistency(m, n, roots[m], roots[n - 1] if n - 1 != m else roots[n][::-1], p)
+                assert not N.merkle_verify_consistency(m, n, roots[m][::-1], roots[n], p)
+                assert not N.merkle_verify_consistency(m, n, roots[m], roots[n], p[:-1])
+                assert not N.merkle_verify_consistency(m, n, roots[m], roots[n], p + [p[-1]])
+        assert not N.merkle_verify_consistency(0, n, roots[1], roots[n], [])
+        lg.close()
+    log.close()
+    big = N.MerkleLog(); marks = {}
+    n = 0
+    for chunk in (1, 4095, 1, 32768, 12345, 20000):
+        data = W.make_leaves(chunk, 48, seed=n + 1).numpy()
+        off = (np.arange(chunk + 1, dtype=np.uint64) * 48)
+        big.append_packed(data, off); n += chunk
+        marks[n] = big.root()
+    for m, rm in marks.items():
+        p = big.consistency(m)
+        assert N.merkle_verify_consistency(m, n, rm, marks[n], p) and oracle.merkle_verify_consistency(m, n, rm, marks[n], p)
+        if m < n:                                            # wrong sizes: whatever RFC 9162's walk says (the oracle), mostly "no"
+            for mm, nn in ((m, n - 1), (m + 1, n), (m, n + 1), (m - 1, n), (m, 2 * n)):
+                assert N.merkle_verify_consistency(mm, nn, rm, marks[n], p) == oracle.merkle_verify_consistency(mm, nn, rm, marks[n], p), (mm, nn)
+            assert not N.merkle_verify_consistency(m + 1, n, rm, marks[n], p)
+    big.close()
+
+
+def test_merkle_log_from_jsonl_bytes(N, oracle):
+    """The event log as it lies on disk (JSON lines, src/audit-trail.ts:151-179): split on the device; every line without
+    its newline is a leaf.  Empty lines, an unterminated last line, lines across the 4 KB pieces of the split kernel."""
+    rng = np.random.default_rng(151)
+    lines = [b'{"id":"%d","verdict":"allow","pad":"%s"}' % (i, b"x" * int(rng.integers(0, 900))) for i in range(3000)]
+    lines[5] = b""; lines[6] = b""; lines[100] = b"y" * 9000; lines[2999] = b"tail"
+    blob = b"\n".join(lines) + b"\n"
+    data, off = N.pack(lines)
+    want = oracle.merkle_root(data, off.astype(np.uint64))
+    log = N.MerkleLog(keep_leaf_digests=False)
+    assert log.append_jsonl(blob) == 3000 and log.size() == 3000 and log.root() == want
+    log.close()
+    log = N.MerkleLog()                                   # in flushes that end mid-file, last one unterminated
+    cut = [0, 1, 4096, 4097, 50000, len(blob) - 1]
+    cut = [blob.rfind(b"\n", 0, c) + 1 for c in cut] + [len(blob) - 1]
+    total = 0
+    for a, b in zip(cut[:-1], cut[1:]):
+        total += log.append_jsonl(blob[a:b])
+    assert total == 3000 and log.root() == want
+    assert log.append_jsonl(b"") == 0 and log.append_jsonl(b"\n") == 1 and log.size() == 3001
+    p = log.proof(100)
+    assert N.merkle_verify_proof(lines[100], 100, 3001, p, log.root())
+    log.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 1023, 1024, 1025, 32767, 32768, 32769, 200001])
+def test_merkle_subtree_reduction_sizes(N, oracle, n):
+    """log roots over n leaves for n around the warp-shuffle reduction's boundaries (32 per warp, 2^15 switch to the level kernels)"""
+    data = W.make_leaves(n, 40, seed=n).numpy()
+    off = np.arange(n + 1, dtype=np.uint64) * 40
+    log = N.MerkleLog(keep_leaf_digests=(n < 40000))
+    log.append_packed(data, off)
+    assert log.root() == oracle.merkle_root_fixed(data, 40, n) == N.merkle_root(data, off)
+    log.close()
+
+
+def test_sha256_ragged_alignment(N, oracle):
+    """word-granular ragged leaves: every start alignment mod 16 x every length 0..200"""
+    rng = np.random.default_rng(256)
+    msgs = []
+    for pad in range(16):
+        msgs.append(bytes(rng.integers(0, 256, pad, dtype=np.uint8)))
+        for ln in list(range(0, 70)) + [119, 120, 127, 128, 129, 200]:
+            msgs.append(bytes(rng.integers(0, 256, ln, dtype=np.uint8)))
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    data = np.frombuffer(b"".join(msgs) + b"\0" * 64, dtype=np.uint8).copy()
+    out = N.sha256_batch(data, off)
+    for i, m in enumerate(msgs):
+        assert out[i].tobytes() == hashlib.sha256(m).digest(), (i, len(m))
+    assert N.merkle_root(data, off) == oracle.merkle_root(data, off)
+    sub = off[7:]                                          # offsets[0] != 0
+    assert N.merkle_root(data, sub) == oracle.merkle_root(data, sub)
+
+
 def test_non_ascii_rule_packs_on_the_kernels(N, oracle):
     """CJK / Cyrillic / Hangul literal alternations, classes with CJK ranges, `.*` between literals and the
     lazy PEM block: policy words, hits and resolved spans equal the oracle's."""

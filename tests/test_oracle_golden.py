@@ -218,3 +218,54 @@ def test_merkle_audit_paths_of_the_oracle(oracle):
             assert not oracle.merkle_verify_path(ls[i] + b"!", i, n, p, root)
             if n > 1:
                 assert not oracle.merkle_verify_path(ls[i], (i + 1) % n, n, p, root) or ls[i] == ls[(i + 1) % n]
+
+
+# ------------------------------------------------------------------- RFC 6962 known answers (CT reference vectors)
+
+def _ct():
+    import json
+    v = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ct_merkle_vectors.json")))
+    return v, [bytes.fromhex(x) for x in v["leaves_hex"]]
+
+
+def test_merkle_ct_reference_roots(oracle):
+    """The oracle's tree convention pinned on the published Certificate Transparency test vectors: the root over the
+    first k of the 8 fixed leaves, k = 1..8, from both the level-wise builder and the recursive RFC 6962 restatement."""
+    v, leaves = _ct()
+    for k in range(1, 9):
+        off = np.zeros(k + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in leaves[:k]])
+        data = np.frombuffer(b"".join(leaves[:k]) + b"\0" * 64, dtype=np.uint8).copy()
+        assert oracle.merkle_root(data, off).hex() == v["roots_hex"][k - 1]
+        assert oracle.merkle_root_rfc6962(data, off).hex() == v["roots_hex"][k - 1]
+    assert oracle.merkle_root(np.zeros(64, dtype=np.uint8), np.zeros(1, dtype=np.uint64)).hex() == \
+        "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"                # RFC 6962 2.1: MTH({}) = SHA-256()
+
+
+def test_merkle_ct_reference_proofs(oracle):
+    v, leaves = _ct()
+    roots = [bytes.fromhex(x) for x in v["roots_hex"]]
+    for c in v["inclusion"]:
+        p = oracle.merkle_audit_path(leaves[:c["size"]], c["index"])
+        assert [x.hex() for x in p] == c["path_hex"]
+        assert oracle.merkle_verify_path(leaves[c["index"]], c["index"], c["size"], p, roots[c["size"] - 1])
+    for c in v["consistency"]:
+        p = oracle.merkle_consistency_proof(leaves[:c["second"]], c["first"])
+        assert [x.hex() for x in p] == c["path_hex"]
+        assert oracle.merkle_verify_consistency(c["first"], c["second"], roots[c["first"] - 1], roots[c["second"] - 1], p)
+
+
+def test_merkle_consistency_every_pair_small(oracle):
+    rng = np.random.default_rng(9162)
+    leaves = [bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8)) for _ in range(41)]
+    hs = [oracle.merkle_leaf_hash(x) for x in leaves]
+    roots = [None] + [oracle._mth(hs[:k]) for k in range(1, 42)]
+    for n in range(1, 42):
+        for m in range(1, n + 1):
+            p = oracle.merkle_consistency_proof(leaves[:n], m)
+            assert oracle.merkle_verify_consistency(m, n, roots[m], roots[n], p)
+            if m < n:
+                assert not oracle.merkle_verify_consistency(m, n, roots[m], roots[n - 1] if n - 1 >= 1 and n - 1 != m else roots[n][::-1], p)
+                assert not oracle.merkle_verify_consistency(m, n, roots[m][::-1], roots[n], p)
+                assert not oracle.merkle_verify_consistency(m, n, roots[m], roots[n], p[:-1])
+                assert not oracle.merkle_verify_consistency(m, n, roots[m], roots[n], p + [p[-1]])

@@ -51,6 +51,7 @@ EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_c
            "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_scan_join", "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch",
            "cg_merkle_log_create", "cg_merkle_log_destroy", "cg_merkle_log_append", "cg_merkle_log_size", "cg_merkle_log_root",
            "cg_merkle_log_frontier", "cg_merkle_log_restore", "cg_merkle_log_proof", "cg_merkle_verify_proof",
+           "cg_merkle_log_append_jsonl", "cg_merkle_log_consistency", "cg_merkle_verify_consistency",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -97,6 +98,9 @@ def load():
     L.cg_merkle_log_restore.argtypes = [vp, u64, vp, u32]; L.cg_merkle_log_restore.restype = i32
     L.cg_merkle_log_proof.argtypes = [vp, u64, vp, u32, vp]; L.cg_merkle_log_proof.restype = i32
     L.cg_merkle_verify_proof.argtypes = [vp, u64, u64, u64, vp, u32, vp, vp]; L.cg_merkle_verify_proof.restype = i32
+    L.cg_merkle_log_append_jsonl.argtypes = [vp, vp, u64, vp]; L.cg_merkle_log_append_jsonl.restype = i32
+    L.cg_merkle_log_consistency.argtypes = [vp, u64, vp, u32, vp]; L.cg_merkle_log_consistency.restype = i32
+    L.cg_merkle_verify_consistency.argtypes = [u64, u64, vp, vp, vp, u32, vp]; L.cg_merkle_verify_consistency.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
     L.cg_ruleset_destroy.argtypes = [vp]; L.cg_ruleset_destroy.restype = None
     L.cg_ruleset_get_info.argtypes = [vp, C.POINTER(cg_ruleset_info)]; L.cg_ruleset_get_info.restype = i32
@@ -354,6 +358,25 @@ class MerkleLog:
         data = np.frombuffer(b"".join(leaves) + b"\0" * 64, dtype=np.uint8).copy()
         check(load().cg_merkle_log_append(self.handle, data.ctypes.data, off.ctypes.data, len(leaves)))
 
+    def append_packed(self, data: np.ndarray, off64: np.ndarray):
+        """leaves already packed: data uint8, off64 uint64 (m + 1 entries)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off64 = np.ascontiguousarray(off64, dtype=np.uint64)
+        check(load().cg_merkle_log_append(self.handle, data.ctypes.data, off64.ctypes.data, len(off64) - 1))
+
+    def append_jsonl(self, data) -> int:
+        """the day file's bytes (JSON lines, src/audit-trail.ts:151-179); returns the number of lines appended."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        k = C.c_uint64(0)
+        check(load().cg_merkle_log_append_jsonl(self.handle, buf.ctypes.data if buf.size else None, buf.size, C.byref(k)))
+        return k.value
+
+    def consistency(self, first_size: int):
+        out = np.zeros((64, 32), dtype=np.uint8)
+        k = C.c_uint32(0)
+        check(load().cg_merkle_log_consistency(self.handle, first_size, out.ctypes.data, 64, C.byref(k)))
+        return [out[i].tobytes() for i in range(k.value)]
+
     def size(self) -> int:
         n = C.c_uint64(0)
         check(load().cg_merkle_log_size(self.handle, C.byref(n)))
@@ -380,6 +403,15 @@ class MerkleLog:
         if self.handle:
             load().cg_merkle_log_destroy(self.handle)
             self.handle = None
+
+
+def merkle_verify_consistency(first_size: int, second_size: int, root_first: bytes, root_second: bytes, path) -> bool:
+    p = np.frombuffer(b"".join(path) + b"\0" * 32, dtype=np.uint8).copy()
+    r1 = np.frombuffer(root_first, dtype=np.uint8).copy()
+    r2 = np.frombuffer(root_second, dtype=np.uint8).copy()
+    ok = C.c_int(0)
+    check(load().cg_merkle_verify_consistency(first_size, second_size, r1.ctypes.data, r2.ctypes.data, p.ctypes.data, len(path), C.byref(ok)))
+    return bool(ok.value)
 
 
 def merkle_verify_proof(leaf: bytes, index: int, tree_size: int, path, root: bytes) -> bool:

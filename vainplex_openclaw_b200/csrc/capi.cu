@@ -33,7 +33,7 @@ struct Ctx {
   cg_stats stats{};
   uint64_t launches = 0;
   // grow-only staging in HBM
-  uint8_t* d_bytes = nullptr; size_t cap_bytes = 0;
+  uint8_t* d_bytes = nullptr; size_t cap_bytes = 0; uint8_t* d_bytes_raw = nullptr;   // d_bytes = d_bytes_raw + 256: readable in front (sha_words)
   uint32_t* d_off32 = nullptr; size_t cap_off32 = 0;
   uint64_t* d_off64 = nullptr; size_t cap_off64 = 0;
   uint64_t* d_words = nullptr; size_t cap_words = 0;
@@ -62,6 +62,19 @@ int grow(T** p, size_t* cap, size_t need_elems) {
   cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
   if (e != cudaSuccess) { *p = nullptr; return cuda_fail(e, "cudaMalloc"); }
   *cap = n;
+  return CG_OK;
+}
+
+// the staging buffer for message / leaf bytes: 256 readable bytes in front of it and 64 + slack behind what is asked for
+int grow_bytes(size_t need) {
+  if (need <= G.cap_bytes && G.d_bytes) return CG_OK;
+  if (G.d_bytes_raw) cudaFree(G.d_bytes_raw);
+  G.d_bytes_raw = G.d_bytes = nullptr; G.cap_bytes = 0;
+  const size_t n = need + need / 4 + 64;
+  cudaError_t e = cudaMalloc((void**)&G.d_bytes_raw, n + 512);
+  if (e != cudaSuccess) { G.d_bytes_raw = nullptr; return cuda_fail(e, "cudaMalloc"); }
+  cudaMemset(G.d_bytes_raw, 0, 256);
+  G.d_bytes = G.d_bytes_raw + 256; G.cap_bytes = n;
   return CG_OK;
 }
 
@@ -182,7 +195,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
   int rc;
   if (n && (rc = check_offsets(offsets, n))) return rc;
   const size_t first = n ? offsets[0] : 0, total = n ? offsets[n] : 0;
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow_bytes(total + 64))) return rc;
   if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
   if ((rc = grow(&G.d_words, &G.cap_words, (size_t)n + 1))) return rc;
   cudaStream_t st = G.stream;
@@ -225,7 +238,7 @@ int scan_host_chunked(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offs
   int rc;
   if ((rc = check_offsets(offsets, n))) return rc;
   const size_t total = offsets[n];
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow_bytes(total + 64))) return rc;
   if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
   if ((rc = grow(&G.d_words, &G.cap_words, (size_t)n + 1))) return rc;
   if (!G.s_h2d) {
@@ -326,7 +339,7 @@ void cg_shutdown(void) {
   cudaFree(G.d_redact_out); cudaFree(G.d_redact_meta); cudaFree(G.d_verdicts);
   if (G.h_chunk_counters) cudaFreeHost(G.h_chunk_counters);
   if (G.s_h2d) { cudaStreamDestroy(G.s_h2d); cudaStreamDestroy(G.s_d2h); for (int c = 0; c < Ctx::kChunks; c++) { cudaEventDestroy(G.e_h2d[c]); cudaEventDestroy(G.e_done[c]); } }
-  cudaFree(G.d_bytes); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
+  cudaFree(G.d_bytes_raw); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
   cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); cudaStreamDestroy(G.stream);
   G = Ctx();
 }
@@ -718,7 +731,7 @@ int cg_sha256_batch(const uint8_t* bytes, const uint64_t* offsets, uint32_t n, u
   if (!n) return CG_OK;
   if (!offsets || !out) return fail(CG_ERR_INVALID_ARG, "null argument");
   size_t total = offsets[n]; int rc;
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow_bytes(total + 64))) return rc;
   if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)n + 1))) return rc;
   if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)n * 8))) return rc;
   cudaStream_t st = G.stream;
@@ -737,9 +750,12 @@ namespace {
 int fold_levels(uint64_t n, uint64_t stop_at, int cur, cudaStream_t st, uint32_t max_levels = 64) {
   uint32_t lv = 0;
   while (n > stop_at && lv < max_levels) {
-    int k = launch_merkle_level(G.d_dig[cur], n, G.d_dig[cur ^ 1], st);
+    // large levels: one kernel per level, every lane busy; from 2^15 nodes down: up to five levels per kernel inside warps
+    uint32_t step = 1;
+    if (n <= (1u << 15)) { step = 5; while (step > 1 && (lv + step > max_levels || ((n + (1ull << step) - 1) >> step) < stop_at)) step--; }
+    int k = step > 1 ? launch_merkle_reduce(G.d_dig[cur], n, step, G.d_dig[cur ^ 1], st) : launch_merkle_level(G.d_dig[cur], n, G.d_dig[cur ^ 1], st);
     G.launches += k; G.stats.kernel_launches += k;
-    n = (n + 1) / 2; cur ^= 1; lv++;
+    n = (n + (1ull << step) - 1) >> step; cur ^= 1; lv += step;
   }
   return cur;
 }
@@ -748,7 +764,7 @@ int empty_root(uint8_t out[32]) {
   int rc;
   if ((rc = grow(&G.d_off64, &G.cap_off64, 2))) return rc;
   if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], 8))) return rc;
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, 64))) return rc;
+  if ((rc = grow_bytes(64))) return rc;
   CU(cudaMemsetAsync(G.d_off64, 0, 16, G.stream));
   int k = launch_sha256_batch(G.d_bytes, G.d_off64, 1, (uint8_t*)G.d_dig[0], G.stream);
   G.launches += k; G.stats.kernel_launches += k;
@@ -765,7 +781,7 @@ int cg_merkle_root(const uint8_t* bytes, const uint64_t* offsets, uint64_t n, ui
   if (n == 0) return empty_root(out_root);
   if (!offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
   size_t total = offsets[n]; int rc;
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow_bytes(total + 64))) return rc;
   if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)n + 1))) return rc;
   if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)n * 8))) return rc;
   if ((rc = grow(&G.d_dig[1], &G.cap_dig[1], (size_t)(n + 1) / 2 * 8 + 8))) return rc;
@@ -790,7 +806,7 @@ int cg_merkle_root_fixed(const uint8_t* bytes, uint64_t leaf_len, uint64_t n, ui
   if (!out_root) return fail(CG_ERR_INVALID_ARG, "null argument");
   if (n == 0) return empty_root(out_root);
   size_t total = (size_t)leaf_len * n; int rc;
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
+  if ((rc = grow_bytes(total + 64))) return rc;
   if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)n * 8))) return rc;
   if ((rc = grow(&G.d_dig[1], &G.cap_dig[1], (size_t)(n + 1) / 2 * 8 + 8))) return rc;
   cudaStream_t st = G.stream;
@@ -846,8 +862,11 @@ int log_range_root(cg_merkle_log* L, const uint32_t* d_in, uint64_t cnt, uint32_
   if ((rc = grow(&L->d_b, &L->cap_b, (size_t)(cnt + 3) / 4 * 8 + 8))) return rc;
   const uint32_t* src = d_in; uint32_t* dst = L->d_a; uint64_t m = cnt;
   while (m > 1) {
-    int k = launch_merkle_level(src, m, dst, st); G.launches += k; G.stats.kernel_launches += k;
-    m = (m + 1) / 2; src = dst; dst = dst == L->d_a ? L->d_b : L->d_a;
+    uint32_t step = 1;
+    if (m <= (1u << 15)) { step = 5; while (step > 1 && (m >> (step - 1)) == 0) step--; while (step > 1 && ((m + (1ull << (step - 1)) - 1) >> (step - 1)) == 1) step--; }
+    int k = step > 1 ? launch_merkle_reduce(src, m, step, dst, st) : launch_merkle_level(src, m, dst, st);
+    G.launches += k; G.stats.kernel_launches += k;
+    m = (m + (1ull << step) - 1) >> step; src = dst; dst = dst == L->d_a ? L->d_b : L->d_a;
   }
   CU(cudaMemcpyAsync(d_out, src, 32, cudaMemcpyDeviceToDevice, st));
   return CG_OK;
@@ -907,17 +926,10 @@ int cg_merkle_log_frontier(cg_merkle_log* L, uint8_t* out_frontier32, uint32_t* 
   return CG_OK;
 }
 
-int cg_merkle_log_append(cg_merkle_log* L, const uint8_t* bytes, const uint64_t* offsets, uint64_t m) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  int rc = log_check(L); if (rc) return rc;
-  if (!m) return CG_OK;
-  if (!offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
-  if (L->n + m < L->n) return fail(CG_ERR_TOO_LARGE, "log size overflows 64 bits");
-  cudaStream_t st = G.stream;
-  const size_t total = offsets[m];
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, total + 64))) return rc;
-  if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)m + 1))) return rc;
-  uint32_t* d_dig;                                          // where this batch's leaf digests go
+namespace {
+// room for m more leaf digests; returns where they go
+int log_digest_room(cg_merkle_log* L, uint64_t m, cudaStream_t st, uint32_t** out) {
+  int rc;
   if (L->keep) {
     if (L->n + m > L->cap_leaves) {                         // grow the digest store (amortised doubling), keeping what is there
       uint64_t cap = std::max<uint64_t>(L->n + m, L->cap_leaves * 2); uint32_t* nd = nullptr;
@@ -925,16 +937,17 @@ int cg_merkle_log_append(cg_merkle_log* L, const uint8_t* bytes, const uint64_t*
       if (L->n) CU(cudaMemcpyAsync(nd, L->d_leaves, (size_t)L->n * 32, cudaMemcpyDeviceToDevice, st));
       CU(cudaStreamSynchronize(st)); cudaFree(L->d_leaves); L->d_leaves = nd; L->cap_leaves = cap;
     }
-    d_dig = L->d_leaves + (size_t)L->n * 8;
+    *out = L->d_leaves + (size_t)L->n * 8;
   } else {
     if ((rc = grow(&L->d_new, &L->cap_new, (size_t)m * 8))) return rc;
-    d_dig = L->d_new;
+    *out = L->d_new;
   }
-  if (total) CU(cudaMemcpyAsync(G.d_bytes, bytes, total, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(G.d_off64, offsets, ((size_t)m + 1) * 8, cudaMemcpyHostToDevice, st));
-  int k = launch_merkle_leaves_var(G.d_bytes, G.d_off64, m, d_dig, st);
-  G.launches += k; G.stats.kernel_launches += k; G.stats.merkle_leaves += m;
-  // cut [n, n+m) into aligned perfect blocks (block size <= lowest set bit of its position), reduce each, carry into the frontier
+  return CG_OK;
+}
+// m new leaf digests at d_dig: cut [n, n+m) into aligned perfect blocks (block size <= lowest set bit of its position),
+// reduce each, carry into the frontier
+int log_absorb(cg_merkle_log* L, const uint32_t* d_dig, uint64_t m, cudaStream_t st) {
+  int rc, k;
   uint64_t pos = L->n, rem = m;
   while (rem) {
     uint64_t s = pos ? (pos & (~pos + 1)) : (1ull << 63);
@@ -952,6 +965,79 @@ int cg_merkle_log_append(cg_merkle_log* L, const uint8_t* bytes, const uint64_t*
   CU(cudaStreamSynchronize(st));
   L->n += m;
   return CG_OK;
+}
+int ensure_copy_streams() {
+  if (G.s_h2d) return CG_OK;
+  const int C = Ctx::kChunks;
+  CU(cudaStreamCreateWithFlags(&G.s_h2d, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&G.s_d2h, cudaStreamNonBlocking));
+  for (int c = 0; c < C; c++) { CU(cudaEventCreateWithFlags(&G.e_h2d[c], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&G.e_done[c], cudaEventDisableTiming)); }
+  CU(cudaMallocHost((void**)&G.h_chunk_counters, (size_t)C * kCounterWords * 4));
+  return CG_OK;
+}
+}  // namespace
+
+int cg_merkle_log_append(cg_merkle_log* L, const uint8_t* bytes, const uint64_t* offsets, uint64_t m) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = log_check(L); if (rc) return rc;
+  if (!m) return CG_OK;
+  if (!offsets) return fail(CG_ERR_INVALID_ARG, "null argument");
+  for (uint64_t i = 0; i < m; i++) if (offsets[i + 1] < offsets[i]) return fail(CG_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  if (L->n + m < L->n) return fail(CG_ERR_TOO_LARGE, "log size overflows 64 bits");
+  cudaStream_t st = G.stream;
+  const size_t first = offsets[0], total = offsets[m];
+  if ((rc = grow_bytes(total + 64))) return rc;
+  if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)m + 1))) return rc;
+  if ((rc = ensure_copy_streams())) return rc;
+  uint32_t* d_dig;                                          // where this batch's leaf digests go
+  if ((rc = log_digest_room(L, m, st, &d_dig))) return rc;
+  CU(cudaStreamSynchronize(st));                            // (whatever still read the staging buffer is done)
+  CU(cudaMemcpyAsync(G.d_off64, offsets, ((size_t)m + 1) * 8, cudaMemcpyHostToDevice, G.s_h2d));
+  // the leaf bytes go over in pieces on the copy stream; the leaf kernel of piece c runs while piece c + 1 is still in flight
+  const int C = (total - first) > ((size_t)4 << 20) ? Ctx::kChunks : 1;
+  const uint64_t per = (m + C - 1) / C;
+  for (int c = 0; c < C; c++) {
+    const uint64_t m0 = std::min<uint64_t>((uint64_t)c * per, m), m1 = std::min<uint64_t>((uint64_t)(c + 1) * per, m);
+    if (m1 <= m0) break;
+    const size_t b0 = offsets[m0], b1 = offsets[m1];
+    if (b1 > b0) CU(cudaMemcpyAsync(G.d_bytes + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, G.s_h2d));
+    CU(cudaEventRecord(G.e_h2d[c], G.s_h2d));
+    CU(cudaStreamWaitEvent(st, G.e_h2d[c], 0));
+    int k = launch_merkle_leaves_var(G.d_bytes, G.d_off64 + m0, m1 - m0, d_dig + (size_t)m0 * 8, st);
+    G.launches += k; G.stats.kernel_launches += k;
+  }
+  G.stats.merkle_leaves += m;
+  return log_absorb(L, d_dig, m, st);
+}
+
+/* The event log as it lies on disk (src/audit-trail.ts:151-179: one JSON.stringify(record) per line, records joined with
+ * "\n", a trailing "\n" per flush): the buffer is split at '\n' ON THE DEVICE, every line (without its '\n') is a leaf. */
+int cg_merkle_log_append_jsonl(cg_merkle_log* L, const uint8_t* bytes, uint64_t len, uint64_t* out_lines) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = log_check(L); if (rc) return rc;
+  if (out_lines) *out_lines = 0;
+  if (!len) return CG_OK;
+  if (!bytes) return fail(CG_ERR_INVALID_ARG, "null argument");
+  cudaStream_t st = G.stream;
+  const uint32_t n_pieces = (uint32_t)((len + 4095) / 4096);
+  if ((rc = grow_bytes((size_t)len + 64))) return rc;
+  if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n_pieces + 4))) return rc;          // newline counts per 4 KB piece
+  if ((rc = grow(&G.d_off64, &G.cap_off64, 2))) return rc;
+  CU(cudaMemcpyAsync(G.d_bytes, bytes, len, cudaMemcpyHostToDevice, st));
+  uint64_t* d_total = G.d_off64;                           // (re-grown below once the line count is known)
+  int k = launch_newline_split(G.d_bytes, len, G.d_off32, d_total, st);
+  uint64_t n_lines = 0;
+  CU(cudaMemcpyAsync(&n_lines, d_total, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (!n_lines) return CG_OK;
+  if (L->n + n_lines < L->n) return fail(CG_ERR_TOO_LARGE, "log size overflows 64 bits");
+  if ((rc = grow(&G.d_off64, &G.cap_off64, (size_t)n_lines + 1))) return rc;
+  k += launch_newline_starts(G.d_bytes, len, G.d_off32, G.d_off64, n_lines, st);
+  uint32_t* d_dig;
+  if ((rc = log_digest_room(L, n_lines, st, &d_dig))) return rc;
+  k += launch_merkle_leaves_var(G.d_bytes, G.d_off64, n_lines, d_dig, st, /*trim_newline=*/true);
+  G.launches += k; G.stats.kernel_launches += k; G.stats.merkle_leaves += n_lines;
+  if (out_lines) *out_lines = n_lines;
+  return log_absorb(L, d_dig, n_lines, st);
 }
 
 int cg_merkle_log_root(cg_merkle_log* L, uint8_t out_root[32]) {
@@ -994,13 +1080,67 @@ int cg_merkle_log_proof(cg_merkle_log* L, uint64_t index, uint8_t* out_path32, u
   return CG_OK;
 }
 
+/* RFC 6962 2.1.2: PROOF(m, D[n]) -- the nodes that show the tree of the first m leaves is a prefix of the current one. */
+int cg_merkle_log_consistency(cg_merkle_log* L, uint64_t first_size, uint8_t* out_path32, uint32_t path_cap, uint32_t* out_len) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = log_check(L); if (rc) return rc;
+  if (!out_len) return fail(CG_ERR_INVALID_ARG, "null argument");
+  if (!L->keep) return fail(CG_ERR_UNSUPPORTED, "log was created without leaf digests (or restored from a frontier): no proofs");
+  if (first_size == 0 || first_size > L->n) return fail(CG_ERR_INVALID_ARG, "first_size must be in [1, size of the log]");
+  // SUBPROOF(m, D[lo:hi], b): k = largest power of two < hi - lo; m <= k: recurse left, then MTH(D[lo+k:hi]);
+  // else recurse right with b = false, then MTH(D[lo:lo+k]); m == hi - lo: {} if b else {MTH(D[lo:hi])}
+  std::vector<std::pair<uint64_t, uint64_t>> ranges;      // in proof order
+  {
+    std::vector<std::pair<uint64_t, uint64_t>> tail;       // appended after the recursion, innermost first
+    uint64_t lo = 0, hi = L->n, m = first_size; bool b = true;
+    while (m != hi - lo) {
+      uint64_t k = 1; while (k * 2 < hi - lo) k *= 2;
+      if (m <= k) { tail.push_back({lo + k, hi}); hi = lo + k; }
+      else { tail.push_back({lo, lo + k}); lo += k; m -= k; b = false; }
+    }
+    if (!b) ranges.push_back({lo, hi});
+    for (size_t i = tail.size(); i-- > 0;) ranges.push_back(tail[i]);
+  }
+  *out_len = (uint32_t)ranges.size();
+  if (ranges.size() > path_cap || ranges.size() > 64 || (ranges.size() && !out_path32)) return fail(CG_ERR_CAPACITY, "path buffer too small");
+  cudaStream_t st = G.stream;
+  for (size_t i = 0; i < ranges.size(); i++)
+    if ((rc = log_range_root(L, L->d_leaves + (size_t)ranges[i].first * 8, ranges[i].second - ranges[i].first, L->d_tmp + 8 * i, st))) return rc;
+  if (!ranges.empty()) CU(cudaMemcpyAsync(out_path32, L->d_tmp, ranges.size() * 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return CG_OK;
+}
+
+/* RFC 9162 2.1.4.2: *out_ok = 1 iff `path` proves that the tree with root_first over first_size leaves is a prefix of the tree
+ * with root_second over second_size leaves (node hashes on the device, as everywhere in this library) */
+int cg_merkle_verify_consistency(uint64_t first_size, uint64_t second_size, const uint8_t root_first[32], const uint8_t root_second[32],
+                                 const uint8_t* path32, uint32_t path_len, int* out_ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!out_ok || !root_first || !root_second || (path_len && !path32) || path_len > 64) return fail(CG_ERR_INVALID_ARG, "bad argument");
+  int rc; cudaStream_t st = G.stream;
+  if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)(path_len + 4) * 8))) return rc;
+  uint32_t* d_r1 = G.d_dig[0]; uint32_t* d_r2 = d_r1 + 8; uint32_t* d_ok = d_r2 + 8; uint32_t* d_path = d_ok + 8;
+  CU(cudaMemcpyAsync(d_r1, root_first, 32, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_r2, root_second, 32, cudaMemcpyHostToDevice, st));
+  if (path_len) CU(cudaMemcpyAsync(d_path, path32, (size_t)path_len * 32, cudaMemcpyHostToDevice, st));
+  int k = launch_merkle_consistency(first_size, second_size, d_r1, d_r2, d_path, path_len, d_ok, st);
+  G.launches += k; G.stats.kernel_launches += k;
+  uint32_t ok = 0;
+  CU(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  *out_ok = (int)ok;
+  return CG_OK;
+}
+
 int cg_merkle_verify_proof(const uint8_t* leaf_bytes, uint64_t leaf_len, uint64_t index, uint64_t tree_size, const uint8_t* path32, uint32_t path_len,
                            const uint8_t root[32], int* out_ok) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
   if (!out_ok || !root || (leaf_len && !leaf_bytes) || (path_len && !path32) || path_len > 64) return fail(CG_ERR_INVALID_ARG, "bad argument");
   int rc; cudaStream_t st = G.stream;
-  if ((rc = grow(&G.d_bytes, &G.cap_bytes, (size_t)leaf_len + 64))) return rc;
+  if ((rc = grow_bytes((size_t)leaf_len + 64))) return rc;
   if ((rc = grow(&G.d_off64, &G.cap_off64, 2))) return rc;
   if ((rc = grow(&G.d_dig[0], &G.cap_dig[0], (size_t)(path_len + 4) * 8))) return rc;
   uint64_t off[2] = {0, leaf_len};

@@ -95,10 +95,16 @@ int launch_redact_splice(const uint8_t* d_bytes, const uint32_t* d_off, const ui
                          uint8_t* d_out, uint32_t n, int sm_count, cudaStream_t stream);
 // leaf digests of fixed-size leaves: out[i] = SHA-256(0x00 || leaf_i)
 int launch_merkle_leaves_fixed(const uint8_t* d_bytes, uint64_t leaf_len, uint64_t n, uint32_t* d_out, cudaStream_t stream);
-int launch_merkle_leaves_var(const uint8_t* d_bytes, const uint64_t* d_off, uint64_t n, uint32_t* d_out, cudaStream_t stream);
+// ragged leaves, word-granular: d_bytes must be one of the library's own buffers (readable 4 bytes before the first leaf and
+// 8 bytes after the last); trim_newline: a final '\n' of a leaf's range is not hashed (JSONL lines)
+int launch_merkle_leaves_var(const uint8_t* d_bytes, const uint64_t* d_off, uint64_t n, uint32_t* d_out, cudaStream_t stream, bool trim_newline = false);
+// JSONL on the device: newline counts per 4 KB piece + their exclusive scan (d_piece_counts, *d_total_lines), then the line starts
+int launch_newline_split(const uint8_t* d_bytes, uint64_t len, uint32_t* d_piece_counts, uint64_t* d_total_lines, cudaStream_t stream);
+int launch_newline_starts(const uint8_t* d_bytes, uint64_t len, const uint32_t* d_piece_rank, uint64_t* d_starts, uint64_t n_lines, cudaStream_t stream);
+int launch_merkle_consistency(uint64_t first, uint64_t second, const uint32_t* d_first32, const uint32_t* d_second32, const uint32_t* d_path, uint32_t path_len, uint32_t* d_ok, cudaStream_t stream);
 // one tree level: out[i] = node(in[2i], in[2i+1]) ; an unpaired last node is copied
 int launch_merkle_level(const uint32_t* d_in, uint64_t n_in, uint32_t* d_out, cudaStream_t stream);
-// reduce up to `levels` levels inside one kernel (aligned blocks of 2^levels nodes -> 1 node each)
+// reduce `levels` (1..5) tree levels inside one kernel: every aligned group of 2^levels nodes -> its root (warp shuffles)
 int launch_merkle_reduce(const uint32_t* d_in, uint64_t n_in, uint32_t levels, uint32_t* d_out, cudaStream_t stream);
 
 }  // namespace cg

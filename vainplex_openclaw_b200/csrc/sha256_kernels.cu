@@ -93,21 +93,63 @@ __device__ void sha_bytes(int prefix, const uint8_t* __restrict__ data, uint64_t
   }
 }
 
+// The same for ragged inputs at any alignment, word-granular: the padded message is a byte stream that starts at address
+// A = data - (1 if there is a prefix byte); message word m is the four bytes at A + 4m, fetched as two ALIGNED 32-bit loads
+// and one funnel shift.  Only the first word (prefix byte) and the words around the end of the data (0x80, zeros, length)
+// are patched.  The caller guarantees that the aligned words covering [A, data + len) are readable (up to 3 bytes before
+// and 7 bytes after the data: every buffer this is called on is one of the library's own, padded on both sides).
+__device__ void sha_words(int prefix, const uint8_t* __restrict__ data, uint64_t len, uint32_t h[8]) {
+  sha_init(h);
+  const uint32_t p = prefix >= 0 ? 1u : 0u;
+  const uint64_t total = p + len, nblk = (total + 9 + 63) / 64;
+  const uintptr_t A = reinterpret_cast<uintptr_t>(data) - p;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(A & ~(uintptr_t)3);
+  const uint32_t sh = 8u * (uint32_t)(A & 3u);
+  uint32_t lo = __ldg(base);                           // aligned word holding stream byte 0
+  uint64_t q = 1;                                      // next aligned word to fetch
+  for (uint64_t blk = 0; blk < nblk; blk++) {
+    uint32_t w[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+      const uint64_t m = blk * 16 + t, b0 = 4 * m;     // stream bytes [b0, b0 + 4)
+      uint32_t v = 0;
+      if (b0 < total) {
+        // (the second aligned word is only touched when the stream word really straddles into it and it still holds data)
+        uint32_t hi = 0;
+        if (sh && b0 + 4 - (sh >> 3) < total) hi = __ldg(base + q);
+        if (!sh) { v = lo; lo = (b0 + 4 < total) ? __ldg(base + q) : 0u; }
+        else { v = __funnelshift_r(lo, hi, sh); lo = hi; }
+        q++;
+        v = bswap(v);
+        if (m == 0 && p) v = (v & 0x00ffffffu) | ((uint32_t)prefix << 24);
+        if (b0 + 4 > total) { const uint32_t k = (uint32_t)(total - b0); v = (v & (0xffffffffu << (32 - 8 * k))) | (0x80u << (24 - 8 * k)); }
+      } else if (b0 == total) v = 0x80000000u;
+      w[t] = v;
+    }
+    if (blk == nblk - 1) { const uint64_t bits = total * 8; w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+    sha_compress(h, w);
+  }
+}
+
 __global__ void __launch_bounds__(128) sha256_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ off,
                                                             uint32_t n, uint32_t* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t h[8];
-  sha_bytes(-1, bytes + off[i], off[i + 1] - off[i], h);
+  sha_words(-1, bytes + off[i], off[i + 1] - off[i], h);
   store_digest(out + (size_t)i * 8, h);
 }
 
+// leaf i = bytes[off[i], off[i+1]) ; with trim_newline a final '\n' of the range is not part of the leaf (JSONL lines,
+// audit-trail.ts:168: records joined with "\n" plus a trailing "\n" per flush)
 __global__ void __launch_bounds__(128) merkle_leaves_var_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ off,
-                                                                 uint64_t n, uint32_t* __restrict__ out) {
+                                                                 uint64_t n, uint32_t* __restrict__ out, int trim_newline) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t h[8];
-  sha_bytes(0x00, bytes + off[i], off[i + 1] - off[i], h);
+  uint64_t b = off[i], e = off[i + 1];
+  if (trim_newline && e > b && bytes[e - 1] == '\n') e--;
+  sha_words(0x00, bytes + b, e - b, h);
   store_digest(out + i * 8, h);
 }
 
@@ -225,6 +267,137 @@ __global__ void merkle_verify_kernel(const uint32_t* __restrict__ leaf32, unsign
   for (int t = 0; t < 8; t++) eq = eq && q[t] == r[t];
   *ok = eq ? 1u : 0u;
 }
+// RFC 9162 2.1.4.2: does `path` prove that the tree of `first` leaves with root first32 is a prefix of the tree of
+// `second` leaves with root second32?
+__global__ void merkle_consistency_kernel(unsigned long long first, unsigned long long second, const uint32_t* __restrict__ first32,
+                                          const uint32_t* __restrict__ second32, const uint32_t* __restrict__ path, uint32_t path_len, uint32_t* __restrict__ ok) {
+  if (threadIdx.x || blockIdx.x) return;
+  *ok = 0;
+  if (first == 0 || first > second) return;
+  uint32_t f1[8], f2[8]; load_digest(first32, f1); load_digest(second32, f2);
+  if (first == second) { bool eq = path_len == 0; for (int t = 0; t < 8; t++) eq = eq && f1[t] == f2[t]; *ok = eq ? 1u : 0u; return; }
+  unsigned long long fn = first - 1, sn = second - 1;
+  const bool pow2 = (first & (first - 1)) == 0;            // then the old root itself is the first element of the walk
+  while (fn & 1ull) { fn >>= 1; sn >>= 1; }
+  uint32_t fr[8], sr[8], k = 0;
+  if (pow2) { for (int t = 0; t < 8; t++) fr[t] = sr[t] = f1[t]; }
+  else { if (path_len == 0) return; load_digest(path, fr); for (int t = 0; t < 8; t++) sr[t] = fr[t]; k = 1; }
+  for (; k < path_len; k++) {
+    if (sn == 0) return;
+    uint32_t c[8], h[8]; load_digest(path + 8 * k, c);
+    if ((fn & 1ull) || fn == sn) {
+      merkle_node(c, fr, h); for (int t = 0; t < 8; t++) fr[t] = h[t];
+      merkle_node(c, sr, h); for (int t = 0; t < 8; t++) sr[t] = h[t];
+      if (!(fn & 1ull)) while (!(fn & 1ull) && fn != 0) { fn >>= 1; sn >>= 1; }
+    } else { merkle_node(sr, c, h); for (int t = 0; t < 8; t++) sr[t] = h[t]; }
+    fn >>= 1; sn >>= 1;
+  }
+  bool eq = sn == 0;
+  for (int t = 0; t < 8; t++) eq = eq && fr[t] == f1[t] && sr[t] == f2[t];
+  *ok = eq ? 1u : 0u;
+}
+
+// Up to five tree levels inside one warp: lane i holds node i of an aligned group of 32 (fewer at the ragged end), the
+// pairwise reduction runs through shuffles -- at step s the lanes with (i mod 2^(s+1)) == 0 hash their node with the one
+// 2^s lanes up, an unpaired node is promoted unchanged -- and only the group's root goes back to HBM.  Used for the small
+// upper levels of every tree and for the short trees of log appends, where a kernel launch per level costs more than the
+// idle lanes do (the large lower levels keep every lane busy in merkle_level_kernel).
+__global__ void __launch_bounds__(256) merkle_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n_in, uint32_t levels, uint32_t* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u, span = 1u << levels;                   // nodes per group (<= 32)
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t gpw = 32u >> levels;                                             // groups per warp
+  const uint64_t group = warp * gpw + lane / span, n_groups = (n_in + span - 1) / span;
+  const uint64_t node = group * span + (lane & (span - 1));
+  bool have = group < n_groups && node < n_in;
+  uint32_t d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (have) load_digest(in + 8 * node, d);
+  for (uint32_t s = 0; s < levels; s++) {
+    uint32_t o[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) o[t] = __shfl_down_sync(0xffffffffu, d[t], 1u << s);
+    const bool ohave = __shfl_down_sync(0xffffffffu, have ? 1u : 0u, 1u << s) != 0;
+    if (((lane & (span - 1)) & ((2u << s) - 1u)) == 0 && have && ohave) {
+      uint32_t h[8]; merkle_node(d, o, h);
+#pragma unroll
+      for (int t = 0; t < 8; t++) d[t] = h[t];
+    }
+  }
+  if ((lane & (span - 1)) == 0 && have) store_digest(out + 8 * group, d);
+}
+
+// JSONL split on the device: line i of the buffer = bytes[starts[i], starts[i+1]) including its '\n' (the last line may
+// lack one).  Three small kernels: newline count per 4 KB piece, exclusive scan over the pieces (one block), line starts.
+constexpr uint32_t kSplitPiece = 4096;
+__global__ void __launch_bounds__(256) newline_count_kernel(const uint8_t* __restrict__ bytes, uint64_t len, uint32_t* __restrict__ counts) {
+  const uint64_t lo = (uint64_t)blockIdx.x * kSplitPiece, hi = lo + kSplitPiece < len ? lo + kSplitPiece : len;
+  uint32_t c = 0;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) c += bytes[i] == '\n';
+  __shared__ uint32_t sm[8];
+  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += sm[k]; counts[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) newline_scan_kernel(uint32_t* __restrict__ counts, uint32_t n_pieces, uint64_t* __restrict__ total_lines, uint64_t len, const uint8_t* __restrict__ bytes) {
+  // exclusive scan in place, one block (n_pieces <= a few hundred thousand: 1 GB of JSONL is 262144 pieces)
+  __shared__ uint32_t carry, warp_sum[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_pieces; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t v = i < n_pieces ? counts[i] : 0, incl = v;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((threadIdx.x & 31) >= (uint32_t)d) incl += t; }
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) { uint32_t w = warp_sum[threadIdx.x], wi = w; for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (threadIdx.x >= (uint32_t)d) wi += t; } warp_sum[threadIdx.x] = wi - w; }
+    __syncthreads();
+    const uint32_t excl = carry + warp_sum[threadIdx.x >> 5] + incl - v;
+    if (i < n_pieces) counts[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_lines = (uint64_t)carry + ((len && bytes[len - 1] != '\n') ? 1u : 0u);      // + an unterminated last line
+}
+__global__ void __launch_bounds__(256) newline_starts_kernel(const uint8_t* __restrict__ bytes, uint64_t len, const uint32_t* __restrict__ piece_rank, uint64_t* __restrict__ starts, uint64_t n_lines) {
+  // starts[0] = 0; the line after the r-th newline (0-based) starts at its position + 1; starts[n_lines] = len
+  const uint64_t lo = (uint64_t)blockIdx.x * kSplitPiece, hi = lo + kSplitPiece < len ? lo + kSplitPiece : len;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { starts[0] = 0; starts[n_lines] = len; }
+  __shared__ uint32_t run;
+  if (threadIdx.x == 0) run = piece_rank[blockIdx.x];
+  __syncthreads();
+  for (uint64_t b = lo; b < hi; b += blockDim.x) {                // 256 bytes at a time, in order
+    const uint64_t i = b + threadIdx.x;
+    const bool nl = i < hi && bytes[i] == '\n';
+    const uint32_t m = __ballot_sync(0xffffffffu, nl);
+    __shared__ uint32_t wcnt[8];
+    if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    uint32_t before = run;
+    for (uint32_t k = 0; k < (threadIdx.x >> 5); k++) before += wcnt[k];
+    if (nl) starts[(uint64_t)before + __popc(m & ((1u << (threadIdx.x & 31)) - 1u)) + 1] = i + 1;     // (the r-th newline ends line r)
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += wcnt[k]; run += t; }
+    __syncthreads();
+  }
+}
+int launch_newline_split(const uint8_t* d_bytes, uint64_t len, uint32_t* d_piece_counts, uint64_t* d_total_lines, cudaStream_t stream) {
+  if (!len) return 0;
+  const uint32_t n_pieces = (uint32_t)((len + kSplitPiece - 1) / kSplitPiece);
+  newline_count_kernel<<<n_pieces, 256, 0, stream>>>(d_bytes, len, d_piece_counts);
+  newline_scan_kernel<<<1, 1024, 0, stream>>>(d_piece_counts, n_pieces, d_total_lines, len, d_bytes);
+  return 2;
+}
+int launch_newline_starts(const uint8_t* d_bytes, uint64_t len, const uint32_t* d_piece_rank, uint64_t* d_starts, uint64_t n_lines, cudaStream_t stream) {
+  if (!len) return 0;
+  const uint32_t n_pieces = (uint32_t)((len + kSplitPiece - 1) / kSplitPiece);
+  newline_starts_kernel<<<n_pieces, 256, 0, stream>>>(d_bytes, len, d_piece_rank, d_starts, n_lines);
+  return 1;
+}
+int launch_merkle_consistency(uint64_t first, uint64_t second, const uint32_t* d_first32, const uint32_t* d_second32, const uint32_t* d_path, uint32_t path_len, uint32_t* d_ok, cudaStream_t stream) {
+  merkle_consistency_kernel<<<1, 32, 0, stream>>>(first, second, d_first32, d_second32, d_path, path_len, d_ok);
+  return 1;
+}
 int launch_merkle_chain(const uint32_t* d_left, uint32_t n_left, const uint32_t* d_acc_in, uint32_t* d_acc_out, cudaStream_t stream) {
   merkle_chain_kernel<<<1, 32, 0, stream>>>(d_left, n_left, d_acc_in, d_acc_out);
   return 1;
@@ -327,9 +500,9 @@ int launch_merkle_leaves_fixed(const uint8_t* d_bytes, uint64_t leaf_len, uint64
   merkle_leaves_fixed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_bytes, (uint32_t)(leaf_len / 4), n, d_out);
   return 1;
 }
-int launch_merkle_leaves_var(const uint8_t* d_bytes, const uint64_t* d_off, uint64_t n, uint32_t* d_out, cudaStream_t stream) {
+int launch_merkle_leaves_var(const uint8_t* d_bytes, const uint64_t* d_off, uint64_t n, uint32_t* d_out, cudaStream_t stream, bool trim_newline) {
   if (!n) return 0;
-  merkle_leaves_var_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_bytes, d_off, n, d_out);
+  merkle_leaves_var_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_bytes, d_off, n, d_out, trim_newline ? 1 : 0);
   return 1;
 }
 int launch_merkle_level(const uint32_t* d_in, uint64_t n_in, uint32_t* d_out, cudaStream_t stream) {
@@ -339,8 +512,10 @@ int launch_merkle_level(const uint32_t* d_in, uint64_t n_in, uint32_t* d_out, cu
   return 1;
 }
 int launch_merkle_reduce(const uint32_t* d_in, uint64_t n_in, uint32_t levels, uint32_t* d_out, cudaStream_t stream) {
-  (void)d_in; (void)n_in; (void)levels; (void)d_out; (void)stream;
-  return 0;   // fused multi-level reduction: see merkle v2
+  if (!n_in || levels == 0 || levels > 5) return 0;
+  const uint64_t n_groups = (n_in + (1ull << levels) - 1) >> levels, warps = (n_groups + (32u >> levels) - 1) / (32u >> levels);
+  merkle_reduce_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(d_in, n_in, levels, d_out);
+  return 1;
 }
 
 }  // namespace cg
