@@ -51,8 +51,8 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   H.pf.trig_offsets.resize(H.pf.trig_offsets.size() + 4, 0); H.pf.trig_list.resize(H.pf.trig_list.size() + 4, 0);
   for (size_t i = 0; i + 1 < H.entry_words.size(); i += 2) h->entries.push_back(make_uint2(H.entry_words[i], H.entry_words[i + 1]));
   h->entries.resize(h->entries.size() + 2, make_uint2(0, 0));
-  d.image = H.image.data(); d.image_bytes = (uint32_t)H.image.size(); d.stride = (uint32_t)H.pf.stride;
-  d.bm_mask = H.bm_mask; d.bloom2 = H.bloom2 ? 1u : 0u; d.tables_resident = H.tables_resident; d.nb_shift = H.nb_shift;
+  d.image = H.image.data(); d.image_bytes = H.bm_bytes; d.stride = (uint32_t)H.pf.stride;
+  d.bm_mask = H.bm_mask; d.bloom2 = H.bloom2 ? 1u : 0u; d.rk_off = H.rk_off; d.rk_mask = H.rk_bytes - 4; d.tables_resident = H.tables_resident; d.nb_shift = H.nb_shift;
   d.n_shapes = (uint32_t)H.pf.shapes.size(); for (uint32_t k = 0; k < d.n_shapes && k < 16; k++) d.shapes[k] = H.pf.shapes[k];
   d.n_trig = (uint32_t)H.pf.trig_bytes.size(); for (uint32_t q = 0; q < 2; q++) d.trig_byte[q] = q < d.n_trig ? H.pf.trig_bytes[q] : 0;
   d.trig_offsets = H.pf.trig_offsets.data(); d.trig_list = H.pf.trig_list.data();
@@ -134,6 +134,7 @@ static uint32_t scan_message(Harness* h, const uint8_t* m, uint32_t len, uint32_
     const uint32_t key = gram_fold_word(wv);
     if (!gram_bitmap_test(d.image, key, d.bm_mask, d.bloom2 != 0)) continue;
     flagged++;
+    if (!gram_recheck_test(d.image + d.rk_off, key, d.rk_mask)) continue;
     gram_lookup(d, h->T, key, buf.data(), begin, end, q, emit);
   }
   for (uint32_t ti = 0; ti < d.n_trig; ti++) for (uint32_t q = begin; q < end; q++) if (buf[q] == d.trig_byte[ti]) gram_trigger(d, h->T, ti, buf.data(), begin, end, q, emit);
@@ -185,7 +186,7 @@ void harness_policy_hits_batch(void* p, const uint8_t* buf, const uint32_t* off,
   for (uint32_t q = (begin >> 4) << 4; q < end; q += d.stride) {
     uint32_t wv; memcpy(&wv, buf + q, 4);
     const uint32_t key = gram_fold_word(wv);
-    if (gram_bitmap_test(d.image, key, d.bm_mask, d.bloom2 != 0)) gram_lookup(d, h->T, key, buf, begin, end, q, emit);
+    if (gram_bitmap_test(d.image, key, d.bm_mask, d.bloom2 != 0) && gram_recheck_test(d.image + d.rk_off, key, d.rk_mask)) gram_lookup(d, h->T, key, buf, begin, end, q, emit);
   }
   for (uint32_t ti = 0; ti < d.n_trig; ti++) for (uint32_t q = begin; q < end; q++) if (buf[q] == d.trig_byte[ti]) gram_trigger(d, h->T, ti, buf, begin, end, q, emit);
   VM vm(d);
@@ -230,6 +231,7 @@ void harness_batch_rates(void* p, const uint8_t* data, uint64_t n_msgs, uint32_t
     const uint32_t key = gram_fold_word(wv);
     if (!gram_bitmap_test(d.image, key, d.bm_mask, d.bloom2 != 0)) continue;
     flagged++;
+    if (!gram_recheck_test(d.image + d.rk_off, key, d.rk_mask)) continue;
     gram_lookup(d, h->T, key, data, 0, (uint32_t)total, (uint32_t)q, emit);
   }
   out2[0] = flagged; out2[1] = occ;

@@ -104,7 +104,7 @@ struct cg_ruleset {
     if (h_counters) cudaFreeHost(h_counters);
     for (auto& e : e_cnt) if (e) cudaEventDestroy(e);
     for (void* p : allocs) cudaFree(p);
-    cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.slot_of_msg);
+    cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.fq); cudaFree(work.slot_of_msg);
     cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
   }
 };
@@ -127,8 +127,8 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
   if (!w.counters) { CU(cudaMalloc((void**)&w.counters, kCounterWords * sizeof(uint32_t))); }
   if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
   if (l1_cap > w.l1_cap) {
-    cudaFree(w.l1_pos); cudaFree(w.l1_fac); w.l1_pos = w.l1_fac = nullptr; w.l1_cap = 0;
-    CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_fac, (size_t)l1_cap * 4));
+    cudaFree(w.l1_pos); cudaFree(w.l1_fac); cudaFree(w.fq); w.l1_pos = w.l1_fac = nullptr; w.fq = nullptr; w.l1_cap = 0;
+    CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_fac, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.fq, (size_t)l1_cap * 8));
     w.l1_cap = l1_cap;
   }
   if (slot_cap > w.slot_cap) {
@@ -152,7 +152,7 @@ int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_of
   if (G.profiling) cudaEventRecord(G.pev[0], st);
   int k = launch_scan(rs->dev, w, d_bytes, d_off, n, d_words, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[1], st);
-  k += launch_resolve(rs->dev, w, d_off, n, spans, G.sm_count, st);
+  k += launch_confirm(rs->dev, w, d_bytes, d_off, n, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[2], st);
   k += launch_verify(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[3], st);
@@ -174,7 +174,7 @@ void default_caps(const cg_ruleset* rs, uint32_t n, uint32_t* l1, uint32_t* slot
 // what an overflowed step teaches about the capacities the next one needs
 void learn_caps(cg_ruleset* rs, const uint32_t* hc) {
   const uint32_t flags = hc[3];
-  if (flags & ERR_L1_OVERFLOW) rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * hc[4], hc[4] + 65536));
+  if (flags & ERR_L1_OVERFLOW) { const uint32_t need = std::max(hc[4], hc[20]); rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * need, need + 65536)); }
   if (flags & ERR_SLOT_OVERFLOW) rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096));
   if (flags & ERR_EVENT_OVERFLOW) rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096));
 }
@@ -219,7 +219,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
     float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_scan_ms = ms;
     uint32_t flags = hs->counters[3];
     if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
-    if (flags & ERR_L1_OVERFLOW) { l1_cap = std::max<uint32_t>(l1_cap * 2, hs->counters[4] + 1024); continue; }
+    if (flags & ERR_L1_OVERFLOW) { l1_cap = std::max<uint32_t>(l1_cap * 2, std::max(hs->counters[4], hs->counters[20]) + 1024); continue; }
     if (flags & ERR_SLOT_OVERFLOW) { slot_cap = std::max<uint32_t>(slot_cap * 4, hs->counters[0] + 1024); continue; }
     if (flags & ERR_EVENT_OVERFLOW) { event_cap = std::max<uint32_t>(event_cap * 4, hs->counters[1] + 1024); continue; }
     if (flags & ERR_SPAN_OVERFLOW) { span_cap = std::max<uint32_t>(span_cap * 4, hs->counters[2] + 1024); continue; }
@@ -360,6 +360,7 @@ int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out16[16]) {
   if (!rs || !out16) return fail(CG_ERR_INVALID_ARG, "null argument");
   if (!rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
   memcpy(out16, rs->last_counters, 64);
+  out16[4] += rs->last_counters[21];          // occurrences confirmed by scan_kernel itself + by confirm_kernel
   return CG_OK;
 }
 
@@ -406,9 +407,9 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   DevRuleset& d = rs->dev;
   int rc;
   const uint8_t* d_image; if ((rc = upload(rs.get(), H.image, &d_image, 16))) return rc;
-  d.image = d_image; d.image_bytes = (uint32_t)H.image.size(); d.stride = (uint32_t)P.stride;
-  d.bm_mask = H.bm_mask; d.bloom2 = H.bloom2 ? 1u : 0u; d.tables_resident = H.tables_resident ? 1u : 0u;
-  d.dir_off = H.dir_off; d.ent_off = H.ent_off; d.fac_off = H.fac_off; d.set_off = H.set_off; d.nb_shift = H.nb_shift;
+  d.image = d_image; d.image_bytes = H.bm_bytes; d.stride = (uint32_t)P.stride;
+  d.bm_mask = H.bm_mask; d.bloom2 = H.bloom2 ? 1u : 0u; d.rk_off = H.rk_off; d.rk_mask = H.rk_bytes - 4; d.tables_resident = H.tables_resident ? 1u : 0u;
+  d.dir_off = H.dir_off; d.ent_off = H.ent_off; d.nb_shift = H.nb_shift;
   d.n_shapes = (uint32_t)P.shapes.size(); for (uint32_t k = 0; k < 16; k++) d.shapes[k] = k < d.n_shapes ? P.shapes[k] : 0;
   d.n_trig = (uint32_t)P.trig_bytes.size(); for (uint32_t t = 0; t < 2; t++) d.trig_byte[t] = t < d.n_trig ? P.trig_bytes[t] : 0;
   d.hot_c5f = 0x5f5f5f5fu; d.hot_c10 = 0x10101010u; d.hot_one = 1u;

@@ -41,6 +41,15 @@ CG_HD bool gram_bitmap_test(const uint8_t* bitmap, uint32_t key, uint32_t bm_mas
   return (wv & bits) == bits;
 }
 
+// The recheck map: a second, smaller bitmap under an independent hash (word = hi32(key * kGramMult2) & rk_mask, bit 31 - top
+// five bits of the same product).  The hot loop never looks at it; a flagged gram is tested against it before the level-1b
+// lookup, 32 flagged grams at a time, which sorts out the first bitmap's false positives for a handful of instructions each.
+CG_HD uint32_t gram_recheck_hash(uint32_t key) { return (uint32_t)(((uint64_t)key * kGramMult2) >> 32); }
+CG_HD bool gram_recheck_test(const uint8_t* rk, uint32_t key, uint32_t rk_mask) {
+  const uint32_t h = gram_recheck_hash(key);
+  return ((*reinterpret_cast<const uint32_t*>(rk + (h & rk_mask)) << (h >> 27)) & 0x80000000u) != 0;
+}
+
 // level-1b tables as the running side sees them (shared-memory copies inside the scan kernel when they fit, else HBM)
 struct GramTables {
   const uint32_t* bucket_start;   // n_buckets + 1

@@ -8,14 +8,15 @@ namespace cg {
 // Everything the scan / verify kernels need to know about a compiled rule set (device pointers).
 struct DevRuleset {
   // gram filter (rulec.h): the image is staged into shared memory by the scan kernel with TMA bulk copies.
-  //   [0, bm_mask + 4)  bitmap ; then, when tables_resident: [dir_off] bucket_start (n_buckets + 1 words)
-  //   [ent_off] level-1b entries (8 B each) [fac_off] factor words [set_off] byte sets.  All offsets 16-byte aligned.
+  //   [0, bm_mask + 4)  bitmap ; [rk_off] recheck map ; then, when tables_resident: [dir_off] bucket_start (n_buckets + 1 words)
+  //   [ent_off] level-1b entries (8 B each).  All offsets 16-byte aligned.  Factor words and byte sets stay in HBM.
   const uint8_t* image;
-  uint32_t image_bytes;          // bytes staged (multiple of 16)
+  uint32_t image_bytes;          // bytes scan_kernel stages: the bitmap (the rest of the image is read in place by confirm_kernel)
   uint32_t stride;               // 4: one probe per aligned word, 2: also the gram at byte offset 2 of every word
   uint32_t bm_mask, bloom2;      // bitmap word address = hi32(key * kGramMult) & bm_mask; bloom2: keys set / need two bits of the word
+  uint32_t rk_off, rk_mask;      // recheck map (gram_filter.h): image offset, bytes - 4; always part of the image
   uint32_t tables_resident;      // level-1b tables are part of the image (else read through the HBM pointers below)
-  uint32_t dir_off, ent_off, fac_off, set_off;
+  uint32_t dir_off, ent_off;
   uint32_t nb_shift;             // bucket = hash >> nb_shift
   uint32_t n_shapes, shapes[16]; // distinct key masks of the level-1b entries
   uint32_t n_trig, trig_byte[2]; // single-byte triggers
@@ -48,9 +49,11 @@ struct DevRuleset {
 // Per-call scratch in HBM.  A "slot" is one message with at least one confirmed candidate.
 struct ScanWork {
   uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (confirmed factor occurrences) [5]=verify cursor
-                                 //           [6]=flagged grams (level 1a) [7..15]=debug [17]=n_heavy [18]=verify cursor (light events)
-  uint32_t* l1_pos;              // [l1_cap] confirmed factor occurrences queued by scan_kernel: buffer offset of the factor's first byte,
-  uint32_t* l1_fac;              //          factor id
+                                 //           [6]=flagged grams (level 1a) [7..15]=debug [17]=n_heavy [18]=verify cursor (light events) [19]=grams past the recheck map
+                                 //           [20]=flag words queued [21]=factor occurrences confirmed by confirm_kernel
+  uint32_t* l1_pos;              // [l1_cap] factor occurrences scan_kernel confirms itself (head check, trigger bytes): buffer offset of the
+  uint32_t* l1_fac;              //          factor's first byte, factor id
+  uint2* fq;                     // [l1_cap] scan_kernel's flag words: x = the lane's chunk number after the round, y = 4 tiles x 8 (4) probe bits
   uint32_t* slot_of_msg;         // [n] 0xffffffff = none yet (reset per step)
   uint32_t* slot_msg;            // [slot_cap]
   uint32_t* cand;                // [slot_cap * rw]  candidate (msg,rule) pairs already queued
@@ -72,8 +75,8 @@ constexpr uint64_t kWordIncomplete = ~0ull;      // result word of every message
 // d_bytes must be 16-byte aligned and readable up to 16 bytes past off[n].
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, int sm_count, cudaStream_t stream);
-// resolve: message of every queued occurrence, slots, candidates for the VM / direct hits
-int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
+// confirm: flag words -> grams -> recheck map -> level-1b lookup -> exact factors -> message, slot, candidates for the VM / direct hits
+int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream);
 // one verdict word per hit message: action | matched policies << 2 | deciding rule << 12 (cg_policy_verdict_batch)

@@ -63,14 +63,19 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     H.entry_words.push_back(e.key & e.mask);
     H.entry_words.push_back(e.factor | ((uint32_t)(e.off + 3) << 20) | (shape_of[i] << 25));
   }
-  // ---- bitmap: one bit per key (optionally two in the same word: blocked Bloom filter); sized for a fill below one per cent
-  uint32_t bm = opt.bitmap_kb ? opt.bitmap_kb * 1024u : 16u * 1024u;
-  if (!opt.bitmap_kb) while (bm < 128u * 1024u && (uint64_t)bm * 8 < (uint64_t)P.keys.size() * 256) bm *= 2;
+  // ---- bitmap: one bit per key (optionally two in the same word: blocked Bloom filter).  Every false positive costs a pass
+  // through stage 1 of the slow path, staging the image costs next to nothing: 128 KB unless the level-1b tables then no
+  // longer fit beside it and the rule set is small enough for a denser bitmap (>= 128 bits per key)
+  uint32_t bm = opt.bitmap_kb ? opt.bitmap_kb * 1024u : 128u * 1024u;
   { uint32_t t = 4096; while (t < bm) t *= 2; bm = std::min<uint32_t>(t, 128u * 1024u); }       // power of two
   auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  const size_t tables = a16(H.bucket_start.size() * 4) + a16(H.entry_words.size() * 4) + a16(H.factor_words.size() * 4 + 64) + a16(P.bytesets.size() * 4 + 32);
-  while (bm > 16u * 1024u && (size_t)bm + tables > opt.budget_bytes && (uint64_t)(bm / 2) * 8 >= (uint64_t)P.keys.size() * 32) bm /= 2;   // tables resident beats a sparser bitmap
-  H.tables_resident = (size_t)bm + tables <= opt.budget_bytes;
+  // recheck map: 32 bits per key (about 3 % of the first bitmap's false positives survive it), 4 .. 16 KB, shrunk before the bitmap is
+  uint32_t rk = 4096; while (rk < 16384u && (uint64_t)rk * 8 < (uint64_t)P.keys.size() * 32) rk *= 2;
+  const size_t tables0 = a16(H.bucket_start.size() * 4) + a16(H.entry_words.size() * 4);     // (factor words and byte sets are read from HBM / L2: only the last, warp-parallel stage of the slow path needs them)
+  while (rk > 4096u && (size_t)bm + rk + tables0 > opt.budget_bytes) rk /= 2;
+  const size_t tables = tables0 + rk;
+  while (bm > 16u * 1024u && (size_t)bm + tables > opt.budget_bytes && (uint64_t)(bm / 2) * 8 >= (uint64_t)P.keys.size() * 128) bm /= 2;   // tables resident beats a sparser bitmap
+  H.tables_resident = false;      // (scan_kernel stages the bitmap alone; the tables are confirm_kernel's, read through L1 / L2)
   if (!H.tables_resident && !opt.bitmap_kb) bm = 128u * 1024u;
   H.bm_bytes = bm; H.bm_mask = bm - 4; H.bloom2 = opt.bloom2 != 0;
   H.image.assign(bm, 0);
@@ -80,12 +85,18 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     wv |= (0x80000000u >> (key & 31u)) | (H.bloom2 ? (0x80000000u >> ((hi >> 17) & 31u)) : 0u);
     memcpy(H.image.data() + addr, &wv, 4);
   }
+  auto append = [&](const void* p, size_t bytes, size_t pad) { uint32_t o = (uint32_t)H.image.size(); H.image.resize(a16(H.image.size() + bytes + pad), 0); if (bytes) memcpy(H.image.data() + o, p, bytes); return o; };
+  {
+    std::vector<uint8_t> map(rk, 0);
+    for (uint32_t key : P.keys) {
+      const uint32_t h = (uint32_t)(((uint64_t)key * kGramMult2) >> 32), addr = h & (rk - 4);
+      uint32_t wv; memcpy(&wv, map.data() + addr, 4); wv |= 0x80000000u >> (h >> 27); memcpy(map.data() + addr, &wv, 4);
+    }
+    H.rk_bytes = rk; H.rk_off = append(map.data(), map.size(), 0);
+  }
   if (H.tables_resident) {
-    auto append = [&](const void* p, size_t bytes, size_t pad) { uint32_t o = (uint32_t)H.image.size(); H.image.resize(a16(H.image.size() + bytes + pad), 0); if (bytes) memcpy(H.image.data() + o, p, bytes); return o; };
     H.dir_off = append(H.bucket_start.data(), H.bucket_start.size() * 4, 0);
     H.ent_off = append(H.entry_words.data(), H.entry_words.size() * 4, 0);
-    H.fac_off = append(H.factor_words.data(), H.factor_words.size() * 4, 64);
-    H.set_off = append(P.bytesets.data(), P.bytesets.size() * 4, 32);
   }
   return true;
 }

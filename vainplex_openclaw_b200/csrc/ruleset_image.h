@@ -10,12 +10,13 @@ namespace cg {
 struct HostImage {
   std::vector<CompiledRule> rules;
   Prefilter pf;
-  // what the scan kernel stages into shared memory: [bitmap][bucket_start][entries][factor words][byte sets]
+  // what the scan kernel stages into shared memory: [bitmap][recheck map][bucket_start][entries]
   // (the level-1b tables only when they fit the budget: tables_resident)
   std::vector<uint8_t> image;
   uint32_t bm_bytes = 0, bm_mask = 0; bool bloom2 = false;
+  uint32_t rk_off = 0, rk_bytes = 0;   // recheck map
   bool tables_resident = false;
-  uint32_t dir_off = 0, ent_off = 0, fac_off = 0, set_off = 0, nb_shift = 0, n_buckets = 0;
+  uint32_t dir_off = 0, ent_off = 0, nb_shift = 0, n_buckets = 0;
   std::vector<uint32_t> bucket_start;  // n_buckets + 1
   std::vector<uint32_t> entry_words;   // 2 words per level-1b entry, sorted by bucket: masked key, factor | (off + 3) << 20 | shape << 25
   std::vector<uint32_t> prog, prog_off, sets, first, alpha;
@@ -26,7 +27,7 @@ struct HostImage {
 
 struct ImageOptions {
   int stride = 0;                       // 0 = choose (rulec.h)
-  size_t budget_bytes = 216 * 1024;     // shared memory the image may take (scan_kernel adds 8 KB of rings; 227 KB per CTA)
+  size_t budget_bytes = 185 * 1024;     // shared memory the image may take (scan_kernel adds 40 KB of rings + 1 KB; 227 KB per CTA)
   uint32_t bitmap_kb = 0;               // 0 = sized from the number of keys (16 .. 128 KB)
   int bloom2 = 0;                       // two bits per key in one bitmap word (costs three more ALU instructions per probe)
   uint32_t max_keys = 24576;

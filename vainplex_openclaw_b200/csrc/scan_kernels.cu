@@ -59,13 +59,13 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {
 //   1a  every aligned 4-byte gram (stride 4) or every even-offset gram (stride 2) is folded SWAR-style, hashed with one
 //       IMAD and tested against the bitmap in shared memory (two bits of one word).  Result bits are funnel-shifted
 //       into a per-lane flag word; a warp ballot decides whether anything has to be looked at.
-//   1b  flagged grams are compacted (ballot + popc) into a per-warp ring in shared memory and drained 32 at a time,
-//       one per lane: level-1b table lookup and exact comparison of the factor (gram_filter.h).  Confirmed factor
+//   1b  lanes with flagged grams push (chunk, flag word) to a per-warp ring in shared memory, which goes to a queue in HBM
+//       32 entries at a time; confirm_kernel takes it from there (recheck map, level-1b lookup, exact factor, message).  Confirmed factor
 //       occurrences go to the queue in HBM, one atomic each (they are rare).
 // ------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 1024;      // 32 warps, one CTA per SM
-constexpr uint32_t kRing = 64;          // flagged grams per warp waiting for the drain (a round adds <= 32, a drain leaves < 32)
-constexpr uint32_t kScanRingBytes = (kScanThreads / 32) * kRing * 4;
+constexpr uint32_t kRing = 64;          // (chunk, flag word) pairs a warp collects before it appends 32 of them to the queue in HBM
+constexpr uint32_t kScanRingBytes = (kScanThreads / 32) * kRing * 8;
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 
@@ -116,26 +116,6 @@ __device__ __forceinline__ uint32_t differs(uint32_t z, uint32_t splat_z, uint32
 // what the rare paths need (kept out of line: the hot loop must stay small enough for the instruction cache)
 struct ScanCtx { GramTables T; const uint8_t* bytes; uint32_t begin, end; };
 
-// level 1b for up to 32 flagged grams of one warp's ring, one per lane.  `shift`: flagged gram = byte position >> shift.
-__device__ __forceinline__ void drain_ring(const DevRuleset& rs, const ScanWork& w, const ScanCtx& c, uint32_t ring, uint32_t head, uint32_t cnt, uint32_t shift) {
-  const uint32_t lane = threadIdx.x & 31u;
-  // all 32 lanes walk gram_lookup together (its phases are separated by warp votes); lanes without an event are inactive
-  uint32_t pos = 0, g = 0; bool active = false;
-  if (lane < cnt) {
-    pos = lds_u32(ring + (((head + lane) & (kRing - 1)) << 2)) << shift;
-    active = pos < c.end && !(rs.debug_flags & 1u);
-  }
-  if (active) {
-    const uint32_t* p4 = reinterpret_cast<const uint32_t*>(c.bytes + (pos & ~3u));
-    g = __ldg(p4);
-    if (pos & 3u) g = __funnelshift_r(g, __ldg(p4 + 1), 8u * (pos & 3u));
-  }
-  QueueEmit emit{w};
-  __syncwarp();
-  gram_lookup(rs, c.T, gram_fold_word(g), c.bytes, c.begin, c.end, pos, emit, active);
-  __syncwarp();
-}
-
 // trigger bytes inside one 16-byte chunk: bit 8k+7 of mk_j set = byte k of word j equals a trigger byte in the folded
 // domain (which merges case and bit 7), so every marked byte is compared again exactly
 __device__ __forceinline__ void trigger_chunk(const DevRuleset& rs, const ScanWork& w, const ScanCtx& c, uint32_t mk0, uint32_t mk1, uint32_t mk2, uint32_t mk3, uint32_t chunk) {
@@ -172,7 +152,7 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
   if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, rs.image_bytes);
+    mbar_expect_tx(&bar, rs.image_bytes);                        // (the bitmap; everything else the rule set consists of is confirm_kernel's)
     for (uint32_t o = 0; o < rs.image_bytes; o += 32768u) {
       uint32_t len = rs.image_bytes - o < 32768u ? rs.image_bytes - o : 32768u;
       tma_bulk_g2s(smem + o, rs.image + o, len, &bar);
@@ -189,46 +169,56 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
   uint32_t lt = (1u << lane) - 1u; const uint32_t FULL = 0xffffffffu;
   asm volatile("" : "+r"(lt));                // (loop invariants the compiler would otherwise recompute in every iteration of the hot loop)
   const uint32_t bm = smem_u32(smem);
-  const uint32_t ring = smem_u32(smem + rs.image_bytes) + warp * (kRing * 4);
-  if (rs.tables_resident) {
-    ctx.T.bucket_start = reinterpret_cast<const uint32_t*>(smem + rs.dir_off); ctx.T.entries = reinterpret_cast<const uint2*>(smem + rs.ent_off);
-    ctx.T.factors = reinterpret_cast<const uint32_t*>(smem + rs.fac_off); ctx.T.bytesets = reinterpret_cast<const uint32_t*>(smem + rs.set_off);
-  } else { ctx.T.bucket_start = rs.bucket_start; ctx.T.entries = rs.entries; ctx.T.factors = rs.factors; ctx.T.bytesets = rs.bytesets; }
+  const uint32_t ring1 = smem_u32(smem + rs.image_bytes) + warp * (kRing * 8);
+  ctx.T.factors = rs.factors; ctx.T.bytesets = rs.bytesets; ctx.T.bucket_start = rs.bucket_start; ctx.T.entries = rs.entries;    // (head check and triggers only)
   constexpr uint32_t kShift = NPROBE == 2 ? 1 : 2;             // flagged gram = its byte position >> kShift
   HotConst hk; hk.c5f = rs.hot_c5f; hk.c10 = rs.hot_c10; hk.one = rs.hot_one; hk.mask = rs.bm_mask;
-  asm volatile("" : "+r"(hk.c5f), "+r"(hk.c10), "+r"(hk.one));
-  uint32_t ring_head = 0, ring_tail = 0;          // flagged grams drained / pushed so far (the ring holds [head, tail))
+  asm volatile("" : "+r"(hk.c5f), "+r"(hk.c10), "+r"(hk.one), "+r"(hk.mask));
   if (blockIdx.x == 0) head_check(rs, w, ctx);
 
-  const uint32_t first_chunk = begin >> 4, end_chunk = (end + 15u) >> 4;       // 16-byte chunks [first, end)
+  const uint32_t first_chunk = begin >> 4;
+  uint32_t end_chunk = (end + 15u) >> 4;       // 16-byte chunks [first, end)
   // folded (z domain) trigger bytes, splatted
   uint32_t splat0 = NTRIG > 0 ? (((rs.trig_byte[0] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u, splat1 = NTRIG > 1 ? (((rs.trig_byte[1] & 0x5fu) ^ 0x10u) * 0x01010101u) : 0u;
   asm volatile("" : "+r"(splat0), "+r"(splat1));
   // this lane's chunk in the warp's current tile (32 chunks = 512 bytes); tiles are dealt round-robin to all warps of the grid
   uint32_t c = first_chunk + (blockIdx.x * wpb + warp) * 32u + lane;
-  const uint32_t cstep = gridDim.x * wpb * 32u;
+  uint32_t cstep = gridDim.x * wpb * 32u;
+  uint32_t shl_bits = hk.one << (4u * NPROBE);
+  asm volatile("" : "+r"(end_chunk), "+r"(cstep), "+r"(shl_bits));
+  const bool last_lane = lane == 31;
 
   auto load_chunk = [&](uint4& v, uint32_t& t, uint32_t cc) {
     v = make_uint4(0, 0, 0, 0); t = 0;
     if (cc < end_chunk) v = ldg_stream(bytes + (size_t)cc * 16);
-    if (NPROBE == 2 && lane == 31 && cc + 1 < end_chunk) t = __ldg(reinterpret_cast<const uint32_t*>(bytes + (size_t)(cc + 1) * 16));
+    if (NPROBE == 2 && last_lane && cc + 1 < end_chunk) t = __ldg(reinterpret_cast<const uint32_t*>(bytes + (size_t)(cc + 1) * 16));
   };
-  // Three tiles per round, each in its own registers: a buffer is refilled (tile + 3 rounds' worth ahead) right after it
-  // has been consumed, so every load has two tiles' worth of work to hide behind and no register is ever copied.
-  // The probe results of the round's three tiles are collected in one register per lane before anything is done about
-  // them: the compaction below then amortises its warp votes over three tiles.
+  // Four tiles per round through two register buffers, one tile ahead: tile k consumes one buffer and, as its first
+  // action after touching that data, issues the load of tile k + 1 into the other (dead since tile k - 1 folded it).
+  // ptxas tracks every load of this loop on ONE scoreboard, and a wait on a scoreboard waits for everything issued on it:
+  // were the next load issued BEFORE the first use of the current data (where the scheduler hoists it if it may), each
+  // tile would wait for the load it has just issued -- the full HBM latency, exposed once per tile.  The address of the
+  // next load therefore depends on the current data (+ word * 0 with a run-time zero), which pins the order.  With
+  // eight warps per scheduler, "one tile ahead" is well over a thousand cycles.
+  // The probe results of the round's four tiles (4 x 8 bits at stride 2) are collected in one register per lane; after the
+  // round every lane with a non-zero flag word pushes (its chunk, the word) to ring 1 -- one ballot per round, no loop.
+  // Tiles past the end load zeros; whatever those flag is dropped by the position checks of the slow path.
   constexpr uint32_t kBits = 4u * NPROBE;
-  uint4 bA, bB, bC; uint32_t tA, tB, tC;
-  load_chunk(bA, tA, c); load_chunk(bB, tB, c + cstep); load_chunk(bC, tC, c + 2u * cstep);
+  uint32_t zero = hk.one - 1u;
+  asm volatile("" : "+r"(zero));
+  uint4 bA, bB; uint32_t tA, tB;
+  load_chunk(bA, tA, c); bB = make_uint4(0, 0, 0, 0); tB = 0;
   uint32_t acc = 0;
-  auto scan_tile = [&](uint4& buf, uint32_t& tl, uint32_t cc) {
+  auto scan_tile = [&](const uint4& buf, const uint32_t& tl, uint4& nbuf, uint32_t& ntl, uint32_t cc) {
     const uint4 cur = buf; const uint32_t ct = tl;
-    load_chunk(buf, tl, cc + 3u * cstep);
+    uint32_t ncc = cc + cstep;
+    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(ncc) : "r"(cur.x), "r"(zero));       // (waits for the current tile's data)
+    load_chunk(nbuf, ntl, ncc);
     const uint32_t z0 = fold_z(cur.x, hk), z1 = fold_z(cur.y, hk), z2 = fold_z(cur.z, hk), z3 = fold_z(cur.w, hk);
     const uint32_t f0 = fold_key(z0, hk), f1 = fold_key(z1, hk), f2 = fold_key(z2, hk), f3 = fold_key(z3, hk);
     uint32_t flags = 0;
     if (NPROBE == 2) {
-      uint32_t w4 = __shfl_down_sync(FULL, cur.x, 1); if (lane == 31) w4 = ct;
+      uint32_t w4 = __shfl_down_sync(FULL, cur.x, 1); if (last_lane) w4 = ct;
       const uint32_t f4 = fold_key(fold_z(w4, hk), hk);
       gram_probe<BLOOM2>(bm, hk, f0, flags); gram_probe<BLOOM2>(bm, hk, __funnelshift_r(f0, f1, 16), flags);
       gram_probe<BLOOM2>(bm, hk, f1, flags); gram_probe<BLOOM2>(bm, hk, __funnelshift_r(f1, f2, 16), flags);
@@ -238,40 +228,52 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
       gram_probe<BLOOM2>(bm, hk, f0, flags); gram_probe<BLOOM2>(bm, hk, f1, flags);
       gram_probe<BLOOM2>(bm, hk, f2, flags); gram_probe<BLOOM2>(bm, hk, f3, flags);
     }
-    if (cc >= end_chunk) flags = 0;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc), "r"(hk.one << kBits), "r"(flags));      // acc = acc << kBits | flags, on the FMA pipe
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc), "r"(shl_bits), "r"(flags));      // acc = acc << kBits | flags, on the FMA pipe
     if (NTRIG > 0) {
       // triggers: d_j has bit 7 of a byte clear where it equals a trigger byte (folded domain)
       uint32_t d0 = differs(z0, splat0, hk.one), d1 = differs(z1, splat0, hk.one), d2 = differs(z2, splat0, hk.one), d3 = differs(z3, splat0, hk.one);
       if (NTRIG > 1) { d0 &= differs(z0, splat1, hk.one); d1 &= differs(z1, splat1, hk.one); d2 &= differs(z2, splat1, hk.one); d3 &= differs(z3, splat1, hk.one); }
-      const bool trig = cc < end_chunk && ((d0 & d1 & d2 & d3 & 0x80808080u) != 0x80808080u);
+      const bool trig = (d0 & d1 & d2 & d3 & 0x80808080u) != 0x80808080u;
       if (__any_sync(FULL, trig)) {
         if (trig) trigger_chunk(rs, w, ctx, ~d0 & 0x80808080u, ~d1 & 0x80808080u, ~d2 & 0x80808080u, ~d3 & 0x80808080u, cc);
         __syncwarp();
       }
     }
   };
+  // Nothing is done about a flagged gram here: looking at one means a chain of dependent loads (the gram again, the
+  // recheck map, the level-1b bucket, the factor, the text around it), and with 32 warps per SM there is nobody to hide
+  // that latency behind -- measured, a slow path inside this kernel cost more time than the whole hot loop's instruction
+  // stream, whatever its instruction count.  The flag words go to a queue in HBM, 32 at a time (one atomic per 32), and
+  // confirm_kernel, with one thread per flag word and the whole GPU's worth of warps, does the looking.
+  uint32_t h1 = 0, t1 = 0;       // the ring holds [h1, t1)
+  auto append32 = [&](uint32_t k) {                         // k <= 32 entries from the ring -> the queue
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&w.counters[20], k);
+    base = __shfl_sync(FULL, base, 0);
+    if (lane < k) {
+      uint32_t cw, aw;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cw), "=r"(aw) : "r"(ring1 + (((h1 + lane) & (kRing - 1)) << 3)));
+      if (base + lane < w.l1_cap) w.fq[base + lane] = make_uint2(cw, aw); else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
+    }
+    h1 += k;
+  };
 #pragma unroll 1
   while (c - lane < end_chunk) {                           // warp-uniform: this warp still has a tile
-    scan_tile(bA, tA, c);
-    scan_tile(bB, tB, c + cstep);                          // (tiles past the end load nothing and flag nothing)
-    scan_tile(bC, tC, c + 2u * cstep);
-    c += 3u * cstep;
+    scan_tile(bA, tA, bB, tB, c);
+    scan_tile(bB, tB, bA, tA, c + cstep);
+    scan_tile(bA, tA, bB, tB, c + 2u * cstep);
+    scan_tile(bB, tB, bA, tA, c + 3u * cstep);
+    c += 4u * cstep;
     // acc: bit (i * kBits + kBits - 1 - j) = probe j of the tile scanned i tiles ago, whose chunk was c - (i + 1) * cstep
-    for (uint32_t m = __ballot_sync(FULL, acc != 0); m; m = __ballot_sync(FULL, acc != 0)) {
-      if (acc) {
-        const uint32_t bit = 31u - __clz(acc);
-        acc ^= 1u << bit;
-        const uint32_t ev = (c - (bit / kBits + 1u) * cstep) * kBits + (kBits - 1u - bit % kBits);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring + (((ring_tail + __popc(m & lt)) & (kRing - 1)) << 2)), "r"(ev) : "memory");
-      }
-      ring_tail += __popc(m);
-      if (ring_tail - ring_head >= 32) { __syncwarp(); drain_ring(rs, w, ctx, ring, ring_head, 32, kShift); ring_head += 32; }
+    const uint32_t m = __ballot_sync(FULL, acc != 0);
+    if (m) {
+      if (acc) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring1 + (((t1 + __popc(m & lt)) & (kRing - 1)) << 3)), "r"(c), "r"(acc) : "memory");
+      t1 += __popc(m); acc = 0;
+      if (t1 - h1 >= 32u) { __syncwarp(); append32(32u); }
     }
   }
   __syncwarp();
-  if (ring_tail != ring_head) drain_ring(rs, w, ctx, ring, ring_head, ring_tail - ring_head, kShift);
-  if (lane == 0 && ring_tail) atomicAdd(&w.counters[6], ring_tail);
+  if (t1 != h1) append32(t1 - h1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -330,21 +332,154 @@ struct SlotSink {
   }
 };
 
-__global__ void __launch_bounds__(256)
-resolve_kernel(DevRuleset rs, ScanWork w, const uint32_t* __restrict__ off, uint32_t n, int want_spans) {
-  const uint32_t n1 = min(w.counters[4], w.l1_cap);
-  const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t i = tid; i < n1; i += stride) {
-    const uint32_t pos = w.l1_pos[i], f = w.l1_fac[i];
-    const uint32_t msg = message_of(off, n, pos);
-    if (pos + (rs.factors[(size_t)f * 12 + 1] & 0xffu) > off[msg + 1]) continue;     // straddles two messages: not an occurrence
-    SlotSink sink(rs, w, msg, want_spans != 0);
-    factor_confirmed(rs, f, pos - off[msg], want_spans != 0, sink);
+// ------------------------------------------------------------------------------------------
+// confirm_kernel: everything between "the bitmap flagged a gram" and "this (message, rule) goes to the VM".
+// A warp takes 32 flag words of scan_kernel's queue at a time, one per lane, and runs them through four stages; between
+// the stages the survivors are compacted through per-warp rings in shared memory, so that every stage runs with (nearly)
+// full warps although each keeps only a fraction of its input:
+//   A  one flag bit per lane and pass -> gram position; gram reloaded, folded, tested against the recheck map (the bitmap's
+//      false positives end here)                                                                       -> ring 2 (grams)
+//   B  level-1b lookup, one step per lane and pass: open the next shape's bucket, or compare one entry.  Grams of digit
+//      runs match dozens of factors: they keep one lane busy for dozens of cheap passes          -> ring 3 (gram, entry)
+//   C  exact comparison of the entry's factor at the position the gram implies                  -> ring 4 (factor occurrences)
+//   D  message of the occurrence (no straddling), slot, candidate for the VM / direct hit
+// Every stage is a chain of dependent loads; nothing synchronises warps with each other, and the grid keeps every SM's warp
+// slots full, so the chains of some thousand warps overlap (a block-wide version of this with barriers between the stages
+// spent half its time waiting for each stage's slowest thread).
+// The few occurrences scan_kernel queued directly (head check, trigger bytes) enter at D; rules without factors are
+// candidates for every message.
+// ------------------------------------------------------------------------------------------
+constexpr int kConfirmThreads = 256;
+constexpr uint32_t kConfirmWarpBytes = kRing * (8 + 8 + 8);     // rings 2 (position, folded gram), 3 (position, entry), 4 (occurrence start, factor)
+
+struct ConfirmCtx {
+  const DevRuleset& rs; const ScanWork& w; GramTables T; const uint8_t* bytes; const uint32_t* off; uint32_t n, begin, end; bool want_spans;
+  __device__ void occurrence(uint32_t t0, uint32_t f) const {                                  // stage D
+    const uint32_t msg = message_of(off, n, t0);
+    if (t0 + (rs.factors[(size_t)f * 12 + 1] & 0xffu) > off[msg + 1]) return;                 // straddles two messages: not an occurrence
+    SlotSink sink(rs, w, msg, want_spans);
+    factor_confirmed(rs, f, t0 - off[msg], want_spans, sink);
   }
-  if (rs.n_always) for (uint32_t msg = tid; msg < n; msg += stride) {
+  __device__ bool pair_matches(uint32_t pos, uint32_t y, uint32_t* t0_out) const {             // stage C
+    const uint32_t f = y & 0xfffffu;
+    const int goff = (int)((y >> 20) & 31u) - 3;
+    const int64_t t0 = (int64_t)pos - goff;
+    const uint32_t* fw = T.factors + (size_t)f * 12;
+    if (t0 < (int64_t)begin || t0 + (int64_t)(fw[1] & 0xffu) > (int64_t)end) return false;
+    if (!factor_at_gram(fw, T.bytesets, bytes + t0, goff)) return false;
+    *t0_out = (uint32_t)t0; return true;
+  }
+};
+
+__global__ void __launch_bounds__(kConfirmThreads)
+confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, int want_spans, uint32_t cstep) {
+  __shared__ __align__(8) uint8_t rings[(kConfirmThreads / 32) * kConfirmWarpBytes];
+  ConfirmCtx cx{rs, w, {rs.bucket_start, rs.entries, rs.factors, rs.bytesets}, bytes, off, n, off[0], off[n], want_spans != 0};
+  const uint8_t* rk = rs.image + rs.rk_off;
+  const uint32_t kbits = rs.stride == 2 ? 8u : 4u, kshift = rs.stride == 2 ? 1u : 2u, n_shapes = rs.n_shapes;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u, FULL = 0xffffffffu;
+  // occurrences scan_kernel found itself (head check, trigger bytes)
+  for (uint32_t i = tid, n1 = min(w.counters[4], w.l1_cap); i < n1; i += nthreads) cx.occurrence(w.l1_pos[i], w.l1_fac[i]);
+  if (rs.n_always) for (uint32_t msg = tid; msg < n; msg += nthreads) {
     SlotSink sink(rs, w, msg, want_spans != 0);
     for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate_always(rs.always_rules[k]);
   }
+  const uint32_t nq = (rs.debug_flags & 1u) ? 0u : min(w.counters[20], w.l1_cap);
+  const uint32_t ring2 = smem_u32(rings) + (threadIdx.x >> 5) * kConfirmWarpBytes, ring3 = ring2 + kRing * 8, ring4 = ring3 + kRing * 8;
+  uint32_t next = (tid >> 5) * 32u;                            // this warp's next batch of the queue
+  const uint32_t stride_q = (nthreads >> 5) * 32u;
+  uint32_t h2 = 0, t2 = 0, h3 = 0, t3 = 0, h4 = 0, t4 = 0;    // ring k holds [hk, tk)
+  uint32_t accw = 0, cw = 0;                                    // stage A: this lane's flag word and chunk
+  uint32_t pos2 = 0, key2 = 0, s2 = n_shapes, e2 = 0, e2end = 0;    // stage B: this lane's gram, next shape, entry cursor
+  uint32_t flagged = 0, passed = 0, confirmed = 0;
+  for (;;) {
+    const uint32_t n4 = t4 - h4, n3 = t3 - h3, n2 = t2 - h2;
+    const bool busyB = __any_sync(FULL, e2 < e2end || s2 < n_shapes);
+    const bool busyA = __any_sync(FULL, accw != 0);
+    const bool more = next < nq;                                // (while the queue has batches left, partial rings wait for more)
+    if (n4 >= 32u || (n4 && !more && !busyA && !busyB && !n2 && !n3)) {
+      // ---- D
+      const uint32_t k = n4 < 32u ? n4 : 32u;
+      if (lane < k) {
+        uint32_t t0, f;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t0), "=r"(f) : "r"(ring4 + (((h4 + lane) & (kRing - 1)) << 3)));
+        cx.occurrence(t0, f);
+      }
+      h4 += k; __syncwarp();
+      continue;
+    }
+    if (n3 >= 32u || (n3 && !more && !busyA && !busyB && !n2)) {
+      // ---- C
+      const uint32_t k = n3 < 32u ? n3 : 32u;
+      bool ok = false; uint32_t t0 = 0, y = 0;
+      if (lane < k) {
+        uint32_t pos;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pos), "=r"(y) : "r"(ring3 + (((h3 + lane) & (kRing - 1)) << 3)));
+        ok = cx.pair_matches(pos, y, &t0);
+      }
+      const uint32_t mo = __ballot_sync(FULL, ok);
+      if (ok) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring4 + (((t4 + __popc(mo & lt)) & (kRing - 1)) << 3)), "r"(t0), "r"(y & 0xfffffu) : "memory");
+      t4 += __popc(mo); confirmed += __popc(mo); h3 += k; __syncwarp();
+      continue;
+    }
+    if (busyB) {
+      // ---- B, one step: compare one entry of the open bucket, or open the next shape's bucket
+      bool found = false; uint32_t y = 0;
+      if (e2 < e2end) {
+        const uint2 en = cx.T.entries[e2]; e2++;
+        if (en.x == (key2 & rs.shapes[s2 - 1u]) && (en.y >> 25) == s2 - 1u) { found = true; y = en.y; }
+      } else if (s2 < n_shapes) {
+        const uint32_t b = gram_bucket(key2 & rs.shapes[s2], s2, rs.nb_shift);
+        e2 = cx.T.bucket_start[b]; e2end = cx.T.bucket_start[b + 1]; s2++;
+      }
+      const uint32_t mf = __ballot_sync(FULL, found);
+      if (found) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring3 + (((t3 + __popc(mf & lt)) & (kRing - 1)) << 3)), "r"(pos2), "r"(y) : "memory");
+      t3 += __popc(mf); __syncwarp();
+      continue;
+    }
+    if (n2 >= 32u || (n2 && !more && !busyA)) {
+      // ---- B, new batch (ring 2 holds position and folded gram)
+      const uint32_t k = n2 < 32u ? n2 : 32u;
+      if (lane < k) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pos2), "=r"(key2) : "r"(ring2 + (((h2 + lane) & (kRing - 1)) << 3)));
+        s2 = 0; e2 = e2end = 0;
+      }
+      h2 += k; __syncwarp();
+      continue;
+    }
+    if (busyA) {
+      // ---- A, one flag bit per lane: gram, recheck map
+      bool pass = false; uint32_t pos = 0, key = 0;
+      if (accw) {
+        const uint32_t bit = 31u - __clz(accw);
+        accw ^= 1u << bit;
+        pos = ((cw - (bit / kbits + 1u) * cstep) * kbits + (kbits - 1u - bit % kbits)) << kshift;
+        if (pos < cx.end) {
+          const uint32_t* p4 = reinterpret_cast<const uint32_t*>(bytes + (pos & ~3u));
+          uint32_t g = __ldg(p4);
+          if (pos & 3u) g = __funnelshift_r(g, __ldg(p4 + 1), 8u * (pos & 3u));
+          key = gram_fold_word(g);
+          pass = gram_recheck_test(rk, key, rs.rk_mask);
+        }
+      }
+      const uint32_t mp = __ballot_sync(FULL, pass);
+      if (pass) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring2 + (((t2 + __popc(mp & lt)) & (kRing - 1)) << 3)), "r"(pos), "r"(key) : "memory");
+      t2 += __popc(mp); passed += __popc(mp); __syncwarp();
+      continue;
+    }
+    if (more) {
+      // ---- A, new batch
+      if (next + lane < nq) { const uint2 q = w.fq[next + lane]; cw = q.x; accw = q.y; }
+      flagged += __popc(accw);
+      next += stride_q;
+      continue;
+    }
+    break;
+  }
+  // statistics (lane 0 holds the warp-uniform counts; `flagged` is per lane)
+  flagged = __reduce_add_sync(FULL, flagged);
+  if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); if (confirmed) atomicAdd(&w.counters[21], confirmed); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -529,13 +664,18 @@ void prepare_scan_kernels() {
   cudaFuncSetAttribute(verify_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
 }
 
+// grid of the scan for a batch of n messages (confirm_kernel decodes the queue's chunk numbers with the same value)
+static uint32_t scan_grid(uint32_t n, int sm_count) {
+  uint32_t grid = (uint32_t)sm_count;
+  if (n < 4096) grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, n / 32u + 1u));         // tiny batches: fewer image loads
+  return grid;
+}
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, int sm_count, cudaStream_t stream) {
   if (n == 0) return 0;
   const size_t smem = (size_t)rs.image_bytes + kScanRingBytes;
   // the scanned range is only known on the device (off[0] .. off[n]); a warp tile is 512 bytes, messages are rarely shorter than 16
-  uint32_t grid = (uint32_t)sm_count;
-  if (n < 4096) grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, n / 32u + 1u));         // tiny batches: fewer image loads
+  const uint32_t grid = scan_grid(n, sm_count);
   const int np = rs.stride == 2 ? 2 : 1, nt = (int)rs.n_trig, bl = rs.bloom2 ? 1 : 0, th = scan_threads();
 #define CG_LAUNCH(P, T, B) if (np == P && nt == T && bl == B) { \
     if (th == 1024) scan_kernel<P, T, B, 1024><<<grid, 1024, smem, stream>>>(rs, w, d_bytes, d_off, n, d_words); \
@@ -546,8 +686,10 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   return 1;
 }
 
-int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
-  resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_off, n, want_spans ? 1 : 0);
+int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
+  if (n == 0) return 0;
+  const uint32_t cstep = scan_grid(n, sm_count) * (uint32_t)(scan_threads() / 32) * 32u;
+  confirm_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, want_spans ? 1 : 0, cstep);
   return 1;
 }
 
