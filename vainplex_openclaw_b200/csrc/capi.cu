@@ -104,7 +104,7 @@ struct cg_ruleset {
     if (h_counters) cudaFreeHost(h_counters);
     for (auto& e : e_cnt) if (e) cudaEventDestroy(e);
     for (void* p : allocs) cudaFree(p);
-    cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.fq); cudaFree(work.slot_of_msg);
+    cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.fq); cudaFree(work.pairs); cudaFree(work.slot_of_msg);
     cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
   }
 };
@@ -127,8 +127,8 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
   if (!w.counters) { CU(cudaMalloc((void**)&w.counters, kCounterWords * sizeof(uint32_t))); }
   if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
   if (l1_cap > w.l1_cap) {
-    cudaFree(w.l1_pos); cudaFree(w.l1_fac); cudaFree(w.fq); w.l1_pos = w.l1_fac = nullptr; w.fq = nullptr; w.l1_cap = 0;
-    CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_fac, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.fq, (size_t)l1_cap * 8));
+    cudaFree(w.l1_pos); cudaFree(w.l1_fac); cudaFree(w.fq); cudaFree(w.pairs); w.l1_pos = w.l1_fac = nullptr; w.fq = w.pairs = nullptr; w.l1_cap = 0;
+    CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_fac, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.fq, (size_t)l1_cap * 8)); CU(cudaMalloc((void**)&w.pairs, (size_t)l1_cap * 8));
     w.l1_cap = l1_cap;
   }
   if (slot_cap > w.slot_cap) {
@@ -174,7 +174,7 @@ void default_caps(const cg_ruleset* rs, uint32_t n, uint32_t* l1, uint32_t* slot
 // what an overflowed step teaches about the capacities the next one needs
 void learn_caps(cg_ruleset* rs, const uint32_t* hc) {
   const uint32_t flags = hc[3];
-  if (flags & ERR_L1_OVERFLOW) { const uint32_t need = std::max(hc[4], hc[20]); rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * need, need + 65536)); }
+  if (flags & ERR_L1_OVERFLOW) { const uint32_t need = std::max(std::max(hc[4], hc[20]), hc[22]); rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * need, need + 65536)); }
   if (flags & ERR_SLOT_OVERFLOW) rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096));
   if (flags & ERR_EVENT_OVERFLOW) rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096));
 }
@@ -219,7 +219,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
     float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_scan_ms = ms;
     uint32_t flags = hs->counters[3];
     if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
-    if (flags & ERR_L1_OVERFLOW) { l1_cap = std::max<uint32_t>(l1_cap * 2, std::max(hs->counters[4], hs->counters[20]) + 1024); continue; }
+    if (flags & ERR_L1_OVERFLOW) { l1_cap = std::max<uint32_t>(l1_cap * 2, std::max(std::max(hs->counters[4], hs->counters[20]), hs->counters[22]) + 1024); continue; }
     if (flags & ERR_SLOT_OVERFLOW) { slot_cap = std::max<uint32_t>(slot_cap * 4, hs->counters[0] + 1024); continue; }
     if (flags & ERR_EVENT_OVERFLOW) { event_cap = std::max<uint32_t>(event_cap * 4, hs->counters[1] + 1024); continue; }
     if (flags & ERR_SPAN_OVERFLOW) { span_cap = std::max<uint32_t>(span_cap * 4, hs->counters[2] + 1024); continue; }
@@ -360,7 +360,7 @@ int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out16[16]) {
   if (!rs || !out16) return fail(CG_ERR_INVALID_ARG, "null argument");
   if (!rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
   memcpy(out16, rs->last_counters, 64);
-  out16[4] += rs->last_counters[21];          // occurrences confirmed by scan_kernel itself + by confirm_kernel
+  if (!(rs->dev.debug_flags & 2u)) { out16[7] = rs->last_counters[19]; out16[8] = rs->last_counters[20]; out16[9] = rs->last_counters[22]; }   // grams past the recheck map, flag words, (gram, entry) pairs
   return CG_OK;
 }
 
@@ -418,6 +418,9 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), P.trig_list, &d.trig_list))) return rc;
   if ((rc = upload(rs.get(), H.bucket_start, &d.bucket_start))) return rc;
   { const uint32_t* ew = nullptr; if ((rc = upload(rs.get(), H.entry_words, &ew, 8))) return rc; d.entries = reinterpret_cast<const uint2*>(ew); }
+  { const uint32_t* sw = nullptr; if ((rc = upload(rs.get(), H.slot_words, &sw, 16))) return rc; d.slots = reinterpret_cast<const uint4*>(sw); }
+  if ((rc = upload(rs.get(), H.group_entries, &d.group_entries))) return rc;
+  d.slot_shift = H.slot_shift; d.slot_mask = H.n_slots - 1;
   d.n_factors = (uint32_t)P.factors.size();
   if ((rc = upload(rs.get(), H.factor_words, &d.factors, 16))) return rc;
   if ((rc = upload(rs.get(), P.bytesets, &d.bytesets, 8))) return rc;
@@ -698,7 +701,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     }
     hit->used = ++rs->graph_clock;
     CU(cudaGraphLaunch(hit->exec, st));
-    const int kk = 4 + (rs->dev.max_prog_len > 192 ? 1 : 0);       // kernels inside the graph: scan, resolve, verify (+ large-VM), finalize
+    const int kk = 6 + (rs->dev.max_prog_len > 192 ? 1 : 0);       // kernels inside the graph: scan, lookup, check, resolve, verify (+ large-VM), finalize
     G.launches += kk; G.stats.kernel_launches += kk;
   }
   if (rc == CG_OK) {

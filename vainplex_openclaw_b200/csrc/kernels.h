@@ -25,6 +25,9 @@ struct DevRuleset {
   const uint32_t* trig_list;
   const uint32_t* bucket_start;  // HBM copies of the level-1b tables
   const uint2* entries;
+  const uint4* slots;            // lookup_kernel's view of the same entries (ruleset_image.h): open-addressing table of groups
+  const uint32_t* group_entries; // entry words (factor | (gram offset + 3) << 20 | shape << 25) in group order
+  uint32_t slot_shift, slot_mask;
   uint32_t n_factors;
   uint32_t max_prog_len;         // longest Pike program of the set (picks the VM capacity)
   uint32_t debug_flags;          // CG_SCAN_DEBUG (experiments only): bit 0 = drop flagged grams (results wrong),
@@ -50,9 +53,10 @@ struct DevRuleset {
 struct ScanWork {
   uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (confirmed factor occurrences) [5]=verify cursor
                                  //           [6]=flagged grams (level 1a) [7..15]=debug [17]=n_heavy [18]=verify cursor (light events) [19]=grams past the recheck map
-                                 //           [20]=flag words queued [21]=factor occurrences confirmed by confirm_kernel
+                                 //           [20]=flag words queued [22]=(gram, entry) pairs queued
   uint32_t* l1_pos;              // [l1_cap] factor occurrences scan_kernel confirms itself (head check, trigger bytes): buffer offset of the
   uint32_t* l1_fac;              //          factor's first byte, factor id
+  uint2* pairs;                  // [l1_cap] lookup_kernel's (gram position, index into group_entries) pairs
   uint2* fq;                     // [l1_cap] scan_kernel's flag words: x = the lane's chunk number after the round, y = 4 tiles x 8 (4) probe bits
   uint32_t* slot_of_msg;         // [n] 0xffffffff = none yet (reset per step)
   uint32_t* slot_msg;            // [slot_cap]
@@ -75,7 +79,7 @@ constexpr uint64_t kWordIncomplete = ~0ull;      // result word of every message
 // d_bytes must be 16-byte aligned and readable up to 16 bytes past off[n].
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, int sm_count, cudaStream_t stream);
-// confirm: flag words -> grams -> recheck map -> level-1b lookup -> exact factors -> message, slot, candidates for the VM / direct hits
+// confirm (three launches): flag words -> grams -> recheck map -> level-1b lookup | exact factors | message, slot, candidates for the VM / direct hits
 int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream);

@@ -63,6 +63,26 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     H.entry_words.push_back(e.key & e.mask);
     H.entry_words.push_back(e.factor | ((uint32_t)(e.off + 3) << 20) | (shape_of[i] << 25));
   }
+  // ---- the same entries grouped by (masked key, shape) behind an open-addressing table (lookup_kernel)
+  {
+    std::vector<uint32_t> idx(P.entries.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
+    auto kof = [&](uint32_t i) { return std::make_pair(shape_of[i], P.entries[i].key & P.entries[i].mask); };
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return kof(a) < kof(b); });
+    uint32_t ns = 16; while (ns < idx.size() * 2) ns *= 2;
+    H.n_slots = ns; H.slot_shift = 32; { uint32_t t = ns; while (t > 1) { t >>= 1; H.slot_shift--; } }
+    H.slot_words.assign((size_t)ns * 4, 0);
+    for (size_t i = 0; i < idx.size();) {
+      size_t j = i; while (j < idx.size() && kof(idx[j]) == kof(idx[i])) j++;
+      const uint32_t s = shape_of[idx[i]], km = P.entries[idx[i]].key & P.entries[idx[i]].mask;
+      uint32_t slot = (uint32_t)(((km ^ (s * 0x9E3779B9u)) * kGramMult2) >> H.slot_shift);
+      while (H.slot_words[(size_t)slot * 4 + 3]) slot = (slot + 1) & (ns - 1);
+      H.slot_words[(size_t)slot * 4] = km; H.slot_words[(size_t)slot * 4 + 1] = s;
+      H.slot_words[(size_t)slot * 4 + 2] = (uint32_t)H.group_entries.size(); H.slot_words[(size_t)slot * 4 + 3] = (uint32_t)(j - i);
+      for (size_t k = i; k < j; k++) { const GramEntry& e = P.entries[idx[k]]; H.group_entries.push_back(e.factor | ((uint32_t)(e.off + 3) << 20) | (s << 25)); }
+      i = j;
+    }
+  }
   // ---- bitmap: one bit per key (optionally two in the same word: blocked Bloom filter).  Every false positive costs a pass
   // through stage 1 of the slow path, staging the image costs next to nothing: 128 KB unless the level-1b tables then no
   // longer fit beside it and the rule set is small enough for a denser bitmap (>= 128 bits per key)

@@ -19,6 +19,9 @@ struct HostImage {
   uint32_t dir_off = 0, ent_off = 0, nb_shift = 0, n_buckets = 0;
   std::vector<uint32_t> bucket_start;  // n_buckets + 1
   std::vector<uint32_t> entry_words;   // 2 words per level-1b entry, sorted by bucket: masked key, factor | (off + 3) << 20 | shape << 25
+  // the same entries as lookup_kernel reads them: grouped by (masked key, shape); an open-addressing table of uint4 slots
+  // {masked key, shape, first entry of the group, entries in the group (0 = empty slot)}, slot = hash >> slot_shift, linear probing
+  std::vector<uint32_t> slot_words, group_entries; uint32_t slot_shift = 0, n_slots = 0;
   std::vector<uint32_t> prog, prog_off, sets, first, alpha;
   std::vector<uint32_t> factor_words;  // 12 words per full factor (device layout)
   std::vector<uint16_t> ranges;

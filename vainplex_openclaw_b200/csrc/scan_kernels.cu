@@ -47,6 +47,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
+// (reads that must not push the level-1b tables out of L1: the text is touched once, the tables by every thread)
+__device__ __forceinline__ uint32_t ldg_stream32(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -333,153 +339,152 @@ struct SlotSink {
 };
 
 // ------------------------------------------------------------------------------------------
-// confirm_kernel: everything between "the bitmap flagged a gram" and "this (message, rule) goes to the VM".
-// A warp takes 32 flag words of scan_kernel's queue at a time, one per lane, and runs them through four stages; between
-// the stages the survivors are compacted through per-warp rings in shared memory, so that every stage runs with (nearly)
-// full warps although each keeps only a fraction of its input:
-//   A  one flag bit per lane and pass -> gram position; gram reloaded, folded, tested against the recheck map (the bitmap's
-//      false positives end here)                                                                       -> ring 2 (grams)
-//   B  level-1b lookup, one step per lane and pass: open the next shape's bucket, or compare one entry.  Grams of digit
-//      runs match dozens of factors: they keep one lane busy for dozens of cheap passes          -> ring 3 (gram, entry)
-//   C  exact comparison of the entry's factor at the position the gram implies                  -> ring 4 (factor occurrences)
-//   D  message of the occurrence (no straddling), slot, candidate for the VM / direct hit
-// Every stage is a chain of dependent loads; nothing synchronises warps with each other, and the grid keeps every SM's warp
-// slots full, so the chains of some thousand warps overlap (a block-wide version of this with barriers between the stages
-// spent half its time waiting for each stage's slowest thread).
-// The few occurrences scan_kernel queued directly (head check, trigger bytes) enter at D; rules without factors are
-// candidates for every message.
+// Everything between "the bitmap flagged a gram" and "this (message, rule) goes to the VM" is a chain of dependent loads
+// per item and keeps only a fraction of its input at every step.  Measured on the B200: inside scan_kernel that chain cost
+// more than the hot loop itself (32 warps per SM cannot hide it); as one kernel with barriers between the steps half the
+// time went into waiting for each step's slowest thread; as one kernel with per-warp pipelines every warp still walked a
+// dozen chains in sequence.  So each step is its own launch, one thread per item, the grid as wide as the item list, and
+// the lists live in HBM (an atomic per item, which the compiler aggregates per warp):
+//   lookup_kernel   flag word -> flag bits -> gram position; gram reloaded, folded, tested against the recheck map (the
+//                   bitmap's false positives end here); level-1b lookup                               -> (gram, entry) pairs
+//   check_kernel    exact comparison of the entry's factor at the position the gram implies          -> factor occurrences
+//   resolve_kernel  message of the occurrence (no straddling), slot, candidate for the VM / direct hit; also the occurrences
+//                   scan_kernel found itself (head check, trigger bytes) and the rules every message is a candidate for
 // ------------------------------------------------------------------------------------------
 constexpr int kConfirmThreads = 256;
-constexpr uint32_t kConfirmWarpBytes = kRing * (8 + 8 + 8);     // rings 2 (position, folded gram), 3 (position, entry), 4 (occurrence start, factor)
 
-struct ConfirmCtx {
-  const DevRuleset& rs; const ScanWork& w; GramTables T; const uint8_t* bytes; const uint32_t* off; uint32_t n, begin, end; bool want_spans;
-  __device__ void occurrence(uint32_t t0, uint32_t f) const {                                  // stage D
-    const uint32_t msg = message_of(off, n, t0);
-    if (t0 + (rs.factors[(size_t)f * 12 + 1] & 0xffu) > off[msg + 1]) return;                 // straddles two messages: not an occurrence
-    SlotSink sink(rs, w, msg, want_spans);
-    factor_confirmed(rs, f, t0 - off[msg], want_spans, sink);
+// Divergent loops are what makes this part slow (a warp walks its lanes' loops one after the other, and every step is a
+// load that has to come back first), so there are none in the common path: a warp takes 32 flag words, spreads their set
+// bits evenly over its lanes (prefix sum + search through shuffles), and every lane then runs a straight line:
+// gram -> recheck map -> one probe per shape of the open-addressing table -> one atomic -> its pairs.
+__global__ void __launch_bounds__(kConfirmThreads, 6)
+lookup_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, uint32_t cstep) {
+  const uint8_t* rk = rs.image + rs.rk_off;
+  const uint32_t kbits = rs.stride == 2 ? 8u : 4u, kshift = rs.stride == 2 ? 1u : 2u, n_shapes = rs.n_shapes, end = off[n];
+  const uint32_t nq = (rs.debug_flags & 1u) ? 0u : min(w.counters[20], w.l1_cap);
+  const uint32_t lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t flagged = 0, passed = 0;
+  for (uint32_t base = gwarp * 32u; base < nq; base += nwarps * 32u) {
+    uint2 q = make_uint2(0u, 0u);
+    if (base + lane < nq) q = w.fq[base + lane];
+    const uint32_t cnt = __popc(q.y);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
+    const uint32_t excl = incl - cnt, total = __shfl_sync(FULL, incl, 31);
+    flagged += lane == 0 ? total : 0u;
+    for (uint32_t g0 = 0; g0 < total; g0 += 32u) {
+      const uint32_t g = g0 + lane;
+      // the flag word that holds this lane's gram: the last lane whose exclusive prefix is <= g
+      uint32_t j = 0;
+#pragma unroll
+      for (int step = 16; step; step >>= 1) { const uint32_t t = __shfl_sync(FULL, excl, (j + step) & 31u); if (j + step < 32u && t <= g) j += step; }
+      uint32_t wj = __shfl_sync(FULL, q.y, j); const uint32_t cj = __shfl_sync(FULL, q.x, j), ej = __shfl_sync(FULL, excl, j);
+      bool active = g < total;
+      for (uint32_t r = active ? g - ej : 0u; r; r--) wj &= wj - 1u;          // drop the (g - ej) lowest set bits: rarely any
+      const uint32_t bit = active ? (uint32_t)__ffs((int)wj) - 1u : 0u;
+      const uint32_t pos = ((cj - (bit / kbits + 1u) * cstep) * kbits + (kbits - 1u - bit % kbits)) << kshift;
+      active = active && pos < end;
+      uint32_t key = 0;
+      if (rs.debug_flags & 8u) continue;                                     // (timing experiments)
+      if (rs.debug_flags & 4u) { key = pos * 2654435761u; active = active && (key & 1u); }
+      else if (active) {
+        const uint32_t* p4 = reinterpret_cast<const uint32_t*>(bytes + (pos & ~3u));
+        uint32_t gw = ldg_stream32(p4);
+        if (pos & 3u) gw = __funnelshift_r(gw, ldg_stream32(p4 + 1), 8u * (pos & 3u));
+        key = gram_fold_word(gw);
+      }
+      // recheck map and the first probe of every shape depend on the key alone: all issued before any is looked at
+      const uint32_t rh = gram_recheck_hash(key);
+      const uint32_t rkw = (rs.debug_flags & 16u) ? 0xffffffffu : active ? *reinterpret_cast<const uint32_t*>(rk + (rh & rs.rk_mask)) : 0u;
+      for (uint32_t s0 = 0; s0 < n_shapes; s0 += 4u) {
+        uint4 sl[4]; uint32_t slot[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+          const uint32_t s = s0 + u, km = key & rs.shapes[s & 15u];
+          slot[u] = ((km ^ (s * 0x9E3779B9u)) * kGramMult2) >> rs.slot_shift;
+          sl[u] = (active && s < n_shapes) ? rs.slots[slot[u]] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        const bool pass = active && ((rkw << (rh >> 27)) & 0x80000000u);
+        if (s0 == 0 && pass) passed++;
+        uint32_t tot = 0;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+          const uint32_t s = s0 + u, km = key & rs.shapes[s & 15u];
+          if (!pass) sl[u].w = 0;
+          while (sl[u].w && (sl[u].x != km || sl[u].y != s)) { slot[u] = (slot[u] + 1u) & rs.slot_mask; sl[u] = rs.slots[slot[u]]; }    // (linear probing; rarely a second slot)
+          tot += sl[u].w;
+        }
+        // one atomic per warp and pass reserves the pairs of all its lanes
+        uint32_t pin = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, pin, d); if (lane >= (uint32_t)d) pin += t; }
+        const uint32_t wtot = __shfl_sync(FULL, pin, 31);
+        if (!wtot) continue;
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&w.counters[22], wtot);
+        k = __shfl_sync(FULL, k, 0) + pin - tot;
+        if (lane == 0 && k + wtot > w.l1_cap) atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) for (uint32_t e = 0; e < sl[u].w; e++, k++) if (k < w.l1_cap) w.pairs[k] = make_uint2(pos, sl[u].z + e);
+      }
+    }
   }
-  __device__ bool pair_matches(uint32_t pos, uint32_t y, uint32_t* t0_out) const {             // stage C
+  passed = __reduce_add_sync(FULL, passed);
+  if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); }
+}
+
+// One thread per (gram, entry) pair, again a straight line: the factor's words and the sixteen text bytes it could cover are
+// fetched at once, then all element tests (one byte-set word each) are in flight together -- no early exit, no loop-carried load.
+__global__ void __launch_bounds__(kConfirmThreads, 8)
+check_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n) {
+  const uint32_t begin = off[0], end = off[n];
+  const uint32_t np = min(w.counters[22], w.l1_cap);
+  QueueEmit emit{w};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+    const uint2 pr = w.pairs[i];
+    const uint32_t y = rs.group_entries[pr.y];
     const uint32_t f = y & 0xfffffu;
     const int goff = (int)((y >> 20) & 31u) - 3;
-    const int64_t t0 = (int64_t)pos - goff;
-    const uint32_t* fw = T.factors + (size_t)f * 12;
-    if (t0 < (int64_t)begin || t0 + (int64_t)(fw[1] & 0xffu) > (int64_t)end) return false;
-    if (!factor_at_gram(fw, T.bytesets, bytes + t0, goff)) return false;
-    *t0_out = (uint32_t)t0; return true;
+    const int64_t t0 = (int64_t)pr.x - goff;
+    const uint4* fw4 = reinterpret_cast<const uint4*>(rs.factors + (size_t)f * 12);
+    const uint4 fa = fw4[0], fb = fw4[1], fc = fw4[2];          // rule, len | exact << 24, 16 x u16 set ids, pre, pre_alpha
+    const uint32_t flen = fa.y & 0xffu;
+    if (t0 < (int64_t)begin || t0 + (int64_t)flen > (int64_t)end) continue;
+    // the sixteen bytes from t0 on, from five aligned words (the buffer is readable 16 bytes past its end)
+    const uint32_t* tp = reinterpret_cast<const uint32_t*>(bytes + ((size_t)t0 & ~(size_t)3));
+    const uint32_t sh = 8u * ((uint32_t)t0 & 3u);
+    const uint32_t need = ((uint32_t)t0 & 3u) + flen;           // bytes from the first aligned word on (nothing past the factor's end is read)
+    const uint32_t a0 = ldg_stream32(tp), a1 = need > 4u ? ldg_stream32(tp + 1) : 0u, a2 = need > 8u ? ldg_stream32(tp + 2) : 0u, a3 = need > 12u ? ldg_stream32(tp + 3) : 0u, a4 = need > 16u ? ldg_stream32(tp + 4) : 0u;
+    const uint32_t tx[4] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh)};
+    const uint32_t sid[8] = {fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, fc.x, fc.y};
+    uint32_t ok = 1u;
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++) {
+      const uint32_t s = (sid[k >> 1] >> (16 * (k & 1))) & 0xffffu, b = (tx[k >> 2] >> (8 * (k & 3))) & 0xffu;
+      const uint32_t bit = (rs.bytesets[(size_t)(k < flen ? s : 0u) * 8 + (b >> 5)] >> (b & 31)) & 1u;
+      ok &= k < flen ? bit : 1u;
+    }
+    if (ok) emit((uint32_t)t0, f);
   }
-};
+}
 
-__global__ void __launch_bounds__(kConfirmThreads)
-confirm_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, int want_spans, uint32_t cstep) {
-  __shared__ __align__(8) uint8_t rings[(kConfirmThreads / 32) * kConfirmWarpBytes];
-  ConfirmCtx cx{rs, w, {rs.bucket_start, rs.entries, rs.factors, rs.bytesets}, bytes, off, n, off[0], off[n], want_spans != 0};
-  const uint8_t* rk = rs.image + rs.rk_off;
-  const uint32_t kbits = rs.stride == 2 ? 8u : 4u, kshift = rs.stride == 2 ? 1u : 2u, n_shapes = rs.n_shapes;
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u, FULL = 0xffffffffu;
-  // occurrences scan_kernel found itself (head check, trigger bytes)
-  for (uint32_t i = tid, n1 = min(w.counters[4], w.l1_cap); i < n1; i += nthreads) cx.occurrence(w.l1_pos[i], w.l1_fac[i]);
-  if (rs.n_always) for (uint32_t msg = tid; msg < n; msg += nthreads) {
+__global__ void __launch_bounds__(256)
+resolve_kernel(DevRuleset rs, ScanWork w, const uint32_t* __restrict__ off, uint32_t n, int want_spans) {
+  const uint32_t n1 = min(w.counters[4], w.l1_cap);
+  const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t i = tid; i < n1; i += stride) {
+    const uint32_t pos = w.l1_pos[i], f = w.l1_fac[i];
+    const uint32_t msg = message_of(off, n, pos);
+    if (pos + (rs.factors[(size_t)f * 12 + 1] & 0xffu) > off[msg + 1]) continue;     // straddles two messages: not an occurrence
+    SlotSink sink(rs, w, msg, want_spans != 0);
+    factor_confirmed(rs, f, pos - off[msg], want_spans != 0, sink);
+  }
+  if (rs.n_always) for (uint32_t msg = tid; msg < n; msg += stride) {
     SlotSink sink(rs, w, msg, want_spans != 0);
     for (uint32_t k = 0; k < rs.n_always; k++) sink.candidate_always(rs.always_rules[k]);
   }
-  const uint32_t nq = (rs.debug_flags & 1u) ? 0u : min(w.counters[20], w.l1_cap);
-  const uint32_t ring2 = smem_u32(rings) + (threadIdx.x >> 5) * kConfirmWarpBytes, ring3 = ring2 + kRing * 8, ring4 = ring3 + kRing * 8;
-  uint32_t next = (tid >> 5) * 32u;                            // this warp's next batch of the queue
-  const uint32_t stride_q = (nthreads >> 5) * 32u;
-  uint32_t h2 = 0, t2 = 0, h3 = 0, t3 = 0, h4 = 0, t4 = 0;    // ring k holds [hk, tk)
-  uint32_t accw = 0, cw = 0;                                    // stage A: this lane's flag word and chunk
-  uint32_t pos2 = 0, key2 = 0, s2 = n_shapes, e2 = 0, e2end = 0;    // stage B: this lane's gram, next shape, entry cursor
-  uint32_t flagged = 0, passed = 0, confirmed = 0;
-  for (;;) {
-    const uint32_t n4 = t4 - h4, n3 = t3 - h3, n2 = t2 - h2;
-    const bool busyB = __any_sync(FULL, e2 < e2end || s2 < n_shapes);
-    const bool busyA = __any_sync(FULL, accw != 0);
-    const bool more = next < nq;                                // (while the queue has batches left, partial rings wait for more)
-    if (n4 >= 32u || (n4 && !more && !busyA && !busyB && !n2 && !n3)) {
-      // ---- D
-      const uint32_t k = n4 < 32u ? n4 : 32u;
-      if (lane < k) {
-        uint32_t t0, f;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t0), "=r"(f) : "r"(ring4 + (((h4 + lane) & (kRing - 1)) << 3)));
-        cx.occurrence(t0, f);
-      }
-      h4 += k; __syncwarp();
-      continue;
-    }
-    if (n3 >= 32u || (n3 && !more && !busyA && !busyB && !n2)) {
-      // ---- C
-      const uint32_t k = n3 < 32u ? n3 : 32u;
-      bool ok = false; uint32_t t0 = 0, y = 0;
-      if (lane < k) {
-        uint32_t pos;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pos), "=r"(y) : "r"(ring3 + (((h3 + lane) & (kRing - 1)) << 3)));
-        ok = cx.pair_matches(pos, y, &t0);
-      }
-      const uint32_t mo = __ballot_sync(FULL, ok);
-      if (ok) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring4 + (((t4 + __popc(mo & lt)) & (kRing - 1)) << 3)), "r"(t0), "r"(y & 0xfffffu) : "memory");
-      t4 += __popc(mo); confirmed += __popc(mo); h3 += k; __syncwarp();
-      continue;
-    }
-    if (busyB) {
-      // ---- B, one step: compare one entry of the open bucket, or open the next shape's bucket
-      bool found = false; uint32_t y = 0;
-      if (e2 < e2end) {
-        const uint2 en = cx.T.entries[e2]; e2++;
-        if (en.x == (key2 & rs.shapes[s2 - 1u]) && (en.y >> 25) == s2 - 1u) { found = true; y = en.y; }
-      } else if (s2 < n_shapes) {
-        const uint32_t b = gram_bucket(key2 & rs.shapes[s2], s2, rs.nb_shift);
-        e2 = cx.T.bucket_start[b]; e2end = cx.T.bucket_start[b + 1]; s2++;
-      }
-      const uint32_t mf = __ballot_sync(FULL, found);
-      if (found) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring3 + (((t3 + __popc(mf & lt)) & (kRing - 1)) << 3)), "r"(pos2), "r"(y) : "memory");
-      t3 += __popc(mf); __syncwarp();
-      continue;
-    }
-    if (n2 >= 32u || (n2 && !more && !busyA)) {
-      // ---- B, new batch (ring 2 holds position and folded gram)
-      const uint32_t k = n2 < 32u ? n2 : 32u;
-      if (lane < k) {
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pos2), "=r"(key2) : "r"(ring2 + (((h2 + lane) & (kRing - 1)) << 3)));
-        s2 = 0; e2 = e2end = 0;
-      }
-      h2 += k; __syncwarp();
-      continue;
-    }
-    if (busyA) {
-      // ---- A, one flag bit per lane: gram, recheck map
-      bool pass = false; uint32_t pos = 0, key = 0;
-      if (accw) {
-        const uint32_t bit = 31u - __clz(accw);
-        accw ^= 1u << bit;
-        pos = ((cw - (bit / kbits + 1u) * cstep) * kbits + (kbits - 1u - bit % kbits)) << kshift;
-        if (pos < cx.end) {
-          const uint32_t* p4 = reinterpret_cast<const uint32_t*>(bytes + (pos & ~3u));
-          uint32_t g = __ldg(p4);
-          if (pos & 3u) g = __funnelshift_r(g, __ldg(p4 + 1), 8u * (pos & 3u));
-          key = gram_fold_word(g);
-          pass = gram_recheck_test(rk, key, rs.rk_mask);
-        }
-      }
-      const uint32_t mp = __ballot_sync(FULL, pass);
-      if (pass) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring2 + (((t2 + __popc(mp & lt)) & (kRing - 1)) << 3)), "r"(pos), "r"(key) : "memory");
-      t2 += __popc(mp); passed += __popc(mp); __syncwarp();
-      continue;
-    }
-    if (more) {
-      // ---- A, new batch
-      if (next + lane < nq) { const uint2 q = w.fq[next + lane]; cw = q.x; accw = q.y; }
-      flagged += __popc(accw);
-      next += stride_q;
-      continue;
-    }
-    break;
-  }
-  // statistics (lane 0 holds the warp-uniform counts; `flagged` is per lane)
-  flagged = __reduce_add_sync(FULL, flagged);
-  if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); if (confirmed) atomicAdd(&w.counters[21], confirmed); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -689,8 +694,11 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
 int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
   if (n == 0) return 0;
   const uint32_t cstep = scan_grid(n, sm_count) * (uint32_t)(scan_threads() / 32) * 32u;
-  confirm_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, want_spans ? 1 : 0, cstep);
-  return 1;
+  // (the list lengths are only known on the device: grids sized for full occupancy, grid-stride loops)
+  lookup_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, cstep);
+  check_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n);
+  resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_off, n, want_spans ? 1 : 0);
+  return 3;
 }
 
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
