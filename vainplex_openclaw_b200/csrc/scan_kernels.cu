@@ -387,9 +387,7 @@ lookup_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, cons
       const uint32_t pos = ((cj - (bit / kbits + 1u) * cstep) * kbits + (kbits - 1u - bit % kbits)) << kshift;
       active = active && pos < end;
       uint32_t key = 0;
-      if (rs.debug_flags & 8u) continue;                                     // (timing experiments)
-      if (rs.debug_flags & 4u) { key = pos * 2654435761u; active = active && (key & 1u); }
-      else if (active) {
+      if (active) {
         const uint32_t* p4 = reinterpret_cast<const uint32_t*>(bytes + (pos & ~3u));
         uint32_t gw = ldg_stream32(p4);
         if (pos & 3u) gw = __funnelshift_r(gw, ldg_stream32(p4 + 1), 8u * (pos & 3u));
@@ -397,7 +395,7 @@ lookup_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, cons
       }
       // recheck map and the first probe of every shape depend on the key alone: all issued before any is looked at
       const uint32_t rh = gram_recheck_hash(key);
-      const uint32_t rkw = (rs.debug_flags & 16u) ? 0xffffffffu : active ? *reinterpret_cast<const uint32_t*>(rk + (rh & rs.rk_mask)) : 0u;
+      const uint32_t rkw = active ? *reinterpret_cast<const uint32_t*>(rk + (rh & rs.rk_mask)) : 0u;
       for (uint32_t s0 = 0; s0 < n_shapes; s0 += 4u) {
         uint4 sl[4]; uint32_t slot[4];
 #pragma unroll
