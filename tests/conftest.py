@@ -32,7 +32,7 @@ def harness_lib():
     csrc = os.path.join(ROOT, "vainplex_openclaw_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "native", "vm_harness.cpp"), os.path.join(csrc, "rulec.cpp"),
             os.path.join(csrc, "ruleset_image.cpp")]
-    deps = srcs + [os.path.join(csrc, h) for h in ("pike_vm.h", "gram_filter.h", "rulec.h", "kernels.h", "ruleset_image.h")]
+    deps = srcs + [os.path.join(csrc, h) for h in ("pike_vm.h", "bitprog.h", "gram_filter.h", "rulec.h", "kernels.h", "ruleset_image.h")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-o", lib] + srcs)
     L = C.CDLL(lib)
@@ -52,4 +52,7 @@ def harness_lib():
     L.harness_l1_factor_counts.restype = C.c_uint32
     L.harness_l1_factor_counts.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p]
     L.harness_dump_factors.argtypes = [C.c_void_p]
+    L.harness_bitprog_stats.argtypes = [C.c_void_p]
+    L.harness_bitprog_eligible.argtypes = [C.c_void_p]
+    L.harness_bitprog_eligible.restype = C.c_uint32
     return L

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../vainplex_openclaw_b200/csrc/pike_vm.h"
+#include "../../vainplex_openclaw_b200/csrc/bitprog.h"
 #include "../../vainplex_openclaw_b200/csrc/gram_filter.h"
 #include "../../vainplex_openclaw_b200/csrc/ruleset_image.h"
 
@@ -61,7 +62,7 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   d.always_rules = H.pf.always_rules.data(); d.n_always = n_always;
   d.prog = H.prog.data(); d.rule_prog_off = H.prog_off.data(); d.sets = H.sets.data(); d.set_ranges = H.ranges.data();
   H.alpha.resize(H.alpha.size() + 8, 0);
-  d.rule_first = H.first.data(); d.rule_alpha = H.alpha.data(); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
+  d.rule_first = H.first.data(); d.rule_alpha = H.alpha.data(); d.bit_words = reinterpret_cast<const unsigned long long*>(H.bit_words.data()); d.bit_off = H.bit_off.data(); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
   h->T = GramTables{d.bucket_start, d.entries, d.factors, d.bytesets};
   return h;
 }
@@ -149,6 +150,7 @@ void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand,
   if (l1_hits) *l1_hits = fl;
 }
 
+static uint64_t g_bit_decided = 0, g_bit_mismatch = 0, g_bit_fallback = 0;
 // policy-mode verification exactly as verify_*_kernel does it: for every confirmed factor occurrence
 // run test_at_factor; returns the bitmap of rules that hit (direct hits included)
 void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits, uint32_t lead, uint32_t seed) {
@@ -164,9 +166,16 @@ void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits
     uint32_t r = occ[k], t0 = occ[k + 1], pre = occ[k + 2];
     if ((hits[r >> 5] >> (r & 31)) & 1u) continue;
     bool any = t0 == 0xffffffffu ? run_rule<false>(vm, d, r, m, len, ns) : test_at_factor(vm, d, r, m, len, t0, pre);
+    // the bit-parallel matcher (what resolve_kernel runs for eligible rules) must say the same whenever it says anything
+    if (t0 != 0xffffffffu && d.bit_off[r] != kBitProgNone) {
+      const int res = bitprog_test(reinterpret_cast<const uint64_t*>(d.bit_words) + d.bit_off[r], m, len, island_start(d, r, m, len, t0, pre), t0);
+      if (res >= 0) { g_bit_decided++; if ((res == 1) != any) g_bit_mismatch++; } else g_bit_fallback++;
+    }
     if (any) hits[r >> 5] |= 1u << (r & 31);
   }
 }
+void harness_bitprog_stats(uint64_t* out3) { out3[0] = g_bit_decided; out3[1] = g_bit_mismatch; out3[2] = g_bit_fallback; }
+uint32_t harness_bitprog_eligible(void* p) { Harness* h = (Harness*)p; uint32_t k = 0; for (uint32_t r = 0; r < h->d.n_rules; r++) k += h->d.bit_off[r] != kBitProgNone; return k; }
 
 // The whole device pipeline restated over a packed batch exactly as scan_kernel / resolve_kernel / verify see it: head
 // check at the start of the scanned range, gram probes over [off[0], off[n]) of the buffer, triggers, message_of() for every

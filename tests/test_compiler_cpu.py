@@ -293,3 +293,37 @@ def test_napi_shim_source_compiles_against_a_stub_header():
     r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "tests", "native"),
                         os.path.join(root, "napi", "openclaw_gov_napi.c")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_bit_parallel_matcher_agrees_with_the_vm(harness_lib, oracle):
+    """bitprog.h: for every confirmed factor occurrence of the tests above's kind of traffic AND of random regexes, the
+    bit-parallel matcher (resolve_kernel's fast path) either declines (non-ASCII island) or answers what the Pike VM
+    answers; most rules are eligible, and it does decide the bulk of the occurrences."""
+    import ctypes as C
+    from vainplex_openclaw_b200 import workload as W
+    stats = (C.c_uint64 * 3)()
+    harness_lib.harness_bitprog_stats(stats)
+    base = list(stats)
+    rl = W.make_rules(300)
+    rules = W.rules_as_tuples(rl)
+    h = Harness(harness_lib, rules)
+    assert harness_lib.harness_bitprog_eligible(h.h) >= 0.8 * len(rules)
+    d, o, _ = W.make_messages(3000, 200, rl, p_hit=0.3, seed=11, utf8_frac=0.1) if "utf8_frac" in W.make_messages.__code__.co_varnames else W.make_messages(3000, 200, rl, p_hit=0.3, seed=11)
+    buf = d.numpy(); off = o.numpy()
+    for i in range(3000):
+        h.policy_hits(bytes(buf[int(off[i]):int(off[i + 1])]), lead=i % 19, seed=i)
+    h.close()
+    rng = np.random.default_rng(77)
+    for k in range(300):
+        src = random_regex(rng)
+        hh = Harness(harness_lib, [(src, int(rng.integers(0, 2)), 0)])
+        if int(hh.status[0]) == 0:
+            for j in range(40):
+                n = int(rng.integers(0, 60))
+                m = bytes(rng.choice(np.frombuffer(b"abcxyz019 _-.@\n", dtype=np.uint8), n)) if n else b""
+                hh.policy_hits(m, lead=j % 5, seed=j)
+        hh.close()
+    harness_lib.harness_bitprog_stats(stats)
+    decided, mismatch, fallback = (int(stats[i]) - int(base[i]) for i in range(3))
+    assert mismatch == 0, (decided, mismatch, fallback)
+    assert decided > 800 and decided > fallback

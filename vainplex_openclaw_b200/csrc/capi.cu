@@ -432,6 +432,9 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), ranges, &d.set_ranges, 8))) return rc;
   if ((rc = upload(rs.get(), first, &d.rule_first, 8))) return rc;
   if ((rc = upload(rs.get(), H.alpha, &d.rule_alpha, 8))) return rc;
+  { const uint64_t* bw = nullptr; if ((rc = upload(rs.get(), H.bit_words, &bw, 8))) return rc; d.bit_words = reinterpret_cast<const unsigned long long*>(bw); }
+  if ((rc = upload(rs.get(), H.bit_off, &d.bit_off))) return rc;
+  if (getenv("CG_NO_BITPROG")) d.bit_words = nullptr;
   d.rule_policy = nullptr; d.rule_action = nullptr;
   d.n_rules = n_rules; d.rw = (n_rules + 31) / 32; if (d.rw == 0) d.rw = 1;
   d.max_prog_len = 0; for (uint32_t i = 0; i < n_rules; i++) d.max_prog_len = std::max(d.max_prog_len, prog_off[i + 1] - prog_off[i]);

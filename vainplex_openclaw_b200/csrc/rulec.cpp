@@ -895,4 +895,54 @@ bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOpti
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bit-parallel form of a Pike program (bitprog.h)
+bool build_bitprog(const CompiledRule& r, uint64_t* out) {
+  const std::vector<uint32_t>& prog = r.prog;
+  if (r.status != RULE_OK || prog.empty()) return false;
+  std::vector<int> bit_of(prog.size(), -1); int nc = 0;
+  for (size_t pc = 0; pc < prog.size(); pc++) {
+    const uint32_t op = prog[pc] & 0xff;
+    if (op == OP_CHAR || op == OP_SET || op == OP_ANY) { if (nc >= 63) return false; bit_of[pc] = nc++; }
+    else if (op == OP_LOOKAHEAD || op == OP_NLOOKAHEAD || op == OP_LOOKBEHIND || op == OP_NLOOKBEHIND) return false;
+  }
+  for (uint32_t i = 0; i < 128 + 8 * 64 + 8; i++) out[i] = 0;
+  // accept[b]: the consuming instructions an ASCII byte satisfies
+  for (size_t pc = 0; pc < prog.size(); pc++) {
+    if (bit_of[pc] < 0) continue;
+    const uint32_t op = prog[pc] & 0xff, arg = prog[pc] >> 8;
+    for (int b = 0; b < 128; b++) {
+      bool ok = op == OP_CHAR ? (uint32_t)b == arg : op == OP_ANY ? !(b == 0x0a || b == 0x0d) : ((r.sets[arg].ascii[b >> 5] >> (b & 31)) & 1u) != 0;
+      if (ok) out[b] |= 1ull << bit_of[pc];
+    }
+  }
+  // closure of the epsilon edges from pc under context ctx (bit 0 word boundary, bit 1 start of message, bit 2 end)
+  auto closure = [&](uint32_t pc0, uint32_t ctx) {
+    uint64_t m = 0; std::vector<char> seen(prog.size(), 0); std::vector<uint32_t> st{pc0};
+    while (!st.empty()) {
+      uint32_t pc = st.back(); st.pop_back();
+      if (pc >= prog.size() || seen[pc]) continue;
+      seen[pc] = 1;
+      const uint32_t op = prog[pc] & 0xff, arg = prog[pc] >> 8;
+      switch (op) {
+        case OP_SPLIT_NEXT: case OP_SPLIT_JUMP: st.push_back(pc + 1); st.push_back(arg); break;
+        case OP_JMP: case OP_JMP_BACK: st.push_back(arg); break;
+        case OP_EMPTYCHK: st.push_back(pc + 1); break;
+        case OP_BOL: if (ctx & 2u) st.push_back(pc + 1); break;
+        case OP_EOL: if (ctx & 4u) st.push_back(pc + 1); break;
+        case OP_WORDB: if (ctx & 1u) st.push_back(pc + 1); break;
+        case OP_NWORDB: if (!(ctx & 1u)) st.push_back(pc + 1); break;
+        case OP_MATCH: m |= 1ull << 63; break;
+        default: m |= 1ull << bit_of[pc]; break;
+      }
+    }
+    return m;
+  };
+  for (uint32_t ctx = 0; ctx < 8; ctx++) {
+    for (size_t pc = 0; pc < prog.size(); pc++) if (bit_of[pc] >= 0) out[128 + ctx * 64 + bit_of[pc]] = closure((uint32_t)pc + 1, ctx);
+    out[128 + 8 * 64 + ctx] = closure(0, ctx);
+  }
+  return true;
+}
+
 }  // namespace cg

@@ -79,6 +79,10 @@ struct CompiledRule {
 // flags: bit0 = ignoreCase ("i").  `src` is the JS pattern source encoded as UTF-8.
 CompiledRule compile_rule(const char* src, size_t len, uint32_t flags);
 
+// Bit-parallel form of a rule's Pike program (bitprog.h): accept[128], follow[8][64], start[8] as uint64 words (648 of them).
+// false when the program has more than 63 consuming instructions or uses lookaround: such rules stay with the Pike VM.
+bool build_bitprog(const CompiledRule& r, uint64_t* out648);
+
 // ---- prefilter: a stateless two-level filter over every rule's *necessary factors* (byte-set sequences every
 // match must contain; <= kMaxFactorElems elements are kept per factor).
 //   level 1a  every aligned 4-byte gram of the batch buffer (stride 4), or every even-offset gram (stride 2), is

@@ -15,6 +15,7 @@
 #include "kernels.h"
 #include "rulec.h"
 #include "pike_vm.h"
+#include "bitprog.h"
 #include "gram_filter.h"
 #include <algorithm>
 
@@ -287,6 +288,7 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
 // ------------------------------------------------------------------------------------------
 struct SlotSink {
   const DevRuleset& rs; const ScanWork& w; uint32_t msg; uint32_t slot;
+  const uint8_t* text = nullptr; uint32_t text_len = 0;       // the message (policy mode: lets candidate() decide eligible rules on the spot)
   __device__ SlotSink(const DevRuleset& r, const ScanWork& wk, uint32_t m, bool ws) : rs(r), w(wk), msg(m), slot(0xffffffffu), want_spans(ws) {}
   __device__ bool ensure_slot() {
     if (slot != 0xffffffffu) return slot < w.slot_cap;
@@ -307,6 +309,17 @@ struct SlotSink {
   // policy mode: one VM run per confirmed factor occurrence, restricted to its island.
   bool want_spans;
   __device__ void candidate(uint32_t r, uint32_t t0, uint32_t pre) {
+    // policy mode, rule with a bit-parallel program, ASCII island: RegExp.test around this occurrence is decided right here
+    // (bitprog.h) -- no slot for a miss, no VM run for a hit
+    if (!want_spans && text && rs.bit_words) {
+      const uint32_t bo = rs.bit_off[r];
+      if (bo != kBitProgNone) {
+        if (slot == 0xffffffffu) { const uint32_t s0 = *reinterpret_cast<volatile uint32_t*>(&w.slot_of_msg[msg]); if (s0 != 0xffffffffu && s0 < w.slot_cap && ((w.hit[(size_t)s0 * rs.rw + (r >> 5)] >> (r & 31)) & 1u)) return; }   // already a hit
+        const int res = bitprog_test(reinterpret_cast<const uint64_t*>(rs.bit_words) + bo, text, text_len, island_start(rs, r, text, text_len, t0, pre), t0, 96u);
+        if (res == 0) return;
+        if (res == 1) { direct(r); return; }
+      }
+    }
     if (!ensure_slot()) return;
     uint32_t bit = 1u << (r & 31);
     uint32_t old = atomicOr(&w.cand[(size_t)slot * rs.rw + (r >> 5)], bit);
@@ -469,7 +482,7 @@ check_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const
 }
 
 __global__ void __launch_bounds__(256)
-resolve_kernel(DevRuleset rs, ScanWork w, const uint32_t* __restrict__ off, uint32_t n, int want_spans) {
+resolve_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, int want_spans) {
   const uint32_t n1 = min(w.counters[4], w.l1_cap);
   const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
   for (uint32_t i = tid; i < n1; i += stride) {
@@ -477,6 +490,7 @@ resolve_kernel(DevRuleset rs, ScanWork w, const uint32_t* __restrict__ off, uint
     const uint32_t msg = message_of(off, n, pos);
     if (pos + (rs.factors[(size_t)f * 12 + 1] & 0xffu) > off[msg + 1]) continue;     // straddles two messages: not an occurrence
     SlotSink sink(rs, w, msg, want_spans != 0);
+    sink.text = bytes + off[msg]; sink.text_len = off[msg + 1] - off[msg];
     factor_confirmed(rs, f, pos - off[msg], want_spans != 0, sink);
   }
   if (rs.n_always) for (uint32_t msg = tid; msg < n; msg += stride) {
@@ -695,7 +709,7 @@ int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byt
   // (the list lengths are only known on the device: grids sized for full occupancy, grid-stride loops)
   lookup_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, cstep);
   check_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n);
-  resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_off, n, want_spans ? 1 : 0);
+  resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_bytes, d_off, n, want_spans ? 1 : 0);
   return 3;
 }
 
