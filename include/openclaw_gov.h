@@ -198,6 +198,8 @@ CG_API void cg_merkle_log_destroy(cg_merkle_log *log);
 CG_API int cg_merkle_log_append(cg_merkle_log *log, const uint8_t *bytes, const uint64_t *offsets, uint64_t n);   /* host buffers */
 /* the day file itself (src/audit-trail.ts:151-179: JSON lines joined with "\n", trailing "\n" per flush): split at '\n' on the
  * device, every line without its '\n' is one leaf (an unterminated last line counts); *out_lines = leaves appended */
+/* capacity for n_leaves more leaves / n_bytes of leaf bytes per append, allocated now instead of by the appends */
+CG_API int cg_merkle_log_reserve(cg_merkle_log *log, uint64_t n_leaves, uint64_t n_bytes);
 CG_API int cg_merkle_log_append_jsonl(cg_merkle_log *log, const uint8_t *bytes, uint64_t len, uint64_t *out_lines);
 CG_API int cg_merkle_log_size(const cg_merkle_log *log, uint64_t *out_n);
 CG_API int cg_merkle_log_root(cg_merkle_log *log, uint8_t out_root[32]);      /* == cg_merkle_root over every leaf appended so far */

@@ -551,6 +551,36 @@ def test_sha256_ragged_alignment(N, oracle):
     assert N.merkle_root(data, sub) == oracle.merkle_root(data, sub)
 
 
+def test_programs_longer_than_the_small_vm(N, oracle):
+    """verify_large_kernel: rules whose Pike program exceeds the shared-memory VM's 192 instructions (and the bit-parallel
+    matcher's 63) -- policy words and spans equal the oracle's."""
+    rules = [(r"tok_[a-f0-9]{200}z", 0, 0), (r"(?:ab|cd|ef){70}!", 0, 1), (r"sk-[a-zA-Z0-9]{20,}", 0, 2), (r"key=[A-Z]{100}[0-9]{100}\\b", 1, 3)]
+    rng = np.random.default_rng(192)
+    hexd = b"0123456789abcdef"
+    msgs = []
+    for i in range(400):
+        k = i % 8
+        if k == 0: body = b"tok_" + bytes(rng.choice(np.frombuffer(hexd, dtype=np.uint8), 200)) + b"z"
+        elif k == 1: body = b"tok_" + bytes(rng.choice(np.frombuffer(hexd, dtype=np.uint8), 199)) + b"z"          # one short
+        elif k == 2: body = b"".join([b"ab", b"cd", b"ef"][int(x)] for x in rng.integers(0, 3, 70)) + b"!"
+        elif k == 3: body = b"".join([b"ab", b"cd", b"ef"][int(x)] for x in rng.integers(0, 3, 69)) + b"x!"
+        elif k == 4: body = b"KEY=" + b"Q" * 100 + b"7" * 100
+        elif k == 5: body = b"key=" + b"q" * 100 + b"7" * 100 + b"a"                                             # \\b fails
+        elif k == 6: body = b"sk-" + b"a1B2" * 6
+        else: body = b"nothing to see"
+        msgs.append(b"pad " * int(rng.integers(0, 5)) + body + b" tail" * int(rng.integers(0, 3)))
+    rs = N.Ruleset(rules, strict=True)
+    assert rs.info().program_words > 600
+    data, off = N.pack(msgs)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert np.array_equal(words, ewords) and [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits and len(ehits) >= 200
+    spans = rs.find_matches_batch(data, off)
+    got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
+    assert got == oracle_spans(oracle, rules, data, off) and len(got) >= 200
+    rs.close()
+
+
 def test_non_ascii_rule_packs_on_the_kernels(N, oracle):
     """CJK / Cyrillic / Hangul literal alternations, classes with CJK ranges, `.*` between literals and the
     lazy PEM block: policy words, hits and resolved spans equal the oracle's."""

@@ -51,7 +51,7 @@ EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_c
            "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_scan_join", "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch",
            "cg_merkle_log_create", "cg_merkle_log_destroy", "cg_merkle_log_append", "cg_merkle_log_size", "cg_merkle_log_root",
            "cg_merkle_log_frontier", "cg_merkle_log_restore", "cg_merkle_log_proof", "cg_merkle_verify_proof",
-           "cg_merkle_log_append_jsonl", "cg_merkle_log_consistency", "cg_merkle_verify_consistency",
+           "cg_merkle_log_append_jsonl", "cg_merkle_log_consistency", "cg_merkle_verify_consistency", "cg_merkle_log_reserve",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -99,6 +99,7 @@ def load():
     L.cg_merkle_log_proof.argtypes = [vp, u64, vp, u32, vp]; L.cg_merkle_log_proof.restype = i32
     L.cg_merkle_verify_proof.argtypes = [vp, u64, u64, u64, vp, u32, vp, vp]; L.cg_merkle_verify_proof.restype = i32
     L.cg_merkle_log_append_jsonl.argtypes = [vp, vp, u64, vp]; L.cg_merkle_log_append_jsonl.restype = i32
+    L.cg_merkle_log_reserve.argtypes = [vp, u64, u64]; L.cg_merkle_log_reserve.restype = i32
     L.cg_merkle_log_consistency.argtypes = [vp, u64, vp, u32, vp]; L.cg_merkle_log_consistency.restype = i32
     L.cg_merkle_verify_consistency.argtypes = [u64, u64, vp, vp, vp, u32, vp]; L.cg_merkle_verify_consistency.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
@@ -357,6 +358,9 @@ class MerkleLog:
         off[1:] = np.cumsum([len(x) for x in leaves])
         data = np.frombuffer(b"".join(leaves) + b"\0" * 64, dtype=np.uint8).copy()
         check(load().cg_merkle_log_append(self.handle, data.ctypes.data, off.ctypes.data, len(leaves)))
+
+    def reserve(self, n_leaves: int, n_bytes: int = 0):
+        check(load().cg_merkle_log_reserve(self.handle, n_leaves, n_bytes))
 
     def append_packed(self, data: np.ndarray, off64: np.ndarray):
         """leaves already packed: data uint8, off64 uint64 (m + 1 entries)."""

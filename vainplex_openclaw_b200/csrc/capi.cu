@@ -983,6 +983,18 @@ int ensure_copy_streams() {
 }
 }  // namespace
 
+/* room for n_leaves more leaf digests and their bytes up front (an append that has to grow the digest store pays a device
+ * allocation and a copy of everything kept so far) */
+int cg_merkle_log_reserve(cg_merkle_log* L, uint64_t n_leaves, uint64_t n_bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = log_check(L); if (rc) return rc;
+  uint32_t* unused;
+  if (n_leaves && (rc = log_digest_room(L, n_leaves, G.stream, &unused))) return rc;
+  if (n_bytes && (rc = grow_bytes((size_t)n_bytes + 64))) return rc;
+  if (n_leaves && (rc = grow(&G.d_off64, &G.cap_off64, (size_t)n_leaves + 1))) return rc;
+  return CG_OK;
+}
+
 int cg_merkle_log_append(cg_merkle_log* L, const uint8_t* bytes, const uint64_t* offsets, uint64_t m) {
   std::lock_guard<std::mutex> lk(g_mu);
   int rc = log_check(L); if (rc) return rc;
