@@ -23,7 +23,7 @@ from __future__ import annotations
 import json
 import re
 import time
-from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -457,6 +457,272 @@ class MessagePolicy:
         return out
 
 
+# ------------------------------------------------------------------------------------- full policy slice
+
+TIER_ORDINAL = {"untrusted": 0, "restricted": 1, "standard": 2, "trusted": 3, "elevated": 4}     # util.ts:201-210
+
+
+def _glob_match(pattern: str, value: str) -> bool:
+    """util.ts:68-74 globToRegex + test (anchored; `*` = `.*`, `?` = `.`; `.` does not match line terminators)."""
+    import re
+    esc = re.sub(r"[.+^${}()|\[\]\\]", lambda m: "\\" + m.group(0), pattern).replace("*", "[^\\n\\r\\u2028\\u2029]*").replace("?", "[^\\n\\r\\u2028\\u2029]")
+    return re.fullmatch(esc, value) is not None
+
+
+class PolicyEvaluator:
+    """policy-evaluator.ts:18-146 with every text test routed to the device in ONE batch per call:
+
+      * matchesScope (:18-26: excludeAgents, channels), sortPolicies (:36-42: priority desc, then specificity
+        agents 10 / channels 5 / hooks 3), matchPolicy (:128-146: first rule whose trust gates and conditions hold),
+        aggregateMatches (:44-80: deny > 2fa > audit > allow, the reference's reason strings);
+      * conditions: `context` (messageContains, conversationContains, channel, hasMetadata, sessionKey --
+        conditions/context.ts:9-76), `tool` (name glob; params equals / contains / matches / startsWith / in --
+        conditions/tool.ts:10-84), `agent` (id glob, trustTier), `any`, `not` (conditions/simple.ts:39-150); `time`, `risk`
+        and `frequency` conditions are not on the scan path and are taken from a caller-supplied callback
+        (`other_condition(cond, ctx) -> bool`, default False like an unknown evaluator, conditions/index.ts:44-46).
+
+    Every regex of every policy (messageContains / conversationContains patterns, `matches` param matchers) is one rule
+    of one device rule set; a call packs the message, the conversation entries and the tool-parameter strings of all its
+    contexts into one batch, scans it once, and the boolean tree is evaluated on the host from the hit list."""
+
+    def __init__(self, policies: Sequence[dict], logger=None, other_condition=None, scanner_cls=None):
+        self.policies = [p for p in policies if p.get("enabled", True)]
+        self.other = other_condition or (lambda cond, ctx: False)
+        self.pattern_rule: Dict[str, int] = {}
+        rules: List[List[str]] = []
+
+        def reg(pat: str):
+            if pat not in self.pattern_rule:
+                self.pattern_rule[pat] = len(rules)
+                rules.append([pat])
+
+        def walk(cond):
+            t = cond.get("type")
+            if t == "context":
+                for key in ("messageContains", "conversationContains"):
+                    v = cond.get(key)
+                    if v is not None:
+                        for pat in ([v] if isinstance(v, str) else v):
+                            reg(pat)
+            elif t == "tool":
+                for m in (cond.get("params") or {}).values():
+                    if "matches" in m:
+                        self.tool_matches.add(m["matches"])
+            elif t == "any":
+                for sub in cond.get("conditions", []):
+                    walk(sub)
+            elif t == "not":
+                walk(cond["condition"])
+
+        self.tool_matches = set()
+        for p in self.policies:
+            for r in p.get("rules", []):
+                for c in r.get("conditions", []):
+                    walk(c)
+        # tool `matches` patterns: an invalid one never matches (tool.ts:39-44), unlike messageContains' includes() fallback
+        self.tool_rule: Dict[str, int] = {}
+        for pat in sorted(self.tool_matches):
+            if N.rule_check(pat, 0) == 0:
+                self.tool_rule[pat] = len(rules)
+                rules.append([pat])
+        self.scanner = (scanner_cls or RuleScanner)(rules, logger) if rules else None
+
+    # -- one batch for all contexts
+    def evaluate_batch(self, contexts: Sequence[dict]) -> List[dict]:
+        texts: List[str] = []
+        where: List[Tuple[int, str, object]] = []          # (context index, kind, key)
+        for ci, ctx in enumerate(contexts):
+            if ctx.get("messageContent"):
+                texts.append(ctx["messageContent"]); where.append((ci, "msg", None))
+            for k, t in enumerate(ctx.get("conversationContext") or []):
+                texts.append(t); where.append((ci, "conv", k))
+            for key, val in (ctx.get("toolParams") or {}).items():
+                if isinstance(val, str):
+                    texts.append(val); where.append((ci, "param", key))
+        hits = self.scanner.scan(texts) if (self.scanner and texts) else [[] for _ in texts]
+        per_ctx = [{"msg": set(), "conv": set(), "param": {}} for _ in contexts]
+        for (ci, kind, key), h in zip(where, hits):
+            if kind == "param":
+                per_ctx[ci]["param"][key] = set(h)
+            else:
+                per_ctx[ci][kind].update(h)
+        return [self._evaluate(ctx, per_ctx[ci]) for ci, ctx in enumerate(contexts)]
+
+    def evaluate(self, ctx: dict) -> dict:
+        return self.evaluate_batch([ctx])[0]
+
+    # -- policy-evaluator.ts
+    @staticmethod
+    def _matches_scope(policy: dict, ctx: dict) -> bool:
+        scope = policy.get("scope") or {}
+        if ctx.get("agentId") in (scope.get("excludeAgents") or []):
+            return False
+        ch = scope.get("channels") or []
+        if ch and (not ctx.get("channel") or ctx["channel"] not in ch):
+            return False
+        return True
+
+    @staticmethod
+    def _specificity(policy: dict) -> int:
+        scope = policy.get("scope") or {}
+        return (10 if scope.get("agents") else 0) + (5 if scope.get("channels") else 0) + (3 if scope.get("hooks") else 0)
+
+    def _evaluate(self, ctx: dict, hit: dict) -> dict:
+        applicable = [p for p in self.policies if self._matches_scope(p, ctx)]
+        applicable.sort(key=lambda p: (-(p.get("priority") or 0), -self._specificity(p)))        # stable, like Array.prototype.sort
+        tier = TIER_ORDINAL[((ctx.get("trust") or {}).get("session") or {}).get("tier", "standard")]
+        matches = []
+        for p in applicable:
+            for r in p.get("rules", []):
+                if r.get("minTrust") and not tier >= TIER_ORDINAL[r["minTrust"]]:
+                    continue
+                if r.get("maxTrust") and not tier <= TIER_ORDINAL[r["maxTrust"]]:
+                    continue
+                if all(self._cond(c, ctx, hit) for c in r.get("conditions", [])):
+                    matches.append({"policyId": p["id"], "ruleId": r.get("id"), "effect": r.get("effect", {"action": "allow"}),
+                                    "controls": p.get("controls") or []})
+                    break
+        deny = next((m for m in matches if m["effect"]["action"] == "deny"), None)
+        twofa = next((m for m in matches if m["effect"]["action"] == "2fa"), None)
+        audit = any(m["effect"]["action"] == "audit" for m in matches)
+        if deny:
+            return {"action": "deny", "reason": deny["effect"].get("reason") or "Denied by governance policy", "matches": matches}
+        if twofa:
+            return {"action": "2fa", "reason": twofa["effect"].get("reason") or "Requires 2FA approval", "matches": matches}
+        if audit:
+            return {"action": "allow", "reason": "Allowed with audit logging", "matches": matches}
+        return {"action": "allow", "reason": "Allowed by governance policy" if matches else "No matching policies", "matches": matches}
+
+    # -- conditions/*.ts
+    def _any_pattern(self, patterns, hitset) -> bool:
+        return any(self.pattern_rule[p] in hitset for p in ([patterns] if isinstance(patterns, str) else patterns))
+
+    def _cond(self, c: dict, ctx: dict, hit: dict) -> bool:
+        t = c.get("type")
+        if t == "context":
+            if c.get("conversationContains") is not None:
+                if not (ctx.get("conversationContext") or []) or not self._any_pattern(c["conversationContains"], hit["conv"]):
+                    return False
+            if c.get("messageContains") is not None:
+                if not ctx.get("messageContent") or not self._any_pattern(c["messageContains"], hit["msg"]):
+                    return False
+            if c.get("hasMetadata") is not None:
+                keys = c["hasMetadata"] if isinstance(c["hasMetadata"], list) else [c["hasMetadata"]]
+                if not all(k in (ctx.get("metadata") or {}) for k in keys):
+                    return False
+            if c.get("channel") is not None:
+                chans = c["channel"] if isinstance(c["channel"], list) else [c["channel"]]
+                if not ctx.get("channel") or ctx["channel"] not in chans:
+                    return False
+            if c.get("sessionKey") is not None:
+                if not ctx.get("sessionKey") or not _glob_match(c["sessionKey"], ctx["sessionKey"]):
+                    return False
+            return True
+        if t == "tool":
+            if c.get("name") is not None:
+                tn = ctx.get("toolName")
+                names = c["name"] if isinstance(c["name"], list) else [c["name"]]
+                if not tn or not any(_glob_match(p, tn) if ("*" in p or "?" in p) else p == tn for p in names):
+                    return False
+            if c.get("params"):
+                tp = ctx.get("toolParams")
+                if not tp:
+                    return False
+                for key, m in c["params"].items():
+                    v = tp.get(key)
+                    if "equals" in m:
+                        ok = v == m["equals"] and type(v) == type(m["equals"])
+                    elif "contains" in m:
+                        ok = isinstance(v, str) and m["contains"] in v
+                    elif "matches" in m:
+                        ok = isinstance(v, str) and m["matches"] in self.tool_rule and self.tool_rule[m["matches"]] in hit["param"].get(key, set())
+                    elif "startsWith" in m:
+                        ok = isinstance(v, str) and v.startswith(m["startsWith"])
+                    elif "in" in m:
+                        ok = v in m["in"]
+                    else:
+                        ok = False
+                    if not ok:
+                        return False
+            return True
+        if t == "agent":
+            if c.get("id") is not None:
+                ids = c["id"] if isinstance(c["id"], list) else [c["id"]]
+                aid = ctx.get("agentId", "")
+                if not any(_glob_match(p, aid) if ("*" in p or "?" in p) else p == aid for p in ids):
+                    return False
+            if c.get("trustTier") is not None:
+                tiers = c["trustTier"] if isinstance(c["trustTier"], list) else [c["trustTier"]]
+                if ((ctx.get("trust") or {}).get("agent") or {}).get("tier", "standard") not in tiers:
+                    return False
+            return True
+        if t == "any":
+            return any(self._cond(sub, ctx, hit) for sub in c.get("conditions", []))
+        if t == "not":
+            return not self._cond(c["condition"], ctx, hit)
+        return bool(self.other(c, ctx))
+
+
+class ResponseGate:
+    """response-gate.ts:23-176: requiredTools / mustMatch / mustNotMatch validators per agent; every mustMatch /
+    mustNotMatch pattern of the configuration is one rule of one device rule set, a batch of messages is scanned once.
+    An invalid pattern blocks (fail-closed, :113-118,134-139)."""
+
+    def __init__(self, config: dict, logger=None, scanner_cls=None):
+        self.config = config
+        self.rule_of: Dict[str, Optional[int]] = {}
+        rules = []
+        for rule in config.get("rules", []):
+            for v in rule.get("validators", []):
+                if v["type"] in ("mustMatch", "mustNotMatch") and v["pattern"] not in self.rule_of:
+                    if N.rule_check(v["pattern"], 0) == 0:
+                        self.rule_of[v["pattern"]] = len(rules); rules.append([v["pattern"]])
+                    else:
+                        self.rule_of[v["pattern"]] = None
+        self.scanner = (scanner_cls or RuleScanner)(rules, logger) if rules else None
+
+    def validate_batch(self, items: Sequence[Tuple[str, str, Sequence[dict]]]) -> List[dict]:
+        """items: (content, agentId, toolCallLog[{toolName, output}]) -> ResponseGateValidationResult per item"""
+        if not self.config.get("enabled"):
+            return [{"passed": True, "failedValidators": [], "reasons": []} for _ in items]
+        hits = self.scanner.scan([it[0] for it in items]) if self.scanner else [[] for _ in items]
+        out = []
+        for (content, agent, log), h in zip(items, hits):
+            hs = set(h); failed, reasons = [], []
+            for rule in self.config.get("rules", []):
+                ra = rule.get("agentId")
+                if ra and (agent not in ra if isinstance(ra, list) else ra != agent):
+                    continue
+                for v in rule.get("validators", []):
+                    if v["type"] == "requiredTools":
+                        called = {e["toolName"] for e in log}
+                        missing = [t for t in v["tools"] if t not in called]
+                        if missing:
+                            failed.append("requiredTools:" + ",".join(v["tools"]))
+                            reasons.append(v.get("message") or "Response Gate: required tool(s) not called: " + ", ".join(missing))
+                        continue
+                    ri = self.rule_of[v["pattern"]]
+                    if ri is None:
+                        failed.append("%s:%s" % (v["type"], v["pattern"]))
+                        reasons.append("Response Gate: invalid regex pattern /%s/ — blocked (fail-closed)" % v["pattern"])
+                    elif v["type"] == "mustMatch" and ri not in hs:
+                        failed.append("mustMatch:" + v["pattern"])
+                        reasons.append(v.get("message") or "Response Gate: content does not match required pattern /%s/" % v["pattern"])
+                    elif v["type"] == "mustNotMatch" and ri in hs:
+                        failed.append("mustNotMatch:" + v["pattern"])
+                        reasons.append(v.get("message") or "Response Gate: content matches forbidden pattern /%s/" % v["pattern"])
+            res = {"passed": not failed, "failedValidators": failed, "reasons": reasons}
+            if failed:
+                tpl = self.config.get("fallbackMessage") or self.config.get("fallbackTemplate")
+                if tpl:
+                    res["fallbackMessage"] = tpl.replace("{reasons}", "; ".join(reasons)).replace("{validators}", ", ".join(failed)).replace("{agent}", agent)
+            out.append(res)
+        return out
+
+    def validate(self, content: str, agent_id: str, tool_call_log: Sequence[dict]) -> dict:
+        return self.validate_batch([(content, agent_id, tool_call_log)])[0]
+
+
 # ------------------------------------------------------------------------------------- plugin entry
 
 DEFAULT_REDACTION_CONFIG = {
@@ -493,14 +759,22 @@ class GovernancePlugin:
         N.init(int(cfg.get("gpu", {}).get("device", -1)))            # optional new key; default: current device
         red = {**DEFAULT_REDACTION_CONFIG, **cfg.get("redaction", {})}
         red["allowlist"] = {**DEFAULT_REDACTION_CONFIG["allowlist"], **red.get("allowlist", {})}
-        self.policy = MessagePolicy(cfg.get("policies", []), logger)
+        self.policy = MessagePolicy([p for p in cfg.get("policies", []) if all("messageContains" in r for r in p.get("rules", []))], logger)
+        self.evaluator = PolicyEvaluator([p for p in cfg.get("policies", []) if any("conditions" in r for r in p.get("rules", []))], logger)
+        self.response_gate = ResponseGate(cfg["responseGate"], logger) if (cfg.get("responseGate") or {}).get("enabled") else None
+        self.tool_call_log: Dict[str, List[dict]] = {}
         api.on("message_sending", self._governance_message_sending(fail_mode, logger), {"priority": 1000})
+        api.on("before_tool_call", self._governance_before_tool_call(fail_mode, logger), {"priority": 1000})
+        api.on("before_message_write", self._governance_before_message_write(fail_mode, logger), {"priority": 1000})
+        api.on("after_tool_call", self._governance_after_tool_call(logger), {"priority": 900})
         if red["enabled"]:
             self.vault = RedactionVault(logger, red["vaultExpirySeconds"])
             self.registry = PatternRegistry(red["categories"], red["customPatterns"], logger)
             self.engine = RedactionEngine(self.registry, self.vault)
             self.credential_engine = RedactionEngine(PatternRegistry(["credential"], [], logger), self.vault)
             api.on("tool_result_persist", self._tool_result_persist(red, logger), {"priority": 800})
+            api.on("after_tool_call", self._redaction_after_tool_call(red, logger), {"priority": 800})
+            api.on("before_tool_call", self._redaction_before_tool_call(red, logger), {"priority": 950})
             api.on("message_sending", self._redaction_message_sending(red, logger), {"priority": 900})
             api.on("before_message_write", self._before_message_write(red, logger), {"priority": 900})
             logger.info("[redaction] Hooks registered (Layer 1 + Layer 2)")
@@ -512,6 +786,115 @@ class GovernancePlugin:
         return {"gpu": {"messagesScanned": int(s.messages_scanned), "bytesScanned": int(s.bytes_scanned), "hits": int(s.hits),
                         "kernelLaunches": int(s.kernel_launches), "lastScanMs": float(s.last_scan_ms)}}
 
+    @staticmethod
+    def _eval_ctx(ctx, **extra) -> dict:
+        ctx = ctx or {}
+        return {"agentId": _agent_id(ctx), "channel": ctx.get("channelId") or ctx.get("channel"), "sessionKey": ctx.get("sessionKey"),
+                "trust": ctx.get("trust") or {"session": {"tier": "standard"}, "agent": {"tier": "standard"}},
+                "conversationContext": ctx.get("conversationContext") or [], "metadata": ctx.get("metadata") or {}, **extra}
+
+    # gov/src/hooks.ts:173-243 (before_tool_call 1000): the tool / params conditions of the policy set; deny -> block, 2fa -> block
+    # with the approval reason (the approval flow itself -- approval-2fa.ts -- is the reference's control plane)
+    def _governance_before_tool_call(self, fail_mode, logger):
+        def handler(event, ctx):
+            try:
+                ev = event or {}
+                v = self.evaluator.evaluate(self._eval_ctx(ctx, toolName=ev.get("toolName"), toolParams=ev.get("params")))
+                if v["action"] in ("deny", "2fa"):
+                    return {"block": True, "blockReason": v["reason"]}
+                return None
+            except Exception as e:                      # noqa: BLE001
+                logger.error("[governance] before_tool_call error: %s" % e)
+                return {"block": True, "blockReason": "Governance engine error (fail-closed)"} if fail_mode == "closed" else None
+        return handler
+
+    # gov/src/hooks.ts:391-430 (after_tool_call 900): the per-session tool log the response gate reads
+    def _governance_after_tool_call(self, logger):
+        def handler(event, ctx):
+            ev, c = event or {}, ctx or {}
+            sid = c.get("sessionKey") or c.get("sessionId") or "agent:%s" % _agent_id(c)
+            out = ev.get("result")
+            self.tool_call_log.setdefault(sid, []).append({"toolName": ev.get("toolName"), "output": out if isinstance(out, str) else json.dumps(out, default=str)})
+        return handler
+
+    # gov/src/hooks.ts:297-389 (before_message_write 1000): response gate (mustMatch / mustNotMatch on the device, requiredTools from
+    # the tool log); fallback message keeps the content's shape (:339-351)
+    def _governance_before_message_write(self, fail_mode, logger):
+        def handler(event, ctx):
+            try:
+                msg = (event or {}).get("message") or {}
+                content = msg.get("content")
+                if isinstance(content, list):
+                    content = "\n".join(b.get("text", "") for b in content if isinstance(b, dict) and b.get("type") == "text")
+                if not content or not isinstance(content, str) or self.response_gate is None:
+                    return None
+                c = ctx or {}
+                agent = _agent_id(c)
+                sid = c.get("sessionKey") or c.get("sessionId") or "agent:%s" % agent
+                res = self.response_gate.validate(content, agent, self.tool_call_log.get(sid, []))
+                if res["passed"]:
+                    return None
+                reason = "Response Gate blocked: " + "; ".join(res["reasons"])
+                logger.warn("[governance] %s (agent=%s, failed=%s)" % (reason, agent, ",".join(res["failedValidators"])))
+                if res.get("fallbackMessage"):
+                    fb = [{"type": "text", "text": res["fallbackMessage"]}] if isinstance(msg.get("content"), list) else res["fallbackMessage"]
+                    return {"message": {**msg, "content": fb}}
+                return {"block": True, "blockReason": reason}
+            except Exception as e:                      # noqa: BLE001
+                logger.error("[governance] before_message_write error: %s" % e)
+                return {"block": True, "blockReason": "Governance engine error (fail-closed)"} if fail_mode == "closed" else None
+        return handler
+
+    # gov/src/redaction/hooks.ts:208-258 (after_tool_call 800: fire-and-forget, mutates the event for audit logging)
+    def _redaction_after_tool_call(self, red, logger):
+        def handler(event, ctx):
+            try:
+                ev = event or {}
+                if ev.get("result") is None:
+                    return
+                eng = self.credential_engine if ev.get("toolName") in red["allowlist"].get("exemptTools", []) else self.engine
+                res = eng.scan(ev["result"])
+                if res["redactionCount"] > 0:
+                    ev["result"] = res["output"]
+            except Exception as e:                      # noqa: BLE001
+                logger.error("[redaction] L1 error: %s" % e)
+                if red["failMode"] == "closed" and event is not None:
+                    event["result"] = "[REDACTION ERROR: Tool output suppressed (fail-closed)]"
+        return handler
+
+    # gov/src/redaction/hooks.ts:260-305, 474-520 (before_tool_call 950: placeholders in tool params back to their originals)
+    def _redaction_before_tool_call(self, red, logger):
+        def handler(event, ctx):
+            try:
+                state = {"count": 0, "has": False, "unresolved": []}
+
+                def res(v):
+                    if isinstance(v, str):
+                        if not RedactionVault.PLACEHOLDER_RE.search(v):
+                            return v
+                        state["has"] = True
+                        r = self.vault.resolve_all(v)
+                        state["count"] += r["resolved"] != v
+                        state["unresolved"] += r["unresolvedHashes"]
+                        return r["resolved"]
+                    if isinstance(v, list):
+                        return [res(x) for x in v]
+                    if isinstance(v, dict):
+                        return {k: res(x) for k, x in v.items()}
+                    return v
+                params = res((event or {}).get("params") or {})
+                if not state["has"]:
+                    return None
+                if state["unresolved"]:
+                    reason = "Unresolvable redacted value(s): %d placeholder(s) could not be resolved (expired or unknown)" % len(state["unresolved"])
+                    logger.warn("[redaction] Vault resolution blocked: %s" % reason)
+                    return {"block": True, "blockReason": reason}
+                return {"params": params}
+            except Exception as e:                      # noqa: BLE001
+                logger.error("[redaction] Vault resolution error: %s" % e)
+                return {"block": True, "blockReason": "Redaction vault error (fail-closed): %s" % e} if red["failMode"] == "closed" else None
+        return handler
+
     # gov/src/hooks.ts:245-290
     def _governance_message_sending(self, fail_mode, logger):
         def handler(event, ctx):
@@ -521,6 +904,8 @@ class GovernancePlugin:
                     return None
                 verdict = self.policy.evaluate(content)
                 if verdict["action"] == "deny":
+                    return {"cancel": True}
+                if self.evaluator.policies and self.evaluator.evaluate(self._eval_ctx(ctx, messageContent=content))["action"] in ("deny", "2fa"):
                     return {"cancel": True}
                 return None
             except Exception as e:                      # noqa: BLE001 -- mirrors the reference's catch-all
