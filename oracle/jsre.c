@@ -365,12 +365,6 @@ static Node *parse_disjunction(Parser *ps) {
     return alt;
 }
 
-static int has_nonascii_literal(const Node *nd) {
-    if (nd->type == N_CHAR && nd->ch >= 128) return 1;
-    if (nd->type == N_CLASS && nd->ch) return 1;   /* explicit non-ASCII endpoint seen by parse_class */
-    for (int i = 0; i < nd->nkids; i++) if (has_nonascii_literal(nd->kids[i])) return 1;
-    return 0;
-}
 
 void jsre_free(jsre *re) {
     if (!re) return;
@@ -389,7 +383,6 @@ jsre *jsre_compile(const uint16_t *pat, int n, int flags, char *err, int errlen)
     if (!ps.failed && ps.i < n) perr(&ps, ps.p[ps.i] == ')' ? "unmatched ')'" : "unexpected character");
     re->ncap = ps.ncap + 1;
     re->icase = flags & 1;
-    if (!ps.failed && re->icase && has_nonascii_literal(re->root)) perr(&ps, "oracle: flag i with non-ASCII literals unsupported");
     if (ps.failed) { jsre_free(re); return NULL; }
     return re;
 }
@@ -408,10 +401,19 @@ typedef struct M {
 typedef int (*ContFn)(M *, const Cont *, int);
 struct Cont { ContFn fn; const Cont *next; const Node *node; int a, b, x, dir; };
 
-static inline int canon(const M *m, int c) {
-    if (m->re->icase && c >= 'a' && c <= 'z') return c - 32;
+/* ECMA-262 22.2.2.7.3 Canonicalize without the unicode flag: toUppercase when that is ONE code unit and does not turn a
+ * non-ASCII unit into an ASCII one.  The non-identity part for units >= 0x80 is generated from the Unicode tables
+ * (vainplex_openclaw_b200/csrc/gen_case_table.py); pinned by the reference's language-pack tests
+ * (tests/golden/cortex_pack_vectors.json). */
+#include "../vainplex_openclaw_b200/csrc/case_canon.inc"
+static int canon_unit(int c) {
+    if (c >= 'a' && c <= 'z') return c - 32;
+    if (c < 0x80) return c;
+    int lo = 0, hi = kCaseCanonCount - 1;
+    while (lo <= hi) { int mid = (lo + hi) / 2; if (kCaseCanon[mid][0] == c) return kCaseCanon[mid][1]; if (kCaseCanon[mid][0] < c) lo = mid + 1; else hi = mid - 1; }
     return c;
 }
+static inline int canon(const M *m, int c) { return m->re->icase ? canon_unit(c) : c; }
 static inline int isword(int c) { return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || c == '_' || (c >= 'a' && c <= 'z'); }
 static inline int is_lineterm(int c) { return c == 0x0a || c == 0x0d || c == 0x2028 || c == 0x2029; }
 
@@ -419,10 +421,18 @@ static int class_has(const M *m, const Node *cls, int c) {
     int found = 0;
     for (int i = 0; i < cls->nranges && !found; i++) if (c >= cls->ranges[2 * i] && c <= cls->ranges[2 * i + 1]) found = 1;
     if (!found && m->re->icase) {
-        /* exists member a with Canonicalize(a) == Canonicalize(c); ASCII letters only */
+        /* exists member a with Canonicalize(a) == Canonicalize(c) (22.2.2.9 CharacterSetMatcher) */
         int alt = -1;
         if (c >= 'a' && c <= 'z') alt = c - 32; else if (c >= 'A' && c <= 'Z') alt = c + 32;
         if (alt >= 0) for (int i = 0; i < cls->nranges && !found; i++) if (alt >= cls->ranges[2 * i] && alt <= cls->ranges[2 * i + 1]) found = 1;
+        if (!found && c >= 0x80) {
+            const int cc = canon_unit(c);
+            for (int i = 0; i < cls->nranges && !found; i++) if (cc >= cls->ranges[2 * i] && cc <= cls->ranges[2 * i + 1]) found = 1;
+            for (int k = 0; k < kCaseCanonCount && !found; k++) if (kCaseCanon[k][1] == cc) {
+                const int u = kCaseCanon[k][0];
+                for (int i = 0; i < cls->nranges && !found; i++) if (u >= cls->ranges[2 * i] && u <= cls->ranges[2 * i + 1]) found = 1;
+            }
+        }
     }
     return cls->negate ? !found : found;
 }

@@ -132,7 +132,7 @@ def test_syntax_and_support_classification(oracle, harness_lib):
         assert N.rule_check(s) == 0, s
         oracle.Regex(s)
     assert N.rule_check("[a-z]{2000}") == N.CG_ERR_TOO_LARGE
-    assert N.rule_check("É", N.FLAG_ICASE) == N.CG_ERR_UNSUPPORTED
+    assert N.rule_check("É", N.FLAG_ICASE) == 0          # (round 1: unsupported; Canonicalize now covers the BMP, test_cortex_language_packs_*)
 
 
 def test_closure_stack_is_bounded_at_compile_time(oracle, harness_lib):
@@ -327,3 +327,32 @@ def test_bit_parallel_matcher_agrees_with_the_vm(harness_lib, oracle):
     decided, mismatch, fallback = (int(stats[i]) - int(base[i]) for i in range(3))
     assert mismatch == 0, (decided, mismatch, fallback)
     assert decided > 800 and decided > fallback
+
+
+def test_cortex_language_packs_compile_and_match(harness_lib, oracle):
+    """SURVEY 8 f4 with the real packs (tests/golden/cortex_pack_vectors.json): all 70 regex literals of the ten language
+    packs compile (flag i on Cyrillic / Latin-1 literals included), and the product's pipeline (gram filter -> factors ->
+    matchers, host harness) answers the reference's 100 anyMatch assertions."""
+    c = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cortex_pack_vectors.json"), encoding="utf-8"))
+    rules, where = [], {}
+    for lang, cats in c["packs"].items():
+        for cat, pats in cats.items():
+            for p in pats:
+                where.setdefault((lang, cat), []).append(len(rules))
+                rules.append((p["source"], 1 if "i" in p["flags"] else 0, 3))
+    h = Harness(harness_lib, rules)
+    assert [int(x) for x in h.status[:len(rules)]] == [0] * len(rules), [(rules[i][0], harness_lib.harness_rule_error(h.h, i)) for i in range(len(rules)) if h.status[i]]
+    for v in c["vectors"]:
+        m = v["text"].encode("utf-8")
+        hits = h.policy_hits(m)
+        assert any(r in hits for r in where[(v["lang"], v["category"])]) == v["expect"], (v["lang"], v["category"], v["text"])
+        assert all(h.test(r, m) == (r in hits) for r in where[(v["lang"], v["category"])])
+    # case folding beyond ASCII, both directions, classes and negated classes (ECMA-262 22.2.2.7.3 / 22.2.2.9)
+    extra = [("привет", 1, "ПРИВЕТ мир", True), ("ÄRGER", 1, "so ein ärger", True), ("straße", 1, "STRASSE", False), ("[а-я]+ть", 1, "ДЕЛАТЬ", True),
+             ("[^а-я]", 1, "Я", False), ("ς", 1, "Σ", True), ("ǆ", 1, "ǅ", True), ("\\u212a", 1, "k", False), ("ſ", 1, "s", False), ("é", 0, "É", False)]
+    for src, fl, text, want in extra:
+        hh = Harness(harness_lib, [(src, fl, 3)])
+        assert int(hh.status[0]) == 0, src
+        assert hh.test(0, text.encode("utf-8")) == want == bool(oracle_spans(oracle, oracle.Regex(src, "i" if fl else ""), [text.encode("utf-8")])), (src, text)
+        hh.close()
+    h.close()

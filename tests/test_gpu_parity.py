@@ -581,6 +581,31 @@ def test_programs_longer_than_the_small_vm(N, oracle):
     rs.close()
 
 
+def test_cortex_language_packs_on_the_kernels(N, oracle):
+    """The ten real language packs of openclaw-cortex as ONE rule set (70 rules, flag i on Cyrillic / Latin-1 literals, CJK,
+    Hangul): the reference's own 100 anyMatch assertions through the kernels, and the policy words of the whole batch
+    against the oracle."""
+    c = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cortex_pack_vectors.json"), encoding="utf-8"))
+    rules, where = [], {}
+    for lang, cats in c["packs"].items():
+        for cat, pats in cats.items():
+            for p in pats:
+                where.setdefault((lang, cat), []).append(len(rules))
+                rules.append((p["source"], 1 if "i" in p["flags"] else 0, 3))
+    rs = N.Ruleset(rules, strict=True)
+    msgs = [v["text"].encode("utf-8") for v in c["vectors"]] * 20
+    data, off = N.pack(msgs)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert np.array_equal(words, ewords) and [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits
+    by_msg = {}
+    for h in hits:
+        by_msg.setdefault(int(h["msg"]), set()).add(int(h["rule"]))
+    for i, v in enumerate(c["vectors"]):
+        assert any(r in by_msg.get(i, set()) for r in where[(v["lang"], v["category"])]) == v["expect"], (v["lang"], v["category"], v["text"])
+    rs.close()
+
+
 def test_non_ascii_rule_packs_on_the_kernels(N, oracle):
     """CJK / Cyrillic / Hangul literal alternations, classes with CJK ranges, `.*` between literals and the
     lazy PEM block: policy words, hits and resolved spans equal the oracle's."""

@@ -269,3 +269,37 @@ def test_merkle_consistency_every_pair_small(oracle):
                 assert not oracle.merkle_verify_consistency(m, n, roots[m][::-1], roots[n], p)
                 assert not oracle.merkle_verify_consistency(m, n, roots[m], roots[n], p[:-1])
                 assert not oracle.merkle_verify_consistency(m, n, roots[m], roots[n], p + [p[-1]])
+
+
+# ------------------------------------------------------- language packs (flag i on non-ASCII literals; CJK; Hangul)
+
+def _cortex():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cortex_pack_vectors.json"), encoding="utf-8"))
+
+
+def test_cortex_language_pack_vectors(oracle):
+    """Every anyMatch assertion of openclaw-cortex test/patterns-lang-*.test.ts (100 of them, 8 languages) on the packs'
+    own regex literals (src/patterns/lang-*.ts): pins Canonicalize for non-ASCII units (Cyrillic, Latin-1) in the oracle."""
+    c = _cortex()
+    assert len(c["vectors"]) >= 100 and sum(len(p) for cats in c["packs"].values() for p in cats.values()) >= 70
+    cache = {}
+    for v in c["vectors"]:
+        pats = c["packs"][v["lang"]][v["category"]]
+        got = False
+        for p in pats:
+            key = (p["source"], "i" in p["flags"])
+            rx = cache.get(key) or cache.setdefault(key, oracle.Regex(p["source"], "i" if "i" in p["flags"] else ""))
+            data, off = oracle.pack([oracle.js_to_utf8(v["text"])])
+            _, words = oracle.scan_policy([rx], data, off, threads=1, want_bits=False)
+            got = got or bool(words[0])
+        assert got == v["expect"], (v["lang"], v["category"], v["text"], v["line"])
+    # a second opinion on case folding: Python's re with IGNORECASE on the same vectors
+    import re
+    for v in c["vectors"]:
+        pats = c["packs"][v["lang"]][v["category"]]
+        try:
+            got = any(re.search(p["source"], v["text"], re.I if "i" in p["flags"] else 0) for p in pats)
+        except re.error:
+            continue
+        assert got == v["expect"], ("python re", v["lang"], v["text"])

@@ -46,13 +46,32 @@ static Ranges negate(const Ranges& r) {
   if (lo <= 0xffff) o.push_back({lo, 0xffff});
   return o;
 }
-static void add_case_closure(Ranges& r) {   // ASCII letters only (flag i)
+#include "case_canon.inc"      // kCaseCanon: ECMA-262 Canonicalize for the BMP units >= 0x80 that change (gen_case_table.py)
+// units grouped by their canonical form (the form itself included): a class under flag i matches ch iff it holds a member
+// with the same canonical form (ECMA-262 22.2.2.9 CharacterSetMatcher)
+static const std::vector<std::vector<int>>& canon_groups() {
+  static const std::vector<std::vector<int>> groups = [] {
+    std::map<int, std::vector<int>> g;
+    for (int i = 0; i < kCaseCanonCount; i++) { auto& v = g[kCaseCanon[i][1]]; if (v.empty()) v.push_back(kCaseCanon[i][1]); v.push_back(kCaseCanon[i][0]); }
+    std::vector<std::vector<int>> out;
+    for (auto& kv : g) out.push_back(kv.second);
+    return out;
+  }();
+  return groups;
+}
+static bool in_ranges(const Ranges& r, int c) { for (auto& p : r) if (c >= p.first && c <= p.second) return true; return false; }
+static void add_case_closure(Ranges& r) {
   Ranges extra;
-  for (auto& p : r) {
+  for (auto& p : r) {                                    // ASCII letters
     int lo = std::max(p.first, (int)'a'), hi = std::min(p.second, (int)'z');
     if (lo <= hi) extra.push_back({lo - 32, hi - 32});
     lo = std::max(p.first, (int)'A'); hi = std::min(p.second, (int)'Z');
     if (lo <= hi) extra.push_back({lo + 32, hi + 32});
+  }
+  bool nonascii = false; for (auto& p : r) nonascii |= p.second >= 0x80;
+  if (nonascii) for (auto& grp : canon_groups()) {      // everything else: whole groups
+    bool any = false; for (int u : grp) if (in_ranges(r, u)) { any = true; break; }
+    if (any) for (int u : grp) extra.push_back({u, u});
   }
   r.insert(r.end(), extra.begin(), extra.end());
   normalise(r);
@@ -200,7 +219,7 @@ struct Parser {
 
   int mkchar(int c) {
     if (c >= 128) explicit_nonascii = true;
-    if (icase && ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))) return finish_set({{c, c}}, false);
+    if (icase && ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80)) return finish_set({{c, c}}, false);
     int n = mk(T_CHAR); nodes[n].ch = c; return n;
   }
 
@@ -723,7 +742,6 @@ CompiledRule compile_rule(const char* src, size_t len, uint32_t flags) {
     ps.prescan();
     int root = ps.parse_disjunction();
     if (ps.i < ps.p.size()) throw Fail{RULE_ERR_SYNTAX, ps.p[ps.i] == ')' ? "unmatched ')'" : "unexpected character"};
-    if (ps.icase && ps.explicit_nonascii) throw Fail{RULE_ERR_UNSUPPORTED, "flag i with non-ASCII literals"};
     Compiler c(ps, out);
     c.check_supported(root);
     c.gen(root);
