@@ -303,3 +303,19 @@ def test_cortex_language_pack_vectors(oracle):
         except re.error:
             continue
         assert got == v["expect"], ("python re", v["lang"], v["text"])
+
+
+def test_napi_shim_compiles_against_declarations():
+    """napi/openclaw_gov_napi.c (the reference-side binding; Node.js is absent here) type-checks against N-API declarations
+    (napi/stub/node_api.h) and the C ABI header, without warnings -- and binds every entry point a JS caller needs."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + os.path.join(root, "napi", "stub"), "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "napi", "openclaw_gov_napi.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(root, "napi", "openclaw_gov_napi.c")).read()
+    for fn in ("cg_init", "cg_shutdown", "cg_get_stats", "cg_rule_check", "cg_ruleset_create", "cg_scan_batch", "cg_scan_one", "cg_find_matches_batch",
+               "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch", "cg_sha256_batch", "cg_merkle_root", "cg_merkle_log_create",
+               "cg_merkle_log_restore", "cg_merkle_log_append", "cg_merkle_log_append_jsonl", "cg_merkle_log_reserve", "cg_merkle_log_size", "cg_merkle_log_root",
+               "cg_merkle_log_frontier", "cg_merkle_log_proof", "cg_merkle_log_consistency", "cg_merkle_verify_proof", "cg_merkle_verify_consistency"):
+        assert fn + "(" in src, fn
