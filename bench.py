@@ -592,7 +592,7 @@ def main():
     # ---- CPU baseline (oracle port) on a strided sample of the SAME batch, rank 0, N=1 only: every 16th message, so that the
     # comparison of result words covers the whole timed batch, not its first corner
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and rank == 0 and (world == 1 or os.environ.get("CG_ORACLE_CHECK")):      # (N > 1: only on request, reported as extra.oracle_check)
         from oracle import oracle as O
         regs = [O.Regex(r["source"], "i" if r["flags"] else "") for r in rl]
         threads = host_threads()
@@ -602,7 +602,8 @@ def main():
         hb_all = h_data.numpy()[: n * L].reshape(n, L)
         hb = np.concatenate([hb_all[pick].reshape(-1), np.zeros(64, dtype=np.uint8)])
         ho = np.arange(sample + 1, dtype=np.uint64) * L
-        O.scan_policy(regs, hb[: 2048 * L + 64], ho[:2049], threads=threads, want_bits=False)
+        warm = min(sample, 2048)
+        O.scan_policy(regs, hb[: warm * L + 64], ho[:warm + 1], threads=threads, want_bits=False)
         t0 = time.perf_counter()
         _, cw = O.scan_policy(regs, hb, ho, threads=threads, want_bits=False)
         dt = time.perf_counter() - t0
@@ -642,12 +643,12 @@ def main():
         "candidates": {"flag_words": counters[8], "flagged_grams": counters[6], "grams_past_recheck_map": counters[7], "gram_entry_pairs": counters[9], "confirmed_factor_occurrences": counters[4], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
                        **({"vm_cycle_hist_2^11..": list(counters[8:16]), "vm_cycle_max": counters[7]} if os.environ.get("CG_SCAN_DEBUG") == "2" else {}),
                        "hit_messages": int((words != 0).sum().item()), "injected": len(inj)},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu if world == 1 else None,
         "e2e": {"value": e2e_value, "unit": "msgs/s", "h2d_bytes_per_step": int(n * L + 4 * (n + 1)), "d2h_bytes_per_step": int(8 * n + 64),
                 "steps": e2e_steps, "words_equal_device_path": same},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "extra": {"variants": variants, "merkle": merkle, "c4": c4, "redact": redact, "scan_one": one, "per_rank_ms_per_step": per_rank_ms},
+        "extra": {"oracle_check": cpu if world > 1 else None, "variants": variants, "merkle": merkle, "c4": c4, "redact": redact, "scan_one": one, "per_rank_ms_per_step": per_rank_ms},
     }
     emit(line)
     if world > 1:
