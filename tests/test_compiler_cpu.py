@@ -285,16 +285,6 @@ def test_no_device_fails_loudly():
         N.Ruleset([("abc", 0, 3)])
 
 
-def test_napi_shim_source_compiles_against_a_stub_header():
-    """Node.js is absent, so the N-API addon cannot be built here; at least its C source must parse and type-check
-    against the C ABI header (a stand-in node_api.h declares the handful of N-API calls it uses)."""
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "tests", "native"),
-                        os.path.join(root, "napi", "openclaw_gov_napi.c")], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-
-
 def test_bit_parallel_matcher_agrees_with_the_vm(harness_lib, oracle):
     """bitprog.h: for every confirmed factor occurrence of the tests above's kind of traffic AND of random regexes, the
     bit-parallel matcher (resolve_kernel's fast path) either declines (non-ASCII island) or answers what the Pike VM

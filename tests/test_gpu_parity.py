@@ -554,7 +554,7 @@ def test_sha256_ragged_alignment(N, oracle):
 def test_programs_longer_than_the_small_vm(N, oracle):
     """verify_large_kernel: rules whose Pike program exceeds the shared-memory VM's 192 instructions (and the bit-parallel
     matcher's 63) -- policy words and spans equal the oracle's."""
-    rules = [(r"tok_[a-f0-9]{200}z", 0, 0), (r"(?:ab|cd|ef){70}!", 0, 1), (r"sk-[a-zA-Z0-9]{20,}", 0, 2), (r"key=[A-Z]{100}[0-9]{100}\\b", 1, 3)]
+    rules = [(r"tok_[a-f0-9]{200}z", 0, 0), (r"(?:ab|cd|ef){70}!", 0, 1), (r"sk-[a-zA-Z0-9]{20,}", 0, 2), (r"key=[A-Z]{100}[0-9]{100}\b", 1, 3)]
     rng = np.random.default_rng(192)
     hexd = b"0123456789abcdef"
     msgs = []
@@ -565,7 +565,7 @@ def test_programs_longer_than_the_small_vm(N, oracle):
         elif k == 2: body = b"".join([b"ab", b"cd", b"ef"][int(x)] for x in rng.integers(0, 3, 70)) + b"!"
         elif k == 3: body = b"".join([b"ab", b"cd", b"ef"][int(x)] for x in rng.integers(0, 3, 69)) + b"x!"
         elif k == 4: body = b"KEY=" + b"Q" * 100 + b"7" * 100
-        elif k == 5: body = b"key=" + b"q" * 100 + b"7" * 100 + b"a"                                             # \\b fails
+        elif k == 5: body = b"key=" + b"q" * 100 + b"7" * 100 + b"a"                                             # \b fails
         elif k == 6: body = b"sk-" + b"a1B2" * 6
         else: body = b"nothing to see"
         msgs.append(b"pad " * int(rng.integers(0, 5)) + body + b" tail" * int(rng.integers(0, 3)))

@@ -19,7 +19,11 @@
 
 namespace cg {
 
-constexpr uint32_t kBitProgWords = 128 + 8 * 64 + 8;     // accept[128], follow[8][64], start[8] (uint64 each)
+// table of one rule (uint64 words): accept[128] | start[8] | header | follow rows [n_rows][64]
+//   header = row of context c in bits 4c..4c+3, n_rows in bits 32..35 (contexts with identical follow rows share one: a rule
+//   without assertions has a single row)
+constexpr uint32_t kBitAccept = 0, kBitStart = 128, kBitHeader = 136, kBitRows = 137;
+constexpr uint32_t kBitProgWords = kBitRows + 8 * 64;
 constexpr uint32_t kBitProgNone = 0xffffffffu;
 constexpr uint64_t kBitMatch = 1ull << 63;
 
@@ -31,7 +35,7 @@ CG_HD uint32_t bitprog_ctx(int prev, int next, bool at_start) {
 // -> 1 a match that starts in [s, t0] exists, 0 none, -1 cannot tell (non-ASCII byte in the island, or more than max_steps
 // bytes to walk: ask the VM, whose warp-wide runs suit long islands better than one thread's chain of table loads)
 CG_HD int bitprog_test(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps = 0xffffffffu) {
-  const uint64_t* accept = bp; const uint64_t* follow = bp + 128; const uint64_t* start = bp + 128 + 8 * 64;
+  const uint64_t* accept = bp + kBitAccept; const uint64_t* start = bp + kBitStart; const uint64_t* rows = bp + kBitRows; const uint64_t header = bp[kBitHeader];
   int prev = s > 0 ? (m[s - 1] < 0x80 ? (int)m[s - 1] : 0x80) : -1;          // (a unit >= 0x80 is not a word character, whatever it is)
   int cur = s < len ? (int)m[s] : -1;
   uint32_t ctx = bitprog_ctx(prev, cur, s == 0);
@@ -45,7 +49,7 @@ CG_HD int bitprog_test(const uint64_t* __restrict__ bp, const uint8_t* __restric
     const int nxt = pos + 1 < len ? (int)m[pos + 1] : -1;
     acc_cur = nxt >= 0 && nxt < 0x80 ? accept[nxt] : 0;
     ctx = bitprog_ctx(cur, nxt < 0x80 ? nxt : 0x80, false);
-    const uint64_t* fw = follow + ctx * 64;
+    const uint64_t* fw = rows + ((header >> (4 * ctx)) & 15u) * 64;
     live = 0;
     while (hit) {
 #if defined(__CUDA_ARCH__)

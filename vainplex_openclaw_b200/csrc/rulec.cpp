@@ -915,7 +915,7 @@ bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOpti
 
 // ---------------------------------------------------------------------------------------------------------------
 // bit-parallel form of a Pike program (bitprog.h)
-bool build_bitprog(const CompiledRule& r, uint64_t* out) {
+bool build_bitprog(const CompiledRule& r, uint64_t* out) {      // out: kBitProgWords = 649 words
   const std::vector<uint32_t>& prog = r.prog;
   if (r.status != RULE_OK || prog.empty()) return false;
   std::vector<int> bit_of(prog.size(), -1); int nc = 0;
@@ -924,7 +924,7 @@ bool build_bitprog(const CompiledRule& r, uint64_t* out) {
     if (op == OP_CHAR || op == OP_SET || op == OP_ANY) { if (nc >= 63) return false; bit_of[pc] = nc++; }
     else if (op == OP_LOOKAHEAD || op == OP_NLOOKAHEAD || op == OP_LOOKBEHIND || op == OP_NLOOKBEHIND) return false;
   }
-  for (uint32_t i = 0; i < 128 + 8 * 64 + 8; i++) out[i] = 0;
+  for (uint32_t i = 0; i < 137 + 8 * 64; i++) out[i] = 0;
   // accept[b]: the consuming instructions an ASCII byte satisfies
   for (size_t pc = 0; pc < prog.size(); pc++) {
     if (bit_of[pc] < 0) continue;
@@ -956,10 +956,20 @@ bool build_bitprog(const CompiledRule& r, uint64_t* out) {
     }
     return m;
   };
+  // layout (bitprog.h): accept[128] | start[8] | header | rows[n][64]; contexts with identical follow rows share one
+  uint64_t rows[8][64]; uint32_t n_rows = 0; uint64_t header = 0;
   for (uint32_t ctx = 0; ctx < 8; ctx++) {
-    for (size_t pc = 0; pc < prog.size(); pc++) if (bit_of[pc] >= 0) out[128 + ctx * 64 + bit_of[pc]] = closure((uint32_t)pc + 1, ctx);
-    out[128 + 8 * 64 + ctx] = closure(0, ctx);
+    uint64_t row[64] = {0};
+    for (size_t pc = 0; pc < prog.size(); pc++) if (bit_of[pc] >= 0) row[bit_of[pc]] = closure((uint32_t)pc + 1, ctx);
+    out[128 + ctx] = closure(0, ctx);
+    uint32_t r = 0;
+    while (r < n_rows && memcmp(rows[r], row, sizeof row) != 0) r++;
+    if (r == n_rows) { memcpy(rows[n_rows], row, sizeof row); n_rows++; }
+    header |= (uint64_t)r << (4 * ctx);
   }
+  header |= (uint64_t)n_rows << 32;
+  out[136] = header;
+  for (uint32_t r = 0; r < n_rows; r++) memcpy(out + 137 + r * 64, rows[r], sizeof rows[r]);
   return true;
 }
 
