@@ -443,10 +443,33 @@ def main():
         root_ok = oracle_block_roots_equal(h_leaves, MERKLE_LEAF, nl, my_roots, all_roots, root)
         check_s = time.perf_counter() - t0
         nblk = my_roots.shape[0]
+        # the same tree with the exchange INSIDE the library (cg_comm_init + cg_merkle_root_sharded_device: NCCL all-gather issued
+        # by the C ABI, bound with dlopen); the id travels over the launcher's process group
+        lib_coll = None
+        try:
+            if world > 1:
+                ids = [N.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                N.comm_init(rank, world, ids[0])
+            lroot = N.merkle_root_sharded_device(leaves.data_ptr(), MERKLE_LEAF, nl, world * nl, MERKLE_BLOCK_LOG2, stream.cuda_stream)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            tl = time.perf_counter()
+            for _ in range(3):
+                lroot = N.merkle_root_sharded_device(leaves.data_ptr(), MERKLE_LEAF, nl, world * nl, MERKLE_BLOCK_LOG2, stream.cuda_stream)
+            lms = (time.perf_counter() - tl) / 3 * 1e3
+            if world > 1:
+                t = torch.tensor([lms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); lms = float(t.item())
+            lib_coll = {"ms_per_tree_host_clock": lms, "leaves_per_s": world * nl / (lms * 1e-3), "root_equals_the_other_path": lroot == root,
+                        "collective": "ncclAllGather issued by libopenclaw_gov.so (cg_merkle_root_sharded_device)" if world > 1 else "none (1 rank)"}
+        except Exception as e:       # noqa: BLE001 -- reported, the torch.distributed path above stays the headline
+            lib_coll = {"error": str(e)[:200]}
         merkle = {"leaves_per_s": world * nl / (mms * 1e-3), "ms_per_tree": mms, "leaves_per_rank": nl, "leaf_bytes": MERKLE_LEAF,
                   "root_hex": root.hex(), "root_equals_oracle": root_ok,
                   "root_check": "every rank: its %d block roots == oracle over its own %d leaves; fold of all %d gathered roots == oracle fold (%.1f s on the host)" % (nblk, nl, world * nblk, check_s),
                   "collective": "all_gather of %d block roots/rank (NCCL)" % nblk if world > 1 else "none (1 rank)",
+                  "library_collective": lib_coll,
                   "hbm_frac_of_measured": (nl * MERKLE_LEAF / (mms * 1e-3)) / (peak * 1e9),
                   "sha256_compressions_per_s": world * (nl * ((MERKLE_LEAF + 1 + 9 + 63) // 64) + 2 * (nl - 1)) / (mms * 1e-3)}
         # (f2) the append-only log fed from PINNED host memory (H2D inside the timed region), rank 0, N = 1 only:

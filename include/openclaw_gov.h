@@ -185,6 +185,20 @@ CG_API int cg_merkle_block_roots_device(const void *d_bytes, uint64_t leaf_len, 
                                         void *d_out_roots, void *stream);
 /* fold m 32-byte subtree roots (host memory) into one root with the same level-wise rule */
 CG_API int cg_merkle_fold(const uint8_t *nodes32, uint64_t m, uint8_t out_root[32]);
+
+/* ---- multi-GPU, one process per GPU (SURVEY.md section 8 e).  The scan shards by message and exchanges nothing:
+ * cg_shard_range is the split rule (contiguous [lo, hi) per rank, every boundary except n a multiple of `align`).  The
+ * Merkle tree exchanges once: cg_merkle_root_sharded_device reduces this rank's leaves to roots of aligned 2^block_log2-leaf
+ * blocks, all-gathers them (NCCL, bound at run time with dlopen: a single-GPU process needs no NCCL) and folds the same list
+ * on every rank -- the root of the single tree over all ranks' leaves.  Bootstrap: rank 0 calls cg_comm_unique_id and hands
+ * the 128 bytes to the other ranks by whatever channel launched them; every rank calls cg_comm_init(rank, world, id). */
+typedef struct { char internal[128]; } cg_nccl_id;
+CG_API void cg_shard_range(uint64_t n, int rank, int world, uint64_t align, uint64_t *lo, uint64_t *hi);
+CG_API int cg_comm_unique_id(cg_nccl_id *out);
+CG_API int cg_comm_init(int rank, int world, const cg_nccl_id *id);
+CG_API void cg_comm_destroy(void);
+CG_API int cg_merkle_root_sharded_device(const void *d_bytes, uint64_t leaf_len, uint64_t n_local, uint64_t n_total, uint32_t block_log2,
+                                         uint8_t out_root[32], void *stream);
 CG_API int cg_merkle_fold_device(const void *d_nodes32, uint64_t m, void *d_out_root32, void *stream);
 
 /* ---- append-only Merkle log over the event log (audit JSONL lines of src/audit-trail.ts:151-179

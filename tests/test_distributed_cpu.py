@@ -90,3 +90,20 @@ def test_shard_range_properties():
                     prev = hi
                 assert prev == n
     assert blocks_of(0, 100, 4) == 7 and blocks_of(16, 16, 4) == 0
+
+
+def test_library_split_rule_equals_the_host_one():
+    """cg_shard_range (the split rule the C ABI exports for one-process-per-GPU callers) == sharding.shard_range for every
+    rank: contiguous, disjoint, covering, every inner boundary a multiple of `align` (needs no device)."""
+    from vainplex_openclaw_b200 import _native as N, sharding as S
+    import random
+    rnd = random.Random(5)
+    for _ in range(300):
+        n = rnd.choice([0, 1, 7, 1000, 65536, 10_000_000, (1 << 40) + 12345])
+        world = rnd.choice([1, 2, 3, 4, 8, 16]); align = rnd.choice([1, 32, 1 << 16])
+        prev = 0
+        for r in range(world):
+            lo, hi = N.shard_range(n, r, world, align)
+            assert (lo, hi) == S.shard_range(n, r, world, align) and lo == prev and (hi == n or hi % align == 0)
+            prev = hi
+        assert prev == n

@@ -52,6 +52,7 @@ EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_c
            "cg_merkle_log_create", "cg_merkle_log_destroy", "cg_merkle_log_append", "cg_merkle_log_size", "cg_merkle_log_root",
            "cg_merkle_log_frontier", "cg_merkle_log_restore", "cg_merkle_log_proof", "cg_merkle_verify_proof",
            "cg_merkle_log_append_jsonl", "cg_merkle_log_consistency", "cg_merkle_verify_consistency", "cg_merkle_log_reserve",
+           "cg_shard_range", "cg_comm_unique_id", "cg_comm_init", "cg_comm_destroy", "cg_merkle_root_sharded_device",
            "cg_ruleset_create", "cg_ruleset_destroy", "cg_ruleset_get_info", "cg_rule_check", "cg_scan_batch",
            "cg_scan_one", "cg_find_matches_batch", "cg_scan_batch_device", "cg_sha256_batch", "cg_merkle_root",
            "cg_merkle_root_fixed", "cg_merkle_block_roots_device", "cg_merkle_fold", "cg_merkle_fold_device"]
@@ -100,6 +101,11 @@ def load():
     L.cg_merkle_verify_proof.argtypes = [vp, u64, u64, u64, vp, u32, vp, vp]; L.cg_merkle_verify_proof.restype = i32
     L.cg_merkle_log_append_jsonl.argtypes = [vp, vp, u64, vp]; L.cg_merkle_log_append_jsonl.restype = i32
     L.cg_merkle_log_reserve.argtypes = [vp, u64, u64]; L.cg_merkle_log_reserve.restype = i32
+    L.cg_shard_range.argtypes = [u64, i32, i32, u64, vp, vp]; L.cg_shard_range.restype = None
+    L.cg_comm_unique_id.argtypes = [vp]; L.cg_comm_unique_id.restype = i32
+    L.cg_comm_init.argtypes = [i32, i32, vp]; L.cg_comm_init.restype = i32
+    L.cg_comm_destroy.argtypes = []; L.cg_comm_destroy.restype = None
+    L.cg_merkle_root_sharded_device.argtypes = [vp, u64, u64, u64, u32, vp, vp]; L.cg_merkle_root_sharded_device.restype = i32
     L.cg_merkle_log_consistency.argtypes = [vp, u64, vp, u32, vp]; L.cg_merkle_log_consistency.restype = i32
     L.cg_merkle_verify_consistency.argtypes = [u64, u64, vp, vp, vp, u32, vp]; L.cg_merkle_verify_consistency.restype = i32
     L.cg_ruleset_create.argtypes = [C.POINTER(cg_rule), u32, u32, C.POINTER(vp), vp]; L.cg_ruleset_create.restype = i32
@@ -407,6 +413,34 @@ class MerkleLog:
         if self.handle:
             load().cg_merkle_log_destroy(self.handle)
             self.handle = None
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 1):
+    """cg_shard_range: this rank's contiguous [lo, hi); needs no device."""
+    lo, hi = C.c_uint64(0), C.c_uint64(0)
+    load().cg_shard_range(n, rank, world, align, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(load().cg_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(rank: int, world: int, uid: bytes):
+    buf = C.create_string_buffer(uid, 128)
+    check(load().cg_comm_init(rank, world, buf))
+
+
+def comm_destroy():
+    load().cg_comm_destroy()
+
+
+def merkle_root_sharded_device(d_ptr: int, leaf_len: int, n_local: int, n_total: int, block_log2: int, stream: int = 0) -> bytes:
+    out = np.zeros(32, dtype=np.uint8)
+    check(load().cg_merkle_root_sharded_device(d_ptr, leaf_len, n_local, n_total, block_log2, out.ctypes.data, stream))
+    return out.tobytes()
 
 
 def merkle_verify_consistency(first_size: int, second_size: int, root_first: bytes, root_second: bytes, path) -> bool:

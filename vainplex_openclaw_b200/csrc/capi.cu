@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <dlfcn.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1192,6 +1193,102 @@ int cg_merkle_fold_device(const void* d_nodes32, uint64_t m, void* d_out_root32,
   CU(cudaMemcpyAsync(d_out_root32, G.d_dig[cur], 32, cudaMemcpyDeviceToDevice, st));
   CU(cudaGetLastError());
   return CG_OK;
+}
+
+// ---------------------------------------------------------------------------------- multi-GPU: one process per GPU
+// The scan shards by message with no exchange at all (cg_shard_range is the split rule).  The Merkle tree has ONE exchange:
+// every rank's roots of aligned 2^k-leaf blocks are all-gathered and every rank folds the same list.  NCCL is bound at run
+// time (dlopen of the process's libnccl.so.2 -- the one the host framework has loaded, if any) so that a single-GPU
+// deployment has no such dependency.
+void cg_shard_range(uint64_t n, int rank, int world, uint64_t align, uint64_t* lo, uint64_t* hi) {
+  if (align == 0) align = 1;
+  if (world < 1) world = 1;
+  const uint64_t blocks = (n + align - 1) / align;
+  const uint64_t lo_b = (uint64_t)((unsigned __int128)blocks * (unsigned)rank / (unsigned)world), hi_b = (uint64_t)((unsigned __int128)blocks * (unsigned)(rank + 1) / (unsigned)world);
+  if (lo) *lo = std::min(lo_b * align, n);
+  if (hi) *hi = std::min(hi_b * align, n);
+}
+
+namespace {
+struct NcclApi {
+  void* h = nullptr; void* comm = nullptr; int rank = 0, world = 1;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, cg_nccl_id, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+} g_nccl;
+int nccl_load() {
+  if (g_nccl.h) return CG_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(CG_ERR_UNSUPPORTED, std::string("NCCL not found: ") + dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, cg_nccl_id, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) { dlclose(h); return fail(CG_ERR_UNSUPPORTED, "NCCL symbols missing"); }
+  g_nccl.h = h;
+  return CG_OK;
+}
+int nccl_fail(int rc, const char* what) { return fail(CG_ERR_CUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error")); }
+}  // namespace
+
+int cg_comm_unique_id(cg_nccl_id* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out) return fail(CG_ERR_INVALID_ARG, "null argument");
+  int rc = nccl_load(); if (rc) return rc;
+  int r = g_nccl.GetUniqueId(out); if (r) return nccl_fail(r, "ncclGetUniqueId");
+  return CG_OK;
+}
+int cg_comm_init(int rank, int world, const cg_nccl_id* id) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!G.ready) return fail(CG_ERR_NOT_INITIALIZED, "cg_init has not been called (or no CUDA device)");
+  if (!id || world < 1 || rank < 0 || rank >= world) return fail(CG_ERR_INVALID_ARG, "bad rank / world / id");
+  int rc = nccl_load(); if (rc) return rc;
+  if (g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
+  int r = g_nccl.CommInitRank(&g_nccl.comm, world, *id, rank); if (r) return nccl_fail(r, "ncclCommInitRank");
+  g_nccl.rank = rank; g_nccl.world = world;
+  return CG_OK;
+}
+void cg_comm_destroy(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_nccl.comm && g_nccl.CommDestroy) { if (G.ready) cudaStreamSynchronize(G.stream); g_nccl.CommDestroy(g_nccl.comm); }
+  g_nccl.comm = nullptr; g_nccl.world = 1; g_nccl.rank = 0;
+}
+
+/* Root of the tree over the leaves of ALL ranks (rank r holds leaves [lo_r, hi_r) of cg_shard_range(n_total, r, world, 2^block_log2),
+ * device-resident): block roots here, one all-gather of (count, roots) per rank, the same fold on every rank. */
+int cg_merkle_root_sharded_device(const void* d_bytes, uint64_t leaf_len, uint64_t n_local, uint64_t n_total, uint32_t block_log2, uint8_t out_root[32], void* stream) {
+  if (!out_root || block_log2 > 40) return fail(CG_ERR_INVALID_ARG, "bad argument");
+  int rank, world; void* comm;
+  { std::lock_guard<std::mutex> lk(g_mu); rank = g_nccl.rank; world = g_nccl.world; comm = g_nccl.comm; }
+  if (world > 1 && !comm) return fail(CG_ERR_NOT_INITIALIZED, "cg_comm_init has not been called");
+  uint64_t lo, hi; cg_shard_range(n_total, rank, world, 1ull << block_log2, &lo, &hi);
+  if (hi - lo != n_local) return fail(CG_ERR_INVALID_ARG, "n_local is not this rank's share of n_total (cg_shard_range with align = 2^block_log2)");
+  cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+  // every rank contributes max_blocks slots (its own roots first); the counts follow from the split rule, no second exchange
+  uint64_t max_blocks = 0; std::vector<uint64_t> nblk((size_t)world);
+  for (int r = 0; r < world; r++) { uint64_t a, b; cg_shard_range(n_total, r, world, 1ull << block_log2, &a, &b); nblk[(size_t)r] = (b - a + (1ull << block_log2) - 1) >> block_log2; max_blocks = std::max(max_blocks, nblk[(size_t)r]); }
+  if (max_blocks == 0) return cg_merkle_fold(nullptr, 0, out_root);
+  uint8_t *d_mine = nullptr, *d_all = nullptr, *d_real = nullptr, *d_root = nullptr;
+  CU(cudaMalloc((void**)&d_mine, max_blocks * 32)); CU(cudaMalloc((void**)&d_all, (size_t)world * max_blocks * 32)); CU(cudaMalloc((void**)&d_real, (size_t)world * max_blocks * 32 + 32)); CU(cudaMalloc((void**)&d_root, 32));
+  int rc = CG_OK;
+  CU(cudaMemsetAsync(d_mine, 0, max_blocks * 32, st));
+  if (n_local) rc = cg_merkle_block_roots_device(d_bytes, leaf_len, n_local, block_log2, d_mine, st);
+  if (rc == CG_OK) {
+    if (world > 1) { int r = g_nccl.AllGather(d_mine, d_all, max_blocks * 32, /*ncclChar*/ 0, comm, st); if (r) rc = nccl_fail(r, "ncclAllGather"); }
+    else CU(cudaMemcpyAsync(d_all, d_mine, max_blocks * 32, cudaMemcpyDeviceToDevice, st));
+  }
+  uint64_t total_blocks = 0;
+  if (rc == CG_OK) {
+    for (int r = 0; r < world; r++) { if (nblk[(size_t)r]) CU(cudaMemcpyAsync(d_real + total_blocks * 32, d_all + (size_t)r * max_blocks * 32, nblk[(size_t)r] * 32, cudaMemcpyDeviceToDevice, st)); total_blocks += nblk[(size_t)r]; }
+    rc = cg_merkle_fold_device(d_real, total_blocks, d_root, st);
+  }
+  if (rc == CG_OK) { CU(cudaMemcpyAsync(out_root, d_root, 32, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+  cudaFree(d_mine); cudaFree(d_all); cudaFree(d_real); cudaFree(d_root);
+  return rc;
 }
 
 int cg_merkle_fold(const uint8_t* nodes32, uint64_t m, uint8_t out_root[32]) {
