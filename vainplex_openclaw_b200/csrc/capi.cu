@@ -30,6 +30,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pev_scan[8] = {};      // profiling: begin / end of scan_kernel for each of the (at most four) pieces of a step
+  uint32_t prof_pieces = 0;
   bool profiling = false;
   cg_stats stats{};
   uint64_t launches = 0;
@@ -151,9 +153,24 @@ int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_of
   CU(cudaMemsetAsync(w.counters, 0, kCounterWords * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(w.slot_of_msg, 0xff, (size_t)n * 4, st));
   if (G.profiling) cudaEventRecord(G.pev[0], st);
-  int k = launch_scan(rs->dev, w, d_bytes, d_off, n, d_words, G.sm_count, st);
+  // The batch is scanned in up to four pieces, each followed by its own lookup + check: a flagged gram has to be read again,
+  // and a piece of <= ~64 MB is still in the 126 MB L2 when that happens -- a million random 32-byte reads from HBM instead
+  // cost more than the whole scan kernel (measured).  Occurrences of all pieces meet in one queue: resolve / verify run once.
+  static const uint32_t forced = [] { const char* e = getenv("CG_PIECES"); return e ? (uint32_t)atoi(e) : 0u; }();
+  const uint32_t K = forced >= 1 && forced <= 4 ? forced : n >= (1u << 19) ? 4u : n >= (1u << 18) ? 2u : 1u;
+  int k = 0;
+  if (G.profiling) G.prof_pieces = K;
+  for (uint32_t piece = 0; piece < K; piece++) {
+    const uint32_t m0 = (uint32_t)((uint64_t)n * piece / K), m1 = (uint32_t)((uint64_t)n * (piece + 1) / K);
+    if (m1 == m0) continue;
+    ScanWork wk = w; wk.q_cap = w.l1_cap / K; wk.q_slot = piece; wk.fq = w.fq + (size_t)piece * wk.q_cap; wk.pairs = w.pairs + (size_t)piece * wk.q_cap;
+    if (G.profiling) cudaEventRecord(G.pev_scan[2 * piece], st);
+    k += launch_scan(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, d_words + m0, G.sm_count, st);
+    if (G.profiling) cudaEventRecord(G.pev_scan[2 * piece + 1], st);
+    k += launch_lookup_check(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, G.sm_count, st);
+  }
   if (G.profiling) cudaEventRecord(G.pev[1], st);
-  k += launch_confirm(rs->dev, w, d_bytes, d_off, n, spans, G.sm_count, st);
+  k += launch_resolve(rs->dev, w, d_bytes, d_off, n, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[2], st);
   k += launch_verify(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[3], st);
@@ -172,10 +189,12 @@ void default_caps(const cg_ruleset* rs, uint32_t n, uint32_t* l1, uint32_t* slot
   *slot = std::max(std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), rs->work.slot_cap), rs->grow_slot);
   *ev = std::max(std::max<uint32_t>(std::max<uint32_t>(n, 4096), rs->work.event_cap), rs->grow_ev);
 }
+// fq / pairs are cut into four equal pieces at most: the fullest piece decides
+static uint32_t queue_need(const uint32_t* hc) { uint32_t m = 0; for (int i = 24; i < 32; i++) m = std::max(m, hc[i]); return m > (0xffffffffu >> 2) ? 0xffffffffu : 4u * m; }
 // what an overflowed step teaches about the capacities the next one needs
 void learn_caps(cg_ruleset* rs, const uint32_t* hc) {
   const uint32_t flags = hc[3];
-  if (flags & ERR_L1_OVERFLOW) { const uint32_t need = std::max(std::max(hc[4], hc[20]), hc[22]); rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * need, need + 65536)); }
+  if (flags & ERR_L1_OVERFLOW) { const uint32_t need = std::max(hc[4], queue_need(hc)); rs->grow_l1 = std::max<uint32_t>(rs->grow_l1, std::max<uint32_t>(2 * need, need + 65536)); }
   if (flags & ERR_SLOT_OVERFLOW) rs->grow_slot = std::max<uint32_t>(rs->grow_slot, std::max<uint32_t>(2 * hc[0], hc[0] + 4096));
   if (flags & ERR_EVENT_OVERFLOW) rs->grow_ev = std::max<uint32_t>(rs->grow_ev, std::max<uint32_t>(2 * hc[1], hc[1] + 4096));
 }
@@ -220,7 +239,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
     float ms = 0; cudaEventElapsedTime(&ms, G.ev0, G.ev1); G.stats.last_scan_ms = ms;
     uint32_t flags = hs->counters[3];
     if (flags & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
-    if (flags & ERR_L1_OVERFLOW) { l1_cap = std::max<uint32_t>(l1_cap * 2, std::max(std::max(hs->counters[4], hs->counters[20]), hs->counters[22]) + 1024); continue; }
+    if (flags & ERR_L1_OVERFLOW) { l1_cap = std::max<uint32_t>(l1_cap * 2, std::max(hs->counters[4], queue_need(hs->counters.data())) + 1024); continue; }
     if (flags & ERR_SLOT_OVERFLOW) { slot_cap = std::max<uint32_t>(slot_cap * 4, hs->counters[0] + 1024); continue; }
     if (flags & ERR_EVENT_OVERFLOW) { event_cap = std::max<uint32_t>(event_cap * 4, hs->counters[1] + 1024); continue; }
     if (flags & ERR_SPAN_OVERFLOW) { span_cap = std::max<uint32_t>(span_cap * 4, hs->counters[2] + 1024); continue; }
@@ -329,6 +348,7 @@ int cg_init(int device) {
   CU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&G.ev0)); CU(cudaEventCreate(&G.ev1));
   for (int i = 0; i < 5; i++) CU(cudaEventCreate(&G.pev[i]));
+  for (int i = 0; i < 8; i++) CU(cudaEventCreate(&G.pev_scan[i]));
   G.ready = true;
   return CG_OK;
 }
@@ -341,7 +361,7 @@ void cg_shutdown(void) {
   if (G.h_chunk_counters) cudaFreeHost(G.h_chunk_counters);
   if (G.s_h2d) { cudaStreamDestroy(G.s_h2d); cudaStreamDestroy(G.s_d2h); for (int c = 0; c < Ctx::kChunks; c++) { cudaEventDestroy(G.e_h2d[c]); cudaEventDestroy(G.e_done[c]); } }
   cudaFree(G.d_bytes_raw); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
-  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); cudaStreamDestroy(G.stream);
+  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); for (int i = 0; i < 8; i++) cudaEventDestroy(G.pev_scan[i]); cudaStreamDestroy(G.stream);
   G = Ctx();
 }
 
@@ -351,6 +371,10 @@ int cg_last_kernel_ms(float out_ms[4]) {
   // device time of scan / confirm / verify / finalize of the most recent *completed* scan step
   if (!G.ready || !out_ms) return fail(CG_ERR_INVALID_ARG, "not initialised");
   for (int i = 0; i < 4; i++) { out_ms[i] = 0; if (cudaEventElapsedTime(&out_ms[i], G.pev[i], G.pev[i + 1]) != cudaSuccess) { cudaGetLastError(); return fail(CG_ERR_CUDA, "profiling events not recorded / not complete"); } }
+  // [0] = scan_kernel alone (summed over the pieces of the step), [1] = everything else before the VM (lookup, check, resolve)
+  float scan = 0;
+  for (uint32_t p = 0; p < G.prof_pieces; p++) { float t = 0; if (cudaEventElapsedTime(&t, G.pev_scan[2 * p], G.pev_scan[2 * p + 1]) == cudaSuccess) scan += t; else cudaGetLastError(); }
+  if (G.prof_pieces) { out_ms[1] += out_ms[0] - scan; out_ms[0] = scan; }
   return CG_OK;
 }
 
@@ -361,7 +385,7 @@ int cg_scan_work_counters(const cg_ruleset* rs, uint32_t out16[16]) {
   if (!rs || !out16) return fail(CG_ERR_INVALID_ARG, "null argument");
   if (!rs->work.counters) return fail(CG_ERR_INVALID_ARG, "no scan has run");
   memcpy(out16, rs->last_counters, 64);
-  if (!(rs->dev.debug_flags & 2u)) { out16[7] = rs->last_counters[19]; out16[8] = rs->last_counters[20]; out16[9] = rs->last_counters[22]; }   // grams past the recheck map, flag words, (gram, entry) pairs
+  if (!(rs->dev.debug_flags & 2u)) { out16[7] = rs->last_counters[19]; out16[8] = out16[9] = 0; for (int i = 0; i < 4; i++) { out16[8] += rs->last_counters[24 + i]; out16[9] += rs->last_counters[28 + i]; } }   // grams past the recheck map, flag words, (gram, entry) pairs
   return CG_OK;
 }
 
@@ -705,7 +729,8 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     }
     hit->used = ++rs->graph_clock;
     CU(cudaGraphLaunch(hit->exec, st));
-    const int kk = 6 + (rs->dev.max_prog_len > 192 ? 1 : 0);       // kernels inside the graph: scan, lookup, check, resolve, verify (+ large-VM), finalize
+    const uint32_t pieces = n >= (1u << 19) ? 4u : n >= (1u << 18) ? 2u : 1u;
+    const int kk = 3 * (int)pieces + 3 + (rs->dev.max_prog_len > 192 ? 1 : 0);       // kernels inside the graph: (scan, lookup, check) per piece, resolve, verify (+ large-VM), finalize
     G.launches += kk; G.stats.kernel_launches += kk;
   }
   if (rc == CG_OK) {

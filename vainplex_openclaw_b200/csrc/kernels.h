@@ -54,7 +54,7 @@ struct DevRuleset {
 struct ScanWork {
   uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (confirmed factor occurrences) [5]=verify cursor
                                  //           [6]=flagged grams (level 1a) [7..15]=debug [17]=n_heavy [18]=verify cursor (light events) [19]=grams past the recheck map
-                                 //           [20]=flag words queued [22]=(gram, entry) pairs queued
+                                 //           [24..27]=flag words queued, [28..31]=(gram, entry) pairs queued, per piece of the batch
   uint32_t* l1_pos;              // [l1_cap] factor occurrences scan_kernel confirms itself (head check, trigger bytes): buffer offset of the
   uint32_t* l1_fac;              //          factor's first byte, factor id
   uint2* pairs;                  // [l1_cap] lookup_kernel's (gram position, index into group_entries) pairs
@@ -69,6 +69,7 @@ struct ScanWork {
   uint32_t* event_pre;           // [event_cap]  policy mode: max units of a match before that factor (0xffff = unbounded)
   uint32_t* spans;               // [span_cap * 6] msg, rule, start_byte, end_byte, start16, end16
   uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap;
+  uint32_t q_cap, q_slot;        // this launch's piece of fq / pairs (a step scans the batch in up to 4 pieces: q_slot 0..3) and its counters [24 + q_slot], [28 + q_slot]
 };
 
 enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32 };
@@ -80,8 +81,10 @@ constexpr uint64_t kWordIncomplete = ~0ull;      // result word of every message
 // d_bytes must be 16-byte aligned and readable up to 16 bytes past off[n].
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, int sm_count, cudaStream_t stream);
-// confirm (three launches): flag words -> grams -> recheck map -> level-1b lookup | exact factors | message, slot, candidates for the VM / direct hits
-int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
+// per piece of the batch: flag words -> grams -> recheck map -> level-1b lookup | exact factors (two launches)
+int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream);
+// once per step: message, slot, candidates for the VM / direct hits / island matcher
+int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream);
 // one verdict word per hit message: action | matched policies << 2 | deciding rule << 12 (cg_policy_verdict_batch)

@@ -255,12 +255,12 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
   uint32_t h1 = 0, t1 = 0;       // the ring holds [h1, t1)
   auto append32 = [&](uint32_t k) {                         // k <= 32 entries from the ring -> the queue
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&w.counters[20], k);
+    if (lane == 0) base = atomicAdd(&w.counters[24 + w.q_slot], k);
     base = __shfl_sync(FULL, base, 0);
     if (lane < k) {
       uint32_t cw, aw;
       asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cw), "=r"(aw) : "r"(ring1 + (((h1 + lane) & (kRing - 1)) << 3)));
-      if (base + lane < w.l1_cap) w.fq[base + lane] = make_uint2(cw, aw); else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
+      if (base + lane < w.q_cap) w.fq[base + lane] = make_uint2(cw, aw); else atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
     }
     h1 += k;
   };
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kConfirmThreads, 6)
 lookup_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, uint32_t cstep) {
   const uint8_t* rk = rs.image + rs.rk_off;
   const uint32_t kbits = rs.stride == 2 ? 8u : 4u, kshift = rs.stride == 2 ? 1u : 2u, n_shapes = rs.n_shapes, end = off[n];
-  const uint32_t nq = (rs.debug_flags & 1u) ? 0u : min(w.counters[20], w.l1_cap);
+  const uint32_t nq = (rs.debug_flags & 1u) ? 0u : min(w.counters[24 + w.q_slot], w.q_cap);
   const uint32_t lane = threadIdx.x & 31u, FULL = 0xffffffffu;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t flagged = 0, passed = 0;
@@ -434,11 +434,11 @@ lookup_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, cons
         const uint32_t wtot = __shfl_sync(FULL, pin, 31);
         if (!wtot) continue;
         uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&w.counters[22], wtot);
+        if (lane == 0) k = atomicAdd(&w.counters[28 + w.q_slot], wtot);
         k = __shfl_sync(FULL, k, 0) + pin - tot;
-        if (lane == 0 && k + wtot > w.l1_cap) atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
+        if (lane == 0 && k + wtot > w.q_cap) atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
 #pragma unroll
-        for (uint32_t u = 0; u < 4; u++) for (uint32_t e = 0; e < sl[u].w; e++, k++) if (k < w.l1_cap) w.pairs[k] = make_uint2(pos, sl[u].z + e);
+        for (uint32_t u = 0; u < 4; u++) for (uint32_t e = 0; e < sl[u].w; e++, k++) if (k < w.q_cap) w.pairs[k] = make_uint2(pos, sl[u].z + e);
       }
     }
   }
@@ -451,7 +451,7 @@ lookup_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, cons
 __global__ void __launch_bounds__(kConfirmThreads, 8)
 check_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n) {
   const uint32_t begin = off[0], end = off[n];
-  const uint32_t np = min(w.counters[22], w.l1_cap);
+  const uint32_t np = min(w.counters[28 + w.q_slot], w.q_cap);
   QueueEmit emit{w};
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
     const uint2 pr = w.pairs[i];
@@ -703,14 +703,18 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   return 1;
 }
 
-int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
+int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream) {
   if (n == 0) return 0;
   const uint32_t cstep = scan_grid(n, sm_count) * (uint32_t)(scan_threads() / 32) * 32u;
   // (the list lengths are only known on the device: grids sized for full occupancy, grid-stride loops)
-  lookup_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, cstep);
+  lookup_kernel<<<sm_count * 6, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, cstep);
   check_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n);
+  return 2;
+}
+int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
+  if (n == 0) return 0;
   resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_bytes, d_off, n, want_spans ? 1 : 0);
-  return 3;
+  return 1;
 }
 
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
