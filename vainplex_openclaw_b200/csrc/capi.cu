@@ -147,17 +147,17 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
   return CG_OK;
 }
 
+static uint32_t scan_pieces() { static const uint32_t k = [] { const char* e = getenv("CG_PIECES"); const int v = e ? atoi(e) : 1; return (uint32_t)(v >= 1 && v <= 4 ? v : 1); }(); return k; }
 // One step on device-resident input: scratch reset, gram scan (+ exact factors), resolve, verify, finalize.  Asynchronous.
 int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words, bool spans, cudaStream_t st) {
   const ScanWork& w = rs->work;
   CU(cudaMemsetAsync(w.counters, 0, kCounterWords * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(w.slot_of_msg, 0xff, (size_t)n * 4, st));
   if (G.profiling) cudaEventRecord(G.pev[0], st);
-  // The batch is scanned in up to four pieces, each followed by its own lookup + check: a flagged gram has to be read again,
-  // and a piece of <= ~64 MB is still in the 126 MB L2 when that happens -- a million random 32-byte reads from HBM instead
-  // cost more than the whole scan kernel (measured).  Occurrences of all pieces meet in one queue: resolve / verify run once.
-  static const uint32_t forced = [] { const char* e = getenv("CG_PIECES"); return e ? (uint32_t)atoi(e) : 0u; }();
-  const uint32_t K = forced >= 1 && forced <= 4 ? forced : n >= (1u << 19) ? 4u : n >= (1u << 18) ? 2u : 1u;
+  // CG_PIECES = 2..4 scans the batch in pieces, each followed by its own lookup + check, so that a flagged gram is read again
+  // while its piece is still in the 126 MB L2.  Measured on 1 Mi x 256 B: 0.292 ms in one piece, 0.322 in two, 0.364 in four --
+  // every extra launch of the latency-bound kernels costs more than the L2 hits save.  One piece unless asked otherwise.
+  const uint32_t K = scan_pieces();
   int k = 0;
   if (G.profiling) G.prof_pieces = K;
   for (uint32_t piece = 0; piece < K; piece++) {
@@ -190,7 +190,7 @@ void default_caps(const cg_ruleset* rs, uint32_t n, uint32_t* l1, uint32_t* slot
   *ev = std::max(std::max<uint32_t>(std::max<uint32_t>(n, 4096), rs->work.event_cap), rs->grow_ev);
 }
 // fq / pairs are cut into four equal pieces at most: the fullest piece decides
-static uint32_t queue_need(const uint32_t* hc) { uint32_t m = 0; for (int i = 24; i < 32; i++) m = std::max(m, hc[i]); return m > (0xffffffffu >> 2) ? 0xffffffffu : 4u * m; }
+static uint32_t queue_need(const uint32_t* hc) { uint32_t m = 0; for (int i = 24; i < 32; i++) m = std::max(m, hc[i]); return m > 0xffffffffu / scan_pieces() ? 0xffffffffu : scan_pieces() * m; }
 // what an overflowed step teaches about the capacities the next one needs
 void learn_caps(cg_ruleset* rs, const uint32_t* hc) {
   const uint32_t flags = hc[3];
@@ -729,7 +729,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     }
     hit->used = ++rs->graph_clock;
     CU(cudaGraphLaunch(hit->exec, st));
-    const uint32_t pieces = n >= (1u << 19) ? 4u : n >= (1u << 18) ? 2u : 1u;
+    const uint32_t pieces = scan_pieces();
     const int kk = 3 * (int)pieces + 3 + (rs->dev.max_prog_len > 192 ? 1 : 0);       // kernels inside the graph: (scan, lookup, check) per piece, resolve, verify (+ large-VM), finalize
     G.launches += kk; G.stats.kernel_launches += kk;
   }
