@@ -48,7 +48,7 @@ SPAN_DTYPE = np.dtype([("msg", np.uint32), ("rule", np.uint32), ("start_byte", n
                        ("start16", np.uint32), ("end16", np.uint32)])
 
 EXPORTS = ["cg_init", "cg_shutdown", "cg_last_error", "cg_version", "cg_device_count", "cg_get_stats", "cg_launch_count",
-           "cg_set_profiling", "cg_last_kernel_ms", "cg_scan_work_counters", "cg_scan_join", "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch",
+           "cg_set_profiling", "cg_last_kernel_ms", "cg_last_tail_ms", "cg_scan_work_counters", "cg_scan_join", "cg_redact_batch", "cg_ruleset_set_policy", "cg_policy_verdict_batch",
            "cg_merkle_log_create", "cg_merkle_log_destroy", "cg_merkle_log_append", "cg_merkle_log_size", "cg_merkle_log_root",
            "cg_merkle_log_frontier", "cg_merkle_log_restore", "cg_merkle_log_proof", "cg_merkle_verify_proof",
            "cg_merkle_log_append_jsonl", "cg_merkle_log_consistency", "cg_merkle_verify_consistency", "cg_merkle_log_reserve",
@@ -85,6 +85,7 @@ def load():
     L.cg_launch_count.restype = u64
     L.cg_set_profiling.argtypes = [i32]; L.cg_set_profiling.restype = i32
     L.cg_last_kernel_ms.argtypes = [vp]; L.cg_last_kernel_ms.restype = i32
+    L.cg_last_tail_ms.argtypes = [vp]; L.cg_last_tail_ms.restype = i32
     L.cg_scan_work_counters.argtypes = [vp, vp]; L.cg_scan_work_counters.restype = i32
     L.cg_scan_join.argtypes = [vp, vp]; L.cg_scan_join.restype = i32
     L.cg_redact_batch.argtypes = [vp, vp, vp, u32, vp, u64, vp, vp, vp, u32, vp, vp]; L.cg_redact_batch.restype = i32
@@ -331,6 +332,13 @@ def last_kernel_ms():
     """(scan_ms, confirm_ms, verify_ms, finalize_ms) of the last completed scan step (profiling must be on)."""
     out = np.zeros(4, dtype=np.float32)
     check(load().cg_last_kernel_ms(out.ctypes.data))
+    return tuple(float(x) for x in out)
+
+
+def last_tail_ms():
+    """(lookup_ms, check_ms, resolve_ms) of the last completed scan step (profiling must be on)."""
+    out = np.zeros(3, dtype=np.float32)
+    check(load().cg_last_tail_ms(out.ctypes.data))
     return tuple(float(x) for x in out)
 
 

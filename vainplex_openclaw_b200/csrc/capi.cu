@@ -30,6 +30,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pev_mid[4] = {};       // profiling: between lookup_kernel and check_kernel of each piece
   cudaEvent_t pev_scan[8] = {};      // profiling: begin / end of scan_kernel for each of the (at most four) pieces of a step
   uint32_t prof_pieces = 0;
   bool profiling = false;
@@ -108,7 +109,7 @@ struct cg_ruleset {
     for (auto& e : e_cnt) if (e) cudaEventDestroy(e);
     for (void* p : allocs) cudaFree(p);
     cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.fq); cudaFree(work.pairs); cudaFree(work.slot_of_msg);
-    cudaFree(work.counters); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
+    cudaFree(work.counters); cudaFree(work.persist); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
   }
 };
 
@@ -127,7 +128,7 @@ int upload(cg_ruleset* rs, const std::vector<T>& v, const T** out, size_t pad_el
 }
 
 int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, uint32_t slot_cap, uint32_t event_cap, uint32_t span_cap) {
-  if (!w.counters) { CU(cudaMalloc((void**)&w.counters, kCounterWords * sizeof(uint32_t))); }
+  if (!w.counters) { CU(cudaMalloc((void**)&w.counters, kCounterWords * sizeof(uint32_t))); CU(cudaMalloc((void**)&w.persist, 16)); CU(cudaMemset(w.persist, 0, 16)); CU(cudaDeviceSynchronize()); }
   if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
   if (l1_cap > w.l1_cap) {
     cudaFree(w.l1_pos); cudaFree(w.l1_fac); cudaFree(w.fq); cudaFree(w.pairs); w.l1_pos = w.l1_fac = nullptr; w.fq = w.pairs = nullptr; w.l1_cap = 0;
@@ -140,6 +141,8 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
     CU(cudaMalloc((void**)&w.slot_msg, (size_t)slot_cap * 4));
     CU(cudaMalloc((void**)&w.cand, (size_t)slot_cap * rw * 4));
     CU(cudaMalloc((void**)&w.hit, (size_t)slot_cap * rw * 4));
+    // rows start out zero and every step clears the ones it used (reset_kernel)
+    CU(cudaMemset(w.cand, 0, (size_t)slot_cap * rw * 4)); CU(cudaMemset(w.hit, 0, (size_t)slot_cap * rw * 4)); CU(cudaMemset(w.persist, 0, 16)); CU(cudaDeviceSynchronize());
     w.slot_cap = slot_cap;
   }
   if (event_cap > w.event_cap) { cudaFree(w.events); cudaFree(w.event_pos); cudaFree(w.event_pre); cudaFree(w.heavy_idx); w.events = nullptr; w.event_pos = w.event_pre = w.heavy_idx = nullptr; w.event_cap = 0; CU(cudaMalloc((void**)&w.events, (size_t)event_cap * sizeof(uint2))); CU(cudaMalloc((void**)&w.heavy_idx, (size_t)event_cap * 4)); CU(cudaMalloc((void**)&w.event_pos, (size_t)event_cap * 4)); CU(cudaMalloc((void**)&w.event_pre, (size_t)event_cap * 4)); w.event_cap = event_cap; }
@@ -151,14 +154,12 @@ static uint32_t scan_pieces() { static const uint32_t k = [] { const char* e = g
 // One step on device-resident input: scratch reset, gram scan (+ exact factors), resolve, verify, finalize.  Asynchronous.
 int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, uint64_t* d_words, bool spans, cudaStream_t st) {
   const ScanWork& w = rs->work;
-  CU(cudaMemsetAsync(w.counters, 0, kCounterWords * sizeof(uint32_t), st));
-  CU(cudaMemsetAsync(w.slot_of_msg, 0xff, (size_t)n * 4, st));
+  int k = launch_reset(rs->dev, w, n, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[0], st);
   // CG_PIECES = 2..4 scans the batch in pieces, each followed by its own lookup + check, so that a flagged gram is read again
   // while its piece is still in the 126 MB L2.  Measured on 1 Mi x 256 B: 0.292 ms in one piece, 0.322 in two, 0.364 in four --
   // every extra launch of the latency-bound kernels costs more than the L2 hits save.  One piece unless asked otherwise.
   const uint32_t K = scan_pieces();
-  int k = 0;
   if (G.profiling) G.prof_pieces = K;
   for (uint32_t piece = 0; piece < K; piece++) {
     const uint32_t m0 = (uint32_t)((uint64_t)n * piece / K), m1 = (uint32_t)((uint64_t)n * (piece + 1) / K);
@@ -167,7 +168,7 @@ int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_of
     if (G.profiling) cudaEventRecord(G.pev_scan[2 * piece], st);
     k += launch_scan(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, d_words + m0, G.sm_count, st);
     if (G.profiling) cudaEventRecord(G.pev_scan[2 * piece + 1], st);
-    k += launch_lookup_check(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, G.sm_count, st);
+    k += launch_lookup_check(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, G.sm_count, st, G.profiling ? G.pev_mid[piece] : nullptr);
   }
   if (G.profiling) cudaEventRecord(G.pev[1], st);
   k += launch_resolve(rs->dev, w, d_bytes, d_off, n, spans, G.sm_count, st);
@@ -349,6 +350,7 @@ int cg_init(int device) {
   CU(cudaEventCreate(&G.ev0)); CU(cudaEventCreate(&G.ev1));
   for (int i = 0; i < 5; i++) CU(cudaEventCreate(&G.pev[i]));
   for (int i = 0; i < 8; i++) CU(cudaEventCreate(&G.pev_scan[i]));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreate(&G.pev_mid[i]));
   G.ready = true;
   return CG_OK;
 }
@@ -361,7 +363,7 @@ void cg_shutdown(void) {
   if (G.h_chunk_counters) cudaFreeHost(G.h_chunk_counters);
   if (G.s_h2d) { cudaStreamDestroy(G.s_h2d); cudaStreamDestroy(G.s_d2h); for (int c = 0; c < Ctx::kChunks; c++) { cudaEventDestroy(G.e_h2d[c]); cudaEventDestroy(G.e_done[c]); } }
   cudaFree(G.d_bytes_raw); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
-  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); for (int i = 0; i < 8; i++) cudaEventDestroy(G.pev_scan[i]); cudaStreamDestroy(G.stream);
+  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); for (int i = 0; i < 8; i++) cudaEventDestroy(G.pev_scan[i]); for (int i = 0; i < 4; i++) cudaEventDestroy(G.pev_mid[i]); cudaStreamDestroy(G.stream);
   G = Ctx();
 }
 
@@ -375,6 +377,15 @@ int cg_last_kernel_ms(float out_ms[4]) {
   float scan = 0;
   for (uint32_t p = 0; p < G.prof_pieces; p++) { float t = 0; if (cudaEventElapsedTime(&t, G.pev_scan[2 * p], G.pev_scan[2 * p + 1]) == cudaSuccess) scan += t; else cudaGetLastError(); }
   if (G.prof_pieces) { out_ms[1] += out_ms[0] - scan; out_ms[0] = scan; }
+  return CG_OK;
+}
+
+int cg_last_tail_ms(float out_ms[3]) {
+  // lookup_kernel / check_kernel / resolve_kernel of the most recent completed step in profiling mode (first piece)
+  if (!G.ready || !out_ms) return fail(CG_ERR_INVALID_ARG, "not initialised");
+  out_ms[0] = out_ms[1] = out_ms[2] = 0;
+  if (cudaEventElapsedTime(&out_ms[0], G.pev_scan[1], G.pev_mid[0]) != cudaSuccess || cudaEventElapsedTime(&out_ms[1], G.pev_mid[0], G.pev[1]) != cudaSuccess ||
+      cudaEventElapsedTime(&out_ms[2], G.pev[1], G.pev[2]) != cudaSuccess) { cudaGetLastError(); return fail(CG_ERR_CUDA, "profiling events not recorded / not complete"); }
   return CG_OK;
 }
 
@@ -446,6 +457,21 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   { const uint32_t* sw = nullptr; if ((rc = upload(rs.get(), H.slot_words, &sw, 16))) return rc; d.slots = reinterpret_cast<const uint4*>(sw); }
   if ((rc = upload(rs.get(), H.group_entries, &d.group_entries))) return rc;
   d.slot_shift = H.slot_shift; d.slot_mask = H.n_slots - 1;
+  {
+    // confirm_kernel's tables in one block (kernels.h)
+    std::vector<uint8_t> cf;
+    auto put = [&](const void* p, size_t bytes, size_t pad = 0) { const uint32_t o = (uint32_t)cf.size(); cf.resize((cf.size() + bytes + pad + 15) & ~(size_t)15, 0); if (bytes) memcpy(cf.data() + o, p, bytes); return o; };
+    put(H.image.data() + H.rk_off, H.rk_bytes);
+    d.cf_slots_off = put(H.slot_words.data(), H.slot_words.size() * 4);
+    d.cf_ge_off = put(H.group_entries.data(), H.group_entries.size() * 4, 16);
+    d.cf_fac_off = put(H.factor_words.data(), H.factor_words.size() * 4, 64);
+    d.cf_bs_off = put(P.bytesets.data(), P.bytesets.size() * 4, 32);
+    d.cf_bytes = (uint32_t)cf.size();
+    static const bool no_smem = getenv("CG_CONFIRM_SMEM") && atoi(getenv("CG_CONFIRM_SMEM")) == 0;
+    d.cf_resident = (!no_smem && d.cf_bytes <= kConfirmTableBudget) ? 1u : 0u;
+    const uint8_t* dcf = nullptr; if ((rc = upload(rs.get(), cf, &dcf, 16))) return rc;
+    d.cf_image = dcf;
+  }
   d.n_factors = (uint32_t)P.factors.size();
   if ((rc = upload(rs.get(), H.factor_words, &d.factors, 16))) return rc;
   if ((rc = upload(rs.get(), P.bytesets, &d.bytesets, 8))) return rc;

@@ -28,6 +28,9 @@ struct DevRuleset {
   const uint4* slots;            // lookup_kernel's view of the same entries (ruleset_image.h): open-addressing table of groups
   const uint32_t* group_entries; // entry words (factor | (gram offset + 3) << 20 | shape << 25) in group order
   uint32_t slot_shift, slot_mask;
+  // confirm_kernel's tables as one block ([recheck map][slots][group entries][factor words][byte sets], 16-byte aligned parts):
+  // staged into shared memory when cf_resident (they fit beside the position rings), read in place otherwise
+  const uint8_t* cf_image; uint32_t cf_bytes, cf_resident, cf_slots_off, cf_ge_off, cf_fac_off, cf_bs_off;
   uint32_t n_factors;
   uint32_t max_prog_len;         // longest Pike program of the set (picks the VM capacity)
   uint32_t debug_flags;          // CG_SCAN_DEBUG (experiments only): bit 0 = drop flagged grams (results wrong),
@@ -40,7 +43,7 @@ struct DevRuleset {
   const uint32_t* rule_prog_off; // n_rules + 1
   const uint32_t* sets;          // 6 words per unit set: ascii[4], range_off, n_ranges
   const uint16_t* set_ranges;    // inclusive lo,hi pairs
-  const unsigned long long* bit_words; const uint32_t* bit_off;   // bitprog.h: 137 + 64 x rows words per eligible rule, bit_off[rule] = first word or 0xffffffff
+  const unsigned long long* bit_words; const uint32_t* bit_off;   // bitprog.h: 139 + 64 x rows words per eligible rule, bit_off[rule] = first word or 0xffffffff
   const uint32_t* rule_first;    // 8 words per rule: first-byte bitmap
   const uint32_t* rule_alpha;    // 8 words per rule: alphabet bitmap (bytes a match can contain)
   // verdict aggregation (policy-evaluator.ts:44-146, messageContains slice): per rule its policy (index in priority order,
@@ -59,6 +62,7 @@ struct ScanWork {
   uint32_t* l1_fac;              //          factor's first byte, factor id
   uint2* pairs;                  // [l1_cap] lookup_kernel's (gram position, index into group_entries) pairs
   uint2* fq;                     // [l1_cap] scan_kernel's flag words: x = the lane's chunk number after the round, y = 4 tiles x 8 (4) probe bits
+  uint32_t* persist;             // [4] survives the per-step reset: [0] = slots the previous step used (their candidate / hit rows are zeroed by the next step's reset_kernel)
   uint32_t* slot_of_msg;         // [n] 0xffffffff = none yet (reset per step)
   uint32_t* slot_msg;            // [slot_cap]
   uint32_t* cand;                // [slot_cap * rw]  candidate (msg,rule) pairs already queued
@@ -74,6 +78,7 @@ struct ScanWork {
 
 enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32 };
 constexpr uint32_t kCounterWords = 32;
+constexpr uint32_t kConfirmTableBudget = 176u * 1024u;     // shared memory confirm_kernel may spend on its tables (beside 32 KB of rings)
 constexpr uint64_t kWordIncomplete = ~0ull;      // result word of every message of a batch whose queues overflowed / whose VM failed
 
 // launchers (all asynchronous on `stream`); return the number of kernels launched.
@@ -82,7 +87,7 @@ constexpr uint64_t kWordIncomplete = ~0ull;      // result word of every message
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, int sm_count, cudaStream_t stream);
 // per piece of the batch: flag words -> grams -> recheck map -> level-1b lookup | exact factors (two launches)
-int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream);
+int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream, cudaEvent_t mid = nullptr);
 // once per step: message, slot, candidates for the VM / direct hits / island matcher
 int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
@@ -90,6 +95,8 @@ int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byte
 // one verdict word per hit message: action | matched policies << 2 | deciding rule << 12 (cg_policy_verdict_batch)
 int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdicts, int sm_count, cudaStream_t stream);
 int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, uint32_t n, int sm_count, cudaStream_t stream);
+// start of a step: counters = 0, slot_of_msg = none, candidate / hit rows of the slots the previous step used = 0
+int launch_reset(const DevRuleset& rs, const ScanWork& w, uint32_t n, int sm_count, cudaStream_t stream);
 
 // raises the dynamic shared-memory limits of every kernel once (not legal inside stream capture)
 void prepare_scan_kernels();

@@ -915,7 +915,7 @@ bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOpti
 
 // ---------------------------------------------------------------------------------------------------------------
 // bit-parallel form of a Pike program (bitprog.h)
-bool build_bitprog(const CompiledRule& r, uint64_t* out) {      // out: kBitProgWords = 649 words
+bool build_bitprog(const CompiledRule& r, uint64_t* out) {      // out: kBitProgWords = 651 words
   const std::vector<uint32_t>& prog = r.prog;
   if (r.status != RULE_OK || prog.empty()) return false;
   std::vector<int> bit_of(prog.size(), -1); int nc = 0;
@@ -924,7 +924,7 @@ bool build_bitprog(const CompiledRule& r, uint64_t* out) {      // out: kBitProg
     if (op == OP_CHAR || op == OP_SET || op == OP_ANY) { if (nc >= 63) return false; bit_of[pc] = nc++; }
     else if (op == OP_LOOKAHEAD || op == OP_NLOOKAHEAD || op == OP_LOOKBEHIND || op == OP_NLOOKBEHIND) return false;
   }
-  for (uint32_t i = 0; i < 137 + 8 * 64; i++) out[i] = 0;
+  for (uint32_t i = 0; i < 139 + 8 * 64; i++) out[i] = 0;
   // accept[b]: the consuming instructions an ASCII byte satisfies
   for (size_t pc = 0; pc < prog.size(); pc++) {
     if (bit_of[pc] < 0) continue;
@@ -968,8 +968,21 @@ bool build_bitprog(const CompiledRule& r, uint64_t* out) {      // out: kBitProg
     header |= (uint64_t)r << (4 * ctx);
   }
   header |= (uint64_t)n_rows << 32;
+  bool start_same = true; for (uint32_t ctx = 1; ctx < 8; ctx++) start_same = start_same && out[128 + ctx] == out[128];
+  if (start_same) header |= 1ull << 40;
   out[136] = header;
-  for (uint32_t r = 0; r < n_rows; r++) memcpy(out + 137 + r * 64, rows[r], sizeof rows[r]);
+  // instructions whose successors are {k + 1} and / or {k} in every row: a shift and a mask instead of a table row (bitprog.h)
+  uint64_t m_next = 0, m_self = 0;
+  for (int k = 0; k < nc; k++) {
+    const uint64_t f = rows[0][k], allowed = (1ull << k) | (1ull << (k + 1));
+    bool simple = (f & ~allowed) == 0;
+    for (uint32_t r = 1; r < n_rows && simple; r++) simple = rows[r][k] == f;
+    if (!simple) continue;
+    if (f & (1ull << (k + 1))) m_next |= 1ull << k;
+    if (f & (1ull << k)) m_self |= 1ull << k;
+  }
+  out[137] = m_next; out[138] = m_self;
+  for (uint32_t r = 0; r < n_rows; r++) memcpy(out + 139 + r * 64, rows[r], sizeof rows[r]);
   return true;
 }
 

@@ -286,6 +286,7 @@ scan_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanW
 // ------------------------------------------------------------------------------------------
 // level 2: which message does every confirmed factor occurrence belong to?  Slots, candidates for the VM, direct hits.
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t kIslandSteps = 96;      // islands the bit-parallel matcher walks itself (longer ones, and those it cannot reach the occurrence in, are the VM's)
 struct SlotSink {
   const DevRuleset& rs; const ScanWork& w; uint32_t msg; uint32_t slot;
   const uint8_t* text = nullptr; uint32_t text_len = 0;       // the message (policy mode: lets candidate() decide eligible rules on the spot)
@@ -296,9 +297,7 @@ struct SlotSink {
     if (s == 0xffffffffu) {
       uint32_t mine = atomicAdd(&w.counters[0], 1u);
       if (mine >= w.slot_cap) { atomicOr(&w.counters[3], ERR_SLOT_OVERFLOW); slot = mine; return false; }
-      for (uint32_t k = 0; k < rs.rw; k++) { w.cand[(size_t)mine * rs.rw + k] = 0; w.hit[(size_t)mine * rs.rw + k] = 0; }
-      w.slot_msg[mine] = msg;
-      __threadfence();                                   // rows are zero before the slot becomes visible
+      w.slot_msg[mine] = msg;                            // (the slot's candidate / hit rows are zero already: reset_kernel; no fence on this path)
       uint32_t old = atomicCAS(&w.slot_of_msg[msg], 0xffffffffu, mine);
       if (old == 0xffffffffu) s = mine; else { s = old; w.slot_msg[mine] = 0xffffffffu; }   // lost the race: slot stays unused
     }
@@ -315,7 +314,8 @@ struct SlotSink {
       const uint32_t bo = rs.bit_off[r];
       if (bo != kBitProgNone) {
         if (slot == 0xffffffffu) { const uint32_t s0 = *reinterpret_cast<volatile uint32_t*>(&w.slot_of_msg[msg]); if (s0 != 0xffffffffu && s0 < w.slot_cap && ((w.hit[(size_t)s0 * rs.rw + (r >> 5)] >> (r & 31)) & 1u)) return; }   // already a hit
-        const int res = bitprog_test(reinterpret_cast<const uint64_t*>(rs.bit_words) + bo, text, text_len, island_start(rs, r, text, text_len, t0, pre), t0, 96u);
+        const uint32_t is = island_start(rs, r, text, text_len, t0, pre, kIslandSteps);
+        const int res = min(t0, text_len) - is >= kIslandSteps ? -1 : bitprog_test(reinterpret_cast<const uint64_t*>(rs.bit_words) + bo, text, text_len, is, t0, kIslandSteps);
         if (res == 0) return;
         if (res == 1) { direct(r); return; }
       }
@@ -481,11 +481,183 @@ check_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const
   }
 }
 
+
+// lookup + check as ONE launch (the default).  What the two launches above cost is not the looking itself -- 850 k random
+// 4-byte places of a 268 MB buffer are read again in 20 us (profiles/micro/gather_micro.cu) -- but the number of
+// uncoalesced loads behind it: measured, both kernels run at about one lane-level request per SM and clock, and an item
+// costs them 5.5 (gram, recheck word, three slots) + 23 (entry, factor words, text words, sixteen byte-set words).  So:
+//   * the tables (recheck map, slots, entries, factor words, byte sets: 127 KB at 500 rules) are staged into SHARED memory,
+//     where a random word costs a bank conflict instead of an L1 tag lookup per lane; rule sets whose tables do not fit are read
+//     in place (same code, generic pointers);
+//   * slots are only probed for grams that passed the recheck map, and a (gram, entry) pair first compares the (up to) four
+//     factor elements that follow the gram -- two text words at most -- before anything else is fetched: nine pairs in ten end there;
+//   * no lane ever loops over its own items while the others wait (the first fused version did: 32 M warp instructions, two
+//     thirds of them in per-lane entry and byte loops with one or two lanes active).  Flag bits become gram positions, and the
+//     entries a gram hits become (position, entry) pairs, in WAVES of at most one item per lane that are compacted with a
+//     ballot into a 64-entry ring per warp in shared memory; whenever a ring holds 32 items, all 32 lanes run the next stage
+//     as a straight line (gram -> recheck -> probes | quick test -> whole factor).  Leftovers wait for the next wave.
+constexpr uint32_t kCfRing = 64;                  // entries per warp and ring (a power of two): 31 leftovers + one wave of 32
+constexpr int kCfThreads = 1024;
+constexpr uint32_t kCfRingBytes = (kCfThreads / 32) * kCfRing * (4 + 8);     // gram positions (4 B) and (position, entry) pairs (8 B)
+
+struct ConfirmCtx {
+  const DevRuleset& rs; const ScanWork& w; const uint8_t* bytes;
+  const uint8_t* rk; const uint4* slots; const uint32_t* group_entries; const uint32_t* factors; const uint32_t* bytesets;     // shared-memory copies when they fit
+  uint2* pring; uint32_t phead, ptail;          // this warp's ring of (gram position, entry) pairs
+  uint32_t begin, end, n_shapes, passed, lane;
+};
+__device__ __forceinline__ uint32_t byteset_bit(const uint32_t* __restrict__ bytesets, uint32_t sid, uint32_t b) { return (bytesets[(size_t)sid * 8 + (b >> 5)] >> (b & 31)) & 1u; }
+
+// one (gram, entry) pair per lane: does the entry's factor start at the position the gram implies?  First the (up to) four
+// elements that follow the gram (the factor's first four when the gram is its tail): two text words at most, and nine pairs
+// in ten end there; the lanes that are left compare the whole factor (five text words at most, every element test in flight).
+__device__ __forceinline__ void confirm_pairs(ConfirmCtx& c, uint2 pr, bool active) {
+  uint32_t f = 0, flen = 0, qb = 0, qe = 0; int64_t t0 = 0; const uint32_t* fw = c.factors;
+  bool ok = false;
+  if (active) {
+    const uint32_t y = c.group_entries[pr.y];
+    f = y & 0xfffffu;
+    const int goff = (int)((y >> 20) & 31u) - 3;
+    t0 = (int64_t)pr.x - goff;
+    fw = c.factors + (size_t)f * 12;          // rule, len | exact << 24, 16 x u16 set ids, pre, pre_alpha
+    flen = fw[1] & 0xffu;
+    ok = t0 >= (int64_t)c.begin && t0 + (int64_t)flen <= (int64_t)c.end;
+    qb = (uint32_t)(goff + (int)kGramLen < 0 ? 0 : goff + (int)kGramLen); if (qb >= flen) qb = 0;
+    qe = min(qb + 4u, flen);
+  }
+  if (ok && qe > qb) {
+    const size_t qp = (size_t)t0 + qb;
+    const uint32_t* tq = reinterpret_cast<const uint32_t*>(c.bytes + (qp & ~(size_t)3));
+    const uint32_t q0 = __ldg(tq), q1 = ((uint32_t)qp & 3u) + (qe - qb) > 4u ? __ldg(tq + 1) : 0u;
+    const uint32_t qt = __funnelshift_r(q0, q1, 8u * ((uint32_t)qp & 3u));
+    uint32_t bits = 1u;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) {
+      const uint32_t k = qb + i;
+      if (k < qe) bits &= byteset_bit(c.bytesets, (fw[2 + (k >> 1)] >> (16 * (k & 1))) & 0xffffu, (qt >> (8 * i)) & 0xffu);
+    }
+    ok = bits != 0;
+  }
+  if (!__any_sync(0xffffffffu, ok)) return;
+  if (ok && flen > qe - qb) {
+    const uint32_t* tp = reinterpret_cast<const uint32_t*>(c.bytes + ((size_t)t0 & ~(size_t)3));
+    const uint32_t sh = 8u * ((uint32_t)t0 & 3u);
+    const uint32_t need = ((uint32_t)t0 & 3u) + flen;           // bytes from the first aligned word on (nothing past the factor's end is read)
+    const uint32_t a0 = __ldg(tp), a1 = need > 4u ? __ldg(tp + 1) : 0u, a2 = need > 8u ? __ldg(tp + 2) : 0u, a3 = need > 12u ? __ldg(tp + 3) : 0u, a4 = need > 16u ? __ldg(tp + 4) : 0u;
+    const uint32_t tx[4] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh)};
+    uint32_t bits = 1u;
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++) {
+      if (k < flen && !(k >= qb && k < qe)) bits &= byteset_bit(c.bytesets, (fw[2 + (k >> 1)] >> (16 * (k & 1))) & 0xffffu, (tx[k >> 2] >> (8 * (k & 3))) & 0xffu);
+    }
+    ok = bits != 0;
+  }
+  if (ok) {
+    const uint32_t k = atomicAdd(&c.w.counters[4], 1u);
+    if (k < c.w.l1_cap) { c.w.l1_pos[k] = (uint32_t)t0; c.w.l1_fac[k] = f; } else atomicOr(&c.w.counters[3], ERR_L1_OVERFLOW);
+  }
+}
+
+// one gram position per lane (active lanes only do loads; everybody takes part in the votes): gram -> recheck map -> one probe
+// per shape; the entries of the groups it hits go to the pair ring in waves of at most one per lane, 32 pairs at a time leave it
+__device__ __forceinline__ void confirm_gram(ConfirmCtx& c, uint32_t pos, bool active) {
+  const DevRuleset& rs = c.rs;
+  const uint32_t FULL = 0xffffffffu, lt = (1u << c.lane) - 1u;
+  active = active && pos < c.end;
+  uint32_t key = 0;
+  if (active) {
+    const uint32_t* p4 = reinterpret_cast<const uint32_t*>(c.bytes + (pos & ~3u));
+    uint32_t gw = __ldg(p4);
+    if (pos & 3u) gw = __funnelshift_r(gw, __ldg(p4 + 1), 8u * (pos & 3u));
+    key = gram_fold_word(gw);
+  }
+  const uint32_t rh = gram_recheck_hash(key);
+  const bool pass = active && ((*reinterpret_cast<const uint32_t*>(c.rk + (rh & rs.rk_mask)) << (rh >> 27)) & 0x80000000u);
+  if (!__any_sync(FULL, pass)) return;
+  if (pass) c.passed++;
+  for (uint32_t s0 = 0; s0 < c.n_shapes; s0 += 4u) {
+    uint32_t first[4], cnt[4], tot = 0;
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++) {
+      const uint32_t s = s0 + u, km = key & rs.shapes[s & 15u];
+      first[u] = 0; cnt[u] = 0;
+      if (pass && s < c.n_shapes) {
+        uint32_t slot = ((km ^ (s * 0x9E3779B9u)) * kGramMult2) >> rs.slot_shift;
+        uint4 sl = c.slots[slot];
+        while (sl.w && (sl.x != km || sl.y != s)) { slot = (slot + 1u) & rs.slot_mask; sl = c.slots[slot]; }    // (linear probing; rarely a second slot)
+        first[u] = sl.z; cnt[u] = sl.w;
+      }
+      tot += cnt[u];
+    }
+    for (uint32_t j = 0;; j++) {
+      const bool has = j < tot;
+      const uint32_t m = __ballot_sync(FULL, has);
+      if (!m) break;
+      if (has) {
+        uint32_t jj = j, ei;
+        if (jj < cnt[0]) ei = first[0] + jj; else { jj -= cnt[0]; if (jj < cnt[1]) ei = first[1] + jj; else { jj -= cnt[1]; if (jj < cnt[2]) ei = first[2] + jj; else ei = first[3] + (jj - cnt[2]); } }
+        c.pring[(c.ptail + __popc(m & lt)) & (kCfRing - 1)] = make_uint2(pos, ei);
+      }
+      c.ptail += __popc(m);
+      __syncwarp();
+      if (c.ptail - c.phead >= 32u) { const uint2 pr = c.pring[(c.phead + c.lane) & (kCfRing - 1)]; c.phead += 32u; __syncwarp(); confirm_pairs(c, pr, true); }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kCfThreads, 1)
+confirm_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, uint32_t cstep) {
+  extern __shared__ __align__(16) uint8_t cf_smem[];          // [pair rings][gram rings][tables, when resident]
+  const uint32_t kbits = rs.stride == 2 ? 8u : 4u, kshift = rs.stride == 2 ? 1u : 2u;
+  const uint32_t nq = (rs.debug_flags & 1u) ? 0u : min(w.counters[24 + w.q_slot], w.q_cap);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5, FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+  uint2* pring = reinterpret_cast<uint2*>(cf_smem) + warp * kCfRing;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(cf_smem + (size_t)wpb * kCfRing * 8) + warp * kCfRing;
+  const uint8_t* T = rs.cf_image;
+  if (rs.cf_resident) {
+    uint8_t* st = cf_smem + (size_t)wpb * kCfRing * 12;
+    if (blockIdx.x * 32u * wpb < nq) {           // (a block without work does not need them)
+      for (uint32_t o = threadIdx.x * 16u; o < rs.cf_bytes; o += blockDim.x * 16u) *reinterpret_cast<uint4*>(st + o) = ldg_stream(rs.cf_image + o);
+    }
+    T = st;
+    __syncthreads();
+  }
+  const uint32_t gwarp = blockIdx.x * wpb + warp, nwarps = gridDim.x * wpb;
+  ConfirmCtx c{rs, w, bytes, T, reinterpret_cast<const uint4*>(T + rs.cf_slots_off), reinterpret_cast<const uint32_t*>(T + rs.cf_ge_off),
+               reinterpret_cast<const uint32_t*>(T + rs.cf_fac_off), reinterpret_cast<const uint32_t*>(T + rs.cf_bs_off), pring, 0u, 0u, off[0], off[n], rs.n_shapes, 0u, lane};
+  uint32_t head = 0, tail = 0, flagged = 0;
+  for (uint32_t base = gwarp * 32u; base < nq; base += nwarps * 32u) {
+    uint2 q = make_uint2(0u, 0u);
+    if (base + lane < nq) q = w.fq[base + lane];
+    // flag bits -> gram positions, one wave per bit rank (the k-th set bit of every lane's word): at most 32 new positions a wave
+    uint32_t bits = q.y;
+    for (;;) {
+      const uint32_t m = __ballot_sync(FULL, bits != 0);
+      if (!m) break;
+      if (bits) {
+        const uint32_t bit = (uint32_t)__ffs((int)bits) - 1u; bits &= bits - 1u;
+        ring[(tail + __popc(m & lt)) & (kCfRing - 1)] = ((q.x - (bit / kbits + 1u) * cstep) * kbits + (kbits - 1u - bit % kbits)) << kshift;
+      }
+      tail += __popc(m); flagged += lane == 0 ? __popc(m) : 0u;
+      __syncwarp();
+      if (tail - head >= 32u) { const uint32_t pos = ring[(head + lane) & (kCfRing - 1)]; head += 32u; __syncwarp(); confirm_gram(c, pos, true); }
+    }
+  }
+  if (tail != head) { const bool a = lane < tail - head; const uint32_t pos = a ? ring[(head + lane) & (kCfRing - 1)] : 0u; __syncwarp(); confirm_gram(c, pos, a); }
+  if (c.ptail != c.phead) { const bool a = lane < c.ptail - c.phead; const uint2 pr = a ? c.pring[(c.phead + lane) & (kCfRing - 1)] : make_uint2(0u, 0u); confirm_pairs(c, pr, a); }
+  const uint32_t passed = __reduce_add_sync(FULL, c.passed);
+  if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); }
+}
+
 __global__ void __launch_bounds__(256)
-resolve_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, int want_spans) {
+resolve_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, int want_spans, uint32_t spread) {
   const uint32_t n1 = min(w.counters[4], w.l1_cap);
   const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t i = tid; i < n1; i += stride) {
+  // Occurrences take different paths of very different lengths (direct hit, island matcher of 5 .. 96 steps, slot allocation),
+  // and a warp executes the union of its lanes' paths one dependent instruction after the other: with 32 occurrences per warp
+  // 1 000 warps ran for the whole 60 us of the kernel (ncu: 5 000 instructions each at ~20 cycles) while 8 000 warp slots stayed
+  // empty.  So only every `spread`-th lane takes an occurrence: more warps, each with a short chain.
+  for (uint32_t i = tid / spread; i < n1 && tid % spread == 0; i += stride / spread) {
     const uint32_t pos = w.l1_pos[i], f = w.l1_fac[i];
     const uint32_t msg = message_of(off, n, pos);
     if (pos + (rs.factors[(size_t)f * 12 + 1] & 0xffu) > off[msg + 1]) continue;     // straddles two messages: not an occurrence
@@ -620,7 +792,19 @@ verify_large_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes
   if (vm.err) atomicOr(&w.counters[3], vm.err);
 }
 
+// Start of a step.  The candidate / hit rows of a slot must be zero when a message takes it; clearing them there cost every
+// first occurrence of a message a loop of stores and a __threadfence in the middle of resolve_kernel's dependency chain.  The
+// rows the PREVIOUS step used are cleared here instead (their number survives in w.persist), together with what two memsets did.
+__global__ void reset_kernel(DevRuleset rs, ScanWork w, uint32_t n) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const uint32_t used = min(w.persist[0], w.slot_cap) * rs.rw;
+  for (uint32_t i = tid; i < used; i += stride) { w.cand[i] = 0; w.hit[i] = 0; }
+  for (uint32_t i = tid; i < n; i += stride) w.slot_of_msg[i] = 0xffffffffu;
+  if (tid < kCounterWords) w.counters[tid] = 0;
+}
+
 __global__ void finalize_kernel(DevRuleset rs, ScanWork w, uint64_t* __restrict__ words, uint32_t n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) w.persist[0] = min(w.counters[0], w.slot_cap);
   // A step whose queues overflowed or whose VM ran out of space has incomplete results: every word of the batch says so
   // (in-band, so that a caller of the asynchronous device path cannot mistake them for "no hit").
   if (w.counters[3]) {
@@ -677,6 +861,7 @@ void prepare_scan_kernels() {
   cudaFuncSetAttribute(scan_kernel<P, T, B, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); cudaFuncSetAttribute(scan_kernel<P, T, B, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   CG_FOR_SCAN_VARIANTS(CG_PREP)
 #undef CG_PREP
+  cudaFuncSetAttribute(confirm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCfRingBytes + kConfirmTableBudget));
   cudaFuncSetAttribute(verify_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
   cudaFuncSetAttribute(verify_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerifySmem);
 }
@@ -703,17 +888,25 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   return 1;
 }
 
-int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream) {
+int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream, cudaEvent_t mid) {
   if (n == 0) return 0;
   const uint32_t cstep = scan_grid(n, sm_count) * (uint32_t)(scan_threads() / 32) * 32u;
   // (the list lengths are only known on the device: grids sized for full occupancy, grid-stride loops)
+  static const bool two_launches = getenv("CG_CONFIRM") && atoi(getenv("CG_CONFIRM")) == 0;      // (the round-2 pair of launches, kept for comparison)
+  if (!two_launches) {
+    confirm_kernel<<<scan_grid(n, sm_count), kCfThreads, (size_t)kCfRingBytes + (rs.cf_resident ? rs.cf_bytes : 0u), stream>>>(rs, w, d_bytes, d_off, n, cstep);
+    if (mid) cudaEventRecord(mid, stream);
+    return 1;
+  }
   lookup_kernel<<<sm_count * 6, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, cstep);
+  if (mid) cudaEventRecord(mid, stream);
   check_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n);
   return 2;
 }
 int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
   if (n == 0) return 0;
-  resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_bytes, d_off, n, want_spans ? 1 : 0);
+  static const uint32_t spread = [] { const char* e = getenv("CG_RESOLVE_SPREAD"); const int v = e ? atoi(e) : 4; return (uint32_t)(v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32 ? v : 4); }();
+  resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(rs, w, d_bytes, d_off, n, want_spans ? 1 : 0, spread);
   return 1;
 }
 
@@ -735,6 +928,11 @@ int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byte
 
 int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdicts, int sm_count, cudaStream_t stream) {
   verdict_kernel<<<sm_count * 2, 256, 0, stream>>>(rs, w, d_verdicts);
+  return 1;
+}
+
+int launch_reset(const DevRuleset& rs, const ScanWork& w, uint32_t n, int sm_count, cudaStream_t stream) {
+  reset_kernel<<<sm_count * 4, 256, 0, stream>>>(rs, w, n);
   return 1;
 }
 
