@@ -151,6 +151,7 @@ void harness_candidates(void* p, const uint8_t* m, uint32_t len, uint32_t* cand,
 }
 
 static uint64_t g_bit_decided = 0, g_bit_mismatch = 0, g_bit_fallback = 0;
+static uint32_t g_vm_rule[8192], g_bit_rule[8192];      // per rule: occurrences left to the VM / decided by the bit-parallel matcher
 // policy-mode verification exactly as verify_*_kernel does it: for every confirmed factor occurrence
 // run test_at_factor; returns the bitmap of rules that hit (direct hits included)
 void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits, uint32_t lead, uint32_t seed) {
@@ -169,11 +170,12 @@ void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits
     // the bit-parallel matcher (what resolve_kernel runs for eligible rules) must say the same whenever it says anything
     if (t0 != 0xffffffffu && d.bit_off[r] != kBitProgNone) {
       const int res = bitprog_test(reinterpret_cast<const uint64_t*>(d.bit_words) + d.bit_off[r], m, len, island_start(d, r, m, len, t0, pre), t0);
-      if (res >= 0) { g_bit_decided++; if ((res == 1) != any) g_bit_mismatch++; } else g_bit_fallback++;
-    }
+      if (res >= 0) { g_bit_decided++; g_bit_rule[r & 8191]++; if ((res == 1) != any) g_bit_mismatch++; } else { g_bit_fallback++; g_vm_rule[r & 8191]++; }
+    } else g_vm_rule[r & 8191]++;
     if (any) hits[r >> 5] |= 1u << (r & 31);
   }
 }
+void harness_rule_counts(uint32_t* vm, uint32_t* bit, uint32_t n) { for (uint32_t i = 0; i < n && i < 8192; i++) { vm[i] = g_vm_rule[i]; bit[i] = g_bit_rule[i]; } }
 void harness_bitprog_stats(uint64_t* out3) { out3[0] = g_bit_decided; out3[1] = g_bit_mismatch; out3[2] = g_bit_fallback; }
 uint32_t harness_bitprog_eligible(void* p) { Harness* h = (Harness*)p; uint32_t k = 0; for (uint32_t r = 0; r < h->d.n_rules; r++) k += h->d.bit_off[r] != kBitProgNone; return k; }
 

@@ -19,42 +19,49 @@
 
 namespace cg {
 
-// table of one rule (uint64 words): accept[128] | start[8] | header | next | self | follow rows [n_rows][64]
-//   header = row of context c in bits 4c..4c+3, n_rows in bits 32..35 (contexts with identical follow rows share one: a rule
-//   without assertions has a single row), bit 40 = start[] is the same in all eight contexts
+// Table of one rule, W = 1 or 2 state words (uint64; consuming instruction k = bit k, MATCH = bit 64 W - 1):
+//   W | accept[128][W] | start[32][W] | meta | rowmap[2] | behind[2] | ahead[2] | next[W] | self[W] | follow rows [n_rows][64 W][W]
+//   context of the position between two units, 5 bits: word boundary, start of message, end of message, previous unit in the
+//   rule's lookbehind set, next unit in its lookahead set (single-unit lookaround, one set per direction, ASCII-only sets:
+//   the token-boundary guards (?<![A-Z0-9]) ... (?![A-Z0-9]) of the credential rules).  Contexts with identical follow rows
+//   share one row: rowmap holds 4 bits per context.
+//   meta = n_rows | W << 4 | start_same << 8 (start[] identical in every context) | has_look << 9
 //   next / self = the instructions k whose follow set is, in every row, a subset of {k, k + 1}: bit k of `next` when it holds
-//   k + 1 (the next unit of a literal or class run; bit 62 -> MATCH), bit k of `self` when it holds k (a loop on one unit).
-//   Their successors are a shift and a mask -- no load; only the other instructions (alternations, group loops) go
-//   through the follow rows.  One thread walks an island, so every load on this path is a round trip to L2.
-constexpr uint32_t kBitAccept = 0, kBitStart = 128, kBitHeader = 136, kBitNext = 137, kBitSelf = 138, kBitRows = 139;
-constexpr uint64_t kBitStartSame = 1ull << 40;
-constexpr uint32_t kBitProgWords = kBitRows + 8 * 64;
+//   k + 1 (the next unit of a literal or class run), bit k of `self` when it holds k (a loop on one unit).  Their successors
+//   are a shift and a mask -- no load; only the other instructions (alternations, group loops) go through the follow rows.
 constexpr uint32_t kBitProgNone = 0xffffffffu;
-constexpr uint64_t kBitMatch = 1ull << 63;
+constexpr uint32_t kBitCtxs = 32;
+CG_HD uint32_t bitprog_meta_off(uint32_t W) { return (128u + kBitCtxs) * W; }
+CG_HD uint32_t bitprog_rows_off(uint32_t W) { return bitprog_meta_off(W) + 7u + 2u * W; }
+CG_HD uint32_t bitprog_words(uint32_t W, uint32_t n_rows) { return bitprog_rows_off(W) + n_rows * 64u * W * W; }
 
-// context of the position between the bytes `prev` and `next` (-1 = none): bit 0 word boundary, bit 1 start of message, bit 2 end
+// context of the position between the bytes `prev` and `next` (-1 = none; 0x80 = some non-ASCII unit)
 CG_HD uint32_t bitprog_ctx(int prev, int next, bool at_start) {
   return (uint32_t)(is_word(prev) != is_word(next)) | (at_start ? 2u : 0u) | (next < 0 ? 4u : 0u);
 }
+CG_HD uint32_t bitprog_in128(uint64_t lo, uint64_t hi, int u) { return u < 0 || u >= 0x80 ? 0u : (uint32_t)(((u & 64) ? hi : lo) >> (u & 63)) & 1u; }
 
 // -> 1 a match that starts in [s, t0] exists, 0 none, -1 cannot tell (non-ASCII byte in the island, or more than max_steps
 // bytes to walk: ask the VM, whose warp-wide runs suit long islands better than one thread's chain of table loads).
 // One thread walks the island, so what this costs is the length of its dependency chain, not its instruction count: the
 // four next bytes and their accept masks are fetched together (loads that depend on the position alone), and only the
 // state update is sequential -- a shift and a mask for most instructions, a follow row from L2 for the others.
-CG_HD int bitprog_test(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps = 0xffffffffu) {
-  const uint64_t* accept = bp + kBitAccept; const uint64_t* start = bp + kBitStart; const uint64_t* rows = bp + kBitRows; const uint64_t header = bp[kBitHeader];
-  const uint64_t m_next = bp[kBitNext], m_self = bp[kBitSelf], m_table = ~(m_next | m_self);
-  const bool start_same = (header & kBitStartSame) != 0, one_row = ((header >> 32) & 15u) == 1u;
+template <int W>
+CG_HD int bitprog_test_w(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps) {
+  const uint64_t* accept = bp; const uint64_t* start = bp + 128 * W; const uint64_t* hd = bp + bitprog_meta_off(W); const uint64_t* rows = bp + bitprog_rows_off(W);
+  const uint64_t meta = hd[0], map0 = hd[1], map1 = hd[2];
+  const bool start_same = (meta >> 8) & 1u, has_look = (meta >> 9) & 1u, one_row = (meta & 15u) == 1u;
+  const uint64_t lb0 = has_look ? hd[3] : 0, lb1 = has_look ? hd[4] : 0, la0 = has_look ? hd[5] : 0, la1 = has_look ? hd[6] : 0;
+  uint64_t m_next[W], m_self[W], live[W], acc_cur[W], start0[W];
+  constexpr uint64_t kMatch = 1ull << 63;            // of the last word
+  for (int w = 0; w < W; w++) { m_next[w] = hd[7 + w]; m_self[w] = hd[7 + W + w]; }
   int prev = s > 0 ? (m[s - 1] < 0x80 ? (int)m[s - 1] : 0x80) : -1;          // (a unit >= 0x80 is not a word character, whatever it is)
   int cur = s < len ? (int)m[s] : -1;
-  uint32_t ctx = bitprog_ctx(prev, cur, s == 0);
-  const uint64_t start0 = start[ctx];
-  uint64_t live = start0;
-  uint64_t acc_cur = cur >= 0 && cur < 0x80 ? accept[cur] : 0;
+  uint32_t ctx = bitprog_ctx(prev, cur, s == 0) | (has_look ? bitprog_in128(lb0, lb1, prev) << 3 | bitprog_in128(la0, la1, cur) << 4 : 0u);
+  for (int w = 0; w < W; w++) { start0[w] = start[ctx * W + w]; live[w] = start0[w]; acc_cur[w] = cur >= 0 && cur < 0x80 ? accept[cur * W + w] : 0; }
   for (uint32_t pos = s;;) {
     // the block's four "next" bytes and their accept masks
-    int nb[4]; uint64_t na[4];
+    int nb[4]; uint64_t na[4][W];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -62,36 +69,50 @@ CG_HD int bitprog_test(const uint64_t* __restrict__ bp, const uint8_t* __restric
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int i = 0; i < 4; i++) na[i] = nb[i] >= 0 && nb[i] < 0x80 ? accept[nb[i]] : 0;
+    for (int i = 0; i < 4; i++) for (int w = 0; w < W; w++) na[i][w] = nb[i] >= 0 && nb[i] < 0x80 ? accept[nb[i] * W + w] : 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int i = 0; i < 4; i++) {
-      if (live & kBitMatch) return 1;
+      if (live[W - 1] & kMatch) return 1;
       if (cur < 0) return 0;
       if (cur >= 0x80 || pos - s >= max_steps) return -1;
-      const uint64_t hit_all = live & acc_cur;
       const int nxt = nb[i];
-      live = ((hit_all & m_next) << 1) | (hit_all & m_self);
-      uint64_t hit = hit_all & m_table;
-      if (!start_same || hit) ctx = bitprog_ctx(cur, nxt < 0x80 ? nxt : 0x80, false);
-      if (hit) {
-        const uint64_t* fw = one_row ? rows : rows + ((header >> (4 * ctx)) & 15u) * 64;
-        while (hit) {
+      uint64_t hit[W], carry = 0, any_hit = 0;
+      for (int w = 0; w < W; w++) {
+        const uint64_t h = live[w] & acc_cur[w], hn = h & m_next[w];
+        live[w] = (hn << 1) | carry | (h & m_self[w]);
+        carry = hn >> 63;
+        hit[w] = h & ~(m_next[w] | m_self[w]); any_hit |= hit[w];
+      }
+      if (!start_same || any_hit) ctx = bitprog_ctx(cur, nxt < 0x80 ? nxt : 0x80, false) | (has_look ? bitprog_in128(lb0, lb1, cur) << 3 | bitprog_in128(la0, la1, nxt) << 4 : 0u);
+      if (any_hit) {
+        const uint32_t row = one_row ? 0u : (uint32_t)(((ctx & 16u) ? map1 : map0) >> (4 * (ctx & 15u))) & 15u;
+        const uint64_t* fw = rows + (size_t)row * 64 * W * W;
+        for (int w = 0; w < W; w++) {
+          uint64_t hw = hit[w];
+          while (hw) {
 #if defined(__CUDA_ARCH__)
-          const int k = __ffsll((long long)hit) - 1;
+            const int k = __ffsll((long long)hw) - 1;
 #else
-          const int k = __builtin_ctzll(hit);
+            const int k = __builtin_ctzll(hw);
 #endif
-          hit &= hit - 1; live |= fw[k];
+            hw &= hw - 1;
+            for (int v = 0; v < W; v++) live[v] |= fw[(size_t)(w * 64 + k) * W + v];
+          }
         }
       }
       pos++;
-      if (pos <= t0) live |= start_same ? start0 : start[ctx];             // a new start position (none beyond the factor occurrence)
-      else if (!live) return 0;
-      cur = nxt; acc_cur = na[i];
+      if (pos <= t0) { for (int w = 0; w < W; w++) live[w] |= start_same ? start0[w] : start[ctx * W + w]; }      // a new start position (none beyond the factor occurrence)
+      else { uint64_t any = 0; for (int w = 0; w < W; w++) any |= live[w]; if (!any) return 0; }
+      cur = nxt;
+      for (int w = 0; w < W; w++) acc_cur[w] = na[i][w];
     }
   }
+}
+CG_HD int bitprog_test(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps = 0xffffffffu) {
+  // (the table's first word is its width W)
+  return bp[0] == 2 ? bitprog_test_w<2>(bp + 1, m, len, s, t0, max_steps) : bitprog_test_w<1>(bp + 1, m, len, s, t0, max_steps);
 }
 
 // one word of a 256-bit set held in eight registers

@@ -915,28 +915,29 @@ bool build_prefilter(const std::vector<CompiledRule>& rules, const PrefilterOpti
 
 // ---------------------------------------------------------------------------------------------------------------
 // bit-parallel form of a Pike program (bitprog.h)
-bool build_bitprog(const CompiledRule& r, uint64_t* out) {      // out: kBitProgWords = 651 words
+bool build_bitprog(const CompiledRule& r, std::vector<uint64_t>* outv) {
   const std::vector<uint32_t>& prog = r.prog;
   if (r.status != RULE_OK || prog.empty()) return false;
   std::vector<int> bit_of(prog.size(), -1); int nc = 0;
+  int lb_set = -1, la_set = -1;                     // the rule's lookbehind / lookahead set (one per direction, ASCII-only)
   for (size_t pc = 0; pc < prog.size(); pc++) {
-    const uint32_t op = prog[pc] & 0xff;
-    if (op == OP_CHAR || op == OP_SET || op == OP_ANY) { if (nc >= 63) return false; bit_of[pc] = nc++; }
-    else if (op == OP_LOOKAHEAD || op == OP_NLOOKAHEAD || op == OP_LOOKBEHIND || op == OP_NLOOKBEHIND) return false;
-  }
-  for (uint32_t i = 0; i < 139 + 8 * 64; i++) out[i] = 0;
-  // accept[b]: the consuming instructions an ASCII byte satisfies
-  for (size_t pc = 0; pc < prog.size(); pc++) {
-    if (bit_of[pc] < 0) continue;
     const uint32_t op = prog[pc] & 0xff, arg = prog[pc] >> 8;
-    for (int b = 0; b < 128; b++) {
-      bool ok = op == OP_CHAR ? (uint32_t)b == arg : op == OP_ANY ? !(b == 0x0a || b == 0x0d) : ((r.sets[arg].ascii[b >> 5] >> (b & 31)) & 1u) != 0;
-      if (ok) out[b] |= 1ull << bit_of[pc];
+    if (op == OP_CHAR || op == OP_SET || op == OP_ANY) { if (nc >= 127) return false; bit_of[pc] = nc++; }
+    else if (op == OP_LOOKAHEAD || op == OP_NLOOKAHEAD || op == OP_LOOKBEHIND || op == OP_NLOOKBEHIND) {
+      if (arg >= r.sets.size() || !r.sets[arg].ranges.empty()) return false;      // a set with non-ASCII members: the byte walk cannot evaluate it
+      int& slot = (op == OP_LOOKBEHIND || op == OP_NLOOKBEHIND) ? lb_set : la_set;
+      if (slot >= 0 && !(r.sets[slot] == r.sets[arg])) return false;
+      if (slot < 0) slot = (int)arg;
     }
   }
-  // closure of the epsilon edges from pc under context ctx (bit 0 word boundary, bit 1 start of message, bit 2 end)
+  const uint32_t W = nc <= 63 ? 1u : 2u, match_bit = 64 * W - 1;
+  struct Mask { uint64_t w[2] = {0, 0}; void set(uint32_t b) { w[b >> 6] |= 1ull << (b & 63); } bool has(uint32_t b) const { return (w[b >> 6] >> (b & 63)) & 1; }
+                bool operator==(const Mask& o) const { return w[0] == o.w[0] && w[1] == o.w[1]; } bool zero() const { return !(w[0] | w[1]); } };
+  const bool has_look = lb_set >= 0 || la_set >= 0;
+  // closure of the epsilon edges from pc under context ctx: bit 0 word boundary, bit 1 start of message, bit 2 end, bit 3 previous
+  // unit in the lookbehind set, bit 4 next unit in the lookahead set
   auto closure = [&](uint32_t pc0, uint32_t ctx) {
-    uint64_t m = 0; std::vector<char> seen(prog.size(), 0); std::vector<uint32_t> st{pc0};
+    Mask m; std::vector<char> seen(prog.size(), 0); std::vector<uint32_t> st{pc0};
     while (!st.empty()) {
       uint32_t pc = st.back(); st.pop_back();
       if (pc >= prog.size() || seen[pc]) continue;
@@ -950,39 +951,58 @@ bool build_bitprog(const CompiledRule& r, uint64_t* out) {      // out: kBitProg
         case OP_EOL: if (ctx & 4u) st.push_back(pc + 1); break;
         case OP_WORDB: if (ctx & 1u) st.push_back(pc + 1); break;
         case OP_NWORDB: if (!(ctx & 1u)) st.push_back(pc + 1); break;
-        case OP_MATCH: m |= 1ull << 63; break;
-        default: m |= 1ull << bit_of[pc]; break;
+        case OP_LOOKBEHIND: if (ctx & 8u) st.push_back(pc + 1); break;
+        case OP_NLOOKBEHIND: if (!(ctx & 8u)) st.push_back(pc + 1); break;
+        case OP_LOOKAHEAD: if (ctx & 16u) st.push_back(pc + 1); break;
+        case OP_NLOOKAHEAD: if (!(ctx & 16u)) st.push_back(pc + 1); break;
+        case OP_MATCH: m.set(match_bit); break;
+        default: m.set((uint32_t)bit_of[pc]); break;
       }
     }
     return m;
   };
-  // layout (bitprog.h): accept[128] | start[8] | header | rows[n][64]; contexts with identical follow rows share one
-  uint64_t rows[8][64]; uint32_t n_rows = 0; uint64_t header = 0;
-  for (uint32_t ctx = 0; ctx < 8; ctx++) {
-    uint64_t row[64] = {0};
+  // layout: bitprog.h
+  std::vector<uint64_t>& out = *outv;
+  const uint32_t n_ctx = 32, meta_off = 1 + (128 + n_ctx) * W, rows_off = meta_off + 7 + 2 * W;
+  out.assign(rows_off, 0);
+  out[0] = W;
+  for (size_t pc = 0; pc < prog.size(); pc++) {
+    if (bit_of[pc] < 0) continue;
+    const uint32_t op = prog[pc] & 0xff, arg = prog[pc] >> 8, k = (uint32_t)bit_of[pc];
+    for (int b = 0; b < 128; b++) {
+      bool ok = op == OP_CHAR ? (uint32_t)b == arg : op == OP_ANY ? !(b == 0x0a || b == 0x0d) : ((r.sets[arg].ascii[b >> 5] >> (b & 31)) & 1u) != 0;
+      if (ok) out[1 + (size_t)b * W + (k >> 6)] |= 1ull << (k & 63);
+    }
+  }
+  std::vector<std::vector<Mask>> rows; uint64_t rowmap[2] = {0, 0};
+  bool start_same = true; Mask start_first;
+  for (uint32_t ctx = 0; ctx < n_ctx; ctx++) {
+    std::vector<Mask> row(64 * W);
     for (size_t pc = 0; pc < prog.size(); pc++) if (bit_of[pc] >= 0) row[bit_of[pc]] = closure((uint32_t)pc + 1, ctx);
-    out[128 + ctx] = closure(0, ctx);
-    uint32_t r = 0;
-    while (r < n_rows && memcmp(rows[r], row, sizeof row) != 0) r++;
-    if (r == n_rows) { memcpy(rows[n_rows], row, sizeof row); n_rows++; }
-    header |= (uint64_t)r << (4 * ctx);
+    const Mask st = closure(0, ctx);
+    for (uint32_t w = 0; w < W; w++) out[1 + (128 + ctx) * W + w] = st.w[w];
+    if (ctx == 0) start_first = st; else start_same = start_same && st == start_first;
+    uint32_t ri = 0;
+    while (ri < rows.size() && !(rows[ri] == row)) ri++;
+    if (ri == rows.size()) { if (rows.size() >= 15) return false; rows.push_back(row); }
+    rowmap[ctx >> 4] |= (uint64_t)ri << (4 * (ctx & 15));
   }
-  header |= (uint64_t)n_rows << 32;
-  bool start_same = true; for (uint32_t ctx = 1; ctx < 8; ctx++) start_same = start_same && out[128 + ctx] == out[128];
-  if (start_same) header |= 1ull << 40;
-  out[136] = header;
-  // instructions whose successors are {k + 1} and / or {k} in every row: a shift and a mask instead of a table row (bitprog.h)
-  uint64_t m_next = 0, m_self = 0;
+  const uint32_t n_rows = (uint32_t)rows.size();
+  out[meta_off] = n_rows | ((uint64_t)W << 4) | (start_same ? 1ull << 8 : 0) | (has_look ? 1ull << 9 : 0);
+  out[meta_off + 1] = rowmap[0]; out[meta_off + 2] = rowmap[1];
+  auto set128 = [&](int sid, uint64_t* o) { o[0] = o[1] = 0; if (sid >= 0) { o[0] = (uint64_t)r.sets[sid].ascii[0] | ((uint64_t)r.sets[sid].ascii[1] << 32); o[1] = (uint64_t)r.sets[sid].ascii[2] | ((uint64_t)r.sets[sid].ascii[3] << 32); } };
+  set128(lb_set, &out[meta_off + 3]); set128(la_set, &out[meta_off + 5]);
+  // instructions whose successors are {k + 1} and / or {k} in every row: a shift and a mask instead of a table row
   for (int k = 0; k < nc; k++) {
-    const uint64_t f = rows[0][k], allowed = (1ull << k) | (1ull << (k + 1));
-    bool simple = (f & ~allowed) == 0;
-    for (uint32_t r = 1; r < n_rows && simple; r++) simple = rows[r][k] == f;
+    const Mask f = rows[0][k];
+    Mask rest = f; rest.w[k >> 6] &= ~(1ull << (k & 63)); rest.w[(k + 1) >> 6] &= ~(1ull << ((k + 1) & 63));
+    bool simple = rest.zero();
+    for (uint32_t ri = 1; ri < n_rows && simple; ri++) simple = rows[ri][k] == f;
     if (!simple) continue;
-    if (f & (1ull << (k + 1))) m_next |= 1ull << k;
-    if (f & (1ull << k)) m_self |= 1ull << k;
+    if (f.has(k + 1)) out[meta_off + 7 + (k >> 6)] |= 1ull << (k & 63);
+    if (f.has(k)) out[meta_off + 7 + W + (k >> 6)] |= 1ull << (k & 63);
   }
-  out[137] = m_next; out[138] = m_self;
-  for (uint32_t r = 0; r < n_rows; r++) memcpy(out + 139 + r * 64, rows[r], sizeof rows[r]);
+  for (uint32_t ri = 0; ri < n_rows; ri++) for (uint32_t k = 0; k < 64 * W; k++) for (uint32_t w = 0; w < W; w++) out.push_back(rows[ri][k].w[w]);
   return true;
 }
 

@@ -79,9 +79,9 @@ struct CompiledRule {
 // flags: bit0 = ignoreCase ("i").  `src` is the JS pattern source encoded as UTF-8.
 CompiledRule compile_rule(const char* src, size_t len, uint32_t flags);
 
-// Bit-parallel form of a rule's Pike program (bitprog.h): accept[128] | start[8] | header | next | self | follow rows, 651 uint64 words at most.
-// false when the program has more than 63 consuming instructions or uses lookaround: such rules stay with the Pike VM.
-bool build_bitprog(const CompiledRule& r, uint64_t* out651);
+// Bit-parallel form of a rule's Pike program (layout: bitprog.h).  false when the program has more than 127 consuming
+// instructions, lookaround over sets with non-ASCII members or more than one set per direction: such rules stay with the Pike VM.
+bool build_bitprog(const CompiledRule& r, std::vector<uint64_t>* out);
 
 // ---- prefilter: a stateless two-level filter over every rule's *necessary factors* (byte-set sequences every
 // match must contain; <= kMaxFactorElems elements are kept per factor).

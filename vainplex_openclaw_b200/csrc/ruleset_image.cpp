@@ -36,11 +36,8 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   H.prog_off[n] = (uint32_t)H.prog.size();
   H.bit_off.assign(std::max<uint32_t>(n, 1), 0xffffffffu);
   for (uint32_t i = 0; i < n; i++) {
-    uint64_t bp[651];
-    if (H.rules[i].status == RULE_OK && build_bitprog(H.rules[i], bp)) {       // (only the rows in use are kept)
-      const uint32_t used = 139 + 64 * (uint32_t)((bp[136] >> 32) & 15u);
-      H.bit_off[i] = (uint32_t)H.bit_words.size(); H.bit_words.insert(H.bit_words.end(), bp, bp + used);
-    }
+    std::vector<uint64_t> bp;
+    if (H.rules[i].status == RULE_OK && build_bitprog(H.rules[i], &bp)) { H.bit_off[i] = (uint32_t)H.bit_words.size(); H.bit_words.insert(H.bit_words.end(), bp.begin(), bp.end()); }
   }
   H.n_sets = (uint32_t)(H.sets.size() / 6);
 

@@ -649,7 +649,7 @@ confirm_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ Sc
   if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 resolve_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, int want_spans, uint32_t spread) {
   const uint32_t n1 = min(w.counters[4], w.l1_cap);
   const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -712,6 +712,7 @@ __global__ void __launch_bounds__(kVerifyBlock, kVerifyCtasPerSm)
 verify_small_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off) {
   extern __shared__ __align__(16) uint8_t vsm[];
   const uint32_t n_events = min(w.counters[1], w.event_cap);
+  if (n_events == 0) return;                    // (the island matcher decided everything: the common case)
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // One run per warp.  All 32 lanes execute it redundantly -- identical registers, uniform control flow, the VM
   // state in shared memory written with identical values -- so that the lanes can split the work wherever a step
