@@ -679,3 +679,34 @@ def test_random_regex_differential_on_the_kernels(N, oracle):
     got = [(int(s["msg"]), int(s["rule"]), int(s["start16"]), int(s["end16"])) for s in spans]
     assert got == oracle_spans(oracle, rules, data, off)
     rs.close()
+
+
+def test_single_message_path_equals_the_batch_path(N, oracle):
+    """cg_scan_one (pinned staging + the step as one graph over fixed addresses) against cg_scan_batch and the oracle:
+    lengths around every boundary of the fast path (0, one chunk, 16 KB, beyond -> general path), non-ASCII text,
+    interleaved with batch calls that grow the scratch (the graph must be re-captured), 160 rules (five hit words)."""
+    rl = W.make_rules(160)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    rng = np.random.default_rng(5)
+    samples = [r["sample"].encode() for r in rl if r["sample"]]
+    msgs = [b"", b"a", b"x" * 15, b"y" * 16, b"z" * 17]
+    for L in (255, 256, 1000, 4096, 16383, 16384, 16385, 40000):
+        body = bytes(rng.integers(97, 123, L, dtype=np.uint8))
+        s = samples[int(rng.integers(0, len(samples)))]
+        p = int(rng.integers(0, max(1, L - len(s))))
+        msgs.append(body[:p] + s + body[p + len(s):] if L > len(s) + 2 else body)
+    msgs += [("пароль sk-" + "a" * 24 + " ключ bob@example.com 4111 1111 1111 1111").encode(), samples[0] + b" " + samples[1], samples[2]]
+    data, off = N.pack(msgs)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert np.array_equal(words, ewords) and [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits
+    for rep in range(2):
+        for i, m in enumerate(msgs):
+            w1, r1 = rs.scan_one(m)
+            assert w1 == int(words[i]), (i, len(m))
+            assert r1 == [r for (mm, r) in ehits if mm == i], (i, len(m))
+        # a batch large enough to grow the scratch in between: the single-message graph is re-captured
+        big, boff, _ = W.make_messages(200000 if rep == 0 else 1000, 64, rl, p_hit=0.05, seed=11)
+        rs.scan_batch(big.numpy(), boff.numpy().astype(np.uint32))
+    rs.close()

@@ -100,11 +100,17 @@ struct cg_ruleset {
   uint32_t sticky_flags = 0;      // error flags of batches since the last cg_scan_join
   uint32_t last_counters[kCounterWords] = {};
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
-  struct CachedGraph { cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint64_t caps[4] = {0, 0, 0, 0}; uint64_t used = 0; };
+  struct CachedGraph { int kernels = 0; cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint64_t caps[4] = {0, 0, 0, 0}; uint64_t used = 0; };
+  // cg_scan_one: pinned staging + one device block ([offsets][message bytes] in, [word][counters][hit row] out) and the
+  // step as a graph over those fixed addresses (the message length is data, so one graph serves every message)
+  struct OnePath { cudaGraphExec_t exec = nullptr; uint8_t* h_pin = nullptr; uint8_t* d_buf = nullptr; uint64_t caps[4] = {0, 0, 0, 0}; int kernels = 0; } one;
   CachedGraph graphs[2];          // two entries: callers that alternate between two input/output buffer sets replay, never re-capture
   uint64_t graph_clock = 0;
   ~cg_ruleset() {
     for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (one.exec) cudaGraphExecDestroy(one.exec);
+    if (one.h_pin) cudaFreeHost(one.h_pin);
+    cudaFree(one.d_buf);
     if (h_counters) cudaFreeHost(h_counters);
     for (auto& e : e_cnt) if (e) cudaEventDestroy(e);
     for (void* p : allocs) cudaFree(p);
@@ -557,7 +563,67 @@ int cg_scan_batch(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets,
   return CG_OK;
 }
 
+namespace {
+constexpr uint32_t kOneBytes = 16384, kOneRw = 128, kOneIn = 256 + kOneBytes + 64, kOneOut = (2 + kCounterWords + kOneRw) * 4;
+// -> CG_OK, an error, or 1 = take the general path (long message, large rule set, a queue overflowed)
+int scan_one_fast(cg_ruleset* rs, const uint8_t* bytes, uint32_t len, uint64_t* out_word, uint32_t* out_rules, uint32_t rules_cap, uint32_t* out_nrules) {
+  static const bool off_ = getenv("CG_ONE_FAST") && atoi(getenv("CG_ONE_FAST")) == 0;
+  if (off_ || !G.ready || !rs || (len && !bytes) || len > kOneBytes || rs->dev.rw > kOneRw - 2 || G.profiling) return 1;
+  cg_ruleset::OnePath& o = rs->one;
+  cudaStream_t st = G.stream;
+  int rc;
+  if (!o.h_pin) { CU(cudaMallocHost((void**)&o.h_pin, kOneIn + kOneOut)); memset(o.h_pin, 0, kOneIn + kOneOut); CU(cudaMalloc((void**)&o.d_buf, kOneIn + kOneOut)); CU(cudaMemset(o.d_buf, 0, kOneIn + kOneOut)); }
+  ScanWork& w = rs->work;
+  uint32_t l1, slot, ev; default_caps(rs, 1, &l1, &slot, &ev);
+  if (!w.counters || !w.msg_cap || l1 > w.l1_cap || slot > w.slot_cap || ev > w.event_cap || !w.spans) {
+    CU(cudaStreamSynchronize(st));
+    for (auto& g : rs->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if ((rc = ensure_work(rs, w, 1, l1, slot, ev, 1))) return rc;
+  }
+  const uint64_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
+  const uint8_t* d_bytes = o.d_buf; const uint32_t* d_off = reinterpret_cast<const uint32_t*>(o.d_buf);
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(o.d_buf + kOneIn); uint64_t* d_word = reinterpret_cast<uint64_t*>(o.d_buf + kOneIn + kOneOut - 8);   // (the word lands behind the hit row, then is packed to the front)
+  if (!o.exec || memcmp(caps, o.caps, sizeof caps)) {
+    if (o.exec) { cudaGraphExecDestroy(o.exec); o.exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    const uint64_t before = G.launches;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = run_scan_device(rs, d_bytes, d_off, 1, d_word, false, st);
+    if (rc == CG_OK) { const int k = launch_pack_one(rs->dev, w, d_word, d_out, kOneRw - 2, st); G.launches += k; }
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    o.kernels = (int)(G.launches - before); G.stats.kernel_launches -= o.kernels - 1; G.launches = before;
+    if (rc != CG_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc != CG_OK ? rc : cuda_fail(e, "cudaStreamEndCapture"); }
+    e = cudaGraphInstantiate(&o.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { o.exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
+    memcpy(o.caps, caps, sizeof caps);
+  }
+  uint32_t* hoff = reinterpret_cast<uint32_t*>(o.h_pin); hoff[0] = 256; hoff[1] = 256 + len;
+  if (len) memcpy(o.h_pin + 256, bytes, len);
+  memset(o.h_pin + 256 + len, 0, 64);
+  CU(cudaMemcpyAsync(o.d_buf, o.h_pin, 256 + (size_t)len + 64, cudaMemcpyHostToDevice, st));
+  CU(cudaGraphLaunch(o.exec, st));
+  CU(cudaMemcpyAsync(o.h_pin + kOneIn, d_out, (2 + kCounterWords + rs->dev.rw) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  G.launches += o.kernels; G.stats.kernel_launches += o.kernels;
+  const uint32_t* ho = reinterpret_cast<const uint32_t*>(o.h_pin + kOneIn);
+  const uint32_t* hc = ho + 2;
+  memcpy(rs->last_counters, hc, sizeof rs->last_counters);
+  if (hc[3] & (ERR_VM_STACK | ERR_VM_LIST)) return fail(CG_ERR_TOO_LARGE, "matcher thread list / stack overflow on device");
+  if (hc[3]) { learn_caps(rs, hc); return 1; }                    // a queue overflowed: the general path retries with larger scratch
+  G.stats.messages_scanned += 1; G.stats.bytes_scanned += len; G.stats.candidate_events += hc[1]; G.stats.verified_pairs += hc[1];
+  if (out_word) *out_word = (uint64_t)ho[0] | ((uint64_t)ho[1] << 32);
+  uint32_t nh = 0;
+  for (uint32_t k = 0; k < rs->dev.rw; k++) { uint32_t v = ho[2 + kCounterWords + k]; while (v) { const uint32_t b = (uint32_t)__builtin_ctz(v); v &= v - 1; if (out_rules && nh < rules_cap) out_rules[nh] = k * 32 + b; nh++; } }
+  if (out_nrules) *out_nrules = nh;
+  G.stats.hits += nh;
+  if (out_rules && nh > rules_cap) return fail(CG_ERR_CAPACITY, "out_rules too small");
+  return CG_OK;
+}
+}  // namespace
+
 int cg_scan_one(cg_ruleset* rs, const uint8_t* bytes, uint32_t len, uint64_t* out_word, uint32_t* out_rules, uint32_t rules_cap, uint32_t* out_nrules) {
+  { std::lock_guard<std::mutex> lk(g_mu); const int frc = scan_one_fast(rs, bytes, len, out_word, out_rules, rules_cap, out_nrules); if (frc != 1) return frc; }
   uint32_t off[2] = {0, len};
   std::vector<cg_hit> hits(rules_cap ? rules_cap : 1);
   uint32_t nh = 0; uint64_t word = 0;
@@ -746,6 +812,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
       CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
       cudaError_t e = cudaStreamEndCapture(st, &g);
+      hit->kernels = (int)(G.launches - launches_before);
       G.stats.kernel_launches -= G.launches - launches_before; G.launches = launches_before;      // counted per replay below
       if (rc != CG_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc != CG_OK ? rc : cuda_fail(e, "cudaStreamEndCapture"); }
       e = cudaGraphInstantiate(&hit->exec, g, 0);
@@ -755,8 +822,7 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     }
     hit->used = ++rs->graph_clock;
     CU(cudaGraphLaunch(hit->exec, st));
-    const uint32_t pieces = scan_pieces();
-    const int kk = 3 * (int)pieces + 3 + (rs->dev.max_prog_len > 192 ? 1 : 0);       // kernels inside the graph: (scan, lookup, check) per piece, resolve, verify (+ large-VM), finalize
+    const int kk = hit->kernels;                 // kernels inside the graph (counted while it was captured)
     G.launches += kk; G.stats.kernel_launches += kk;
   }
   if (rc == CG_OK) {

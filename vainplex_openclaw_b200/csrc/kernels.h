@@ -98,6 +98,9 @@ int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, 
 // start of a step: counters = 0, slot_of_msg = none, candidate / hit rows of the slots the previous step used = 0
 int launch_reset(const DevRuleset& rs, const ScanWork& w, uint32_t n, int sm_count, cudaStream_t stream);
 
+// single-message path: result word, counters and the message's hit row packed into one block (one D2H copy)
+int launch_pack_one(const DevRuleset& rs, const ScanWork& w, const uint64_t* d_word, uint32_t* d_out, uint32_t rw_cap, cudaStream_t stream);
+
 // raises the dynamic shared-memory limits of every kernel once (not legal inside stream capture)
 void prepare_scan_kernels();
 

@@ -932,6 +932,19 @@ int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdict
   return 1;
 }
 
+// cg_scan_one: out = [word lo, word hi][counters x 32][hit row of the message, rw words]
+__global__ void pack_one_kernel(DevRuleset rs, ScanWork w, const uint64_t* __restrict__ word, uint32_t* __restrict__ out, uint32_t rw_cap) {
+  const uint32_t t = threadIdx.x;
+  if (t == 0) { out[0] = (uint32_t)word[0]; out[1] = (uint32_t)(word[0] >> 32); }
+  if (t < kCounterWords) out[2 + t] = w.counters[t];
+  const uint32_t s = w.slot_of_msg[0];
+  for (uint32_t k = t; k < rs.rw && k < rw_cap; k += blockDim.x) out[2 + kCounterWords + k] = (s != 0xffffffffu && s < w.slot_cap) ? w.hit[(size_t)s * rs.rw + k] : 0u;
+}
+int launch_pack_one(const DevRuleset& rs, const ScanWork& w, const uint64_t* d_word, uint32_t* d_out, uint32_t rw_cap, cudaStream_t stream) {
+  pack_one_kernel<<<1, 64, 0, stream>>>(rs, w, d_word, d_out, rw_cap);
+  return 1;
+}
+
 int launch_reset(const DevRuleset& rs, const ScanWork& w, uint32_t n, int sm_count, cudaStream_t stream) {
   reset_kernel<<<sm_count * 4, 256, 0, stream>>>(rs, w, n);
   return 1;
