@@ -62,7 +62,7 @@ void* harness_create(const char** srcs, const uint32_t* lens, const uint32_t* fl
   d.always_rules = H.pf.always_rules.data(); d.n_always = n_always;
   d.prog = H.prog.data(); d.rule_prog_off = H.prog_off.data(); d.sets = H.sets.data(); d.set_ranges = H.ranges.data();
   H.alpha.resize(H.alpha.size() + 8, 0);
-  d.rule_first = H.first.data(); d.rule_alpha = H.alpha.data(); d.bit_words = reinterpret_cast<const unsigned long long*>(H.bit_words.data()); d.bit_off = H.bit_off.data(); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
+  d.rule_first = H.first.data(); d.rule_alpha = H.alpha.data(); d.bit_words = reinterpret_cast<const unsigned long long*>(H.bit_words.data()); d.bit_off = H.bit_off.data(); d.factor_skip = reinterpret_cast<const unsigned long long*>(H.factor_skip.data()); d.n_rules = n; d.rw = (n + 31) / 32; if (!d.rw) d.rw = 1;
   h->T = GramTables{d.bucket_start, d.entries, d.factors, d.bytesets};
   return h;
 }
@@ -107,8 +107,8 @@ int harness_test(void* p, uint32_t rule, const uint8_t* m, uint32_t len) {
 // of a batch; seeded filler here): bitmaps (rw words each) of queued candidates and of direct hits
 struct BitSink {
   uint32_t* cand; uint32_t* direct_;
-  std::vector<uint32_t>* occ;   // (rule, t0, pre) triples of confirmed occurrences
-  void candidate(uint32_t r, uint32_t t0 = 0xffffffffu, uint32_t pre = 0xffffffffu) { cand[r >> 5] |= 1u << (r & 31); if (occ) { occ->push_back(r); occ->push_back(t0); occ->push_back(pre); } }
+  std::vector<uint32_t>* occ;   // (rule, t0, pre, factor) of confirmed occurrences
+  void candidate(uint32_t r, uint32_t t0 = 0xffffffffu, uint32_t pre = 0xffffffffu, uint32_t f = 0xffffffffu) { cand[r >> 5] |= 1u << (r & 31); if (occ) { occ->push_back(r); occ->push_back(t0); occ->push_back(pre); occ->push_back(f); } }
   void direct(uint32_t r) { direct_[r >> 5] |= 1u << (r & 31); }
 };
 struct OccEmit {
@@ -163,13 +163,13 @@ void harness_policy_hits(void* p, const uint8_t* m, uint32_t len, uint32_t* hits
   scan_message(h, m, len, lead, seed, false, sink, nullptr);
   VM vm(d);
   struct Null { void span(uint32_t, uint32_t, uint32_t, uint32_t) {} } ns;
-  for (size_t k = 0; k + 2 < occ.size(); k += 3) {
+  for (size_t k = 0; k + 3 < occ.size(); k += 4) {
     uint32_t r = occ[k], t0 = occ[k + 1], pre = occ[k + 2];
     if ((hits[r >> 5] >> (r & 31)) & 1u) continue;
     bool any = t0 == 0xffffffffu ? run_rule<false>(vm, d, r, m, len, ns) : test_at_factor(vm, d, r, m, len, t0, pre);
     // the bit-parallel matcher (what resolve_kernel runs for eligible rules) must say the same whenever it says anything
     if (t0 != 0xffffffffu && d.bit_off[r] != kBitProgNone) {
-      const int res = bitprog_test(reinterpret_cast<const uint64_t*>(d.bit_words) + d.bit_off[r], m, len, island_start(d, r, m, len, t0, pre), t0);
+      const int res = island_test(d, occ[k + 3], r, m, len, t0, pre, 0xffffffffu);
       if (res >= 0) { g_bit_decided++; g_bit_rule[r & 8191]++; if ((res == 1) != any) g_bit_mismatch++; } else { g_bit_fallback++; g_vm_rule[r & 8191]++; }
     } else g_vm_rule[r & 8191]++;
     if (any) hits[r >> 5] |= 1u << (r & 31);
@@ -210,7 +210,7 @@ void harness_policy_hits_batch(void* p, const uint8_t* buf, const uint32_t* off,
     std::vector<uint32_t> one;
     BitSink sink{cand.data(), hm, &one};
     factor_confirmed(d, o.second, o.first - off[msg], false, sink);
-    for (size_t k = 0; k + 2 < one.size(); k += 3) {
+    for (size_t k = 0; k + 3 < one.size(); k += 4) {
       const uint32_t r = one[k];
       if ((hm[r >> 5] >> (r & 31)) & 1u) continue;
       if (test_at_factor(vm, d, r, buf + off[msg], off[msg + 1] - off[msg], one[k + 1], one[k + 2])) hm[r >> 5] |= 1u << (r & 31);
@@ -280,7 +280,7 @@ extern "C" void harness_vm_stats(void* p, const uint8_t* data, uint64_t n_msgs, 
     std::vector<uint32_t> cand(d.rw, 0), hits(d.rw, 0), occ;
     BitSink sink{cand.data(), hits.data(), &occ};
     scan_message(h, m, len, 16, 1, false, sink, nullptr);
-    for (size_t k = 0; k + 2 < occ.size(); k += 3) {
+    for (size_t k = 0; k + 3 < occ.size(); k += 4) {
       uint32_t r = occ[k], t0 = occ[k + 1], pre = occ[k + 2];
       if ((hits[r >> 5] >> (r & 31)) & 1u) continue;
       if (t0 == 0xffffffffu) continue;

@@ -46,8 +46,10 @@ CG_HD uint32_t bitprog_in128(uint64_t lo, uint64_t hi, int u) { return u < 0 || 
 // One thread walks the island, so what this costs is the length of its dependency chain, not its instruction count: the
 // four next bytes and their accept masks are fetched together (loads that depend on the position alone), and only the
 // state update is sequential -- a shift and a mask for most instructions, a follow row from L2 for the others.
+// resume != nullptr: the walk starts at s with the given state and no further start positions (the compiler has already run the
+// rule's program over the confirmed factor, whose elements the instructions accept as a whole or not at all: factor_skip below)
 template <int W>
-CG_HD int bitprog_test_w(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps) {
+CG_HD int bitprog_test_w(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps, const uint64_t* __restrict__ resume = nullptr) {
   const uint64_t* accept = bp; const uint64_t* start = bp + 128 * W; const uint64_t* hd = bp + bitprog_meta_off(W); const uint64_t* rows = bp + bitprog_rows_off(W);
   const uint64_t meta = hd[0], map0 = hd[1], map1 = hd[2];
   const bool start_same = (meta >> 8) & 1u, has_look = (meta >> 9) & 1u, one_row = (meta & 15u) == 1u;
@@ -58,7 +60,8 @@ CG_HD int bitprog_test_w(const uint64_t* __restrict__ bp, const uint8_t* __restr
   int prev = s > 0 ? (m[s - 1] < 0x80 ? (int)m[s - 1] : 0x80) : -1;          // (a unit >= 0x80 is not a word character, whatever it is)
   int cur = s < len ? (int)m[s] : -1;
   uint32_t ctx = bitprog_ctx(prev, cur, s == 0) | (has_look ? bitprog_in128(lb0, lb1, prev) << 3 | bitprog_in128(la0, la1, cur) << 4 : 0u);
-  for (int w = 0; w < W; w++) { start0[w] = start[ctx * W + w]; live[w] = start0[w]; acc_cur[w] = cur >= 0 && cur < 0x80 ? accept[cur * W + w] : 0; }
+  for (int w = 0; w < W; w++) { start0[w] = resume ? 0 : start[ctx * W + w]; live[w] = resume ? resume[w] : start0[w]; acc_cur[w] = cur >= 0 && cur < 0x80 ? accept[cur * W + w] : 0; }
+  if (resume) t0 = s - 1;                        // (s >= 1: at least one factor element lies before it)
   for (uint32_t pos = s;;) {
     // the block's four "next" bytes and their accept masks
     int nb[4]; uint64_t na[4][W];
@@ -110,9 +113,9 @@ CG_HD int bitprog_test_w(const uint64_t* __restrict__ bp, const uint8_t* __restr
     }
   }
 }
-CG_HD int bitprog_test(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps = 0xffffffffu) {
+CG_HD int bitprog_test(const uint64_t* __restrict__ bp, const uint8_t* __restrict__ m, uint32_t len, uint32_t s, uint32_t t0, uint32_t max_steps = 0xffffffffu, const uint64_t* __restrict__ resume = nullptr) {
   // (the table's first word is its width W)
-  return bp[0] == 2 ? bitprog_test_w<2>(bp + 1, m, len, s, t0, max_steps) : bitprog_test_w<1>(bp + 1, m, len, s, t0, max_steps);
+  return bp[0] == 2 ? bitprog_test_w<2>(bp + 1, m, len, s, t0, max_steps, resume) : bitprog_test_w<1>(bp + 1, m, len, s, t0, max_steps, resume);
 }
 
 // one word of a 256-bit set held in eight registers
@@ -152,6 +155,27 @@ CG_HD uint32_t island_start(const DevRuleset& rs, uint32_t rule, const uint8_t* 
       s--;
     }
   }
+}
+
+
+// RegExp.test around the occurrence of factor f of rule r at message offset t0: 1 / 0 / -1 (ask the VM).
+// factor_skip[3 f] = L | state words: for a factor that starts its rule's matches (no pattern unit before it, no assertion in
+// the rule) the compiler has run the program over the first L factor elements -- every live instruction accepts an element's
+// whole byte set or none of it, so the state after them does not depend on the text -- and check_kernel has compared those
+// very elements exactly: the walk resumes behind them.  A `sk-...` token costs 4 steps instead of 20.
+CG_HD int island_test(const DevRuleset& rs, uint32_t f, uint32_t r, const uint8_t* __restrict__ m, uint32_t len, uint32_t t0, uint32_t pre, uint32_t max_steps) {
+  const uint64_t* bp = reinterpret_cast<const uint64_t*>(rs.bit_words) + rs.bit_off[r];
+  const uint64_t* resume = nullptr; uint32_t s = 0;
+  if (f != 0xffffffffu && rs.factor_skip) {
+    const uint64_t* sk = reinterpret_cast<const uint64_t*>(rs.factor_skip) + (size_t)f * 3;
+    const uint32_t L = (uint32_t)sk[0];
+    if (L && t0 + L <= len) { resume = sk + 1; s = t0 + L; }
+  }
+  if (!resume) {
+    s = island_start(rs, r, m, len, t0, pre, max_steps);
+    if (max_steps != 0xffffffffu && (t0 < len ? t0 : len) - s >= max_steps) return -1;
+  }
+  return bitprog_test(bp, m, len, s, t0, max_steps, resume);
 }
 
 }  // namespace cg

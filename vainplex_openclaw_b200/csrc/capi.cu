@@ -491,6 +491,7 @@ int cg_ruleset_create(const cg_rule* rules, uint32_t n_rules, uint32_t options, 
   if ((rc = upload(rs.get(), H.alpha, &d.rule_alpha, 8))) return rc;
   { const uint64_t* bw = nullptr; if ((rc = upload(rs.get(), H.bit_words, &bw, 8))) return rc; d.bit_words = reinterpret_cast<const unsigned long long*>(bw); }
   if ((rc = upload(rs.get(), H.bit_off, &d.bit_off))) return rc;
+  { const uint64_t* fs = nullptr; if ((rc = upload(rs.get(), H.factor_skip, &fs, 8))) return rc; d.factor_skip = getenv("CG_NO_SKIP") ? nullptr : reinterpret_cast<const unsigned long long*>(fs); }
   if (getenv("CG_NO_BITPROG")) d.bit_words = nullptr;
   d.rule_policy = nullptr; d.rule_action = nullptr;
   d.n_rules = n_rules; d.rw = (n_rules + 31) / 32; if (d.rw == 0) d.rw = 1;

@@ -165,7 +165,7 @@ CG_HD uint32_t message_of(const uint32_t* __restrict__ off, uint32_t n, uint32_t
 template <class Sink>
 CG_HD void factor_confirmed(const DevRuleset& rs, uint32_t f, uint32_t t0, bool want_spans, Sink& sink) {
   const uint32_t* fw = rs.factors + (size_t)f * 12;
-  if ((fw[1] >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0], t0, fw[10] | (fw[11] << 16));   // max prefix units | prefix-alphabet set id << 16
+  if ((fw[1] >> 24) && !want_spans) sink.direct(fw[0]); else sink.candidate(fw[0], t0, fw[10] | (fw[11] << 16), f);   // max prefix units | prefix-alphabet set id << 16
 }
 
 }  // namespace cg

@@ -44,6 +44,7 @@ struct DevRuleset {
   const uint32_t* sets;          // 6 words per unit set: ascii[4], range_off, n_ranges
   const uint16_t* set_ranges;    // inclusive lo,hi pairs
   const unsigned long long* bit_words; const uint32_t* bit_off;   // bitprog.h: 139 + 64 x rows words per eligible rule, bit_off[rule] = first word or 0xffffffff
+  const unsigned long long* factor_skip;   // 3 words per factor: elements the island matcher may skip | its state behind them (bitprog.h: island_test); nullptr = none
   const uint32_t* rule_first;    // 8 words per rule: first-byte bitmap
   const uint32_t* rule_alpha;    // 8 words per rule: alphabet bitmap (bytes a match can contain)
   // verdict aggregation (policy-evaluator.ts:44-146, messageContains slice): per rule its policy (index in priority order,

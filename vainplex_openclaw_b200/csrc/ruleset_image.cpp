@@ -51,6 +51,35 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
     for (int k = 0; k < kMaxFactorElems; k += 2) H.factor_words.push_back((uint32_t)f.elem[k] | ((uint32_t)f.elem[k + 1] << 16));
     H.factor_words.push_back(f.pre); H.factor_words.push_back(f.pre_alpha);
   }
+  // ---- what the island matcher may skip (bitprog.h: island_test): the rule's bit-parallel program run over the factor's own
+  // elements, for factors that start the match in rules without assertions (one follow row, one start state)
+  H.factor_skip.assign(3 * P.factors.size(), 0);
+  for (size_t f = 0; f < P.factors.size(); f++) {
+    const FullFactor& ff = P.factors[f];
+    if (ff.pre != 0 || ff.exact || H.bit_off[ff.rule] == 0xffffffffu) continue;
+    const uint64_t* bp = H.bit_words.data() + H.bit_off[ff.rule];
+    const uint32_t W = (uint32_t)bp[0]; const uint64_t* t = bp + 1;
+    const uint64_t meta = t[(128 + 32) * W];
+    if ((meta & 15u) != 1u || !((meta >> 8) & 1u) || ((meta >> 9) & 1u)) continue;          // assertions / lookaround: the state depends on the text
+    const uint64_t* rows = t + (128 + 32) * W + 7 + 2 * W;
+    uint64_t live[2] = {t[128 * W], W == 2 ? t[128 * W + 1] : 0};
+    uint32_t L = 0; uint64_t keep[2] = {0, 0};
+    for (uint32_t k = 0; k < ff.len; k++) {
+      const uint32_t* bs = P.bytesets.data() + (size_t)ff.elem[k] * 8;
+      if (bs[4] | bs[5] | bs[6] | bs[7]) break;                                                // bytes >= 0x80: units, not bytes
+      if (!(bs[0] | bs[1] | bs[2] | bs[3])) break;
+      uint64_t all[2] = {~0ull, ~0ull}, some[2] = {0, 0};
+      for (int b = 0; b < 128; b++) if ((bs[b >> 5] >> (b & 31)) & 1u) for (uint32_t w = 0; w < W; w++) { all[w] &= t[(size_t)b * W + w]; some[w] |= t[(size_t)b * W + w]; }
+      bool ambiguous = false; uint64_t hit[2] = {0, 0};
+      for (uint32_t w = 0; w < W; w++) { const uint64_t lw = w == W - 1 ? live[w] & ~(1ull << 63) : live[w]; hit[w] = lw & all[w]; if (lw & some[w] & ~all[w]) ambiguous = true; }
+      if (ambiguous) break;
+      uint64_t nl[2] = {0, 0};
+      for (uint32_t w = 0; w < W; w++) for (uint64_t hw = hit[w]; hw; hw &= hw - 1) { const int j = __builtin_ctzll(hw); for (uint32_t v = 0; v < W; v++) nl[v] |= rows[(size_t)(w * 64 + j) * W + v]; }
+      live[0] = nl[0]; live[1] = nl[1]; L = k + 1; keep[0] = live[0]; keep[1] = live[1];
+      if (!(live[0] | live[1])) break;
+    }
+    H.factor_skip[3 * f] = L; H.factor_skip[3 * f + 1] = keep[0]; H.factor_skip[3 * f + 2] = keep[1];
+  }
   // ---- level-1b hash table: entries sorted by bucket
   uint32_t nb = 16; while (nb < P.entries.size() * 2) nb *= 2;      // sparse: the lookup reads a bucket's first two entries without a loop
   H.n_buckets = nb; H.nb_shift = 32; { uint32_t t = nb; while (t > 1) { t >>= 1; H.nb_shift--; } }

@@ -23,6 +23,7 @@ struct HostImage {
   // {masked key, shape, first entry of the group, entries in the group (0 = empty slot)}, slot = hash >> slot_shift, linear probing
   std::vector<uint32_t> slot_words, group_entries; uint32_t slot_shift = 0, n_slots = 0;
   std::vector<uint64_t> bit_words; std::vector<uint32_t> bit_off;     // bitprog.h tables, 139 + 64 x rows words per eligible rule; bit_off[rule] = first word or 0xffffffff
+  std::vector<uint64_t> factor_skip;   // 3 words per factor (bitprog.h: island_test)
   std::vector<uint32_t> prog, prog_off, sets, first, alpha;
   std::vector<uint32_t> factor_words;  // 12 words per full factor (device layout)
   std::vector<uint16_t> ranges;

@@ -307,15 +307,14 @@ struct SlotSink {
   // spans mode: one VM run per (message, rule), over the whole message (cand bitmap dedupes).
   // policy mode: one VM run per confirmed factor occurrence, restricted to its island.
   bool want_spans;
-  __device__ void candidate(uint32_t r, uint32_t t0, uint32_t pre) {
+  __device__ void candidate(uint32_t r, uint32_t t0, uint32_t pre, uint32_t f) {
     // policy mode, rule with a bit-parallel program, ASCII island: RegExp.test around this occurrence is decided right here
     // (bitprog.h) -- no slot for a miss, no VM run for a hit
     if (!want_spans && text && rs.bit_words) {
       const uint32_t bo = rs.bit_off[r];
       if (bo != kBitProgNone) {
         if (slot == 0xffffffffu) { const uint32_t s0 = *reinterpret_cast<volatile uint32_t*>(&w.slot_of_msg[msg]); if (s0 != 0xffffffffu && s0 < w.slot_cap && ((w.hit[(size_t)s0 * rs.rw + (r >> 5)] >> (r & 31)) & 1u)) return; }   // already a hit
-        const uint32_t is = island_start(rs, r, text, text_len, t0, pre, kIslandSteps);
-        const int res = min(t0, text_len) - is >= kIslandSteps ? -1 : bitprog_test(reinterpret_cast<const uint64_t*>(rs.bit_words) + bo, text, text_len, is, t0, kIslandSteps);
+        const int res = island_test(rs, f, r, text, text_len, t0, pre, kIslandSteps);
         if (res == 0) return;
         if (res == 1) { direct(r); return; }
       }
