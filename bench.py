@@ -336,7 +336,7 @@ def main():
             d, o, _ = gen(nmsgs, vrl, p_hit, seed_off, vocab, frag)
             ms, vk, vc, _, _ = measure(vrs, d, o, nmsgs, 6, 3, 3)
             variants[name] = {"rules": nrules, "p_hit": p_hit, "vocab_words": vocab, "frag_frac": frag, "ms_per_step": ms, "msgs_per_s": nmsgs / (ms * 1e-3),
-                              "scan_ms": float(vk[0]), "tail_ms": {"lookup": float(vk[4]), "check": float(vk[5]), "resolve": float(vk[6]), "verify": float(vk[2]), "finalize": float(vk[3])}, "scan_roofline_frac": nmsgs * (L + 12) / (float(vk[0]) * 1e-3) / 1e9 / peak,
+                              "scan_ms": float(vk[0]), "tail_ms": {"confirm_kernel": float(vk[4]), "resolve_kernel": float(vk[5]), "verify": float(vk[2]), "finalize": float(vk[3])}, "scan_roofline_frac": nmsgs * (L + 12) / (float(vk[0]) * 1e-3) / 1e9 / peak,
                               "flagged_grams": vc[6], "confirmed_factor_occurrences": vc[4], "vm_pairs": vc[1], "stride": int(vrs.info().stride)}
             if vrs is not rs:
                 vrs.close()
@@ -663,7 +663,7 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms, "whole_step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
         "kernel_ms_note": "kernel_ms: CUDA events inside the library around each kernel of one step (profiling mode, no graph); ms_per_step: the graph-replayed steady state",
         "kernel_ms": {"scan": scan_ms, "confirm": float(kms[1]), "verify": float(kms[2]), "finalize": float(kms[3]),
-                      "confirm_parts": {"lookup": float(kms[4]), "check": float(kms[5]), "resolve": float(kms[6])}},
+                      "confirm_parts": {"confirm_kernel": float(kms[4]), "resolve_kernel": float(kms[5])}},
         "candidates": {"flag_words": counters[8], "flagged_grams": counters[6], "grams_past_recheck_map": counters[7], "gram_entry_pairs": counters[9], "confirmed_factor_occurrences": counters[4], "messages_with_candidates": counters[0], "vm_pairs": counters[1], "flags": counters[3],
                        **({"vm_cycle_hist_2^11..": list(counters[8:16]), "vm_cycle_max": counters[7]} if os.environ.get("CG_SCAN_DEBUG") == "2" else {}),
                        "hit_messages": int((words != 0).sum().item()), "injected": len(inj)},

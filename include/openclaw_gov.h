@@ -97,7 +97,7 @@ CG_API uint64_t cg_launch_count(void);   /* kernels launched by this library so 
 /* measurement hooks (the reference's ScanResult.elapsedMs / evaluationUs, src/redaction/engine.ts:54,65):
  * with profiling on, CUDA events bracket each kernel of a scan step on its stream. */
 CG_API int cg_set_profiling(int on);
-CG_API int cg_last_tail_ms(float out_ms[3]);            /* lookup, check, resolve kernels of that step (profiling mode) */
+CG_API int cg_last_tail_ms(float out_ms[2]);            /* confirm_kernel, resolve_kernel of that step (profiling mode) */
 CG_API int cg_last_kernel_ms(float out_ms[4]);          /* scan, resolve, verify, finalize of the last completed step */
 CG_API int cg_scan_work_counters(const cg_ruleset *rs, uint32_t out16[16]); /* slots, VM pairs, spans, flags, confirmed factor occurrences, (internal), flagged grams, reserved */
 

@@ -336,8 +336,8 @@ def last_kernel_ms():
 
 
 def last_tail_ms():
-    """(lookup_ms, check_ms, resolve_ms) of the last completed scan step (profiling must be on)."""
-    out = np.zeros(3, dtype=np.float32)
+    """(confirm_kernel_ms, resolve_kernel_ms) of the last completed scan step (profiling must be on)."""
+    out = np.zeros(2, dtype=np.float32)
     check(load().cg_last_tail_ms(out.ctypes.data))
     return tuple(float(x) for x in out)
 

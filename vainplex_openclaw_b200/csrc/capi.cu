@@ -30,7 +30,6 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t pev_mid[4] = {};       // profiling: between lookup_kernel and check_kernel of each piece
   cudaEvent_t pev_scan[8] = {};      // profiling: begin / end of scan_kernel for each of the (at most four) pieces of a step
   uint32_t prof_pieces = 0;
   bool profiling = false;
@@ -114,7 +113,7 @@ struct cg_ruleset {
     if (h_counters) cudaFreeHost(h_counters);
     for (auto& e : e_cnt) if (e) cudaEventDestroy(e);
     for (void* p : allocs) cudaFree(p);
-    cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.fq); cudaFree(work.pairs); cudaFree(work.slot_of_msg);
+    cudaFree(work.heavy_idx); cudaFree(work.l1_pos); cudaFree(work.l1_fac); cudaFree(work.fq); cudaFree(work.slot_of_msg);
     cudaFree(work.counters); cudaFree(work.persist); cudaFree(work.slot_msg); cudaFree(work.cand); cudaFree(work.hit); cudaFree(work.events); cudaFree(work.event_pos); cudaFree(work.event_pre); cudaFree(work.spans);
   }
 };
@@ -137,8 +136,8 @@ int ensure_work(cg_ruleset* rs, ScanWork& w, uint32_t n_msgs, uint32_t l1_cap, u
   if (!w.counters) { CU(cudaMalloc((void**)&w.counters, kCounterWords * sizeof(uint32_t))); CU(cudaMalloc((void**)&w.persist, 16)); CU(cudaMemset(w.persist, 0, 16)); CU(cudaDeviceSynchronize()); }
   if (n_msgs > w.msg_cap) { cudaFree(w.slot_of_msg); w.slot_of_msg = nullptr; w.msg_cap = 0; CU(cudaMalloc((void**)&w.slot_of_msg, (size_t)n_msgs * 4)); w.msg_cap = n_msgs; }
   if (l1_cap > w.l1_cap) {
-    cudaFree(w.l1_pos); cudaFree(w.l1_fac); cudaFree(w.fq); cudaFree(w.pairs); w.l1_pos = w.l1_fac = nullptr; w.fq = w.pairs = nullptr; w.l1_cap = 0;
-    CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_fac, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.fq, (size_t)l1_cap * 8)); CU(cudaMalloc((void**)&w.pairs, (size_t)l1_cap * 8));
+    cudaFree(w.l1_pos); cudaFree(w.l1_fac); cudaFree(w.fq); w.l1_pos = w.l1_fac = nullptr; w.fq = nullptr; w.l1_cap = 0;
+    CU(cudaMalloc((void**)&w.l1_pos, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.l1_fac, (size_t)l1_cap * 4)); CU(cudaMalloc((void**)&w.fq, (size_t)l1_cap * 8));
     w.l1_cap = l1_cap;
   }
   if (slot_cap > w.slot_cap) {
@@ -170,11 +169,11 @@ int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_of
   for (uint32_t piece = 0; piece < K; piece++) {
     const uint32_t m0 = (uint32_t)((uint64_t)n * piece / K), m1 = (uint32_t)((uint64_t)n * (piece + 1) / K);
     if (m1 == m0) continue;
-    ScanWork wk = w; wk.q_cap = w.l1_cap / K; wk.q_slot = piece; wk.fq = w.fq + (size_t)piece * wk.q_cap; wk.pairs = w.pairs + (size_t)piece * wk.q_cap;
+    ScanWork wk = w; wk.q_cap = w.l1_cap / K; wk.q_slot = piece; wk.fq = w.fq + (size_t)piece * wk.q_cap;
     if (G.profiling) cudaEventRecord(G.pev_scan[2 * piece], st);
     k += launch_scan(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, d_words + m0, G.sm_count, st);
     if (G.profiling) cudaEventRecord(G.pev_scan[2 * piece + 1], st);
-    k += launch_lookup_check(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, G.sm_count, st, G.profiling ? G.pev_mid[piece] : nullptr);
+    k += launch_confirm(rs->dev, wk, d_bytes, d_off + m0, m1 - m0, G.sm_count, st);
   }
   if (G.profiling) cudaEventRecord(G.pev[1], st);
   k += launch_resolve(rs->dev, w, d_bytes, d_off, n, spans, G.sm_count, st);
@@ -196,8 +195,8 @@ void default_caps(const cg_ruleset* rs, uint32_t n, uint32_t* l1, uint32_t* slot
   *slot = std::max(std::max<uint32_t>(std::max<uint32_t>(n / 4, 4096), rs->work.slot_cap), rs->grow_slot);
   *ev = std::max(std::max<uint32_t>(std::max<uint32_t>(n, 4096), rs->work.event_cap), rs->grow_ev);
 }
-// fq / pairs are cut into four equal pieces at most: the fullest piece decides
-static uint32_t queue_need(const uint32_t* hc) { uint32_t m = 0; for (int i = 24; i < 32; i++) m = std::max(m, hc[i]); return m > 0xffffffffu / scan_pieces() ? 0xffffffffu : scan_pieces() * m; }
+// fq is cut into four equal pieces at most: the fullest piece decides
+static uint32_t queue_need(const uint32_t* hc) { uint32_t m = 0; for (int i = 24; i < 28; i++) m = std::max(m, hc[i]); return m > 0xffffffffu / scan_pieces() ? 0xffffffffu : scan_pieces() * m; }
 // what an overflowed step teaches about the capacities the next one needs
 void learn_caps(cg_ruleset* rs, const uint32_t* hc) {
   const uint32_t flags = hc[3];
@@ -356,7 +355,7 @@ int cg_init(int device) {
   CU(cudaEventCreate(&G.ev0)); CU(cudaEventCreate(&G.ev1));
   for (int i = 0; i < 5; i++) CU(cudaEventCreate(&G.pev[i]));
   for (int i = 0; i < 8; i++) CU(cudaEventCreate(&G.pev_scan[i]));
-  for (int i = 0; i < 4; i++) CU(cudaEventCreate(&G.pev_mid[i]));
+
   G.ready = true;
   return CG_OK;
 }
@@ -369,7 +368,7 @@ void cg_shutdown(void) {
   if (G.h_chunk_counters) cudaFreeHost(G.h_chunk_counters);
   if (G.s_h2d) { cudaStreamDestroy(G.s_h2d); cudaStreamDestroy(G.s_d2h); for (int c = 0; c < Ctx::kChunks; c++) { cudaEventDestroy(G.e_h2d[c]); cudaEventDestroy(G.e_done[c]); } }
   cudaFree(G.d_bytes_raw); cudaFree(G.d_off32); cudaFree(G.d_off64); cudaFree(G.d_words); cudaFree(G.d_dig[0]); cudaFree(G.d_dig[1]);
-  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); for (int i = 0; i < 8; i++) cudaEventDestroy(G.pev_scan[i]); for (int i = 0; i < 4; i++) cudaEventDestroy(G.pev_mid[i]); cudaStreamDestroy(G.stream);
+  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); for (int i = 0; i < 5; i++) cudaEventDestroy(G.pev[i]); for (int i = 0; i < 8; i++) cudaEventDestroy(G.pev_scan[i]); cudaStreamDestroy(G.stream);
   G = Ctx();
 }
 
@@ -386,12 +385,14 @@ int cg_last_kernel_ms(float out_ms[4]) {
   return CG_OK;
 }
 
-int cg_last_tail_ms(float out_ms[3]) {
-  // lookup_kernel / check_kernel / resolve_kernel of the most recent completed step in profiling mode (first piece)
+int cg_last_tail_ms(float out_ms[2]) {
+  // confirm_kernel / resolve_kernel of the most recent completed step in profiling mode (all pieces)
   if (!G.ready || !out_ms) return fail(CG_ERR_INVALID_ARG, "not initialised");
-  out_ms[0] = out_ms[1] = out_ms[2] = 0;
-  if (cudaEventElapsedTime(&out_ms[0], G.pev_scan[1], G.pev_mid[0]) != cudaSuccess || cudaEventElapsedTime(&out_ms[1], G.pev_mid[0], G.pev[1]) != cudaSuccess ||
-      cudaEventElapsedTime(&out_ms[2], G.pev[1], G.pev[2]) != cudaSuccess) { cudaGetLastError(); return fail(CG_ERR_CUDA, "profiling events not recorded / not complete"); }
+  float scan = 0, pre = 0;
+  for (uint32_t p = 0; p < G.prof_pieces; p++) { float t = 0; if (cudaEventElapsedTime(&t, G.pev_scan[2 * p], G.pev_scan[2 * p + 1]) == cudaSuccess) scan += t; else cudaGetLastError(); }
+  out_ms[0] = out_ms[1] = 0;
+  if (cudaEventElapsedTime(&pre, G.pev[0], G.pev[1]) != cudaSuccess || cudaEventElapsedTime(&out_ms[1], G.pev[1], G.pev[2]) != cudaSuccess) { cudaGetLastError(); return fail(CG_ERR_CUDA, "profiling events not recorded / not complete"); }
+  out_ms[0] = pre - scan;
   return CG_OK;
 }
 

@@ -25,7 +25,7 @@ struct DevRuleset {
   const uint32_t* trig_list;
   const uint32_t* bucket_start;  // HBM copies of the level-1b tables
   const uint2* entries;
-  const uint4* slots;            // lookup_kernel's view of the same entries (ruleset_image.h): open-addressing table of groups
+  const uint4* slots;            // confirm_kernel's view of the same entries (ruleset_image.h): open-addressing table of groups
   const uint32_t* group_entries; // entry words (factor | (gram offset + 3) << 20 | shape << 25) in group order
   uint32_t slot_shift, slot_mask;
   // confirm_kernel's tables as one block ([recheck map][slots][group entries][factor words][byte sets], 16-byte aligned parts):
@@ -58,10 +58,9 @@ struct DevRuleset {
 struct ScanWork {
   uint32_t* counters;            // 32 words: [0]=n_slots [1]=n_events [2]=n_spans [3]=error flags [4]=n_l1 (confirmed factor occurrences) [5]=verify cursor
                                  //           [6]=flagged grams (level 1a) [7..15]=debug [17]=n_heavy [18]=verify cursor (light events) [19]=grams past the recheck map
-                                 //           [24..27]=flag words queued, [28..31]=(gram, entry) pairs queued, per piece of the batch
+                                 //           [24..27]=flag words queued, [28..31]=(gram, entry) pairs compared, per piece of the batch
   uint32_t* l1_pos;              // [l1_cap] factor occurrences scan_kernel confirms itself (head check, trigger bytes): buffer offset of the
   uint32_t* l1_fac;              //          factor's first byte, factor id
-  uint2* pairs;                  // [l1_cap] lookup_kernel's (gram position, index into group_entries) pairs
   uint2* fq;                     // [l1_cap] scan_kernel's flag words: x = the lane's chunk number after the round, y = 4 tiles x 8 (4) probe bits
   uint32_t* persist;             // [4] survives the per-step reset: [0] = slots the previous step used (their candidate / hit rows are zeroed by the next step's reset_kernel)
   uint32_t* slot_of_msg;         // [n] 0xffffffff = none yet (reset per step)
@@ -74,7 +73,7 @@ struct ScanWork {
   uint32_t* event_pre;           // [event_cap]  policy mode: max units of a match before that factor (0xffff = unbounded)
   uint32_t* spans;               // [span_cap * 6] msg, rule, start_byte, end_byte, start16, end16
   uint32_t l1_cap, msg_cap, slot_cap, event_cap, span_cap;
-  uint32_t q_cap, q_slot;        // this launch's piece of fq / pairs (a step scans the batch in up to 4 pieces: q_slot 0..3) and its counters [24 + q_slot], [28 + q_slot]
+  uint32_t q_cap, q_slot;        // this launch's piece of fq (a step scans the batch in up to 4 pieces: q_slot 0..3) and its counter [24 + q_slot]
 };
 
 enum : uint32_t { ERR_EVENT_OVERFLOW = 1, ERR_SPAN_OVERFLOW = 2, ERR_VM_STACK = 4, ERR_VM_LIST = 8, ERR_SLOT_OVERFLOW = 16, ERR_L1_OVERFLOW = 32 };
@@ -87,8 +86,8 @@ constexpr uint64_t kWordIncomplete = ~0ull;      // result word of every message
 // d_bytes must be 16-byte aligned and readable up to 16 bytes past off[n].
 int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n,
                 uint64_t* d_words, int sm_count, cudaStream_t stream);
-// per piece of the batch: flag words -> grams -> recheck map -> level-1b lookup | exact factors (two launches)
-int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream, cudaEvent_t mid = nullptr);
+// per piece of the batch: flag words -> grams -> recheck map -> table probes -> exact factors (confirm_kernel)
+int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream);
 // once per step: message, slot, candidates for the VM / direct hits / island matcher
 int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,

@@ -123,10 +123,9 @@ bool build_host_image(const RuleSrc* src, uint32_t n, const ImageOptions& opt, H
   uint32_t bm = opt.bitmap_kb ? opt.bitmap_kb * 1024u : 128u * 1024u;
   { uint32_t t = 4096; while (t < bm) t *= 2; bm = std::min<uint32_t>(t, 128u * 1024u); }       // power of two
   auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  // recheck map: 32 bits per key (about 3 % of the first bitmap's false positives survive it), 4 .. 16 KB, shrunk before the bitmap is
+  // recheck map: 32 bits per key (about 3 % of the first bitmap's false positives survive it), 4 .. 16 KB (confirm_kernel stages it into its own shared memory)
   uint32_t rk = 4096; while (rk < 16384u && (uint64_t)rk * 8 < (uint64_t)P.keys.size() * 32) rk *= 2;
   const size_t tables0 = a16(H.bucket_start.size() * 4) + a16(H.entry_words.size() * 4);     // (factor words and byte sets are read from HBM / L2: only the last, warp-parallel stage of the slow path needs them)
-  while (rk > 4096u && (size_t)bm + rk + tables0 > opt.budget_bytes) rk /= 2;
   const size_t tables = tables0 + rk;
   while (bm > 16u * 1024u && (size_t)bm + tables > opt.budget_bytes && (uint64_t)(bm / 2) * 8 >= (uint64_t)P.keys.size() * 128) bm /= 2;   // tables resident beats a sparser bitmap
   H.tables_resident = false;      // (scan_kernel stages the bitmap alone; the tables are confirm_kernel's, read through L1 / L2)

@@ -354,134 +354,14 @@ struct SlotSink {
 // Everything between "the bitmap flagged a gram" and "this (message, rule) goes to the VM" is a chain of dependent loads
 // per item and keeps only a fraction of its input at every step.  Measured on the B200: inside scan_kernel that chain cost
 // more than the hot loop itself (32 warps per SM cannot hide it); as one kernel with barriers between the steps half the
-// time went into waiting for each step's slowest thread; as one kernel with per-warp pipelines every warp still walked a
-// dozen chains in sequence.  So each step is its own launch, one thread per item, the grid as wide as the item list, and
-// the lists live in HBM (an atomic per item, which the compiler aggregates per warp):
-//   lookup_kernel   flag word -> flag bits -> gram position; gram reloaded, folded, tested against the recheck map (the
-//                   bitmap's false positives end here); level-1b lookup                               -> (gram, entry) pairs
-//   check_kernel    exact comparison of the entry's factor at the position the gram implies          -> factor occurrences
-//   resolve_kernel  message of the occurrence (no straddling), slot, candidate for the VM / direct hit; also the occurrences
-//                   scan_kernel found itself (head check, trigger bytes) and the rules every message is a candidate for
+// time went into waiting for each step's slowest thread.  Round 2 first ran it as three launches with lists in HBM between
+// them (lookup_kernel: flag words -> grams -> recheck map -> table probes -> (gram, entry) pairs; check_kernel: exact factor;
+// resolve_kernel), 70 + 24 + 65 us; now:
+//   confirm_kernel  flag word -> gram positions -> gram reloaded, folded, recheck map, table probes -> exact factor  -> factor occurrences
+//   resolve_kernel  message of the occurrence (no straddling), slot, island matcher / candidate for the VM / direct hit; also the
+//                   occurrences scan_kernel found itself (head check, trigger bytes) and the rules every message is a candidate for
 // ------------------------------------------------------------------------------------------
-constexpr int kConfirmThreads = 256;
-
-// Divergent loops are what makes this part slow (a warp walks its lanes' loops one after the other, and every step is a
-// load that has to come back first), so there are none in the common path: a warp takes 32 flag words, spreads their set
-// bits evenly over its lanes (prefix sum + search through shuffles), and every lane then runs a straight line:
-// gram -> recheck map -> one probe per shape of the open-addressing table -> one atomic -> its pairs.
-__global__ void __launch_bounds__(kConfirmThreads, 6)
-lookup_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n, uint32_t cstep) {
-  const uint8_t* rk = rs.image + rs.rk_off;
-  const uint32_t kbits = rs.stride == 2 ? 8u : 4u, kshift = rs.stride == 2 ? 1u : 2u, n_shapes = rs.n_shapes, end = off[n];
-  const uint32_t nq = (rs.debug_flags & 1u) ? 0u : min(w.counters[24 + w.q_slot], w.q_cap);
-  const uint32_t lane = threadIdx.x & 31u, FULL = 0xffffffffu;
-  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  uint32_t flagged = 0, passed = 0;
-  for (uint32_t base = gwarp * 32u; base < nq; base += nwarps * 32u) {
-    uint2 q = make_uint2(0u, 0u);
-    if (base + lane < nq) q = w.fq[base + lane];
-    const uint32_t cnt = __popc(q.y);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
-    const uint32_t excl = incl - cnt, total = __shfl_sync(FULL, incl, 31);
-    flagged += lane == 0 ? total : 0u;
-    for (uint32_t g0 = 0; g0 < total; g0 += 32u) {
-      const uint32_t g = g0 + lane;
-      // the flag word that holds this lane's gram: the last lane whose exclusive prefix is <= g
-      uint32_t j = 0;
-#pragma unroll
-      for (int step = 16; step; step >>= 1) { const uint32_t t = __shfl_sync(FULL, excl, (j + step) & 31u); if (j + step < 32u && t <= g) j += step; }
-      uint32_t wj = __shfl_sync(FULL, q.y, j); const uint32_t cj = __shfl_sync(FULL, q.x, j), ej = __shfl_sync(FULL, excl, j);
-      bool active = g < total;
-      for (uint32_t r = active ? g - ej : 0u; r; r--) wj &= wj - 1u;          // drop the (g - ej) lowest set bits: rarely any
-      const uint32_t bit = active ? (uint32_t)__ffs((int)wj) - 1u : 0u;
-      const uint32_t pos = ((cj - (bit / kbits + 1u) * cstep) * kbits + (kbits - 1u - bit % kbits)) << kshift;
-      active = active && pos < end;
-      uint32_t key = 0;
-      if (active) {
-        const uint32_t* p4 = reinterpret_cast<const uint32_t*>(bytes + (pos & ~3u));
-        uint32_t gw = ldg_stream32(p4);
-        if (pos & 3u) gw = __funnelshift_r(gw, ldg_stream32(p4 + 1), 8u * (pos & 3u));
-        key = gram_fold_word(gw);
-      }
-      // recheck map and the first probe of every shape depend on the key alone: all issued before any is looked at
-      const uint32_t rh = gram_recheck_hash(key);
-      const uint32_t rkw = active ? *reinterpret_cast<const uint32_t*>(rk + (rh & rs.rk_mask)) : 0u;
-      for (uint32_t s0 = 0; s0 < n_shapes; s0 += 4u) {
-        uint4 sl[4]; uint32_t slot[4];
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) {
-          const uint32_t s = s0 + u, km = key & rs.shapes[s & 15u];
-          slot[u] = ((km ^ (s * 0x9E3779B9u)) * kGramMult2) >> rs.slot_shift;
-          sl[u] = (active && s < n_shapes) ? rs.slots[slot[u]] : make_uint4(0u, 0u, 0u, 0u);
-        }
-        const bool pass = active && ((rkw << (rh >> 27)) & 0x80000000u);
-        if (s0 == 0 && pass) passed++;
-        uint32_t tot = 0;
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) {
-          const uint32_t s = s0 + u, km = key & rs.shapes[s & 15u];
-          if (!pass) sl[u].w = 0;
-          while (sl[u].w && (sl[u].x != km || sl[u].y != s)) { slot[u] = (slot[u] + 1u) & rs.slot_mask; sl[u] = rs.slots[slot[u]]; }    // (linear probing; rarely a second slot)
-          tot += sl[u].w;
-        }
-        // one atomic per warp and pass reserves the pairs of all its lanes
-        uint32_t pin = tot;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, pin, d); if (lane >= (uint32_t)d) pin += t; }
-        const uint32_t wtot = __shfl_sync(FULL, pin, 31);
-        if (!wtot) continue;
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&w.counters[28 + w.q_slot], wtot);
-        k = __shfl_sync(FULL, k, 0) + pin - tot;
-        if (lane == 0 && k + wtot > w.q_cap) atomicOr(&w.counters[3], ERR_L1_OVERFLOW);
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) for (uint32_t e = 0; e < sl[u].w; e++, k++) if (k < w.q_cap) w.pairs[k] = make_uint2(pos, sl[u].z + e);
-      }
-    }
-  }
-  passed = __reduce_add_sync(FULL, passed);
-  if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); }
-}
-
-// One thread per (gram, entry) pair, again a straight line: the factor's words and the sixteen text bytes it could cover are
-// fetched at once, then all element tests (one byte-set word each) are in flight together -- no early exit, no loop-carried load.
-__global__ void __launch_bounds__(kConfirmThreads, 8)
-check_kernel(DevRuleset rs, ScanWork w, const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ off, uint32_t n) {
-  const uint32_t begin = off[0], end = off[n];
-  const uint32_t np = min(w.counters[28 + w.q_slot], w.q_cap);
-  QueueEmit emit{w};
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
-    const uint2 pr = w.pairs[i];
-    const uint32_t y = rs.group_entries[pr.y];
-    const uint32_t f = y & 0xfffffu;
-    const int goff = (int)((y >> 20) & 31u) - 3;
-    const int64_t t0 = (int64_t)pr.x - goff;
-    const uint4* fw4 = reinterpret_cast<const uint4*>(rs.factors + (size_t)f * 12);
-    const uint4 fa = fw4[0], fb = fw4[1], fc = fw4[2];          // rule, len | exact << 24, 16 x u16 set ids, pre, pre_alpha
-    const uint32_t flen = fa.y & 0xffu;
-    if (t0 < (int64_t)begin || t0 + (int64_t)flen > (int64_t)end) continue;
-    // the sixteen bytes from t0 on, from five aligned words (the buffer is readable 16 bytes past its end)
-    const uint32_t* tp = reinterpret_cast<const uint32_t*>(bytes + ((size_t)t0 & ~(size_t)3));
-    const uint32_t sh = 8u * ((uint32_t)t0 & 3u);
-    const uint32_t need = ((uint32_t)t0 & 3u) + flen;           // bytes from the first aligned word on (nothing past the factor's end is read)
-    const uint32_t a0 = ldg_stream32(tp), a1 = need > 4u ? ldg_stream32(tp + 1) : 0u, a2 = need > 8u ? ldg_stream32(tp + 2) : 0u, a3 = need > 12u ? ldg_stream32(tp + 3) : 0u, a4 = need > 16u ? ldg_stream32(tp + 4) : 0u;
-    const uint32_t tx[4] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh)};
-    const uint32_t sid[8] = {fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, fc.x, fc.y};
-    uint32_t ok = 1u;
-#pragma unroll
-    for (uint32_t k = 0; k < 16; k++) {
-      const uint32_t s = (sid[k >> 1] >> (16 * (k & 1))) & 0xffffu, b = (tx[k >> 2] >> (8 * (k & 3))) & 0xffu;
-      const uint32_t bit = (rs.bytesets[(size_t)(k < flen ? s : 0u) * 8 + (b >> 5)] >> (b & 31)) & 1u;
-      ok &= k < flen ? bit : 1u;
-    }
-    if (ok) emit((uint32_t)t0, f);
-  }
-}
-
-
-// lookup + check as ONE launch (the default).  What the two launches above cost is not the looking itself -- 850 k random
+// What the two launches cost was not the looking itself -- 850 k random
 // 4-byte places of a 268 MB buffer are read again in 20 us (profiles/micro/gather_micro.cu) -- but the number of
 // uncoalesced loads behind it: measured, both kernels run at about one lane-level request per SM and clock, and an item
 // costs them 5.5 (gram, recheck word, three slots) + 23 (entry, factor words, text words, sixteen byte-set words).  So:
@@ -645,7 +525,7 @@ confirm_kernel(const __grid_constant__ DevRuleset rs, const __grid_constant__ Sc
   if (tail != head) { const bool a = lane < tail - head; const uint32_t pos = a ? ring[(head + lane) & (kCfRing - 1)] : 0u; __syncwarp(); confirm_gram(c, pos, a); }
   if (c.ptail != c.phead) { const bool a = lane < c.ptail - c.phead; const uint2 pr = a ? c.pring[(c.phead + lane) & (kCfRing - 1)] : make_uint2(0u, 0u); confirm_pairs(c, pr, a); }
   const uint32_t passed = __reduce_add_sync(FULL, c.passed);
-  if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); }
+  if (lane == 0) { if (flagged) atomicAdd(&w.counters[6], flagged); if (passed) atomicAdd(&w.counters[19], passed); if (c.ptail) atomicAdd(&w.counters[28 + w.q_slot], c.ptail); }
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -888,20 +768,11 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
   return 1;
 }
 
-int launch_lookup_check(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream, cudaEvent_t mid) {
+int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream) {
   if (n == 0) return 0;
-  const uint32_t cstep = scan_grid(n, sm_count) * (uint32_t)(scan_threads() / 32) * 32u;
-  // (the list lengths are only known on the device: grids sized for full occupancy, grid-stride loops)
-  static const bool two_launches = getenv("CG_CONFIRM") && atoi(getenv("CG_CONFIRM")) == 0;      // (the round-2 pair of launches, kept for comparison)
-  if (!two_launches) {
-    confirm_kernel<<<scan_grid(n, sm_count), kCfThreads, (size_t)kCfRingBytes + (rs.cf_resident ? rs.cf_bytes : 0u), stream>>>(rs, w, d_bytes, d_off, n, cstep);
-    if (mid) cudaEventRecord(mid, stream);
-    return 1;
-  }
-  lookup_kernel<<<sm_count * 6, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n, cstep);
-  if (mid) cudaEventRecord(mid, stream);
-  check_kernel<<<sm_count * 8, kConfirmThreads, 0, stream>>>(rs, w, d_bytes, d_off, n);
-  return 2;
+  const uint32_t cstep = scan_grid(n, sm_count) * (uint32_t)(scan_threads() / 32) * 32u;       // (the queue's chunk numbers are decoded with the scan's grid)
+  confirm_kernel<<<scan_grid(n, sm_count), kCfThreads, (size_t)kCfRingBytes + (rs.cf_resident ? rs.cf_bytes : 0u), stream>>>(rs, w, d_bytes, d_off, n, cstep);
+  return 1;
 }
 int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream) {
   if (n == 0) return 0;
