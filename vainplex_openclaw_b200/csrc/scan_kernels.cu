@@ -1,10 +1,13 @@
 // scan_kernels.cu -- sm_100a kernels of the message-scan hot path.
 //
+//   reset_kernel    start of a step: counters, slot table, the candidate / hit rows the previous step used.
 //   scan_kernel     every byte of the batch buffer through the gram filter: 4-byte grams folded, hashed and tested against
-//                   a bitmap in shared memory (image staged with TMA bulk copies, completion on an mbarrier); flagged
-//                   grams are compacted with warp ballots and confirmed exactly against the factor tables.
-//   resolve_kernel  level 2: message of every confirmed factor occurrence; queues (message, rule) pairs for the VM
-//                   (or records a direct hit).
+//                   a bitmap in shared memory (image staged with TMA bulk copies, completion on an mbarrier); lanes with
+//                   flagged grams push (chunk, flag word) to a queue in HBM, compacted with warp ballots.
+//   confirm_kernel  flagged grams: reloaded, recheck map, table probes, exact factor comparison -- tables in shared memory,
+//                   work handed from stage to stage in ballot-compacted waves.
+//   resolve_kernel  level 2: message of every confirmed factor occurrence; RegExp.test around it by the bit-parallel
+//                   island matcher (bitprog.h), or a direct hit, or a (message, rule) pair for the VM.
 //   verify_kernel   exact ECMAScript semantics for the queued pairs: a Pike VM over UTF-16 units
 //                   decoded on the fly from the UTF-8 bytes (leftmost-first, global-exec
 //                   iteration of registry.ts:225-236, RegExp.test of context.ts:9-25).
