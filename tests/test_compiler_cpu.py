@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from helpers import Harness, PACK_RULES, PACK_TEXTS, random_regex
+from helpers import Harness, PACK_RULES, PACK_TEXTS, random_regex, oracle_regexes
 from vainplex_openclaw_b200 import workload as W
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -317,6 +317,53 @@ def test_bit_parallel_matcher_agrees_with_the_vm(harness_lib, oracle):
     decided, mismatch, fallback = (int(stats[i]) - int(base[i]) for i in range(3))
     assert mismatch == 0, (decided, mismatch, fallback)
     assert decided > 800 and decided > fallback
+
+
+def test_island_matcher_two_words_lookaround_and_factor_skip(harness_lib, oracle):
+    """bitprog.h beyond one word: programs with 64 .. 127 consuming instructions (two state words), single-unit lookaround over
+    ASCII sets (token-boundary guards: 32 contexts), and the resume behind a confirmed factor (factor_skip).  Every text is
+    built around the places where those differ from the plain walk: the guard bytes on both sides, a match ending exactly at
+    the end of the message, class runs one short of / at / beyond their bounds, a state that crosses the 64-bit word.  The
+    harness decides each occurrence with island_test AND the Pike VM and counts disagreements; hits must equal the oracle's."""
+    import ctypes as C
+    rules = [
+        (r"(?<![A-Z0-9])PZULOYQ[0-9A-Z]{16}(?![A-Z0-9])", 0, 0),
+        (r"(?<!\d)\+?[1-9]\d{6,14}(?!\d)", 0, 0),
+        (r"(?:password|passwd|pwd|secret|token|api_key|apikey)\s*[:=]\s*['\"]?[^\s'\"]{8,64}", 1, 0),
+        (r"sk-ant-[a-zA-Z0-9-]{80,}", 0, 0),
+        (r"hgisr[a-zA-Z0-9_-]{36,}", 0, 0),
+        (r"(?<=[a-f])zq[0-9]{3}(?=[xy])", 0, 0),
+        (r"\bkey_[a-z]{70,90}\b", 0, 0),
+        (r"abc-[A-Za-z0-9]{16,40}", 0, 0),
+    ]
+    h = Harness(harness_lib, rules)
+    assert all(int(x) == 0 for x in h.status[:len(rules)])
+    assert harness_lib.harness_bitprog_eligible(h.h) == len(rules)
+    regs = oracle_regexes(oracle, rules)
+    stats = (C.c_uint64 * 3)()
+    harness_lib.harness_bitprog_stats(stats)
+    base = list(stats)
+    tok = "PZULOYQ" + "A1B2C3D4E5F6G7H8"
+    texts = [tok, " " + tok, tok + " ", "x" + tok + ".", "X" + tok, tok + "9", "-" + tok + "-", tok[:-1], tok + tok,
+             "+4915112345678", "call +4915112345678 now", "1234567", "123456", "a1234567b", "91234567890123456", "x+1234567",
+             "token=abcdefgh", "TOKEN : 'abcdefghij'", "secret=short", "password = \"" + "p" * 64 + "\"", "api_key=" + "k" * 70, "pwd:1234567", "pwd:12345678",
+             "sk-ant-" + "a" * 79, "sk-ant-" + "a" * 80, "say sk-ant-" + "Ab-9" * 25 + " end", "sk-ant-" + "a" * 200,
+             "hgisr" + "_" * 35, "hgisr" + "_" * 36, "hgisr" + "x" * 120,
+             "azq123x", "gzq123x", "fzq123y!", "azq12x", "zq123x", "azq123",
+             "key_" + "a" * 69, "key_" + "a" * 70, "key_" + "a" * 90, "key_" + "a" * 91, "a key_" + "b" * 80 + " z", "xkey_" + "b" * 80,
+             "abc-" + "Z" * 15, "abc-" + "Z" * 16, "abc-" + "Z" * 41, "abc-abc-" + "Q" * 16, "\u00e9abc-" + "Z" * 16, "abc-" + "Z" * 10 + "\u00e9" + "Z" * 16]
+    msgs = [t.encode("utf-8") for t in texts]
+    data, off = oracle.pack(msgs)
+    bits, _ = oracle.scan_policy(regs, data, off)
+    for i, (t, m) in enumerate(zip(texts, msgs)):
+        got = h.policy_hits(m, lead=len(m) % 7, seed=3)
+        row = np.unpackbits(bits[i], bitorder="little")[:len(rules)]
+        exp = {int(r) for r in np.nonzero(row)[0]}
+        assert got == exp, (t, got, exp)
+    harness_lib.harness_bitprog_stats(stats)
+    decided, mismatch, fallback = (int(stats[i]) - int(base[i]) for i in range(3))
+    assert mismatch == 0 and decided >= 40, (decided, mismatch, fallback)
+    h.close()
 
 
 def test_cortex_language_packs_compile_and_match(harness_lib, oracle):

@@ -710,3 +710,42 @@ def test_single_message_path_equals_the_batch_path(N, oracle):
         big, boff, _ = W.make_messages(200000 if rep == 0 else 1000, 64, rl, p_hit=0.05, seed=11)
         rs.scan_batch(big.numpy(), boff.numpy().astype(np.uint32))
     rs.close()
+
+
+def test_island_matcher_features_through_the_kernels(N, oracle):
+    """resolve_kernel's island matcher on the device: two-word programs (64 .. 127 consuming instructions), lookaround guards,
+    resume behind the confirmed factor, islands longer than the 96 steps it walks itself (those go to the VM) -- the same
+    rules and boundary texts as the CPU tier's test_island_matcher_two_words_lookaround_and_factor_skip, plus long messages."""
+    rules = [
+        (r"(?<![A-Z0-9])PZULOYQ[0-9A-Z]{16}(?![A-Z0-9])", 0, 3),
+        (r"(?<!\d)\+?[1-9]\d{6,14}(?!\d)", 0, 3),
+        (r"(?:password|passwd|pwd|secret|token|api_key|apikey)\s*[:=]\s*['\"]?[^\s'\"]{8,64}", 1, 3),
+        (r"sk-ant-[a-zA-Z0-9-]{80,}", 0, 3),
+        (r"hgisr[a-zA-Z0-9_-]{36,}", 0, 3),
+        (r"(?<=[a-f])zq[0-9]{3}(?=[xy])", 0, 3),
+        (r"\bkey_[a-z]{70,90}\b", 0, 3),
+        (r"abc-[A-Za-z0-9]{16,40}", 0, 3),
+        (r"[a-z]+@[a-z]+\.com", 0, 3),
+    ]
+    tok = "PZULOYQ" + "A1B2C3D4E5F6G7H8"
+    texts = [tok, " " + tok, tok + " ", "x" + tok + ".", "X" + tok, tok + "9", "-" + tok + "-", tok[:-1], tok + tok,
+             "+4915112345678", "call +4915112345678 now", "1234567", "123456", "a1234567b", "91234567890123456", "x+1234567",
+             "token=abcdefgh", "TOKEN : 'abcdefghij'", "secret=short", "password = \"" + "p" * 64 + "\"", "api_key=" + "k" * 70, "pwd:1234567", "pwd:12345678",
+             "sk-ant-" + "a" * 79, "sk-ant-" + "a" * 80, "say sk-ant-" + "Ab-9" * 25 + " end", "sk-ant-" + "a" * 200,
+             "hgisr" + "_" * 35, "hgisr" + "_" * 36, "hgisr" + "x" * 120,
+             "azq123x", "gzq123x", "fzq123y!", "azq12x", "zq123x", "azq123",
+             "key_" + "a" * 69, "key_" + "a" * 70, "key_" + "a" * 90, "key_" + "a" * 91, "a key_" + "b" * 80 + " z", "xkey_" + "b" * 80,
+             "abc-" + "Z" * 15, "abc-" + "Z" * 16, "abc-" + "Z" * 41, "abc-abc-" + "Q" * 16, "éabc-" + "Z" * 16, "abc-" + "Z" * 10 + "é" + "Z" * 16,
+             "q" * 300 + "@example.com", "q" * 95 + "@example.com", "q" * 96 + "@example.com", "q" * 97 + "@example.com", "é" + "q" * 50 + "@example.com",
+             ("lorem ipsum " * 400) + tok + (" dolor sit amet" * 300) + " token = " + "v" * 30]
+    msgs = [N.js_utf8(t) for t in texts] * 3
+    rs = N.Ruleset(rules, strict=True)
+    data, off = N.pack(msgs)
+    words, hits = rs.scan_batch(data, off)
+    ewords, ehits = oracle_policy(oracle, rules, data, off)
+    assert [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits
+    assert np.array_equal(words, ewords)
+    assert len({r for (_, r) in ehits}) == len(rules)        # every rule hits somewhere
+    for i in (0, 25, len(texts) - 1):
+        assert rs.scan_one(msgs[i])[1] == [r for (m, r) in ehits if m == i]
+    rs.close()

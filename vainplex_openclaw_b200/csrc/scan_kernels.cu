@@ -787,10 +787,12 @@ int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byt
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
                   bool want_spans, int sm_count, cudaStream_t stream) {
   int k = 1;
+  // (events are handed out by an atomic cursor, so any grid is correct; CG_VERIFY_CTAS = CTAs per SM, experiments)
+  static const int ctas = [] { const char* e = getenv("CG_VERIFY_CTAS"); const int v = e ? atoi(e) : kVerifyCtasPerSm; return v >= 1 && v <= kVerifyCtasPerSm ? v : kVerifyCtasPerSm; }();
   if (want_spans) {
-    verify_small_kernel<true><<<sm_count * kVerifyCtasPerSm, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+    verify_small_kernel<true><<<sm_count * ctas, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   } else {
-    verify_small_kernel<false><<<sm_count * kVerifyCtasPerSm, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
+    verify_small_kernel<false><<<sm_count * ctas, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   }
   if (rs.max_prog_len > (uint32_t)kSmallProg) {
     k++;
