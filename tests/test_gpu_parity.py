@@ -749,3 +749,38 @@ def test_island_matcher_features_through_the_kernels(N, oracle):
     for i in (0, 25, len(texts) - 1):
         assert rs.scan_one(msgs[i])[1] == [r for (m, r) in ehits if m == i]
     rs.close()
+
+
+def test_vm_grid_follows_the_traffic(N, oracle):
+    """verify_small_kernel's grid is sized by what the previous step sent to the VM (one CTA per SM while the island matcher
+    decides everything, four above 2048 pairs): ASCII traffic, then traffic whose islands are full of non-ASCII text (the VM's),
+    twice (the second time with the large grid), then ASCII again -- every batch equal to the oracle, on the host path and on
+    the device path (whose cached graph is keyed on the grid)."""
+    import torch
+    rl = W.make_rules(120)
+    rules = W.rules_as_tuples(rl)
+    rs = N.Ruleset(rules, strict=True)
+    plain_t, poff_t, _ = W.make_messages(6000, 256, rl, p_hit=0.3, seed=21)
+    heavy_t, hoff_t, _ = W.make_messages(30000, 256, rl, p_hit=0.5, seed=22, utf8_frac=0.6)
+    seen = []
+    for name, (dt, ot) in [("plain", (plain_t, poff_t)), ("heavy", (heavy_t, hoff_t)), ("heavy", (heavy_t, hoff_t)), ("plain", (plain_t, poff_t))]:
+        data, off = dt.numpy(), ot.numpy().astype(np.uint32)
+        words, hits = rs.scan_batch(data, off)
+        seen.append((name, rs.work_counters()[1]))
+        ewords, ehits = oracle_policy(oracle, rules, data, off)
+        assert np.array_equal(words, ewords), name
+        assert [(int(h["msg"]), int(h["rule"])) for h in hits] == ehits, name
+    assert max(ev for name, ev in seen if name == "heavy") > 2048, seen         # the large grid was in use
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream()
+    for dt, ot in [(heavy_t, hoff_t), (plain_t, poff_t), (heavy_t, hoff_t)]:
+        d, o = dt.to(dev), ot.to(torch.int32).to(dev)
+        n = o.numel() - 1
+        out = torch.zeros(n, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                rs.scan_batch_device(d.data_ptr(), o.data_ptr(), n, out.data_ptr(), stream.cuda_stream)
+                rs.scan_join(stream.cuda_stream)
+        ewords, _ = oracle_policy(oracle, rules, dt.numpy(), ot.numpy().astype(np.uint32))
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), ewords)
+    rs.close()

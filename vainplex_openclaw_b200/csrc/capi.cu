@@ -97,6 +97,10 @@ struct cg_ruleset {
   uint32_t* h_counters = nullptr; cudaEvent_t e_cnt[kMirror] = {}; bool cnt_pending[kMirror] = {};
   uint32_t grow_l1 = 0, grow_slot = 0, grow_ev = 0;     // capacities learnt from overflows
   uint32_t sticky_flags = 0;      // error flags of batches since the last cg_scan_join
+  // verify_small_kernel's grid (CTAs per SM): one while the island matcher decides (nearly) everything, four once a step has
+  // sent more than 2048 pairs to the VM (non-ASCII traffic); back to one below 256.  Part of the cached graphs' keys.
+  int verify_ctas = 1;
+  void size_verify_grid() { const uint32_t ev = last_counters[1]; if (ev > 2048u) verify_ctas = 4; else if (ev < 256u) verify_ctas = 1; }
   uint32_t last_counters[kCounterWords] = {};
   // the device-resident step replayed as one CUDA graph (keyed on its arguments and scratch capacities)
   struct CachedGraph { int kernels = 0; cudaGraphExec_t exec = nullptr; const void* bytes = nullptr; const void* off = nullptr; void* words = nullptr; uint32_t n = 0; uint64_t caps[4] = {0, 0, 0, 0}; uint64_t used = 0; };
@@ -178,7 +182,7 @@ int run_scan_device(cg_ruleset* rs, const uint8_t* d_bytes, const uint32_t* d_of
   if (G.profiling) cudaEventRecord(G.pev[1], st);
   k += launch_resolve(rs->dev, w, d_bytes, d_off, n, spans, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[2], st);
-  k += launch_verify(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st);
+  k += launch_verify(rs->dev, w, d_bytes, d_off, spans, G.sm_count, st, spans ? 4 : rs->verify_ctas);
   if (G.profiling) cudaEventRecord(G.pev[3], st);
   k += launch_finalize(rs->dev, w, d_words, n, G.sm_count, st);
   if (G.profiling) cudaEventRecord(G.pev[4], st);
@@ -220,6 +224,7 @@ int scan_host(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offsets, uin
   if (!rs || (n && (!bytes || !offsets))) return fail(CG_ERR_INVALID_ARG, "null argument");
   int rc;
   if (n && (rc = check_offsets(offsets, n))) return rc;
+  rs->size_verify_grid();
   const size_t first = n ? offsets[0] : 0, total = n ? offsets[n] : 0;
   if ((rc = grow_bytes(total + 64))) return rc;
   if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
@@ -263,6 +268,7 @@ int scan_host_chunked(cg_ruleset* rs, const uint8_t* bytes, const uint32_t* offs
   const int C = Ctx::kChunks;
   int rc;
   if ((rc = check_offsets(offsets, n))) return rc;
+  rs->size_verify_grid();
   const size_t total = offsets[n];
   if ((rc = grow_bytes(total + 64))) return rc;
   if ((rc = grow(&G.d_off32, &G.cap_off32, (size_t)n + 1))) return rc;
@@ -582,7 +588,8 @@ int scan_one_fast(cg_ruleset* rs, const uint8_t* bytes, uint32_t len, uint64_t* 
     for (auto& g : rs->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if ((rc = ensure_work(rs, w, 1, l1, slot, ev, 1))) return rc;
   }
-  const uint64_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
+  rs->size_verify_grid();
+  const uint64_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap | ((uint64_t)rs->verify_ctas << 40), w.msg_cap};
   const uint8_t* d_bytes = o.d_buf; const uint32_t* d_off = reinterpret_cast<const uint32_t*>(o.d_buf);
   uint32_t* d_out = reinterpret_cast<uint32_t*>(o.d_buf + kOneIn); uint64_t* d_word = reinterpret_cast<uint64_t*>(o.d_buf + kOneIn + kOneOut - 8);   // (the word lands behind the hit row, then is packed to the front)
   if (!o.exec || memcmp(caps, o.caps, sizeof caps)) {
@@ -798,12 +805,13 @@ int cg_scan_batch_device(cg_ruleset* rs, const void* d_bytes, const void* d_offs
     for (auto& g : rs->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if ((rc = ensure_work(rs, w, std::max<uint32_t>(n, 1), want_l1, want_slot, want_ev, 1))) return rc;
   }
+  rs->size_verify_grid();
   if (!use_graph || G.profiling) {
     rc = run_scan_device(rs, (const uint8_t*)d_bytes, (const uint32_t*)d_offsets, n, (uint64_t*)d_out_words, false, st);
   } else {
     // memsets + scan + resolve + verify + finalize captured once per (arguments, capacities), then replayed:
     // one launch per step instead of six, so the host never becomes the bottleneck
-    const uint64_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap, w.msg_cap};
+    const uint64_t caps[4] = {w.l1_cap, w.slot_cap, w.event_cap | ((uint64_t)rs->verify_ctas << 40), w.msg_cap};
     cg_ruleset::CachedGraph* hit = nullptr;
     for (auto& g : rs->graphs) if (g.exec && g.bytes == d_bytes && g.off == d_offsets && g.words == d_out_words && g.n == n && !memcmp(caps, g.caps, sizeof caps)) hit = &g;
     if (!hit) {

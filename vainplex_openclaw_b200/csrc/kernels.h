@@ -90,8 +90,10 @@ int launch_scan(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes,
 int launch_confirm(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, int sm_count, cudaStream_t stream);
 // once per step: message, slot, candidates for the VM / direct hits / island matcher
 int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off, uint32_t n, bool want_spans, int sm_count, cudaStream_t stream);
+// ctas_per_sm (1 .. 4): events are handed out by an atomic cursor, so any grid is correct; an empty launch costs 8 us at one CTA
+// per SM and 13 us at four (measured), so the caller sizes the grid by what the previous steps sent to the VM
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
-                  bool want_spans, int sm_count, cudaStream_t stream);
+                  bool want_spans, int sm_count, cudaStream_t stream, int ctas_per_sm = 4);
 // one verdict word per hit message: action | matched policies << 2 | deciding rule << 12 (cg_policy_verdict_batch)
 int launch_verdicts(const DevRuleset& rs, const ScanWork& w, uint32_t* d_verdicts, int sm_count, cudaStream_t stream);
 int launch_finalize(const DevRuleset& rs, const ScanWork& w, uint64_t* d_words, uint32_t n, int sm_count, cudaStream_t stream);

@@ -785,10 +785,10 @@ int launch_resolve(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_byt
 }
 
 int launch_verify(const DevRuleset& rs, const ScanWork& w, const uint8_t* d_bytes, const uint32_t* d_off,
-                  bool want_spans, int sm_count, cudaStream_t stream) {
+                  bool want_spans, int sm_count, cudaStream_t stream, int ctas_per_sm) {
   int k = 1;
-  // (events are handed out by an atomic cursor, so any grid is correct; CG_VERIFY_CTAS = CTAs per SM, experiments)
-  static const int ctas = [] { const char* e = getenv("CG_VERIFY_CTAS"); const int v = e ? atoi(e) : kVerifyCtasPerSm; return v >= 1 && v <= kVerifyCtasPerSm ? v : kVerifyCtasPerSm; }();
+  static const int forced = [] { const char* e = getenv("CG_VERIFY_CTAS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= kVerifyCtasPerSm ? v : 0; }();       // (experiments)
+  const int ctas = forced ? forced : (ctas_per_sm >= 1 && ctas_per_sm <= kVerifyCtasPerSm ? ctas_per_sm : kVerifyCtasPerSm);
   if (want_spans) {
     verify_small_kernel<true><<<sm_count * ctas, kVerifyBlock, kVerifySmem, stream>>>(rs, w, d_bytes, d_off);
   } else {
