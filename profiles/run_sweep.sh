@@ -10,7 +10,7 @@ for R in $RULES; do
     N=$(( 268435456 / L ))
     if [ "$G" = "1" ]; then RUN="python bench.py"; else RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $G"; fi
     S=$(( 524288 / L )); if [ $S -lt 32 ]; then S=32; fi; if [ $S -gt 2048 ]; then S=2048; fi
-    CG_ORACLE_CHECK=1 CG_CPU_SAMPLE=$S $RUN --steps 10 --warmup 3 --rules $R --len $L --msgs $N --no-merkle --no-variants --no-c4 2>/dev/null | tail -1 | python -c "
+    CG_ORACLE_CHECK=1 CG_CPU_SAMPLE=$S $RUN --steps 10 --warmup 3 --rules $R --len $L --msgs $N --no-merkle --no-variants --no-c4 2>/dev/null | grep '^{"metric"' | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 cb=d.get('cpu_baseline') or d['extra'].get('oracle_check') or {}
